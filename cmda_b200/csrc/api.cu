@@ -1,0 +1,280 @@
+// extern "C" entry points of libcmda_b200.so (see include/cmda_b200.h): argument
+// validation, workspace carving, launch sequencing.  No allocation, no global state, no
+// synchronisation, no CPU fallback.
+#include "common.cuh"
+
+namespace cmda {
+
+thread_local int g_last_cuda_error = 0;
+
+// launchers defined in the kernel translation units
+int launch_scatter_global_raw(const uint32_t*, const uint16_t*, const uint16_t*, const uint8_t*, const WindowTable&, int,
+                              long long, const float*, int, int, int, long long*, int64_t*, cudaStream_t);
+int launch_scatter_global_f32(const float*, const float*, const float*, const float*, long long, int, int, int,
+                              long long*, int64_t*, cudaStream_t);
+int launch_remap(const uint32_t*, const uint16_t*, const uint16_t*, const uint8_t*, long long, long long, const float*,
+                 int, int, int, float*, float*, float*, int*, int*, int*, cudaStream_t);
+int launch_convert_stats(const long long*, float*, int, long long, PartialStats*, cudaStream_t);
+int launch_norm_apply(const float*, float*, int, long long, const PartialStats*, const WindowTable&, float, int,
+                      cudaStream_t);
+int launch_rgb_to_gray(const uint8_t*, int64_t, uint8_t*, cudaStream_t);
+int launch_isr(const uint8_t*, int, int, int, int, int, const float*, float, float, float*, unsigned*, cudaStream_t);
+int launch_pair(const uint8_t*, const uint8_t*, int, int, int, const float*, float, float, float*, uint8_t*, unsigned*,
+                cudaStream_t);
+// TILED mode (voxel_tiled.cu)
+size_t tiled_workspace_bytes(int64_t total_events, int S, int H, int W, int B);
+int tiled_supported(int H, int W, int B);
+int launch_tiled_raw(const uint32_t*, const uint16_t*, const uint16_t*, const uint8_t*, const WindowTable&, int,
+                     const float*, int, int, int, float*, PartialStats*, int64_t*, void*, size_t, cudaStream_t);
+int launch_tiled_f32(const float*, const float*, const float*, const float*, long long, int, int, int, float*,
+                     PartialStats*, int64_t*, void*, size_t, cudaStream_t);
+
+static size_t stats_bytes(int S) { return align_up(sizeof(PartialStats) * kStatBlocks * static_cast<size_t>(S), 256); }
+static size_t acc_bytes(int S, int H, int W, int B) {
+    return align_up(sizeof(long long) * static_cast<size_t>(S) * B * H * W, 256);
+}
+
+// windows smaller than this take the GLOBAL path under CMDA_VOXEL_AUTO: the partition +
+// band passes have a fixed cost that only pays off once the atomics dominate
+constexpr long long kAutoTiledMinEvents = 200000;
+
+static int resolve_mode(int mode, long long total_events, int S, int H, int W, int B) {
+    if (mode == CMDA_VOXEL_AUTO)
+        return (tiled_supported(H, W, B) && total_events >= kAutoTiledMinEvents * (S > 0 ? S : 1)) ? CMDA_VOXEL_TILED
+                                                                                                  : CMDA_VOXEL_GLOBAL;
+    return mode;
+}
+
+}  // namespace cmda
+
+using namespace cmda;
+
+extern "C" {
+
+const char* cmda_strerror(int code) {
+    switch (code) {
+        case CMDA_OK: return "ok";
+        case CMDA_ERR_BAD_ARG: return "bad argument";
+        case CMDA_ERR_CUDA: return "CUDA runtime error";
+        case CMDA_ERR_WORKSPACE: return "workspace too small or misaligned";
+        case CMDA_ERR_UNSUPPORTED: return "unsupported shape";
+        case CMDA_ERR_NO_DEVICE: return "no sm_100 device";
+        default: return "unknown error";
+    }
+}
+
+int cmda_version(void) { return CMDA_B200_VERSION; }
+int cmda_last_cuda_error(void) { return g_last_cuda_error; }
+
+int cmda_searchsorted_right_u32(const uint32_t* d_t, int64_t n, const int64_t* d_q, int nq, int64_t* d_out,
+                                void* stream) {
+    if (n < 0 || nq < 0) return CMDA_ERR_BAD_ARG;
+    if (nq == 0) return CMDA_OK;
+    if ((n > 0 && !d_t) || !d_q || !d_out) return CMDA_ERR_BAD_ARG;
+    return launch_searchsorted(d_t, n, d_q, nq, d_out, static_cast<cudaStream_t>(stream));
+}
+
+int cmda_images_to_events_index(const uint32_t* d_t, int64_t n, const int64_t* d_ms_to_idx, int64_t n_ms,
+                                int64_t t_offset, const int64_t* d_timestamps, int n_ts, int64_t* d_index,
+                                int32_t* d_status, void* stream) {
+    if (n <= 0 || n_ms <= 0 || n_ts < 0) return CMDA_ERR_BAD_ARG;
+    if (n_ts == 0) return CMDA_OK;
+    if (!d_t || !d_ms_to_idx || !d_timestamps || !d_index || !d_status) return CMDA_ERR_BAD_ARG;
+    return launch_images_to_events_index(d_t, n, d_ms_to_idx, n_ms, t_offset, d_timestamps, n_ts, d_index, d_status,
+                                         static_cast<cudaStream_t>(stream));
+}
+
+size_t cmda_events_vg_workspace_bytes(int64_t total_events, int S, int H, int W, int B, int mode) {
+    if (S <= 0 || H <= 0 || W <= 0 || B <= 0 || total_events < 0) return 0;
+    const int group = S < kMaxWindows ? S : kMaxWindows;
+    size_t need = stats_bytes(S);
+    const size_t g = acc_bytes(group, H, W, B);
+    size_t t = 0;
+    if (mode != CMDA_VOXEL_GLOBAL && tiled_supported(H, W, B)) t = tiled_workspace_bytes(total_events, S, H, W, B);
+    // AUTO may resolve to either path, so it reserves the larger of the two
+    if (mode == CMDA_VOXEL_GLOBAL) need += g;
+    else if (mode == CMDA_VOXEL_TILED) need += (t ? t : g);
+    else need += (t > g ? t : g);
+    return need + 256;
+}
+
+int cmda_events_vg_batch(const uint32_t* d_t, const uint16_t* d_x, const uint16_t* d_y, const uint8_t* d_p,
+                         const int64_t* h_win_start, const int64_t* h_win_end, int S, const float* d_rectify_map,
+                         const int32_t* h_map_id, int H, int W, int B, const float* h_clip, float final_range,
+                         int enforce_no_events_zero, int normalize, float* d_out, float* d_raw_out,
+                         int64_t* d_bin_counts, void* d_workspace, size_t workspace_bytes, int mode, void* stream) {
+    if (S < 0 || H <= 0 || W <= 0 || B <= 0) return CMDA_ERR_BAD_ARG;
+    if (S == 0) return CMDA_OK;
+    if (!d_t || !d_x || !d_y || !d_p || !h_win_start || !h_win_end || !d_out || !d_workspace) return CMDA_ERR_BAD_ARG;
+    if (normalize && !h_clip) return CMDA_ERR_BAD_ARG;
+    if (mode != CMDA_VOXEL_GLOBAL && mode != CMDA_VOXEL_TILED && mode != CMDA_VOXEL_AUTO) return CMDA_ERR_BAD_ARG;
+    if (reinterpret_cast<uintptr_t>(d_workspace) & 255) return CMDA_ERR_WORKSPACE;
+    long long total = 0;
+    for (int s = 0; s < S; ++s) {
+        if (h_win_start[s] < 0) return CMDA_ERR_BAD_ARG;
+        if (h_map_id && h_map_id[s] < 0) return CMDA_ERR_BAD_ARG;
+        const long long n = h_win_end[s] - h_win_start[s];
+        if (n > 0) total += n;
+    }
+    if (workspace_bytes < cmda_events_vg_workspace_bytes(total, S, H, W, B, mode)) return CMDA_ERR_WORKSPACE;
+    const int use_mode = resolve_mode(mode, total, S, H, W, B);
+    if (use_mode == CMDA_VOXEL_TILED && !tiled_supported(H, W, B)) return CMDA_ERR_UNSUPPORTED;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long V = static_cast<long long>(B) * H * W;
+
+    char* ws = static_cast<char*>(d_workspace);
+    PartialStats* partials = reinterpret_cast<PartialStats*>(ws);
+    char* scratch = ws + stats_bytes(S);
+    const size_t scratch_bytes = workspace_bytes - stats_bytes(S);
+    if (d_bin_counts) CMDA_CUDA_TRY(cudaMemsetAsync(d_bin_counts, 0, sizeof(int64_t) * S * B, st));
+
+    for (int s0 = 0; s0 < S; s0 += kMaxWindows) {
+        const int sn = (S - s0) < kMaxWindows ? (S - s0) : kMaxWindows;
+        WindowTable tab{};
+        long long max_events = 0;
+        for (int k = 0; k < sn; ++k) {
+            const int s = s0 + k;
+            tab.w[k].start = h_win_start[s];
+            tab.w[k].end = h_win_end[s] > h_win_start[s] ? h_win_end[s] : h_win_start[s];
+            tab.w[k].map_id = h_map_id ? h_map_id[s] : 0;
+            tab.w[k].clip = h_clip ? h_clip[s] : 1.0f;
+            const long long n = tab.w[k].end - tab.w[k].start;
+            if (n > max_events) max_events = n;
+        }
+        float* out_g = d_out + static_cast<size_t>(s0) * V;
+        float* raw_g = (normalize && d_raw_out) ? d_raw_out + static_cast<size_t>(s0) * V : out_g;
+        PartialStats* part_g = partials + static_cast<size_t>(s0) * kStatBlocks;
+        int64_t* bins_g = d_bin_counts ? d_bin_counts + static_cast<size_t>(s0) * B : nullptr;
+        int rc;
+        if (use_mode == CMDA_VOXEL_TILED) {
+            rc = launch_tiled_raw(d_t, d_x, d_y, d_p, tab, sn, d_rectify_map, H, W, B, raw_g, part_g, bins_g, scratch,
+                                  scratch_bytes, st);
+            if (rc != CMDA_OK) return rc;
+        } else {
+            long long* acc = reinterpret_cast<long long*>(scratch);
+            CMDA_CUDA_TRY(cudaMemsetAsync(acc, 0, sizeof(long long) * sn * V, st));
+            rc = launch_scatter_global_raw(d_t, d_x, d_y, d_p, tab, sn, max_events, d_rectify_map, H, W, B, acc, bins_g, st);
+            if (rc != CMDA_OK) return rc;
+            rc = launch_convert_stats(acc, raw_g, sn, V, part_g, st);
+            if (rc != CMDA_OK) return rc;
+        }
+        if (normalize) {
+            rc = launch_norm_apply(raw_g, out_g, sn, V, part_g, tab, final_range, enforce_no_events_zero, st);
+            if (rc != CMDA_OK) return rc;
+        }
+    }
+    return CMDA_OK;
+}
+
+int cmda_voxel_grid_f32(const float* d_time, const float* d_x, const float* d_y, const float* d_pol, int64_t n, int W,
+                        int H, int B, float* d_grid, int64_t* d_bin_counts, void* d_workspace, size_t workspace_bytes,
+                        int mode, void* stream) {
+    if (n < 0 || H <= 0 || W <= 0 || B <= 0 || !d_grid || !d_workspace) return CMDA_ERR_BAD_ARG;
+    if (n > 0 && (!d_time || !d_x || !d_y || !d_pol)) return CMDA_ERR_BAD_ARG;
+    if (mode != CMDA_VOXEL_GLOBAL && mode != CMDA_VOXEL_TILED && mode != CMDA_VOXEL_AUTO) return CMDA_ERR_BAD_ARG;
+    if (reinterpret_cast<uintptr_t>(d_workspace) & 255) return CMDA_ERR_WORKSPACE;
+    if (workspace_bytes < cmda_events_vg_workspace_bytes(n, 1, H, W, B, mode)) return CMDA_ERR_WORKSPACE;
+    const int use_mode = resolve_mode(mode, n, 1, H, W, B);
+    if (use_mode == CMDA_VOXEL_TILED && !tiled_supported(H, W, B)) return CMDA_ERR_UNSUPPORTED;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long V = static_cast<long long>(B) * H * W;
+    char* ws = static_cast<char*>(d_workspace);
+    PartialStats* partials = reinterpret_cast<PartialStats*>(ws);
+    char* scratch = ws + stats_bytes(1);
+    if (d_bin_counts) CMDA_CUDA_TRY(cudaMemsetAsync(d_bin_counts, 0, sizeof(int64_t) * B, st));
+    if (use_mode == CMDA_VOXEL_TILED)
+        return launch_tiled_f32(d_time, d_x, d_y, d_pol, n, H, W, B, d_grid, partials, d_bin_counts, scratch,
+                                workspace_bytes - stats_bytes(1), st);
+    long long* acc = reinterpret_cast<long long*>(scratch);
+    CMDA_CUDA_TRY(cudaMemsetAsync(acc, 0, sizeof(long long) * V, st));
+    int rc = launch_scatter_global_f32(d_time, d_x, d_y, d_pol, n, H, W, B, acc, d_bin_counts, st);
+    if (rc != CMDA_OK) return rc;
+    return launch_convert_stats(acc, d_grid, 1, V, partials, st);
+}
+
+size_t cmda_events_norm_workspace_bytes(int S) { return S > 0 ? stats_bytes(S) + 256 : 0; }
+
+int cmda_events_norm_batch(float* d_grid, int S, int64_t voxels, const float* h_clip, float final_range,
+                           int enforce_no_events_zero, void* d_workspace, size_t workspace_bytes, void* stream) {
+    if (S < 0 || voxels <= 0) return CMDA_ERR_BAD_ARG;
+    if (S == 0) return CMDA_OK;
+    if (!d_grid || !h_clip || !d_workspace) return CMDA_ERR_BAD_ARG;
+    if ((reinterpret_cast<uintptr_t>(d_workspace) & 255) || workspace_bytes < cmda_events_norm_workspace_bytes(S))
+        return CMDA_ERR_WORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    PartialStats* partials = static_cast<PartialStats*>(d_workspace);
+    for (int s0 = 0; s0 < S; s0 += kMaxWindows) {
+        const int sn = (S - s0) < kMaxWindows ? (S - s0) : kMaxWindows;
+        WindowTable tab{};
+        for (int k = 0; k < sn; ++k) tab.w[k].clip = h_clip[s0 + k];
+        float* g = d_grid + static_cast<size_t>(s0) * voxels;
+        PartialStats* pg = partials + static_cast<size_t>(s0) * kStatBlocks;
+        int rc = launch_convert_stats(nullptr, g, sn, voxels, pg, st);
+        if (rc != CMDA_OK) return rc;
+        rc = launch_norm_apply(g, g, sn, voxels, pg, tab, final_range, enforce_no_events_zero, st);
+        if (rc != CMDA_OK) return rc;
+    }
+    return CMDA_OK;
+}
+
+int cmda_remap_events(const uint32_t* d_t, const uint16_t* d_x, const uint16_t* d_y, const uint8_t* d_p, int64_t start,
+                      int64_t end, const float* d_rectify_map, int H, int W, int B, float* d_xr, float* d_yr,
+                      float* d_tn, int32_t* d_x0, int32_t* d_y0, int32_t* d_t0, void* stream) {
+    if (start < 0 || H <= 0 || W <= 0 || B <= 0) return CMDA_ERR_BAD_ARG;
+    if (end <= start) return CMDA_OK;
+    if (!d_t || !d_x || !d_y || !d_p) return CMDA_ERR_BAD_ARG;
+    return launch_remap(d_t, d_x, d_y, d_p, start, end, d_rectify_map, H, W, B, d_xr, d_yr, d_tn, d_x0, d_y0, d_t0,
+                        static_cast<cudaStream_t>(stream));
+}
+
+size_t cmda_image_workspace_bytes(int S, int H, int W, int channels) {
+    if (S <= 0 || H <= 0 || W <= 0) return 0;
+    size_t need = align_up(sizeof(unsigned) * 16 * static_cast<size_t>(S), 256);
+    if (channels == 3) need += align_up(static_cast<size_t>(S) * H * W, 256);
+    return need + 256;
+}
+
+int cmda_logdiff_pair_u8(const uint8_t* d_now, const uint8_t* d_front, int S, int H, int W, const float* h_lut,
+                         float thr, float clip, float* d_out_f32, uint8_t* d_out_u8, void* d_workspace,
+                         size_t workspace_bytes, void* stream) {
+    if (S < 0 || H <= 0 || W <= 0) return CMDA_ERR_BAD_ARG;
+    if (S == 0) return CMDA_OK;
+    if (!d_now || !d_front || !h_lut || (!d_out_f32 && !d_out_u8) || !d_workspace) return CMDA_ERR_BAD_ARG;
+    if ((reinterpret_cast<uintptr_t>(d_workspace) & 255) || workspace_bytes < cmda_image_workspace_bytes(S, H, W, 1))
+        return CMDA_ERR_WORKSPACE;
+    return launch_pair(d_now, d_front, S, H, W, h_lut, thr, clip, d_out_f32, d_out_u8,
+                       static_cast<unsigned*>(d_workspace), static_cast<cudaStream_t>(stream));
+}
+
+int cmda_isr_shift_u8(const uint8_t* d_img, int channels, int S, int H, int W, int shift_pixel, int direction,
+                      const float* h_lut, float thr, float clip, float* d_out, void* d_workspace,
+                      size_t workspace_bytes, void* stream) {
+    if (S < 0 || H <= 0 || W <= 0 || (channels != 1 && channels != 3)) return CMDA_ERR_BAD_ARG;
+    if (direction < CMDA_DIR_RIGHTDOWN || direction > CMDA_DIR_ALL) return CMDA_ERR_BAD_ARG;
+    // numpy slicing of the reference (utils.py:129-132) needs 0 <= shift <= min(H, W)
+    if (shift_pixel < 0 || shift_pixel > W || shift_pixel > H) return CMDA_ERR_BAD_ARG;
+    if (S == 0) return CMDA_OK;
+    if (!d_img || !h_lut || !d_out || !d_workspace) return CMDA_ERR_BAD_ARG;
+    if ((reinterpret_cast<uintptr_t>(d_workspace) & 255) ||
+        workspace_bytes < cmda_image_workspace_bytes(S, H, W, channels))
+        return CMDA_ERR_WORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned* slots = static_cast<unsigned*>(d_workspace);
+    const uint8_t* gray = d_img;
+    if (channels == 3) {
+        uint8_t* g = reinterpret_cast<uint8_t*>(d_workspace) + align_up(sizeof(unsigned) * 16 * static_cast<size_t>(S), 256);
+        int rc = launch_rgb_to_gray(d_img, static_cast<int64_t>(S) * H * W, g, st);
+        if (rc != CMDA_OK) return rc;
+        gray = g;
+    }
+    return launch_isr(gray, S, H, W, shift_pixel, direction, h_lut, thr, clip, d_out, slots, st);
+}
+
+int cmda_rgb_to_gray_u8(const uint8_t* d_rgb, int64_t n_pixels, uint8_t* d_gray, void* stream) {
+    if (n_pixels < 0) return CMDA_ERR_BAD_ARG;
+    if (n_pixels == 0) return CMDA_OK;
+    if (!d_rgb || !d_gray) return CMDA_ERR_BAD_ARG;
+    return launch_rgb_to_gray(d_rgb, n_pixels, d_gray, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,128 @@
+// Per-event arithmetic shared by every voxel kernel: window-relative time, rectify-map
+// gather, truncation, tent weights, fixed-point quantisation.  Every float operation is
+// an explicit round-to-nearest intrinsic so that nvcc can neither contract into FMA nor
+// reassociate: the per-contribution float32 weights are bit-identical to the reference's
+// (mmseg/datasets/dsec.py:38-52, 347-355).
+#pragma once
+#include "common.cuh"
+
+namespace cmda {
+
+// What one event contributes, before the corner expansion.
+struct Event {
+    float x, y;     // rectified coordinates (dsec.py:351-355)
+    float tn;       // t_norm in [0, B-1] or NaN (dsec.py:38-39)
+    float value;    // 2*pol - 1 (dsec.py:45)
+};
+
+// Window constants of the raw DSEC path (dsec.py:347-348 followed by dsec.py:38-39).
+struct RawWindowTime {
+    uint32_t t_first;
+    float fdT;        // float32(t[-1] - t[0])
+    float t01_first;  // (t - t[0])[0] / fdT  = 0 or NaN
+    float den;        // t01[-1] - t01[0]     = 1 or NaN
+    float cm1;        // C - 1
+};
+
+__device__ __forceinline__ RawWindowTime raw_window_time(const uint32_t* __restrict__ t, long long start,
+                                                         long long end, int B) {
+    RawWindowTime w;
+    w.t_first = __ldg(t + start);
+    w.fdT = __uint2float_rn(__ldg(t + end - 1) - w.t_first);       // uint32 subtraction, then astype(float32)
+    w.t01_first = __fdiv_rn(0.0f, w.fdT);                          // events_t[0] after the division
+    const float t01_last = __fdiv_rn(w.fdT, w.fdT);                // events_t[-1] after the division
+    w.den = __fsub_rn(t01_last, w.t01_first);
+    w.cm1 = static_cast<float>(B - 1);
+    return w;
+}
+
+__device__ __forceinline__ float raw_t_norm(uint32_t t, const RawWindowTime& w) {
+    const float t01 = __fdiv_rn(__uint2float_rn(t - w.t_first), w.fdT);   // dsec.py:347-348
+    const float a = __fsub_rn(t01, w.t01_first);                          // dsec.py:39
+    const float b = __fmul_rn(w.cm1, a);
+    return __fdiv_rn(b, w.den);
+}
+
+__device__ __forceinline__ Event make_raw_event(uint32_t t, unsigned x, unsigned y, unsigned p,
+                                                const float2* __restrict__ map, int H, int W,
+                                                const RawWindowTime& w, bool& in_map) {
+    Event e;
+    in_map = (x < static_cast<unsigned>(W)) && (y < static_cast<unsigned>(H));
+    if (map != nullptr) {
+        // numpy would raise IndexError for an out-of-range (y, x); such events are dropped
+        const float2 m = in_map ? __ldg(map + static_cast<size_t>(y) * W + x) : make_float2(-2.0f, -2.0f);
+        e.x = m.x; e.y = m.y;                                             // dsec.py:351-353
+    } else {
+        e.x = static_cast<float>(x); e.y = static_cast<float>(y);
+        in_map = true;
+    }
+    e.tn = raw_t_norm(t, w);
+    e.value = __fsub_rn(__fmul_rn(2.0f, static_cast<float>(p)), 1.0f);    // dsec.py:349, 45
+    return e;
+}
+
+// Window constants of the float path (events_to_voxel_grid called directly).
+struct F32WindowTime {
+    float t_first, den, cm1;
+};
+__device__ __forceinline__ F32WindowTime f32_window_time(const float* __restrict__ time, long long n, int B) {
+    F32WindowTime w;
+    w.t_first = __ldg(time);
+    w.den = __fsub_rn(__ldg(time + n - 1), w.t_first);
+    w.cm1 = static_cast<float>(B - 1);
+    return w;
+}
+__device__ __forceinline__ Event make_f32_event(float t, float x, float y, float pol, const F32WindowTime& w) {
+    Event e;
+    e.x = x; e.y = y;
+    e.tn = __fdiv_rn(__fmul_rn(w.cm1, __fsub_rn(t, w.t_first)), w.den);   // dsec.py:38-39
+    e.value = __fsub_rn(__fmul_rn(2.0f, pol), 1.0f);
+    return e;
+}
+
+// Corner origin of an event; `any` is false when no corner can be inside the grid.
+struct Origin {
+    int x0, y0, t0;
+    bool any;
+};
+__device__ __forceinline__ Origin origin_of(const Event& e, int H, int W, int B) {
+    Origin o;
+    o.x0 = trunc_like_x86(e.x);                                           // dsec.py:41
+    o.y0 = trunc_like_x86(e.y);                                           // dsec.py:42
+    o.t0 = trunc_like_x86(e.tn);                                          // dsec.py:43
+    o.any = (o.x0 >= -1) && (o.x0 < W) && (o.y0 >= -1) && (o.y0 < H) && (o.t0 >= -1) && (o.t0 < B);
+    return o;
+}
+
+// Quantise one float32 contribution to a 2^-30 fixed-point integer.  Scaling by a power
+// of two is exact, so the only rounding is the float->int conversion, which is exact for
+// |w| >= 2^-7 and otherwise rounds at 2^-30 (9.3e-10 absolute).
+__device__ __forceinline__ long long quantise(float w) {
+    return __float2ll_rn(__fmul_rn(w, kFixScale));
+}
+
+// Calls f(xl, yl, tl, w) for each in-bounds corner, in the reference's nest order
+// (x outer, y, t inner: dsec.py:47-52) with the reference's left-to-right products.
+template <typename F>
+__device__ __forceinline__ void for_each_corner(const Event& e, const Origin& o, int H, int W, int B, F&& f) {
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+        const int xl = o.x0 + dx;
+        if (xl < 0 || xl >= W) continue;
+        const float vx = __fmul_rn(e.value, tent(xl, e.x));
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+            const int yl = o.y0 + dy;
+            if (yl < 0 || yl >= H) continue;
+            const float vxy = __fmul_rn(vx, tent(yl, e.y));
+#pragma unroll
+            for (int dt = 0; dt < 2; ++dt) {
+                const int tl = o.t0 + dt;
+                if (tl < 0 || tl >= B) continue;
+                f(xl, yl, tl, __fmul_rn(vxy, tent(tl, e.tn)));
+            }
+        }
+    }
+}
+
+}  // namespace cmda

@@ -1,0 +1,220 @@
+// K3 -- events_norm: global z-score over the non-zero voxels of one window, sign split,
+// clamp, min-max to [0, r] / [-r, 0], sum.
+// Follows /root/reference/mmseg/datasets/dsec.py:80-121 (numeric clip_range) and
+// tensor_normalize_to_range dsec.py:73-77.
+//
+// Two phases per window: (1) statistics (count / sum / sum of squares / min and max of the
+// non-zero voxels) reduced in a FIXED order -- kStatBlocks partials per window, each a fixed
+// thread->element mapping and a fixed butterfly, merged sequentially -- so the result is
+// bit-reproducible; (2) an element-wise apply.  The min/max of the clamped positive and
+// negative parts that the reference obtains with four more full-grid reductions follow
+// from the non-zero min/max, because every step between the raw value and the clamped
+// part is a monotone non-decreasing float32 map.  Sums are accumulated in float64 (the
+// reference's float32 torch.sum order is third-party; effect on the output <= 2e-7).
+#include "common.cuh"
+
+namespace cmda {
+
+constexpr int kNormThreads = 256;
+
+struct BlockStats {
+    double sum, sumsq;
+    long long nnz;
+    float mn, mx;
+};
+
+__device__ __forceinline__ void stats_add(BlockStats& st, float v) {
+    if (v != 0.0f) {                                   // dsec.py:88
+        st.nnz += 1;
+        st.mn = fminf(st.mn, v);
+        st.mx = fmaxf(st.mx, v);
+    }
+    st.sum += static_cast<double>(v);                  // dsec.py:91 events.sum()
+    st.sumsq += static_cast<double>(__fmul_rn(v, v));  // dsec.py:92 (events ** 2).sum()
+}
+
+__device__ void block_stats_store(BlockStats st, PartialStats* __restrict__ dst) {
+    __shared__ double s_sum[kNormThreads / 32], s_sq[kNormThreads / 32];
+    __shared__ long long s_n[kNormThreads / 32];
+    __shared__ float s_mn[kNormThreads / 32], s_mx[kNormThreads / 32];
+    st.sum = warp_sum(st.sum);
+    st.sumsq = warp_sum(st.sumsq);
+    st.nnz = warp_sum(st.nnz);
+    st.mn = warp_min(st.mn);
+    st.mx = warp_max(st.mx);
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { s_sum[wid] = st.sum; s_sq[wid] = st.sumsq; s_n[wid] = st.nnz; s_mn[wid] = st.mn; s_mx[wid] = st.mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        PartialStats o;
+        o.sum = 0.0; o.sumsq = 0.0; o.nnz = 0; o.min_nz = INFINITY; o.max_nz = -INFINITY;
+        for (int w = 0; w < kNormThreads / 32; ++w) {   // fixed order
+            o.sum += s_sum[w]; o.sumsq += s_sq[w]; o.nnz += s_n[w];
+            o.min_nz = fminf(o.min_nz, s_mn[w]); o.max_nz = fmaxf(o.max_nz, s_mx[w]);
+        }
+        *dst = o;
+    }
+}
+
+// FROM_I64: src is the 2^-30 fixed-point accumulator grid; the float32 raw grid is written
+// to raw (value = correctly rounded float32 of the exact integer sum, times 2^-30).
+template <bool FROM_I64>
+__global__ void __launch_bounds__(kNormThreads)
+convert_stats_kernel(const long long* __restrict__ acc, float* __restrict__ raw, long long V,
+                     PartialStats* __restrict__ partials) {
+    const int s = blockIdx.y;
+    const long long seg = (V + kStatBlocks - 1) / kStatBlocks;
+    const long long lo = static_cast<long long>(blockIdx.x) * seg;
+    const long long hi = (lo + seg < V) ? lo + seg : V;
+    BlockStats st{0.0, 0.0, 0, INFINITY, -INFINITY};
+    float* r = raw + static_cast<size_t>(s) * V;
+    const long long* a = FROM_I64 ? acc + static_cast<size_t>(s) * V : nullptr;
+    for (long long i = lo + threadIdx.x; i < hi; i += kNormThreads) {
+        float v;
+        if (FROM_I64) {
+            v = __fmul_rn(__ll2float_rn(a[i]), kFixInv);
+            r[i] = v;
+        } else {
+            v = r[i];
+        }
+        stats_add(st, v);
+    }
+    block_stats_store(st, partials + static_cast<size_t>(s) * kStatBlocks + blockIdx.x);
+}
+
+struct NormParams {
+    int has_nz;      // num_nonzeros > 0 (dsec.py:90)
+    int all_nan;     // stddev is NaN -> every output is NaN, as in the reference
+    float mean, den; // dsec.py:91-93
+    float clip, final_range;
+    float pmin, pden, nmin, nden;
+};
+
+__device__ __forceinline__ float zscore(float e, const NormParams& q) {
+    if (!q.has_nz) return e;
+    const float m = (e != 0.0f) ? 1.0f : 0.0f;                          // dsec.py:93 mask
+    return __fdiv_rn(__fmul_rn(m, __fsub_rn(e, q.mean)), q.den);        // dsec.py:94
+}
+__device__ __forceinline__ float pos_part(float z, float clip) {
+    const float p = z < 0.0f ? 0.0f : z;                                // dsec.py:108
+    return fminf(fmaxf(p, 0.0f), clip);                                 // dsec.py:110
+}
+__device__ __forceinline__ float neg_part(float z, float clip) {
+    const float n = z > 0.0f ? 0.0f : z;                                // dsec.py:112
+    return fminf(fmaxf(n, -clip), 0.0f);                                // dsec.py:114
+}
+
+__device__ NormParams make_norm_params(const PartialStats* __restrict__ partials, long long V, float clip,
+                                       float final_range) {
+    double sum = 0.0, sumsq = 0.0;
+    long long nnz = 0;
+    float mn = INFINITY, mx = -INFINITY;
+    for (int b = 0; b < kStatBlocks; ++b) {             // fixed order
+        const PartialStats p = partials[b];
+        sum += p.sum; sumsq += p.sumsq; nnz += p.nnz;
+        mn = fminf(mn, p.min_nz); mx = fmaxf(mx, p.max_nz);
+    }
+    NormParams q{};
+    q.clip = clip;
+    q.final_range = final_range;
+    q.has_nz = nnz > 0;
+    q.mean = 0.0f;
+    q.den = 1.0f;
+    if (q.has_nz) {
+        const float fn = __ll2float_rn(nnz);
+        q.mean = __fdiv_rn(__double2float_rn(sum), fn);                                  // dsec.py:91
+        const float var = __fsub_rn(__fdiv_rn(__double2float_rn(sumsq), fn), __fmul_rn(q.mean, q.mean));
+        const float sd = __fsqrt_rn(var);                                                // dsec.py:92
+        q.den = __fadd_rn(sd, 1e-8f);
+        q.all_nan = isnan(sd);
+    }
+    // min / max of the clamped parts over the whole grid: values come from the non-zero
+    // extremes and, when any voxel is zero, from z(0)
+    const bool has_zero = nnz < V;
+    float pmax = -INFINITY, pmin = INFINITY, nmax = -INFINITY, nmin = INFINITY;
+    if (q.has_nz) {
+        const float zhi = zscore(mx, q), zlo = zscore(mn, q);
+        pmax = pos_part(zhi, clip); pmin = pos_part(zlo, clip);
+        nmax = neg_part(zhi, clip); nmin = neg_part(zlo, clip);
+    }
+    if (has_zero) {
+        const float z0 = zscore(0.0f, q);
+        pmax = fmaxf(pmax, pos_part(z0, clip)); pmin = fminf(pmin, pos_part(z0, clip));
+        nmax = fmaxf(nmax, neg_part(z0, clip)); nmin = fminf(nmin, neg_part(z0, clip));
+    }
+    q.pmin = pmin;
+    q.pden = __fadd_rn(__fsub_rn(pmax, pmin), 1e-8f);                                    // dsec.py:76
+    q.nmin = nmin;
+    q.nden = __fadd_rn(__fsub_rn(nmax, nmin), 1e-8f);
+    return q;
+}
+
+__device__ __forceinline__ float norm_one(float e, const NormParams& q, bool enforce) {
+    if (q.all_nan) return __int_as_float(0x7fc00000);
+    const float z = zscore(e, q);
+    if (enforce) {                                                                       // dsec.py:106-117
+        float p = __fdiv_rn(__fsub_rn(pos_part(z, q.clip), q.pmin), q.pden);
+        p = __fadd_rn(__fmul_rn(p, q.final_range), 0.0f);                                // * (r - 0) + 0
+        float n = __fdiv_rn(__fsub_rn(neg_part(z, q.clip), q.nmin), q.nden);
+        n = __fadd_rn(__fmul_rn(n, q.final_range), -q.final_range);                      // * (0 - (-r)) + (-r)
+        return __fadd_rn(p, n);
+    }
+    float c = fminf(fmaxf(z, -q.clip), q.clip);                                          // dsec.py:119
+    c = __fmul_rn(c, q.final_range);
+    return __fmul_rn(__fdiv_rn(c, q.clip), q.final_range);                               // dsec.py:120
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(kNormThreads)
+norm_apply_kernel(const float* raw, float* out, long long V,   // raw may alias out (in-place call)
+                  const PartialStats* __restrict__ partials, WindowTable tab, float final_range, int enforce) {
+    __shared__ NormParams s_q;
+    const int s = blockIdx.y;
+    if (threadIdx.x == 0)
+        s_q = make_norm_params(partials + static_cast<size_t>(s) * kStatBlocks, V, tab.w[s].clip, final_range);
+    __syncthreads();
+    const NormParams q = s_q;
+    const float* r = raw + static_cast<size_t>(s) * V;
+    float* o = out + static_cast<size_t>(s) * V;
+    if (VEC) {
+        const long long n4 = V / 4;
+        for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+             i += static_cast<long long>(gridDim.x) * blockDim.x) {
+            const float4 v = reinterpret_cast<const float4*>(r)[i];
+            stg_stream_f4(o + i * 4, make_float4(norm_one(v.x, q, enforce), norm_one(v.y, q, enforce),
+                                                 norm_one(v.z, q, enforce), norm_one(v.w, q, enforce)));
+        }
+    } else {
+        for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < V;
+             i += static_cast<long long>(gridDim.x) * blockDim.x)
+            o[i] = norm_one(r[i], q, enforce);
+    }
+}
+
+int launch_convert_stats(const long long* acc, float* raw, int S, long long V, PartialStats* partials,
+                         cudaStream_t s) {
+    dim3 grid(kStatBlocks, S);
+    if (acc) convert_stats_kernel<true><<<grid, kNormThreads, 0, s>>>(acc, raw, V, partials);
+    else convert_stats_kernel<false><<<grid, kNormThreads, 0, s>>>(nullptr, raw, V, partials);
+    CMDA_LAUNCH_CHECK();
+    return CMDA_OK;
+}
+
+int launch_norm_apply(const float* raw, float* out, int S, long long V, const PartialStats* partials,
+                      const WindowTable& tab, float final_range, int enforce, cudaStream_t s) {
+    const bool vec = (V % 4 == 0) && ((reinterpret_cast<uintptr_t>(raw) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    long long per = vec ? V / 4 : V;
+    long long gx = (per + kNormThreads - 1) / kNormThreads;
+    long long cap = (148LL * 8 + S - 1) / S;
+    if (cap < 1) cap = 1;
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    dim3 grid(static_cast<unsigned>(gx), S);
+    if (vec) norm_apply_kernel<true><<<grid, kNormThreads, 0, s>>>(raw, out, V, partials, tab, final_range, enforce);
+    else norm_apply_kernel<false><<<grid, kNormThreads, 0, s>>>(raw, out, V, partials, tab, final_range, enforce);
+    CMDA_LAUNCH_CHECK();
+    return CMDA_OK;
+}
+
+}  // namespace cmda

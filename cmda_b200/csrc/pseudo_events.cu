@@ -1,0 +1,404 @@
+// K4 / K5 -- log-intensity-change pseudo-events.
+//   K4 frame pair : /root/reference/create_cityscapes_image_change.py:16-35 (get_image_change)
+//   K5 shift pair : /root/reference/mmseg/datasets/utils.py:87-152 (get_ic, get_image_change_from_pil)
+//
+// Both are u8 -> f32 element-wise maps around two global min/max pairs per term, so each
+// is two passes over the (L2-resident) u8 input: pass 1 reduces min/max of the clamped
+// positive and negative parts, pass 2 re-evaluates the difference and writes the result
+// with 128-bit stores.  There are only 256 distinct log values, so the logarithm is a
+// 256-entry table the CALLER computes with numpy exactly as the reference does; every
+// other operation is an IEEE float32 op with one rounding, which makes the whole path
+// bit-exact against the reference.  HBM-bound: algorithmic bytes (1+1+4)·H·W per pair,
+// (1+4)·H·W per gray shift-pair image.
+#include "common.cuh"
+
+namespace cmda {
+
+constexpr int kPxPerThread = 4;
+constexpr int kImgThreads = 256;
+
+// Direction codes of one term: 0 left, 1 right, 2 up, 3 down (utils.py:129-132).
+struct TermList {
+    int n;
+    int dir[4];
+};
+
+__host__ __device__ inline TermList terms_of(int direction) {
+    TermList t{};
+    if (direction == CMDA_DIR_ALL) {  // up, left, down, right -- utils.py:133-137
+        t.n = 4; t.dir[0] = 2; t.dir[1] = 0; t.dir[2] = 3; t.dir[3] = 1;
+    } else {                           // column-shift term first, row-shift term second -- utils.py:139-151
+        t.n = 2;
+        t.dir[0] = (direction == CMDA_DIR_LEFTDOWN || direction == CMDA_DIR_LEFTUP) ? 0 : 1;
+        t.dir[1] = (direction == CMDA_DIR_RIGHTUP || direction == CMDA_DIR_LEFTUP) ? 2 : 3;
+    }
+    return t;
+}
+
+// gray value of the shifted copy at (r, c): the first (right/down) or last (left/up)
+// `s` columns/rows are left unshifted (utils.py:129-132, 140-148)
+__device__ __forceinline__ int shifted_at(const uint8_t* __restrict__ g, int H, int W, int r, int c, int s, int dir) {
+    int rr = r, cc = c;
+    if (dir == 0) { if (c < W - s) cc = c + s; }
+    else if (dir == 1) { if (c >= s) cc = c - s; }
+    else if (dir == 2) { if (r < H - s) rr = r + s; }
+    else { if (r >= s) rr = r - s; }
+    return __ldg(g + static_cast<size_t>(rr) * W + cc);
+}
+
+// dead zone + sign split + clamp (utils.py:95-101 / create_cityscapes_image_change.py:22-28)
+__device__ __forceinline__ void split_clamp(float d, float thr, float clip, float& pos, float& neg) {
+    if (fabsf(d) <= thr) d = 0.0f;
+    pos = d < 0.0f ? 0.0f : d;
+    pos = fminf(fmaxf(pos, 0.0f), clip);
+    neg = d > 0.0f ? 0.0f : d;
+    neg = fminf(fmaxf(neg, -clip), 0.0f);
+}
+
+// Running min/max of one term, kept as unsigned bit patterns so that a zero-initialised
+// workspace is the neutral element of every slot and the merge is atomicMax (exact and
+// order independent): [0] max pos, [1] ~min pos, [2] max |neg|, [3] ~min |neg|.
+struct MinMaxAcc {
+    unsigned s[4];
+    __device__ __forceinline__ void init() { s[0] = s[1] = s[2] = s[3] = 0u; }
+    __device__ __forceinline__ void add(float pos, float neg) {
+        const unsigned pb = __float_as_uint(pos + 0.0f);          // +0.0f folds -0 into +0
+        const unsigned nb = __float_as_uint(fabsf(neg));
+        s[0] = max(s[0], pb);
+        s[1] = max(s[1], ~pb);
+        s[2] = max(s[2], nb);
+        s[3] = max(s[3], ~nb);
+    }
+};
+
+struct TermRange {
+    float pmin, pden, nmin, nden;
+};
+
+__device__ __forceinline__ TermRange decode_range(const unsigned* __restrict__ slots) {
+    const float pmax = __uint_as_float(slots[0]);
+    const float pmin = __uint_as_float(~slots[1]);
+    const float nmin = -__uint_as_float(slots[2]);
+    const float nmax = -__uint_as_float(~slots[3]);
+    TermRange r;
+    r.pmin = pmin;
+    r.pden = __fadd_rn(__fsub_rn(pmax, pmin), 1e-8f);   // tensor_max - tensor_min + 1e-8
+    r.nmin = nmin;
+    r.nden = __fadd_rn(__fsub_rn(nmax, nmin), 1e-8f);
+    return r;
+}
+
+// tensor_normalize_to_range of both parts and their sum (utils.py:101-104)
+__device__ __forceinline__ float normalize_term(float pos, float neg, const TermRange& r) {
+    float p = __fdiv_rn(__fsub_rn(pos, r.pmin), r.pden);
+    p = __fadd_rn(__fmul_rn(p, 1.0f), 0.0f);               // * (1 - 0) + 0
+    float n = __fdiv_rn(__fsub_rn(neg, r.nmin), r.nden);
+    n = __fadd_rn(__fmul_rn(n, 1.0f), -1.0f);              // * (0 - (-1)) + (-1)
+    return __fadd_rn(p, n);
+}
+
+template <int NT>
+__device__ __forceinline__ void flush_minmax(MinMaxAcc (&acc)[NT], unsigned* __restrict__ slots) {
+#pragma unroll
+    for (int k = 0; k < NT; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const unsigned v = __reduce_max_sync(0xffffffffu, acc[k].s[j]);
+            if ((threadIdx.x & 31) == 0 && v != 0u) atomicMax(slots + k * 4 + j, v);
+        }
+}
+
+// ------------------------------------------------------------------ K5 shift pair
+template <int NT>
+__global__ void __launch_bounds__(kImgThreads)
+isr_minmax_kernel(const uint8_t* __restrict__ gray, int H, int W, int shift, TermList terms, LogLut lut_in,
+                  float thr, float clip, unsigned* __restrict__ ws) {
+    __shared__ float lut[256];
+    if (threadIdx.x < 256) lut[threadIdx.x] = lut_in.v[threadIdx.x];
+    __syncthreads();
+    const int img = blockIdx.y;
+    const uint8_t* g = gray + static_cast<size_t>(img) * H * W;
+    const long long npx = static_cast<long long>(H) * W;
+    MinMaxAcc acc[NT];
+#pragma unroll
+    for (int k = 0; k < NT; ++k) acc[k].init();
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < npx;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int r = static_cast<int>(i / W), c = static_cast<int>(i - static_cast<long long>(r) * W);
+        const float base = lut[__ldg(g + i)];
+#pragma unroll
+        for (int k = 0; k < NT; ++k) {
+            const float d = __fsub_rn(lut[shifted_at(g, H, W, r, c, shift, terms.dir[k])], base);  // utils.py:92
+            float pos, neg;
+            split_clamp(d, thr, clip, pos, neg);
+            acc[k].add(pos, neg);
+        }
+    }
+    flush_minmax<NT>(acc, ws + static_cast<size_t>(img) * 16);
+}
+
+template <int NT, bool VEC>
+__global__ void __launch_bounds__(kImgThreads)
+isr_apply_kernel(const uint8_t* __restrict__ gray, int H, int W, int shift, TermList terms, LogLut lut_in, float thr,
+                 float clip, const unsigned* __restrict__ ws, float* __restrict__ out) {
+    __shared__ float lut[256];
+    if (threadIdx.x < 256) lut[threadIdx.x] = lut_in.v[threadIdx.x];
+    __syncthreads();
+    const int img = blockIdx.y;
+    const uint8_t* g = gray + static_cast<size_t>(img) * H * W;
+    float* o = out + static_cast<size_t>(img) * H * W;
+    TermRange rng[NT];
+#pragma unroll
+    for (int k = 0; k < NT; ++k) rng[k] = decode_range(ws + static_cast<size_t>(img) * 16 + k * 4);
+    const float inv = NT == 4 ? 0.25f : 0.5f;   // x / 4 and x / 2 are exact scalings
+    const long long npx = static_cast<long long>(H) * W;
+    const long long ngroups = (npx + kPxPerThread - 1) / kPxPerThread;
+    for (long long gi = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; gi < ngroups;
+         gi += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long i0 = gi * kPxPerThread;
+        float res[kPxPerThread];
+#pragma unroll
+        for (int j = 0; j < kPxPerThread; ++j) {
+            const long long i = i0 + j;
+            res[j] = 0.0f;
+            if (i < npx) {
+                const int r = static_cast<int>(i / W), c = static_cast<int>(i - static_cast<long long>(r) * W);
+                const float base = lut[__ldg(g + i)];
+                float sum = 0.0f;
+#pragma unroll
+                for (int k = 0; k < NT; ++k) {
+                    const float d = __fsub_rn(lut[shifted_at(g, H, W, r, c, shift, terms.dir[k])], base);
+                    float pos, neg;
+                    split_clamp(d, thr, clip, pos, neg);
+                    const float t = __fmul_rn(normalize_term(pos, neg, rng[k]), inv);
+                    sum = (k == 0) ? t : __fadd_rn(sum, t);       // utils.py:137 / 151, left to right
+                }
+                res[j] = sum;
+            }
+        }
+        if (VEC) {
+            stg_stream_f4(o + i0, make_float4(res[0], res[1], res[2], res[3]));
+        } else {
+#pragma unroll
+            for (int j = 0; j < kPxPerThread; ++j)
+                if (i0 + j < npx) o[i0 + j] = res[j];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ K4 frame pair
+__global__ void __launch_bounds__(kImgThreads)
+pair_minmax_kernel(const uint8_t* __restrict__ now, const uint8_t* __restrict__ front, long long npx, bool vec,
+                   LogLut lut_in, float thr, float clip, unsigned* __restrict__ ws) {
+    __shared__ float lut[256];
+    if (threadIdx.x < 256) lut[threadIdx.x] = lut_in.v[threadIdx.x];
+    __syncthreads();
+    const int img = blockIdx.y;
+    const uint8_t* a = now + static_cast<size_t>(img) * npx;
+    const uint8_t* b = front + static_cast<size_t>(img) * npx;
+    MinMaxAcc acc[1];
+    acc[0].init();
+    if (vec) {
+        const long long n16 = npx / 16;
+        for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n16;
+             i += static_cast<long long>(gridDim.x) * blockDim.x) {
+            const uint4 va = __ldg(reinterpret_cast<const uint4*>(a) + i);
+            const uint4 vb = __ldg(reinterpret_cast<const uint4*>(b) + i);
+            const unsigned wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float d = __fsub_rn(lut[(wa[q] >> (8 * j)) & 255u], lut[(wb[q] >> (8 * j)) & 255u]);  // :21
+                    float pos, neg;
+                    split_clamp(d, thr, clip, pos, neg);
+                    acc[0].add(pos, neg);
+                }
+        }
+    } else {
+        for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < npx;
+             i += static_cast<long long>(gridDim.x) * blockDim.x) {
+            const float d = __fsub_rn(lut[__ldg(a + i)], lut[__ldg(b + i)]);
+            float pos, neg;
+            split_clamp(d, thr, clip, pos, neg);
+            acc[0].add(pos, neg);
+        }
+    }
+    flush_minmax<1>(acc, ws + static_cast<size_t>(img) * 16);
+}
+
+__device__ __forceinline__ unsigned quantise_u8(float v) {
+    // np.uint8(np.around((v + 1) / 2 * 255)) -- create_cityscapes_image_change.py:33
+    const float q = __fmul_rn(__fmul_rn(__fadd_rn(v, 1.0f), 0.5f), 255.0f);
+    return static_cast<unsigned>(__float2int_rn(q)) & 255u;   // rint = round half to even
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(kImgThreads)
+pair_apply_kernel(const uint8_t* __restrict__ now, const uint8_t* __restrict__ front, long long npx, LogLut lut_in,
+                  float thr, float clip, const unsigned* __restrict__ ws, float* __restrict__ out_f32,
+                  uint8_t* __restrict__ out_u8) {
+    __shared__ float lut[256];
+    if (threadIdx.x < 256) lut[threadIdx.x] = lut_in.v[threadIdx.x];
+    __syncthreads();
+    const int img = blockIdx.y;
+    const uint8_t* a = now + static_cast<size_t>(img) * npx;
+    const uint8_t* b = front + static_cast<size_t>(img) * npx;
+    const TermRange rng = decode_range(ws + static_cast<size_t>(img) * 16);
+    float* of = out_f32 ? out_f32 + static_cast<size_t>(img) * npx : nullptr;
+    uint8_t* ou = out_u8 ? out_u8 + static_cast<size_t>(img) * npx : nullptr;
+    if (VEC) {
+        const long long n16 = npx / 16;
+        for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n16;
+             i += static_cast<long long>(gridDim.x) * blockDim.x) {
+            const uint4 va = __ldg(reinterpret_cast<const uint4*>(a) + i);
+            const uint4 vb = __ldg(reinterpret_cast<const uint4*>(b) + i);
+            const unsigned wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
+            unsigned packed[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float r[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float d = __fsub_rn(lut[(wa[q] >> (8 * j)) & 255u], lut[(wb[q] >> (8 * j)) & 255u]);
+                    float pos, neg;
+                    split_clamp(d, thr, clip, pos, neg);
+                    r[j] = normalize_term(pos, neg, rng);
+                }
+                if (of) stg_stream_f4(of + i * 16 + q * 4, make_float4(r[0], r[1], r[2], r[3]));
+                packed[q] = quantise_u8(r[0]) | (quantise_u8(r[1]) << 8) | (quantise_u8(r[2]) << 16) |
+                            (quantise_u8(r[3]) << 24);
+            }
+            if (ou) reinterpret_cast<uint4*>(ou)[i] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        }
+    } else {
+        for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < npx;
+             i += static_cast<long long>(gridDim.x) * blockDim.x) {
+            const float d = __fsub_rn(lut[__ldg(a + i)], lut[__ldg(b + i)]);
+            float pos, neg;
+            split_clamp(d, thr, clip, pos, neg);
+            const float r = normalize_term(pos, neg, rng);
+            if (of) of[i] = r;
+            if (ou) ou[i] = static_cast<uint8_t>(quantise_u8(r));
+        }
+    }
+}
+
+// ------------------------------------------------------------------ PIL 'L'
+__global__ void rgb_to_gray_kernel(const uint8_t* __restrict__ rgb, long long n, uint8_t* __restrict__ gray) {
+    // Pillow rgb2l: (19595 R + 38470 G + 7471 B + 0x8000) >> 16  (utils.py:126 convert('L'))
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    const bool vec = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(rgb) & 3) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(gray) & 3) == 0);
+    if (vec) {
+        for (long long k = i; k < n / 4; k += stride) {   // 4 pixels = 12 bytes in, 4 bytes out
+            const unsigned* src = reinterpret_cast<const unsigned*>(rgb) + k * 3;
+            const unsigned w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
+            const unsigned char bts[12] = {
+                (unsigned char)(w0), (unsigned char)(w0 >> 8), (unsigned char)(w0 >> 16), (unsigned char)(w0 >> 24),
+                (unsigned char)(w1), (unsigned char)(w1 >> 8), (unsigned char)(w1 >> 16), (unsigned char)(w1 >> 24),
+                (unsigned char)(w2), (unsigned char)(w2 >> 8), (unsigned char)(w2 >> 16), (unsigned char)(w2 >> 24)};
+            unsigned o = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const unsigned l = (19595u * bts[3 * j] + 38470u * bts[3 * j + 1] + 7471u * bts[3 * j + 2] + 32768u) >> 16;
+                o |= l << (8 * j);
+            }
+            reinterpret_cast<unsigned*>(gray)[k] = o;
+        }
+    } else {
+        for (long long k = i; k < n; k += stride) {
+            const unsigned r = rgb[3 * k], g = rgb[3 * k + 1], b = rgb[3 * k + 2];
+            gray[k] = static_cast<uint8_t>((19595u * r + 38470u * g + 7471u * b + 32768u) >> 16);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ launchers
+static int image_grid_x(long long work_items) {
+    // 148 SMs x 8 resident 256-thread CTAs; never more blocks than work
+    long long b = (work_items + kImgThreads - 1) / kImgThreads;
+    const long long cap = 148LL * 8;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return static_cast<int>(b);
+}
+
+int launch_rgb_to_gray(const uint8_t* rgb, int64_t n, uint8_t* gray, cudaStream_t s) {
+    if (n <= 0) return CMDA_OK;
+    rgb_to_gray_kernel<<<image_grid_x(n / 4 + 1), kImgThreads, 0, s>>>(rgb, n, gray);
+    CMDA_LAUNCH_CHECK();
+    return CMDA_OK;
+}
+
+int launch_isr(const uint8_t* gray, int S, int H, int W, int shift, int direction, const float* h_lut, float thr,
+               float clip, float* out, unsigned* ws, cudaStream_t s) {
+    LogLut lut;
+    for (int i = 0; i < 256; ++i) lut.v[i] = h_lut[i];
+    const TermList terms = terms_of(direction);
+    const long long npx = static_cast<long long>(H) * W;
+    CMDA_CUDA_TRY(cudaMemsetAsync(ws, 0, sizeof(unsigned) * 16 * S, s));
+    // images per launch are bounded by gridDim.y
+    for (int s0 = 0; s0 < S; s0 += 32768) {
+        const int sn = (S - s0) < 32768 ? (S - s0) : 32768;
+        const uint8_t* g = gray + static_cast<size_t>(s0) * npx;
+        float* o = out + static_cast<size_t>(s0) * npx;
+        unsigned* w = ws + static_cast<size_t>(s0) * 16;
+        // split the 148x8 resident CTAs across the images of the batch
+        int gx = image_grid_x(npx);
+        int per_img = (148 * 8 + sn - 1) / sn;
+        if (per_img < 1) per_img = 1;
+        if (gx > per_img) gx = per_img;
+        dim3 grid(gx, sn);
+        int gxa = image_grid_x((npx + kPxPerThread - 1) / kPxPerThread);
+        if (gxa > per_img) gxa = per_img;
+        dim3 grida(gxa, sn);
+        const bool vec = (npx % 4 == 0) && ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
+        if (terms.n == 4) {
+            isr_minmax_kernel<4><<<grid, kImgThreads, 0, s>>>(g, H, W, shift, terms, lut, thr, clip, w);
+            if (vec) isr_apply_kernel<4, true><<<grida, kImgThreads, 0, s>>>(g, H, W, shift, terms, lut, thr, clip, w, o);
+            else isr_apply_kernel<4, false><<<grida, kImgThreads, 0, s>>>(g, H, W, shift, terms, lut, thr, clip, w, o);
+        } else {
+            isr_minmax_kernel<2><<<grid, kImgThreads, 0, s>>>(g, H, W, shift, terms, lut, thr, clip, w);
+            if (vec) isr_apply_kernel<2, true><<<grida, kImgThreads, 0, s>>>(g, H, W, shift, terms, lut, thr, clip, w, o);
+            else isr_apply_kernel<2, false><<<grida, kImgThreads, 0, s>>>(g, H, W, shift, terms, lut, thr, clip, w, o);
+        }
+        CMDA_LAUNCH_CHECK();
+    }
+    return CMDA_OK;
+}
+
+int launch_pair(const uint8_t* now, const uint8_t* front, int S, int H, int W, const float* h_lut, float thr,
+                float clip, float* out_f32, uint8_t* out_u8, unsigned* ws, cudaStream_t s) {
+    LogLut lut;
+    for (int i = 0; i < 256; ++i) lut.v[i] = h_lut[i];
+    const long long npx = static_cast<long long>(H) * W;
+    CMDA_CUDA_TRY(cudaMemsetAsync(ws, 0, sizeof(unsigned) * 16 * S, s));
+    for (int s0 = 0; s0 < S; s0 += 32768) {
+        const int sn = (S - s0) < 32768 ? (S - s0) : 32768;
+        const size_t off = static_cast<size_t>(s0) * npx;
+        int per_img = (148 * 8 + sn - 1) / sn;
+        const bool vec = (npx % 16 == 0) && ((reinterpret_cast<uintptr_t>(now + off) & 15) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(front + off) & 15) == 0) &&
+                         (!out_f32 || (reinterpret_cast<uintptr_t>(out_f32 + off) & 15) == 0) &&
+                         (!out_u8 || (reinterpret_cast<uintptr_t>(out_u8 + off) & 15) == 0);
+        int gx = image_grid_x(vec ? npx / 16 : npx);
+        if (gx > per_img) gx = per_img;
+        dim3 grid(gx, sn);
+        unsigned* w = ws + static_cast<size_t>(s0) * 16;
+        pair_minmax_kernel<<<grid, kImgThreads, 0, s>>>(now + off, front + off, npx, vec, lut, thr, clip, w);
+        if (vec)
+            pair_apply_kernel<true><<<grid, kImgThreads, 0, s>>>(now + off, front + off, npx, lut, thr, clip, w,
+                                                                 out_f32 ? out_f32 + off : nullptr,
+                                                                 out_u8 ? out_u8 + off : nullptr);
+        else
+            pair_apply_kernel<false><<<grid, kImgThreads, 0, s>>>(now + off, front + off, npx, lut, thr, clip, w,
+                                                                  out_f32 ? out_f32 + off : nullptr,
+                                                                  out_u8 ? out_u8 + off : nullptr);
+        CMDA_LAUNCH_CHECK();
+    }
+    return CMDA_OK;
+}
+
+}  // namespace cmda

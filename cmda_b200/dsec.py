@@ -1,0 +1,103 @@
+"""The events branch of ``DSECDataset.__getitem__`` over the CUDA path.
+
+Mirrors reference mmseg/datasets/dsec.py:286-320 and 341-366 with the same attribute and
+argument names.  File handling (events.h5 through h5py/hdf5plugin, rectify_map.h5,
+images_to_events_index.txt) is I/O and stays with the caller: a ``DSECEvents`` is built
+from arrays that are already in memory and keeps them resident on the GPU, instead of
+re-opening three files per sample as the reference does (dsec.py:287-293).
+
+CUDA cannot run in forked DataLoader workers, so this object is meant to be used from the
+process that owns the GPU; the returned dict entry has the
+reference's key, shape, dtype and value range.
+"""
+from __future__ import annotations
+
+import random
+
+import torch
+import torch.nn.functional as F
+
+from .slicer import window_bounds
+from .voxel import EventStore, events_vg_batch
+
+__all__ = ["DSECEvents"]
+
+
+class DSECEvents:
+    def __init__(self, t, x, y, p, rectify_map, images_to_events_index, events_num=-1, events_bins=5,
+                 events_clip_range=None, crop_size=(400, 400), after_crop_resize_size=(512, 512),
+                 image_change_range=1, outputs={'events_vg', 'image'}, output_num=1, events_bins_5_avg_1=False,
+                 enforce_3_channels=True, device=None, mode="auto"):
+        self.events_num = events_num
+        self.events_bins = events_bins
+        self.events_bins_5_avg_1 = events_bins_5_avg_1
+        if self.events_bins_5_avg_1:                           # dsec.py:145-148
+            assert events_bins == 1
+            self.events_bins = 5
+        self.events_clip_range = events_clip_range
+        self.outputs = outputs
+        # (H, W) --> (W, H) unless labels are requested -- dsec.py:150-152
+        self.crop_size = (crop_size[1], crop_size[0]) if 'label' not in outputs else crop_size
+        self.after_crop_resize_size = (after_crop_resize_size[1], after_crop_resize_size[0]) \
+            if 'label' not in outputs else after_crop_resize_size
+        self.image_change_range = image_change_range
+        assert self.image_change_range in {1, 2}               # dsec.py:154
+        self.output_num = output_num
+        self.events_height = 480                               # dsec.py:160
+        self.events_width = 640                                # dsec.py:161
+        self.rectify_events = True                             # dsec.py:167
+        self.enforce_3_channels = enforce_3_channels
+        self.images_to_events_index = [int(v) for v in images_to_events_index]
+        self.mode = mode
+        self.store = EventStore(t, x, y, p, rectify_map if self.rectify_events else None,
+                                height=self.events_height, width=self.events_width, device=device)
+
+    # ---- dsec.py:341-366 -------------------------------------------------------------
+    def _clip_for(self, finish, start):
+        if self.events_clip_range is not None:                 # dsec.py:359-360
+            return random.uniform(self.events_clip_range[0], self.events_clip_range[1])
+        return (finish - start) / 500000 * 1.5                 # dsec.py:362
+
+    def get_events_vg(self, events_finish_index, events_start_index):
+        """``[events_bins, 480, 640]`` float32 in [-1, 1] on the GPU."""
+        clip = self._clip_for(events_finish_index, events_start_index)
+        return events_vg_batch(self.store, [events_start_index], [events_finish_index], self.events_bins, [clip],
+                               mode=self.mode)[0]
+
+    # ---- dsec.py:286-320 -------------------------------------------------------------
+    def events_vg_for_image(self, now_image_index, crop_xy=None, flip_flag=False):
+        """The ``'events_vg'`` entry of ``__getitem__`` for image ``now_image_index``.
+        ``crop_xy``/``flip_flag`` are the augmentation draws of dsec.py:206-210 (made by the
+        caller so that image, ISR and events share them).  Returns ``None`` where the
+        reference does (start > finish, dsec.py:301-302)."""
+        bounds = []
+        for i in range(self.output_num):                       # dsec.py:295-302
+            b = window_bounds(self.images_to_events_index, now_image_index, self.image_change_range,
+                              self.events_num, i)
+            if b is None:
+                return None
+            bounds.append(b)
+        clips = [self._clip_for(f, s) for s, f in bounds]
+        vg = events_vg_batch(self.store, [s for s, _ in bounds], [f for _, f in bounds], self.events_bins, clips,
+                             mode=self.mode)
+        events_vg = vg.flip(0)                                 # events_vg[output_num - 1 - i] = window i, :303
+        if self.events_bins_5_avg_1:
+            events_vg = torch.mean(events_vg, dim=1, keepdim=True)   # dsec.py:304-305
+        if self.output_num == 1:
+            events_vg = events_vg[0]                           # dsec.py:306-307
+        if 'label' not in self.outputs:                        # train-time augmentation, dsec.py:309-315
+            x, y = crop_xy if crop_xy is not None else (0, 0)
+            events_vg = events_vg[..., y: y + self.crop_size[1], x: x + self.crop_size[0]]
+            if flip_flag:
+                events_vg = events_vg.flip(-1)
+            hw = (self.after_crop_resize_size[1], self.after_crop_resize_size[0])
+            lead = events_vg.shape[:-2]
+            events_vg = F.interpolate(events_vg.reshape(1, -1, *events_vg.shape[-2:]), size=hw, mode='bilinear',
+                                      align_corners=False)[0].reshape(*lead, *hw)
+        else:                                                  # test mode, dsec.py:316-317
+            events_vg = events_vg[..., :440, :]
+        if self.enforce_3_channels:                            # dsec.py:318-319
+            reps = [1] * events_vg.ndim
+            reps[-3] = 3
+            events_vg = events_vg.repeat(*reps)
+        return events_vg

@@ -1,0 +1,171 @@
+"""Log-intensity-change pseudo-events: the reference's call signatures over K4 / K5.
+
+Mirrors ``get_ic`` / ``get_image_change_from_pil`` (reference mmseg/datasets/utils.py:87-152)
+and ``get_image_change`` (reference create_cityscapes_image_change.py:16-35).  The 256-entry
+log table is evaluated here by numpy with the reference's own expression, so the values the
+kernel subtracts are the values the reference subtracts.  Outputs live where the inputs
+live (PIL / numpy / CPU tensor -> CPU tensor, CUDA tensor -> CUDA tensor) unless
+``out_device`` says otherwise.
+"""
+from __future__ import annotations
+
+import functools
+
+import numpy as np
+import torch
+
+from . import _lib
+from .voxel import _cuda_device
+
+__all__ = ["get_ic", "get_image_change_from_pil", "get_image_change", "isr_batch", "image_change_batch",
+           "rgb_to_gray", "log_lut_val_range", "log_lut_log_add"]
+
+# module-level parameters of create_cityscapes_image_change.py:169-172
+image_change_range = 1
+log_add = 50
+threshold = 0.1
+clip_range = 0.8
+
+
+@functools.lru_cache(maxsize=64)
+def _lut_val_range(v0, v1) -> np.ndarray:
+    g = np.arange(256, dtype=np.float32)
+    with np.errstate(all="ignore"):
+        return np.ascontiguousarray(np.log(g / 255 * (v1 - v0) + v0), dtype=np.float32)    # utils.py:88-91
+
+
+def log_lut_val_range(val_range) -> np.ndarray:
+    return _lut_val_range(val_range[0], val_range[1])
+
+
+@functools.lru_cache(maxsize=64)
+def log_lut_log_add(add) -> np.ndarray:
+    g = np.arange(256, dtype=np.float32)
+    with np.errstate(all="ignore"):
+        return np.ascontiguousarray(np.log(g + add), dtype=np.float32)   # create_cityscapes_image_change.py:17-20
+
+
+def _to_u8_cuda(img, dev) -> torch.Tensor:
+    if isinstance(img, torch.Tensor):
+        assert img.dtype == torch.uint8, "uint8 image expected"
+        return img.to(dev, non_blocking=True).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(img, dtype=np.uint8)).to(dev, non_blocking=True)
+
+
+def _home(img) -> torch.device:
+    return img.device if isinstance(img, torch.Tensor) else torch.device("cpu")
+
+
+def rgb_to_gray(rgb, *, out_device=None) -> torch.Tensor:
+    """``PIL.Image.convert('L')`` of ``[..., 3]`` uint8 RGB (utils.py:126) on the device."""
+    home = _home(rgb)
+    dev = _cuda_device(home if home.type == "cuda" else None)
+    src = _to_u8_cuda(rgb, dev)
+    assert src.shape[-1] == 3
+    out = torch.empty(src.shape[:-1], dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().cmda_rgb_to_gray_u8(_lib.ptr(src), out.numel(), _lib.ptr(out), _lib.stream_ptr(dev)),
+                   "cmda_rgb_to_gray_u8")
+    return out.to(out_device if out_device is not None else home)
+
+
+def isr_batch(images, shift_pixel, val_range, _threshold, _clip_range, shift_direction="rightdown", *,
+              out=None, out_device=None) -> torch.Tensor:
+    """Shift-pair pseudo-events of ``[S, H, W]`` gray or ``[S, H, W, 3]`` RGB uint8 images
+    -> ``[S, 1, H, W]`` float32 (``get_image_change_from_pil`` batched)."""
+    home = _home(images)
+    dev = _cuda_device(home if home.type == "cuda" else None)
+    src = _to_u8_cuda(images, dev)
+    channels = 3 if (src.ndim == 4 and src.shape[-1] == 3) else 1
+    assert src.ndim == 3 + (channels == 3)
+    S, H, W = int(src.shape[0]), int(src.shape[1]), int(src.shape[2])
+    if shift_direction not in _lib.DIRECTIONS:
+        raise AssertionError(shift_direction)                      # utils.py:142 / 147
+    lut = log_lut_val_range(tuple(val_range))
+    span = np.log(val_range[1]) - np.log(val_range[0])             # utils.py:93-94, float64
+    thr = np.float32(span * _threshold)                            # compared in float32
+    clip = np.float32(span * _clip_range)
+    L = _lib.lib()
+    if out is None:
+        out = torch.empty((S, 1, H, W), dtype=torch.float32, device=dev)
+    assert out.is_cuda and out.is_contiguous() and out.numel() == S * H * W
+    with torch.cuda.device(dev):
+        ws = _lib.workspace(dev, L.cmda_image_workspace_bytes(S, H, W, channels))
+        _lib.check(L.cmda_isr_shift_u8(_lib.ptr(src), channels, S, H, W, int(shift_pixel),
+                                       _lib.DIRECTIONS[shift_direction], _lib.host_ptr(lut), float(thr), float(clip),
+                                       _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)),
+                   "cmda_isr_shift_u8")
+    return out.to(out_device if out_device is not None else home)
+
+
+def get_image_change_from_pil(pil_image, width, height, data_type=None, shift_pixel=4, val_range=None,
+                              _threshold=None, _clip_range=None, auto_threshold=None, shift_direction='rightdown',
+                              *, out_device=None):
+    """Drop-in for ``get_image_change_from_pil`` (reference utils.py:108-152) -> ``[1, H, W]``.
+
+    ``pil_image`` may be a PIL image ('RGB' or 'L'), a uint8 array or a uint8 tensor
+    (``[H, W, 3]`` or ``[H, W]``).  ``width`` / ``height`` / ``data_type`` are accepted for
+    signature compatibility; like the reference's slicing, the image's own size rules.
+    """
+    if auto_threshold is not None:
+        raise ValueError('auto_threshold function not implement！')   # utils.py:124-125
+    if hasattr(pil_image, "convert"):
+        if pil_image.mode not in ("RGB", "L"):
+            pil_image = pil_image.convert("RGB")
+        pil_image = np.asarray(pil_image)
+    img = pil_image[None]
+    return isr_batch(img, shift_pixel, val_range, _threshold, _clip_range, shift_direction, out_device=out_device)[0]
+
+
+def get_ic(image_front, image_now, val_range, threshold, clip_range, *, out_device=None):
+    """Drop-in for ``get_ic`` (reference utils.py:87-105) on two uint8 gray images ->
+    ``[1, H, W]`` float32.  Same arithmetic as K4 with the val_range table."""
+    home = _home(image_now)
+    dev = _cuda_device(home if home.type == "cuda" else None)
+    now, front = _to_u8_cuda(image_now, dev), _to_u8_cuda(image_front, dev)
+    span = np.log(val_range[1]) - np.log(val_range[0])
+    out, _ = _pair(now[None], front[None], log_lut_val_range(tuple(val_range)), np.float32(span * threshold),
+                   np.float32(span * clip_range), dev, want_f32=True, want_u8=False)
+    return out[0][None].to(out_device if out_device is not None else home)
+
+
+def _pair(now, front, lut, thr, clip, dev, want_f32, want_u8):
+    assert now.shape == front.shape and now.ndim == 3
+    S, H, W = (int(v) for v in now.shape)
+    L = _lib.lib()
+    out_f = torch.empty((S, H, W), dtype=torch.float32, device=dev) if want_f32 else None
+    out_u = torch.empty((S, H, W), dtype=torch.uint8, device=dev) if want_u8 else None
+    with torch.cuda.device(dev):
+        ws = _lib.workspace(dev, L.cmda_image_workspace_bytes(S, H, W, 1))
+        _lib.check(L.cmda_logdiff_pair_u8(_lib.ptr(now), _lib.ptr(front), S, H, W, _lib.host_ptr(lut), float(thr),
+                                          float(clip), _lib.ptr(out_f), _lib.ptr(out_u), _lib.ptr(ws), ws.numel(),
+                                          _lib.stream_ptr(dev)), "cmda_logdiff_pair_u8")
+    return out_f, out_u
+
+
+def image_change_batch(now, front, *, log_add=None, threshold=None, clip_range=None, want_f32=False, want_u8=True,
+                       out_device=None):
+    """Frame-pair pseudo-events of ``[S, H, W]`` uint8 gray stacks (``get_image_change``
+    batched).  Returns the uint8 'L' payload and/or the float32 image in [-1, 1]."""
+    g = globals()
+    la = g["log_add"] if log_add is None else log_add
+    th = g["threshold"] if threshold is None else threshold
+    cr = g["clip_range"] if clip_range is None else clip_range
+    home = _home(now)
+    dev = _cuda_device(home if home.type == "cuda" else None)
+    a, b = _to_u8_cuda(now, dev), _to_u8_cuda(front, dev)
+    out_f, out_u = _pair(a, b, log_lut_log_add(la), np.float32(th), np.float32(cr), dev, want_f32, want_u8)
+    tgt = out_device if out_device is not None else home
+    res = tuple(o.to(tgt) for o in (out_f, out_u) if o is not None)
+    return res[0] if len(res) == 1 else res
+
+
+def get_image_change(image_now, image_front):
+    """Drop-in for ``get_image_change`` (reference create_cityscapes_image_change.py:16-35):
+    two 'L' images -> PIL 'L' image, using this module's ``log_add`` / ``threshold`` /
+    ``clip_range`` globals exactly like the reference script uses its own."""
+    from PIL import Image
+    now = np.asarray(image_now, dtype=np.uint8)
+    front = np.asarray(image_front, dtype=np.uint8)
+    u8 = image_change_batch(now[None], front[None], want_u8=True)[0]
+    return Image.fromarray(u8.cpu().numpy(), mode='L')

@@ -1,0 +1,161 @@
+/* cmda_b200 -- C ABI of the B200-native event-representation path of XiaRho/CMDA.
+ *
+ * The reference is pure Python and has NO FFI: its boundary for this path is a set of
+ * Python call signatures.  This header is the operator ABI those
+ * signatures bind to in this build; each entry point cites the reference function it
+ * replaces.  INTEGRATION.md shows the ctypes stub a maintainer of the reference adds.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch / CUDA types in the signatures
+ *    (`stream` is a cudaStream_t passed as void*; NULL = legacy default stream);
+ *  - pointers named `d_*` are DEVICE pointers, `h_*` are HOST pointers read during the
+ *    call (small per-window tables, 256-entry LUTs); they may be freed on return;
+ *  - the caller owns every buffer including the workspace; the library allocates
+ *    nothing and keeps no global state; calls are asynchronous on `stream`, never
+ *    synchronise, and are re-entrant with one workspace per concurrent stream;
+ *  - every function returns CMDA_OK (0) or a negative CMDA_ERR_* code; nothing throws
+ *    or exits.  There is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef CMDA_B200_H
+#define CMDA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CMDA_B200_VERSION 100
+
+enum {
+    CMDA_OK = 0,
+    CMDA_ERR_BAD_ARG = -1,     /* NULL pointer, non-positive size, unknown mode ...        */
+    CMDA_ERR_CUDA = -2,        /* a CUDA runtime call or launch failed (see cmda_last_cuda_error) */
+    CMDA_ERR_WORKSPACE = -3,   /* workspace too small or misaligned (needs 256-byte alignment) */
+    CMDA_ERR_UNSUPPORTED = -4, /* shape outside what the kernels are built for              */
+    CMDA_ERR_NO_DEVICE = -5    /* no sm_100 device / driver                                  */
+};
+
+/* Accumulation modes of the voxel scatter (all deterministic, all bit-identical to
+ * each other: contributions are quantised to 2^-30 and summed as 64-bit integers,
+ * which is order independent). */
+enum {
+    CMDA_VOXEL_GLOBAL = 0, /* one 64-bit integer RED per corner into an L2-resident grid   */
+    CMDA_VOXEL_TILED = 1,  /* chunk-local band partition + shared-memory band accumulation */
+    CMDA_VOXEL_AUTO = 2    /* TILED for large windows, GLOBAL for small ones                */
+};
+
+/* Directions of the shift-pair generator (reference mmseg/datasets/utils.py:128-151). */
+enum {
+    CMDA_DIR_RIGHTDOWN = 0,
+    CMDA_DIR_RIGHTUP = 1,
+    CMDA_DIR_LEFTDOWN = 2,
+    CMDA_DIR_LEFTUP = 3,
+    CMDA_DIR_ALL = 4
+};
+
+const char* cmda_strerror(int code);
+int cmda_version(void);
+/* cudaError_t of the last failing CUDA call made by this thread inside the library. */
+int cmda_last_cuda_error(void);
+
+/* ------------------------------------------------------------------------------------
+ * K1  window slicer.
+ * Replaces: create_images_to_events_index, /root/reference/create_dsec_dataset_txt.py:19-42
+ * (np.searchsorted(..., 'right') inside the ms_to_idx bracket).
+ * out[i] = number of elements of the ascending array d_t[0..n) that are <= d_q[i]. */
+int cmda_searchsorted_right_u32(const uint32_t* d_t, int64_t n, const int64_t* d_q, int nq,
+                                int64_t* d_out, void* stream);
+
+/* The whole per-image computation of create_dsec_dataset_txt.py:19-42 for n_ts image
+ * timestamps: d_index[i] = index of the last event with t <= ts - t_offset, or -1 when
+ * ts - t_offset <= 0 or > t[n-1]; d_status[i] = 1 when the reference would raise
+ * ValueError('range error!') (line 37-39), else 0. */
+int cmda_images_to_events_index(const uint32_t* d_t, int64_t n, const int64_t* d_ms_to_idx, int64_t n_ms,
+                                int64_t t_offset, const int64_t* d_timestamps, int n_ts,
+                                int64_t* d_index, int32_t* d_status, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * K2+K3  event windows -> voxel grids.
+ * Replaces: DSECDataset.get_events_vg, /root/reference/mmseg/datasets/dsec.py:341-366
+ * (window-relative time, rectify_map[y, x] gather, events_to_voxel_grid dsec.py:26-58,
+ * events_norm dsec.py:80-121), batched over S independent windows of one SoA store.
+ *
+ *  d_t/d_x/d_y/d_p   SoA event store in DSEC dtypes (16-byte aligned for the fast path)
+ *  h_win_start/end   [S] window bounds as event indices, end EXCLUSIVE (= finish + 1)
+ *  d_rectify_map     [n_maps, H, W, 2] float32 (channel 0 = x, 1 = y) or NULL (no remap)
+ *  h_map_id          [S] map index per window, or NULL (all windows use map 0)
+ *  h_clip            [S] clip_range per window (dsec.py:359-362); ignored if !normalize
+ *  normalize         0: d_out receives the raw grid (events_to_voxel_grid output)
+ *                    1: d_out receives events_norm(raw, clip, final_range, enforce)
+ *  d_out             [S, B, H, W] float32
+ *  d_raw_out         optional [S, B, H, W] raw grid when normalize=1 (may be NULL)
+ *  d_bin_counts      optional [S, B] int64: events per temporal bin t0 (may be NULL)
+ *  empty windows (end <= start) and single-timestamp windows (NaN time)
+ *  produce an all-zero raw grid, exactly like the reference. */
+size_t cmda_events_vg_workspace_bytes(int64_t total_events, int S, int H, int W, int B, int mode);
+
+int cmda_events_vg_batch(const uint32_t* d_t, const uint16_t* d_x, const uint16_t* d_y, const uint8_t* d_p,
+                         const int64_t* h_win_start, const int64_t* h_win_end, int S,
+                         const float* d_rectify_map, const int32_t* h_map_id, int H, int W, int B,
+                         const float* h_clip, float final_range, int enforce_no_events_zero, int normalize,
+                         float* d_out, float* d_raw_out, int64_t* d_bin_counts,
+                         void* d_workspace, size_t workspace_bytes, int mode, void* stream);
+
+/* Replaces: events_to_voxel_grid(time, x, y, pol, width, height, num_bins),
+ * /root/reference/mmseg/datasets/dsec.py:26-58 (normalize_flag=False), on float32 SoA
+ * inputs that are already rectified.  d_grid is [B, H, W] float32. */
+int cmda_voxel_grid_f32(const float* d_time, const float* d_x, const float* d_y, const float* d_pol, int64_t n,
+                        int W, int H, int B, float* d_grid, int64_t* d_bin_counts,
+                        void* d_workspace, size_t workspace_bytes, int mode, void* stream);
+
+/* Replaces: events_norm(events, clip_range, final_range, enforce_no_events_zero),
+ * /root/reference/mmseg/datasets/dsec.py:80-121 (numeric clip_range), for S independent
+ * grids of `voxels` elements each; in place on d_grid. */
+size_t cmda_events_norm_workspace_bytes(int S);
+int cmda_events_norm_batch(float* d_grid, int S, int64_t voxels, const float* h_clip, float final_range,
+                           int enforce_no_events_zero, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Integer side outputs for parity checks (bit-exact against dsec.py:41-43, 347-355):
+ * per event of ONE window [start, end): rectified float coordinates, t_norm, and the
+ * truncated integer corner origin (INT32_MIN where the reference's .int() is
+ * 'integer indefinite').  Any output pointer may be NULL. */
+int cmda_remap_events(const uint32_t* d_t, const uint16_t* d_x, const uint16_t* d_y, const uint8_t* d_p,
+                      int64_t start, int64_t end, const float* d_rectify_map, int H, int W, int B,
+                      float* d_xr, float* d_yr, float* d_tn, int32_t* d_x0, int32_t* d_y0, int32_t* d_t0,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * K4  frame-pair pseudo-events.
+ * Replaces: get_image_change(image_now, image_front),
+ * /root/reference/create_cityscapes_image_change.py:16-35.
+ *  d_now/d_front  [S, H, W] uint8 gray
+ *  h_lut          256 floats = np.log(arange(256, float32) + log_add), computed by the
+ *                 caller with numpy exactly as the reference evaluates it
+ *  thr, clip      float32(threshold), float32(clip_range)
+ *  d_out_f32      optional [S, H, W] float32 in [-1, 1] (line 31)
+ *  d_out_u8       optional [S, H, W] uint8 = uint8(around((d+1)/2*255)) (line 33) */
+size_t cmda_image_workspace_bytes(int S, int H, int W, int channels);
+int cmda_logdiff_pair_u8(const uint8_t* d_now, const uint8_t* d_front, int S, int H, int W, const float* h_lut,
+                         float thr, float clip, float* d_out_f32, uint8_t* d_out_u8,
+                         void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* K5  shift-pair pseudo-events (ISR).
+ * Replaces: get_image_change_from_pil + get_ic, /root/reference/mmseg/datasets/utils.py:87-152.
+ *  d_img      [S, H, W] gray (channels=1) or [S, H, W, 3] RGB (channels=3; converted with
+ *             PIL's 'L' formula (19595 R + 38470 G + 7471 B + 32768) >> 16, utils.py:126)
+ *  h_lut      256 floats = np.log(arange(256, float32)/255*(v1-v0)+v0) (utils.py:88-91)
+ *  thr, clip  float32((ln v1 - ln v0)*threshold), float32((ln v1 - ln v0)*clip_range)
+ *  d_out      [S, H, W] float32 */
+int cmda_isr_shift_u8(const uint8_t* d_img, int channels, int S, int H, int W, int shift_pixel, int direction,
+                      const float* h_lut, float thr, float clip, float* d_out,
+                      void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* PIL 'L' conversion alone (parity of the integer stage). d_rgb [n,3] -> d_gray [n]. */
+int cmda_rgb_to_gray_u8(const uint8_t* d_rgb, int64_t n_pixels, uint8_t* d_gray, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMDA_B200_H */

@@ -105,7 +105,7 @@ def events_to_voxel_grid(time, x, y, pol, width, height, num_bins, return_aux=Fa
     return grid
 
 
-def voxel_grid_f64(time, x, y, pol, width, height, num_bins):
+def voxel_grid_f64(time, x, y, pol, width, height, num_bins, return_aux=False):
     """Independent float64 'truth' of the same scatter: the float32 per-corner
     weights of the reference (bit-exact per contribution) summed exactly in
     float64.  Used to show which of two float32 summation orders is closer."""
@@ -115,6 +115,8 @@ def voxel_grid_f64(time, x, y, pol, width, height, num_bins):
     pol = np.ascontiguousarray(pol, dtype=F32)
     C, H, W = int(num_bins), int(height), int(width)
     grid = np.zeros(C * H * W, dtype=np.float64)
+    abs_w = np.zeros(C * H * W, dtype=np.float64)
+    n_contrib = np.zeros(C * H * W, dtype=np.int64)
     t_norm = t_norm_of(time, C)
     x0, y0, t0 = trunc_to_int(x), trunc_to_int(y), trunc_to_int(t_norm)
     value = F32(2) * pol - F32(1)
@@ -127,6 +129,11 @@ def voxel_grid_f64(time, x, y, pol, width, height, num_bins):
                          * (F32(1) - np.abs(ylim.astype(F32) - y))) * (F32(1) - np.abs(tlim.astype(F32) - t_norm))
                     idx = (H * W * tlim + W * ylim + xlim)[mask]
                     grid += np.bincount(idx, weights=w[mask].astype(np.float64), minlength=C * H * W)
+                    if return_aux:
+                        abs_w += np.bincount(idx, weights=np.abs(w[mask]).astype(np.float64), minlength=C * H * W)
+                        n_contrib += np.bincount(idx, minlength=C * H * W)
+    if return_aux:
+        return grid.reshape(C, H, W), abs_w.reshape(C, H, W), n_contrib.reshape(C, H, W)
     return grid.reshape(C, H, W)
 
 

@@ -1,0 +1,363 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (via cmda_b200's ctypes
+shims), against the golden fixtures (reference outputs) and the CPU oracle.
+
+Tolerances (north_star): integer / byte / index outputs and the whole pseudo-event path
+are BIT-EXACT.  Raw voxel sums: |gpu - ref| <= 1e-5 * max(|ref|, sum|w|) + n * 2^-31 per
+voxel (1e-5 relative to the magnitude of the summands -- the reference's own float32 sum
+is only that close to the exact sum -- plus the 2^-31 quantisation of each of the n
+contributions).  Normalised grids live in [-1, 1]: <= 1e-5 absolute.
+"""
+import numpy as np
+import pytest
+import torch
+
+import golden_io
+from oracle import c_oracle as C
+from oracle import cmda_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+VOXEL = golden_io.load("voxel")
+NORM = golden_io.load("norm")
+VG = golden_io.load("events_vg")
+ISR = golden_io.load("isr")
+IC = golden_io.load("image_change")
+INDEX = golden_io.load("index")
+
+MODES = ["global", "tiled"]
+
+
+@pytest.fixture(scope="module")
+def cm():
+    import cmda_b200
+    cmda_b200.lib()   # raises when the CUDA extension is missing: no fallback
+    return cmda_b200
+
+
+def bits(a):
+    if isinstance(a, torch.Tensor):
+        a = a.detach().cpu().numpy()
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def assert_raw_close(gpu, ref, abs_w, n_contrib):
+    gpu = gpu.detach().cpu().numpy() if isinstance(gpu, torch.Tensor) else gpu
+    tol = 1e-5 * np.maximum(np.abs(ref), abs_w) + n_contrib * 2.0 ** -31
+    err = np.abs(gpu.astype(np.float64) - ref.astype(np.float64))
+    bad = err > tol
+    assert not bad.any(), f"{bad.sum()} voxels out of tolerance, worst excess {np.max(err - tol):.3e}"
+    # a voxel no event touches must be exactly zero
+    assert np.all(gpu[n_contrib == 0] == 0.0)
+
+
+# ------------------------------------------------------------------ a4: events_to_voxel_grid
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("name", sorted(VOXEL))
+def test_voxel_grid_golden(cm, name, mode):
+    c = VOXEL[name]
+    W, H, B = int(c["width"]), int(c["height"]), int(c["bins"])
+    dev = torch.device("cuda:0")
+    args = [torch.from_numpy(c[k]).to(dev) for k in ("time", "x", "y", "pol")]
+    try:
+        got, counts = cm.events_to_voxel_grid(*args, W, H, B, mode=mode, return_bin_counts=True)
+    except cm.CmdaError as e:
+        if mode == "tiled" and "unsupported" in str(e):
+            pytest.skip("tiled mode not built for this shape")
+        raise
+    assert got.is_cuda and got.shape == (B, H, W) and got.dtype == torch.float32
+    _, aux = O.events_to_voxel_grid(c["time"], c["x"], c["y"], c["pol"], W, H, B, return_aux=True)
+    assert_raw_close(got, c["grid"], aux["abs_weight_sum"], aux["n_contrib"])
+    assert np.array_equal(counts.cpu().numpy(), aux["bin_counts"]), "per-bin event counts are bit-exact"
+    again = cm.events_to_voxel_grid(*args, W, H, B, mode=mode)
+    assert np.array_equal(bits(got), bits(again)), "run-to-run bit reproducibility"
+
+
+def test_voxel_grid_modes_identical(cm):
+    """GLOBAL and TILED quantise identically and sum exactly -> bit-identical grids."""
+    c = VOXEL["voxel_b5"]
+    dev = torch.device("cuda:0")
+    args = [torch.from_numpy(c[k]).to(dev) for k in ("time", "x", "y", "pol")]
+    a = cm.events_to_voxel_grid(*args, int(c["width"]), int(c["height"]), int(c["bins"]), mode="global")
+    try:
+        b = cm.events_to_voxel_grid(*args, int(c["width"]), int(c["height"]), int(c["bins"]), mode="tiled")
+    except cm.CmdaError:
+        pytest.skip("tiled mode not built for this shape")
+    assert np.array_equal(bits(a), bits(b))
+
+
+def test_voxel_grid_host_inputs_roundtrip(cm):
+    """CPU tensors in -> CPU tensor out (the reference's contract), same values."""
+    c = VOXEL["voxel_b3"]
+    args = [torch.from_numpy(c[k]) for k in ("time", "x", "y", "pol")]
+    got = cm.events_to_voxel_grid(*args, int(c["width"]), int(c["height"]), int(c["bins"]))
+    assert got.device.type == "cpu"
+    dev_args = [a.cuda() for a in args]
+    ref = cm.events_to_voxel_grid(*dev_args, int(c["width"]), int(c["height"]), int(c["bins"]))
+    assert np.array_equal(bits(got), bits(ref))
+
+
+def test_voxel_grid_order_independent(cm):
+    """Shuffling the events between the first and the last one (which define t_norm) must
+    give the bit-identical grid: accumulation is an exact integer sum."""
+    c = VOXEL["voxel_b5"]
+    n = c["time"].shape[0]
+    rng = np.random.default_rng(3)
+    perm = np.concatenate([[0], 1 + rng.permutation(n - 2), [n - 1]])
+    dev = torch.device("cuda:0")
+    W, H, B = int(c["width"]), int(c["height"]), int(c["bins"])
+    a = cm.events_to_voxel_grid(*[torch.from_numpy(c[k]).to(dev) for k in ("time", "x", "y", "pol")], W, H, B)
+    b = cm.events_to_voxel_grid(*[torch.from_numpy(c[k][perm]).to(dev) for k in ("time", "x", "y", "pol")], W, H, B)
+    assert np.array_equal(bits(a), bits(b))
+
+
+def test_voxel_grid_polarity_flip_negates(cm):
+    c = VOXEL["voxel_b5"]
+    dev = torch.device("cuda:0")
+    W, H, B = int(c["width"]), int(c["height"]), int(c["bins"])
+    t, x, y, p = [torch.from_numpy(c[k]).to(dev) for k in ("time", "x", "y", "pol")]
+    a = cm.events_to_voxel_grid(t, x, y, p, W, H, B)
+    b = cm.events_to_voxel_grid(t, x, y, 1 - p, W, H, B)
+    assert torch.equal(a, -b)
+
+
+def test_voxel_grid_empty_raises(cm):
+    e = torch.zeros(0, device="cuda")
+    with pytest.raises(IndexError):
+        cm.events_to_voxel_grid(e, e, e, e, 8, 8, 2)
+    with pytest.raises(AssertionError):
+        cm.events_to_voxel_grid(torch.zeros(3, device="cuda"), torch.zeros(2, device="cuda"),
+                                torch.zeros(3, device="cuda"), torch.zeros(3, device="cuda"), 8, 8, 2)
+
+
+# ------------------------------------------------------------------ a5: events_norm
+@pytest.mark.parametrize("name", sorted(k for k in NORM if k.startswith("norm_")))
+def test_events_norm_golden(cm, name):
+    c = NORM[name]
+    events = NORM["normgrid_" + str(c["grid"])]["events"]
+    src = torch.from_numpy(events).cuda()
+    keep = src.clone()
+    got = cm.events_norm(src, clip_range=float(c["clip_range"]), final_range=float(c["final_range"]),
+                         enforce_no_events_zero=bool(c["enforce"]))
+    assert torch.equal(src, keep), "input must not be mutated"
+    assert got.shape == src.shape and got.is_cuda
+    np.testing.assert_allclose(got.cpu().numpy(), c["result"], rtol=0, atol=1e-5, equal_nan=True)
+
+
+def test_events_norm_auto_not_built(cm):
+    with pytest.raises(NotImplementedError):
+        cm.events_norm(torch.zeros(1, 4, 4, device="cuda"), clip_range="auto")
+
+
+# ------------------------------------------------------------------ a2/a3: get_events_vg
+def _store(cm, c):
+    rmap = golden_io.rectify_map_of(c)
+    return cm.EventStore(c["t"], c["x"], c["y"], c["p"], rmap, height=int(c["height"]), width=int(c["width"]),
+                         device="cuda:0"), rmap
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("name", sorted(VG))
+def test_events_vg_golden(cm, name, mode):
+    c = VG[name]
+    store, rmap = _store(cm, c)
+    W, H, B = int(c["width"]), int(c["height"]), int(c["bins"])
+    start, finish = int(c["start"]), int(c["finish"])
+    clip = [float(c["clip"][0])] if c["clip"].size else None
+    try:
+        out, raw, counts = cm.events_vg_batch(store, [start], [finish], B, clip, mode=mode, return_raw=True,
+                                              return_bin_counts=True)
+    except cm.CmdaError as e:
+        if mode == "tiled" and "unsupported" in str(e):
+            pytest.skip("tiled mode not built for this shape")
+        raise
+    np.testing.assert_allclose(out[0].cpu().numpy(), c["result"], rtol=0, atol=1e-5)
+    # raw grid and integer outputs against the oracle on the same slice
+    sl = slice(start, finish + 1)
+    tf, xf, yf, pf = O.rectify_events(c["t"][sl], c["x"][sl], c["y"][sl], c["p"][sl], rmap)
+    ref_raw, aux = O.events_to_voxel_grid(tf, xf, yf, pf, W, H, B, return_aux=True)
+    assert_raw_close(raw[0], ref_raw, aux["abs_weight_sum"], aux["n_contrib"])
+    assert np.array_equal(counts[0].cpu().numpy(), aux["bin_counts"])
+    rm = cm.remap_events(store, start, finish, B)
+    assert np.array_equal(bits(rm["x"]), bits(xf)) and np.array_equal(bits(rm["y"]), bits(yf))
+    tn = O.t_norm_of(tf, B)
+    assert np.array_equal(np.isnan(rm["t_norm"].cpu().numpy()), np.isnan(tn))
+    ok = ~np.isnan(tn)
+    assert np.array_equal(bits(rm["t_norm"].cpu().numpy()[ok]), bits(tn[ok]))
+    for k in ("x0", "y0", "t0"):
+        assert np.array_equal(rm[k].cpu().numpy().astype(np.int64), aux[k]), f"{k} must be bit-exact"
+
+
+def test_events_vg_dsec_shim(cm):
+    """DSECEvents.get_events_vg / events_vg_for_image mirror dsec.py:286-320, 341-366."""
+    c = VG["vg_w64_b5"]
+    rmap = golden_io.rectify_map_of(c)
+    # the shim is fixed at 480x640 like the reference; embed the 48x64 fixture in a DSEC-size map
+    H, W = 480, 640
+    t, x, y, p = c["t"], c["x"], c["y"], c["p"]
+    big = np.full((H, W, 2), -5.0, np.float32)
+    big[:48, :64] = rmap
+    idx = [int(c["start"]), int(c["finish"])]
+    ds = cm.DSECEvents(t, x, y, p, big, idx, events_bins=5, outputs={'events_vg', 'warp_image', 'label'}, device="cuda:0")
+    vg = ds.get_events_vg(int(c["finish"]), int(c["start"]))
+    assert vg.shape == (5, 480, 640)
+    ref = O.get_events_vg(t, x, y, p, big, W, H, 5, int(c["finish"]), int(c["start"]))
+    np.testing.assert_allclose(vg.cpu().numpy(), ref, rtol=0, atol=1e-5)
+    item = ds.events_vg_for_image(1)
+    assert item.shape == (15, 440, 640)
+    np.testing.assert_allclose(item[:5].cpu().numpy(), ref[:, :440], rtol=0, atol=1e-5)
+    assert torch.equal(item[:5], item[5:10])
+    ds_train = cm.DSECEvents(t, x, y, p, big, idx, events_bins=5, outputs={'events_vg', 'warp_image'}, device="cuda:0")
+    item = ds_train.events_vg_for_image(1, crop_xy=(3, 7), flip_flag=True)
+    assert item.shape == (15, 512, 512)
+    import torch.nn.functional as F
+    exp = torch.from_numpy(ref)[:, 7:407, 3:403].flip(-1)
+    exp = F.interpolate(exp[None], size=(512, 512), mode='bilinear', align_corners=False)[0].repeat(3, 1, 1)
+    np.testing.assert_allclose(item.cpu().numpy(), exp.numpy(), rtol=0, atol=2e-5)
+    # start > finish -> None (dsec.py:301-302)
+    ds_bad = cm.DSECEvents(t, x, y, p, big, [idx[1], idx[0]], events_bins=5, device="cuda:0")
+    assert ds_bad.events_vg_for_image(1) is None
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("bins,n,skew", [(5, 300_000, 0.0), (1, 300_000, 0.0), (5, 200_000, 0.3)])
+def test_events_vg_batch_vs_c_oracle(cm, mode, bins, n, skew):
+    """Ragged batch of DSEC-sized windows (one empty, one single-event) against the C oracle."""
+    from cmda_b200 import synth
+    H, W = 480, 640
+    t, x, y, p = synth.make_events(n, H, W, seed=synth.seed_for(1, bins), skew=skew)
+    rmap = synth.make_rectify_map(H, W, seed=77)
+    store = cm.EventStore(t, x, y, p, rmap, height=H, width=W, device="cuda:0")
+    starts = [0, n // 3, 17, n - 1, 1000]
+    fins = [n - 1, 2 * n // 3, 40_000, n - 1, 999 + 1]
+    try:
+        out, raw = cm.events_vg_batch(store, starts, fins, bins, mode=mode, return_raw=True)
+    except cm.CmdaError as e:
+        if mode == "tiled" and "unsupported" in str(e):
+            pytest.skip("tiled mode not built for this shape")
+        raise
+    ref, ref_raw = C.get_events_vg_batch(t, x, y, p, starts, fins, rmap, W, H, bins, return_raw=True)
+    for s in range(len(starts)):
+        sl = slice(starts[s], fins[s] + 1)
+        tf, xf, yf, pf = O.rectify_events(t[sl], x[sl], y[sl], p[sl], rmap)
+        # the GPU grid is the float32 rounding of the exact sum of the 2^-30-quantised weights:
+        # against the float64 sum of the same float32 weights it may differ by the quantisation
+        # of each contribution plus one float32 rounding -- tighter than the reference itself
+        truth, abs_w, n_contrib = O.voxel_grid_f64(tf, xf, yf, pf, W, H, bins, return_aux=True)
+        err = np.abs(raw[s].cpu().numpy().astype(np.float64) - truth)
+        assert np.all(err <= n_contrib * 2.0 ** -31 + 1.2e-7 * np.abs(truth))
+        assert_raw_close(raw[s], ref_raw[s], abs_w, n_contrib)
+        np.testing.assert_allclose(out[s].cpu().numpy(), ref[s], rtol=0, atol=1e-5)
+
+
+def test_events_vg_bad_windows(cm):
+    from cmda_b200 import synth
+    t, x, y, p = synth.make_events(1000, 48, 64, seed=1)
+    store = cm.EventStore(t, x, y, p, None, height=48, width=64, device="cuda:0")
+    with pytest.raises(IndexError):
+        cm.events_vg_batch(store, [0], [1000], 2)
+    out = cm.events_vg_batch(store, [10], [9], 2, normalize=False)    # empty window -> zero raw grid
+    assert torch.count_nonzero(out) == 0
+
+
+# ------------------------------------------------------------------ a6-a8: pseudo-events
+def test_rgb_to_gray_bit_exact(cm):
+    c = ISR["isr_input"]
+    assert np.array_equal(cm.rgb_to_gray(c["rgb"]).numpy(), c["gray"])
+    rng = np.random.default_rng(5)
+    rgb = rng.integers(0, 256, size=(37, 53, 3), dtype=np.uint8)
+    assert np.array_equal(cm.rgb_to_gray(torch.from_numpy(rgb).cuda()).cpu().numpy(), O.pil_gray_L(rgb))
+
+
+@pytest.mark.parametrize("name", sorted(k for k in ISR if "lut" in ISR[k]))
+def test_isr_golden_bit_exact(cm, name):
+    c = ISR[name]
+    rgb = ISR["isr_input"]["rgb"]
+    vr = tuple(float(v) for v in c["val_range"])
+    from cmda_b200 import image_change as ic
+    assert np.array_equal(bits(ic.log_lut_val_range(vr)), bits(c["lut"])), "host LUT == the reference's np.log values"
+    from PIL import Image
+    got = cm.get_image_change_from_pil(Image.fromarray(rgb, mode="RGB"), width=rgb.shape[1], height=rgb.shape[0],
+                                       shift_pixel=int(c["shift_pixel"]), val_range=vr,
+                                       _threshold=float(c["threshold"]), _clip_range=float(c["clip_range"]),
+                                       shift_direction=str(c["direction"]))
+    assert got.device.type == "cpu" and got.shape == c["result"].shape
+    assert np.array_equal(bits(got), bits(c["result"]))
+    # gray input on the device takes the channels=1 path: same bits
+    g = torch.from_numpy(ISR["isr_input"]["gray"]).cuda()
+    got2 = cm.get_image_change_from_pil(g, width=rgb.shape[1], height=rgb.shape[0], shift_pixel=int(c["shift_pixel"]),
+                                        val_range=vr, _threshold=float(c["threshold"]),
+                                        _clip_range=float(c["clip_range"]), shift_direction=str(c["direction"]))
+    assert got2.is_cuda and np.array_equal(bits(got2), bits(c["result"]))
+
+
+def test_isr_flat_direct_and_errors(cm):
+    c = ISR["isr_flat"]
+    got = cm.get_image_change_from_pil(c["rgb"], 24, 16, val_range=(1, 100), _threshold=0.04, _clip_range=0.2,
+                                       shift_pixel=3)
+    assert np.array_equal(bits(got), bits(c["result"]))
+    c = ISR["get_ic_direct"]
+    got = cm.get_ic(c["front"], c["now"], val_range=(1, 100), threshold=0.04, clip_range=0.2)
+    assert np.array_equal(bits(got), bits(c["result"]))
+    with pytest.raises(ValueError):
+        cm.get_image_change_from_pil(c["now"], 56, 40, auto_threshold=("img", "image_gray"))
+    with pytest.raises(AssertionError):
+        cm.get_image_change_from_pil(c["now"], 56, 40, val_range=(1, 100), _threshold=0.04, _clip_range=0.2,
+                                     shift_direction="sideways")
+
+
+@pytest.mark.parametrize("name", sorted(IC))
+def test_image_change_pair_golden(cm, name):
+    c = IC[name]
+    from PIL import Image
+    img = cm.get_image_change(Image.fromarray(c["now"], mode="L"), Image.fromarray(c["front"], mode="L"))
+    assert img.mode == "L" and np.array_equal(np.array(img), c["result"])
+    f32, u8 = cm.image_change_batch(c["now"][None], c["front"][None], want_f32=True, want_u8=True)
+    ref = O.get_image_change(c["now"], c["front"], return_float=True)
+    assert np.array_equal(bits(f32[0]), bits(ref)) and np.array_equal(u8[0].numpy(), c["result"])
+
+
+@pytest.mark.parametrize("h,w", [(1024, 2048), (480, 640), (67, 131)])
+def test_pseudo_events_large_vs_c_oracle(cm, h, w):
+    """BASELINE C3 sizes (2048x1024) and odd sizes that leave the vector paths: bit-exact."""
+    from cmda_b200 import synth
+    S = 3
+    pairs = [synth.make_frame_pair(h, w, seed=synth.seed_for(3, s)) for s in range(S)]
+    now = np.stack([a for a, _ in pairs])
+    front = np.stack([b for _, b in pairs])
+    f32, u8 = cm.image_change_batch(torch.from_numpy(now).cuda(), torch.from_numpy(front).cuda(), want_f32=True,
+                                    want_u8=True)
+    rf, ru = C.image_change_batch(now, front)
+    assert np.array_equal(bits(f32), bits(rf)) and np.array_equal(u8.cpu().numpy(), ru)
+    for direction, parms in [("rightdown", dict(val_range=(1, 100), thr=0.04, clip=0.2, shift=3)),
+                             ("leftup", dict(val_range=(0.01, 1.01), thr=0.005, clip=0.1, shift=1)),
+                             ("all", dict(val_range=(1, 100), thr=0.01, clip=0.1, shift=3))]:
+        got = cm.isr_batch(torch.from_numpy(now).cuda(), parms["shift"], parms["val_range"], parms["thr"],
+                           parms["clip"], direction)
+        ref = C.isr_batch(now, parms["shift"], parms["val_range"], parms["thr"], parms["clip"], direction)
+        assert np.array_equal(bits(got[:, 0]), bits(ref)), direction
+
+
+# ------------------------------------------------------------------ a1: slicer
+def test_images_to_events_index_golden(cm):
+    c = INDEX["index_table"]
+    got = cm.images_to_events_index(c["t"], int(c["t_offset"]), c["ms_to_idx"], c["timestamps"], device="cuda:0")
+    assert got == [int(v) for v in c["result"]]
+
+
+def test_images_to_events_index_range_error(cm):
+    c = INDEX["index_table"]
+    bad = c["ms_to_idx"].copy()
+    bad[:] = bad[-1]      # brackets no longer contain the timestamps
+    ts = np.array([int(c["t_offset"]) + 500_000], np.int64)
+    with pytest.raises(ValueError):
+        cm.images_to_events_index(c["t"], int(c["t_offset"]), bad, ts, device="cuda:0")
+    with pytest.raises(ValueError):
+        O.images_to_events_index(c["t"], int(c["t_offset"]), bad, ts)
+
+
+def test_searchsorted_right(cm):
+    rng = np.random.default_rng(9)
+    t = np.sort(rng.integers(0, 1 << 31, size=100_000, dtype=np.int64)).astype(np.uint32)
+    q = np.concatenate([rng.integers(-5, 1 << 31, size=1000), t[::997].astype(np.int64), [0, int(t[-1]), 1 << 33]])
+    got = cm.searchsorted_right(torch.from_numpy(t).cuda(), q).cpu().numpy()
+    assert np.array_equal(got, np.searchsorted(t.astype(np.int64), q, "right"))
