@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path's headline benchmark (BASELINE.json: voxelized Mevents/s).
+
+    python bench.py --gpus N --steps K --warmup W            # this build (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path
+
+A "step" is one pass of the voxel path over one batch of synthetic windows per GPU:
+BASELINE config C2 -- 16 DSEC-shaped (640x480) 50 ms windows of 5 M Poisson events each,
+rectify_map remap + trilinear voxel grid (B bins) + events_norm.  Windows are independent,
+so N GPUs each take their own 16 windows (weak scaling, no collective on the data path).
+
+value   : whole-job Mevents/s with the events already resident in HBM (device timed)
+e2e     : the same metric through the host-buffer front door (pinned host SoA in, host grids
+          out, H2D and D2H inside the timed region)
+roofline: the dominant kernel's algorithmic bytes / its own device time vs the measured HBM peak
+cpu_baseline : the CPU oracle port (C restatement of the reference, exact reference order)
+          timed on a bounded sample on the host cores
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W = 480, 640
+WINDOWS_PER_GPU = 16
+EVENTS_PER_WINDOW = 5_000_000
+WINDOW_US = 50_000
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def algorithmic_bytes_per_window(n, bins):
+    """events read once in native dtypes + map read once + final grid written once."""
+    return 9 * n + 8 * H * W + 4 * bins * H * W
+
+
+def make_workload(n_windows, n_events, seed_base):
+    """Concatenated SoA store of n_windows independent Poisson windows + their inclusive bounds."""
+    from cmda_b200 import synth
+    ts, xs, ys, ps, starts, fins = [], [], [], [], [], []
+    pos = 0
+    for w in range(n_windows):
+        t, x, y, p = synth.make_events(n_events, H, W, window_us=WINDOW_US, t_base=10_000_000 + w * WINDOW_US,
+                                       seed=synth.seed_for(2, seed_base + w))
+        ts.append(t); xs.append(x); ys.append(y); ps.append(p)
+        starts.append(pos)
+        fins.append(pos + n_events - 1)
+        pos += n_events
+    rmap = synth.make_rectify_map(H, W, seed=synth.seed_for(2, 999))
+    return (np.concatenate(ts), np.concatenate(xs), np.concatenate(ys), np.concatenate(ps), rmap,
+            np.array(starts, np.int64), np.array(fins, np.int64))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [v.strip() for v in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel_key):
+    """dram__bytes_read+write per launch of the dominant kernel from the committed ncu capture."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.isfile(path):
+        try:
+            return json.load(open(path)).get(kernel_key)
+        except Exception:
+            return None
+    return None
+
+
+# ------------------------------------------------------------------------------------ CPU legs
+def cpu_oracle_rate(t, x, y, p, rmap, starts, fins, bins, n_windows, threads):
+    """Mevents/s of the oracle port on `n_windows` windows with `threads` OpenMP threads."""
+    from oracle import c_oracle
+    c_oracle.build()
+    s, f = starts[:n_windows], fins[:n_windows]
+    t0 = time.perf_counter()
+    c_oracle.get_events_vg_batch(t, x, y, p, s, f, rmap, W, H, bins, nthreads=threads)
+    dt = time.perf_counter() - t0
+    return float((f - s + 1).sum()) / dt / 1e6, dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path.  The reference is
+    pure Python (no sources to compile into oracle/_ref) and /root/reference does not travel to
+    the GPU box, so this arm times the oracle port: the C restatement that performs the
+    reference's arithmetic in the reference's order, one window per host thread."""
+    if rank != 0:
+        return
+    from oracle import c_oracle
+    c_oracle.build()
+    cores = max(1, min(os.cpu_count() or 1, c_oracle.max_threads()))
+    n_windows = max(1, min(WINDOWS_PER_GPU, cores))
+    n_events = args.events                 # bounded sample: one window per host thread, at most 16
+    t, x, y, p, rmap, starts, fins = make_workload(n_windows, n_events, seed_base=0)
+    for _ in range(min(args.warmup, 1)):
+        cpu_oracle_rate(t, x, y, p, rmap, starts, fins, args.bins, n_windows, cores)
+    rates, times = [], []
+    for _ in range(args.steps):
+        r, dt = cpu_oracle_rate(t, x, y, p, rmap, starts, fins, args.bins, n_windows, cores)
+        rates.append(r); times.append(dt)
+    total = float((fins - starts + 1).sum()) * args.steps
+    value = total / sum(times) / 1e6
+    sample = f"{n_windows} windows x {n_events} events per step ({args.steps} steps), one window per thread"
+    line = {
+        "impl": "reference", "metric": "voxelized_events_per_s", "value": value, "unit": "Mevents/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sum(times) / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, world),
+        "cpu_baseline": {"value": value, "unit": "Mevents/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Mevents/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": f"C2: {WINDOWS_PER_GPU} DSEC 640x480 50ms windows x {args.events} events per GPU, "
+                        f"rectify_map remap + voxel grid (B={args.bins}) + events_norm",
+            "windows_per_gpu": WINDOWS_PER_GPU, "events_per_window": args.events, "bins": args.bins,
+            "height": H, "width": W, "voxel_mode": args.mode, "parallelism": f"shard-by-window x{world}",
+            "l2": "inputs (720 MB/step) exceed L2 (126 MB); no flush needed"}
+
+
+# ------------------------------------------------------------------------------------ GPU leg
+def run_gpu(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+
+    import cmda_b200
+    from cmda_b200 import _lib
+    from cmda_b200.pipeline import HostEventsPipeline
+
+    L = cmda_b200.lib()     # raises if the CUDA extension is missing
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    t, x, y, p, rmap, starts, fins = make_workload(WINDOWS_PER_GPU, args.events, seed_base=rank * WINDOWS_PER_GPU)
+    store = cmda_b200.EventStore(t, x, y, p, rmap, height=H, width=W, device=dev)
+    out = torch.empty((WINDOWS_PER_GPU, args.bins, H, W), dtype=torch.float32, device=dev)
+    events_per_step = int((fins - starts + 1).sum())
+
+    def step():
+        cmda_b200.events_vg_batch(store, starts, fins, args.bins, mode=args.mode, out=out)
+
+    # ---- device-resident timing ------------------------------------------------------------
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    # per-step phase events (cmda_profiler_attach) for the per-kernel roofline
+    n_phase = 8
+    phase_events = [[L.cmda_event_create() for _ in range(n_phase)] for _ in range(args.steps)]
+    phase_arrays = [(ctypes.c_void_p * n_phase)(*pe) for pe in phase_events]
+    used = 0
+    barrier()
+    ev[0].record()
+    for k in range(args.steps):
+        L.cmda_profiler_attach(phase_arrays[k], n_phase)
+        step()
+        used = L.cmda_profiler_detach()
+    ev[1].record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = ev[0].elapsed_time(ev[1])
+    phase_ms = np.zeros(max(used - 1, 0))
+    for pe in phase_events:
+        for j in range(used - 1):
+            ms = ctypes.c_float()
+            L.cmda_event_elapsed_ms(pe[j], pe[j + 1], ctypes.byref(ms))
+            phase_ms[j] += ms.value / args.steps
+    for pe in phase_events:
+        for e in pe:
+            L.cmda_event_destroy(e)
+
+    # ---- end to end through the host-buffer front door ----------------------------------------
+    pipe = HostEventsPipeline(t, x, y, p, rmap, args.bins, H, W, device=dev, windows_per_group=4, mode=args.mode,
+                              max_window_events=args.events)
+    host_out = torch.empty((WINDOWS_PER_GPU, args.bins, H, W), dtype=torch.float32).pin_memory()
+    for _ in range(max(1, min(args.warmup, 2))):
+        pipe(starts, fins, out=host_out)
+    e2e_steps = max(1, min(args.steps, 5))
+    barrier()
+    t0 = time.perf_counter()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        pipe(starts, fins, out=host_out)
+    e1.record()
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0)) / e2e_steps
+    h2d, d2h = pipe.bytes_per_call(starts, fins)
+    # the two paths must agree bit for bit (same kernels, same inputs)
+    same = bool(torch.equal(host_out, out.cpu()))
+
+    # ---- max over ranks ----------------------------------------------------------------------
+    times = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(times[0]), float(times[1])
+
+    if rank == 0:
+        ms_per_step = ms_total / args.steps
+        value = world * events_per_step / (ms_per_step * 1e-3) / 1e6
+        e2e_value = world * events_per_step / (e2e_ms * 1e-3) / 1e6
+        peak, peak_src = measured_peaks()
+        resolved = L.cmda_events_vg_resolved_mode(events_per_step, WINDOWS_PER_GPU, H, W, args.bins,
+                                                  _lib.VOXEL_MODES[args.mode])
+        if resolved == _lib.VOXEL_GLOBAL:
+            names = ["memset(int64 grid)", "voxel_scatter_global_kernel", "convert_stats_kernel", "norm_apply_kernel"]
+            launches_per_step = 3
+        else:
+            names = ["voxel_partition_kernel", "voxel_band_accumulate_kernel", "norm_apply_kernel"]
+            launches_per_step = 3
+        phases = {names[j] if j < len(names) else f"phase{j}": float(phase_ms[j]) for j in range(len(phase_ms))}
+        kernel_phases = {k: v for k, v in phases.items() if not k.startswith("memset")}
+        dom = max(kernel_phases, key=kernel_phases.get) if kernel_phases else None
+        alg = WINDOWS_PER_GPU * algorithmic_bytes_per_window(args.events, args.bins)
+        roofline = None
+        if dom:
+            achieved = alg / (kernel_phases[dom] * 1e-3) / 1e9
+            roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": achieved / peak, "traffic": ncu_traffic(dom), "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": alg, "kernel_ms": kernel_phases[dom],
+                        "phase_ms": phases,
+                        "whole_step": {"achieved": alg / (ms_per_step * 1e-3) / 1e9,
+                                       "frac": alg / (ms_per_step * 1e-3) / 1e9 / peak}}
+        # CPU baseline on a bounded sample of the same workload (rank 0, N=1 only)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import c_oracle
+            c_oracle.build()
+            cores = max(1, min(os.cpu_count() or 1, c_oracle.max_threads()))
+            nw = max(1, min(WINDOWS_PER_GPU, cores))
+            rate, dt = cpu_oracle_rate(t, x, y, p, rmap, starts, fins, args.bins, nw, cores)
+            cpu = {"value": rate, "unit": "Mevents/s", "cores": min(cores, nw), "kind": "port",
+                   "sample": f"{nw} of the step's {WINDOWS_PER_GPU} windows x {args.events} events, one window "
+                             f"per thread, {dt:.1f} s"}
+        line = {
+            "metric": "voxelized_events_per_s", "value": value, "unit": "Mevents/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(workload_config(args, world), resolved_mode=["global", "tiled", "auto", "exact"][resolved]),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "Mevents/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms, "steps": e2e_steps, "matches_device_path": same},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cmda_b200", choices=["cmda_b200", "reference"])
+    ap.add_argument("--bins", type=int, default=5)
+    ap.add_argument("--events", type=int, default=EVENTS_PER_WINDOW)
+    ap.add_argument("--mode", default="auto", choices=["auto", "global", "tiled"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "cmda_b200" else args.warmup
+    rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        # plain `python bench.py --gpus N`: re-launch one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000), os.path.abspath(__file__)]
+        cmd += sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_gpu(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

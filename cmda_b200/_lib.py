@@ -18,7 +18,8 @@ LIB_PATH = os.path.join(_HERE, "libcmda_b200.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 OK = 0
-VOXEL_GLOBAL, VOXEL_TILED, VOXEL_AUTO = 0, 1, 2
+VOXEL_GLOBAL, VOXEL_TILED, VOXEL_AUTO, VOXEL_EXACT = 0, 1, 2, 3
+VOXEL_MODES = {"global": VOXEL_GLOBAL, "tiled": VOXEL_TILED, "auto": VOXEL_AUTO, "exact": VOXEL_EXACT}
 DIRECTIONS = {"rightdown": 0, "rightup": 1, "leftdown": 2, "leftup": 3, "all": 4}
 
 _vp = ctypes.c_void_p
@@ -32,9 +33,15 @@ SIGNATURES = {
     "cmda_strerror": (ctypes.c_char_p, [_int]),
     "cmda_version": (_int, []),
     "cmda_last_cuda_error": (_int, []),
+    "cmda_profiler_attach": (_int, [_vp, _int]),
+    "cmda_profiler_detach": (_int, []),
+    "cmda_event_create": (_vp, []),
+    "cmda_event_destroy": (_int, [_vp]),
+    "cmda_event_elapsed_ms": (_int, [_vp, _vp, _vp]),
     "cmda_searchsorted_right_u32": (_int, [_vp, _i64, _vp, _int, _vp, _vp]),
     "cmda_images_to_events_index": (_int, [_vp, _i64, _vp, _i64, _i64, _vp, _int, _vp, _vp, _vp]),
     "cmda_events_vg_workspace_bytes": (_sz, [_i64, _int, _int, _int, _int, _int]),
+    "cmda_events_vg_resolved_mode": (_int, [_i64, _int, _int, _int, _int, _int]),
     "cmda_events_vg_batch": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _vp, _vp, _int, _int, _int, _vp, _f32, _int,
                                     _int, _vp, _vp, _vp, _vp, _sz, _int, _vp]),
     "cmda_voxel_grid_f32": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _int, _int, _vp, _vp, _vp, _sz, _int, _vp]),

@@ -6,6 +6,7 @@
 namespace cmda {
 
 thread_local int g_last_cuda_error = 0;
+thread_local PhaseTimer g_phase_timer = {nullptr, 0, 0};
 
 // launchers defined in the kernel translation units
 int launch_scatter_global_raw(const uint32_t*, const uint16_t*, const uint16_t*, const uint8_t*, const WindowTable&, int,
@@ -64,6 +65,31 @@ const char* cmda_strerror(int code) {
 }
 
 int cmda_version(void) { return CMDA_B200_VERSION; }
+
+int cmda_profiler_attach(void* const* h_events, int n) {
+    if (!h_events || n <= 0) return CMDA_ERR_BAD_ARG;
+    g_phase_timer = {h_events, n, 0};
+    return CMDA_OK;
+}
+int cmda_profiler_detach(void) {
+    const int used = g_phase_timer.next;
+    g_phase_timer = {nullptr, 0, 0};
+    return used;
+}
+void* cmda_event_create(void) {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+    return e;
+}
+int cmda_event_destroy(void* e) {
+    if (e) CMDA_CUDA_TRY(cudaEventDestroy(static_cast<cudaEvent_t>(e)));
+    return CMDA_OK;
+}
+int cmda_event_elapsed_ms(void* a, void* b, float* h_ms) {
+    if (!a || !b || !h_ms) return CMDA_ERR_BAD_ARG;
+    CMDA_CUDA_TRY(cudaEventElapsedTime(h_ms, static_cast<cudaEvent_t>(a), static_cast<cudaEvent_t>(b)));
+    return CMDA_OK;
+}
 int cmda_last_cuda_error(void) { return g_last_cuda_error; }
 
 int cmda_searchsorted_right_u32(const uint32_t* d_t, int64_t n, const int64_t* d_q, int nq, int64_t* d_out,
@@ -82,6 +108,12 @@ int cmda_images_to_events_index(const uint32_t* d_t, int64_t n, const int64_t* d
     if (!d_t || !d_ms_to_idx || !d_timestamps || !d_index || !d_status) return CMDA_ERR_BAD_ARG;
     return launch_images_to_events_index(d_t, n, d_ms_to_idx, n_ms, t_offset, d_timestamps, n_ts, d_index, d_status,
                                          static_cast<cudaStream_t>(stream));
+}
+
+int cmda_events_vg_resolved_mode(int64_t total_events, int S, int H, int W, int B, int mode) {
+    if (S <= 0 || H <= 0 || W <= 0 || B <= 0 || total_events < 0) return CMDA_ERR_BAD_ARG;
+    if (mode < CMDA_VOXEL_GLOBAL || mode > CMDA_VOXEL_EXACT) return CMDA_ERR_BAD_ARG;
+    return resolve_mode(mode, total_events, S, H, W, B);
 }
 
 size_t cmda_events_vg_workspace_bytes(int64_t total_events, int S, int H, int W, int B, int mode) {
@@ -107,7 +139,7 @@ int cmda_events_vg_batch(const uint32_t* d_t, const uint16_t* d_x, const uint16_
     if (S == 0) return CMDA_OK;
     if (!d_t || !d_x || !d_y || !d_p || !h_win_start || !h_win_end || !d_out || !d_workspace) return CMDA_ERR_BAD_ARG;
     if (normalize && !h_clip) return CMDA_ERR_BAD_ARG;
-    if (mode != CMDA_VOXEL_GLOBAL && mode != CMDA_VOXEL_TILED && mode != CMDA_VOXEL_AUTO) return CMDA_ERR_BAD_ARG;
+    if (mode < CMDA_VOXEL_GLOBAL || mode > CMDA_VOXEL_EXACT) return CMDA_ERR_BAD_ARG;
     if (reinterpret_cast<uintptr_t>(d_workspace) & 255) return CMDA_ERR_WORKSPACE;
     long long total = 0;
     for (int s = 0; s < S; ++s) {
@@ -119,6 +151,7 @@ int cmda_events_vg_batch(const uint32_t* d_t, const uint16_t* d_x, const uint16_
     if (workspace_bytes < cmda_events_vg_workspace_bytes(total, S, H, W, B, mode)) return CMDA_ERR_WORKSPACE;
     const int use_mode = resolve_mode(mode, total, S, H, W, B);
     if (use_mode == CMDA_VOXEL_TILED && !tiled_supported(H, W, B)) return CMDA_ERR_UNSUPPORTED;
+    if (use_mode == CMDA_VOXEL_EXACT) return CMDA_ERR_UNSUPPORTED;  // TODO exact-order mode
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long V = static_cast<long long>(B) * H * W;
 
@@ -146,6 +179,7 @@ int cmda_events_vg_batch(const uint32_t* d_t, const uint16_t* d_x, const uint16_
         PartialStats* part_g = partials + static_cast<size_t>(s0) * kStatBlocks;
         int64_t* bins_g = d_bin_counts ? d_bin_counts + static_cast<size_t>(s0) * B : nullptr;
         int rc;
+        phase_mark(st);
         if (use_mode == CMDA_VOXEL_TILED) {
             rc = launch_tiled_raw(d_t, d_x, d_y, d_p, tab, sn, d_rectify_map, H, W, B, raw_g, part_g, bins_g, scratch,
                                   scratch_bytes, st);
@@ -153,14 +187,18 @@ int cmda_events_vg_batch(const uint32_t* d_t, const uint16_t* d_x, const uint16_
         } else {
             long long* acc = reinterpret_cast<long long*>(scratch);
             CMDA_CUDA_TRY(cudaMemsetAsync(acc, 0, sizeof(long long) * sn * V, st));
+            phase_mark(st);
             rc = launch_scatter_global_raw(d_t, d_x, d_y, d_p, tab, sn, max_events, d_rectify_map, H, W, B, acc, bins_g, st);
             if (rc != CMDA_OK) return rc;
+            phase_mark(st);
             rc = launch_convert_stats(acc, raw_g, sn, V, part_g, st);
             if (rc != CMDA_OK) return rc;
         }
+        phase_mark(st);
         if (normalize) {
             rc = launch_norm_apply(raw_g, out_g, sn, V, part_g, tab, final_range, enforce_no_events_zero, st);
             if (rc != CMDA_OK) return rc;
+            phase_mark(st);
         }
     }
     return CMDA_OK;
@@ -171,11 +209,12 @@ int cmda_voxel_grid_f32(const float* d_time, const float* d_x, const float* d_y,
                         int mode, void* stream) {
     if (n < 0 || H <= 0 || W <= 0 || B <= 0 || !d_grid || !d_workspace) return CMDA_ERR_BAD_ARG;
     if (n > 0 && (!d_time || !d_x || !d_y || !d_pol)) return CMDA_ERR_BAD_ARG;
-    if (mode != CMDA_VOXEL_GLOBAL && mode != CMDA_VOXEL_TILED && mode != CMDA_VOXEL_AUTO) return CMDA_ERR_BAD_ARG;
+    if (mode < CMDA_VOXEL_GLOBAL || mode > CMDA_VOXEL_EXACT) return CMDA_ERR_BAD_ARG;
     if (reinterpret_cast<uintptr_t>(d_workspace) & 255) return CMDA_ERR_WORKSPACE;
     if (workspace_bytes < cmda_events_vg_workspace_bytes(n, 1, H, W, B, mode)) return CMDA_ERR_WORKSPACE;
     const int use_mode = resolve_mode(mode, n, 1, H, W, B);
     if (use_mode == CMDA_VOXEL_TILED && !tiled_supported(H, W, B)) return CMDA_ERR_UNSUPPORTED;
+    if (use_mode == CMDA_VOXEL_EXACT) return CMDA_ERR_UNSUPPORTED;  // TODO exact-order mode
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long V = static_cast<long long>(B) * H * W;
     char* ws = static_cast<char*>(d_workspace);

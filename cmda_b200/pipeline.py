@@ -1,0 +1,134 @@
+"""Host-buffer front door of the voxel path: pinned host SoA events in, host grids out.
+
+This is what a DataLoader-side caller uses when the event arrays live in host memory (the
+reference reads them from events.h5 into numpy, dsec.py:342-345): windows are cut into
+groups, each group's slices are copied host->device on a copy stream while the previous
+group is voxelised on the compute stream and the group before that is copied back.  The
+kernels only ever see device memory; the overlap is plain CUDA streams + events.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from .voxel import _cuda_device, default_clip_range
+
+__all__ = ["HostEventsPipeline"]
+
+
+class HostEventsPipeline:
+    """Voxelise windows of a HOST-resident event store.
+
+    ``t, x, y, p`` are numpy arrays or CPU tensors in DSEC dtypes; they are wrapped (and
+    pinned once, if they are not already) so that every later call is pure DMA.  The
+    rectify map is uploaded once.
+    """
+
+    def __init__(self, t, x, y, p, rectify_map, num_bins, height=480, width=640, device=None,
+                 windows_per_group=4, mode="auto", max_window_events=None):
+        self.device = _cuda_device(device)
+        self.H, self.W, self.B = int(height), int(width), int(num_bins)
+        self.mode = mode
+        self.group = int(windows_per_group)
+        self.host = [self._pin(a, dt) for a, dt in ((t, np.uint32), (x, np.uint16), (y, np.uint16), (p, np.uint8))]
+        self.n_total = int(self.host[0].shape[0])
+        self.rmap = None
+        if rectify_map is not None:
+            m = torch.as_tensor(np.ascontiguousarray(rectify_map, dtype=np.float32))
+            self.rmap = m.to(self.device).reshape(-1, self.H, self.W, 2).contiguous()
+        self.copy_in = torch.cuda.Stream(self.device)
+        self.copy_out = torch.cuda.Stream(self.device)
+        self.compute = torch.cuda.Stream(self.device)
+        self._cap = 0
+        self._slots = []
+        if max_window_events:
+            self._ensure(int(max_window_events) * self.group + 64 * self.group)
+
+    @staticmethod
+    def _pin(a, np_dtype):
+        if isinstance(a, torch.Tensor):
+            tns = a.contiguous()
+        else:
+            tns = torch.from_numpy(np.ascontiguousarray(a, dtype=np_dtype))
+        assert tns.element_size() == np.dtype(np_dtype).itemsize and tns.ndim == 1
+        return tns if tns.is_pinned() else tns.pin_memory()
+
+    def _ensure(self, n_events):
+        if n_events <= self._cap and self._slots:
+            return
+        self._cap = int(n_events)
+        dts = [h.dtype for h in self.host]
+        V = self.B * self.H * self.W
+        self._slots = []
+        for _ in range(2):   # double buffering
+            self._slots.append(dict(
+                ev=[torch.empty((self._cap,), dtype=dt, device=self.device) for dt in dts],
+                out=torch.empty((self.group, self.B, self.H, self.W), dtype=torch.float32, device=self.device),
+                ready=torch.cuda.Event(), done=torch.cuda.Event(), drained=torch.cuda.Event()))
+        L = _lib.lib()
+        nbytes = L.cmda_events_vg_workspace_bytes(self._cap, self.group, self.H, self.W, self.B,
+                                                  _lib.VOXEL_MODES[self.mode])
+        self._ws = torch.empty((nbytes,), dtype=torch.uint8, device=self.device)
+
+    def __call__(self, starts, finishes, clip_ranges=None, out=None):
+        """Inclusive windows ``[start, finish]`` -> pinned host tensor ``[S, B, H, W]``.
+        Returns after the last device->host copy has completed."""
+        L = _lib.lib()
+        starts = np.ascontiguousarray(starts, dtype=np.int64)
+        ends = np.ascontiguousarray(finishes, dtype=np.int64) + 1
+        S = int(starts.shape[0])
+        if S and (starts.min() < 0 or ends.max() > self.n_total):
+            raise IndexError("event window outside the store")
+        if out is None:
+            out = torch.empty((S, self.B, self.H, self.W), dtype=torch.float32).pin_memory()
+        assert out.is_pinned() and out.shape == (S, self.B, self.H, self.W)
+        groups = [list(range(g, min(g + self.group, S))) for g in range(0, S, self.group)]
+        # each window starts on a 64-event boundary of the staging buffer (keeps the 16-byte alignment
+        # the vector loads of the kernels want)
+        need = max((sum(((int(ends[s] - starts[s]) + 63) // 64 + 1) * 64 for s in g) for g in groups), default=0)
+        self._ensure(need)
+        mode_id = _lib.VOXEL_MODES[self.mode]
+        with torch.cuda.device(self.device):
+            for gi, g in enumerate(groups):
+                slot = self._slots[gi % 2]
+                # the slot's previous result must have left the device before it is overwritten
+                self.copy_in.wait_event(slot["drained"])
+                self.copy_in.wait_event(slot["done"])
+                d_starts, d_ends, pos = [], [], 0
+                with torch.cuda.stream(self.copy_in):
+                    for s in g:
+                        a, b = int(starts[s]), int(ends[s])
+                        n = max(b - a, 0)
+                        for dev_arr, host_arr in zip(slot["ev"], self.host):
+                            if n:
+                                dev_arr[pos:pos + n].copy_(host_arr[a:b], non_blocking=True)
+                        d_starts.append(pos)
+                        d_ends.append(pos + n)
+                        pos += (n + 63) // 64 * 64 + 64
+                    slot["ready"].record(self.copy_in)
+                clips = np.array([default_clip_range(int(ends[s]) - 1, int(starts[s]))
+                                  if (clip_ranges is None or clip_ranges[s] is None) else clip_ranges[s] for s in g],
+                                 dtype=np.float32)
+                hs = np.array(d_starts, dtype=np.int64)
+                he = np.array(d_ends, dtype=np.int64)
+                self.compute.wait_event(slot["ready"])
+                with torch.cuda.stream(self.compute):
+                    ev = slot["ev"]
+                    _lib.check(L.cmda_events_vg_batch(
+                        _lib.ptr(ev[0]), _lib.ptr(ev[1]), _lib.ptr(ev[2]), _lib.ptr(ev[3]), _lib.host_ptr(hs),
+                        _lib.host_ptr(he), len(g), _lib.ptr(self.rmap), None, self.H, self.W, self.B,
+                        _lib.host_ptr(clips), 1.0, 1, 1, _lib.ptr(slot["out"]), None, None, _lib.ptr(self._ws),
+                        self._ws.numel(), mode_id, self.compute.cuda_stream), "cmda_events_vg_batch")
+                    slot["done"].record(self.compute)
+                self.copy_out.wait_event(slot["done"])
+                with torch.cuda.stream(self.copy_out):
+                    out[g[0]:g[0] + len(g)].copy_(slot["out"][:len(g)], non_blocking=True)
+                    slot["drained"].record(self.copy_out)
+            self.copy_out.synchronize()
+        return out
+
+    def bytes_per_call(self, starts, finishes):
+        n = int(np.clip(np.asarray(finishes, dtype=np.int64) + 1 - np.asarray(starts, dtype=np.int64), 0, None).sum())
+        S = len(starts)
+        return 9 * n, 4 * S * self.B * self.H * self.W

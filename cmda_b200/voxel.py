@@ -61,7 +61,7 @@ def events_to_voxel_grid(time, x, y, pol, width, height, num_bins, normalize_fla
     n = int(t_.shape[0])
     if n == 0:
         raise IndexError("index 0 is out of bounds for dimension 0 with size 0")   # t_norm[0], dsec.py:39
-    mode_id = {"global": _lib.VOXEL_GLOBAL, "tiled": _lib.VOXEL_TILED, "auto": _lib.VOXEL_AUTO}[mode]
+    mode_id = _lib.VOXEL_MODES[mode]
     L = _lib.lib()
     grid = torch.empty((num_bins, height, width), dtype=torch.float32, device=dev)
     counts = torch.empty((num_bins,), dtype=torch.int64, device=dev) if return_bin_counts else None
@@ -160,7 +160,7 @@ def events_vg_batch(store: EventStore, starts, finishes, num_bins, clip_ranges=N
     if mids is not None and store.rectify_map is not None and S and mids.max() >= store.rectify_map.shape[0]:
         raise IndexError("map_id outside the store's rectify maps")
     H, W, B = store.height, store.width, int(num_bins)
-    mode_id = {"global": _lib.VOXEL_GLOBAL, "tiled": _lib.VOXEL_TILED, "auto": _lib.VOXEL_AUTO}[mode]
+    mode_id = _lib.VOXEL_MODES[mode]
     if out is None:
         out = torch.empty((S, B, H, W), dtype=torch.float32, device=dev)
     assert out.is_cuda and out.is_contiguous() and out.shape == (S, B, H, W) and out.dtype == torch.float32

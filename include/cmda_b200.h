@@ -37,13 +37,18 @@ enum {
     CMDA_ERR_NO_DEVICE = -5    /* no sm_100 device / driver                                  */
 };
 
-/* Accumulation modes of the voxel scatter (all deterministic, all bit-identical to
- * each other: contributions are quantised to 2^-30 and summed as 64-bit integers,
- * which is order independent). */
+/* Accumulation modes of the voxel scatter.  All are deterministic (bit-reproducible).
+ * GLOBAL and TILED quantise each float32 contribution to 2^-30 and sum 64-bit integers,
+ * which is order independent: they are bit-identical to each other and closer to the
+ * exact sum than the reference's float32 accumulation.  EXACT performs the reference's
+ * own float32 additions in the reference's own order (corner pass major, event index
+ * minor: dsec.py:47-58), so its raw grid is BIT-IDENTICAL to the single-thread reference,
+ * including the rounding residue the reference leaves where ON/OFF events cancel. */
 enum {
     CMDA_VOXEL_GLOBAL = 0, /* one 64-bit integer RED per corner into an L2-resident grid   */
     CMDA_VOXEL_TILED = 1,  /* chunk-local band partition + shared-memory band accumulation */
-    CMDA_VOXEL_AUTO = 2    /* TILED for large windows, GLOBAL for small ones                */
+    CMDA_VOXEL_AUTO = 2,   /* TILED for large windows, GLOBAL for small ones                */
+    CMDA_VOXEL_EXACT = 3   /* stable cell sort + ordered float32 accumulation               */
 };
 
 /* Directions of the shift-pair generator (reference mmseg/datasets/utils.py:128-151). */
@@ -59,6 +64,18 @@ const char* cmda_strerror(int code);
 int cmda_version(void);
 /* cudaError_t of the last failing CUDA call made by this thread inside the library. */
 int cmda_last_cuda_error(void);
+
+/* Optional phase timer used by bench.py for the per-kernel roofline: attach a host array
+ * of n cudaEvent_t (created with cmda_event_create) to the CALLING THREAD; every phase
+ * boundary of the following cmda_events_vg_batch calls records the next event of the list
+ * on the call's stream (GLOBAL: start | memset | scatter | convert+stats | apply;
+ * TILED: start | partition | band accumulate | apply).  detach returns how many events were
+ * recorded.  Off by default. */
+int cmda_profiler_attach(void* const* h_events, int n);
+int cmda_profiler_detach(void);
+void* cmda_event_create(void);
+int cmda_event_destroy(void* event);
+int cmda_event_elapsed_ms(void* start_event, void* end_event, float* h_ms);
 
 /* ------------------------------------------------------------------------------------
  * K1  window slicer.
@@ -95,6 +112,8 @@ int cmda_images_to_events_index(const uint32_t* d_t, int64_t n, const int64_t* d
  *  empty windows (end <= start) and single-timestamp windows (NaN time)
  *  produce an all-zero raw grid, exactly like the reference. */
 size_t cmda_events_vg_workspace_bytes(int64_t total_events, int S, int H, int W, int B, int mode);
+/* The concrete mode CMDA_VOXEL_AUTO resolves to for this batch (or `mode` itself). */
+int cmda_events_vg_resolved_mode(int64_t total_events, int S, int H, int W, int B, int mode);
 
 int cmda_events_vg_batch(const uint32_t* d_t, const uint16_t* d_x, const uint16_t* d_y, const uint8_t* d_p,
                          const int64_t* h_win_start, const int64_t* h_win_end, int S,
