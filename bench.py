@@ -290,8 +290,9 @@ def run_gpu(args, rank, local_rank, world):
             names = ["memset(int64 grid)", "voxel_scatter_global_kernel", "convert_stats_kernel", "norm_apply_kernel"]
             launches_per_step = 3
         else:
-            names = ["voxel_partition_kernel", "voxel_band_accumulate_kernel", "norm_apply_kernel"]
-            launches_per_step = 3
+            names = ["memset(int64 grid)", "tile_bbox+tile_count+tile_scan kernels", "tile_partition_kernel",
+                     "tile_accumulate_kernel", "convert_stats_kernel", "norm_apply_kernel"]
+            launches_per_step = 7
         phases = {names[j] if j < len(names) else f"phase{j}": float(phase_ms[j]) for j in range(len(phase_ms))}
         kernel_phases = {k: v for k, v in phases.items() if not k.startswith("memset")}
         dom = max(kernel_phases, key=kernel_phases.get) if kernel_phases else None

@@ -25,18 +25,17 @@ int launch_pair(const uint8_t*, const uint8_t*, int, int, int, const float*, flo
 // TILED mode (voxel_tiled.cu)
 size_t tiled_workspace_bytes(int64_t total_events, int S, int H, int W, int B);
 int tiled_supported(int H, int W, int B);
-int launch_tiled_raw(const uint32_t*, const uint16_t*, const uint16_t*, const uint8_t*, const WindowTable&, int,
-                     const float*, int, int, int, float*, PartialStats*, int64_t*, void*, size_t, cudaStream_t);
-int launch_tiled_f32(const float*, const float*, const float*, const float*, long long, int, int, int, float*,
-                     PartialStats*, int64_t*, void*, size_t, cudaStream_t);
+int launch_tiled_scatter(const uint32_t*, const uint16_t*, const uint16_t*, const uint8_t*, const WindowTable&, int,
+                         const float*, int, int, int, long long*, int64_t*, void*, size_t, cudaStream_t);
 
 static size_t stats_bytes(int S) { return align_up(sizeof(PartialStats) * kStatBlocks * static_cast<size_t>(S), 256); }
 static size_t acc_bytes(int S, int H, int W, int B) {
     return align_up(sizeof(long long) * static_cast<size_t>(S) * B * H * W, 256);
 }
 
-// windows smaller than this take the GLOBAL path under CMDA_VOXEL_AUTO: the partition +
-// band passes have a fixed cost that only pays off once the atomics dominate
+// batches smaller than this (events per window, on average) take the GLOBAL path under
+// CMDA_VOXEL_AUTO: the count / partition / accumulate passes have a fixed cost that only pays
+// off once the L2 atomics of the GLOBAL path dominate
 constexpr long long kAutoTiledMinEvents = 200000;
 
 static int resolve_mode(int mode, long long total_events, int S, int H, int W, int B) {
@@ -119,14 +118,8 @@ int cmda_events_vg_resolved_mode(int64_t total_events, int S, int H, int W, int 
 size_t cmda_events_vg_workspace_bytes(int64_t total_events, int S, int H, int W, int B, int mode) {
     if (S <= 0 || H <= 0 || W <= 0 || B <= 0 || total_events < 0) return 0;
     const int group = S < kMaxWindows ? S : kMaxWindows;
-    size_t need = stats_bytes(S);
-    const size_t g = acc_bytes(group, H, W, B);
-    size_t t = 0;
-    if (mode != CMDA_VOXEL_GLOBAL && tiled_supported(H, W, B)) t = tiled_workspace_bytes(total_events, S, H, W, B);
-    // AUTO may resolve to either path, so it reserves the larger of the two
-    if (mode == CMDA_VOXEL_GLOBAL) need += g;
-    else if (mode == CMDA_VOXEL_TILED) need += (t ? t : g);
-    else need += (t > g ? t : g);
+    size_t need = stats_bytes(S) + acc_bytes(group, H, W, B);       // both paths sum into the int64 grid
+    if (mode != CMDA_VOXEL_GLOBAL && tiled_supported(H, W, B)) need += tiled_workspace_bytes(total_events, S, H, W, B);
     return need + 256;
 }
 
@@ -180,20 +173,20 @@ int cmda_events_vg_batch(const uint32_t* d_t, const uint16_t* d_x, const uint16_
         int64_t* bins_g = d_bin_counts ? d_bin_counts + static_cast<size_t>(s0) * B : nullptr;
         int rc;
         phase_mark(st);
+        long long* acc = reinterpret_cast<long long*>(scratch);
+        CMDA_CUDA_TRY(cudaMemsetAsync(acc, 0, sizeof(long long) * sn * V, st));
+        phase_mark(st);
         if (use_mode == CMDA_VOXEL_TILED) {
-            rc = launch_tiled_raw(d_t, d_x, d_y, d_p, tab, sn, d_rectify_map, H, W, B, raw_g, part_g, bins_g, scratch,
-                                  scratch_bytes, st);
-            if (rc != CMDA_OK) return rc;
+            const size_t ab = acc_bytes(sn, H, W, B);
+            rc = launch_tiled_scatter(d_t, d_x, d_y, d_p, tab, sn, d_rectify_map, H, W, B, acc, bins_g, scratch + ab,
+                                      scratch_bytes - ab, st);       // marks: count+scan | partition
         } else {
-            long long* acc = reinterpret_cast<long long*>(scratch);
-            CMDA_CUDA_TRY(cudaMemsetAsync(acc, 0, sizeof(long long) * sn * V, st));
-            phase_mark(st);
             rc = launch_scatter_global_raw(d_t, d_x, d_y, d_p, tab, sn, max_events, d_rectify_map, H, W, B, acc, bins_g, st);
-            if (rc != CMDA_OK) return rc;
-            phase_mark(st);
-            rc = launch_convert_stats(acc, raw_g, sn, V, part_g, st);
-            if (rc != CMDA_OK) return rc;
         }
+        if (rc != CMDA_OK) return rc;
+        phase_mark(st);
+        rc = launch_convert_stats(acc, raw_g, sn, V, part_g, st);
+        if (rc != CMDA_OK) return rc;
         phase_mark(st);
         if (normalize) {
             rc = launch_norm_apply(raw_g, out_g, sn, V, part_g, tab, final_range, enforce_no_events_zero, st);
@@ -212,18 +205,15 @@ int cmda_voxel_grid_f32(const float* d_time, const float* d_x, const float* d_y,
     if (mode < CMDA_VOXEL_GLOBAL || mode > CMDA_VOXEL_EXACT) return CMDA_ERR_BAD_ARG;
     if (reinterpret_cast<uintptr_t>(d_workspace) & 255) return CMDA_ERR_WORKSPACE;
     if (workspace_bytes < cmda_events_vg_workspace_bytes(n, 1, H, W, B, mode)) return CMDA_ERR_WORKSPACE;
-    const int use_mode = resolve_mode(mode, n, 1, H, W, B);
-    if (use_mode == CMDA_VOXEL_TILED && !tiled_supported(H, W, B)) return CMDA_ERR_UNSUPPORTED;
-    if (use_mode == CMDA_VOXEL_EXACT) return CMDA_ERR_UNSUPPORTED;  // TODO exact-order mode
+    // float32 events are already rectified: there is no map gather to tile, so this entry point
+    // runs the GLOBAL scatter (AUTO resolves to it); TILED / EXACT are refused explicitly
+    if (mode == CMDA_VOXEL_TILED || mode == CMDA_VOXEL_EXACT) return CMDA_ERR_UNSUPPORTED;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long V = static_cast<long long>(B) * H * W;
     char* ws = static_cast<char*>(d_workspace);
     PartialStats* partials = reinterpret_cast<PartialStats*>(ws);
     char* scratch = ws + stats_bytes(1);
     if (d_bin_counts) CMDA_CUDA_TRY(cudaMemsetAsync(d_bin_counts, 0, sizeof(int64_t) * B, st));
-    if (use_mode == CMDA_VOXEL_TILED)
-        return launch_tiled_f32(d_time, d_x, d_y, d_pol, n, H, W, B, d_grid, partials, d_bin_counts, scratch,
-                                workspace_bytes - stats_bytes(1), st);
     long long* acc = reinterpret_cast<long long*>(scratch);
     CMDA_CUDA_TRY(cudaMemsetAsync(acc, 0, sizeof(long long) * V, st));
     int rc = launch_scatter_global_f32(d_time, d_x, d_y, d_pol, n, H, W, B, acc, d_bin_counts, st);

@@ -36,11 +36,15 @@ __device__ __forceinline__ RawWindowTime raw_window_time(const uint32_t* __restr
     return w;
 }
 
-__device__ __forceinline__ float raw_t_norm(uint32_t t, const RawWindowTime& w) {
-    const float t01 = __fdiv_rn(__uint2float_rn(t - w.t_first), w.fdT);   // dsec.py:347-348
+// t_norm of an event dt = t - t[0] microseconds into its window (uint32 subtraction first).
+__device__ __forceinline__ float raw_t_norm_dt(uint32_t dt, const RawWindowTime& w) {
+    const float t01 = __fdiv_rn(__uint2float_rn(dt), w.fdT);              // dsec.py:347-348
     const float a = __fsub_rn(t01, w.t01_first);                          // dsec.py:39
     const float b = __fmul_rn(w.cm1, a);
     return __fdiv_rn(b, w.den);
+}
+__device__ __forceinline__ float raw_t_norm(uint32_t t, const RawWindowTime& w) {
+    return raw_t_norm_dt(t - w.t_first, w);
 }
 
 __device__ __forceinline__ Event make_raw_event(uint32_t t, unsigned x, unsigned y, unsigned p,

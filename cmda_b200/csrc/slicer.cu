@@ -44,8 +44,10 @@ __global__ void images_to_events_index_kernel(const uint32_t* __restrict__ t, lo
             const long long left = ms_to_idx[ms];                                 // :26
             long long right = ms_to_idx[ms + 2];                                  // :33
             if (right > n - 1) right = n - 1;                                     // :34-35
-            const long long tl = __ldg(t + left), tr = __ldg(t + right);
-            if (!(tl <= ts_us && ts_us <= tr)) {                                  // :37-39
+            if (left < 0 || left >= n || right < 0) {
+                st = 2;  // t[left] / t[right] would raise IndexError in the reference (:37)
+            } else if (!(static_cast<long long>(__ldg(t + left)) <= ts_us &&
+                         ts_us <= static_cast<long long>(__ldg(t + right)))) {    // :37-39
                 st = 1;
             } else {
                 res = upper_bound_u32(t, left, right + 1, ts_us) - 1;             // :40-42

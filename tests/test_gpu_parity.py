@@ -380,7 +380,7 @@ def test_images_to_events_index_golden(cm):
 def test_images_to_events_index_range_error(cm):
     c = INDEX["index_table"]
     bad = c["ms_to_idx"].copy()
-    bad[:] = bad[-1]      # brackets no longer contain the timestamps
+    bad[:] = 0            # brackets no longer contain the timestamps
     ts = np.array([int(c["t_offset"]) + 500_000], np.int64)
     with pytest.raises(ValueError):
         cm.images_to_events_index(c["t"], int(c["t_offset"]), bad, ts, device="cuda:0")
