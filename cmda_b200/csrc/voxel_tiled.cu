@@ -32,9 +32,8 @@ constexpr int kPartThreads = 512;
 constexpr int kPartGroupsPerThread = 2;                                    // 16 events per thread
 constexpr int kPartChunk = kPartThreads * kPartGroupsPerThread * 8;        // 8192 events per CTA
 constexpr int kAccThreads = 512;
-constexpr int kItemRecords = 32000;    // < 32768: the 16-bit carry fields of one work item cannot overflow
+constexpr int kItemRecords = 32768;    // records per work item (load-balance granularity of the accumulate pass)
 constexpr int kMaxTiles = 4096;
-constexpr unsigned kHiBias = 0x80008000u;
 
 struct TileGeom {
     int tw_log2, th_log2;   // raw-sensor tile size (powers of two)
@@ -278,7 +277,7 @@ tile_scan_kernel(const unsigned* __restrict__ counts, TileGeom g, unsigned* __re
 
 // ---- partition --------------------------------------------------------------------------------
 template <bool HAS_T, bool VEC>
-__global__ void __launch_bounds__(kPartThreads)
+__global__ void __launch_bounds__(kPartThreads, 2)
 tile_partition_kernel(const uint32_t* __restrict__ t, const uint16_t* __restrict__ x, const uint16_t* __restrict__ y,
                       const uint8_t* __restrict__ p, WindowTable tab, TiledTable tt, TileGeom g, int H, int W,
                       const unsigned* __restrict__ bucket_off, unsigned* __restrict__ cursor, void* __restrict__ records) {
@@ -286,7 +285,8 @@ tile_partition_kernel(const uint32_t* __restrict__ t, const uint16_t* __restrict
     extern __shared__ __align__(16) unsigned char s_raw[];
     unsigned* s_hist = reinterpret_cast<unsigned*>(s_raw);     // [T] counts, later the run's global base
     unsigned* s_loff = s_hist + g.T;                            // [T + 1] local exclusive offsets
-    Rec* s_stage = reinterpret_cast<Rec*>(s_loff + g.T + 2);    // [kPartChunk]  (T + 2 keeps 8-byte alignment for even T)
+    unsigned* s_dst = s_loff + g.T + 2;                         // [kPartChunk] destination record index
+    Rec* s_stage = reinterpret_cast<Rec*>(s_dst + kPartChunk);  // [kPartChunk] records sorted by tile
     __shared__ unsigned s_warp[kPartThreads / 32];
 
     const int s = blockIdx.y;
@@ -404,32 +404,49 @@ tile_partition_kernel(const uint32_t* __restrict__ t, const uint16_t* __restrict
             } else {
                 r = static_cast<Rec2>(lx | (ly << 6) | ((pol & 15u) << 12));
             }
-            s_stage[s_loff[tile] + rank] = r;
+            const unsigned pos = s_loff[tile] + rank;
+            s_stage[pos] = r;
+            s_dst[pos] = s_hist[tile] + rank;      // bucket base of this chunk's run + rank inside the run
         }
     }
     __syncthreads();
-    // copy every tile's run to its bucket: one warp per tile, lanes over the run
+    // copy out: consecutive staged records of one tile go to consecutive bucket slots, so a
+    // warp's stores coalesce into the tile runs
     Rec* out = reinterpret_cast<Rec*>(records) + tt.rec_base[s];
-    for (int k = wid; k < g.T; k += kPartThreads / 32) {
-        const unsigned lo = s_loff[k], n = s_loff[k + 1] - lo;
-        Rec* dst = out + s_hist[k];
-        for (unsigned i = lane; i < n; i += 32) dst[i] = s_stage[lo + i];
-    }
+    const unsigned total = s_loff[g.T];
+    for (unsigned i = threadIdx.x; i < total; i += kPartThreads) out[s_dst[i]] = s_stage[i];
 }
 
 // ---- accumulate -------------------------------------------------------------------------------
-// One contribution into the shared-memory footprint: 32-bit ATOMS on the low word; the
-// value it returns tells whether this very addition wrapped, which is the carry (or, for a
-// negative addend, the missing borrow) into the 16-bit biased upper field.
-__device__ __forceinline__ void smem_accumulate(unsigned* __restrict__ lo, unsigned* __restrict__ hi, unsigned v, int q) {
-    const unsigned uq = static_cast<unsigned>(q);
-    const unsigned old = atomicAdd(lo + v, uq);
-    const unsigned nw = old + uq;
-    if (q > 0) {
-        if (nw < old) atomicAdd(hi + (v >> 1), 1u << ((v & 1u) * 16u));
+// One contribution into the shared-memory footprint: a native 32-bit ATOMS.ADD on the low
+// word; the value it returns tells whether this very addition carried (or borrowed) across
+// bit 32, and only then (about 1 contribution in 16) a second ATOMS updates the upper word.
+// (lo, hi) is therefore the exact 64-bit sum, like the RED.64 of mode GLOBAL.
+__device__ __forceinline__ void smem_accumulate(unsigned* __restrict__ lo, int* __restrict__ hi, unsigned v, int q) {
+    const unsigned old = atomicAdd(lo + v, static_cast<unsigned>(q));
+    const long long s = static_cast<long long>(static_cast<unsigned long long>(old)) + static_cast<long long>(q);
+    const int d = static_cast<int>(s >> 32);
+    if (d != 0) atomicAdd(hi + v, d);
+}
+__device__ __forceinline__ void smem_accumulate_w(unsigned* __restrict__ lo, int* __restrict__ hi, unsigned v, float w30) {
+    const int q = __float2int_rn(w30);      // w30 = weight * 2^30, |w30| <= 2^30
+    if (q != 0) smem_accumulate(lo, hi, v, q);
+}
+
+struct AccRecord {
+    unsigned a, b;
+};
+template <bool HAS_T>
+__device__ __forceinline__ AccRecord load_record(const void* __restrict__ rec, unsigned i) {
+    AccRecord r;
+    if constexpr (HAS_T) {
+        const uint2 v = ldg_stream_u2(reinterpret_cast<const Rec8*>(rec) + i);
+        r.a = v.x; r.b = v.y;
     } else {
-        if (nw > old) atomicAdd(hi + (v >> 1), 0xffffffffu << ((v & 1u) * 16u));
+        r.a = 0u;
+        r.b = __ldg(reinterpret_cast<const unsigned short*>(rec) + i);
     }
+    return r;
 }
 
 template <bool HAS_T>
@@ -443,13 +460,12 @@ tile_accumulate_kernel(const void* __restrict__ records, const uint32_t* __restr
     const int TW = 1 << g.tw_log2, TH = 1 << g.th_log2;
     const unsigned cap = static_cast<unsigned>(g.cap_voxels);
     unsigned* s_lo = reinterpret_cast<unsigned*>(s_raw);                        // [cap]
-    unsigned* s_hi = s_lo + cap;                                                // [cap / 2]
-    float2* s_map = reinterpret_cast<float2*>(s_hi + cap / 2);                  // [TW * TH]
+    int* s_hi = reinterpret_cast<int*>(s_lo + cap);                             // [cap]
+    float2* s_map = reinterpret_cast<float2*>(s_hi + cap);                      // [TW * TH]
     unsigned* s_bins = reinterpret_cast<unsigned*>(s_map + TW * TH);            // [32]
     __shared__ unsigned s_item;
 
-    for (unsigned i = threadIdx.x; i < cap; i += kAccThreads) s_lo[i] = 0u;
-    for (unsigned i = threadIdx.x; i < cap / 2; i += kAccThreads) s_hi[i] = kHiBias;
+    for (unsigned i = threadIdx.x; i < cap; i += kAccThreads) { s_lo[i] = 0u; s_hi[i] = 0; }
     if (threadIdx.x < 32) s_bins[threadIdx.x] = 0u;
     const unsigned n_items = queue[0];
     const size_t V = static_cast<size_t>(B) * H * W;
@@ -473,64 +489,98 @@ tile_accumulate_kernel(const void* __restrict__ records, const uint32_t* __restr
             if (map != nullptr && gx < W && gy < H) m = __ldg(map + static_cast<size_t>(gy) * W + gx);
             s_map[i] = m;
         }
-        __syncthreads();
         const RawWindowTime rw = raw_window_time(t, wd.start, wd.end, B);
-        const bool window_nan = !(rw.den == rw.den);      // single-timestamp window: every t_norm is NaN
+        // den is 1 (then t01[0] is 0 and t_norm = (C-1) * (dt / dT), dsec.py:38-39 after 347-348)
+        // or NaN (single-timestamp window: every t_norm is NaN, nothing is accumulated or counted)
+        const bool window_nan = !(rw.den == 1.0f);
         const Rec* rec = reinterpret_cast<const Rec*>(records) + tt.rec_base[s];
         unsigned long long* gacc = acc + static_cast<size_t>(s) * V;
         const unsigned bw = static_cast<unsigned>(bb.z), bh = static_cast<unsigned>(bb.w);
-        if (!window_nan) {
-            for (unsigned i = static_cast<unsigned>(it.z) + threadIdx.x; i < static_cast<unsigned>(it.w); i += kAccThreads) {
-                Event e;
-                unsigned lx, ly, pol;
+        const unsigned plane = bw * bh;
+        const bool fits = plane * static_cast<unsigned>(B) <= cap;
+        const unsigned end = static_cast<unsigned>(it.w);
+        unsigned i = static_cast<unsigned>(it.z) + threadIdx.x;
+        AccRecord cur{0u, 0u};
+        if (!window_nan && i < end) cur = load_record<HAS_T>(rec, i);
+        __syncthreads();
+        while (!window_nan && i < end) {
+            const unsigned inext = i + kAccThreads;
+            AccRecord nxt{0u, 0u};
+            if (inext < end) nxt = load_record<HAS_T>(rec, inext);      // in flight while this record is processed
+            unsigned lx, ly, pol;
+            if constexpr (HAS_T) { lx = cur.b & 0xffu; ly = (cur.b >> 8) & 0xffu; pol = cur.b >> 16; }
+            else { lx = cur.b & 63u; ly = (cur.b >> 6) & 63u; pol = cur.b >> 12; }
+            const float2 m = s_map[(ly << g.tw_log2) + lx];
+            const float value = __fsub_rn(__fmul_rn(2.0f, static_cast<float>(pol)), 1.0f);     // dsec.py:45
+            // dsec.py:347-348 then 38-39 with t01[0] = 0 and den = 1 (both exact identities)
+            const float tn = HAS_T ? __fmul_rn(rw.cm1, __fdiv_rn(__uint2float_rn(cur.a), rw.fdT)) : 0.0f;
+            const int x0 = trunc_like_x86(m.x), y0 = trunc_like_x86(m.y);                       // dsec.py:41-42
+            const int t0 = HAS_T ? trunc_like_x86(tn) : 0;                                      // dsec.py:43
+            if (bin_counts != nullptr && t0 >= 0 && t0 < B) atomicAdd(&s_bins[t0], 1u);
+            const bool interior = fits && x0 >= 0 && x0 < W - 1 && y0 >= 0 && y0 < H - 1 &&
+                                  (!HAS_T || (t0 >= 0 && t0 < B - 1));
+            if (interior) {
+                // all corners are inside the grid and inside the footprint: no per-corner tests.
+                // Weights are carried pre-scaled by 2^30 (exact: a power of two commutes with
+                // every rounding of the left-to-right product of dsec.py:51-52).
+                const float v30 = __fmul_rn(value, kFixScale);
+                const float vx0 = __fmul_rn(v30, tent(x0, m.x)), vx1 = __fmul_rn(v30, tent(x0 + 1, m.x));
+                const float wy0 = tent(y0, m.y), wy1 = tent(y0 + 1, m.y);
+                const float w00 = __fmul_rn(vx0, wy0), w01 = __fmul_rn(vx0, wy1);
+                const float w10 = __fmul_rn(vx1, wy0), w11 = __fmul_rn(vx1, wy1);
+                const unsigned v = (static_cast<unsigned>(t0) * bh + static_cast<unsigned>(y0 - bb.y)) * bw +
+                                   static_cast<unsigned>(x0 - bb.x);
                 if constexpr (HAS_T) {
-                    const uint2 r = ldg_stream_u2(rec + i);
-                    lx = r.y & 0xffu; ly = (r.y >> 8) & 0xffu; pol = r.y >> 16;
-                    e.tn = raw_t_norm_dt(r.x, rw);
+                    const float wt0 = tent(t0, tn), wt1 = tent(t0 + 1, tn);
+                    smem_accumulate_w(s_lo, s_hi, v, __fmul_rn(w00, wt0));
+                    smem_accumulate_w(s_lo, s_hi, v + plane, __fmul_rn(w00, wt1));
+                    smem_accumulate_w(s_lo, s_hi, v + bw, __fmul_rn(w01, wt0));
+                    smem_accumulate_w(s_lo, s_hi, v + bw + plane, __fmul_rn(w01, wt1));
+                    smem_accumulate_w(s_lo, s_hi, v + 1, __fmul_rn(w10, wt0));
+                    smem_accumulate_w(s_lo, s_hi, v + 1 + plane, __fmul_rn(w10, wt1));
+                    smem_accumulate_w(s_lo, s_hi, v + bw + 1, __fmul_rn(w11, wt0));
+                    smem_accumulate_w(s_lo, s_hi, v + bw + 1 + plane, __fmul_rn(w11, wt1));
                 } else {
-                    const unsigned r = __ldg(reinterpret_cast<const unsigned short*>(rec) + i);
-                    lx = r & 63u; ly = (r >> 6) & 63u; pol = r >> 12;
-                    e.tn = raw_t_norm_dt(0u, rw);   // B == 1: (C - 1) = 0 makes every finite t_norm 0 (dsec.py:38-39)
+                    // B == 1: t_norm = 0, the only temporal corner is bin 0 with weight 1
+                    smem_accumulate_w(s_lo, s_hi, v, w00);
+                    smem_accumulate_w(s_lo, s_hi, v + bw, w01);
+                    smem_accumulate_w(s_lo, s_hi, v + 1, w10);
+                    smem_accumulate_w(s_lo, s_hi, v + bw + 1, w11);
                 }
-                const float2 m = s_map[(ly << g.tw_log2) + lx];
-                e.x = m.x; e.y = m.y;
-                e.value = __fsub_rn(__fmul_rn(2.0f, static_cast<float>(pol)), 1.0f);
+            } else {
+                // border events (some corner outside the grid) and over-capacity footprints
+                Event e;
+                e.x = m.x; e.y = m.y; e.tn = tn; e.value = value;
                 const Origin o = origin_of(e, H, W, B);
-                if (bin_counts != nullptr && o.t0 >= 0 && o.t0 < B) atomicAdd(&s_bins[o.t0], 1u);
-                if (!o.any) continue;
-                for_each_corner(e, o, H, W, B, [&](int xl, int yl, int tl, float w) {
-                    const int q = __float2int_rn(__fmul_rn(w, kFixScale));     // |w| <= 1: fits 32 bits
-                    if (q == 0) return;
-                    const unsigned cx = static_cast<unsigned>(xl - bb.x), cy = static_cast<unsigned>(yl - bb.y);
-                    const unsigned v = (static_cast<unsigned>(tl) * bh + cy) * bw + cx;
-                    if (cx < bw && cy < bh && v < cap) smem_accumulate(s_lo, s_hi, v, q);
-                    else atomicAdd(gacc + (static_cast<size_t>(tl) * H + yl) * W + xl,
-                                   static_cast<unsigned long long>(static_cast<long long>(q)));
-                });
+                if (o.any) {
+                    for_each_corner(e, o, H, W, B, [&](int xl, int yl, int tl, float w) {
+                        const int q = __float2int_rn(__fmul_rn(w, kFixScale));     // |w| <= 1: fits 32 bits
+                        if (q == 0) return;
+                        const unsigned cx = static_cast<unsigned>(xl - bb.x), cy = static_cast<unsigned>(yl - bb.y);
+                        const unsigned vv = (static_cast<unsigned>(tl) * bh + cy) * bw + cx;
+                        if (cx < bw && cy < bh && vv < cap) smem_accumulate(s_lo, s_hi, vv, q);
+                        else atomicAdd(gacc + (static_cast<size_t>(tl) * H + yl) * W + xl,
+                                       static_cast<unsigned long long>(static_cast<long long>(q)));
+                    });
+                }
             }
-        } else if (bin_counts != nullptr) {
-            // NaN t_norm: t0 is 'integer indefinite', no bin counts any event
+            cur = nxt;
+            i = inext;
         }
         __syncthreads();
         // flush the non-zero voxels of the footprint and restore the all-zero state
-        const unsigned nvox = min(bw * bh * static_cast<unsigned>(B), cap);
-        for (unsigned w2 = threadIdx.x; w2 < (nvox + 1) / 2; w2 += kAccThreads) {
-            const unsigned hw = s_hi[w2];
-            s_hi[w2] = kHiBias;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const unsigned v = 2 * w2 + h;
-                if (v >= nvox) break;
-                const unsigned l = s_lo[v];
-                const int hv = static_cast<int>((hw >> (16 * h)) & 0xffffu) - 0x8000;
-                if (l == 0u && hv == 0) continue;
-                s_lo[v] = 0u;
-                const long long val = (static_cast<long long>(hv) << 32) + static_cast<long long>(l);
-                const unsigned cx = v % bw, r = v / bw;
-                const unsigned cy = r % bh, tl = r / bh;
-                atomicAdd(gacc + (static_cast<size_t>(tl) * H + (bb.y + cy)) * W + (bb.x + cx),
-                          static_cast<unsigned long long>(val));
-            }
+        const unsigned nvox = min(plane * static_cast<unsigned>(B), cap);
+        for (unsigned v = threadIdx.x; v < nvox; v += kAccThreads) {
+            const unsigned l = s_lo[v];
+            const int h = s_hi[v];
+            if (l == 0u && h == 0) continue;
+            s_lo[v] = 0u;
+            s_hi[v] = 0;
+            const long long val = (static_cast<long long>(h) << 32) + static_cast<long long>(l);
+            const unsigned cx = v % bw, r = v / bw;
+            const unsigned cy = r % bh, tl = r / bh;
+            atomicAdd(gacc + (static_cast<size_t>(tl) * H + (bb.y + cy)) * W + (bb.x + cx),
+                      static_cast<unsigned long long>(val));
         }
         if (bin_counts != nullptr && threadIdx.x < B) {
             const unsigned c = s_bins[threadIdx.x];
@@ -590,7 +640,7 @@ int launch_tiled_scatter(const uint32_t* t, const uint16_t* x, const uint16_t* y
         const long long per = static_cast<long long>(kPartThreads) * kPartGroupsPerThread;
         dim3 grid(static_cast<unsigned>((groups + per - 1) / per), S);
         const size_t rec = (B == 1) ? sizeof(Rec2) : sizeof(Rec8);
-        const size_t shm = sizeof(unsigned) * (2 * g.T + 2) + rec * kPartChunk;
+        const size_t shm = sizeof(unsigned) * (2 * g.T + 2) + (rec + sizeof(unsigned)) * kPartChunk;
         int rc;
         if (B == 1) {
             if (vec) {
@@ -613,7 +663,7 @@ int launch_tiled_scatter(const uint32_t* t, const uint16_t* x, const uint16_t* y
     }
     phase_mark(st);
     {
-        const size_t shm = sizeof(unsigned) * (g.cap_voxels + g.cap_voxels / 2) +
+        const size_t shm = sizeof(unsigned) * 2 * g.cap_voxels +
                            sizeof(float2) * (static_cast<size_t>(1) << (g.tw_log2 + g.th_log2)) + sizeof(unsigned) * 32;
         int per_sm = static_cast<int>((220 * 1024) / (shm + 1024));
         if (per_sm < 1) per_sm = 1;
