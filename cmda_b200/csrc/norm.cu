@@ -88,6 +88,7 @@ struct NormParams {
     float mean, den; // dsec.py:91-93
     float clip, final_range;
     float pmin, pden, nmin, nden;
+    float p_of_zero, n_of_zero;   // the normalised positive / negative part of a voxel whose part is 0
 };
 
 __device__ __forceinline__ float zscore(float e, const NormParams& q) {
@@ -146,6 +147,10 @@ __device__ NormParams make_norm_params(const PartialStats* __restrict__ partials
     q.pden = __fadd_rn(__fsub_rn(pmax, pmin), 1e-8f);                                    // dsec.py:76
     q.nmin = nmin;
     q.nden = __fadd_rn(__fsub_rn(nmax, nmin), 1e-8f);
+    // a voxel with z >= 0 has negative part 0 and vice versa: that half of dsec.py:111 / 115 is
+    // the same value for every such voxel
+    q.p_of_zero = __fadd_rn(__fmul_rn(__fdiv_rn(__fsub_rn(0.0f, q.pmin), q.pden), final_range), 0.0f);
+    q.n_of_zero = __fadd_rn(__fmul_rn(__fdiv_rn(__fsub_rn(0.0f, q.nmin), q.nden), final_range), -final_range);
     return q;
 }
 
@@ -153,11 +158,13 @@ __device__ __forceinline__ float norm_one(float e, const NormParams& q, bool enf
     if (q.all_nan) return __int_as_float(0x7fc00000);
     const float z = zscore(e, q);
     if (enforce) {                                                                       // dsec.py:106-117
-        float p = __fdiv_rn(__fsub_rn(pos_part(z, q.clip), q.pmin), q.pden);
-        p = __fadd_rn(__fmul_rn(p, q.final_range), 0.0f);                                // * (r - 0) + 0
-        float n = __fdiv_rn(__fsub_rn(neg_part(z, q.clip), q.nmin), q.nden);
-        n = __fadd_rn(__fmul_rn(n, q.final_range), -q.final_range);                      // * (0 - (-r)) + (-r)
-        return __fadd_rn(p, n);
+        // only the part on z's side of zero differs from voxel to voxel; the other one is the
+        // per-grid constant computed in make_norm_params (same operations, same bits)
+        const bool neg = z < 0.0f;
+        const float part = neg ? neg_part(z, q.clip) : pos_part(z, q.clip);
+        float v = __fdiv_rn(__fsub_rn(part, neg ? q.nmin : q.pmin), neg ? q.nden : q.pden);
+        v = __fadd_rn(__fmul_rn(v, q.final_range), neg ? -q.final_range : 0.0f);         // * (r - 0) + 0 | * (0 - (-r)) + (-r)
+        return neg ? __fadd_rn(q.p_of_zero, v) : __fadd_rn(v, q.n_of_zero);
     }
     float c = fminf(fmaxf(z, -q.clip), q.clip);                                          // dsec.py:119
     c = __fmul_rn(c, q.final_range);
@@ -165,7 +172,7 @@ __device__ __forceinline__ float norm_one(float e, const NormParams& q, bool enf
 }
 
 template <bool VEC>
-__global__ void __launch_bounds__(kNormThreads)
+__global__ void __launch_bounds__(kNormThreads, 4)
 norm_apply_kernel(const float* raw, float* out, long long V,   // raw may alias out (in-place call)
                   const PartialStats* __restrict__ partials, WindowTable tab, float final_range, int enforce) {
     __shared__ NormParams s_q;

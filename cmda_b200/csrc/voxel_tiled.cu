@@ -28,9 +28,6 @@ namespace cmda {
 
 constexpr int kCountThreads = 256;
 constexpr int kCountGroupsPerThread = 16;                                  // 8 events per group
-constexpr int kPartThreads = 512;
-constexpr int kPartGroupsPerThread = 2;                                    // 16 events per thread
-constexpr int kPartChunk = kPartThreads * kPartGroupsPerThread * 8;        // 8192 events per CTA
 constexpr int kAccThreads = 512;
 constexpr int kItemRecords = 32768;    // records per work item (load-balance granularity of the accumulate pass)
 constexpr int kMaxTiles = 4096;
@@ -276,8 +273,57 @@ tile_scan_kernel(const unsigned* __restrict__ counts, TileGeom g, unsigned* __re
 }
 
 // ---- partition --------------------------------------------------------------------------------
+#ifndef CMDA_PART_THREADS
+#define CMDA_PART_THREADS 512
+#endif
+#ifndef CMDA_PART_GROUPS
+#define CMDA_PART_GROUPS 1
+#endif
+#ifndef CMDA_PART_MINBLOCKS
+#define CMDA_PART_MINBLOCKS 2
+#endif
+constexpr int kPartThreads = CMDA_PART_THREADS;
+constexpr int kPartGroupsPerThread = CMDA_PART_GROUPS;                     // 8 events per group
+constexpr int kPartChunk = kPartThreads * kPartGroupsPerThread * 8;        // events per CTA
+
+// 8 consecutive events of one window in registers (vector loads when aligned and interior).
+struct Ev8 {
+    uint4 x, y, t0, t1;
+    uint2 p;
+};
 template <bool HAS_T, bool VEC>
-__global__ void __launch_bounds__(kPartThreads, 2)
+__device__ __forceinline__ Ev8 load_ev8(const uint32_t* __restrict__ t, const uint16_t* __restrict__ x,
+                                        const uint16_t* __restrict__ y, const uint8_t* __restrict__ p, long long i0,
+                                        long long lo, long long hi) {
+    Ev8 r;
+    if (VEC && i0 >= lo && i0 + 8 <= hi) {
+        r.x = ldg_stream_u4(x + i0);
+        r.y = ldg_stream_u4(y + i0);
+        if (HAS_T) { r.t0 = ldg_stream_u4(t + i0); r.t1 = ldg_stream_u4(t + i0 + 4); }
+        else { r.t0 = make_uint4(0, 0, 0, 0); r.t1 = r.t0; }
+        r.p = ldg_stream_u2(p + i0);
+    } else {
+        unsigned vx[8], vy[8], tv[8];
+        unsigned long long pv = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const bool in = (i0 + j >= lo) && (i0 + j < hi);
+            vx[j] = in ? __ldg(x + i0 + j) : 0xffffu;       // 0xffff is outside any sensor: dropped
+            vy[j] = in ? __ldg(y + i0 + j) : 0xffffu;
+            tv[j] = (HAS_T && in) ? __ldg(t + i0 + j) : 0u;
+            if (in) pv |= static_cast<unsigned long long>(__ldg(p + i0 + j)) << (8 * j);
+        }
+        r.x = make_uint4(vx[0] | (vx[1] << 16), vx[2] | (vx[3] << 16), vx[4] | (vx[5] << 16), vx[6] | (vx[7] << 16));
+        r.y = make_uint4(vy[0] | (vy[1] << 16), vy[2] | (vy[3] << 16), vy[4] | (vy[5] << 16), vy[6] | (vy[7] << 16));
+        r.t0 = make_uint4(tv[0], tv[1], tv[2], tv[3]);
+        r.t1 = make_uint4(tv[4], tv[5], tv[6], tv[7]);
+        r.p = make_uint2(static_cast<unsigned>(pv), static_cast<unsigned>(pv >> 32));
+    }
+    return r;
+}
+
+template <bool HAS_T, bool VEC>
+__global__ void __launch_bounds__(kPartThreads, CMDA_PART_MINBLOCKS)
 tile_partition_kernel(const uint32_t* __restrict__ t, const uint16_t* __restrict__ x, const uint16_t* __restrict__ y,
                       const uint8_t* __restrict__ p, WindowTable tab, TiledTable tt, TileGeom g, int H, int W,
                       const unsigned* __restrict__ bucket_off, unsigned* __restrict__ cursor, void* __restrict__ records) {
@@ -294,25 +340,35 @@ tile_partition_kernel(const uint32_t* __restrict__ t, const uint16_t* __restrict
     const long long g0 = wd.start >> 3, g1 = (wd.end + 7) >> 3;
     const long long first = g0 + static_cast<long long>(blockIdx.x) * (kPartThreads * kPartGroupsPerThread);
     if (wd.end <= wd.start || first >= g1) return;
-    for (int k = threadIdx.x; k < g.T; k += kPartThreads) s_hist[k] = 0u;
-    __syncthreads();
 
-    const uint32_t t_first = HAS_T ? __ldg(t + wd.start) : 0u;
-    const unsigned tile_mask_x = (1u << g.tw_log2) - 1u, tile_mask_y = (1u << g.th_log2) - 1u;
-    XY8 xy[kPartGroupsPerThread];
-    unsigned slot[kPartGroupsPerThread][8];      // tile << 16 | rank   (0xffffffff: dropped)
+    // every load of the chunk is issued before anything waits on one
+    Ev8 ev[kPartGroupsPerThread];
 #pragma unroll
     for (int j = 0; j < kPartGroupsPerThread; ++j) {
         const long long grp = first + static_cast<long long>(j) * kPartThreads + threadIdx.x;
         if (grp < g1) {
-            xy[j] = load_xy8<VEC>(x, y, grp << 3, wd.start, wd.end);
+            ev[j] = load_ev8<HAS_T, VEC>(t, x, y, p, grp << 3, wd.start, wd.end);
         } else {
-            xy[j].x = make_uint4(~0u, ~0u, ~0u, ~0u);
-            xy[j].y = xy[j].x;
+            ev[j].x = make_uint4(~0u, ~0u, ~0u, ~0u);
+            ev[j].y = ev[j].x; ev[j].t0 = ev[j].x; ev[j].t1 = ev[j].x; ev[j].p = make_uint2(0u, 0u);
         }
+    }
+    const uint32_t t_first = HAS_T ? __ldg(t + wd.start) : 0u;
+    for (int k = threadIdx.x; k < g.T; k += kPartThreads) s_hist[k] = 0u;
+    __syncthreads();
+
+    const unsigned tile_mask_x = (1u << g.tw_log2) - 1u, tile_mask_y = (1u << g.th_log2) - 1u;
+    unsigned slot[kPartGroupsPerThread][8];      // tile << 16 | rank   (0xffffffff: dropped)
+    unsigned lxyp[kPartGroupsPerThread][8];      // the record's pixel / polarity word
+#pragma unroll
+    for (int j = 0; j < kPartGroupsPerThread; ++j) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const unsigned ex = u16_of(xy[j].x, e), ey = u16_of(xy[j].y, e);
+            const unsigned ex = u16_of(ev[j].x, e), ey = u16_of(ev[j].y, e);
+            // reference dsec.py:349 casts p to float32 and 2*p-1 follows; DSEC stores 0 / 1
+            const unsigned pol = ((e < 4 ? ev[j].p.x : ev[j].p.y) >> (8 * (e & 3))) & 0xffu;
+            const unsigned lx = ex & tile_mask_x, ly = ey & tile_mask_y;
+            lxyp[j][e] = HAS_T ? (lx | (ly << 8) | (pol << 16)) : (lx | (ly << 6) | ((pol & 15u) << 12));
             slot[j][e] = 0xffffffffu;
             if (ex < static_cast<unsigned>(W) && ey < static_cast<unsigned>(H)) {
                 const unsigned tile = (ey >> g.th_log2) * g.ntx + (ex >> g.tw_log2);
@@ -366,43 +422,19 @@ tile_partition_kernel(const uint32_t* __restrict__ t, const uint16_t* __restrict
     // stage the records sorted by tile
 #pragma unroll
     for (int j = 0; j < kPartGroupsPerThread; ++j) {
-        const long long grp = first + static_cast<long long>(j) * kPartThreads + threadIdx.x;
-        uint4 t0 = make_uint4(0, 0, 0, 0), t1 = t0;
-        uint2 pp = make_uint2(0, 0);
-        if (grp < g1) {
-            const long long i0 = grp << 3;
-            if (VEC && i0 >= wd.start && i0 + 8 <= wd.end) {
-                if (HAS_T) { t0 = ldg_stream_u4(t + i0); t1 = ldg_stream_u4(t + i0 + 4); }
-                pp = ldg_stream_u2(p + i0);
-            } else {
-                unsigned tv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                unsigned long long pv = 0;
-#pragma unroll
-                for (int e = 0; e < 8; ++e)
-                    if (i0 + e >= wd.start && i0 + e < wd.end) {
-                        if (HAS_T) tv[e] = __ldg(t + i0 + e);
-                        pv |= static_cast<unsigned long long>(__ldg(p + i0 + e)) << (8 * e);
-                    }
-                t0 = make_uint4(tv[0], tv[1], tv[2], tv[3]);
-                t1 = make_uint4(tv[4], tv[5], tv[6], tv[7]);
-                pp = make_uint2(static_cast<unsigned>(pv), static_cast<unsigned>(pv >> 32));
-            }
-        }
-        const unsigned tv[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+        const unsigned tv[8] = {ev[j].t0.x, ev[j].t0.y, ev[j].t0.z, ev[j].t0.w,
+                                ev[j].t1.x, ev[j].t1.y, ev[j].t1.z, ev[j].t1.w};
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const unsigned sl = slot[j][e];
             if (sl == 0xffffffffu) continue;
             const unsigned tile = sl >> 16, rank = sl & 0xffffu;
-            const unsigned lx = u16_of(xy[j].x, e) & tile_mask_x, ly = u16_of(xy[j].y, e) & tile_mask_y;
-            // reference dsec.py:349 casts p to float32 and 2*p-1 follows; DSEC stores 0 / 1
-            const unsigned pol = ((e < 4 ? pp.x : pp.y) >> (8 * (e & 3))) & 0xffu;
             Rec r;
             if constexpr (HAS_T) {
                 r.dt = tv[e] - t_first;
-                r.lxyp = lx | (ly << 8) | (pol << 16);
+                r.lxyp = lxyp[j][e];
             } else {
-                r = static_cast<Rec2>(lx | (ly << 6) | ((pol & 15u) << 12));
+                r = static_cast<Rec2>(lxyp[j][e]);
             }
             const unsigned pos = s_loff[tile] + rank;
             s_stage[pos] = r;
@@ -420,17 +452,28 @@ tile_partition_kernel(const uint32_t* __restrict__ t, const uint16_t* __restrict
 // ---- accumulate -------------------------------------------------------------------------------
 // One contribution into the shared-memory footprint: a native 32-bit ATOMS.ADD on the low
 // word; the value it returns tells whether this very addition carried (or borrowed) across
-// bit 32, and only then (about 1 contribution in 16) a second ATOMS updates the upper word.
-// (lo, hi) is therefore the exact 64-bit sum, like the RED.64 of mode GLOBAL.
-__device__ __forceinline__ void smem_accumulate(unsigned* __restrict__ lo, int* __restrict__ hi, unsigned v, int q) {
-    const unsigned old = atomicAdd(lo + v, static_cast<unsigned>(q));
-    const long long s = static_cast<long long>(static_cast<unsigned long long>(old)) + static_cast<long long>(q);
-    const int d = static_cast<int>(s >> 32);
-    if (d != 0) atomicAdd(hi + v, d);
+// bit 32, and only then (about 1 contribution in 16) a predicated RED updates the upper word.
+// (lo, hi) is therefore the exact 64-bit sum, like the RED.64 of mode GLOBAL.  Straight-line
+// PTX: the compiler would otherwise wrap each of the 8 corners in divergence regions.
+// `addr` is the shared-window byte address of the low word, XOFF selects the x + 1 neighbour,
+// `hi_off` the byte distance from the low to the high array.
+template <int XOFF>
+__device__ __forceinline__ void smem_accumulate_at(unsigned addr, unsigned hi_off, int q) {
+    unsigned old;
+    if constexpr (XOFF == 0) asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(q) : "memory");
+    else asm volatile("atom.shared.add.u32 %0, [%1+4], %2;" : "=r"(old) : "r"(addr), "r"(q) : "memory");
+    const unsigned nw = old + static_cast<unsigned>(q);
+    const int d = static_cast<int>(nw < old) + (q >> 31);      // carry out of the unsigned add, minus 1 for a negative addend
+    const unsigned haddr = addr + hi_off;
+    if constexpr (XOFF == 0)
+        asm volatile("{ .reg .pred p; setp.ne.s32 p, %1, 0; @p red.shared.add.s32 [%0], %1; }" ::"r"(haddr), "r"(d) : "memory");
+    else
+        asm volatile("{ .reg .pred p; setp.ne.s32 p, %1, 0; @p red.shared.add.s32 [%0+4], %1; }" ::"r"(haddr), "r"(d) : "memory");
 }
-__device__ __forceinline__ void smem_accumulate_w(unsigned* __restrict__ lo, int* __restrict__ hi, unsigned v, float w30) {
-    const int q = __float2int_rn(w30);      // w30 = weight * 2^30, |w30| <= 2^30
-    if (q != 0) smem_accumulate(lo, hi, v, q);
+__device__ __forceinline__ void smem_accumulate(unsigned* __restrict__ lo, int* __restrict__ hi, unsigned v, int q) {
+    const unsigned addr = static_cast<unsigned>(__cvta_generic_to_shared(lo + v));
+    const unsigned hi_off = static_cast<unsigned>(__cvta_generic_to_shared(hi)) - static_cast<unsigned>(__cvta_generic_to_shared(lo));
+    smem_accumulate_at<0>(addr, hi_off, q);
 }
 
 struct AccRecord {
@@ -469,6 +512,8 @@ tile_accumulate_kernel(const void* __restrict__ records, const uint32_t* __restr
     if (threadIdx.x < 32) s_bins[threadIdx.x] = 0u;
     const unsigned n_items = queue[0];
     const size_t V = static_cast<size_t>(B) * H * W;
+    const unsigned lo_base = static_cast<unsigned>(__cvta_generic_to_shared(s_lo));
+    const unsigned hi_off = cap * 4u;
 
     for (;;) {
         __syncthreads();
@@ -530,22 +575,24 @@ tile_accumulate_kernel(const void* __restrict__ records, const uint32_t* __restr
                 const float w10 = __fmul_rn(vx1, wy0), w11 = __fmul_rn(vx1, wy1);
                 const unsigned v = (static_cast<unsigned>(t0) * bh + static_cast<unsigned>(y0 - bb.y)) * bw +
                                    static_cast<unsigned>(x0 - bb.x);
+                const unsigned a00 = lo_base + v * 4u, a01 = a00 + bw * 4u;     // (y0, t0), (y0 + 1, t0)
                 if constexpr (HAS_T) {
                     const float wt0 = tent(t0, tn), wt1 = tent(t0 + 1, tn);
-                    smem_accumulate_w(s_lo, s_hi, v, __fmul_rn(w00, wt0));
-                    smem_accumulate_w(s_lo, s_hi, v + plane, __fmul_rn(w00, wt1));
-                    smem_accumulate_w(s_lo, s_hi, v + bw, __fmul_rn(w01, wt0));
-                    smem_accumulate_w(s_lo, s_hi, v + bw + plane, __fmul_rn(w01, wt1));
-                    smem_accumulate_w(s_lo, s_hi, v + 1, __fmul_rn(w10, wt0));
-                    smem_accumulate_w(s_lo, s_hi, v + 1 + plane, __fmul_rn(w10, wt1));
-                    smem_accumulate_w(s_lo, s_hi, v + bw + 1, __fmul_rn(w11, wt0));
-                    smem_accumulate_w(s_lo, s_hi, v + bw + 1 + plane, __fmul_rn(w11, wt1));
+                    const unsigned a10 = a00 + plane * 4u, a11 = a01 + plane * 4u;   // bin t0 + 1
+                    smem_accumulate_at<0>(a00, hi_off, __float2int_rn(__fmul_rn(w00, wt0)));
+                    smem_accumulate_at<0>(a10, hi_off, __float2int_rn(__fmul_rn(w00, wt1)));
+                    smem_accumulate_at<0>(a01, hi_off, __float2int_rn(__fmul_rn(w01, wt0)));
+                    smem_accumulate_at<0>(a11, hi_off, __float2int_rn(__fmul_rn(w01, wt1)));
+                    smem_accumulate_at<4>(a00, hi_off, __float2int_rn(__fmul_rn(w10, wt0)));
+                    smem_accumulate_at<4>(a10, hi_off, __float2int_rn(__fmul_rn(w10, wt1)));
+                    smem_accumulate_at<4>(a01, hi_off, __float2int_rn(__fmul_rn(w11, wt0)));
+                    smem_accumulate_at<4>(a11, hi_off, __float2int_rn(__fmul_rn(w11, wt1)));
                 } else {
                     // B == 1: t_norm = 0, the only temporal corner is bin 0 with weight 1
-                    smem_accumulate_w(s_lo, s_hi, v, w00);
-                    smem_accumulate_w(s_lo, s_hi, v + bw, w01);
-                    smem_accumulate_w(s_lo, s_hi, v + 1, w10);
-                    smem_accumulate_w(s_lo, s_hi, v + bw + 1, w11);
+                    smem_accumulate_at<0>(a00, hi_off, __float2int_rn(w00));
+                    smem_accumulate_at<0>(a01, hi_off, __float2int_rn(w01));
+                    smem_accumulate_at<4>(a00, hi_off, __float2int_rn(w10));
+                    smem_accumulate_at<4>(a01, hi_off, __float2int_rn(w11));
                 }
             } else {
                 // border events (some corner outside the grid) and over-capacity footprints
