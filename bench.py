@@ -289,6 +289,10 @@ def run_gpu(args, rank, local_rank, world):
         if resolved == _lib.VOXEL_GLOBAL:
             names = ["memset(int64 grid)", "voxel_scatter_global_kernel", "convert_stats_kernel", "norm_apply_kernel"]
             launches_per_step = 3
+        elif resolved == _lib.VOXEL_FACTORED:
+            names = ["memset(sensor grid)", "rectify_cell_{count,scan,fill} kernels", "sensor_accumulate_kernel",
+                     "rectify_gather_kernel", "norm_apply_kernel"]
+            launches_per_step = 6
         else:
             names = ["memset(int64 grid)", "tile_bbox+tile_count+tile_scan kernels", "tile_partition_kernel",
                      "tile_accumulate_kernel", "convert_stats_kernel", "norm_apply_kernel"]
@@ -321,7 +325,7 @@ def run_gpu(args, rank, local_rank, world):
             "metric": "voxelized_events_per_s", "value": value, "unit": "Mevents/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(args, world), resolved_mode=["global", "tiled", "auto", "exact"][resolved]),
+            "config": dict(workload_config(args, world), resolved_mode=_lib.VOXEL_MODE_NAMES[resolved]),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mevents/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "steps": e2e_steps, "matches_device_path": same},
@@ -341,7 +345,7 @@ def main():
     ap.add_argument("--impl", default="cmda_b200", choices=["cmda_b200", "reference"])
     ap.add_argument("--bins", type=int, default=5)
     ap.add_argument("--events", type=int, default=EVENTS_PER_WINDOW)
-    ap.add_argument("--mode", default="auto", choices=["auto", "global", "tiled"])
+    ap.add_argument("--mode", default="auto", choices=["auto", "global", "tiled", "factored"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cmda_b200" else args.warmup

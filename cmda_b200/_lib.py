@@ -18,8 +18,10 @@ LIB_PATH = os.path.join(_HERE, "libcmda_b200.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 OK = 0
-VOXEL_GLOBAL, VOXEL_TILED, VOXEL_AUTO, VOXEL_EXACT = 0, 1, 2, 3
-VOXEL_MODES = {"global": VOXEL_GLOBAL, "tiled": VOXEL_TILED, "auto": VOXEL_AUTO, "exact": VOXEL_EXACT}
+VOXEL_GLOBAL, VOXEL_TILED, VOXEL_AUTO, VOXEL_EXACT, VOXEL_FACTORED = 0, 1, 2, 3, 4
+VOXEL_MODES = {"global": VOXEL_GLOBAL, "tiled": VOXEL_TILED, "auto": VOXEL_AUTO, "exact": VOXEL_EXACT,
+               "factored": VOXEL_FACTORED}
+VOXEL_MODE_NAMES = {v: k for k, v in VOXEL_MODES.items()}
 DIRECTIONS = {"rightdown": 0, "rightup": 1, "leftdown": 2, "leftup": 3, "all": 4}
 
 _vp = ctypes.c_void_p

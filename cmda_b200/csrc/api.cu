@@ -25,6 +25,10 @@ int launch_pair(const uint8_t*, const uint8_t*, int, int, int, const float*, flo
 // TILED mode (voxel_tiled.cu)
 size_t tiled_workspace_bytes(int64_t total_events, int S, int H, int W, int B);
 int tiled_supported(int H, int W, int B);
+int factored_supported(int H, int W, int B);
+size_t factored_index_bytes(int group, int H, int W);
+int launch_factored(const uint32_t*, const uint16_t*, const uint16_t*, const uint8_t*, const WindowTable&, int, long long,
+                    const float*, int, int, int, void*, int64_t*, float*, PartialStats*, void*, size_t, cudaStream_t);
 int launch_tiled_scatter(const uint32_t*, const uint16_t*, const uint16_t*, const uint8_t*, const WindowTable&, int,
                          const float*, int, int, int, long long*, int64_t*, void*, size_t, cudaStream_t);
 
@@ -33,15 +37,9 @@ static size_t acc_bytes(int S, int H, int W, int B) {
     return align_up(sizeof(long long) * static_cast<size_t>(S) * B * H * W, 256);
 }
 
-// batches smaller than this (events per window, on average) take the GLOBAL path under
-// CMDA_VOXEL_AUTO: the count / partition / accumulate passes have a fixed cost that only pays
-// off once the L2 atomics of the GLOBAL path dominate
-constexpr long long kAutoTiledMinEvents = 200000;
-
 static int resolve_mode(int mode, long long total_events, int S, int H, int W, int B) {
-    if (mode == CMDA_VOXEL_AUTO)
-        return (tiled_supported(H, W, B) && total_events >= kAutoTiledMinEvents * (S > 0 ? S : 1)) ? CMDA_VOXEL_TILED
-                                                                                                  : CMDA_VOXEL_GLOBAL;
+    (void)total_events; (void)S;
+    if (mode == CMDA_VOXEL_AUTO) return factored_supported(H, W, B) ? CMDA_VOXEL_FACTORED : CMDA_VOXEL_GLOBAL;
     return mode;
 }
 
@@ -111,7 +109,7 @@ int cmda_images_to_events_index(const uint32_t* d_t, int64_t n, const int64_t* d
 
 int cmda_events_vg_resolved_mode(int64_t total_events, int S, int H, int W, int B, int mode) {
     if (S <= 0 || H <= 0 || W <= 0 || B <= 0 || total_events < 0) return CMDA_ERR_BAD_ARG;
-    if (mode < CMDA_VOXEL_GLOBAL || mode > CMDA_VOXEL_EXACT) return CMDA_ERR_BAD_ARG;
+    if (mode < CMDA_VOXEL_GLOBAL || mode > CMDA_VOXEL_FACTORED) return CMDA_ERR_BAD_ARG;
     return resolve_mode(mode, total_events, S, H, W, B);
 }
 
@@ -119,7 +117,9 @@ size_t cmda_events_vg_workspace_bytes(int64_t total_events, int S, int H, int W,
     if (S <= 0 || H <= 0 || W <= 0 || B <= 0 || total_events < 0) return 0;
     const int group = S < kMaxWindows ? S : kMaxWindows;
     size_t need = stats_bytes(S) + acc_bytes(group, H, W, B);       // both paths sum into the int64 grid
-    if (mode != CMDA_VOXEL_GLOBAL && tiled_supported(H, W, B)) need += tiled_workspace_bytes(total_events, S, H, W, B);
+    if (mode == CMDA_VOXEL_TILED && tiled_supported(H, W, B)) need += tiled_workspace_bytes(total_events, S, H, W, B);
+    if ((mode == CMDA_VOXEL_FACTORED || mode == CMDA_VOXEL_AUTO) && factored_supported(H, W, B))
+        need += factored_index_bytes(group, H, W);
     return need + 256;
 }
 
@@ -132,7 +132,7 @@ int cmda_events_vg_batch(const uint32_t* d_t, const uint16_t* d_x, const uint16_
     if (S == 0) return CMDA_OK;
     if (!d_t || !d_x || !d_y || !d_p || !h_win_start || !h_win_end || !d_out || !d_workspace) return CMDA_ERR_BAD_ARG;
     if (normalize && !h_clip) return CMDA_ERR_BAD_ARG;
-    if (mode < CMDA_VOXEL_GLOBAL || mode > CMDA_VOXEL_EXACT) return CMDA_ERR_BAD_ARG;
+    if (mode < CMDA_VOXEL_GLOBAL || mode > CMDA_VOXEL_FACTORED) return CMDA_ERR_BAD_ARG;
     if (reinterpret_cast<uintptr_t>(d_workspace) & 255) return CMDA_ERR_WORKSPACE;
     long long total = 0;
     for (int s = 0; s < S; ++s) {
@@ -144,6 +144,7 @@ int cmda_events_vg_batch(const uint32_t* d_t, const uint16_t* d_x, const uint16_
     if (workspace_bytes < cmda_events_vg_workspace_bytes(total, S, H, W, B, mode)) return CMDA_ERR_WORKSPACE;
     const int use_mode = resolve_mode(mode, total, S, H, W, B);
     if (use_mode == CMDA_VOXEL_TILED && !tiled_supported(H, W, B)) return CMDA_ERR_UNSUPPORTED;
+    if (use_mode == CMDA_VOXEL_FACTORED && !factored_supported(H, W, B)) return CMDA_ERR_UNSUPPORTED;
     if (use_mode == CMDA_VOXEL_EXACT) return CMDA_ERR_UNSUPPORTED;  // TODO exact-order mode
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long V = static_cast<long long>(B) * H * W;
@@ -174,6 +175,19 @@ int cmda_events_vg_batch(const uint32_t* d_t, const uint16_t* d_x, const uint16_
         int rc;
         phase_mark(st);
         long long* acc = reinterpret_cast<long long*>(scratch);
+        if (use_mode == CMDA_VOXEL_FACTORED) {
+            const size_t ab = acc_bytes(sn, H, W, B);
+            rc = launch_factored(d_t, d_x, d_y, d_p, tab, sn, max_events, d_rectify_map, H, W, B, acc, bins_g, raw_g,
+                                 part_g, scratch + ab, scratch_bytes - ab, st);   // marks: memset | index | accumulate
+            if (rc != CMDA_OK) return rc;
+            phase_mark(st);
+            if (normalize) {
+                rc = launch_norm_apply(raw_g, out_g, sn, V, part_g, tab, final_range, enforce_no_events_zero, st);
+                if (rc != CMDA_OK) return rc;
+                phase_mark(st);
+            }
+            continue;
+        }
         CMDA_CUDA_TRY(cudaMemsetAsync(acc, 0, sizeof(long long) * sn * V, st));
         phase_mark(st);
         if (use_mode == CMDA_VOXEL_TILED) {
@@ -202,12 +216,12 @@ int cmda_voxel_grid_f32(const float* d_time, const float* d_x, const float* d_y,
                         int mode, void* stream) {
     if (n < 0 || H <= 0 || W <= 0 || B <= 0 || !d_grid || !d_workspace) return CMDA_ERR_BAD_ARG;
     if (n > 0 && (!d_time || !d_x || !d_y || !d_pol)) return CMDA_ERR_BAD_ARG;
-    if (mode < CMDA_VOXEL_GLOBAL || mode > CMDA_VOXEL_EXACT) return CMDA_ERR_BAD_ARG;
+    if (mode < CMDA_VOXEL_GLOBAL || mode > CMDA_VOXEL_FACTORED) return CMDA_ERR_BAD_ARG;
     if (reinterpret_cast<uintptr_t>(d_workspace) & 255) return CMDA_ERR_WORKSPACE;
     if (workspace_bytes < cmda_events_vg_workspace_bytes(n, 1, H, W, B, mode)) return CMDA_ERR_WORKSPACE;
     // float32 events are already rectified: there is no map gather to tile, so this entry point
     // runs the GLOBAL scatter (AUTO resolves to it); TILED / EXACT are refused explicitly
-    if (mode == CMDA_VOXEL_TILED || mode == CMDA_VOXEL_EXACT) return CMDA_ERR_UNSUPPORTED;
+    if (mode == CMDA_VOXEL_TILED || mode == CMDA_VOXEL_EXACT || mode == CMDA_VOXEL_FACTORED) return CMDA_ERR_UNSUPPORTED;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long V = static_cast<long long>(B) * H * W;
     char* ws = static_cast<char*>(d_workspace);

@@ -38,17 +38,24 @@ enum {
 };
 
 /* Accumulation modes of the voxel scatter.  All are deterministic (bit-reproducible).
- * GLOBAL and TILED quantise each float32 contribution to 2^-30 and sum 64-bit integers,
- * which is order independent: they are bit-identical to each other and closer to the
- * exact sum than the reference's float32 accumulation.  EXACT performs the reference's
- * own float32 additions in the reference's own order (corner pass major, event index
- * minor: dsec.py:47-58), so its raw grid is BIT-IDENTICAL to the single-thread reference,
- * including the rounding residue the reference leaves where ON/OFF events cancel. */
+ * GLOBAL and TILED evaluate the reference's float32 corner weight of every event
+ * (dsec.py:51-52, bit-identical per contribution), quantise it to 2^-30 and sum 64-bit
+ * integers, which is order independent: they are bit-identical to each other and closer to
+ * the exact sum than the reference's float32 accumulation.
+ * FACTORED uses that rectify_map is a function of the raw pixel only: it sums the temporal
+ * weights of each raw pixel exactly (one 64-bit RED per EVENT, no map gather) and multiplies
+ * by the pixel's four spatial weights once per pixel (gather through an inverse index of the
+ * map, no atomics).  Each contribution differs from the reference's by at most one float32
+ * rounding (2^-24 relative); for B == 1 it is the exact sum of the reference's weights.
+ * Capacity: fewer than 2^19 events of net polarity per (raw pixel, temporal bin, window).
+ * EXACT performs the reference's own float32 additions in the reference's own order
+ * (corner pass major, event index minor: dsec.py:47-58). */
 enum {
-    CMDA_VOXEL_GLOBAL = 0, /* one 64-bit integer RED per corner into an L2-resident grid   */
-    CMDA_VOXEL_TILED = 1,  /* chunk-local band partition + shared-memory band accumulation */
-    CMDA_VOXEL_AUTO = 2,   /* TILED for large windows, GLOBAL for small ones                */
-    CMDA_VOXEL_EXACT = 3   /* stable cell sort + ordered float32 accumulation               */
+    CMDA_VOXEL_GLOBAL = 0,   /* one 64-bit integer RED per corner into an L2-resident grid     */
+    CMDA_VOXEL_TILED = 1,    /* raw-tile multisplit + shared-memory fixed-point accumulation   */
+    CMDA_VOXEL_AUTO = 2,     /* FACTORED where it applies (raw DSEC events), else GLOBAL       */
+    CMDA_VOXEL_EXACT = 3,    /* stable cell sort + ordered float32 accumulation (not built yet) */
+    CMDA_VOXEL_FACTORED = 4  /* sensor-space temporal accumulation + per-pixel rectify gather  */
 };
 
 /* Directions of the shift-pair generator (reference mmseg/datasets/utils.py:128-151). */
@@ -69,8 +76,9 @@ int cmda_last_cuda_error(void);
  * of n cudaEvent_t (created with cmda_event_create) to the CALLING THREAD; every phase
  * boundary of the following cmda_events_vg_batch calls records the next event of the list
  * on the call's stream (GLOBAL: start | memset | scatter | convert+stats | apply;
- * TILED: start | partition | band accumulate | apply).  detach returns how many events were
- * recorded.  Off by default. */
+ * TILED: start | memset | bbox+count+scan | partition | accumulate | convert+stats | apply;
+ * FACTORED: start | memset | inverse index | sensor accumulate | rectify gather+stats | apply).
+ * detach returns how many events were recorded.  Off by default. */
 int cmda_profiler_attach(void* const* h_events, int n);
 int cmda_profiler_detach(void);
 void* cmda_event_create(void);

@@ -24,7 +24,7 @@ ISR = golden_io.load("isr")
 IC = golden_io.load("image_change")
 INDEX = golden_io.load("index")
 
-MODES = ["global", "tiled", "exact"]
+MODES = ["global", "tiled", "factored", "exact"]
 
 
 @pytest.fixture(scope="module")
@@ -275,11 +275,46 @@ def test_events_vg_batch_vs_c_oracle(cm, mode, bins, n, skew):
         # of each contribution plus one float32 rounding -- tighter than the reference itself
         truth, abs_w, n_contrib = O.voxel_grid_f64(tf, xf, yf, pf, W, H, bins, return_aux=True)
         err = np.abs(raw[s].cpu().numpy().astype(np.float64) - truth)
-        if mode != "exact":
+        if mode == "factored":
+            # temporal weights are summed exactly and multiplied by the spatial weight once per pixel: each
+            # contribution is within one float32 rounding (2^-24 relative) of the reference's weight
+            assert np.all(err <= 2.0 ** -23 * abs_w + n_contrib * 2.0 ** -31 + 1.2e-7 * np.abs(truth))
+            if bins == 1:   # wt == 1: the exact sum of the reference's float32 weights, rounded once
+                assert np.all(err <= n_contrib * 2.0 ** -31 + 1.2e-7 * np.abs(truth))
+        elif mode != "exact":
             assert np.all(err <= n_contrib * 2.0 ** -31 + 1.2e-7 * np.abs(truth))
         assert_raw_close(raw[s], ref_raw[s], abs_w, n_contrib)
         clip = O.default_clip_range(fins[s], starts[s])
         check_normalised(out[s], raw[s], ref[s], ref_raw[s], clip, exact=(mode == "exact"))
+
+
+def test_events_vg_modes_agree(cm):
+    """GLOBAL and TILED sum the same quantised weights exactly -> bit-identical raw grids; FACTORED
+    regroups the sum per raw pixel -> within its stated bound of them; every mode is bit-reproducible
+    run to run; AUTO resolves to FACTORED for raw DSEC events."""
+    from cmda_b200 import synth
+    H, W, n = 480, 640, 400_000
+    t, x, y, p = synth.make_events(n, H, W, seed=synth.seed_for(1, 42), skew=0.2)
+    rmaps = np.stack([synth.make_rectify_map(H, W, seed=5), synth.make_rectify_map(H, W, seed=6, k1=0.03)])
+    store = cm.EventStore(t, x, y, p, rmaps, height=H, width=W, device="cuda:0")
+    starts, fins, mids = [0, 1000, 7], [n - 1, 250_000, 120_000], [0, 1, 0]
+    for bins in (1, 3, 5):
+        g = cm.events_vg_batch(store, starts, fins, bins, map_ids=mids, mode="global", normalize=False)
+        tl = cm.events_vg_batch(store, starts, fins, bins, map_ids=mids, mode="tiled", normalize=False)
+        fa = cm.events_vg_batch(store, starts, fins, bins, map_ids=mids, mode="factored", normalize=False)
+        au = cm.events_vg_batch(store, starts, fins, bins, map_ids=mids, mode="auto", normalize=False)
+        assert np.array_equal(bits(g), bits(tl)), "GLOBAL and TILED must be bit-identical"
+        assert np.array_equal(bits(fa), bits(au)), "AUTO resolves to FACTORED"
+        for mode, first in (("tiled", tl), ("factored", fa)):
+            again = cm.events_vg_batch(store, starts, fins, bins, map_ids=mids, mode=mode, normalize=False)
+            assert np.array_equal(bits(first), bits(again)), f"{mode}: run-to-run bit reproducibility"
+        for s in range(len(starts)):
+            sl = slice(starts[s], fins[s] + 1)
+            tf, xf, yf, pf = O.rectify_events(t[sl], x[sl], y[sl], p[sl], rmaps[mids[s]])
+            _, abs_w, n_contrib = O.voxel_grid_f64(tf, xf, yf, pf, W, H, bins, return_aux=True)
+            d = np.abs(fa[s].cpu().numpy().astype(np.float64) - g[s].cpu().numpy().astype(np.float64))
+            assert np.all(d <= 2.0 ** -22 * abs_w + n_contrib * 2.0 ** -30 + 1e-12)
+            assert np.all(fa[s].cpu().numpy()[n_contrib == 0] == 0.0)
 
 
 def test_events_vg_bad_windows(cm):
