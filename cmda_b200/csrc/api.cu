@@ -26,7 +26,8 @@ int launch_pair(const uint8_t*, const uint8_t*, int, int, int, const float*, flo
 size_t tiled_workspace_bytes(int64_t total_events, int S, int H, int W, int B);
 int tiled_supported(int H, int W, int B);
 int factored_supported(int H, int W, int B);
-size_t factored_index_bytes(int group, int H, int W);
+size_t factored_scratch_bytes(int group, int H, int W);
+int factored_max_maps(void);
 int launch_factored(const uint32_t*, const uint16_t*, const uint16_t*, const uint8_t*, const WindowTable&, int, long long,
                     const float*, int, int, int, void*, int64_t*, float*, PartialStats*, void*, size_t, cudaStream_t);
 int launch_tiled_scatter(const uint32_t*, const uint16_t*, const uint16_t*, const uint8_t*, const WindowTable&, int,
@@ -119,7 +120,7 @@ size_t cmda_events_vg_workspace_bytes(int64_t total_events, int S, int H, int W,
     size_t need = stats_bytes(S) + acc_bytes(group, H, W, B);       // both paths sum into the int64 grid
     if (mode == CMDA_VOXEL_TILED && tiled_supported(H, W, B)) need += tiled_workspace_bytes(total_events, S, H, W, B);
     if ((mode == CMDA_VOXEL_FACTORED || mode == CMDA_VOXEL_AUTO) && factored_supported(H, W, B))
-        need += factored_index_bytes(group, H, W);
+        need += factored_scratch_bytes(group, H, W);
     return need + 256;
 }
 
@@ -155,8 +156,23 @@ int cmda_events_vg_batch(const uint32_t* d_t, const uint16_t* d_x, const uint16_
     const size_t scratch_bytes = workspace_bytes - stats_bytes(S);
     if (d_bin_counts) CMDA_CUDA_TRY(cudaMemsetAsync(d_bin_counts, 0, sizeof(int64_t) * S * B, st));
 
-    for (int s0 = 0; s0 < S; s0 += kMaxWindows) {
-        const int sn = (S - s0) < kMaxWindows ? (S - s0) : kMaxWindows;
+    for (int s0 = 0, sn = 0; s0 < S; s0 += sn) {
+        // a launch group: at most kMaxWindows windows and, for FACTORED, at most factored_max_maps()
+        // distinct rectify maps (one inverse index each)
+        sn = (S - s0) < kMaxWindows ? (S - s0) : kMaxWindows;
+        if (use_mode == CMDA_VOXEL_FACTORED && h_map_id && d_rectify_map) {
+            int ids[kMaxWindows], n_ids = 0, k = 0;
+            for (; k < sn; ++k) {
+                const int id = h_map_id[s0 + k];
+                int j = 0;
+                while (j < n_ids && ids[j] != id) ++j;
+                if (j == n_ids) {
+                    if (n_ids == factored_max_maps()) break;
+                    ids[n_ids++] = id;
+                }
+            }
+            sn = k;
+        }
         WindowTable tab{};
         long long max_events = 0;
         for (int k = 0; k < sn; ++k) {

@@ -37,8 +37,20 @@
 
 namespace cmda {
 
-constexpr int kSensThreads = 256;
-constexpr int kSensGroupsPerThread = 4;                 // 8 events per group -> 8192 events per CTA
+#ifndef CMDA_SENS_THREADS
+#define CMDA_SENS_THREADS 256
+#endif
+#ifndef CMDA_SENS_GROUPS
+#define CMDA_SENS_GROUPS 4
+#endif
+#ifndef CMDA_SENS_MINBLOCKS
+#define CMDA_SENS_MINBLOCKS 4
+#endif
+#ifndef CMDA_SENS_PREFETCH
+#define CMDA_SENS_PREFETCH 1
+#endif
+constexpr int kSensThreads = CMDA_SENS_THREADS;
+constexpr int kSensGroupsPerThread = CMDA_SENS_GROUPS;  // 8 events per group
 constexpr int kFracBits = 24;                           // f = t_norm - t0 as 2^-24 fixed point
 constexpr int kCountShift = 44;                         // event count lives above bit 44
 constexpr int kGatherThreads = 256;
@@ -50,8 +62,44 @@ struct MapSlots {
 };
 
 // ---- stage A ----------------------------------------------------------------------------------
+struct SensEv8 {
+    uint4 x, y, t0, t1;
+    uint2 p;
+};
 template <bool HAS_T, bool VEC>
-__global__ void __launch_bounds__(kSensThreads)
+__device__ __forceinline__ SensEv8 sens_load8(const uint32_t* __restrict__ t, const uint16_t* __restrict__ x,
+                                              const uint16_t* __restrict__ y, const uint8_t* __restrict__ p, long long i0,
+                                              long long lo, long long hi) {
+    SensEv8 r;
+    r.t0 = make_uint4(0, 0, 0, 0);
+    r.t1 = r.t0;
+    if (VEC && i0 >= lo && i0 + 8 <= hi) {
+        r.x = ldg_stream_u4(x + i0);
+        r.y = ldg_stream_u4(y + i0);
+        if (HAS_T) { r.t0 = ldg_stream_u4(t + i0); r.t1 = ldg_stream_u4(t + i0 + 4); }
+        r.p = ldg_stream_u2(p + i0);
+    } else {
+        unsigned ax[8], ay[8], at[8];
+        unsigned long long ap = 0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const bool in = (i0 + e >= lo) && (i0 + e < hi);
+            ax[e] = in ? __ldg(x + i0 + e) : 0xffffu;       // 0xffff is outside any sensor: dropped
+            ay[e] = in ? __ldg(y + i0 + e) : 0xffffu;
+            at[e] = (HAS_T && in) ? __ldg(t + i0 + e) : 0u;
+            if (in) ap |= static_cast<unsigned long long>(__ldg(p + i0 + e)) << (8 * e);
+        }
+        r.x = make_uint4(ax[0] | (ax[1] << 16), ax[2] | (ax[3] << 16), ax[4] | (ax[5] << 16), ax[6] | (ax[7] << 16));
+        r.y = make_uint4(ay[0] | (ay[1] << 16), ay[2] | (ay[3] << 16), ay[4] | (ay[5] << 16), ay[6] | (ay[7] << 16));
+        r.t0 = make_uint4(at[0], at[1], at[2], at[3]);
+        r.t1 = make_uint4(at[4], at[5], at[6], at[7]);
+        r.p = make_uint2(static_cast<unsigned>(ap), static_cast<unsigned>(ap >> 32));
+    }
+    return r;
+}
+
+template <bool HAS_T, bool VEC>
+__global__ void __launch_bounds__(kSensThreads, CMDA_SENS_MINBLOCKS)
 sensor_accumulate_kernel(const uint32_t* __restrict__ t, const uint16_t* __restrict__ x, const uint16_t* __restrict__ y,
                          const uint8_t* __restrict__ p, WindowTable tab, int H, int W, int B, void* __restrict__ R,
                          unsigned long long* __restrict__ bin_counts) {
@@ -74,49 +122,30 @@ sensor_accumulate_kernel(const uint32_t* __restrict__ t, const uint16_t* __restr
     unsigned long long* R64 = reinterpret_cast<unsigned long long*>(R) + static_cast<size_t>(s) * B * plane;
     int* R32 = reinterpret_cast<int*>(R) + static_cast<size_t>(s) * plane;
     unsigned local_bins = 0;   // B == 1: every in-sensor event falls into bin 0
-#pragma unroll
-    for (int j = 0; j < kSensGroupsPerThread; ++j) {
-        const long long grp = first + static_cast<long long>(j) * kSensThreads + threadIdx.x;
-        if (grp >= g1) break;
-        const long long i0 = grp << 3;
-        uint4 vx, vy, t0v = make_uint4(0, 0, 0, 0), t1v = t0v;
-        uint2 vp;
-        if (VEC && i0 >= wd.start && i0 + 8 <= wd.end) {
-            vx = ldg_stream_u4(x + i0);
-            vy = ldg_stream_u4(y + i0);
-            if (HAS_T) { t0v = ldg_stream_u4(t + i0); t1v = ldg_stream_u4(t + i0 + 4); }
-            vp = ldg_stream_u2(p + i0);
-        } else {
-            unsigned ax[8], ay[8], at[8];
-            unsigned long long ap = 0;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const bool in = (i0 + e >= wd.start) && (i0 + e < wd.end);
-                ax[e] = in ? __ldg(x + i0 + e) : 0xffffu;       // 0xffff is outside any sensor: dropped
-                ay[e] = in ? __ldg(y + i0 + e) : 0xffffu;
-                at[e] = (HAS_T && in) ? __ldg(t + i0 + e) : 0u;
-                if (in) ap |= static_cast<unsigned long long>(__ldg(p + i0 + e)) << (8 * e);
-            }
-            vx = make_uint4(ax[0] | (ax[1] << 16), ax[2] | (ax[3] << 16), ax[4] | (ax[5] << 16), ax[6] | (ax[7] << 16));
-            vy = make_uint4(ay[0] | (ay[1] << 16), ay[2] | (ay[3] << 16), ay[4] | (ay[5] << 16), ay[6] | (ay[7] << 16));
-            t0v = make_uint4(at[0], at[1], at[2], at[3]);
-            t1v = make_uint4(at[4], at[5], at[6], at[7]);
-            vp = make_uint2(static_cast<unsigned>(ap), static_cast<unsigned>(ap >> 32));
-        }
-        const unsigned xs[4] = {vx.x, vx.y, vx.z, vx.w}, ys[4] = {vy.x, vy.y, vy.z, vy.w};
-        const unsigned ts[8] = {t0v.x, t0v.y, t0v.z, t0v.w, t1v.x, t1v.y, t1v.z, t1v.w};
+
+    long long grp = first + threadIdx.x;
+    SensEv8 cur{};
+    if (grp < g1) cur = sens_load8<HAS_T, VEC>(t, x, y, p, grp << 3, wd.start, wd.end);
+#pragma unroll 1
+    for (int j = 0; j < kSensGroupsPerThread && grp < g1; ++j) {
+        // the next group's loads are in flight while this group's atomics are issued
+        const long long nxt_grp = grp + kSensThreads;
+        SensEv8 nxt{};
+        if (CMDA_SENS_PREFETCH && j + 1 < kSensGroupsPerThread && nxt_grp < g1) nxt = sens_load8<HAS_T, VEC>(t, x, y, p, nxt_grp << 3, wd.start, wd.end);
+        const unsigned xs[4] = {cur.x.x, cur.x.y, cur.x.z, cur.x.w}, ys[4] = {cur.y.x, cur.y.y, cur.y.z, cur.y.w};
+        const unsigned ts[8] = {cur.t0.x, cur.t0.y, cur.t0.z, cur.t0.w, cur.t1.x, cur.t1.y, cur.t1.z, cur.t1.w};
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const unsigned ex = (e & 1) ? (xs[e >> 1] >> 16) : (xs[e >> 1] & 0xffffu);
             const unsigned ey = (e & 1) ? (ys[e >> 1] >> 16) : (ys[e >> 1] & 0xffffu);
             if (ex >= static_cast<unsigned>(W) || ey >= static_cast<unsigned>(H)) continue;
-            const int pol = static_cast<int>(((e < 4 ? vp.x : vp.y) >> (8 * (e & 3))) & 0xffu);
+            const int pol = static_cast<int>(((e < 4 ? cur.p.x : cur.p.y) >> (8 * (e & 3))) & 0xffu);
             const int value = 2 * pol - 1;                                     // dsec.py:45 on the uint8 polarity
-            const size_t pix = static_cast<size_t>(ey) * W + ex;
+            const unsigned pix = ey * static_cast<unsigned>(W) + ex;
             if constexpr (HAS_T) {
                 const float tn = __fmul_rn(rw.cm1, __fdiv_rn(__uint2float_rn(ts[e] - rw.t_first), rw.fdT));
                 const int tb = trunc_like_x86(tn);                             // dsec.py:43
-                if (tb < 0 || tb >= B) continue;                               // both temporal corners masked or t0 + 1 only: see below
+                if (tb < 0 || tb >= B) continue;                               // corner t0 masked; t0 + 1 cannot be in range either
                 const float f = __fsub_rn(tn, __int2float_rn(tb));             // exact (Sterbenz)
                 const long long fq = static_cast<long long>(__float2int_rn(__fmul_rn(f, 16777216.0f)));
                 const long long cell = static_cast<long long>(value) * ((1LL << kCountShift) + fq);
@@ -127,6 +156,9 @@ sensor_accumulate_kernel(const uint32_t* __restrict__ t, const uint16_t* __restr
                 ++local_bins;
             }
         }
+        grp = nxt_grp;
+        if (CMDA_SENS_PREFETCH) cur = nxt;
+        else if (j + 1 < kSensGroupsPerThread && grp < g1) cur = sens_load8<HAS_T, VEC>(t, x, y, p, grp << 3, wd.start, wd.end);
     }
     if (count_bins) {
         if (!HAS_T) {
@@ -141,9 +173,41 @@ sensor_accumulate_kernel(const uint32_t* __restrict__ t, const uint16_t* __restr
     }
 }
 
+// R cells -> planes, in place (B > 1): plane_b = C_b - F_b + F_(b-1) (the temporal corners 1 - f and
+// f of dsec.py:49-52) as a float64 holding the exact 2^-30 fixed-point integer.  One thread per
+// (window, raw pixel), bins in order.
+__global__ void __launch_bounds__(256)
+plane_finalize_kernel(long long* __restrict__ R, int B, size_t plane) {
+    const size_t P = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (P >= plane) return;
+    long long* r = R + static_cast<size_t>(blockIdx.y) * B * plane + P;
+    long long f_prev = 0;
+    for (int b = 0; b < B; ++b) {
+        const long long cell = r[static_cast<size_t>(b) * plane];
+        if (cell == 0 && f_prev == 0) continue;                    // +0.0 has the all-zero pattern already
+        const long long f = static_cast<long long>(static_cast<unsigned long long>(cell) << (64 - kCountShift)) >>
+                            (64 - kCountShift);                    // low 44 bits, signed
+        const long long c = (cell - f) >> kCountShift;
+        const long long pl = c * (1LL << kFracBits) - f + f_prev;  // 2^-24 fixed point, |pl| < 2^44
+        f_prev = f;
+        r[static_cast<size_t>(b) * plane] = __double_as_longlong(static_cast<double>(pl * 64));   // 2^-30, exact
+    }
+}
+
 // ---- inverse index of one rectify map ------------------------------------------------------------
 // cell (cx, cy) = (x0 + 1, y0 + 1) over a (W + 1) x (H + 1) grid: x0 = -1 keeps the pixels whose only
-// in-grid corner is x0 + 1 = 0 (int() truncates toward zero).
+// in-grid corner is x0 + 1 = 0 (int() truncates toward zero).  Every cell has
+// kCellSlots inline slots (a rectification map is close to injective: a cell almost never holds
+// more); pixels beyond that go to one overflow list that the rare overfull cell scans.
+constexpr int kCellSlots = 4;
+
+struct MapIndex {
+    unsigned* cnt;        // [ncells]               pixels per cell
+    uint4* slots;         // [ncells]               first kCellSlots raw pixel indices of the cell
+    unsigned* ovf_cnt;    // [1]
+    uint2* ovf;           // [H * W]                (cell, pixel) of the pixels beyond the inline slots
+};
+
 __device__ __forceinline__ bool cell_of(float2 m, int H, int W, unsigned& cell) {
     const int x0 = trunc_like_x86(m.x), y0 = trunc_like_x86(m.y);          // dsec.py:41-42
     if (x0 < -1 || x0 >= W || y0 < -1 || y0 >= H) return false;          // no corner inside the grid
@@ -151,70 +215,31 @@ __device__ __forceinline__ bool cell_of(float2 m, int H, int W, unsigned& cell) 
     return true;
 }
 
-__global__ void __launch_bounds__(256)
-rectify_cell_count_kernel(const float2* __restrict__ maps, MapSlots ms, int H, int W, unsigned* __restrict__ counts,
-                          size_t ncells_padded) {
-    const int slot = blockIdx.y;
-    const float2* map = maps + static_cast<size_t>(ms.map_of_slot[slot]) * H * W;
-    unsigned* c = counts + static_cast<size_t>(slot) * ncells_padded;
-    const int npx = H * W;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += gridDim.x * blockDim.x) {
-        unsigned cell;
-        if (cell_of(__ldg(map + i), H, W, cell)) atomicAdd(c + cell, 1u);
-    }
-}
-
-// in place: counts -> exclusive starts; starts[ncells] = total.  One CTA per map.
-__global__ void __launch_bounds__(kScanThreads)
-rectify_cell_scan_kernel(unsigned* __restrict__ counts, unsigned* __restrict__ fill, int ncells, size_t ncells_padded) {
-    __shared__ unsigned s_warp[32];
-    unsigned* c = counts + static_cast<size_t>(blockIdx.x) * ncells_padded;
-    unsigned* f = fill + static_cast<size_t>(blockIdx.x) * ncells_padded;
-    const int per = (ncells + kScanThreads - 1) / kScanThreads;
-    const int lo = threadIdx.x * per, hi = min(lo + per, ncells);
-    unsigned mine = 0;
-    for (int i = lo; i < hi; ++i) mine += c[i];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    unsigned inc = mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned a = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += a;
-    }
-    if (lane == 31) s_warp[wid] = inc;
-    __syncthreads();
-    if (wid == 0) {
-        const unsigned a = s_warp[lane];
-        unsigned ia = a;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned u = __shfl_up_sync(0xffffffffu, ia, o);
-            if (lane >= o) ia += u;
-        }
-        s_warp[lane] = ia - a;
-    }
-    __syncthreads();
-    unsigned run = s_warp[wid] + inc - mine;
-    for (int i = lo; i < hi; ++i) {
-        const unsigned v = c[i];
-        c[i] = run;
-        f[i] = run;
-        run += v;
-    }
-    if (threadIdx.x == kScanThreads - 1) c[ncells] = run;
+__device__ __forceinline__ MapIndex map_index_at(char* base, int slot, size_t ncells_padded, size_t npx) {
+    const size_t per = ncells_padded * (sizeof(unsigned) + sizeof(uint4)) + 256 + npx * sizeof(uint2);
+    char* b = base + static_cast<size_t>(slot) * per;
+    MapIndex ix;
+    ix.slots = reinterpret_cast<uint4*>(b);
+    ix.cnt = reinterpret_cast<unsigned*>(b + ncells_padded * sizeof(uint4));
+    ix.ovf_cnt = ix.cnt + ncells_padded;
+    ix.ovf = reinterpret_cast<uint2*>(b + ncells_padded * (sizeof(unsigned) + sizeof(uint4)) + 256);
+    return ix;
 }
 
 __global__ void __launch_bounds__(256)
-rectify_cell_fill_kernel(const float2* __restrict__ maps, MapSlots ms, int H, int W, unsigned* __restrict__ fill,
-                         unsigned* __restrict__ pix_list, size_t ncells_padded) {
+rectify_index_build_kernel(const float2* __restrict__ maps, MapSlots ms, int H, int W, char* __restrict__ index_ws,
+                           size_t ncells_padded) {
     const int slot = blockIdx.y;
-    const float2* map = maps + static_cast<size_t>(ms.map_of_slot[slot]) * H * W;
-    unsigned* f = fill + static_cast<size_t>(slot) * ncells_padded;
-    unsigned* list = pix_list + static_cast<size_t>(slot) * H * W;
     const int npx = H * W;
+    const float2* map = maps + static_cast<size_t>(ms.map_of_slot[slot]) * npx;
+    const MapIndex ix = map_index_at(index_ws, slot, ncells_padded, npx);
+    unsigned* slots = reinterpret_cast<unsigned*>(ix.slots);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += gridDim.x * blockDim.x) {
         unsigned cell;
-        if (cell_of(__ldg(map + i), H, W, cell)) list[atomicAdd(f + cell, 1u)] = static_cast<unsigned>(i);
+        if (!cell_of(__ldg(map + i), H, W, cell)) continue;
+        const unsigned r = atomicAdd(ix.cnt + cell, 1u);
+        if (r < kCellSlots) slots[static_cast<size_t>(cell) * kCellSlots + r] = static_cast<unsigned>(i);
+        else ix.ovf[atomicAdd(ix.ovf_cnt, 1u)] = make_uint2(cell, static_cast<unsigned>(i));
     }
 }
 
@@ -225,29 +250,27 @@ struct GatherStats {
     float mn, mx;
 };
 
-// BMAX: compile-time bound of the per-thread bin accumulators (B <= BMAX).
+// One thread per output pixel, all B bins.  BMAX: compile-time bound of the bin accumulators.
 template <bool HAS_T, int BMAX>
 __global__ void __launch_bounds__(kGatherThreads)
 rectify_gather_kernel(const void* __restrict__ R, WindowTable tab, MapSlots ms, const float2* __restrict__ maps,
-                      const unsigned* __restrict__ cell_start, const unsigned* __restrict__ pix_list,
-                      size_t ncells_padded, int H, int W, int B, float* __restrict__ raw,
-                      PartialStats* __restrict__ partials) {
+                      char* __restrict__ index_ws, size_t ncells_padded, int H, int W, int B, float* __restrict__ raw,
+                      PartialStats* __restrict__ block_partials) {
     const int s = blockIdx.y;
     const WindowDesc wd = tab.w[s];
     const int npx = H * W;
     const size_t plane = static_cast<size_t>(npx);
-    const int seg = (npx + kStatBlocks - 1) / kStatBlocks;
-    const int lo = blockIdx.x * seg, hi = min(lo + seg, npx);
     const bool identity = maps == nullptr;
     const float2* map = identity ? nullptr : maps + static_cast<size_t>(wd.map_id) * npx;
-    const unsigned* cs = identity ? nullptr : cell_start + static_cast<size_t>(ms.slot[s]) * ncells_padded;
-    const unsigned* list = identity ? nullptr : pix_list + static_cast<size_t>(ms.slot[s]) * npx;
-    const long long* R64 = reinterpret_cast<const long long*>(R) + static_cast<size_t>(s) * B * plane;
+    MapIndex ix{};
+    if (!identity) ix = map_index_at(index_ws, ms.slot[s], ncells_padded, npx);
+    const double* planes = reinterpret_cast<const double*>(R) + static_cast<size_t>(s) * B * plane;   // plane_finalize_kernel
     const int* R32 = reinterpret_cast<const int*>(R) + static_cast<size_t>(s) * plane;
     float* out = raw + static_cast<size_t>(s) * B * plane;
 
     GatherStats st{0.0, 0.0, 0, INFINITY, -INFINITY};
-    for (int px = lo + threadIdx.x; px < hi; px += kGatherThreads) {
+    const int px = blockIdx.x * kGatherThreads + threadIdx.x;
+    if (px < npx) {
         const int X = px % W, Y = px / W;
         long long acc[BMAX];
 #pragma unroll
@@ -257,20 +280,9 @@ rectify_gather_kernel(const void* __restrict__ R, WindowTable tab, MapSlots ms, 
             const double md = static_cast<double>(__fmul_rn(tent(X, m.x), tent(Y, m.y)));
             if (md == 0.0) return;
             if constexpr (HAS_T) {
-                long long f_prev = 0;
 #pragma unroll
-                for (int b = 0; b < BMAX; ++b) {
-                    if (b < B) {
-                        const long long cell = __ldg(R64 + static_cast<size_t>(b) * plane + P);
-                        const long long f = static_cast<long long>(static_cast<unsigned long long>(cell) << (64 - kCountShift)) >>
-                                            (64 - kCountShift);                                   // low 44 bits, signed
-                        const long long c = (cell - f) >> kCountShift;
-                        // temporal corners of dsec.py:49-52: (1 - f) to bin t0, f to bin t0 + 1
-                        const long long pl = c * (1LL << kFracBits) - f + f_prev;                 // 2^-24 fixed point
-                        f_prev = f;
-                        if (pl != 0) acc[b] += __double2ll_rn(md * static_cast<double>(pl) * 64.0);  // -> 2^-30
-                    }
-                }
+                for (int b = 0; b < BMAX; ++b)
+                    if (b < B) acc[b] += __double2ll_rn(md * __ldg(planes + static_cast<size_t>(b) * plane + P));  // 2^-30 units
             } else {
                 const int c = __ldg(R32 + P);
                 if (c != 0) acc[0] += __double2ll_rn(md * static_cast<double>(c) * 1073741824.0);
@@ -279,14 +291,28 @@ rectify_gather_kernel(const void* __restrict__ R, WindowTable tab, MapSlots ms, 
         if (identity) {
             add_pixel(static_cast<unsigned>(px), make_float2(static_cast<float>(X), static_cast<float>(Y)));
         } else {
+            // the four cells whose corner set contains (X, Y): x0 in {X - 1, X}, y0 in {Y - 1, Y}
+            unsigned n[4];
+            uint4 sl[4];
 #pragma unroll
-            for (int dy = 0; dy < 2; ++dy) {
-                // cells (X, Y + dy) and (X + 1, Y + dy) are adjacent: one contiguous list range
-                const unsigned c0 = static_cast<unsigned>(Y + dy) * static_cast<unsigned>(W + 1) + static_cast<unsigned>(X);
-                const unsigned beg = __ldg(cs + c0), end = __ldg(cs + c0 + 2);
-                for (unsigned k = beg; k < end; ++k) {
-                    const unsigned P = __ldg(list + k);
-                    add_pixel(P, __ldg(map + P));
+            for (int q = 0; q < 4; ++q) {
+                const unsigned c = static_cast<unsigned>(Y + (q >> 1)) * static_cast<unsigned>(W + 1) + static_cast<unsigned>(X + (q & 1));
+                n[q] = __ldg(ix.cnt + c);
+                sl[q] = n[q] ? __ldg(ix.slots + c) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const unsigned e[4] = {sl[q].x, sl[q].y, sl[q].z, sl[q].w};
+#pragma unroll
+                for (int k = 0; k < kCellSlots; ++k)
+                    if (static_cast<unsigned>(k) < n[q]) add_pixel(e[k], __ldg(map + e[k]));
+                if (n[q] > kCellSlots) {                      // overfull cell: its other pixels are in the overflow list
+                    const unsigned c = static_cast<unsigned>(Y + (q >> 1)) * static_cast<unsigned>(W + 1) + static_cast<unsigned>(X + (q & 1));
+                    const unsigned no = __ldg(ix.ovf_cnt);
+                    for (unsigned k = 0; k < no; ++k) {
+                        const uint2 o = __ldg(ix.ovf + k);
+                        if (o.x == c) add_pixel(o.y, __ldg(map + o.y));
+                    }
                 }
             }
         }
@@ -324,32 +350,56 @@ rectify_gather_kernel(const void* __restrict__ R, WindowTable tab, MapSlots ms, 
             o.sum += s_sum[w]; o.sumsq += s_sq[w]; o.nnz += s_n[w];
             o.min_nz = fminf(o.min_nz, s_mn[w]); o.max_nz = fmaxf(o.max_nz, s_mx[w]);
         }
-        partials[static_cast<size_t>(s) * kStatBlocks + blockIdx.x] = o;
+        block_partials[static_cast<size_t>(s) * gridDim.x + blockIdx.x] = o;
     }
 }
 
+// [S][nblk] block partials -> the [S][kStatBlocks] partials the normaliser consumes; slot j is the
+// in-order sum of blocks [j*q, (j+1)*q): a fixed order, hence bit-reproducible.
+__global__ void __launch_bounds__(kStatBlocks)
+regroup_partials_kernel(const PartialStats* __restrict__ block_partials, int nblk, PartialStats* __restrict__ partials) {
+    const int s = blockIdx.x, j = threadIdx.x;
+    const int q = (nblk + kStatBlocks - 1) / kStatBlocks;
+    PartialStats o;
+    o.sum = 0.0; o.sumsq = 0.0; o.nnz = 0; o.min_nz = INFINITY; o.max_nz = -INFINITY;
+    for (int k = j * q; k < min((j + 1) * q, nblk); ++k) {
+        const PartialStats p = block_partials[static_cast<size_t>(s) * nblk + k];
+        o.sum += p.sum; o.sumsq += p.sumsq; o.nnz += p.nnz;
+        o.min_nz = fminf(o.min_nz, p.min_nz); o.max_nz = fmaxf(o.max_nz, p.max_nz);
+    }
+    partials[static_cast<size_t>(s) * kStatBlocks + j] = o;
+}
+
 // ---- workspace + launch sequence ---------------------------------------------------------------
+constexpr int kMaxDistinctMaps = 8;    // inverse indices held at once; api.cu cuts window groups accordingly
+
 static size_t ncells_padded_of(int H, int W) {
     return align_up(static_cast<size_t>(H + 1) * (W + 1) + 2, 64);
 }
-
-int factored_supported(int H, int W, int B) {
-    return B >= 1 && B <= 24 && H >= 1 && W >= 1 && static_cast<long long>(H + 1) * (W + 1) < (1LL << 31);
+static int gather_blocks(int H, int W) { return (H * W + kGatherThreads - 1) / kGatherThreads; }
+static size_t index_bytes_per_map(int H, int W) {
+    return ncells_padded_of(H, W) * (sizeof(unsigned) + sizeof(uint4)) + 256 + static_cast<size_t>(H) * W * sizeof(uint2);
 }
 
-// inverse index of up to `group` distinct maps (cell starts + fill cursors + pixel lists)
-size_t factored_index_bytes(int group, int H, int W) {
-    const size_t nc = ncells_padded_of(H, W);
-    return align_up(static_cast<size_t>(group) * (2 * nc * sizeof(unsigned) + static_cast<size_t>(H) * W * sizeof(unsigned)), 256);
+int factored_supported(int H, int W, int B) {
+    return B >= 1 && B <= 24 && H >= 1 && W >= 1 && static_cast<long long>(H + 1) * (W + 1) < (1LL << 30);
+}
+int factored_max_maps(void) { return kMaxDistinctMaps; }
+
+// inverse indices of the distinct maps of one window group + the per-block statistics partials
+size_t factored_scratch_bytes(int group, int H, int W) {
+    const int maps = group < kMaxDistinctMaps ? group : kMaxDistinctMaps;
+    return align_up(static_cast<size_t>(maps) * index_bytes_per_map(H, W), 256) +
+           align_up(sizeof(PartialStats) * static_cast<size_t>(group) * gather_blocks(H, W), 256);
 }
 
 int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, const uint8_t* p, const WindowTable& tab, int S,
                     long long max_events, const float* maps, int H, int W, int B, void* R, int64_t* bin_counts,
-                    float* raw, PartialStats* partials, void* index_ws, size_t index_bytes, cudaStream_t st) {
+                    float* raw, PartialStats* partials, void* scratch, size_t scratch_bytes, cudaStream_t st) {
     if (!factored_supported(H, W, B)) return CMDA_ERR_UNSUPPORTED;
     const size_t npx = static_cast<size_t>(H) * W;
     const size_t nc = ncells_padded_of(H, W);
-    const int ncells = (H + 1) * (W + 1);
+    const int nblk = gather_blocks(H, W);
     // distinct maps of this group of windows
     MapSlots ms{};
     int n_slots = 0;
@@ -358,26 +408,30 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
             int found = -1;
             for (int k = 0; k < n_slots; ++k)
                 if (ms.map_of_slot[k] == tab.w[s].map_id) { found = k; break; }
-            if (found < 0) { found = n_slots; ms.map_of_slot[n_slots++] = tab.w[s].map_id; }
+            if (found < 0) {
+                if (n_slots == kMaxDistinctMaps) return CMDA_ERR_BAD_ARG;   // api.cu cuts the groups: cannot happen
+                found = n_slots;
+                ms.map_of_slot[n_slots++] = tab.w[s].map_id;
+            }
             ms.slot[s] = found;
         }
-        if (factored_index_bytes(n_slots, H, W) > index_bytes) return CMDA_ERR_WORKSPACE;
     }
-    unsigned* cell_start = static_cast<unsigned*>(index_ws);
-    unsigned* cell_fill = cell_start + static_cast<size_t>(n_slots) * nc;
-    unsigned* pix_list = cell_fill + static_cast<size_t>(n_slots) * nc;
+    const size_t index_bytes = align_up(static_cast<size_t>(n_slots) * index_bytes_per_map(H, W), 256);
+    if (index_bytes + sizeof(PartialStats) * static_cast<size_t>(S) * nblk > scratch_bytes) return CMDA_ERR_WORKSPACE;
+    char* index_ws = static_cast<char*>(scratch);
+    PartialStats* block_partials = reinterpret_cast<PartialStats*>(index_ws + index_bytes);
     const float2* maps2 = reinterpret_cast<const float2*>(maps);
 
-    // zero R (int64 cells for B > 1, int32 counts for B == 1) and the cell counters
+    // zero R (int64 cells for B > 1, int32 counts for B == 1) and the cell counters of the indices
     const size_t r_bytes = (B == 1) ? sizeof(int) * S * npx : sizeof(long long) * S * B * npx;
     CMDA_CUDA_TRY(cudaMemsetAsync(R, 0, r_bytes, st));
-    if (n_slots) CMDA_CUDA_TRY(cudaMemsetAsync(cell_start, 0, sizeof(unsigned) * n_slots * nc, st));
+    for (int k = 0; k < n_slots; ++k)
+        CMDA_CUDA_TRY(cudaMemsetAsync(index_ws + static_cast<size_t>(k) * index_bytes_per_map(H, W) + nc * sizeof(uint4), 0,
+                                      nc * sizeof(unsigned) + 256, st));
     phase_mark(st);
     if (n_slots) {
-        dim3 grid(148 * 2, n_slots);
-        rectify_cell_count_kernel<<<grid, 256, 0, st>>>(maps2, ms, H, W, cell_start, nc);
-        rectify_cell_scan_kernel<<<n_slots, kScanThreads, 0, st>>>(cell_start, cell_fill, ncells, nc);
-        rectify_cell_fill_kernel<<<grid, 256, 0, st>>>(maps2, ms, H, W, cell_fill, pix_list, nc);
+        dim3 grid(static_cast<unsigned>((npx + 255) / 256), n_slots);
+        rectify_index_build_kernel<<<grid, 256, 0, st>>>(maps2, ms, H, W, index_ws, nc);
         CMDA_LAUNCH_CHECK();
     }
     phase_mark(st);
@@ -398,16 +452,21 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
         CMDA_LAUNCH_CHECK();
     }
     phase_mark(st);
+    if (B > 1) {
+        plane_finalize_kernel<<<dim3(static_cast<unsigned>((npx + 255) / 256), S), 256, 0, st>>>(static_cast<long long*>(R), B, npx);
+        CMDA_LAUNCH_CHECK();
+    }
     {
-        dim3 grid(kStatBlocks, S);
+        dim3 grid(nblk, S);
 #define CMDA_GATHER(HAS_T, BMAX)                                                                                      \
-    rectify_gather_kernel<HAS_T, BMAX><<<grid, kGatherThreads, 0, st>>>(R, tab, ms, maps2, cell_start, pix_list, nc, H, W, \
-                                                                        B, raw, partials)
+    rectify_gather_kernel<HAS_T, BMAX><<<grid, kGatherThreads, 0, st>>>(R, tab, ms, maps2, index_ws, nc, H, W, B, raw, \
+                                                                        block_partials)
         if (B == 1) CMDA_GATHER(false, 1);
         else if (B <= 5) CMDA_GATHER(true, 5);
         else if (B <= 10) CMDA_GATHER(true, 10);
         else CMDA_GATHER(true, 24);
 #undef CMDA_GATHER
+        regroup_partials_kernel<<<S, kStatBlocks, 0, st>>>(block_partials, nblk, partials);
         CMDA_LAUNCH_CHECK();
     }
     return CMDA_OK;
