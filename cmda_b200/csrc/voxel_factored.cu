@@ -243,6 +243,89 @@ rectify_index_build_kernel(const float2* __restrict__ maps, MapSlots ms, int H, 
     }
 }
 
+// ---- gather stencil of one map ---------------------------------------------------------------------
+// The rectification splat is a sparse linear map from sensor space to the rectified grid (about four
+// non-zeros per output pixel) that depends on the map only, not on the window or the bin.  It is
+// materialised once per call per distinct map in ELL form (kEll entries per output pixel, SoA so that a
+// warp's loads coalesce): raw pixel index + float32 weight fl(tent(X, x) * tent(Y, y)) (dsec.py:51-52
+// with value = 1).  Rows with more than kEll entries (degenerate maps) are flagged and gathered from
+// the cell lists directly.
+constexpr int kEll = 8;
+constexpr unsigned kEllOverflow = 0xffu;
+
+struct Stencil {
+    unsigned* P;          // [kEll][npx]
+    float* w;             // [kEll][npx]
+    unsigned char* n;     // [npx]   entries of the row, or kEllOverflow
+};
+__device__ __host__ __forceinline__ size_t stencil_bytes(size_t npx) {
+    return (npx * kEll * (sizeof(unsigned) + sizeof(float)) + npx + 255) / 256 * 256;
+}
+__device__ __forceinline__ Stencil stencil_at(char* base, int slot, size_t npx) {
+    char* b = base + static_cast<size_t>(slot) * stencil_bytes(npx);
+    Stencil st;
+    st.P = reinterpret_cast<unsigned*>(b);
+    st.w = reinterpret_cast<float*>(b + npx * kEll * sizeof(unsigned));
+    st.n = reinterpret_cast<unsigned char*>(b + npx * kEll * (sizeof(unsigned) + sizeof(float)));
+    return st;
+}
+
+// Calls f(P, weight) for every raw pixel whose corner set contains output pixel (X, Y).
+template <typename F>
+__device__ __forceinline__ void for_each_source(const MapIndex& ix, const float2* __restrict__ map, int X, int Y, int W, F&& f) {
+    unsigned ovf = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        // the four cells: x0 in {X - 1, X}, y0 in {Y - 1, Y}
+        const unsigned c = static_cast<unsigned>(Y + (q >> 1)) * static_cast<unsigned>(W + 1) + static_cast<unsigned>(X + (q & 1));
+        const unsigned n = __ldg(ix.cnt + c);
+        if (n == 0) continue;
+        const uint4 sl = __ldg(ix.slots + c);
+        const unsigned e[4] = {sl.x, sl.y, sl.z, sl.w};
+#pragma unroll
+        for (int k = 0; k < kCellSlots; ++k)
+            if (static_cast<unsigned>(k) < n) {
+                const float2 m = __ldg(map + e[k]);
+                f(e[k], __fmul_rn(tent(X, m.x), tent(Y, m.y)));
+            }
+        if (n > kCellSlots) ovf |= 1u << q;
+    }
+    if (ovf) {   // overfull cells: their other pixels are in the overflow list
+        const unsigned no = __ldg(ix.ovf_cnt);
+        for (int q = 0; q < 4; ++q) {
+            if (!(ovf & (1u << q))) continue;
+            const unsigned c = static_cast<unsigned>(Y + (q >> 1)) * static_cast<unsigned>(W + 1) + static_cast<unsigned>(X + (q & 1));
+            for (unsigned k = 0; k < no; ++k) {
+                const uint2 o = __ldg(ix.ovf + k);
+                if (o.x == c) {
+                    const float2 m = __ldg(map + o.y);
+                    f(o.y, __fmul_rn(tent(X, m.x), tent(Y, m.y)));
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+stencil_build_kernel(const float2* __restrict__ maps, MapSlots ms, int H, int W, char* __restrict__ index_ws,
+                     size_t ncells_padded, char* __restrict__ stencil_ws) {
+    const int slot = blockIdx.y;
+    const unsigned npx = static_cast<unsigned>(H) * static_cast<unsigned>(W);
+    const unsigned px = blockIdx.x * blockDim.x + threadIdx.x;
+    if (px >= npx) return;
+    const float2* map = maps + static_cast<size_t>(ms.map_of_slot[slot]) * npx;
+    const MapIndex ix = map_index_at(index_ws, slot, ncells_padded, npx);
+    const Stencil sc = stencil_at(stencil_ws, slot, npx);
+    const int X = static_cast<int>(px % static_cast<unsigned>(W)), Y = static_cast<int>(px / static_cast<unsigned>(W));
+    unsigned n = 0;
+    for_each_source(ix, map, X, Y, W, [&](unsigned P, float w) {
+        if (w == 0.0f) return;
+        if (n < kEll) { sc.P[n * npx + px] = P; sc.w[n * npx + px] = w; }
+        ++n;
+    });
+    sc.n[px] = static_cast<unsigned char>(n <= kEll ? n : kEllOverflow);
+}
+
 // ---- stage B ----------------------------------------------------------------------------------
 struct GatherStats {
     double sum, sumsq;
@@ -254,73 +337,52 @@ struct GatherStats {
 template <bool HAS_T, int BMAX>
 __global__ void __launch_bounds__(kGatherThreads)
 rectify_gather_kernel(const void* __restrict__ R, WindowTable tab, MapSlots ms, const float2* __restrict__ maps,
-                      char* __restrict__ index_ws, size_t ncells_padded, int H, int W, int B, float* __restrict__ raw,
-                      PartialStats* __restrict__ block_partials) {
+                      char* __restrict__ index_ws, size_t ncells_padded, char* __restrict__ stencil_ws, int H, int W, int B,
+                      float* __restrict__ raw, PartialStats* __restrict__ block_partials) {
     const int s = blockIdx.y;
     const WindowDesc wd = tab.w[s];
-    const int npx = H * W;
-    const size_t plane = static_cast<size_t>(npx);
+    const unsigned npx = static_cast<unsigned>(H) * static_cast<unsigned>(W);
     const bool identity = maps == nullptr;
-    const float2* map = identity ? nullptr : maps + static_cast<size_t>(wd.map_id) * npx;
-    MapIndex ix{};
-    if (!identity) ix = map_index_at(index_ws, ms.slot[s], ncells_padded, npx);
-    const double* planes = reinterpret_cast<const double*>(R) + static_cast<size_t>(s) * B * plane;   // plane_finalize_kernel
-    const int* R32 = reinterpret_cast<const int*>(R) + static_cast<size_t>(s) * plane;
-    float* out = raw + static_cast<size_t>(s) * B * plane;
+    const double* planes = reinterpret_cast<const double*>(R) + static_cast<size_t>(s) * B * npx;   // plane_finalize_kernel
+    const int* R32 = reinterpret_cast<const int*>(R) + static_cast<size_t>(s) * npx;
+    float* out = raw + static_cast<size_t>(s) * B * npx;
 
     GatherStats st{0.0, 0.0, 0, INFINITY, -INFINITY};
-    const int px = blockIdx.x * kGatherThreads + threadIdx.x;
+    const unsigned px = blockIdx.x * kGatherThreads + threadIdx.x;
     if (px < npx) {
-        const int X = px % W, Y = px / W;
         long long acc[BMAX];
 #pragma unroll
         for (int b = 0; b < BMAX; ++b) acc[b] = 0;
-        auto add_pixel = [&](unsigned P, float2 m) {
-            // dsec.py:51-52 with value = 1: (1 - |xl - x|) * (1 - |yl - y|), one rounding
-            const double md = static_cast<double>(__fmul_rn(tent(X, m.x), tent(Y, m.y)));
-            if (md == 0.0) return;
+        // one source pixel: quantise its contribution to 2^-30 (order-independent integer sum)
+        auto accumulate = [&](unsigned P, float w) {
+            const double md = static_cast<double>(w);
             if constexpr (HAS_T) {
 #pragma unroll
                 for (int b = 0; b < BMAX; ++b)
-                    if (b < B) acc[b] += __double2ll_rn(md * __ldg(planes + static_cast<size_t>(b) * plane + P));  // 2^-30 units
+                    if (b < B) acc[b] += __double2ll_rn(md * __ldg(planes + static_cast<unsigned>(b) * npx + P));  // 2^-30 units
             } else {
-                const int c = __ldg(R32 + P);
-                if (c != 0) acc[0] += __double2ll_rn(md * static_cast<double>(c) * 1073741824.0);
+                acc[0] += __double2ll_rn(md * (static_cast<double>(__ldg(R32 + P)) * 1073741824.0));
             }
         };
         if (identity) {
-            add_pixel(static_cast<unsigned>(px), make_float2(static_cast<float>(X), static_cast<float>(Y)));
+            accumulate(px, 1.0f);          // x = float(x), y = float(y): the only non-zero corner is the pixel itself
         } else {
-            // the four cells whose corner set contains (X, Y): x0 in {X - 1, X}, y0 in {Y - 1, Y}
-            unsigned n[4];
-            uint4 sl[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const unsigned c = static_cast<unsigned>(Y + (q >> 1)) * static_cast<unsigned>(W + 1) + static_cast<unsigned>(X + (q & 1));
-                n[q] = __ldg(ix.cnt + c);
-                sl[q] = n[q] ? __ldg(ix.slots + c) : make_uint4(0, 0, 0, 0);
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const unsigned e[4] = {sl[q].x, sl[q].y, sl[q].z, sl[q].w};
-#pragma unroll
-                for (int k = 0; k < kCellSlots; ++k)
-                    if (static_cast<unsigned>(k) < n[q]) add_pixel(e[k], __ldg(map + e[k]));
-                if (n[q] > kCellSlots) {                      // overfull cell: its other pixels are in the overflow list
-                    const unsigned c = static_cast<unsigned>(Y + (q >> 1)) * static_cast<unsigned>(W + 1) + static_cast<unsigned>(X + (q & 1));
-                    const unsigned no = __ldg(ix.ovf_cnt);
-                    for (unsigned k = 0; k < no; ++k) {
-                        const uint2 o = __ldg(ix.ovf + k);
-                        if (o.x == c) add_pixel(o.y, __ldg(map + o.y));
-                    }
-                }
+            const Stencil sc = stencil_at(stencil_ws, ms.slot[s], npx);
+            const unsigned n = sc.n[px];
+            if (n != kEllOverflow) {
+                for (unsigned k = 0; k < n; ++k) accumulate(__ldg(sc.P + k * npx + px), __ldg(sc.w + k * npx + px));
+            } else {
+                const float2* map = maps + static_cast<size_t>(wd.map_id) * npx;
+                const MapIndex ix = map_index_at(index_ws, ms.slot[s], ncells_padded, npx);
+                const int X = static_cast<int>(px % static_cast<unsigned>(W)), Y = static_cast<int>(px / static_cast<unsigned>(W));
+                for_each_source(ix, map, X, Y, W, [&](unsigned P, float w) { if (w != 0.0f) accumulate(P, w); });
             }
         }
 #pragma unroll
         for (int b = 0; b < BMAX; ++b) {
             if (b < B) {
                 const float v = __fmul_rn(__ll2float_rn(acc[b]), kFixInv);
-                out[static_cast<size_t>(b) * plane + px] = v;
+                out[static_cast<unsigned>(b) * npx + px] = v;
                 if (v != 0.0f) {                                   // dsec.py:88
                     st.nnz += 1;
                     st.mn = fminf(st.mn, v);
@@ -371,7 +433,7 @@ regroup_partials_kernel(const PartialStats* __restrict__ block_partials, int nbl
 }
 
 // ---- workspace + launch sequence ---------------------------------------------------------------
-constexpr int kMaxDistinctMaps = 8;    // inverse indices held at once; api.cu cuts window groups accordingly
+constexpr int kMaxDistinctMaps = 4;    // inverse indices held at once; api.cu cuts window groups accordingly
 
 static size_t ncells_padded_of(int H, int W) {
     return align_up(static_cast<size_t>(H + 1) * (W + 1) + 2, 64);
@@ -390,6 +452,7 @@ int factored_max_maps(void) { return kMaxDistinctMaps; }
 size_t factored_scratch_bytes(int group, int H, int W) {
     const int maps = group < kMaxDistinctMaps ? group : kMaxDistinctMaps;
     return align_up(static_cast<size_t>(maps) * index_bytes_per_map(H, W), 256) +
+           static_cast<size_t>(maps) * stencil_bytes(static_cast<size_t>(H) * W) +
            align_up(sizeof(PartialStats) * static_cast<size_t>(group) * gather_blocks(H, W), 256);
 }
 
@@ -417,9 +480,11 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
         }
     }
     const size_t index_bytes = align_up(static_cast<size_t>(n_slots) * index_bytes_per_map(H, W), 256);
-    if (index_bytes + sizeof(PartialStats) * static_cast<size_t>(S) * nblk > scratch_bytes) return CMDA_ERR_WORKSPACE;
+    const size_t sten_bytes = static_cast<size_t>(n_slots) * stencil_bytes(npx);
+    if (index_bytes + sten_bytes + sizeof(PartialStats) * static_cast<size_t>(S) * nblk > scratch_bytes) return CMDA_ERR_WORKSPACE;
     char* index_ws = static_cast<char*>(scratch);
-    PartialStats* block_partials = reinterpret_cast<PartialStats*>(index_ws + index_bytes);
+    char* stencil_ws = index_ws + index_bytes;
+    PartialStats* block_partials = reinterpret_cast<PartialStats*>(stencil_ws + sten_bytes);
     const float2* maps2 = reinterpret_cast<const float2*>(maps);
 
     // zero R (int64 cells for B > 1, int32 counts for B == 1) and the cell counters of the indices
@@ -432,6 +497,7 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
     if (n_slots) {
         dim3 grid(static_cast<unsigned>((npx + 255) / 256), n_slots);
         rectify_index_build_kernel<<<grid, 256, 0, st>>>(maps2, ms, H, W, index_ws, nc);
+        stencil_build_kernel<<<grid, 256, 0, st>>>(maps2, ms, H, W, index_ws, nc, stencil_ws);
         CMDA_LAUNCH_CHECK();
     }
     phase_mark(st);
@@ -459,8 +525,8 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
     {
         dim3 grid(nblk, S);
 #define CMDA_GATHER(HAS_T, BMAX)                                                                                      \
-    rectify_gather_kernel<HAS_T, BMAX><<<grid, kGatherThreads, 0, st>>>(R, tab, ms, maps2, index_ws, nc, H, W, B, raw, \
-                                                                        block_partials)
+    rectify_gather_kernel<HAS_T, BMAX><<<grid, kGatherThreads, 0, st>>>(R, tab, ms, maps2, index_ws, nc, stencil_ws, H, W, \
+                                                                        B, raw, block_partials)
         if (B == 1) CMDA_GATHER(false, 1);
         else if (B <= 5) CMDA_GATHER(true, 5);
         else if (B <= 10) CMDA_GATHER(true, 10);
