@@ -290,9 +290,9 @@ def run_gpu(args, rank, local_rank, world):
             names = ["memset(int64 grid)", "voxel_scatter_global_kernel", "convert_stats_kernel", "norm_apply_kernel"]
             launches_per_step = 3
         elif resolved == _lib.VOXEL_FACTORED:
-            names = ["memset(sensor grid)", "rectify_cell_{count,scan,fill} kernels", "sensor_accumulate_kernel",
-                     "rectify_gather_kernel", "norm_apply_kernel"]
-            launches_per_step = 6
+            names = ["memset(sensor grid)", "rectify_index_build+stencil_build kernels", "sensor_accumulate_kernel",
+                     "plane_finalize+rectify_gather+regroup_partials kernels", "norm_apply_kernel"]
+            launches_per_step = 7 if args.bins > 1 else 6   # kernels only (memsets not counted)
         else:
             names = ["memset(int64 grid)", "tile_bbox+tile_count+tile_scan kernels", "tile_partition_kernel",
                      "tile_accumulate_kernel", "convert_stats_kernel", "norm_apply_kernel"]
