@@ -68,53 +68,83 @@ def make_workload(n_windows, n_events, seed_base):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clocks and throttle reasons sampled DURING the timed region (B200_PROFILING.md).  The timed
+    region of this path lasts milliseconds, so the sampler polls NVML in a thread (every ~2 ms) instead of
+    waiting for `nvidia-smi -lms`; nvidia-smi is the fallback when the NVML binding is missing."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, gpu_index):
         self.gpu_index = gpu_index
-        self.proc = None
-        self.lines = []
+        self.samples = []     # (time, sm_mhz, max_mhz, power_w, reasons_bitmask)
+        self.stop_flag = False
+        self.thread = None
+        self.t_begin = self.t_end = None
+
+    def _nvml_loop(self):
+        import pynvml
+        pynvml.nvmlInit()
+        # honour CUDA_VISIBLE_DEVICES: map through the torch device's UUID when possible
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.gpu_index).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode() if not uuid.startswith("GPU-") else uuid.encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu_index)
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        while not self.stop_flag:
+            try:
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                try:
+                    rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((time.perf_counter(), float(sm), float(mx), pw, int(rs)))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def _smi_loop(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.gpu_index)], capture_output=True, text=True, timeout=5).stdout
+                f = [v.strip() for v in out.strip().split(",")]
+                self.samples.append((time.perf_counter(), float(f[0]), float(f[1]), float(f[2]), int(f[3], 16)))
+            except Exception:
+                time.sleep(0.05)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu_index)], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
-            self.thread.start()
-        except OSError:
-            self.proc = None
+            import pynvml  # noqa: F401
+            target = self._nvml_loop
+        except Exception:
+            target = self._smi_loop
+        self.thread = threading.Thread(target=target, daemon=True)
+        self.thread.start()
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
+
+    def mark_end(self):
+        self.t_end = time.perf_counter()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [v.strip() for v in ln.split(",")]
-            if len(f) < 8:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
-            except ValueError:
-                continue
-            for name, v in zip(names, f[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=6)
+        inside = [x for x in self.samples if self.t_begin is not None and self.t_begin <= x[0] <= (self.t_end or 1e30)]
+        used = inside if inside else self.samples
+        if not used:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["no clock samples"]}
+        mask = 0
+        for x in used:
+            mask |= x[4]
+        return {"sm_mhz": float(np.median([x[1] for x in used])), "sm_max_mhz": max(x[2] for x in used),
+                "power_w_max": max(x[3] for x in used), "samples": len(used),
+                "samples_in_timed_region": len(inside),
+                "reasons": sorted(k for k, bit in self.REASONS.items() if mask & bit)}
 
 
 def measured_peaks():
@@ -234,6 +264,7 @@ def run_gpu(args, rank, local_rank, world):
     phase_arrays = [(ctypes.c_void_p * n_phase)(*pe) for pe in phase_events]
     used = 0
     barrier()
+    sampler.mark_begin()
     ev[0].record()
     for k in range(args.steps):
         L.cmda_profiler_attach(phase_arrays[k], n_phase)
@@ -241,6 +272,7 @@ def run_gpu(args, rank, local_rank, world):
         used = L.cmda_profiler_detach()
     ev[1].record()
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     ms_total = ev[0].elapsed_time(ev[1])
     phase_ms = np.zeros(max(used - 1, 0))
