@@ -67,75 +67,94 @@ def make_workload(n_windows, n_events, seed_base):
             np.array(starts, np.int64), np.array(fins, np.int64))
 
 
+_SAMPLER_CHILD = r"""
+import sys, time
+idx, uuid = int(sys.argv[1]), sys.argv[2]
+import pynvml
+pynvml.nvmlInit()
+try:
+    h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode()) if uuid else pynvml.nvmlDeviceGetHandleByIndex(idx)
+except Exception:
+    h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+out = sys.stdout
+while True:
+    try:
+        sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+        pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+        try:
+            rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        out.write("%.6f %d %d %.1f %d\n" % (time.time(), sm, mx, pw, rs))
+        out.flush()
+    except Exception:
+        pass
+    time.sleep(0.0005)
+"""
+
+
 class ClockSampler:
     """SM clocks and throttle reasons sampled DURING the timed region (B200_PROFILING.md).  The timed
-    region of this path lasts milliseconds, so the sampler polls NVML in a thread (every ~2 ms) instead of
-    waiting for `nvidia-smi -lms`; nvidia-smi is the fallback when the NVML binding is missing."""
+    region of this path lasts milliseconds, so a child process polls NVML as fast as it answers (about every
+    millisecond) from before the warm-up on; the samples whose wall-clock stamp falls inside the timed
+    region are the ones reported (all samples under load if the region was shorter than one poll)."""
     REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, gpu_index):
         self.gpu_index = gpu_index
-        self.samples = []     # (time, sm_mhz, max_mhz, power_w, reasons_bitmask)
-        self.stop_flag = False
-        self.thread = None
+        self.proc = None
+        self.lines = []
         self.t_begin = self.t_end = None
 
-    def _nvml_loop(self):
-        import pynvml
-        pynvml.nvmlInit()
-        # honour CUDA_VISIBLE_DEVICES: map through the torch device's UUID when possible
+    def start(self):
+        uuid = ""
         try:
             import torch
-            uuid = str(torch.cuda.get_device_properties(self.gpu_index).uuid)
-            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode() if not uuid.startswith("GPU-") else uuid.encode())
+            u = str(torch.cuda.get_device_properties(self.gpu_index).uuid)
+            uuid = u if u.startswith("GPU-") else "GPU-" + u
         except Exception:
-            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu_index)
-        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
-        while not self.stop_flag:
-            try:
-                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
-                pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
-                try:
-                    rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
-                except Exception:
-                    rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                self.samples.append((time.perf_counter(), float(sm), float(mx), pw, int(rs)))
-            except Exception:
-                pass
-            time.sleep(0.002)
-
-    def _smi_loop(self):
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active"
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.gpu_index)], capture_output=True, text=True, timeout=5).stdout
-                f = [v.strip() for v in out.strip().split(",")]
-                self.samples.append((time.perf_counter(), float(f[0]), float(f[1]), float(f[2]), int(f[3], 16)))
-            except Exception:
-                time.sleep(0.05)
-
-    def start(self):
+            pass
         try:
-            import pynvml  # noqa: F401
-            target = self._nvml_loop
-        except Exception:
-            target = self._smi_loop
-        self.thread = threading.Thread(target=target, daemon=True)
-        self.thread.start()
+            self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_CHILD, str(self.gpu_index), uuid],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line)
+
+    def wait_ready(self, timeout=10.0):
+        t0 = time.time()
+        while self.proc is not None and not self.lines and time.time() - t0 < timeout:
+            time.sleep(0.01)
 
     def mark_begin(self):
-        self.t_begin = time.perf_counter()
+        self.t_begin = time.time()
 
     def mark_end(self):
-        self.t_end = time.perf_counter()
+        self.t_end = time.time()
 
     def stop(self):
-        self.stop_flag = True
-        if self.thread is not None:
-            self.thread.join(timeout=6)
-        inside = [x for x in self.samples if self.t_begin is not None and self.t_begin <= x[0] <= (self.t_end or 1e30)]
-        used = inside if inside else self.samples
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["NVML sampler unavailable"]}
+        time.sleep(0.005)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        samples = []
+        for ln in list(self.lines):
+            f = ln.split()
+            if len(f) == 5:
+                samples.append((float(f[0]), float(f[1]), float(f[2]), float(f[3]), int(f[4])))
+        inside = [x for x in samples if self.t_begin is not None and self.t_begin <= x[0] <= (self.t_end or 1e30)]
+        # fall back to the samples taken under load since the warm-up began
+        used = inside if inside else [x for x in samples if self.t_begin is None or x[0] <= (self.t_end or 1e30)][-20:]
         if not used:
             return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["no clock samples"]}
         mask = 0
@@ -222,6 +241,47 @@ def workload_config(args, world):
             "l2": "inputs (720 MB/step) exceed L2 (126 MB); no flush needed"}
 
 
+# ------------------------------------------------------------------------------------ pseudo-event leg
+def pseudo_events_leg(dev, peak, steps=10, warmup=3):
+    """BASELINE config C3 on one GPU: 32 pairs of 2048x1024 uint8 gray frames -> frame-pair pseudo-events
+    (f32 and u8 output) and shift-pair ISR (shipped cs2dsec parameters), images/s + achieved algorithmic
+    GB/s (SURVEY.md 8(d): (1+1+4)HW, (1+1+1)HW, (1+4)HW bytes per image).  Device resident, CUDA-event timed;
+    the 64 MB of inputs are re-read by the second pass out of L2 by design."""
+    import torch
+    import cmda_b200
+    from cmda_b200 import synth
+    Hc, Wc, S = 1024, 2048, 32
+    base = [synth.make_frame_pair(Hc, Wc, seed=synth.seed_for(3, k)) for k in range(2)]
+    now = torch.from_numpy(np.stack([base[k % 2][0] for k in range(S)])).to(dev)
+    front = torch.from_numpy(np.stack([base[k % 2][1] for k in range(S)])).to(dev)
+    for k in range(S):                      # make the 32 pairs distinct
+        now[k] = torch.roll(now[k], shifts=(3 * k, 5 * k), dims=(0, 1))
+        front[k] = torch.roll(front[k], shifts=(3 * k, 5 * k), dims=(0, 1))
+    out_isr = torch.empty((S, 1, Hc, Wc), dtype=torch.float32, device=dev)
+
+    def timed(fn):
+        for _ in range(warmup):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / steps
+
+    res = {"config": f"C3: {S} pairs of {Wc}x{Hc} uint8 gray frames, device resident"}
+    for name, fn, bpp in (
+            ("frame_pair_f32", lambda: cmda_b200.image_change_batch(now, front, want_f32=True, want_u8=False), 6),
+            ("frame_pair_u8", lambda: cmda_b200.image_change_batch(now, front, want_f32=False, want_u8=True), 3),
+            ("shift_pair_isr", lambda: cmda_b200.isr_batch(now, 1, (0.01, 1.01), 0.005, 0.1, "rightdown", out=out_isr), 5)):
+        ms = timed(fn)
+        gbs = S * Hc * Wc * bpp / (ms * 1e-3) / 1e9
+        res[name] = {"images_per_s": S / (ms * 1e-3), "ms_per_batch": ms, "algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / peak}
+    return res
+
+
 # ------------------------------------------------------------------------------------ GPU leg
 def run_gpu(args, rank, local_rank, world):
     import torch
@@ -251,12 +311,13 @@ def run_gpu(args, rank, local_rank, world):
         cmda_b200.events_vg_batch(store, starts, fins, args.bins, mode=args.mode, out=out)
 
     # ---- device-resident timing ------------------------------------------------------------
-    for _ in range(args.warmup):
-        step()
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        sampler.wait_ready()
+    for _ in range(args.warmup):
+        step()
+    barrier()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     # per-step phase events (cmda_profiler_attach) for the per-kernel roofline
     n_phase = 8
@@ -353,6 +414,9 @@ def run_gpu(args, rank, local_rank, world):
             cpu = {"value": rate, "unit": "Mevents/s", "cores": min(cores, nw), "kind": "port",
                    "sample": f"{nw} of the step's {WINDOWS_PER_GPU} windows x {args.events} events, one window "
                              f"per thread, {dt:.1f} s"}
+        pseudo = None
+        if world == 1 and not args.no_pseudo:
+            pseudo = pseudo_events_leg(dev, peak)
         line = {
             "metric": "voxelized_events_per_s", "value": value, "unit": "Mevents/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -362,7 +426,7 @@ def run_gpu(args, rank, local_rank, world):
             "e2e": {"value": e2e_value, "unit": "Mevents/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "steps": e2e_steps, "matches_device_path": same},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "cpu_baseline": cpu, "pseudo_events": pseudo,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -372,13 +436,14 @@ def run_gpu(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cmda_b200", choices=["cmda_b200", "reference"])
     ap.add_argument("--bins", type=int, default=5)
     ap.add_argument("--events", type=int, default=EVENTS_PER_WINDOW)
     ap.add_argument("--mode", default="auto", choices=["auto", "global", "tiled", "factored"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pseudo", action="store_true", help="skip the pseudo-event (config C3) leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cmda_b200" else args.warmup
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)

@@ -91,10 +91,16 @@ struct NormParams {
     float p_of_zero, n_of_zero;   // the normalised positive / negative part of a voxel whose part is 0
 };
 
+// x / den.  A zero numerator (every empty voxel) would send the IEEE division into its slow path; for a
+// positive finite den, +-0 / den is +-0, i.e. the numerator itself.
+__device__ __forceinline__ float div_fast_zero(float num, float den) {
+    return (num == 0.0f && den > 0.0f && den < INFINITY) ? num : __fdiv_rn(num, den);
+}
+
 __device__ __forceinline__ float zscore(float e, const NormParams& q) {
     if (!q.has_nz) return e;
     const float m = (e != 0.0f) ? 1.0f : 0.0f;                          // dsec.py:93 mask
-    return __fdiv_rn(__fmul_rn(m, __fsub_rn(e, q.mean)), q.den);        // dsec.py:94
+    return div_fast_zero(__fmul_rn(m, __fsub_rn(e, q.mean)), q.den);    // dsec.py:94
 }
 __device__ __forceinline__ float pos_part(float z, float clip) {
     const float p = z < 0.0f ? 0.0f : z;                                // dsec.py:108
@@ -162,7 +168,7 @@ __device__ __forceinline__ float norm_one(float e, const NormParams& q, bool enf
         // per-grid constant computed in make_norm_params (same operations, same bits)
         const bool neg = z < 0.0f;
         const float part = neg ? neg_part(z, q.clip) : pos_part(z, q.clip);
-        float v = __fdiv_rn(__fsub_rn(part, neg ? q.nmin : q.pmin), neg ? q.nden : q.pden);
+        float v = div_fast_zero(__fsub_rn(part, neg ? q.nmin : q.pmin), neg ? q.nden : q.pden);
         v = __fadd_rn(__fmul_rn(v, q.final_range), neg ? -q.final_range : 0.0f);         // * (r - 0) + 0 | * (0 - (-r)) + (-r)
         return neg ? __fadd_rn(q.p_of_zero, v) : __fadd_rn(v, q.n_of_zero);
     }

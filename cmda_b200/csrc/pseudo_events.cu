@@ -3,9 +3,9 @@
 //   K5 shift pair : /root/reference/mmseg/datasets/utils.py:87-152 (get_ic, get_image_change_from_pil)
 //
 // Both are u8 -> f32 element-wise maps around two global min/max pairs per term, so each
-// is two passes over the (L2-resident) u8 input: pass 1 reduces min/max of the clamped
-// positive and negative parts, pass 2 re-evaluates the difference and writes the result
-// with 128-bit stores.  There are only 256 distinct log values, so the logarithm is a
+// is two passes over the (L2-resident) u8 input: pass 1 reduces the min/max of the log
+// difference (the min/max of the clamped parts follow from it, every step in between being
+// monotone), pass 2 re-evaluates the difference and writes the result with 128-bit stores.  There are only 256 distinct log values, so the logarithm is a
 // 256-entry table the CALLER computes with numpy exactly as the reference does; every
 // other operation is an IEEE float32 op with one rounding, which makes the whole path
 // bit-exact against the reference.  HBM-bound: algorithmic bytes (1+1+4)·H·W per pair,
@@ -16,6 +16,15 @@ namespace cmda {
 
 constexpr int kPxPerThread = 4;
 constexpr int kImgThreads = 256;
+
+// The 256-entry log table lives in shared memory once per bank (32 KB): lane l reads entry v at
+// word v * 32 + l, i.e. always from its own bank -- a data-dependent table lookup with no bank
+// conflicts.  The fill reads the kernel-parameter copy with a warp-uniform index (one broadcast).
+constexpr int kLutWords = 256 * 32;
+__device__ __forceinline__ void load_banked_lut(float* __restrict__ s_lut, const LogLut& in) {
+    for (int i = threadIdx.x; i < kLutWords; i += blockDim.x) s_lut[i] = in.v[i >> 5];
+}
+#define CMDA_LUT(v) s_lut[((v) << 5) | (threadIdx.x & 31)]
 
 // Direction codes of one term: 0 left, 1 right, 2 up, 3 down (utils.py:129-132).
 struct TermList {
@@ -55,57 +64,87 @@ __device__ __forceinline__ void split_clamp(float d, float thr, float clip, floa
     neg = fminf(fmaxf(neg, -clip), 0.0f);
 }
 
-// Running min/max of one term, kept as unsigned bit patterns so that a zero-initialised
-// workspace is the neutral element of every slot and the merge is atomicMax (exact and
-// order independent): [0] max pos, [1] ~min pos, [2] max |neg|, [3] ~min |neg|.
+// Every step between the log difference d and the clamped positive / negative part is a monotone
+// non-decreasing float32 map (dead zone, sign split, clamp: utils.py:95-100), so the global min / max of
+// the two parts that tensor_normalize_to_range needs (utils.py:10-14) are the parts of the global min /
+// max of d.  Pass 1 therefore only tracks d's range, as order-preserving unsigned keys so that a
+// zero-initialised workspace is the neutral element and the merge is an exact, order-independent
+// atomicMax: slot [0] = max key(d), slot [1] = max ~key(d) (i.e. the minimum).
+__device__ __forceinline__ unsigned ordered_key(float f) {
+    const unsigned b = __float_as_uint(f);
+    return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+}
+__device__ __forceinline__ float ordered_unkey(unsigned k) {
+    return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xffffffffu));
+}
+
 struct MinMaxAcc {
-    unsigned s[4];
-    __device__ __forceinline__ void init() { s[0] = s[1] = s[2] = s[3] = 0u; }
-    __device__ __forceinline__ void add(float pos, float neg) {
-        const unsigned pb = __float_as_uint(pos + 0.0f);          // +0.0f folds -0 into +0
-        const unsigned nb = __float_as_uint(fabsf(neg));
-        s[0] = max(s[0], pb);
-        s[1] = max(s[1], ~pb);
-        s[2] = max(s[2], nb);
-        s[3] = max(s[3], ~nb);
-    }
+    float dmin, dmax;
+    __device__ __forceinline__ void init() { dmin = INFINITY; dmax = -INFINITY; }
+    __device__ __forceinline__ void add(float d) { dmin = fminf(dmin, d); dmax = fmaxf(dmax, d); }
 };
 
 struct TermRange {
     float pmin, pden, nmin, nden;
+    float p_of_zero, n_of_zero;   // normalised part of a pixel whose part is 0 (the side of zero it is not on)
 };
 
-__device__ __forceinline__ TermRange decode_range(const unsigned* __restrict__ slots) {
-    const float pmax = __uint_as_float(slots[0]);
-    const float pmin = __uint_as_float(~slots[1]);
-    const float nmin = -__uint_as_float(slots[2]);
-    const float nmax = -__uint_as_float(~slots[3]);
+// tensor_normalize_to_range of one part (utils.py:10-14): positive part -> [0, 1], negative part -> [-1, 0]
+// x / den for a positive finite den.  A zero numerator (every pixel of the dead zone) would send the
+// IEEE division into its slow path (FCHK flags it); +-0 / den is +-0, so the quotient is the numerator.
+__device__ __forceinline__ float div_pos_den(float num, float den) {
+    return (num == 0.0f && den > 0.0f) ? num : __fdiv_rn(num, den);
+}
+
+__device__ __forceinline__ float normalize_pos(float pos, const TermRange& r) {
+    const float p = div_pos_den(__fsub_rn(pos, r.pmin), r.pden);
+    return __fadd_rn(__fmul_rn(p, 1.0f), 0.0f);             // * (1 - 0) + 0
+}
+__device__ __forceinline__ float normalize_neg(float neg, const TermRange& r) {
+    const float n = div_pos_den(__fsub_rn(neg, r.nmin), r.nden);
+    return __fadd_rn(__fmul_rn(n, 1.0f), -1.0f);            // * (0 - (-1)) + (-1)
+}
+
+__device__ __forceinline__ TermRange decode_range(const unsigned* __restrict__ slots, float thr, float clip) {
+    const float dmax = ordered_unkey(slots[0]);
+    const float dmin = ordered_unkey(~slots[1]);
+    float pmax, pmin, nmax, nmin;
+    split_clamp(dmax, thr, clip, pmax, nmax);
+    split_clamp(dmin, thr, clip, pmin, nmin);
     TermRange r;
     r.pmin = pmin;
     r.pden = __fadd_rn(__fsub_rn(pmax, pmin), 1e-8f);   // tensor_max - tensor_min + 1e-8
     r.nmin = nmin;
     r.nden = __fadd_rn(__fsub_rn(nmax, nmin), 1e-8f);
+    r.p_of_zero = normalize_pos(0.0f, r);
+    r.n_of_zero = normalize_neg(0.0f, r);
     return r;
 }
 
-// tensor_normalize_to_range of both parts and their sum (utils.py:101-104)
-__device__ __forceinline__ float normalize_term(float pos, float neg, const TermRange& r) {
-    float p = __fdiv_rn(__fsub_rn(pos, r.pmin), r.pden);
-    p = __fadd_rn(__fmul_rn(p, 1.0f), 0.0f);               // * (1 - 0) + 0
-    float n = __fdiv_rn(__fsub_rn(neg, r.nmin), r.nden);
-    n = __fadd_rn(__fmul_rn(n, 1.0f), -1.0f);              // * (0 - (-1)) + (-1)
-    return __fadd_rn(p, n);
+// dead zone, sign split, clamp, both normalisations and their sum (utils.py:95-104) for one pixel.  Only
+// the part on d's side of zero varies; the other part is 0 and its normalised value is the per-image
+// constant above (same operations, same bits).
+__device__ __forceinline__ float normalize_term(float d, float thr, float clip, const TermRange& r) {
+    if (fabsf(d) <= thr) d = 0.0f;
+    if (d < 0.0f) {
+        const float neg = fminf(fmaxf(d, -clip), 0.0f);
+        return __fadd_rn(r.p_of_zero, normalize_neg(neg, r));
+    }
+    const float pos = fminf(fmaxf(d, 0.0f), clip);
+    return __fadd_rn(normalize_pos(pos, r), r.n_of_zero);
 }
 
 template <int NT>
 __device__ __forceinline__ void flush_minmax(MinMaxAcc (&acc)[NT], unsigned* __restrict__ slots) {
 #pragma unroll
-    for (int k = 0; k < NT; ++k)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const unsigned v = __reduce_max_sync(0xffffffffu, acc[k].s[j]);
-            if ((threadIdx.x & 31) == 0 && v != 0u) atomicMax(slots + k * 4 + j, v);
+    for (int k = 0; k < NT; ++k) {
+        const unsigned hi = __reduce_max_sync(0xffffffffu, ordered_key(acc[k].dmax));
+        const unsigned lo = __reduce_max_sync(0xffffffffu, ~ordered_key(acc[k].dmin));
+        if ((threadIdx.x & 31) == 0) {
+            atomicMax(slots + k * 4 + 0, hi);
+            atomicMax(slots + k * 4 + 1, lo);
         }
+    }
 }
 
 // ------------------------------------------------------------------ K5 shift pair
@@ -113,8 +152,8 @@ template <int NT>
 __global__ void __launch_bounds__(kImgThreads)
 isr_minmax_kernel(const uint8_t* __restrict__ gray, int H, int W, int shift, TermList terms, LogLut lut_in,
                   float thr, float clip, unsigned* __restrict__ ws) {
-    __shared__ float lut[256];
-    if (threadIdx.x < 256) lut[threadIdx.x] = lut_in.v[threadIdx.x];
+    __shared__ float s_lut[kLutWords];
+    load_banked_lut(s_lut, lut_in);
     __syncthreads();
     const int img = blockIdx.y;
     const uint8_t* g = gray + static_cast<size_t>(img) * H * W;
@@ -125,13 +164,10 @@ isr_minmax_kernel(const uint8_t* __restrict__ gray, int H, int W, int shift, Ter
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < npx;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const int r = static_cast<int>(i / W), c = static_cast<int>(i - static_cast<long long>(r) * W);
-        const float base = lut[__ldg(g + i)];
+        const float base = CMDA_LUT(__ldg(g + i));
 #pragma unroll
         for (int k = 0; k < NT; ++k) {
-            const float d = __fsub_rn(lut[shifted_at(g, H, W, r, c, shift, terms.dir[k])], base);  // utils.py:92
-            float pos, neg;
-            split_clamp(d, thr, clip, pos, neg);
-            acc[k].add(pos, neg);
+            acc[k].add(__fsub_rn(CMDA_LUT(shifted_at(g, H, W, r, c, shift, terms.dir[k])), base));  // utils.py:92
         }
     }
     flush_minmax<NT>(acc, ws + static_cast<size_t>(img) * 16);
@@ -141,15 +177,15 @@ template <int NT, bool VEC>
 __global__ void __launch_bounds__(kImgThreads)
 isr_apply_kernel(const uint8_t* __restrict__ gray, int H, int W, int shift, TermList terms, LogLut lut_in, float thr,
                  float clip, const unsigned* __restrict__ ws, float* __restrict__ out) {
-    __shared__ float lut[256];
-    if (threadIdx.x < 256) lut[threadIdx.x] = lut_in.v[threadIdx.x];
+    __shared__ float s_lut[kLutWords];
+    load_banked_lut(s_lut, lut_in);
     __syncthreads();
     const int img = blockIdx.y;
     const uint8_t* g = gray + static_cast<size_t>(img) * H * W;
     float* o = out + static_cast<size_t>(img) * H * W;
     TermRange rng[NT];
 #pragma unroll
-    for (int k = 0; k < NT; ++k) rng[k] = decode_range(ws + static_cast<size_t>(img) * 16 + k * 4);
+    for (int k = 0; k < NT; ++k) rng[k] = decode_range(ws + static_cast<size_t>(img) * 16 + k * 4, thr, clip);
     const float inv = NT == 4 ? 0.25f : 0.5f;   // x / 4 and x / 2 are exact scalings
     const long long npx = static_cast<long long>(H) * W;
     const long long ngroups = (npx + kPxPerThread - 1) / kPxPerThread;
@@ -163,14 +199,12 @@ isr_apply_kernel(const uint8_t* __restrict__ gray, int H, int W, int shift, Term
             res[j] = 0.0f;
             if (i < npx) {
                 const int r = static_cast<int>(i / W), c = static_cast<int>(i - static_cast<long long>(r) * W);
-                const float base = lut[__ldg(g + i)];
+                const float base = CMDA_LUT(__ldg(g + i));
                 float sum = 0.0f;
 #pragma unroll
                 for (int k = 0; k < NT; ++k) {
-                    const float d = __fsub_rn(lut[shifted_at(g, H, W, r, c, shift, terms.dir[k])], base);
-                    float pos, neg;
-                    split_clamp(d, thr, clip, pos, neg);
-                    const float t = __fmul_rn(normalize_term(pos, neg, rng[k]), inv);
+                    const float d = __fsub_rn(CMDA_LUT(shifted_at(g, H, W, r, c, shift, terms.dir[k])), base);
+                    const float t = __fmul_rn(normalize_term(d, thr, clip, rng[k]), inv);
                     sum = (k == 0) ? t : __fadd_rn(sum, t);       // utils.py:137 / 151, left to right
                 }
                 res[j] = sum;
@@ -186,12 +220,114 @@ isr_apply_kernel(const uint8_t* __restrict__ gray, int H, int W, int shift, Term
     }
 }
 
+// ------------------------------------------------------------------ K5 shift pair, vector path
+// The fast path (W % 4 == 0, 4-byte aligned rows): a thread produces 4 consecutive pixels of one row from
+// 32-bit loads -- its own word, the word `shift` rows above / below, and the two aligned words that hold the
+// columns `shift` to the left / right (funnel-shifted into place); all of them L1 / L2 hits after the first
+// touch.  The shifted copy of utils.py:129-132 never reads outside the image: border pixels stay unshifted,
+// which is a per-byte select here.  Same arithmetic as the generic kernels above; rows are the work items of
+// persistent CTAs so that the bank-replicated log table is filled once per CTA.
+__device__ __forceinline__ unsigned load_cols_u32(const uint8_t* __restrict__ row, int W, int start) {
+    // byte j of the result = row[start + j] for every start + j inside [0, W); bytes outside the row are
+    // undefined (the caller's border select discards them)
+    if (start < 0) {
+        if (start <= -4) return 0u;
+        return __ldg(reinterpret_cast<const unsigned*>(row)) << (8 * -start);
+    }
+    if (start > W - 4) {
+        if (start >= W) return 0u;
+        return __ldg(reinterpret_cast<const unsigned*>(row + W - 4)) >> (8 * (start - (W - 4)));
+    }
+    const int a = start & ~3, off = start - a;
+    const unsigned w0 = __ldg(reinterpret_cast<const unsigned*>(row + a));
+    if (off == 0) return w0;
+    const unsigned w1 = __ldg(reinterpret_cast<const unsigned*>(row + a + 4));     // a <= W - 8 here
+    return __funnelshift_r(w0, w1, off * 8);
+}
+
+template <int NT, bool APPLY>
+__global__ void __launch_bounds__(256)
+isr_vec_kernel(const uint8_t* __restrict__ gray, int S, int H, int W, int shift, TermList terms, LogLut lut_in, float thr,
+               float clip, unsigned* __restrict__ ws, float* __restrict__ out) {
+    __shared__ float s_lut[kLutWords];
+    load_banked_lut(s_lut, lut_in);
+    __syncthreads();
+    const int words = W >> 2;
+    const int cw = blockIdx.x * 256 + threadIdx.x;
+    const int c = cw * 4;
+    const float inv = NT == 4 ? 0.25f : 0.5f;   // x / 4 and x / 2 are exact scalings
+    const long long n_rows = static_cast<long long>(S) * H;
+    // consecutive rows per CTA: an image's rows stay together (one min/max flush per image)
+    const long long per_cta = (n_rows + gridDim.y - 1) / gridDim.y;
+    const long long row_begin = per_cta * blockIdx.y, row_end = min(row_begin + per_cta, n_rows);
+    int cur_img = -1;
+    TermRange rng[NT];
+    MinMaxAcc acc[NT];
+#pragma unroll
+    for (int k = 0; k < NT; ++k) acc[k].init();
+    for (long long row = row_begin; row < row_end; ++row) {
+        const int img = static_cast<int>(row / H), r = static_cast<int>(row - static_cast<long long>(img) * H);
+        if (img != cur_img) {
+            if (!APPLY && cur_img >= 0) {
+                flush_minmax<NT>(acc, ws + static_cast<size_t>(cur_img) * 16);
+#pragma unroll
+                for (int k = 0; k < NT; ++k) acc[k].init();
+            }
+            if (APPLY) {
+#pragma unroll
+                for (int k = 0; k < NT; ++k) rng[k] = decode_range(ws + static_cast<size_t>(img) * 16 + k * 4, thr, clip);
+            }
+            cur_img = img;
+        }
+        if (cw >= words) continue;
+        const uint8_t* g = gray + static_cast<size_t>(img) * H * W;
+        const uint8_t* grow = g + static_cast<size_t>(r) * W;
+        const unsigned base_w = __ldg(reinterpret_cast<const unsigned*>(grow + c));
+        float base[4], res[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) base[j] = CMDA_LUT((base_w >> (8 * j)) & 255u);
+#pragma unroll
+        for (int k = 0; k < NT; ++k) {
+            const int dir = terms.dir[k];
+            unsigned shw;
+            if (dir >= 2) {                          // row shift: one aligned word holds the four shifted pixels
+                int rr = r;
+                if (dir == 2) { if (r < H - shift) rr = r + shift; }      // up:   utils.py:131
+                else { if (r >= shift) rr = r - shift; }                  // down: utils.py:132
+                shw = __ldg(reinterpret_cast<const unsigned*>(g + static_cast<size_t>(rr) * W + c));
+            } else {
+                const int delta = dir == 0 ? shift : -shift;              // left: c + s (utils.py:129); right: c - s (utils.py:130)
+                shw = load_cols_u32(grow, W, c + delta);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int cj = c + j;
+                    const bool shifted = dir == 0 ? (cj < W - shift) : (cj >= shift);
+                    if (!shifted) shw = (shw & ~(255u << (8 * j))) | (base_w & (255u << (8 * j)));   // border: unshifted
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float d = __fsub_rn(CMDA_LUT((shw >> (8 * j)) & 255u), base[j]);   // utils.py:92
+                if (APPLY) {
+                    const float tv = __fmul_rn(normalize_term(d, thr, clip, rng[k]), inv);
+                    res[j] = (k == 0) ? tv : __fadd_rn(res[j], tv);                       // utils.py:137 / 151, left to right
+                } else {
+                    acc[k].add(d);
+                }
+            }
+        }
+        if (APPLY) stg_stream_f4(out + static_cast<size_t>(img) * H * W + static_cast<size_t>(r) * W + c,
+                                 make_float4(res[0], res[1], res[2], res[3]));
+    }
+    if (!APPLY && cur_img >= 0) flush_minmax<NT>(acc, ws + static_cast<size_t>(cur_img) * 16);
+}
+
 // ------------------------------------------------------------------ K4 frame pair
 __global__ void __launch_bounds__(kImgThreads)
 pair_minmax_kernel(const uint8_t* __restrict__ now, const uint8_t* __restrict__ front, long long npx, bool vec,
                    LogLut lut_in, float thr, float clip, unsigned* __restrict__ ws) {
-    __shared__ float lut[256];
-    if (threadIdx.x < 256) lut[threadIdx.x] = lut_in.v[threadIdx.x];
+    __shared__ float s_lut[kLutWords];
+    load_banked_lut(s_lut, lut_in);
     __syncthreads();
     const int img = blockIdx.y;
     const uint8_t* a = now + static_cast<size_t>(img) * npx;
@@ -209,19 +345,13 @@ pair_minmax_kernel(const uint8_t* __restrict__ now, const uint8_t* __restrict__ 
             for (int q = 0; q < 4; ++q)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float d = __fsub_rn(lut[(wa[q] >> (8 * j)) & 255u], lut[(wb[q] >> (8 * j)) & 255u]);  // :21
-                    float pos, neg;
-                    split_clamp(d, thr, clip, pos, neg);
-                    acc[0].add(pos, neg);
+                    acc[0].add(__fsub_rn(CMDA_LUT((wa[q] >> (8 * j)) & 255u), CMDA_LUT((wb[q] >> (8 * j)) & 255u)));  // :21
                 }
         }
     } else {
         for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < npx;
              i += static_cast<long long>(gridDim.x) * blockDim.x) {
-            const float d = __fsub_rn(lut[__ldg(a + i)], lut[__ldg(b + i)]);
-            float pos, neg;
-            split_clamp(d, thr, clip, pos, neg);
-            acc[0].add(pos, neg);
+            acc[0].add(__fsub_rn(CMDA_LUT(__ldg(a + i)), CMDA_LUT(__ldg(b + i))));
         }
     }
     flush_minmax<1>(acc, ws + static_cast<size_t>(img) * 16);
@@ -238,13 +368,13 @@ __global__ void __launch_bounds__(kImgThreads)
 pair_apply_kernel(const uint8_t* __restrict__ now, const uint8_t* __restrict__ front, long long npx, LogLut lut_in,
                   float thr, float clip, const unsigned* __restrict__ ws, float* __restrict__ out_f32,
                   uint8_t* __restrict__ out_u8) {
-    __shared__ float lut[256];
-    if (threadIdx.x < 256) lut[threadIdx.x] = lut_in.v[threadIdx.x];
+    __shared__ float s_lut[kLutWords];
+    load_banked_lut(s_lut, lut_in);
     __syncthreads();
     const int img = blockIdx.y;
     const uint8_t* a = now + static_cast<size_t>(img) * npx;
     const uint8_t* b = front + static_cast<size_t>(img) * npx;
-    const TermRange rng = decode_range(ws + static_cast<size_t>(img) * 16);
+    const TermRange rng = decode_range(ws + static_cast<size_t>(img) * 16, thr, clip);
     float* of = out_f32 ? out_f32 + static_cast<size_t>(img) * npx : nullptr;
     uint8_t* ou = out_u8 ? out_u8 + static_cast<size_t>(img) * npx : nullptr;
     if (VEC) {
@@ -260,10 +390,8 @@ pair_apply_kernel(const uint8_t* __restrict__ now, const uint8_t* __restrict__ f
                 float r[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float d = __fsub_rn(lut[(wa[q] >> (8 * j)) & 255u], lut[(wb[q] >> (8 * j)) & 255u]);
-                    float pos, neg;
-                    split_clamp(d, thr, clip, pos, neg);
-                    r[j] = normalize_term(pos, neg, rng);
+                    const float d = __fsub_rn(CMDA_LUT((wa[q] >> (8 * j)) & 255u), CMDA_LUT((wb[q] >> (8 * j)) & 255u));
+                    r[j] = normalize_term(d, thr, clip, rng);
                 }
                 if (of) stg_stream_f4(of + i * 16 + q * 4, make_float4(r[0], r[1], r[2], r[3]));
                 packed[q] = quantise_u8(r[0]) | (quantise_u8(r[1]) << 8) | (quantise_u8(r[2]) << 16) |
@@ -274,10 +402,8 @@ pair_apply_kernel(const uint8_t* __restrict__ now, const uint8_t* __restrict__ f
     } else {
         for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < npx;
              i += static_cast<long long>(gridDim.x) * blockDim.x) {
-            const float d = __fsub_rn(lut[__ldg(a + i)], lut[__ldg(b + i)]);
-            float pos, neg;
-            split_clamp(d, thr, clip, pos, neg);
-            const float r = normalize_term(pos, neg, rng);
+            const float d = __fsub_rn(CMDA_LUT(__ldg(a + i)), CMDA_LUT(__ldg(b + i)));
+            const float r = normalize_term(d, thr, clip, rng);
             if (of) of[i] = r;
             if (ou) ou[i] = static_cast<uint8_t>(quantise_u8(r));
         }
@@ -339,6 +465,23 @@ int launch_isr(const uint8_t* gray, int S, int H, int W, int shift, int directio
     const TermList terms = terms_of(direction);
     const long long npx = static_cast<long long>(H) * W;
     CMDA_CUDA_TRY(cudaMemsetAsync(ws, 0, sizeof(unsigned) * 16 * S, s));
+    if ((W % 4) == 0 && W >= 8 && (reinterpret_cast<uintptr_t>(gray) & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+        // vector fast path
+        const int gx = (W / 4 + 255) / 256;
+        const long long n_rows = static_cast<long long>(S) * H;
+        long long gy = (148LL * 6 + gx - 1) / gx;          // 6 CTAs of 33 KB shared memory per SM
+        if (gy > n_rows) gy = n_rows;
+        dim3 grid(gx, static_cast<unsigned>(gy));
+        if (terms.n == 4) {
+            isr_vec_kernel<4, false><<<grid, 256, 0, s>>>(gray, S, H, W, shift, terms, lut, thr, clip, ws, out);
+            isr_vec_kernel<4, true><<<grid, 256, 0, s>>>(gray, S, H, W, shift, terms, lut, thr, clip, ws, out);
+        } else {
+            isr_vec_kernel<2, false><<<grid, 256, 0, s>>>(gray, S, H, W, shift, terms, lut, thr, clip, ws, out);
+            isr_vec_kernel<2, true><<<grid, 256, 0, s>>>(gray, S, H, W, shift, terms, lut, thr, clip, ws, out);
+        }
+        CMDA_LAUNCH_CHECK();
+        return CMDA_OK;
+    }
     // images per launch are bounded by gridDim.y
     for (int s0 = 0; s0 < S; s0 += 32768) {
         const int sn = (S - s0) < 32768 ? (S - s0) : 32768;
