@@ -26,7 +26,7 @@ int launch_pair(const uint8_t*, const uint8_t*, int, int, int, const float*, flo
 size_t tiled_workspace_bytes(int64_t total_events, int S, int H, int W, int B);
 int tiled_supported(int H, int W, int B);
 int factored_supported(int H, int W, int B);
-size_t factored_scratch_bytes(int group, int H, int W);
+size_t factored_scratch_bytes(int group, int H, int W, int B);
 int factored_max_maps(void);
 int launch_factored(const uint32_t*, const uint16_t*, const uint16_t*, const uint8_t*, const WindowTable&, int, long long,
                     const float*, int, int, int, void*, int64_t*, float*, PartialStats*, void*, size_t, cudaStream_t);
@@ -120,7 +120,7 @@ size_t cmda_events_vg_workspace_bytes(int64_t total_events, int S, int H, int W,
     size_t need = stats_bytes(S) + acc_bytes(group, H, W, B);       // both paths sum into the int64 grid
     if (mode == CMDA_VOXEL_TILED && tiled_supported(H, W, B)) need += tiled_workspace_bytes(total_events, S, H, W, B);
     if ((mode == CMDA_VOXEL_FACTORED || mode == CMDA_VOXEL_AUTO) && factored_supported(H, W, B))
-        need += factored_scratch_bytes(group, H, W);
+        need += factored_scratch_bytes(group, H, W, B);
     return need + 256;
 }
 

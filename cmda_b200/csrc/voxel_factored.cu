@@ -173,24 +173,25 @@ sensor_accumulate_kernel(const uint32_t* __restrict__ t, const uint16_t* __restr
     }
 }
 
-// R cells -> planes, in place (B > 1): plane_b = C_b - F_b + F_(b-1) (the temporal corners 1 - f and
-// f of dsec.py:49-52) as a float64 holding the exact 2^-30 fixed-point integer.  One thread per
-// (window, raw pixel), bins in order.
-__global__ void __launch_bounds__(256)
-plane_finalize_kernel(long long* __restrict__ R, int B, size_t plane) {
-    const size_t P = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (P >= plane) return;
-    long long* r = R + static_cast<size_t>(blockIdx.y) * B * plane + P;
+// One R cell chain -> planes: plane_b = C_b - F_b + F_(b-1), the temporal corners 1 - f and f of
+// dsec.py:49-52, as a float64 holding the exact 2^-30 fixed-point integer; for B == 1 the plane is the
+// signed event count.  f(b, value) is called for b = 0 .. B-1 in order.
+template <typename F>
+__device__ __forceinline__ void planes_of_pixel(const void* __restrict__ R, unsigned s, unsigned P, unsigned npx, int B, F&& f) {
+    if (B == 1) {
+        f(0, static_cast<double>(__ldg(reinterpret_cast<const int*>(R) + static_cast<size_t>(s) * npx + P)) * 1073741824.0);
+        return;
+    }
+    const long long* r = reinterpret_cast<const long long*>(R) + static_cast<size_t>(s) * B * npx + P;
     long long f_prev = 0;
     for (int b = 0; b < B; ++b) {
-        const long long cell = r[static_cast<size_t>(b) * plane];
-        if (cell == 0 && f_prev == 0) continue;                    // +0.0 has the all-zero pattern already
-        const long long f = static_cast<long long>(static_cast<unsigned long long>(cell) << (64 - kCountShift)) >>
-                            (64 - kCountShift);                    // low 44 bits, signed
-        const long long c = (cell - f) >> kCountShift;
-        const long long pl = c * (1LL << kFracBits) - f + f_prev;  // 2^-24 fixed point, |pl| < 2^44
-        f_prev = f;
-        r[static_cast<size_t>(b) * plane] = __double_as_longlong(static_cast<double>(pl * 64));   // 2^-30, exact
+        const long long cell = __ldg(r + static_cast<size_t>(b) * npx);
+        const long long fr = static_cast<long long>(static_cast<unsigned long long>(cell) << (64 - kCountShift)) >>
+                             (64 - kCountShift);                   // low 44 bits, signed
+        const long long c = (cell - fr) >> kCountShift;
+        const long long pl = c * (1LL << kFracBits) - fr + f_prev; // 2^-24 fixed point, |pl| < 2^44
+        f_prev = fr;
+        f(b, static_cast<double>(pl * 64));                        // 2^-30 fixed point, exact
     }
 }
 
@@ -243,6 +244,25 @@ rectify_index_build_kernel(const float2* __restrict__ maps, MapSlots ms, int H, 
     }
 }
 
+// The slots of a cell fill in atomic order; sorting them (<= 4 values) makes every later walk over the
+// cells deterministic.  One thread per cell.
+__global__ void __launch_bounds__(256)
+rectify_index_sort_kernel(MapSlots ms, int H, int W, char* __restrict__ index_ws, size_t ncells_padded) {
+    const int slot = blockIdx.y;
+    const unsigned ncells = static_cast<unsigned>(H + 1) * static_cast<unsigned>(W + 1);
+    const unsigned c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncells) return;
+    const MapIndex ix = map_index_at(index_ws, slot, ncells_padded, static_cast<size_t>(H) * W);
+    const unsigned n = min(ix.cnt[c], static_cast<unsigned>(kCellSlots));
+    if (n < 2) return;
+    uint4 v = ix.slots[c];
+    unsigned e[4] = {v.x, n > 1 ? v.y : 0xffffffffu, n > 2 ? v.z : 0xffffffffu, n > 3 ? v.w : 0xffffffffu};
+#define CMDA_CSWAP(i, j) { const unsigned lo = min(e[i], e[j]), hi = max(e[i], e[j]); e[i] = lo; e[j] = hi; }
+    CMDA_CSWAP(0, 1) CMDA_CSWAP(2, 3) CMDA_CSWAP(0, 2) CMDA_CSWAP(1, 3) CMDA_CSWAP(1, 2)
+#undef CMDA_CSWAP
+    ix.slots[c] = make_uint4(e[0], e[1], e[2], e[3]);
+}
+
 // ---- gather stencil of one map ---------------------------------------------------------------------
 // The rectification splat is a sparse linear map from sensor space to the rectified grid (about four
 // non-zeros per output pixel) that depends on the map only, not on the window or the bin.  It is
@@ -270,9 +290,12 @@ __device__ __forceinline__ Stencil stencil_at(char* base, int slot, size_t npx) 
     return st;
 }
 
-// Calls f(P, weight) for every raw pixel whose corner set contains output pixel (X, Y).
+// Calls f(P, weight) for every raw pixel whose corner set contains output pixel (X, Y): cells in a fixed
+// order, the (sorted) inline slots of each in order, then the overflow list of overfull cells (whose order
+// is not reproducible: callers that need a fixed order must not use it).  Returns true if a cell overflowed.
 template <typename F>
-__device__ __forceinline__ void for_each_source(const MapIndex& ix, const float2* __restrict__ map, int X, int Y, int W, F&& f) {
+__device__ __forceinline__ bool for_each_source(const MapIndex& ix, const float2* __restrict__ map, int X, int Y, int W,
+                                                bool with_overflow, F&& f) {
     unsigned ovf = 0;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -290,7 +313,7 @@ __device__ __forceinline__ void for_each_source(const MapIndex& ix, const float2
             }
         if (n > kCellSlots) ovf |= 1u << q;
     }
-    if (ovf) {   // overfull cells: their other pixels are in the overflow list
+    if (ovf && with_overflow) {   // overfull cells: their other pixels are in the overflow list
         const unsigned no = __ldg(ix.ovf_cnt);
         for (int q = 0; q < 4; ++q) {
             if (!(ovf & (1u << q))) continue;
@@ -304,6 +327,7 @@ __device__ __forceinline__ void for_each_source(const MapIndex& ix, const float2
             }
         }
     }
+    return ovf != 0;
 }
 
 __global__ void __launch_bounds__(256)
@@ -318,12 +342,16 @@ stencil_build_kernel(const float2* __restrict__ maps, MapSlots ms, int H, int W,
     const Stencil sc = stencil_at(stencil_ws, slot, npx);
     const int X = static_cast<int>(px % static_cast<unsigned>(W)), Y = static_cast<int>(px / static_cast<unsigned>(W));
     unsigned n = 0;
-    for_each_source(ix, map, X, Y, W, [&](unsigned P, float w) {
+    const bool overfull = for_each_source(ix, map, X, Y, W, false, [&](unsigned P, float w) {
         if (w == 0.0f) return;
-        if (n < kEll) { sc.P[n * npx + px] = P; sc.w[n * npx + px] = w; }
+        if (n < kEll) {   // the source pixel as (row << 16 | column): the gather needs no division
+            sc.P[n * npx + px] = ((P / static_cast<unsigned>(W)) << 16) | (P % static_cast<unsigned>(W));
+            sc.w[n * npx + px] = w;
+        }
         ++n;
     });
-    sc.n[px] = static_cast<unsigned char>(n <= kEll ? n : kEllOverflow);
+    // a row is usable when it is complete and its order reproducible (sorted slots only)
+    sc.n[px] = static_cast<unsigned char>((n <= kEll && !overfull) ? n : kEllOverflow);
 }
 
 // ---- stage B ----------------------------------------------------------------------------------
@@ -333,55 +361,150 @@ struct GatherStats {
     float mn, mx;
 };
 
-// One thread per output pixel, all B bins.  BMAX: compile-time bound of the bin accumulators.
-template <bool HAS_T, int BMAX>
-__global__ void __launch_bounds__(kGatherThreads)
+// ---- stage B: fused plane finalisation + gather, one CTA per output tile -----------------------------
+// A CTA owns a kOutW x kOutH tile of OUTPUT pixels of one window.  The raw pixels its stencil rows refer to
+// lie in a small box of the sensor (the map is smooth); the box is known per (map, tile) from
+// out_tile_box_kernel.  The CTA stages the R cells of the box (row segments: coalesced), turns them into
+// planes in shared memory, then every thread gathers its output pixel from shared memory: R is read once,
+// no intermediate plane buffer exists, and the only global traffic besides R is the stencil row and the
+// output.  Tiles whose box does not fit (degenerate maps) or whose rows are incomplete gather straight from
+// R, one pixel at a time.
+constexpr int kOutW = 64, kOutH = 8, kOutThreads = kOutW * kOutH;
+constexpr int kStageBytes = 64 * 1024;       // shared memory for the staged planes of one tile
+
+__global__ void __launch_bounds__(kOutThreads)
+out_tile_box_kernel(MapSlots ms, int H, int W, char* __restrict__ stencil_ws, int4* __restrict__ boxes) {
+    const int slot = blockIdx.y;
+    const unsigned npx = static_cast<unsigned>(H) * static_cast<unsigned>(W);
+    const int tiles_x = (W + kOutW - 1) / kOutW;
+    const int X = (blockIdx.x % tiles_x) * kOutW + (threadIdx.x % kOutW), Y = (blockIdx.x / tiles_x) * kOutH + (threadIdx.x / kOutW);
+    const Stencil sc = stencil_at(stencil_ws, slot, npx);
+    int x0 = INT32_MAX, y0 = INT32_MAX, x1 = -1, y1 = -1, bad = 0;
+    if (X < W && Y < H) {
+        const unsigned px = static_cast<unsigned>(Y) * W + X;
+        const unsigned n = sc.n[px];
+        if (n == kEllOverflow) bad = 1;
+        else
+            for (unsigned k = 0; k < n; ++k) {
+                const unsigned P = sc.P[k * npx + px];
+                const int pxx = static_cast<int>(P & 0xffffu), pyy = static_cast<int>(P >> 16);
+                x0 = min(x0, pxx); x1 = max(x1, pxx); y0 = min(y0, pyy); y1 = max(y1, pyy);
+            }
+    }
+    __shared__ int s_r[5][kOutThreads / 32];
+    x0 = __reduce_min_sync(0xffffffffu, x0); y0 = __reduce_min_sync(0xffffffffu, y0);
+    x1 = __reduce_max_sync(0xffffffffu, x1); y1 = __reduce_max_sync(0xffffffffu, y1);
+    bad = __reduce_max_sync(0xffffffffu, bad);
+    const int wid = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { s_r[0][wid] = x0; s_r[1][wid] = y0; s_r[2][wid] = x1; s_r[3][wid] = y1; s_r[4][wid] = bad; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kOutThreads / 32; ++w) {
+            x0 = min(x0, s_r[0][w]); y0 = min(y0, s_r[1][w]); x1 = max(x1, s_r[2][w]); y1 = max(y1, s_r[3][w]);
+            bad = max(bad, s_r[4][w]);
+        }
+        int4 box = make_int4(0, 0, 0, 0);                          // w == 0, h == 0: nothing to stage
+        if (bad) box = make_int4(0, 0, -1, -1);                    // incomplete rows: per-pixel path
+        else if (x1 >= x0) box = make_int4(x0, y0, x1 - x0 + 1, y1 - y0 + 1);
+        boxes[static_cast<size_t>(slot) * gridDim.x + blockIdx.x] = box;
+    }
+}
+
+template <int BT>
+struct GatherRow {
+    double v[BT];
+};
+// Per-pixel path: walks the cell lists (overflow list included) and reads R directly.  Integer accumulation
+// (2^-30 quanta) keeps the sum independent of the order of the overflow list.
+template <int BT>
+__device__ __noinline__ GatherRow<BT> gather_pixel_from_cells(const void* __restrict__ R, unsigned s, unsigned npx,
+                                                              const float2* __restrict__ map, MapIndex ix, int X, int Y,
+                                                              int W, int B) {
+    long long iacc[BT];
+#pragma unroll
+    for (int b = 0; b < BT; ++b) iacc[b] = 0;
+    for_each_source(ix, map, X, Y, W, true, [&](unsigned P, float w) {
+        planes_of_pixel(R, s, P, npx, B, [&](int b, double pl) {
+#pragma unroll
+            for (int bb = 0; bb < BT; ++bb)
+                if (bb == b) iacc[bb] += __double2ll_rn(static_cast<double>(w) * pl);
+        });
+    });
+    GatherRow<BT> r;
+#pragma unroll
+    for (int b = 0; b < BT; ++b) r.v[b] = static_cast<double>(iacc[b]);
+    return r;
+}
+
+// BT: compile-time number of bins (0: run-time B <= 24).
+template <int BT>
+__global__ void __launch_bounds__(kOutThreads)
 rectify_gather_kernel(const void* __restrict__ R, WindowTable tab, MapSlots ms, const float2* __restrict__ maps,
-                      char* __restrict__ index_ws, size_t ncells_padded, char* __restrict__ stencil_ws, int H, int W, int B,
-                      float* __restrict__ raw, PartialStats* __restrict__ block_partials) {
-    const int s = blockIdx.y;
-    const WindowDesc wd = tab.w[s];
+                      char* __restrict__ index_ws, size_t ncells_padded, char* __restrict__ stencil_ws,
+                      const int4* __restrict__ boxes, int H, int W, int Brt, float* __restrict__ raw,
+                      PartialStats* __restrict__ block_partials) {
+    extern __shared__ double s_planes[];                     // [box pixels][B]
+    constexpr int BA = BT ? BT : 24;
+    const int B = BT ? BT : Brt;
+    const unsigned s = blockIdx.y;
     const unsigned npx = static_cast<unsigned>(H) * static_cast<unsigned>(W);
     const bool identity = maps == nullptr;
-    const double* planes = reinterpret_cast<const double*>(R) + static_cast<size_t>(s) * B * npx;   // plane_finalize_kernel
-    const int* R32 = reinterpret_cast<const int*>(R) + static_cast<size_t>(s) * npx;
+    const int tiles_x = (W + kOutW - 1) / kOutW;
+    const int X = (blockIdx.x % tiles_x) * kOutW + (threadIdx.x % kOutW), Y = (blockIdx.x / tiles_x) * kOutH + (threadIdx.x / kOutW);
+    const bool inside = X < W && Y < H;
+    const unsigned px = static_cast<unsigned>(Y) * W + X;
     float* out = raw + static_cast<size_t>(s) * B * npx;
 
+    int4 box;
+    if (identity) {
+        // x = float(x), y = float(y): the only non-zero corner of a raw pixel is the pixel itself
+        const int bx = (blockIdx.x % tiles_x) * kOutW, by = (blockIdx.x / tiles_x) * kOutH;
+        box = make_int4(bx, by, min(kOutW, W - bx), min(kOutH, H - by));
+    } else {
+        box = __ldg(boxes + static_cast<size_t>(ms.slot[s]) * gridDim.x + blockIdx.x);
+    }
+    const bool staged = box.z > 0 && static_cast<size_t>(box.z) * box.w * B * sizeof(double) <= kStageBytes;
+    if (staged) {
+        // warps over the rows of the box, lanes over its columns (coalesced row segments of R)
+        for (unsigned ly = threadIdx.x >> 5; ly < static_cast<unsigned>(box.w); ly += kOutThreads / 32)
+            for (unsigned lx = threadIdx.x & 31; lx < static_cast<unsigned>(box.z); lx += 32) {
+                const unsigned P = (box.y + ly) * W + box.x + lx;
+                double* dst = s_planes + static_cast<size_t>(ly * box.z + lx) * B;
+                planes_of_pixel(R, s, P, npx, B, [&](int b, double pl) { dst[b] = pl; });
+            }
+    }
+    __syncthreads();
+
     GatherStats st{0.0, 0.0, 0, INFINITY, -INFINITY};
-    const unsigned px = blockIdx.x * kGatherThreads + threadIdx.x;
-    if (px < npx) {
-        long long acc[BMAX];
+    if (inside) {
+        double acc[BA];
 #pragma unroll
-        for (int b = 0; b < BMAX; ++b) acc[b] = 0;
-        // one source pixel: quantise its contribution to 2^-30 (order-independent integer sum)
-        auto accumulate = [&](unsigned P, float w) {
-            const double md = static_cast<double>(w);
-            if constexpr (HAS_T) {
+        for (int b = 0; b < BA; ++b) acc[b] = 0.0;
+        if (staged) {
+            auto accumulate = [&](unsigned yx, float w) {     // yx = row << 16 | column of the source pixel
+                const double md = static_cast<double>(w);
+                const double* src = s_planes + (((yx >> 16) - box.y) * box.z + ((yx & 0xffffu) - box.x)) * B;
 #pragma unroll
-                for (int b = 0; b < BMAX; ++b)
-                    if (b < B) acc[b] += __double2ll_rn(md * __ldg(planes + static_cast<unsigned>(b) * npx + P));  // 2^-30 units
+                for (int b = 0; b < BA; ++b)
+                    if (b < B) acc[b] = fma(md, src[b], acc[b]);       // the row's fixed order: reproducible
+            };
+            if (identity) {
+                accumulate((static_cast<unsigned>(Y) << 16) | static_cast<unsigned>(X), 1.0f);
             } else {
-                acc[0] += __double2ll_rn(md * (static_cast<double>(__ldg(R32 + P)) * 1073741824.0));
-            }
-        };
-        if (identity) {
-            accumulate(px, 1.0f);          // x = float(x), y = float(y): the only non-zero corner is the pixel itself
-        } else {
-            const Stencil sc = stencil_at(stencil_ws, ms.slot[s], npx);
-            const unsigned n = sc.n[px];
-            if (n != kEllOverflow) {
+                const Stencil sc = stencil_at(stencil_ws, ms.slot[s], npx);
+                const unsigned n = sc.n[px];
                 for (unsigned k = 0; k < n; ++k) accumulate(__ldg(sc.P + k * npx + px), __ldg(sc.w + k * npx + px));
-            } else {
-                const float2* map = maps + static_cast<size_t>(wd.map_id) * npx;
-                const MapIndex ix = map_index_at(index_ws, ms.slot[s], ncells_padded, npx);
-                const int X = static_cast<int>(px % static_cast<unsigned>(W)), Y = static_cast<int>(px / static_cast<unsigned>(W));
-                for_each_source(ix, map, X, Y, W, [&](unsigned P, float w) { if (w != 0.0f) accumulate(P, w); });
             }
+        } else if (box.z != 0) {     // box.z == 0: no source pixel reaches this tile, the sums stay 0
+            const GatherRow<BA> row = gather_pixel_from_cells<BA>(R, s, npx, maps + static_cast<size_t>(tab.w[s].map_id) * npx,
+                                                                  map_index_at(index_ws, ms.slot[s], ncells_padded, npx), X, Y, W, B);
+#pragma unroll
+            for (int b = 0; b < BA; ++b) acc[b] = row.v[b];
         }
 #pragma unroll
-        for (int b = 0; b < BMAX; ++b) {
+        for (int b = 0; b < BA; ++b) {
             if (b < B) {
-                const float v = __fmul_rn(__ll2float_rn(acc[b]), kFixInv);
+                const float v = __double2float_rn(acc[b] * 9.31322574615478515625e-10);   // * 2^-30 (exact), one rounding
                 out[static_cast<unsigned>(b) * npx + px] = v;
                 if (v != 0.0f) {                                   // dsec.py:88
                     st.nnz += 1;
@@ -394,9 +517,9 @@ rectify_gather_kernel(const void* __restrict__ R, WindowTable tab, MapSlots ms, 
         }
     }
     // fixed-order block reduction -> one partial per (window, block)
-    __shared__ double s_sum[kGatherThreads / 32], s_sq[kGatherThreads / 32];
-    __shared__ long long s_n[kGatherThreads / 32];
-    __shared__ float s_mn[kGatherThreads / 32], s_mx[kGatherThreads / 32];
+    __shared__ double s_sum[kOutThreads / 32], s_sq[kOutThreads / 32];
+    __shared__ long long s_n[kOutThreads / 32];
+    __shared__ float s_mn[kOutThreads / 32], s_mx[kOutThreads / 32];
     st.sum = warp_sum(st.sum);
     st.sumsq = warp_sum(st.sumsq);
     st.nnz = warp_sum(st.nnz);
@@ -408,7 +531,7 @@ rectify_gather_kernel(const void* __restrict__ R, WindowTable tab, MapSlots ms, 
     if (threadIdx.x == 0) {
         PartialStats o;
         o.sum = 0.0; o.sumsq = 0.0; o.nnz = 0; o.min_nz = INFINITY; o.max_nz = -INFINITY;
-        for (int w = 0; w < kGatherThreads / 32; ++w) {
+        for (int w = 0; w < kOutThreads / 32; ++w) {
             o.sum += s_sum[w]; o.sumsq += s_sq[w]; o.nnz += s_n[w];
             o.min_nz = fminf(o.min_nz, s_mn[w]); o.max_nz = fmaxf(o.max_nz, s_mx[w]);
         }
@@ -438,20 +561,22 @@ constexpr int kMaxDistinctMaps = 4;    // inverse indices held at once; api.cu c
 static size_t ncells_padded_of(int H, int W) {
     return align_up(static_cast<size_t>(H + 1) * (W + 1) + 2, 64);
 }
-static int gather_blocks(int H, int W) { return (H * W + kGatherThreads - 1) / kGatherThreads; }
+static int gather_blocks(int H, int W) { return ((W + kOutW - 1) / kOutW) * ((H + kOutH - 1) / kOutH); }
 static size_t index_bytes_per_map(int H, int W) {
     return ncells_padded_of(H, W) * (sizeof(unsigned) + sizeof(uint4)) + 256 + static_cast<size_t>(H) * W * sizeof(uint2);
 }
 
 int factored_supported(int H, int W, int B) {
-    return B >= 1 && B <= 24 && H >= 1 && W >= 1 && static_cast<long long>(H + 1) * (W + 1) < (1LL << 30);
+    return B >= 1 && B <= 24 && H >= 1 && W >= 1 && H < 65536 && W < 65536 && static_cast<long long>(H + 1) * (W + 1) < (1LL << 30);
 }
 int factored_max_maps(void) { return kMaxDistinctMaps; }
 
 // inverse indices of the distinct maps of one window group + the per-block statistics partials
-size_t factored_scratch_bytes(int group, int H, int W) {
+size_t factored_scratch_bytes(int group, int H, int W, int B) {
+    (void)B;
     const int maps = group < kMaxDistinctMaps ? group : kMaxDistinctMaps;
     return align_up(static_cast<size_t>(maps) * index_bytes_per_map(H, W), 256) +
+           align_up(sizeof(int4) * static_cast<size_t>(maps) * gather_blocks(H, W), 256) +
            static_cast<size_t>(maps) * stencil_bytes(static_cast<size_t>(H) * W) +
            align_up(sizeof(PartialStats) * static_cast<size_t>(group) * gather_blocks(H, W), 256);
 }
@@ -481,10 +606,13 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
     }
     const size_t index_bytes = align_up(static_cast<size_t>(n_slots) * index_bytes_per_map(H, W), 256);
     const size_t sten_bytes = static_cast<size_t>(n_slots) * stencil_bytes(npx);
-    if (index_bytes + sten_bytes + sizeof(PartialStats) * static_cast<size_t>(S) * nblk > scratch_bytes) return CMDA_ERR_WORKSPACE;
+    const size_t box_bytes = align_up(sizeof(int4) * static_cast<size_t>(n_slots) * nblk, 256);
+    if (index_bytes + sten_bytes + box_bytes + sizeof(PartialStats) * static_cast<size_t>(S) * nblk > scratch_bytes)
+        return CMDA_ERR_WORKSPACE;
     char* index_ws = static_cast<char*>(scratch);
     char* stencil_ws = index_ws + index_bytes;
-    PartialStats* block_partials = reinterpret_cast<PartialStats*>(stencil_ws + sten_bytes);
+    int4* boxes = reinterpret_cast<int4*>(stencil_ws + sten_bytes);
+    PartialStats* block_partials = reinterpret_cast<PartialStats*>(reinterpret_cast<char*>(boxes) + box_bytes);
     const float2* maps2 = reinterpret_cast<const float2*>(maps);
 
     // zero R (int64 cells for B > 1, int32 counts for B == 1) and the cell counters of the indices
@@ -497,7 +625,10 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
     if (n_slots) {
         dim3 grid(static_cast<unsigned>((npx + 255) / 256), n_slots);
         rectify_index_build_kernel<<<grid, 256, 0, st>>>(maps2, ms, H, W, index_ws, nc);
+        rectify_index_sort_kernel<<<dim3(static_cast<unsigned>(((H + 1) * (W + 1) + 255) / 256), n_slots), 256, 0, st>>>(
+            ms, H, W, index_ws, nc);
         stencil_build_kernel<<<grid, 256, 0, st>>>(maps2, ms, H, W, index_ws, nc, stencil_ws);
+        out_tile_box_kernel<<<dim3(nblk, n_slots), kOutThreads, 0, st>>>(ms, H, W, stencil_ws, boxes);
         CMDA_LAUNCH_CHECK();
     }
     phase_mark(st);
@@ -518,19 +649,22 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
         CMDA_LAUNCH_CHECK();
     }
     phase_mark(st);
-    if (B > 1) {
-        plane_finalize_kernel<<<dim3(static_cast<unsigned>((npx + 255) / 256), S), 256, 0, st>>>(static_cast<long long*>(R), B, npx);
-        CMDA_LAUNCH_CHECK();
-    }
     {
         dim3 grid(nblk, S);
-#define CMDA_GATHER(HAS_T, BMAX)                                                                                      \
-    rectify_gather_kernel<HAS_T, BMAX><<<grid, kGatherThreads, 0, st>>>(R, tab, ms, maps2, index_ws, nc, stencil_ws, H, W, \
-                                                                        B, raw, block_partials)
-        if (B == 1) CMDA_GATHER(false, 1);
-        else if (B <= 5) CMDA_GATHER(true, 5);
-        else if (B <= 10) CMDA_GATHER(true, 10);
-        else CMDA_GATHER(true, 24);
+#define CMDA_GATHER(BT)                                                                                                  \
+    do {                                                                                                                 \
+        CMDA_CUDA_TRY(cudaFuncSetAttribute(rectify_gather_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageBytes)); \
+        rectify_gather_kernel<BT><<<grid, kOutThreads, kStageBytes, st>>>(R, tab, ms, maps2, index_ws, nc, stencil_ws, boxes, H, W, \
+                                                                         B, raw, block_partials);                       \
+    } while (0)
+        switch (B) {
+            case 1: CMDA_GATHER(1); break;
+            case 2: CMDA_GATHER(2); break;
+            case 3: CMDA_GATHER(3); break;
+            case 4: CMDA_GATHER(4); break;
+            case 5: CMDA_GATHER(5); break;
+            default: CMDA_GATHER(0); break;
+        }
 #undef CMDA_GATHER
         regroup_partials_kernel<<<S, kStatBlocks, 0, st>>>(block_partials, nblk, partials);
         CMDA_LAUNCH_CHECK();
