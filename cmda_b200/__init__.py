@@ -4,10 +4,10 @@ Only what the hot path needs: ``csrc/`` (CUDA kernels + the C ABI, built into
 ``libcmda_b200.so``) and thin host-side mirrors of the reference's call signatures.
 """
 from ._lib import CmdaError, build, lib  # noqa: F401
-from .voxel import (EventStore, default_clip_range, events_norm, events_to_voxel_grid, events_vg_batch,  # noqa: F401
-                    remap_events)
-from .image_change import (get_ic, get_image_change, get_image_change_from_pil, image_change_batch, isr_batch,  # noqa: F401
-                           rgb_to_gray)
+from .voxel import (EventStore, default_clip_range, events_norm, events_to_voxel_grid, events_vg_augmented_batch,  # noqa: F401
+                    events_vg_batch, remap_events)
+from .image_change import (denorm_to_gray, get_ic, get_image_change, get_image_change_from_pil,  # noqa: F401
+                           image_change_batch, isr_batch, mixed_image_isr, rgb_to_gray)
 from .slicer import images_to_events_index, searchsorted_right, window_bounds, write_index_txt  # noqa: F401
 from .dsec import DSECEvents  # noqa: F401
 from . import sharding, synth  # noqa: F401

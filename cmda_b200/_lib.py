@@ -46,6 +46,9 @@ SIGNATURES = {
     "cmda_events_vg_resolved_mode": (_int, [_i64, _int, _int, _int, _int, _int]),
     "cmda_events_vg_batch": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _vp, _vp, _int, _int, _int, _vp, _f32, _int,
                                     _int, _vp, _vp, _vp, _vp, _sz, _int, _vp]),
+    "cmda_events_vg_augmented_workspace_bytes": (_sz, [_i64, _int, _int, _int, _int, _int]),
+    "cmda_events_vg_augmented_batch": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _vp, _vp, _int, _int, _int, _vp, _f32, _int,
+                                              _vp, _int, _int, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _sz, _int, _vp]),
     "cmda_voxel_grid_f32": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _int, _int, _vp, _vp, _vp, _sz, _int, _vp]),
     "cmda_events_norm_workspace_bytes": (_sz, [_int]),
     "cmda_events_norm_batch": (_int, [_vp, _int, _i64, _vp, _f32, _int, _vp, _sz, _vp]),
@@ -55,6 +58,7 @@ SIGNATURES = {
     "cmda_logdiff_pair_u8": (_int, [_vp, _vp, _int, _int, _int, _vp, _f32, _f32, _vp, _vp, _vp, _sz, _vp]),
     "cmda_isr_shift_u8": (_int, [_vp, _int, _int, _int, _int, _int, _int, _vp, _f32, _f32, _vp, _vp, _sz, _vp]),
     "cmda_rgb_to_gray_u8": (_int, [_vp, _i64, _vp, _vp]),
+    "cmda_denorm_rgb_to_gray_u8": (_int, [_vp, _int, _int, _int, _vp, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -18,7 +18,10 @@ int launch_remap(const uint32_t*, const uint16_t*, const uint16_t*, const uint8_
 int launch_convert_stats(const long long*, float*, int, long long, PartialStats*, cudaStream_t);
 int launch_norm_apply(const float*, float*, int, long long, const PartialStats*, const WindowTable&, float, int,
                       cudaStream_t);
+int launch_norm_augment(const float*, float*, int, int, int, int, const PartialStats*, const WindowTable&, const int*,
+                        const int*, const int*, int, int, int, int, int, int, float, int, cudaStream_t);
 int launch_rgb_to_gray(const uint8_t*, int64_t, uint8_t*, cudaStream_t);
+int launch_denorm_to_gray(const float*, int, int, int, const float*, const float*, uint8_t*, uint8_t*, cudaStream_t);
 int launch_isr(const uint8_t*, int, int, int, int, int, const float*, float, float, float*, unsigned*, cudaStream_t);
 int launch_pair(const uint8_t*, const uint8_t*, int, int, int, const float*, float, float, float*, uint8_t*, unsigned*,
                 cudaStream_t);
@@ -124,11 +127,19 @@ size_t cmda_events_vg_workspace_bytes(int64_t total_events, int S, int H, int W,
     return need + 256;
 }
 
-int cmda_events_vg_batch(const uint32_t* d_t, const uint16_t* d_x, const uint16_t* d_y, const uint8_t* d_p,
-                         const int64_t* h_win_start, const int64_t* h_win_end, int S, const float* d_rectify_map,
-                         const int32_t* h_map_id, int H, int W, int B, const float* h_clip, float final_range,
-                         int enforce_no_events_zero, int normalize, float* d_out, float* d_raw_out,
-                         int64_t* d_bin_counts, void* d_workspace, size_t workspace_bytes, int mode, void* stream) {
+}  // extern "C"
+
+namespace {
+struct AugmentArgs {      // post-voxel augmentation fused into the normaliser (dsec.py:304-319), or none
+    const cmda_vg_augment* h_aug;
+    int crop_w, crop_h, out_w, out_h, avg_bins, repeat;
+};
+
+int events_vg_impl(const uint32_t* d_t, const uint16_t* d_x, const uint16_t* d_y, const uint8_t* d_p,
+                   const int64_t* h_win_start, const int64_t* h_win_end, int S, const float* d_rectify_map,
+                   const int32_t* h_map_id, int H, int W, int B, const float* h_clip, float final_range,
+                   int enforce_no_events_zero, int normalize, float* d_out, float* d_raw_out, int64_t* d_bin_counts,
+                   void* d_workspace, size_t workspace_bytes, int mode, void* stream, const AugmentArgs* aug) {
     if (S < 0 || H <= 0 || W <= 0 || B <= 0) return CMDA_ERR_BAD_ARG;
     if (S == 0) return CMDA_OK;
     if (!d_t || !d_x || !d_y || !d_p || !h_win_start || !h_win_end || !d_out || !d_workspace) return CMDA_ERR_BAD_ARG;
@@ -142,7 +153,21 @@ int cmda_events_vg_batch(const uint32_t* d_t, const uint16_t* d_x, const uint16_
         const long long n = h_win_end[s] - h_win_start[s];
         if (n > 0) total += n;
     }
-    if (workspace_bytes < cmda_events_vg_workspace_bytes(total, S, H, W, B, mode)) return CMDA_ERR_WORKSPACE;
+    size_t base_need = cmda_events_vg_workspace_bytes(total, S, H, W, B, mode);
+    float* raw_ws = nullptr;      // augmented output: the raw grid lives in the workspace unless the caller wants it
+    if (aug) {
+        if (!aug->h_aug || aug->crop_w <= 0 || aug->crop_h <= 0 || aug->out_w <= 0 || aug->out_h <= 0 || aug->repeat <= 0)
+            return CMDA_ERR_BAD_ARG;
+        for (int s = 0; s < S; ++s)
+            if (aug->h_aug[s].crop_x < 0 || aug->h_aug[s].crop_y < 0 || aug->h_aug[s].crop_x + aug->crop_w > W ||
+                aug->h_aug[s].crop_y + aug->crop_h > H)
+                return CMDA_ERR_BAD_ARG;
+        if (!d_raw_out) {
+            raw_ws = reinterpret_cast<float*>(static_cast<char*>(d_workspace) + base_need);
+            base_need += sizeof(float) * static_cast<size_t>(S) * B * H * W;
+        }
+    }
+    if (workspace_bytes < base_need) return CMDA_ERR_WORKSPACE;
     const int use_mode = resolve_mode(mode, total, S, H, W, B);
     if (use_mode == CMDA_VOXEL_TILED && !tiled_supported(H, W, B)) return CMDA_ERR_UNSUPPORTED;
     if (use_mode == CMDA_VOXEL_FACTORED && !factored_supported(H, W, B)) return CMDA_ERR_UNSUPPORTED;
@@ -187,6 +212,23 @@ int cmda_events_vg_batch(const uint32_t* d_t, const uint16_t* d_x, const uint16_
         float* out_g = d_out + static_cast<size_t>(s0) * V;
         float* raw_g = (normalize && d_raw_out) ? d_raw_out + static_cast<size_t>(s0) * V : out_g;
         PartialStats* part_g = partials + static_cast<size_t>(s0) * kStatBlocks;
+        int crop_x[kMaxWindows], crop_y[kMaxWindows], flip[kMaxWindows];
+        if (aug) {
+            const int Bo = aug->avg_bins ? 1 : B;
+            out_g = d_out + static_cast<size_t>(s0) * aug->repeat * Bo * aug->out_h * aug->out_w;
+            raw_g = (d_raw_out ? d_raw_out : raw_ws) + static_cast<size_t>(s0) * V;
+            for (int k = 0; k < sn; ++k) {
+                crop_x[k] = aug->h_aug[s0 + k].crop_x; crop_y[k] = aug->h_aug[s0 + k].crop_y; flip[k] = aug->h_aug[s0 + k].flip;
+            }
+        }
+        // the last stage: events_norm apply, alone or fused with the dataset's crop / flip / resize / repeat
+        auto finish = [&]() -> int {
+            if (aug)
+                return launch_norm_augment(raw_g, out_g, sn, B, H, W, part_g, tab, crop_x, crop_y, flip, aug->crop_w, aug->crop_h,
+                                           aug->out_w, aug->out_h, aug->avg_bins, aug->repeat, final_range,
+                                           enforce_no_events_zero, st);
+            return launch_norm_apply(raw_g, out_g, sn, V, part_g, tab, final_range, enforce_no_events_zero, st);
+        };
         int64_t* bins_g = d_bin_counts ? d_bin_counts + static_cast<size_t>(s0) * B : nullptr;
         int rc;
         phase_mark(st);
@@ -198,7 +240,7 @@ int cmda_events_vg_batch(const uint32_t* d_t, const uint16_t* d_x, const uint16_
             if (rc != CMDA_OK) return rc;
             phase_mark(st);
             if (normalize) {
-                rc = launch_norm_apply(raw_g, out_g, sn, V, part_g, tab, final_range, enforce_no_events_zero, st);
+                rc = finish();
                 if (rc != CMDA_OK) return rc;
                 phase_mark(st);
             }
@@ -219,12 +261,43 @@ int cmda_events_vg_batch(const uint32_t* d_t, const uint16_t* d_x, const uint16_
         if (rc != CMDA_OK) return rc;
         phase_mark(st);
         if (normalize) {
-            rc = launch_norm_apply(raw_g, out_g, sn, V, part_g, tab, final_range, enforce_no_events_zero, st);
+            rc = finish();
             if (rc != CMDA_OK) return rc;
             phase_mark(st);
         }
     }
     return CMDA_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int cmda_events_vg_batch(const uint32_t* d_t, const uint16_t* d_x, const uint16_t* d_y, const uint8_t* d_p,
+                         const int64_t* h_win_start, const int64_t* h_win_end, int S, const float* d_rectify_map,
+                         const int32_t* h_map_id, int H, int W, int B, const float* h_clip, float final_range,
+                         int enforce_no_events_zero, int normalize, float* d_out, float* d_raw_out,
+                         int64_t* d_bin_counts, void* d_workspace, size_t workspace_bytes, int mode, void* stream) {
+    return events_vg_impl(d_t, d_x, d_y, d_p, h_win_start, h_win_end, S, d_rectify_map, h_map_id, H, W, B, h_clip, final_range,
+                          enforce_no_events_zero, normalize, d_out, d_raw_out, d_bin_counts, d_workspace, workspace_bytes, mode,
+                          stream, nullptr);
+}
+
+size_t cmda_events_vg_augmented_workspace_bytes(int64_t total_events, int S, int H, int W, int B, int mode) {
+    const size_t base = cmda_events_vg_workspace_bytes(total_events, S, H, W, B, mode);
+    return base ? base + sizeof(float) * static_cast<size_t>(S) * B * H * W : 0;
+}
+
+int cmda_events_vg_augmented_batch(const uint32_t* d_t, const uint16_t* d_x, const uint16_t* d_y, const uint8_t* d_p,
+                                   const int64_t* h_win_start, const int64_t* h_win_end, int S,
+                                   const float* d_rectify_map, const int32_t* h_map_id, int H, int W, int B,
+                                   const float* h_clip, float final_range, int enforce_no_events_zero,
+                                   const cmda_vg_augment* h_aug, int crop_w, int crop_h, int out_w, int out_h,
+                                   int avg_bins, int repeat, float* d_out, float* d_raw_out, int64_t* d_bin_counts,
+                                   void* d_workspace, size_t workspace_bytes, int mode, void* stream) {
+    const AugmentArgs aug{h_aug, crop_w, crop_h, out_w, out_h, avg_bins, repeat};
+    return events_vg_impl(d_t, d_x, d_y, d_p, h_win_start, h_win_end, S, d_rectify_map, h_map_id, H, W, B, h_clip, final_range,
+                          enforce_no_events_zero, 1, d_out, d_raw_out, d_bin_counts, d_workspace, workspace_bytes, mode, stream,
+                          &aug);
 }
 
 int cmda_voxel_grid_f32(const float* d_time, const float* d_x, const float* d_y, const float* d_pol, int64_t n, int W,
@@ -327,6 +400,14 @@ int cmda_isr_shift_u8(const uint8_t* d_img, int channels, int S, int H, int W, i
         gray = g;
     }
     return launch_isr(gray, S, H, W, shift_pixel, direction, h_lut, thr, clip, d_out, slots, st);
+}
+
+int cmda_denorm_rgb_to_gray_u8(const float* d_img, int S, int H, int W, const float* h_mean, const float* h_std,
+                               uint8_t* d_gray, uint8_t* d_rgb, void* stream) {
+    if (S < 0 || H <= 0 || W <= 0) return CMDA_ERR_BAD_ARG;
+    if (S == 0) return CMDA_OK;
+    if (!d_img || !h_mean || !h_std || !d_gray) return CMDA_ERR_BAD_ARG;
+    return launch_denorm_to_gray(d_img, S, H, W, h_mean, h_std, d_gray, d_rgb, static_cast<cudaStream_t>(stream));
 }
 
 int cmda_rgb_to_gray_u8(const uint8_t* d_rgb, int64_t n_pixels, uint8_t* d_gray, void* stream) {

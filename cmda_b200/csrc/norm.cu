@@ -204,6 +204,89 @@ norm_apply_kernel(const float* raw, float* out, long long V,   // raw may alias 
     }
 }
 
+// events_norm apply fused with the dataset's post-voxel augmentation (dsec.py:304-319): every output
+// pixel of the resized crop normalises its four raw taps on the fly, so the normalised full grid is never
+// materialised.  Bilinear weights follow ATen's upsample_bilinear2d with align_corners=False
+// (src = scale * (dst + 0.5) - 0.5 clamped at 0, scale = in / out in float32).
+struct AugTable {
+    int crop_x[kMaxWindows], crop_y[kMaxWindows];
+    unsigned char flip[kMaxWindows];
+};
+struct AugSpec {
+    int crop_w, crop_h, out_w, out_h, avg_bins, repeat;
+};
+
+__global__ void __launch_bounds__(256)
+norm_augment_kernel(const float* __restrict__ raw, float* __restrict__ out, int B, int H, int W,
+                    const PartialStats* __restrict__ partials, WindowTable tab, AugTable aug, AugSpec sp, float final_range,
+                    int enforce) {
+    __shared__ NormParams s_q;
+    const int s = blockIdx.y;
+    const long long V = static_cast<long long>(B) * H * W;
+    if (threadIdx.x == 0) s_q = make_norm_params(partials + static_cast<size_t>(s) * kStatBlocks, V, tab.w[s].clip, final_range);
+    __syncthreads();
+    const NormParams q = s_q;
+    const float* r = raw + static_cast<size_t>(s) * V;
+    const int Bo = sp.avg_bins ? 1 : B;
+    const size_t oplane = static_cast<size_t>(sp.out_h) * sp.out_w;
+    float* o = out + static_cast<size_t>(s) * sp.repeat * Bo * oplane;
+    const float sy = static_cast<float>(sp.crop_h) / static_cast<float>(sp.out_h);
+    const float sx = static_cast<float>(sp.crop_w) / static_cast<float>(sp.out_w);
+    const int cx = aug.crop_x[s], cy = aug.crop_y[s];
+    const bool flip = aug.flip[s] != 0;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < static_cast<long long>(oplane);
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int oy = static_cast<int>(i / sp.out_w), ox = static_cast<int>(i - static_cast<long long>(oy) * sp.out_w);
+        float fy = sy * (static_cast<float>(oy) + 0.5f) - 0.5f;
+        float fx = sx * (static_cast<float>(ox) + 0.5f) - 0.5f;
+        fy = fy < 0.0f ? 0.0f : fy;
+        fx = fx < 0.0f ? 0.0f : fx;
+        const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+        const int y1 = y0 + (y0 < sp.crop_h - 1 ? 1 : 0), x1 = x0 + (x0 < sp.crop_w - 1 ? 1 : 0);
+        const float ly1 = fy - static_cast<float>(y0), ly0 = 1.0f - ly1;
+        const float lx1 = fx - static_cast<float>(x0), lx0 = 1.0f - lx1;
+        // crop then flip: flipped[x] = crop[crop_w - 1 - x]
+        const int gx0 = cx + (flip ? sp.crop_w - 1 - x0 : x0), gx1 = cx + (flip ? sp.crop_w - 1 - x1 : x1);
+        const int gy0 = cy + y0, gy1 = cy + y1;
+        float m00 = 0.0f, m01 = 0.0f, m10 = 0.0f, m11 = 0.0f;
+        for (int b = 0; b < B; ++b) {
+            const float* pb = r + static_cast<size_t>(b) * H * W;
+            const float v00 = norm_one(__ldg(pb + static_cast<size_t>(gy0) * W + gx0), q, enforce);
+            const float v01 = norm_one(__ldg(pb + static_cast<size_t>(gy0) * W + gx1), q, enforce);
+            const float v10 = norm_one(__ldg(pb + static_cast<size_t>(gy1) * W + gx0), q, enforce);
+            const float v11 = norm_one(__ldg(pb + static_cast<size_t>(gy1) * W + gx1), q, enforce);
+            if (sp.avg_bins) {
+                m00 += v00; m01 += v01; m10 += v10; m11 += v11;            // torch.mean(dim=1): sum, then / B
+                if (b + 1 < B) continue;
+                const float fb = static_cast<float>(B);
+                m00 /= fb; m01 /= fb; m10 /= fb; m11 /= fb;
+            } else {
+                m00 = v00; m01 = v01; m10 = v10; m11 = v11;
+            }
+            const float val = ly0 * (lx0 * m00 + lx1 * m01) + ly1 * (lx0 * m10 + lx1 * m11);
+            const int ob = sp.avg_bins ? 0 : b;
+            for (int rep = 0; rep < sp.repeat; ++rep) o[static_cast<size_t>(rep * Bo + ob) * oplane + i] = val;
+        }
+    }
+}
+
+int launch_norm_augment(const float* raw, float* out, int S, int B, int H, int W, const PartialStats* partials,
+                        const WindowTable& tab, const int* crop_x, const int* crop_y, const int* flip, int crop_w, int crop_h,
+                        int out_w, int out_h, int avg_bins, int repeat, float final_range, int enforce, cudaStream_t s) {
+    AugTable aug{};
+    for (int k = 0; k < S; ++k) { aug.crop_x[k] = crop_x[k]; aug.crop_y[k] = crop_y[k]; aug.flip[k] = flip[k] ? 1 : 0; }
+    AugSpec sp{crop_w, crop_h, out_w, out_h, avg_bins, repeat};
+    const long long oplane = static_cast<long long>(out_h) * out_w;
+    long long gx = (oplane + kNormThreads - 1) / kNormThreads;
+    long long cap = (148LL * 8 + S - 1) / S;
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    norm_augment_kernel<<<dim3(static_cast<unsigned>(gx), S), kNormThreads, 0, s>>>(raw, out, B, H, W, partials, tab, aug, sp,
+                                                                                  final_range, enforce);
+    CMDA_LAUNCH_CHECK();
+    return CMDA_OK;
+}
+
 int launch_convert_stats(const long long* acc, float* raw, int S, long long V, PartialStats* partials,
                          cudaStream_t s) {
     dim3 grid(kStatBlocks, S);

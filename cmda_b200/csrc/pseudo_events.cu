@@ -441,6 +441,56 @@ __global__ void rgb_to_gray_kernel(const uint8_t* __restrict__ rgb, long long n,
     }
 }
 
+// ------------------------------------------------------------------ a9: normalised float image -> 'L' bytes
+// dacs.py:730-733: clamp(denorm(img, mean, std), 0, 1) * 255 -> np.uint8 (truncation) -> PIL 'L'.  denorm is
+// img.mul(std).add(mean) / 255.0 (mmseg/models/utils/dacs_transforms.py:52-53); every step one float32
+// rounding, as torch evaluates it.  d_img is [S, 3, H, W]; the gray plane (and optionally the HWC bytes PIL
+// would have been handed) come out without the image ever leaving the device.
+struct Denorm3 {
+    float mean[3], std[3];
+};
+__global__ void __launch_bounds__(256)
+denorm_to_gray_kernel(const float* __restrict__ img, long long npx, Denorm3 q, uint8_t* __restrict__ gray,
+                      uint8_t* __restrict__ rgb) {
+    const int s = blockIdx.y;
+    const float* base = img + static_cast<size_t>(s) * 3 * npx;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < npx;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        unsigned c8[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float v = __fdiv_rn(__fadd_rn(__fmul_rn(__ldg(base + c * npx + i), q.std[c]), q.mean[c]), 255.0f);   // denorm
+            v = fminf(fmaxf(v, 0.0f), 1.0f);                                                                    // torch.clamp(0, 1)
+            c8[c] = static_cast<unsigned>(__float2int_rz(__fmul_rn(v, 255.0f))) & 255u;                           // * 255 -> np.uint8
+        }
+        gray[static_cast<size_t>(s) * npx + i] =
+            static_cast<uint8_t>((19595u * c8[0] + 38470u * c8[1] + 7471u * c8[2] + 32768u) >> 16);              // convert('L')
+        if (rgb != nullptr) {
+            uint8_t* o = rgb + (static_cast<size_t>(s) * npx + i) * 3;
+            o[0] = static_cast<uint8_t>(c8[0]); o[1] = static_cast<uint8_t>(c8[1]); o[2] = static_cast<uint8_t>(c8[2]);
+        }
+    }
+}
+
+int launch_denorm_to_gray(const float* img, int S, int H, int W, const float* h_mean, const float* h_std, uint8_t* gray,
+                          uint8_t* rgb, cudaStream_t st) {
+    Denorm3 q;
+    for (int c = 0; c < 3; ++c) { q.mean[c] = h_mean[c]; q.std[c] = h_std[c]; }
+    const long long npx = static_cast<long long>(H) * W;
+    long long gx = (npx + 255) / 256;
+    const long long cap = (148LL * 8 + S - 1) / S;
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    for (int s0 = 0; s0 < S; s0 += 32768) {
+        const int sn = (S - s0) < 32768 ? (S - s0) : 32768;
+        denorm_to_gray_kernel<<<dim3(static_cast<unsigned>(gx), sn), 256, 0, st>>>(
+            img + static_cast<size_t>(s0) * 3 * npx, npx, q, gray + static_cast<size_t>(s0) * npx,
+            rgb ? rgb + static_cast<size_t>(s0) * npx * 3 : nullptr);
+        CMDA_LAUNCH_CHECK();
+    }
+    return CMDA_OK;
+}
+
 // ------------------------------------------------------------------ launchers
 static int image_grid_x(long long work_items) {
     // 148 SMs x 8 resident 256-thread CTAs; never more blocks than work

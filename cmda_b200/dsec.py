@@ -18,7 +18,7 @@ import torch
 import torch.nn.functional as F
 
 from .slicer import window_bounds
-from .voxel import EventStore, events_vg_batch
+from .voxel import EventStore, events_vg_augmented_batch, events_vg_batch
 
 __all__ = ["DSECEvents"]
 
@@ -27,7 +27,7 @@ class DSECEvents:
     def __init__(self, t, x, y, p, rectify_map, images_to_events_index, events_num=-1, events_bins=5,
                  events_clip_range=None, crop_size=(400, 400), after_crop_resize_size=(512, 512),
                  image_change_range=1, outputs={'events_vg', 'image'}, output_num=1, events_bins_5_avg_1=False,
-                 enforce_3_channels=True, device=None, mode="auto"):
+                 enforce_3_channels=True, device=None, mode="auto", fused_augment=True):
         self.events_num = events_num
         self.events_bins = events_bins
         self.events_bins_5_avg_1 = events_bins_5_avg_1
@@ -49,6 +49,8 @@ class DSECEvents:
         self.enforce_3_channels = enforce_3_channels
         self.images_to_events_index = [int(v) for v in images_to_events_index]
         self.mode = mode
+        self.fused_augment = fused_augment     # crop / flip / resize / repeat inside the normaliser kernel (one launch less,
+                                               # no normalised full grid); False keeps them as torch ops on the grid
         self.store = EventStore(t, x, y, p, rectify_map if self.rectify_events else None,
                                 height=self.events_height, width=self.events_width, device=device)
 
@@ -78,6 +80,16 @@ class DSECEvents:
                 return None
             bounds.append(b)
         clips = [self._clip_for(f, s) for s, f in bounds]
+        if self.output_num == 1 and self.fused_augment:
+            # dsec.py:304-319 fused into the normaliser (one window: the squeeze of :306-307 applies)
+            train = 'label' not in self.outputs
+            crop_size = self.crop_size if train else (self.events_width, 440)
+            out_size = self.after_crop_resize_size if train else crop_size
+            x, y = (crop_xy if crop_xy is not None else (0, 0)) if train else (0, 0)
+            return events_vg_augmented_batch(self.store, [bounds[0][0]], [bounds[0][1]], self.events_bins, clips,
+                                             crop_xy=[(x, y)], crop_size=crop_size, out_size=out_size,
+                                             flips=[int(bool(flip_flag) and train)], avg_bins=self.events_bins_5_avg_1,
+                                             repeat=3 if self.enforce_3_channels else 1, mode=self.mode)[0]
         vg = events_vg_batch(self.store, [s for s, _ in bounds], [f for _, f in bounds], self.events_bins, clips,
                              mode=self.mode)
         events_vg = vg.flip(0)                                 # events_vg[output_num - 1 - i] = window i, :303

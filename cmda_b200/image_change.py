@@ -117,6 +117,38 @@ def get_image_change_from_pil(pil_image, width, height, data_type=None, shift_pi
     return isr_batch(img, shift_pixel, val_range, _threshold, _clip_range, shift_direction, out_device=out_device)[0]
 
 
+def denorm_to_gray(img, means, stds, *, return_rgb=False):
+    """``clamp(denorm(img, means, stds), 0, 1) * 255 -> uint8 -> PIL 'L'`` on the device
+    (reference dacs.py:730-733 with dacs_transforms.py:52-53).  ``img`` is a CUDA float32
+    ``[S, 3, H, W]`` batch, ``means`` / ``stds`` anything holding 3 numbers (the reference's
+    ``[1, 3, 1, 1]`` tensors are fine).  Returns uint8 ``[S, H, W]`` (and ``[S, H, W, 3]``)."""
+    img = _lib.require_cuda(img, "img")
+    assert img.ndim == 4 and img.shape[1] == 3 and img.dtype == torch.float32
+    img = img.contiguous()
+    dev = img.device
+    m = np.ascontiguousarray(torch.as_tensor(means).detach().float().cpu().reshape(-1).numpy(), dtype=np.float32)
+    sd = np.ascontiguousarray(torch.as_tensor(stds).detach().float().cpu().reshape(-1).numpy(), dtype=np.float32)
+    assert m.size == 3 and sd.size == 3
+    S, _, H, W = (int(v) for v in img.shape)
+    gray = torch.empty((S, H, W), dtype=torch.uint8, device=dev)
+    rgb = torch.empty((S, H, W, 3), dtype=torch.uint8, device=dev) if return_rgb else None
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().cmda_denorm_rgb_to_gray_u8(_lib.ptr(img), S, H, W, _lib.host_ptr(m), _lib.host_ptr(sd),
+                                                         _lib.ptr(gray), _lib.ptr(rgb), _lib.stream_ptr(dev)),
+                   "cmda_denorm_rgb_to_gray_u8")
+    return (gray, rgb) if return_rgb else gray
+
+
+def mixed_image_isr(mixed_img, means, stds, shift_direction='rightdown', shift_pixel=4, val_range=None, _threshold=None,
+                    _clip_range=None):
+    """The mixed-image ISR of the DACS train step (reference dacs.py:729-744) without leaving the
+    GPU: ``[S, 3, H, W]`` normalised float image batch -> ``[S, 3, H, W]`` ISR
+    (``get_image_change_from_pil(...).repeat(3, 1, 1)[None]`` per sample, stacked)."""
+    gray = denorm_to_gray(mixed_img, means, stds)
+    isr = isr_batch(gray, shift_pixel, val_range, _threshold, _clip_range, shift_direction)
+    return isr.expand(-1, 3, -1, -1).contiguous()
+
+
 def get_ic(image_front, image_now, val_range, threshold, clip_range, *, out_device=None):
     """Drop-in for ``get_ic`` (reference utils.py:87-105) on two uint8 gray images ->
     ``[1, H, W]`` float32.  Same arithmetic as K4 with the val_range table."""

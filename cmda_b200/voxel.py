@@ -15,8 +15,8 @@ import torch
 
 from . import _lib
 
-__all__ = ["events_to_voxel_grid", "events_norm", "EventStore", "events_vg_batch", "remap_events",
-           "default_clip_range"]
+__all__ = ["events_to_voxel_grid", "events_norm", "EventStore", "events_vg_batch", "events_vg_augmented_batch",
+           "remap_events", "default_clip_range"]
 
 
 def _cuda_device(device=None) -> torch.device:
@@ -180,6 +180,54 @@ def events_vg_batch(store: EventStore, starts, finishes, num_bins, clip_ranges=N
     if return_bin_counts:
         res.append(counts)
     return res[0] if len(res) == 1 else tuple(res)
+
+
+def events_vg_augmented_batch(store: EventStore, starts, finishes, num_bins, clip_ranges=None, *, crop_xy, crop_size,
+                              out_size, flips=None, avg_bins=False, repeat=1, map_ids=None, final_range=1.0,
+                              enforce_no_events_zero=True, mode="auto", out=None):
+    """``get_events_vg`` + the post-voxel stage of ``DSECDataset.__getitem__`` (reference dsec.py:304-319) in
+    one call: mean over bins (``events_bins_5_avg_1``) -> crop ``crop_size = (w, h)`` at ``crop_xy[s] = (x, y)``
+    -> horizontal flip -> bilinear resize to ``out_size = (w, h)`` (``F.interpolate(align_corners=False)``) ->
+    ``repeat(repeat, 1, 1)``.  The normaliser applies the augmentation itself: the normalised full grid is
+    never written.  Test mode of the reference (dsec.py:316-317) is ``crop_xy=(0, 0)``,
+    ``crop_size = out_size = (W, 440)``.  Returns ``[S, repeat * Bo, out_h, out_w]`` float32 on the device."""
+    L = _lib.lib()
+    dev = store.device
+    starts = np.ascontiguousarray(starts, dtype=np.int64)
+    ends = np.ascontiguousarray(finishes, dtype=np.int64) + 1
+    S = int(starts.shape[0])
+    if S and (starts.min() < 0 or ends.max() > len(store)):
+        raise IndexError("event window outside the store")
+    clips = np.empty(S, dtype=np.float32)
+    for s in range(S):
+        c = None if clip_ranges is None else clip_ranges[s]
+        clips[s] = default_clip_range(int(ends[s]) - 1, int(starts[s])) if c is None else c
+    mids = None if map_ids is None else np.ascontiguousarray(map_ids, dtype=np.int32)
+    H, W, B = store.height, store.width, int(num_bins)
+    cw, ch = (int(v) for v in crop_size)
+    ow, oh = (int(v) for v in out_size)
+    aug = np.zeros((S, 3), dtype=np.int32)
+    xy = np.asarray(crop_xy, dtype=np.int64).reshape(-1, 2)
+    aug[:, 0:2] = xy if xy.shape[0] == S else np.broadcast_to(xy, (S, 2))
+    if flips is not None:
+        aug[:, 2] = np.asarray(flips, dtype=np.int32).reshape(-1)
+    if S and (aug[:, 0].min() < 0 or aug[:, 1].min() < 0 or (aug[:, 0] + cw).max() > W or (aug[:, 1] + ch).max() > H):
+        raise IndexError("crop outside the voxel grid")
+    Bo = 1 if avg_bins else B
+    mode_id = _lib.VOXEL_MODES[mode]
+    if out is None:
+        out = torch.empty((S, int(repeat) * Bo, oh, ow), dtype=torch.float32, device=dev)
+    assert out.is_cuda and out.is_contiguous() and out.shape == (S, int(repeat) * Bo, oh, ow)
+    total = int(np.clip(ends - starts, 0, None).sum())
+    with torch.cuda.device(dev):
+        ws = _lib.workspace(dev, L.cmda_events_vg_augmented_workspace_bytes(total, S, H, W, B, mode_id))
+        _lib.check(L.cmda_events_vg_augmented_batch(
+            _lib.ptr(store.t), _lib.ptr(store.x), _lib.ptr(store.y), _lib.ptr(store.p), _lib.host_ptr(starts),
+            _lib.host_ptr(ends), S, _lib.ptr(store.rectify_map), _lib.host_ptr(mids), H, W, B, _lib.host_ptr(clips),
+            float(final_range), int(bool(enforce_no_events_zero)), _lib.host_ptr(aug), cw, ch, ow, oh, int(bool(avg_bins)),
+            int(repeat), _lib.ptr(out), None, None, _lib.ptr(ws), ws.numel(), mode_id, _lib.stream_ptr(dev)),
+            "cmda_events_vg_augmented_batch")
+    return out
 
 
 def remap_events(store: EventStore, start: int, finish: int, num_bins: int, map_id: int = 0):

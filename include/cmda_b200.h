@@ -130,6 +130,36 @@ int cmda_events_vg_batch(const uint32_t* d_t, const uint16_t* d_x, const uint16_
                          float* d_out, float* d_raw_out, int64_t* d_bin_counts,
                          void* d_workspace, size_t workspace_bytes, int mode, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * K2+K3 with the post-voxel augmentation of the dataset fused into the normaliser's apply phase
+ * (SURVEY.md 8 f-1).
+ * Replaces: DSECDataset.__getitem__, events branch after get_events_vg,
+ * /root/reference/mmseg/datasets/dsec.py:304-319 --
+ *   mean over the bins (events_bins_5_avg_1, :304-305) -> crop [crop_h, crop_w] at (crop_x, crop_y) (:310)
+ *   -> HorizontalFlip (:311-312) -> F.interpolate(size=(out_h, out_w), mode='bilinear',
+ *   align_corners=False) (:313-315) -> repeat(3, 1, 1) (:318-319).
+ * Test mode (:316-317) is crop (0, 0, W, 440), flip 0, out = crop size: the resize is then an exact copy.
+ * The normalised [S, B, H, W] grid is never written: every output pixel normalises its four raw taps.
+ *  h_aug      [S] per-window crop origin and flip flag (the augmentation draws of dsec.py:206-210)
+ *  avg_bins   1: average the B bins first (output has 1 bin), 0: keep B bins
+ *  repeat     copies along the channel axis (3 for enforce_3_channels, else 1)
+ *  d_out      [S, repeat * Bo, out_h, out_w] float32, Bo = avg_bins ? 1 : B; channel r * Bo + b = bin b
+ * Workspace: cmda_events_vg_workspace_bytes(...) + 4 * S * B * H * W bytes (the raw grid), unless
+ * d_raw_out is given (then the raw grid goes there). */
+typedef struct cmda_vg_augment {
+    int32_t crop_x, crop_y;
+    int32_t flip;
+} cmda_vg_augment;
+
+size_t cmda_events_vg_augmented_workspace_bytes(int64_t total_events, int S, int H, int W, int B, int mode);
+int cmda_events_vg_augmented_batch(const uint32_t* d_t, const uint16_t* d_x, const uint16_t* d_y, const uint8_t* d_p,
+                                   const int64_t* h_win_start, const int64_t* h_win_end, int S,
+                                   const float* d_rectify_map, const int32_t* h_map_id, int H, int W, int B,
+                                   const float* h_clip, float final_range, int enforce_no_events_zero,
+                                   const cmda_vg_augment* h_aug, int crop_w, int crop_h, int out_w, int out_h,
+                                   int avg_bins, int repeat, float* d_out, float* d_raw_out, int64_t* d_bin_counts,
+                                   void* d_workspace, size_t workspace_bytes, int mode, void* stream);
+
 /* Replaces: events_to_voxel_grid(time, x, y, pol, width, height, num_bins),
  * /root/reference/mmseg/datasets/dsec.py:26-58 (normalize_flag=False), on float32 SoA
  * inputs that are already rectified.  d_grid is [B, H, W] float32. */
@@ -178,6 +208,17 @@ int cmda_logdiff_pair_u8(const uint8_t* d_now, const uint8_t* d_front, int S, in
 int cmda_isr_shift_u8(const uint8_t* d_img, int channels, int S, int H, int W, int shift_pixel, int direction,
                       const float* h_lut, float thr, float clip, float* d_out,
                       void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Mixed-image ISR inside the train step without the GPU -> CPU -> PIL -> GPU bounce.
+ * Replaces: /root/reference/mmseg/models/uda/dacs.py:730-733 --
+ *   clamp(denorm(img, mean, std), 0, 1) * 255 -> np.uint8 -> Image.fromarray -> convert('L')
+ * (denorm = img.mul(std).add(mean) / 255.0, mmseg/models/utils/dacs_transforms.py:52-53).
+ *  d_img   [S, 3, H, W] float32, the normalised image batch as the model sees it
+ *  h_mean, h_std  3 floats each (img_norm_cfg mean / std)
+ *  d_gray  [S, H, W] uint8 'L' plane: feed it to cmda_isr_shift_u8(channels = 1)
+ *  d_rgb   optional [S, H, W, 3] uint8, the bytes PIL would have been handed (may be NULL) */
+int cmda_denorm_rgb_to_gray_u8(const float* d_img, int S, int H, int W, const float* h_mean, const float* h_std,
+                               uint8_t* d_gray, uint8_t* d_rgb, void* stream);
 
 /* PIL 'L' conversion alone (parity of the integer stage). d_rgb [n,3] -> d_gray [n]. */
 int cmda_rgb_to_gray_u8(const uint8_t* d_rgb, int64_t n_pixels, uint8_t* d_gray, void* stream);

@@ -250,6 +250,32 @@ def images_to_events_index(t, t_offset, ms_to_idx, timestamps):
     return out
 
 
+def events_vg_post(events_vg, crop_xy=None, crop_size=None, out_size=None, flip_flag=False, avg_bins=False,
+                   enforce_3_channels=True, test_mode=False):
+    """dsec.py:304-319 on one window's normalised ``[B, H, W]`` grid, statement by statement, with the
+    reference's own torch calls (``torch.mean``, slicing, ``flip``, ``F.interpolate(bilinear,
+    align_corners=False)``, ``repeat``): third-party arithmetic pinned by execution.  ``crop_size`` and
+    ``out_size`` are ``(w, h)`` as ``self.crop_size`` / ``self.after_crop_resize_size`` are after the swap of
+    dsec.py:150-152."""
+    import torch
+    import torch.nn.functional as F
+    ev = torch.from_numpy(np.ascontiguousarray(events_vg, dtype=F32))[None]          # [output_num = 1, B, H, W]
+    if avg_bins:
+        ev = torch.mean(ev, dim=1, keepdim=True)                                      # :304-305
+    ev = ev[0]                                                                        # :306-307
+    if not test_mode:
+        x, y = crop_xy
+        ev = ev[:, y: y + crop_size[1], x: x + crop_size[0]]                           # :310
+        if flip_flag:
+            ev = torch.flip(ev, dims=[-1])                                            # :311-312 (transforms.RandomHorizontalFlip(p=1))
+        ev = F.interpolate(ev[None], size=(out_size[1], out_size[0]), mode='bilinear', align_corners=False)[0]   # :313-315
+    else:
+        ev = ev[:, :440, :]                                                           # :316-317
+    if enforce_3_channels:
+        ev = ev.repeat(3, 1, 1)                                                       # :318-319
+    return ev.numpy()
+
+
 def window_bounds(index_table, now_image_index, image_change_range=1, events_num=-1, i=0):
     """dsec.py:296-302: inclusive ``(start, finish)`` of output window ``i`` or
     ``None`` when ``start > finish``."""
@@ -273,6 +299,22 @@ def pil_gray_L(rgb: np.ndarray) -> np.ndarray:
         return rgb
     r, g, b = (rgb[..., c].astype(np.uint32) for c in range(3))
     return ((19595 * r + 38470 * g + 7471 * b + 32768) >> 16).astype(np.uint8)
+
+
+def mixed_image_to_gray(img, means, stds, return_rgb=False):
+    """dacs.py:730-733 on one normalised float32 image ``[3, H, W]``:
+    ``clamp(denorm(img, means, stds), 0, 1) * 255`` -> HWC -> ``np.uint8`` (truncation) ->
+    ``Image.fromarray`` -> ``convert('L')`` (the first statement of get_image_change_from_pil,
+    utils.py:126).  ``denorm`` is ``img.mul(std).add(mean) / 255.0``
+    (mmseg/models/utils/dacs_transforms.py:52-53); float32, one rounding per operation."""
+    img = np.asarray(img, dtype=F32)
+    m = np.asarray(means, dtype=F32).reshape(3, 1, 1)
+    sd = np.asarray(stds, dtype=F32).reshape(3, 1, 1)
+    v = ((img * sd).astype(F32) + m).astype(F32) / F32(255.0)
+    v = np.clip(v.astype(F32), F32(0.0), F32(1.0)) * F32(255.0)
+    rgb = np.uint8(np.transpose(v.astype(F32), (1, 2, 0)))
+    gray = pil_gray_L(rgb)
+    return (gray, rgb) if return_rgb else gray
 
 
 def log_lut_val_range(val_range) -> np.ndarray:

@@ -249,6 +249,42 @@ def test_events_vg_dsec_shim(cm):
     assert ds_bad.events_vg_for_image(1) is None
 
 
+@pytest.mark.parametrize("bins,avg,flip,test_mode", [(5, False, True, False), (1, False, False, False), (5, True, True, False),
+                                                     (5, False, False, True), (3, False, True, False)])
+def test_events_vg_fused_augment(cm, bins, avg, flip, test_mode):
+    """f-1 (dsec.py:304-319): crop / flip / bilinear resize / repeat fused into the normaliser against the
+    reference's torch statements applied to our own normalised grid (<= 1e-5, the normalised-grid bar) and
+    against the full CPU oracle chain."""
+    from cmda_b200 import synth
+    H, W, n = 480, 640, 150_000
+    t, x, y, p = synth.make_events(n, H, W, seed=synth.seed_for(5, bins))
+    rmap = synth.make_rectify_map(H, W, seed=12)
+    store = cm.EventStore(t, x, y, p, rmap, height=H, width=W, device="cuda:0")
+    starts, fins = [0, 5000], [n - 1, 90_000]
+    crops = [(37, 61), (240, 80)]
+    crop_size, out_size = ((400, 400), (512, 512)) if not test_mode else ((W, 440), (W, 440))
+    xy = crops if not test_mode else [(0, 0), (0, 0)]
+    flips = [int(flip), 0]
+    got = cm.events_vg_augmented_batch(store, starts, fins, bins, crop_xy=xy, crop_size=crop_size, out_size=out_size,
+                                       flips=flips, avg_bins=avg, repeat=3)
+    Bo = 1 if avg else bins
+    assert got.shape == (2, 3 * Bo, out_size[1], out_size[0])
+    grid, raw = cm.events_vg_batch(store, starts, fins, bins, return_raw=True)
+    ref_grids, ref_raws = C.get_events_vg_batch(t, x, y, p, starts, fins, rmap, W, H, bins, return_raw=True)
+    for s in range(2):
+        exp = O.events_vg_post(grid[s].cpu().numpy(), crop_xy=xy[s], crop_size=crop_size, out_size=out_size,
+                               flip_flag=bool(flips[s]), avg_bins=avg, enforce_3_channels=True, test_mode=test_mode)
+        np.testing.assert_allclose(got[s].cpu().numpy(), exp, rtol=0, atol=1e-5)
+        # against the whole reference chain, whenever no voxel's zero / non-zero status differs (rounding
+        # residue of exactly cancelling ON/OFF sums moves the reference's mean / std: see check_normalised)
+        if not ((raw[s].cpu().numpy() == 0) != (ref_raws[s] == 0)).any():
+            ref = O.events_vg_post(ref_grids[s], crop_xy=xy[s], crop_size=crop_size, out_size=out_size,
+                                   flip_flag=bool(flips[s]), avg_bins=avg, enforce_3_channels=True, test_mode=test_mode)
+            np.testing.assert_allclose(got[s].cpu().numpy(), ref, rtol=0, atol=2e-5)
+    if test_mode:    # crop == out: the resize is an exact copy of the normalised grid
+        assert torch.equal(got[:, :Bo], grid[:, :, :440, :])
+
+
 @pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("bins,n,skew", [(5, 300_000, 0.0), (1, 300_000, 0.0), (5, 200_000, 0.3)])
 def test_events_vg_batch_vs_c_oracle(cm, mode, bins, n, skew):
@@ -403,6 +439,31 @@ def test_pseudo_events_large_vs_c_oracle(cm, h, w):
                            parms["clip"], direction)
         ref = C.isr_batch(now, parms["shift"], parms["val_range"], parms["thr"], parms["clip"], direction)
         assert np.array_equal(bits(got[:, 0]), bits(ref)), direction
+
+
+def test_mixed_image_isr_on_device(cm):
+    """a9 (dacs.py:729-744): normalised float image on the GPU -> ISR on the GPU, bit-exact against the
+    reference's sequence (denorm, clamp, uint8, PIL 'L', get_image_change_from_pil, repeat 3)."""
+    rng = np.random.default_rng(21)
+    means, stds = [123.675, 116.28, 103.53], [58.395, 57.12, 57.375]
+    S, H, W = 3, 96, 128
+    img = rng.normal(0.0, 1.4, size=(S, 3, H, W)).astype(np.float32)
+    parms = dict(shift_pixel=1, val_range=(0.01, 1.01), _threshold=0.005, _clip_range=0.1)     # shipped cs2dsec
+    d_img = torch.from_numpy(img).cuda()
+    m = torch.tensor(means).view(1, 3, 1, 1).cuda()
+    sd = torch.tensor(stds).view(1, 3, 1, 1).cuda()
+    gray, rgb = cm.denorm_to_gray(d_img, m, sd, return_rgb=True)
+    for s in range(S):
+        g_ref, rgb_ref = O.mixed_image_to_gray(img[s], means, stds, return_rgb=True)
+        assert np.array_equal(gray[s].cpu().numpy(), g_ref) and np.array_equal(rgb[s].cpu().numpy(), rgb_ref)
+    for direction in ("leftdown", "rightup"):
+        got = cm.mixed_image_isr(d_img, m, sd, shift_direction=direction, **parms)
+        assert got.is_cuda and got.shape == (S, 3, H, W)
+        for s in range(S):
+            ref = O.get_image_change_from_pil(O.mixed_image_to_gray(img[s], means, stds), W, H, shift_direction=direction,
+                                              **parms)
+            for c in range(3):
+                assert np.array_equal(bits(got[s, c]), bits(ref[0]))
 
 
 # ------------------------------------------------------------------ a1: slicer

@@ -122,3 +122,20 @@ def test_images_to_events_index():
     got = O.images_to_events_index(c["t"], int(c["t_offset"]), c["ms_to_idx"], c["timestamps"])
     assert got == [int(v) for v in c["result"]]
     assert -1 in got and max(got) == len(c["t"]) - 1
+
+
+def test_mixed_image_to_gray_matches_torch_and_pil():
+    """a9 (dacs.py:730-733): the oracle's float32 restatement against the reference's own statements
+    executed with torch + PIL (both present here): denorm, clamp, * 255, np.uint8, fromarray, convert('L')."""
+    import torch
+    from PIL import Image
+    rng = np.random.default_rng(11)
+    means = torch.tensor([123.675, 116.28, 103.53]).view(1, 3, 1, 1)      # img_norm_cfg, dsec.py:325-326
+    stds = torch.tensor([58.395, 57.12, 57.375]).view(1, 3, 1, 1)
+    img = torch.from_numpy(rng.normal(0.0, 1.4, size=(1, 3, 37, 53)).astype(np.float32))
+    mixed = torch.clamp(img.mul(stds).add(means) / 255.0, 0, 1) * 255     # dacs.py:730 + dacs_transforms.py:52-53
+    mixed = np.transpose(mixed.cpu().numpy()[0], (1, 2, 0))               # dacs.py:731
+    pil = Image.fromarray(np.uint8(mixed))                                # dacs.py:733
+    gray, rgb = O.mixed_image_to_gray(img[0].numpy(), means.numpy().ravel(), stds.numpy().ravel(), return_rgb=True)
+    assert np.array_equal(rgb, np.asarray(pil))
+    assert np.array_equal(gray, np.asarray(pil.convert('L')))             # utils.py:126
