@@ -282,6 +282,57 @@ def pseudo_events_leg(dev, peak, steps=10, warmup=3):
     return res
 
 
+# ------------------------------------------------------------------------------------ train-step input path leg
+def train_step_input_leg(dev, steps=20, warmup=3):
+    """BASELINE config C5: the input path of one CMDA fusion train step on one GPU, as the reference's loader
+    and DACS step produce it for samples_per_gpu = 2 (configs/_base_/datasets/...512x512.py:11): per sample one
+    50 ms DSEC window at real density (330 k events, create_dsec_dataset_txt.py:15-18) -> voxel grid -> events_norm
+    -> crop 400x400 -> flip -> resize -> x3 (dsec.py:286-320), the target ISR of the warp image and the
+    mixed-image ISR of the train step (dacs.py:729-744), at the reference's 512x512 and at BASELINE's 1024x512.
+    Latency per step, device resident, CUDA-event timed."""
+    import torch
+    import cmda_b200
+    from cmda_b200 import synth
+    n, S = 330_000, 2
+    ts, xs, ys, ps, starts, fins = [], [], [], [], [], []
+    for k in range(S):
+        t, x, y, p = synth.make_events(n, H, W, seed=synth.seed_for(5, k))
+        ts.append(t); xs.append(x); ys.append(y); ps.append(p)
+        starts.append(k * n); fins.append((k + 1) * n - 1)
+    rmap = synth.make_rectify_map(H, W, seed=synth.seed_for(5, 99))
+    store = cmda_b200.EventStore(np.concatenate(ts), np.concatenate(xs), np.concatenate(ys), np.concatenate(ps), rmap,
+                                 height=H, width=W, device=dev)
+    parms = dict(shift_pixel=1, val_range=(0.01, 1.01), _threshold=0.005, _clip_range=0.1)      # shipped cs2dsec isr_parms
+    means = torch.tensor([123.675, 116.28, 103.53], device=dev).view(1, 3, 1, 1)
+    stds = torch.tensor([58.395, 57.12, 57.375], device=dev).view(1, 3, 1, 1)
+    res = {"config": f"C5: {S} samples/GPU, {n} events per 50 ms window, B=1 (shipped events_bins), device resident"}
+    for name, (ow, oh) in (("crop_512x512", (512, 512)), ("crop_1024x512", (1024, 512))):
+        g = torch.Generator(device="cpu").manual_seed(7)
+        mixed = torch.randn((S, 3, oh, ow), generator=g).to(dev)
+        warp = (torch.rand((S, oh, ow), generator=g) * 255).to(torch.uint8).to(dev)
+
+        def step():
+            ev = cmda_b200.events_vg_augmented_batch(store, starts, fins, 1, crop_xy=[(37, 61), (140, 20)], crop_size=(400, 400),
+                                                     out_size=(ow, oh), flips=[1, 0], repeat=3)
+            tgt = cmda_b200.isr_batch(warp, parms["shift_pixel"], parms["val_range"], parms["_threshold"],
+                                      parms["_clip_range"], "rightdown")
+            mix = cmda_b200.mixed_image_isr(mixed, means, stds, shift_direction="leftup", **parms)
+            return ev, tgt, mix
+
+        for _ in range(warmup):
+            step()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / steps
+        res[name] = {"ms_per_step": ms, "samples_per_s": S / (ms * 1e-3), "events_per_s": S * n / (ms * 1e-3)}
+    return res
+
+
 # ------------------------------------------------------------------------------------ GPU leg
 def run_gpu(args, rank, local_rank, world):
     import torch
@@ -414,9 +465,10 @@ def run_gpu(args, rank, local_rank, world):
             cpu = {"value": rate, "unit": "Mevents/s", "cores": min(cores, nw), "kind": "port",
                    "sample": f"{nw} of the step's {WINDOWS_PER_GPU} windows x {args.events} events, one window "
                              f"per thread, {dt:.1f} s"}
-        pseudo = None
+        pseudo = c5 = None
         if world == 1 and not args.no_pseudo:
             pseudo = pseudo_events_leg(dev, peak)
+            c5 = train_step_input_leg(dev)
         line = {
             "metric": "voxelized_events_per_s", "value": value, "unit": "Mevents/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -426,7 +478,7 @@ def run_gpu(args, rank, local_rank, world):
             "e2e": {"value": e2e_value, "unit": "Mevents/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "steps": e2e_steps, "matches_device_path": same},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": roofline, "cpu_baseline": cpu, "pseudo_events": pseudo,
+            "roofline": roofline, "cpu_baseline": cpu, "pseudo_events": pseudo, "train_step_input_path": c5,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
