@@ -33,6 +33,12 @@ size_t factored_scratch_bytes(int group, int H, int W, int B);
 int factored_max_maps(void);
 int launch_factored(const uint32_t*, const uint16_t*, const uint16_t*, const uint8_t*, const WindowTable&, int, long long,
                     const float*, int, int, int, void*, int64_t*, float*, PartialStats*, void*, size_t, cudaStream_t);
+int exact_supported(int H, int W, int B);
+size_t exact_workspace_bytes(long long max_window_events);
+int launch_exact_raw(const uint32_t*, const uint16_t*, const uint16_t*, const uint8_t*, const WindowTable&, int, const float*, int,
+                     int, int, float*, int64_t*, void*, size_t, cudaStream_t);
+int launch_exact_f32(const float*, const float*, const float*, const float*, long long, int, int, int, float*, int64_t*, void*,
+                     size_t, cudaStream_t);
 int launch_tiled_scatter(const uint32_t*, const uint16_t*, const uint16_t*, const uint8_t*, const WindowTable&, int,
                          const float*, int, int, int, long long*, int64_t*, void*, size_t, cudaStream_t);
 
@@ -124,6 +130,7 @@ size_t cmda_events_vg_workspace_bytes(int64_t total_events, int S, int H, int W,
     if (mode == CMDA_VOXEL_TILED && tiled_supported(H, W, B)) need += tiled_workspace_bytes(total_events, S, H, W, B);
     if ((mode == CMDA_VOXEL_FACTORED || mode == CMDA_VOXEL_AUTO) && factored_supported(H, W, B))
         need += factored_scratch_bytes(group, H, W, B);
+    if (mode == CMDA_VOXEL_EXACT) need += exact_workspace_bytes(total_events);    // total_events bounds the largest window
     return need + 256;
 }
 
@@ -171,7 +178,7 @@ int events_vg_impl(const uint32_t* d_t, const uint16_t* d_x, const uint16_t* d_y
     const int use_mode = resolve_mode(mode, total, S, H, W, B);
     if (use_mode == CMDA_VOXEL_TILED && !tiled_supported(H, W, B)) return CMDA_ERR_UNSUPPORTED;
     if (use_mode == CMDA_VOXEL_FACTORED && !factored_supported(H, W, B)) return CMDA_ERR_UNSUPPORTED;
-    if (use_mode == CMDA_VOXEL_EXACT) return CMDA_ERR_UNSUPPORTED;  // TODO exact-order mode
+    if (use_mode == CMDA_VOXEL_EXACT && !exact_supported(H, W, B)) return CMDA_ERR_UNSUPPORTED;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long V = static_cast<long long>(B) * H * W;
 
@@ -246,6 +253,23 @@ int events_vg_impl(const uint32_t* d_t, const uint16_t* d_x, const uint16_t* d_y
             }
             continue;
         }
+        if (use_mode == CMDA_VOXEL_EXACT) {
+            // reference-order float32 sums straight into the raw grid; statistics from the float grid
+            const size_t ab = acc_bytes(sn, H, W, B);
+            rc = launch_exact_raw(d_t, d_x, d_y, d_p, tab, sn, d_rectify_map, H, W, B, raw_g, bins_g, scratch + ab,
+                                  scratch_bytes - ab, st);
+            if (rc != CMDA_OK) return rc;
+            phase_mark(st);
+            rc = launch_convert_stats(nullptr, raw_g, sn, V, part_g, st);
+            if (rc != CMDA_OK) return rc;
+            phase_mark(st);
+            if (normalize) {
+                rc = finish();
+                if (rc != CMDA_OK) return rc;
+                phase_mark(st);
+            }
+            continue;
+        }
         CMDA_CUDA_TRY(cudaMemsetAsync(acc, 0, sizeof(long long) * sn * V, st));
         phase_mark(st);
         if (use_mode == CMDA_VOXEL_TILED) {
@@ -310,13 +334,18 @@ int cmda_voxel_grid_f32(const float* d_time, const float* d_x, const float* d_y,
     if (workspace_bytes < cmda_events_vg_workspace_bytes(n, 1, H, W, B, mode)) return CMDA_ERR_WORKSPACE;
     // float32 events are already rectified: there is no map gather to tile, so this entry point
     // runs the GLOBAL scatter (AUTO resolves to it); TILED / EXACT are refused explicitly
-    if (mode == CMDA_VOXEL_TILED || mode == CMDA_VOXEL_EXACT || mode == CMDA_VOXEL_FACTORED) return CMDA_ERR_UNSUPPORTED;
+    if (mode == CMDA_VOXEL_TILED || mode == CMDA_VOXEL_FACTORED) return CMDA_ERR_UNSUPPORTED;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long V = static_cast<long long>(B) * H * W;
     char* ws = static_cast<char*>(d_workspace);
     PartialStats* partials = reinterpret_cast<PartialStats*>(ws);
     char* scratch = ws + stats_bytes(1);
     if (d_bin_counts) CMDA_CUDA_TRY(cudaMemsetAsync(d_bin_counts, 0, sizeof(int64_t) * B, st));
+    if (mode == CMDA_VOXEL_EXACT) {
+        const size_t ab = acc_bytes(1, H, W, B);
+        return launch_exact_f32(d_time, d_x, d_y, d_pol, n, H, W, B, d_grid, d_bin_counts, scratch + ab,
+                                workspace_bytes - stats_bytes(1) - ab, st);
+    }
     long long* acc = reinterpret_cast<long long*>(scratch);
     CMDA_CUDA_TRY(cudaMemsetAsync(acc, 0, sizeof(long long) * V, st));
     int rc = launch_scatter_global_f32(d_time, d_x, d_y, d_pol, n, H, W, B, acc, d_bin_counts, st);

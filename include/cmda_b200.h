@@ -49,12 +49,14 @@ enum {
  * rounding (2^-24 relative); for B == 1 it is the exact sum of the reference's weights.
  * Capacity: fewer than 2^19 events of net polarity per (raw pixel, temporal bin, window).
  * EXACT performs the reference's own float32 additions in the reference's own order
- * (corner pass major, event index minor: dsec.py:47-58). */
+ * (corner pass major, event index minor: dsec.py:47-58): its raw grid is BIT-IDENTICAL to the
+ * single-thread reference.  A verification mode (stable sort of every event-corner pair, 64 bytes of
+ * workspace per pair of the largest window), not a fast one. */
 enum {
     CMDA_VOXEL_GLOBAL = 0,   /* one 64-bit integer RED per corner into an L2-resident grid     */
     CMDA_VOXEL_TILED = 1,    /* raw-tile multisplit + shared-memory fixed-point accumulation   */
     CMDA_VOXEL_AUTO = 2,     /* FACTORED where it applies (raw DSEC events), else GLOBAL       */
-    CMDA_VOXEL_EXACT = 3,    /* stable cell sort + ordered float32 accumulation (not built yet) */
+    CMDA_VOXEL_EXACT = 3,    /* stable sort by (voxel, corner pass) + ordered float32 accumulation */
     CMDA_VOXEL_FACTORED = 4  /* sensor-space temporal accumulation + per-pixel rectify gather  */
 };
 
