@@ -353,6 +353,35 @@ def test_events_vg_modes_agree(cm):
             assert np.all(fa[s].cpu().numpy()[n_contrib == 0] == 0.0)
 
 
+def test_events_vg_large_window_b1(cm):
+    """B == 1 (the shipped events_bins) on a ragged batch with a > 2^20-event window, an unaligned start and a
+    single-timestamp window: exact against the float64 sum of the reference's weights, bit-reproducible,
+    per-bin counts equal to GLOBAL's."""
+    from cmda_b200 import synth
+    H, W, n = 480, 640, 1_300_000
+    t, x, y, p = synth.make_events(n, H, W, seed=synth.seed_for(1, 77), skew=0.1)
+    t[-5000:] = t[-5000]                                   # a run of identical timestamps at the end
+    rmap = synth.make_rectify_map(H, W, seed=8)
+    store = cm.EventStore(t, x, y, p, rmap, height=H, width=W, device="cuda:0")
+    starts, fins = [3, 100_001, n - 4000], [n - 6000, 160_000, n - 1]       # large, small, single-timestamp
+    fa, counts = cm.events_vg_batch(store, starts, fins, 1, mode="factored", normalize=False, return_bin_counts=True)
+    gl, counts_g = cm.events_vg_batch(store, starts, fins, 1, mode="global", normalize=False, return_bin_counts=True)
+    again = cm.events_vg_batch(store, starts, fins, 1, mode="factored", normalize=False)
+    assert np.array_equal(bits(fa), bits(again))
+    assert torch.equal(counts, counts_g)
+    assert torch.count_nonzero(fa[2]) == 0 and int(counts[2].sum()) == 0     # NaN t_norm: nothing lands (Q3)
+    for s in range(2):
+        sl = slice(starts[s], fins[s] + 1)
+        tf, xf, yf, pf = O.rectify_events(t[sl], x[sl], y[sl], p[sl], rmap)
+        truth, abs_w, n_contrib = O.voxel_grid_f64(tf, xf, yf, pf, W, H, 1, return_aux=True)
+        err = np.abs(fa[s].cpu().numpy().astype(np.float64) - truth)
+        assert np.all(err <= n_contrib * 2.0 ** -31 + 1.2e-7 * np.abs(truth))
+        assert_raw_close(gl[s], truth.astype(np.float32), abs_w, n_contrib)
+    out = cm.events_vg_batch(store, starts[:1], fins[:1], 1, mode="factored")
+    ref = C.get_events_vg_batch(t, x, y, p, starts[:1], fins[:1], rmap, W, H, 1)
+    assert np.isfinite(out.cpu().numpy()).all() and out.shape == (1, 1, H, W) and ref.shape == (1, 1, H, W)
+
+
 def test_events_vg_bad_windows(cm):
     from cmda_b200 import synth
     t, x, y, p = synth.make_events(1000, 48, 64, seed=1)
