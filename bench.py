@@ -434,9 +434,9 @@ def run_gpu(args, rank, local_rank, world):
             names = ["memset(int64 grid)", "voxel_scatter_global_kernel", "convert_stats_kernel", "norm_apply_kernel"]
             launches_per_step = 3
         elif resolved == _lib.VOXEL_FACTORED:
-            names = ["memset(sensor grid)", "rectify_index_build+stencil_build kernels", "sensor_accumulate_kernel",
-                     "plane_finalize+rectify_gather+regroup_partials kernels", "norm_apply_kernel"]
-            launches_per_step = 7 if args.bins > 1 else 6   # kernels only (memsets not counted)
+            names = ["memset(sensor grid)", "rectify_index_{build,sort}+stencil_build+out_tile_box kernels",
+                     "sensor_accumulate_kernel", "rectify_gather+regroup_partials kernels", "norm_apply_kernel"]
+            launches_per_step = 8   # kernels only (memsets not counted)
         else:
             names = ["memset(int64 grid)", "tile_bbox+tile_count+tile_scan kernels", "tile_partition_kernel",
                      "tile_accumulate_kernel", "convert_stats_kernel", "norm_apply_kernel"]
