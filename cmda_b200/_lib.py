@@ -48,7 +48,12 @@ SIGNATURES = {
                                     _int, _vp, _vp, _vp, _vp, _sz, _int, _vp]),
     "cmda_events_vg_augmented_workspace_bytes": (_sz, [_i64, _int, _int, _int, _int, _int]),
     "cmda_events_vg_augmented_batch": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _vp, _vp, _int, _int, _int, _vp, _f32, _int,
-                                              _vp, _int, _int, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _sz, _int, _vp]),
+                                              _vp, _int, _int, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _sz, _int, _vp,
+                                              _vp]),
+    "cmda_rectify_plan_bytes": (_sz, [_int, _int]),
+    "cmda_rectify_plan_build": (_int, [_vp, _int, _int, _int, _vp, _vp]),
+    "cmda_events_vg_batch_planned": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _vp, _vp, _int, _int, _int, _vp, _f32, _int,
+                                            _int, _vp, _vp, _vp, _vp, _sz, _int, _vp, _vp]),
     "cmda_voxel_grid_f32": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _int, _int, _vp, _vp, _vp, _sz, _int, _vp]),
     "cmda_events_norm_workspace_bytes": (_sz, [_int]),
     "cmda_events_norm_batch": (_int, [_vp, _int, _i64, _vp, _f32, _int, _vp, _sz, _vp]),

@@ -31,8 +31,10 @@ int tiled_supported(int H, int W, int B);
 int factored_supported(int H, int W, int B);
 size_t factored_scratch_bytes(int group, int H, int W, int B);
 int factored_max_maps(void);
+size_t factored_plan_bytes(int H, int W);
+int launch_plan_build(const float*, int, int, int, void*, cudaStream_t);
 int launch_factored(const uint32_t*, const uint16_t*, const uint16_t*, const uint8_t*, const WindowTable&, int, long long,
-                    const float*, int, int, int, void*, int64_t*, float*, PartialStats*, void*, size_t, cudaStream_t);
+                    const float*, int, int, int, void*, int64_t*, float*, PartialStats*, void*, size_t, const void*, cudaStream_t);
 int exact_supported(int H, int W, int B);
 size_t exact_workspace_bytes(long long max_window_events);
 int launch_exact_raw(const uint32_t*, const uint16_t*, const uint16_t*, const uint8_t*, const WindowTable&, int, const float*, int,
@@ -146,7 +148,8 @@ int events_vg_impl(const uint32_t* d_t, const uint16_t* d_x, const uint16_t* d_y
                    const int64_t* h_win_start, const int64_t* h_win_end, int S, const float* d_rectify_map,
                    const int32_t* h_map_id, int H, int W, int B, const float* h_clip, float final_range,
                    int enforce_no_events_zero, int normalize, float* d_out, float* d_raw_out, int64_t* d_bin_counts,
-                   void* d_workspace, size_t workspace_bytes, int mode, void* stream, const AugmentArgs* aug) {
+                   void* d_workspace, size_t workspace_bytes, int mode, void* stream, const AugmentArgs* aug,
+                   const void* d_plans) {
     if (S < 0 || H <= 0 || W <= 0 || B <= 0) return CMDA_ERR_BAD_ARG;
     if (S == 0) return CMDA_OK;
     if (!d_t || !d_x || !d_y || !d_p || !h_win_start || !h_win_end || !d_out || !d_workspace) return CMDA_ERR_BAD_ARG;
@@ -192,7 +195,7 @@ int events_vg_impl(const uint32_t* d_t, const uint16_t* d_x, const uint16_t* d_y
         // a launch group: at most kMaxWindows windows and, for FACTORED, at most factored_max_maps()
         // distinct rectify maps (one inverse index each)
         sn = (S - s0) < kMaxWindows ? (S - s0) : kMaxWindows;
-        if (use_mode == CMDA_VOXEL_FACTORED && h_map_id && d_rectify_map) {
+        if (use_mode == CMDA_VOXEL_FACTORED && h_map_id && d_rectify_map && !d_plans) {
             int ids[kMaxWindows], n_ids = 0, k = 0;
             for (; k < sn; ++k) {
                 const int id = h_map_id[s0 + k];
@@ -243,7 +246,7 @@ int events_vg_impl(const uint32_t* d_t, const uint16_t* d_x, const uint16_t* d_y
         if (use_mode == CMDA_VOXEL_FACTORED) {
             const size_t ab = acc_bytes(sn, H, W, B);
             rc = launch_factored(d_t, d_x, d_y, d_p, tab, sn, max_events, d_rectify_map, H, W, B, acc, bins_g, raw_g,
-                                 part_g, scratch + ab, scratch_bytes - ab, st);   // marks: memset | index | accumulate
+                                 part_g, scratch + ab, scratch_bytes - ab, d_plans, st);   // marks: memset | plans | accumulate
             if (rc != CMDA_OK) return rc;
             phase_mark(st);
             if (normalize) {
@@ -303,7 +306,31 @@ int cmda_events_vg_batch(const uint32_t* d_t, const uint16_t* d_x, const uint16_
                          int64_t* d_bin_counts, void* d_workspace, size_t workspace_bytes, int mode, void* stream) {
     return events_vg_impl(d_t, d_x, d_y, d_p, h_win_start, h_win_end, S, d_rectify_map, h_map_id, H, W, B, h_clip, final_range,
                           enforce_no_events_zero, normalize, d_out, d_raw_out, d_bin_counts, d_workspace, workspace_bytes, mode,
-                          stream, nullptr);
+                          stream, nullptr, nullptr);
+}
+
+int cmda_events_vg_batch_planned(const uint32_t* d_t, const uint16_t* d_x, const uint16_t* d_y, const uint8_t* d_p,
+                                 const int64_t* h_win_start, const int64_t* h_win_end, int S, const float* d_rectify_map,
+                                 const int32_t* h_map_id, int H, int W, int B, const float* h_clip, float final_range,
+                                 int enforce_no_events_zero, int normalize, float* d_out, float* d_raw_out,
+                                 int64_t* d_bin_counts, void* d_workspace, size_t workspace_bytes, int mode,
+                                 const void* d_plans, void* stream) {
+    return events_vg_impl(d_t, d_x, d_y, d_p, h_win_start, h_win_end, S, d_rectify_map, h_map_id, H, W, B, h_clip, final_range,
+                          enforce_no_events_zero, normalize, d_out, d_raw_out, d_bin_counts, d_workspace, workspace_bytes, mode,
+                          stream, nullptr, d_plans);
+}
+
+size_t cmda_rectify_plan_bytes(int H, int W) {
+    if (H <= 0 || W <= 0) return 0;
+    return factored_plan_bytes(H, W);
+}
+
+int cmda_rectify_plan_build(const float* d_rectify_map, int n_maps, int H, int W, void* d_plans, void* stream) {
+    if (n_maps < 0 || H <= 0 || W <= 0) return CMDA_ERR_BAD_ARG;
+    if (n_maps == 0) return CMDA_OK;
+    if (!d_rectify_map || !d_plans) return CMDA_ERR_BAD_ARG;
+    if (reinterpret_cast<uintptr_t>(d_plans) & 255) return CMDA_ERR_WORKSPACE;
+    return launch_plan_build(d_rectify_map, n_maps, H, W, d_plans, static_cast<cudaStream_t>(stream));
 }
 
 size_t cmda_events_vg_augmented_workspace_bytes(int64_t total_events, int S, int H, int W, int B, int mode) {
@@ -317,11 +344,11 @@ int cmda_events_vg_augmented_batch(const uint32_t* d_t, const uint16_t* d_x, con
                                    const float* h_clip, float final_range, int enforce_no_events_zero,
                                    const cmda_vg_augment* h_aug, int crop_w, int crop_h, int out_w, int out_h,
                                    int avg_bins, int repeat, float* d_out, float* d_raw_out, int64_t* d_bin_counts,
-                                   void* d_workspace, size_t workspace_bytes, int mode, void* stream) {
+                                   void* d_workspace, size_t workspace_bytes, int mode, const void* d_plans, void* stream) {
     const AugmentArgs aug{h_aug, crop_w, crop_h, out_w, out_h, avg_bins, repeat};
     return events_vg_impl(d_t, d_x, d_y, d_p, h_win_start, h_win_end, S, d_rectify_map, h_map_id, H, W, B, h_clip, final_range,
                           enforce_no_events_zero, 1, d_out, d_raw_out, d_bin_counts, d_workspace, workspace_bytes, mode, stream,
-                          &aug);
+                          &aug, d_plans);
 }
 
 int cmda_voxel_grid_f32(const float* d_time, const float* d_x, const float* d_y, const float* d_pol, int64_t n, int W,

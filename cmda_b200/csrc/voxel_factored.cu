@@ -56,10 +56,19 @@ constexpr int kCountShift = 44;                         // event count lives abo
 constexpr int kGatherThreads = 256;
 constexpr int kScanThreads = 1024;
 
+// Everything stage B needs to know about one rectify map -- inverse index, gather stencil, tile boxes --
+// is one contiguous "plan" blob (layout below).  Plans are built per call into the workspace (one per
+// distinct map of the window group) or once by the caller with cmda_rectify_plan_build (one per map id).
 struct MapSlots {
-    int slot[kMaxWindows];     // which inverse index (distinct map of this group) a window uses
-    int map_of_slot[kMaxWindows];
+    int slot[kMaxWindows];          // which plan slot (distinct map of this group) a window uses
+    int map_of_slot[kMaxWindows];   // the map id of a slot
+    int plan_of_slot[kMaxWindows];  // index of the slot's plan in the plan array
+    char* plan_base;
+    size_t plan_stride;
 };
+__device__ __forceinline__ char* plan_of(const MapSlots& ms, int slot) {
+    return ms.plan_base + static_cast<size_t>(ms.plan_of_slot[slot]) * ms.plan_stride;
+}
 
 // ---- stage A ----------------------------------------------------------------------------------
 struct SensEv8 {
@@ -216,9 +225,11 @@ __device__ __forceinline__ bool cell_of(float2 m, int H, int W, unsigned& cell) 
     return true;
 }
 
-__device__ __forceinline__ MapIndex map_index_at(char* base, int slot, size_t ncells_padded, size_t npx) {
-    const size_t per = ncells_padded * (sizeof(unsigned) + sizeof(uint4)) + 256 + npx * sizeof(uint2);
-    char* b = base + static_cast<size_t>(slot) * per;
+__device__ __host__ __forceinline__ size_t index_bytes_of(size_t ncells_padded, size_t npx) {
+    return (ncells_padded * (sizeof(unsigned) + sizeof(uint4)) + 256 + npx * sizeof(uint2) + 255) / 256 * 256;
+}
+__device__ __forceinline__ MapIndex map_index_at(char* plan, size_t ncells_padded, size_t npx) {
+    char* b = plan;
     MapIndex ix;
     ix.slots = reinterpret_cast<uint4*>(b);
     ix.cnt = reinterpret_cast<unsigned*>(b + ncells_padded * sizeof(uint4));
@@ -228,12 +239,11 @@ __device__ __forceinline__ MapIndex map_index_at(char* base, int slot, size_t nc
 }
 
 __global__ void __launch_bounds__(256)
-rectify_index_build_kernel(const float2* __restrict__ maps, MapSlots ms, int H, int W, char* __restrict__ index_ws,
-                           size_t ncells_padded) {
+rectify_index_build_kernel(const float2* __restrict__ maps, MapSlots ms, int H, int W, size_t ncells_padded) {
     const int slot = blockIdx.y;
     const int npx = H * W;
     const float2* map = maps + static_cast<size_t>(ms.map_of_slot[slot]) * npx;
-    const MapIndex ix = map_index_at(index_ws, slot, ncells_padded, npx);
+    const MapIndex ix = map_index_at(plan_of(ms, slot), ncells_padded, npx);
     unsigned* slots = reinterpret_cast<unsigned*>(ix.slots);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += gridDim.x * blockDim.x) {
         unsigned cell;
@@ -247,12 +257,12 @@ rectify_index_build_kernel(const float2* __restrict__ maps, MapSlots ms, int H, 
 // The slots of a cell fill in atomic order; sorting them (<= 4 values) makes every later walk over the
 // cells deterministic.  One thread per cell.
 __global__ void __launch_bounds__(256)
-rectify_index_sort_kernel(MapSlots ms, int H, int W, char* __restrict__ index_ws, size_t ncells_padded) {
+rectify_index_sort_kernel(MapSlots ms, int H, int W, size_t ncells_padded) {
     const int slot = blockIdx.y;
     const unsigned ncells = static_cast<unsigned>(H + 1) * static_cast<unsigned>(W + 1);
     const unsigned c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncells) return;
-    const MapIndex ix = map_index_at(index_ws, slot, ncells_padded, static_cast<size_t>(H) * W);
+    const MapIndex ix = map_index_at(plan_of(ms, slot), ncells_padded, static_cast<size_t>(H) * W);
     const unsigned n = min(ix.cnt[c], static_cast<unsigned>(kCellSlots));
     if (n < 2) return;
     uint4 v = ix.slots[c];
@@ -281,8 +291,8 @@ struct Stencil {
 __device__ __host__ __forceinline__ size_t stencil_bytes(size_t npx) {
     return (npx * kEll * (sizeof(unsigned) + sizeof(float)) + npx + 255) / 256 * 256;
 }
-__device__ __forceinline__ Stencil stencil_at(char* base, int slot, size_t npx) {
-    char* b = base + static_cast<size_t>(slot) * stencil_bytes(npx);
+__device__ __forceinline__ Stencil stencil_at(char* plan, size_t ncells_padded, size_t npx) {
+    char* b = plan + index_bytes_of(ncells_padded, npx);
     Stencil st;
     st.P = reinterpret_cast<unsigned*>(b);
     st.w = reinterpret_cast<float*>(b + npx * kEll * sizeof(unsigned));
@@ -331,15 +341,14 @@ __device__ __forceinline__ bool for_each_source(const MapIndex& ix, const float2
 }
 
 __global__ void __launch_bounds__(256)
-stencil_build_kernel(const float2* __restrict__ maps, MapSlots ms, int H, int W, char* __restrict__ index_ws,
-                     size_t ncells_padded, char* __restrict__ stencil_ws) {
+stencil_build_kernel(const float2* __restrict__ maps, MapSlots ms, int H, int W, size_t ncells_padded) {
     const int slot = blockIdx.y;
     const unsigned npx = static_cast<unsigned>(H) * static_cast<unsigned>(W);
     const unsigned px = blockIdx.x * blockDim.x + threadIdx.x;
     if (px >= npx) return;
     const float2* map = maps + static_cast<size_t>(ms.map_of_slot[slot]) * npx;
-    const MapIndex ix = map_index_at(index_ws, slot, ncells_padded, npx);
-    const Stencil sc = stencil_at(stencil_ws, slot, npx);
+    const MapIndex ix = map_index_at(plan_of(ms, slot), ncells_padded, npx);
+    const Stencil sc = stencil_at(plan_of(ms, slot), ncells_padded, npx);
     const int X = static_cast<int>(px % static_cast<unsigned>(W)), Y = static_cast<int>(px / static_cast<unsigned>(W));
     unsigned n = 0;
     const bool overfull = for_each_source(ix, map, X, Y, W, false, [&](unsigned P, float w) {
@@ -373,12 +382,13 @@ constexpr int kOutW = 64, kOutH = 8, kOutThreads = kOutW * kOutH;
 constexpr int kStageBytes = 64 * 1024;       // shared memory for the staged planes of one tile
 
 __global__ void __launch_bounds__(kOutThreads)
-out_tile_box_kernel(MapSlots ms, int H, int W, char* __restrict__ stencil_ws, int4* __restrict__ boxes) {
+out_tile_box_kernel(MapSlots ms, int H, int W, size_t ncells_padded) {
     const int slot = blockIdx.y;
     const unsigned npx = static_cast<unsigned>(H) * static_cast<unsigned>(W);
     const int tiles_x = (W + kOutW - 1) / kOutW;
     const int X = (blockIdx.x % tiles_x) * kOutW + (threadIdx.x % kOutW), Y = (blockIdx.x / tiles_x) * kOutH + (threadIdx.x / kOutW);
-    const Stencil sc = stencil_at(stencil_ws, slot, npx);
+    const Stencil sc = stencil_at(plan_of(ms, slot), ncells_padded, npx);
+    int4* boxes = reinterpret_cast<int4*>(plan_of(ms, slot) + index_bytes_of(ncells_padded, npx) + stencil_bytes(npx));
     int x0 = INT32_MAX, y0 = INT32_MAX, x1 = -1, y1 = -1, bad = 0;
     if (X < W && Y < H) {
         const unsigned px = static_cast<unsigned>(Y) * W + X;
@@ -406,7 +416,7 @@ out_tile_box_kernel(MapSlots ms, int H, int W, char* __restrict__ stencil_ws, in
         int4 box = make_int4(0, 0, 0, 0);                          // w == 0, h == 0: nothing to stage
         if (bad) box = make_int4(0, 0, -1, -1);                    // incomplete rows: per-pixel path
         else if (x1 >= x0) box = make_int4(x0, y0, x1 - x0 + 1, y1 - y0 + 1);
-        boxes[static_cast<size_t>(slot) * gridDim.x + blockIdx.x] = box;
+        boxes[blockIdx.x] = box;
     }
 }
 
@@ -440,8 +450,7 @@ __device__ __noinline__ GatherRow<BT> gather_pixel_from_cells(const void* __rest
 template <int BT>
 __global__ void __launch_bounds__(kOutThreads)
 rectify_gather_kernel(const void* __restrict__ R, WindowTable tab, MapSlots ms, const float2* __restrict__ maps,
-                      char* __restrict__ index_ws, size_t ncells_padded, char* __restrict__ stencil_ws,
-                      const int4* __restrict__ boxes, int H, int W, int Brt, float* __restrict__ raw,
+                      size_t ncells_padded, int H, int W, int Brt, float* __restrict__ raw,
                       PartialStats* __restrict__ block_partials) {
     extern __shared__ double s_planes[];                     // [box pixels][B]
     constexpr int BA = BT ? BT : 24;
@@ -461,7 +470,8 @@ rectify_gather_kernel(const void* __restrict__ R, WindowTable tab, MapSlots ms, 
         const int bx = (blockIdx.x % tiles_x) * kOutW, by = (blockIdx.x / tiles_x) * kOutH;
         box = make_int4(bx, by, min(kOutW, W - bx), min(kOutH, H - by));
     } else {
-        box = __ldg(boxes + static_cast<size_t>(ms.slot[s]) * gridDim.x + blockIdx.x);
+        box = __ldg(reinterpret_cast<const int4*>(plan_of(ms, ms.slot[s]) + index_bytes_of(ncells_padded, npx) + stencil_bytes(npx)) +
+                    blockIdx.x);
     }
     const bool staged = box.z > 0 && static_cast<size_t>(box.z) * box.w * B * sizeof(double) <= kStageBytes;
     if (staged) {
@@ -491,13 +501,13 @@ rectify_gather_kernel(const void* __restrict__ R, WindowTable tab, MapSlots ms, 
             if (identity) {
                 accumulate((static_cast<unsigned>(Y) << 16) | static_cast<unsigned>(X), 1.0f);
             } else {
-                const Stencil sc = stencil_at(stencil_ws, ms.slot[s], npx);
+                const Stencil sc = stencil_at(plan_of(ms, ms.slot[s]), ncells_padded, npx);
                 const unsigned n = sc.n[px];
                 for (unsigned k = 0; k < n; ++k) accumulate(__ldg(sc.P + k * npx + px), __ldg(sc.w + k * npx + px));
             }
         } else if (box.z != 0) {     // box.z == 0: no source pixel reaches this tile, the sums stay 0
             const GatherRow<BA> row = gather_pixel_from_cells<BA>(R, s, npx, maps + static_cast<size_t>(tab.w[s].map_id) * npx,
-                                                                  map_index_at(index_ws, ms.slot[s], ncells_padded, npx), X, Y, W, B);
+                                                                  map_index_at(plan_of(ms, ms.slot[s]), ncells_padded, npx), X, Y, W, B);
 #pragma unroll
             for (int b = 0; b < BA; ++b) acc[b] = row.v[b];
         }
@@ -562,74 +572,98 @@ static size_t ncells_padded_of(int H, int W) {
     return align_up(static_cast<size_t>(H + 1) * (W + 1) + 2, 64);
 }
 static int gather_blocks(int H, int W) { return ((W + kOutW - 1) / kOutW) * ((H + kOutH - 1) / kOutH); }
-static size_t index_bytes_per_map(int H, int W) {
-    return ncells_padded_of(H, W) * (sizeof(unsigned) + sizeof(uint4)) + 256 + static_cast<size_t>(H) * W * sizeof(uint2);
+static size_t plan_bytes_of(int H, int W) {
+    const size_t npx = static_cast<size_t>(H) * W;
+    return index_bytes_of(ncells_padded_of(H, W), npx) + stencil_bytes(npx) +
+           align_up(sizeof(int4) * static_cast<size_t>(gather_blocks(H, W)), 256);
 }
 
 int factored_supported(int H, int W, int B) {
     return B >= 1 && B <= 24 && H >= 1 && W >= 1 && H < 65536 && W < 65536 && static_cast<long long>(H + 1) * (W + 1) < (1LL << 30);
 }
 int factored_max_maps(void) { return kMaxDistinctMaps; }
+size_t factored_plan_bytes(int H, int W) { return factored_supported(H, W, 1) ? plan_bytes_of(H, W) : 0; }
 
-// inverse indices of the distinct maps of one window group + the per-block statistics partials
+// plans of the distinct maps of one window group (when the caller brings none) + the per-block statistics partials
 size_t factored_scratch_bytes(int group, int H, int W, int B) {
     (void)B;
     const int maps = group < kMaxDistinctMaps ? group : kMaxDistinctMaps;
-    return align_up(static_cast<size_t>(maps) * index_bytes_per_map(H, W), 256) +
-           align_up(sizeof(int4) * static_cast<size_t>(maps) * gather_blocks(H, W), 256) +
-           static_cast<size_t>(maps) * stencil_bytes(static_cast<size_t>(H) * W) +
+    return static_cast<size_t>(maps) * plan_bytes_of(H, W) +
            align_up(sizeof(PartialStats) * static_cast<size_t>(group) * gather_blocks(H, W), 256);
+}
+
+// Builds the plans of `n` slots (ms.map_of_slot / plan_of_slot / plan_base / plan_stride filled in).
+static int build_plans(const float2* maps2, const MapSlots& ms, int n, int H, int W, cudaStream_t st) {
+    const size_t npx = static_cast<size_t>(H) * W;
+    const size_t nc = ncells_padded_of(H, W);
+    const int nblk = gather_blocks(H, W);
+    for (int k = 0; k < n; ++k)      // the cell counters (and the overflow counter) start at zero
+        CMDA_CUDA_TRY(cudaMemsetAsync(ms.plan_base + static_cast<size_t>(ms.plan_of_slot[k]) * ms.plan_stride + nc * sizeof(uint4), 0,
+                                      nc * sizeof(unsigned) + 256, st));
+    dim3 grid(static_cast<unsigned>((npx + 255) / 256), n);
+    rectify_index_build_kernel<<<grid, 256, 0, st>>>(maps2, ms, H, W, nc);
+    rectify_index_sort_kernel<<<dim3(static_cast<unsigned>(((H + 1) * (W + 1) + 255) / 256), n), 256, 0, st>>>(ms, H, W, nc);
+    stencil_build_kernel<<<grid, 256, 0, st>>>(maps2, ms, H, W, nc);
+    out_tile_box_kernel<<<dim3(nblk, n), kOutThreads, 0, st>>>(ms, H, W, nc);
+    CMDA_LAUNCH_CHECK();
+    return CMDA_OK;
+}
+
+// cmda_rectify_plan_build: one plan per map id, built once by the caller
+int launch_plan_build(const float* maps, int n_maps, int H, int W, void* plans, cudaStream_t st) {
+    if (!factored_supported(H, W, 1)) return CMDA_ERR_UNSUPPORTED;
+    for (int m0 = 0; m0 < n_maps; m0 += kMaxWindows) {
+        const int n = (n_maps - m0) < kMaxWindows ? (n_maps - m0) : kMaxWindows;
+        MapSlots ms{};
+        ms.plan_base = static_cast<char*>(plans);
+        ms.plan_stride = plan_bytes_of(H, W);
+        for (int k = 0; k < n; ++k) { ms.map_of_slot[k] = m0 + k; ms.plan_of_slot[k] = m0 + k; }
+        const int rc = build_plans(reinterpret_cast<const float2*>(maps), ms, n, H, W, st);
+        if (rc != CMDA_OK) return rc;
+    }
+    return CMDA_OK;
 }
 
 int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, const uint8_t* p, const WindowTable& tab, int S,
                     long long max_events, const float* maps, int H, int W, int B, void* R, int64_t* bin_counts,
-                    float* raw, PartialStats* partials, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+                    float* raw, PartialStats* partials, void* scratch, size_t scratch_bytes, const void* plans, cudaStream_t st) {
     if (!factored_supported(H, W, B)) return CMDA_ERR_UNSUPPORTED;
     const size_t npx = static_cast<size_t>(H) * W;
     const size_t nc = ncells_padded_of(H, W);
     const int nblk = gather_blocks(H, W);
-    // distinct maps of this group of windows
+    // distinct maps of this group of windows; their plans come from the caller or are built here
     MapSlots ms{};
     int n_slots = 0;
+    const bool own_plans = maps != nullptr && plans == nullptr;
     if (maps != nullptr) {
         for (int s = 0; s < S; ++s) {
             int found = -1;
             for (int k = 0; k < n_slots; ++k)
                 if (ms.map_of_slot[k] == tab.w[s].map_id) { found = k; break; }
             if (found < 0) {
-                if (n_slots == kMaxDistinctMaps) return CMDA_ERR_BAD_ARG;   // api.cu cuts the groups: cannot happen
+                if (own_plans && n_slots == kMaxDistinctMaps) return CMDA_ERR_BAD_ARG;   // api.cu cuts the groups: cannot happen
                 found = n_slots;
-                ms.map_of_slot[n_slots++] = tab.w[s].map_id;
+                ms.map_of_slot[n_slots] = tab.w[s].map_id;
+                ms.plan_of_slot[n_slots] = own_plans ? n_slots : tab.w[s].map_id;
+                ++n_slots;
             }
             ms.slot[s] = found;
         }
     }
-    const size_t index_bytes = align_up(static_cast<size_t>(n_slots) * index_bytes_per_map(H, W), 256);
-    const size_t sten_bytes = static_cast<size_t>(n_slots) * stencil_bytes(npx);
-    const size_t box_bytes = align_up(sizeof(int4) * static_cast<size_t>(n_slots) * nblk, 256);
-    if (index_bytes + sten_bytes + box_bytes + sizeof(PartialStats) * static_cast<size_t>(S) * nblk > scratch_bytes)
-        return CMDA_ERR_WORKSPACE;
-    char* index_ws = static_cast<char*>(scratch);
-    char* stencil_ws = index_ws + index_bytes;
-    int4* boxes = reinterpret_cast<int4*>(stencil_ws + sten_bytes);
-    PartialStats* block_partials = reinterpret_cast<PartialStats*>(reinterpret_cast<char*>(boxes) + box_bytes);
+    ms.plan_stride = plan_bytes_of(H, W);
+    ms.plan_base = own_plans ? static_cast<char*>(scratch) : const_cast<char*>(static_cast<const char*>(plans));
+    const size_t own_bytes = own_plans ? static_cast<size_t>(n_slots) * ms.plan_stride : 0;
+    if (own_bytes + sizeof(PartialStats) * static_cast<size_t>(S) * nblk > scratch_bytes) return CMDA_ERR_WORKSPACE;
+    PartialStats* block_partials = reinterpret_cast<PartialStats*>(static_cast<char*>(scratch) + own_bytes);
     const float2* maps2 = reinterpret_cast<const float2*>(maps);
 
-    // zero R (int64 cells for B > 1, int32 counts for B == 1) and the cell counters of the indices
+    // zero R (int64 cells for B > 1, int32 counts for B == 1)
     const size_t r_bytes = (B == 1) ? sizeof(int) * S * npx : sizeof(long long) * S * B * npx;
     CMDA_CUDA_TRY(cudaMemsetAsync(R, 0, r_bytes, st));
-    for (int k = 0; k < n_slots; ++k)
-        CMDA_CUDA_TRY(cudaMemsetAsync(index_ws + static_cast<size_t>(k) * index_bytes_per_map(H, W) + nc * sizeof(uint4), 0,
-                                      nc * sizeof(unsigned) + 256, st));
     phase_mark(st);
-    if (n_slots) {
-        dim3 grid(static_cast<unsigned>((npx + 255) / 256), n_slots);
-        rectify_index_build_kernel<<<grid, 256, 0, st>>>(maps2, ms, H, W, index_ws, nc);
-        rectify_index_sort_kernel<<<dim3(static_cast<unsigned>(((H + 1) * (W + 1) + 255) / 256), n_slots), 256, 0, st>>>(
-            ms, H, W, index_ws, nc);
-        stencil_build_kernel<<<grid, 256, 0, st>>>(maps2, ms, H, W, index_ws, nc, stencil_ws);
-        out_tile_box_kernel<<<dim3(nblk, n_slots), kOutThreads, 0, st>>>(ms, H, W, stencil_ws, boxes);
-        CMDA_LAUNCH_CHECK();
+    if (own_plans && n_slots) {
+        const int rc = build_plans(maps2, ms, n_slots, H, W, st);
+        if (rc != CMDA_OK) return rc;
     }
     phase_mark(st);
     if (max_events > 0) {
@@ -654,8 +688,7 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
 #define CMDA_GATHER(BT)                                                                                                  \
     do {                                                                                                                 \
         CMDA_CUDA_TRY(cudaFuncSetAttribute(rectify_gather_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageBytes)); \
-        rectify_gather_kernel<BT><<<grid, kOutThreads, kStageBytes, st>>>(R, tab, ms, maps2, index_ws, nc, stencil_ws, boxes, H, W, \
-                                                                         B, raw, block_partials);                       \
+        rectify_gather_kernel<BT><<<grid, kOutThreads, kStageBytes, st>>>(R, tab, ms, maps2, nc, H, W, B, raw, block_partials);  \
     } while (0)
         switch (B) {
             case 1: CMDA_GATHER(1); break;

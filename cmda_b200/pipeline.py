@@ -37,6 +37,17 @@ class HostEventsPipeline:
         if rectify_map is not None:
             m = torch.as_tensor(np.ascontiguousarray(rectify_map, dtype=np.float32))
             self.rmap = m.to(self.device).reshape(-1, self.H, self.W, 2).contiguous()
+        self.plans = None
+        if self.rmap is not None:        # map-derived gather plans: built once, the map is static
+            L = _lib.lib()
+            nbytes = L.cmda_rectify_plan_bytes(self.H, self.W)
+            if nbytes:
+                self.plans = torch.empty((int(self.rmap.shape[0]) * nbytes,), dtype=torch.uint8, device=self.device)
+                with torch.cuda.device(self.device):
+                    _lib.check(L.cmda_rectify_plan_build(_lib.ptr(self.rmap), int(self.rmap.shape[0]), self.H, self.W,
+                                                         _lib.ptr(self.plans), _lib.stream_ptr(self.device)),
+                               "cmda_rectify_plan_build")
+                torch.cuda.current_stream(self.device).synchronize()
         self.copy_in = torch.cuda.Stream(self.device)
         self.copy_out = torch.cuda.Stream(self.device)
         self.compute = torch.cuda.Stream(self.device)
@@ -115,11 +126,12 @@ class HostEventsPipeline:
                 self.compute.wait_event(slot["ready"])
                 with torch.cuda.stream(self.compute):
                     ev = slot["ev"]
-                    _lib.check(L.cmda_events_vg_batch(
+                    _lib.check(L.cmda_events_vg_batch_planned(
                         _lib.ptr(ev[0]), _lib.ptr(ev[1]), _lib.ptr(ev[2]), _lib.ptr(ev[3]), _lib.host_ptr(hs),
                         _lib.host_ptr(he), len(g), _lib.ptr(self.rmap), None, self.H, self.W, self.B,
                         _lib.host_ptr(clips), 1.0, 1, 1, _lib.ptr(slot["out"]), None, None, _lib.ptr(self._ws),
-                        self._ws.numel(), mode_id, self.compute.cuda_stream), "cmda_events_vg_batch")
+                        self._ws.numel(), mode_id, _lib.ptr(self.plans), self.compute.cuda_stream),
+                        "cmda_events_vg_batch_planned")
                     slot["done"].record(self.compute)
                 self.copy_out.wait_event(slot["done"])
                 with torch.cuda.stream(self.copy_out):

@@ -107,7 +107,7 @@ class EventStore:
     rectify map(s).  Stands in for the reference's ``self.events_h5`` + ``self.rectify_map``
     (dsec.py:287-291); decoding events.h5 itself is file I/O and out of scope."""
 
-    def __init__(self, t, x, y, p, rectify_map=None, height=480, width=640, device=None):
+    def __init__(self, t, x, y, p, rectify_map=None, height=480, width=640, device=None, plan=True):
         self.device = _cuda_device(device)
         def put(a, np_dtype, torch_dtype):
             if isinstance(a, torch.Tensor):
@@ -130,6 +130,19 @@ class EventStore:
                 m = m[None]
             assert m.shape[1:] == (self.height, self.width, 2), "rectify_map is [H, W, 2] (dsec.py:351-353)"
             self.rectify_map = m.contiguous()
+        # the maps are static for a sequence: their gather plans (inverse index, stencil, tile boxes) are
+        # built once here instead of on every voxel call
+        self.plans = None
+        if self.rectify_map is not None and plan:
+            L = _lib.lib()
+            nbytes = L.cmda_rectify_plan_bytes(self.height, self.width)
+            if nbytes:
+                n_maps = int(self.rectify_map.shape[0])
+                self.plans = torch.empty((n_maps * nbytes,), dtype=torch.uint8, device=self.device)
+                with torch.cuda.device(self.device):
+                    _lib.check(L.cmda_rectify_plan_build(_lib.ptr(self.rectify_map), n_maps, self.height, self.width,
+                                                         _lib.ptr(self.plans), _lib.stream_ptr(self.device)),
+                               "cmda_rectify_plan_build")
 
     def __len__(self):
         return int(self.t.shape[0])
@@ -169,11 +182,12 @@ def events_vg_batch(store: EventStore, starts, finishes, num_bins, clip_ranges=N
     total = int(np.clip(ends - starts, 0, None).sum())
     with torch.cuda.device(dev):
         ws = _lib.workspace(dev, L.cmda_events_vg_workspace_bytes(total, S, H, W, B, mode_id))
-        _lib.check(L.cmda_events_vg_batch(
+        _lib.check(L.cmda_events_vg_batch_planned(
             _lib.ptr(store.t), _lib.ptr(store.x), _lib.ptr(store.y), _lib.ptr(store.p), _lib.host_ptr(starts),
             _lib.host_ptr(ends), S, _lib.ptr(store.rectify_map), _lib.host_ptr(mids), H, W, B, _lib.host_ptr(clips),
             float(final_range), int(bool(enforce_no_events_zero)), int(bool(normalize)), _lib.ptr(out), _lib.ptr(raw),
-            _lib.ptr(counts), _lib.ptr(ws), ws.numel(), mode_id, _lib.stream_ptr(dev)), "cmda_events_vg_batch")
+            _lib.ptr(counts), _lib.ptr(ws), ws.numel(), mode_id, _lib.ptr(store.plans), _lib.stream_ptr(dev)),
+            "cmda_events_vg_batch_planned")
     res = [out]
     if return_raw:
         res.append(raw if normalize else out)
@@ -225,8 +239,8 @@ def events_vg_augmented_batch(store: EventStore, starts, finishes, num_bins, cli
             _lib.ptr(store.t), _lib.ptr(store.x), _lib.ptr(store.y), _lib.ptr(store.p), _lib.host_ptr(starts),
             _lib.host_ptr(ends), S, _lib.ptr(store.rectify_map), _lib.host_ptr(mids), H, W, B, _lib.host_ptr(clips),
             float(final_range), int(bool(enforce_no_events_zero)), _lib.host_ptr(aug), cw, ch, ow, oh, int(bool(avg_bins)),
-            int(repeat), _lib.ptr(out), None, None, _lib.ptr(ws), ws.numel(), mode_id, _lib.stream_ptr(dev)),
-            "cmda_events_vg_augmented_batch")
+            int(repeat), _lib.ptr(out), None, None, _lib.ptr(ws), ws.numel(), mode_id, _lib.ptr(store.plans),
+            _lib.stream_ptr(dev)), "cmda_events_vg_augmented_batch")
     return out
 
 

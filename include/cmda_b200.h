@@ -132,6 +132,22 @@ int cmda_events_vg_batch(const uint32_t* d_t, const uint16_t* d_x, const uint16_
                          float* d_out, float* d_raw_out, int64_t* d_bin_counts,
                          void* d_workspace, size_t workspace_bytes, int mode, void* stream);
 
+/* Rectify-map plans.  Everything the FACTORED mode derives from a rectify map alone -- the inverse index
+ * of the map, the sparse gather stencil, the source box of every output tile -- is a "plan" of
+ * cmda_rectify_plan_bytes(H, W) bytes per map.  cmda_events_vg_batch builds the plans of a call's maps
+ * into its workspace on every call (the reference, too, re-reads the map for every sample:
+ * dsec.py:289-291); a caller that keeps a sequence resident builds them once and passes them to the
+ * *_planned entry point: d_plans is [n_maps] plans, 256-byte aligned, plan m belongs to map id m.
+ * Plans are only read by the voxel calls; NULL means "build per call". */
+size_t cmda_rectify_plan_bytes(int H, int W);
+int cmda_rectify_plan_build(const float* d_rectify_map, int n_maps, int H, int W, void* d_plans, void* stream);
+int cmda_events_vg_batch_planned(const uint32_t* d_t, const uint16_t* d_x, const uint16_t* d_y, const uint8_t* d_p,
+                                 const int64_t* h_win_start, const int64_t* h_win_end, int S,
+                                 const float* d_rectify_map, const int32_t* h_map_id, int H, int W, int B,
+                                 const float* h_clip, float final_range, int enforce_no_events_zero, int normalize,
+                                 float* d_out, float* d_raw_out, int64_t* d_bin_counts, void* d_workspace,
+                                 size_t workspace_bytes, int mode, const void* d_plans, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * K2+K3 with the post-voxel augmentation of the dataset fused into the normaliser's apply phase
  * (SURVEY.md 8 f-1).
@@ -160,7 +176,8 @@ int cmda_events_vg_augmented_batch(const uint32_t* d_t, const uint16_t* d_x, con
                                    const float* h_clip, float final_range, int enforce_no_events_zero,
                                    const cmda_vg_augment* h_aug, int crop_w, int crop_h, int out_w, int out_h,
                                    int avg_bins, int repeat, float* d_out, float* d_raw_out, int64_t* d_bin_counts,
-                                   void* d_workspace, size_t workspace_bytes, int mode, void* stream);
+                                   void* d_workspace, size_t workspace_bytes, int mode, const void* d_plans /* or NULL */,
+                                   void* stream);
 
 /* Replaces: events_to_voxel_grid(time, x, y, pol, width, height, num_bins),
  * /root/reference/mmseg/datasets/dsec.py:26-58 (normalize_flag=False), on float32 SoA

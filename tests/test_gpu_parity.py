@@ -382,6 +382,23 @@ def test_events_vg_large_window_b1(cm):
     assert np.isfinite(out.cpu().numpy()).all() and out.shape == (1, 1, H, W) and ref.shape == (1, 1, H, W)
 
 
+def test_events_vg_prebuilt_plans_identical(cm):
+    """cmda_rectify_plan_build once per sequence vs. plans rebuilt inside every call: bit-identical grids,
+    with several maps and map ids in arbitrary order."""
+    from cmda_b200 import synth
+    H, W, n = 480, 640, 200_000
+    t, x, y, p = synth.make_events(n, H, W, seed=synth.seed_for(1, 5))
+    rmaps = np.stack([synth.make_rectify_map(H, W, seed=k, k1=k1) for k, k1 in ((1, -0.08), (2, 0.02), (3, -0.01))])
+    a = cm.EventStore(t, x, y, p, rmaps, height=H, width=W, device="cuda:0", plan=True)
+    b = cm.EventStore(t, x, y, p, rmaps, height=H, width=W, device="cuda:0", plan=False)
+    assert a.plans is not None and b.plans is None
+    starts, fins, mids = [0, 10, 5000, 777], [n - 1, 90_000, 60_000, 150_000], [2, 0, 2, 1]
+    for bins in (1, 5):
+        ga = cm.events_vg_batch(a, starts, fins, bins, map_ids=mids, mode="factored")
+        gb = cm.events_vg_batch(b, starts, fins, bins, map_ids=mids, mode="factored")
+        assert np.array_equal(bits(ga), bits(gb))
+
+
 def test_events_vg_bad_windows(cm):
     from cmda_b200 import synth
     t, x, y, p = synth.make_events(1000, 48, 64, seed=1)
