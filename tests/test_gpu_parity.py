@@ -399,6 +399,61 @@ def test_events_vg_prebuilt_plans_identical(cm):
         assert np.array_equal(bits(ga), bits(gb))
 
 
+@pytest.mark.parametrize("bins", [5, 1])
+def test_events_vg_full_size_properties(cm, bins):
+    """BASELINE config C2 at full size (16 windows x 5 M events, 640 x 480) through size-independent
+    properties -- the oracle takes minutes at this size:
+      * per-bin counts are exact: every in-sensor event is counted once, in the bin of its t0;
+      * mass conservation: an event whose corners all lie inside the grid spreads exactly its polarity
+        (the tent weights of each axis sum to 1), so sum(raw) = sum of polarities over interior events up to
+        float32 rounding and the border events' partial mass (bounded separately);
+      * polarity flip negates the raw grid exactly (an exact integer sum of negated terms);
+      * splitting a window's events in two sets (same time base) adds up: grid(A) + grid(B) = grid(A u B);
+      * bit-reproducible run to run; normalised output inside [-1, 1] with zeros preserved."""
+    import bench
+    S, n = 16, 5_000_000
+    t, x, y, p, rmap, starts, fins = bench.make_workload(S, n, seed_base=0)
+    H, W = bench.H, bench.W
+    store = cm.EventStore(t, x, y, p, rmap, height=H, width=W, device="cuda:0")
+    out, raw, counts = cm.events_vg_batch(store, starts, fins, bins, return_raw=True, return_bin_counts=True)
+    again = cm.events_vg_batch(store, starts, fins, bins, normalize=False)
+    assert np.array_equal(bits(raw), bits(again)), "bit-reproducible at full size"
+    assert int(counts.sum()) == S * n and torch.all(counts.sum(dim=1) == n)      # synthetic x, y are always in-sensor
+    # bins: t0 = int((B-1) * dt / dT): host recomputation of the exact integer histogram for window 0
+    sl = slice(int(starts[0]), int(fins[0]) + 1)
+    tn = O.t_norm_of(((t[sl] - t[sl][0]).astype(np.float32) / np.float32(t[sl][-1] - t[sl][0])).astype(np.float32), bins)
+    assert np.array_equal(np.bincount(np.trunc(tn).astype(np.int64), minlength=bins), counts[0].cpu().numpy())
+    # mass conservation (window 0)
+    m = rmap[y[sl], x[sl]]
+    x0, y0 = np.trunc(m[:, 0]).astype(np.int64), np.trunc(m[:, 1]).astype(np.int64)
+    t0 = np.trunc(tn).astype(np.int64)
+    interior = (m[:, 0] >= 0) & (x0 + 1 < W) & (m[:, 1] >= 0) & (y0 + 1 < H) & ((t0 + 1 < bins) | (bins == 1))
+    sign = 2.0 * p[sl].astype(np.float64) - 1.0
+    total = float(raw[0].double().sum())
+    slack = float((~interior).sum()) + 1e-3 * n ** 0.5 + 1.0      # border events carry at most |1| each
+    assert abs(total - float(sign[interior].sum())) <= slack
+    # polarity flip
+    flipped = cm.EventStore(t, x, y, 1 - p, rmap, height=H, width=W, device="cuda:0")
+    neg = cm.events_vg_batch(flipped, starts[:4], fins[:4], bins, normalize=False)
+    assert torch.equal(neg, -raw[:4])
+    del flipped
+    # additivity: even / odd events of window 1 as two windows sharing the first and last event (same t_norm map)
+    a, b = int(starts[1]), int(fins[1])
+    idx = np.arange(a, b + 1)
+    keep_a = np.concatenate([[a], idx[1:-1][::2], [b]])
+    keep_b = np.concatenate([[a], idx[1:-1][1::2], [b]])
+    def grid_of(sel):
+        st = cm.EventStore(t[sel], x[sel], y[sel], p[sel], rmap, height=H, width=W, device="cuda:0", plan=False)
+        return cm.events_vg_batch(st, [0], [len(sel) - 1], bins, normalize=False, mode="factored")[0].double()
+    ends_only = grid_of(np.array([a, b]))                       # the two shared events are counted twice
+    diff = (grid_of(keep_a) + grid_of(keep_b) - ends_only - raw[1].double()).abs().max()
+    assert float(diff) <= 4e-6 * float(raw[1].abs().max())       # three float32 roundings of exact integer sums
+    # normalised output
+    o = out.cpu().numpy()
+    assert np.isfinite(o).all() and o.min() >= -1.0 and o.max() <= 1.0
+    assert np.all(o[raw.cpu().numpy() == 0] == 0)
+
+
 def test_events_vg_bad_windows(cm):
     from cmda_b200 import synth
     t, x, y, p = synth.make_events(1000, 48, 64, seed=1)
