@@ -17,7 +17,7 @@ import random
 import torch
 import torch.nn.functional as F
 
-from .slicer import window_bounds
+from .slicer import images_to_events_index, window_bounds
 from .voxel import EventStore, events_vg_augmented_batch, events_vg_batch
 
 __all__ = ["DSECEvents"]
@@ -53,6 +53,18 @@ class DSECEvents:
                                                # no normalised full grid); False keeps them as torch ops on the grid
         self.store = EventStore(t, x, y, p, rectify_map if self.rectify_events else None,
                                 height=self.events_height, width=self.events_width, device=device)
+
+    @classmethod
+    def from_timestamps(cls, t, x, y, p, rectify_map, ms_to_idx, t_offset, images_timestamps, **kwargs):
+        """Build the object from what a DSEC sequence holds on disk (events.h5: ``events/{t,x,y,p}``,
+        ``ms_to_idx``, ``t_offset``; images/timestamps.txt) instead of from a precomputed
+        ``images_to_events_index.txt``: the per-image event index of create_dsec_dataset_txt.py:10-47 is computed
+        on the device from the resident ``t`` array (K1), once, instead of being read back with ``np.loadtxt`` for
+        every sample (dsec.py:292-293).  Same exceptions as the reference script (``ValueError('range error!')``)."""
+        obj = cls(t, x, y, p, rectify_map, [], **kwargs)
+        obj.images_to_events_index = images_to_events_index(obj.store.t, t_offset, ms_to_idx, images_timestamps,
+                                                            device=obj.store.device)
+        return obj
 
     # ---- dsec.py:341-366 -------------------------------------------------------------
     def _clip_for(self, finish, start):

@@ -574,6 +574,30 @@ def test_images_to_events_index_golden(cm):
     assert got == [int(v) for v in c["result"]]
 
 
+def test_dsec_events_from_timestamps(cm):
+    """f-3 (first step): the event index of create_dsec_dataset_txt.py:10-47 computed from the resident t array
+    at construction, then the events branch of __getitem__ for an image: same windows as the index table."""
+    c = INDEX["index_table"]
+    n = c["t"].shape[0]
+    rng = np.random.default_rng(4)
+    x = rng.integers(0, 640, n).astype(np.uint16)
+    y = rng.integers(0, 480, n).astype(np.uint16)
+    p = rng.integers(0, 2, n).astype(np.uint8)
+    from cmda_b200 import synth
+    rmap = synth.make_rectify_map(480, 640, seed=2)
+    ds = cm.DSECEvents.from_timestamps(c["t"], x, y, p, rmap, c["ms_to_idx"], int(c["t_offset"]), c["timestamps"],
+                                       events_bins=1, outputs={'events_vg', 'label'}, device="cuda:0")
+    assert ds.images_to_events_index == [int(v) for v in c["result"]]
+    valid = [i for i in range(1, len(ds.images_to_events_index))
+             if ds.images_to_events_index[i - 1] >= 0 and ds.images_to_events_index[i] > ds.images_to_events_index[i - 1]]
+    i = valid[len(valid) // 2]
+    item = ds.events_vg_for_image(i)
+    start, finish = ds.images_to_events_index[i - 1], ds.images_to_events_index[i]
+    ref = O.get_events_vg(c["t"], x, y, p, rmap, 640, 480, 1, finish, start)
+    assert item.shape == (3, 440, 640)
+    np.testing.assert_allclose(item[0].cpu().numpy(), ref[0, :440], rtol=0, atol=1e-5)
+
+
 def test_images_to_events_index_range_error(cm):
     c = INDEX["index_table"]
     bad = c["ms_to_idx"].copy()
