@@ -88,19 +88,14 @@ struct NormParams {
     float mean, den; // dsec.py:91-93
     float clip, final_range;
     float pmin, pden, nmin, nden;
+    float rden, rpden, rnden;     // correctly rounded reciprocals of den / pden / nden (div_by_reused)
     float p_of_zero, n_of_zero;   // the normalised positive / negative part of a voxel whose part is 0
 };
-
-// x / den.  A zero numerator (every empty voxel) would send the IEEE division into its slow path; for a
-// positive finite den, +-0 / den is +-0, i.e. the numerator itself.
-__device__ __forceinline__ float div_fast_zero(float num, float den) {
-    return (num == 0.0f && den > 0.0f && den < INFINITY) ? num : __fdiv_rn(num, den);
-}
 
 __device__ __forceinline__ float zscore(float e, const NormParams& q) {
     if (!q.has_nz) return e;
     const float m = (e != 0.0f) ? 1.0f : 0.0f;                          // dsec.py:93 mask
-    return div_fast_zero(__fmul_rn(m, __fsub_rn(e, q.mean)), q.den);    // dsec.py:94
+    return div_by_reused(__fmul_rn(m, __fsub_rn(e, q.mean)), q.den, q.rden);   // dsec.py:94
 }
 __device__ __forceinline__ float pos_part(float z, float clip) {
     const float p = z < 0.0f ? 0.0f : z;                                // dsec.py:108
@@ -127,12 +122,14 @@ __device__ NormParams make_norm_params(const PartialStats* __restrict__ partials
     q.has_nz = nnz > 0;
     q.mean = 0.0f;
     q.den = 1.0f;
+    q.rden = 1.0f;
     if (q.has_nz) {
         const float fn = __ll2float_rn(nnz);
         q.mean = __fdiv_rn(__double2float_rn(sum), fn);                                  // dsec.py:91
         const float var = __fsub_rn(__fdiv_rn(__double2float_rn(sumsq), fn), __fmul_rn(q.mean, q.mean));
         const float sd = __fsqrt_rn(var);                                                // dsec.py:92
         q.den = __fadd_rn(sd, 1e-8f);
+        q.rden = __frcp_rn(q.den);
         q.all_nan = isnan(sd);
     }
     // min / max of the clamped parts over the whole grid: values come from the non-zero
@@ -153,6 +150,8 @@ __device__ NormParams make_norm_params(const PartialStats* __restrict__ partials
     q.pden = __fadd_rn(__fsub_rn(pmax, pmin), 1e-8f);                                    // dsec.py:76
     q.nmin = nmin;
     q.nden = __fadd_rn(__fsub_rn(nmax, nmin), 1e-8f);
+    q.rpden = __frcp_rn(q.pden);
+    q.rnden = __frcp_rn(q.nden);
     // a voxel with z >= 0 has negative part 0 and vice versa: that half of dsec.py:111 / 115 is
     // the same value for every such voxel
     q.p_of_zero = __fadd_rn(__fmul_rn(__fdiv_rn(__fsub_rn(0.0f, q.pmin), q.pden), final_range), 0.0f);
@@ -168,7 +167,7 @@ __device__ __forceinline__ float norm_one(float e, const NormParams& q, bool enf
         // per-grid constant computed in make_norm_params (same operations, same bits)
         const bool neg = z < 0.0f;
         const float part = neg ? neg_part(z, q.clip) : pos_part(z, q.clip);
-        float v = div_fast_zero(__fsub_rn(part, neg ? q.nmin : q.pmin), neg ? q.nden : q.pden);
+        float v = div_by_reused(__fsub_rn(part, neg ? q.nmin : q.pmin), neg ? q.nden : q.pden, neg ? q.rnden : q.rpden);
         v = __fadd_rn(__fmul_rn(v, q.final_range), neg ? -q.final_range : 0.0f);         // * (r - 0) + 0 | * (0 - (-r)) + (-r)
         return neg ? __fadd_rn(q.p_of_zero, v) : __fadd_rn(v, q.n_of_zero);
     }

@@ -86,23 +86,19 @@ struct MinMaxAcc {
 
 struct TermRange {
     float pmin, pden, nmin, nden;
+    float rpden, rnden;           // correctly rounded reciprocals of the two denominators
     float p_of_zero, n_of_zero;   // normalised part of a pixel whose part is 0 (the side of zero it is not on)
 };
 
 // tensor_normalize_to_range of one part (utils.py:10-14): positive part -> [0, 1], negative part -> [-1, 0]
-// x / den for a positive finite den.  A zero numerator (every pixel of the dead zone) would send the
-// IEEE division into its slow path (FCHK flags it); +-0 / den is +-0, so the quotient is the numerator.
-__device__ __forceinline__ float div_pos_den(float num, float den) {
-    return (num == 0.0f && den > 0.0f) ? num : __fdiv_rn(num, den);
-}
-
+// tensor_normalize_to_range of one part (utils.py:10-14): positive part -> [0, 1], negative part -> [-1, 0].
+// "* (1 - 0) + 0" is the identity on the non-negative quotient and is not spelled out; the divisions by the
+// per-image denominators are div_by_reused (correctly rounded, common.cuh).
 __device__ __forceinline__ float normalize_pos(float pos, const TermRange& r) {
-    const float p = div_pos_den(__fsub_rn(pos, r.pmin), r.pden);
-    return __fadd_rn(__fmul_rn(p, 1.0f), 0.0f);             // * (1 - 0) + 0
+    return div_by_reused(__fsub_rn(pos, r.pmin), r.pden, r.rpden);
 }
 __device__ __forceinline__ float normalize_neg(float neg, const TermRange& r) {
-    const float n = div_pos_den(__fsub_rn(neg, r.nmin), r.nden);
-    return __fadd_rn(__fmul_rn(n, 1.0f), -1.0f);            // * (0 - (-1)) + (-1)
+    return __fadd_rn(div_by_reused(__fsub_rn(neg, r.nmin), r.nden, r.rnden), -1.0f);      // * (0 - (-1)) + (-1)
 }
 
 __device__ __forceinline__ TermRange decode_range(const unsigned* __restrict__ slots, float thr, float clip) {
@@ -116,6 +112,8 @@ __device__ __forceinline__ TermRange decode_range(const unsigned* __restrict__ s
     r.pden = __fadd_rn(__fsub_rn(pmax, pmin), 1e-8f);   // tensor_max - tensor_min + 1e-8
     r.nmin = nmin;
     r.nden = __fadd_rn(__fsub_rn(nmax, nmin), 1e-8f);
+    r.rpden = __frcp_rn(r.pden);
+    r.rnden = __frcp_rn(r.nden);
     r.p_of_zero = normalize_pos(0.0f, r);
     r.n_of_zero = normalize_neg(0.0f, r);
     return r;
