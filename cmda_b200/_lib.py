@@ -63,6 +63,9 @@ SIGNATURES = {
     "cmda_logdiff_pair_u8": (_int, [_vp, _vp, _int, _int, _int, _vp, _f32, _f32, _vp, _vp, _vp, _sz, _vp]),
     "cmda_isr_shift_u8": (_int, [_vp, _int, _int, _int, _int, _int, _int, _vp, _f32, _f32, _vp, _vp, _sz, _vp]),
     "cmda_rgb_to_gray_u8": (_int, [_vp, _i64, _vp, _vp]),
+    "cmda_resize_bilinear_workspace_bytes": (_sz, [_int, _int, _int, _int, _int, _int]),
+    "cmda_resize_bilinear_u8": (_int, [_vp, _int, _int, _int, _int, _int, _int, _vp, _vp, _sz, _vp]),
+    "cmda_u8_crop_to_centered_f32": (_int, [_vp, _int, _int, _int, _vp, _int, _int, _int, _vp, _vp]),
     "cmda_denorm_rgb_to_gray_u8": (_int, [_vp, _int, _int, _int, _vp, _vp, _vp, _vp, _vp]),
 }
 

@@ -20,6 +20,9 @@ int launch_norm_apply(const float*, float*, int, long long, const PartialStats*,
                       cudaStream_t);
 int launch_norm_augment(const float*, float*, int, int, int, int, const PartialStats*, const WindowTable&, const int*,
                         const int*, const int*, int, int, int, int, int, int, float, int, cudaStream_t);
+size_t resize_workspace_bytes(int, int, int, int, int, int);
+int launch_resize_bilinear(const uint8_t*, int, int, int, int, int, int, uint8_t*, void*, size_t, cudaStream_t);
+int launch_u8_crop_center(const uint8_t*, int, int, int, const int*, const int*, const int*, int, int, int, float*, cudaStream_t);
 int launch_rgb_to_gray(const uint8_t*, int64_t, uint8_t*, cudaStream_t);
 int launch_denorm_to_gray(const float*, int, int, int, const float*, const float*, uint8_t*, uint8_t*, cudaStream_t);
 int launch_isr(const uint8_t*, int, int, int, int, int, const float*, float, float, float*, unsigned*, cudaStream_t);
@@ -464,6 +467,42 @@ int cmda_denorm_rgb_to_gray_u8(const float* d_img, int S, int H, int W, const fl
     if (S == 0) return CMDA_OK;
     if (!d_img || !h_mean || !h_std || !d_gray) return CMDA_ERR_BAD_ARG;
     return launch_denorm_to_gray(d_img, S, H, W, h_mean, h_std, d_gray, d_rgb, static_cast<cudaStream_t>(stream));
+}
+
+size_t cmda_resize_bilinear_workspace_bytes(int S, int H, int W, int channels, int out_h, int out_w) {
+    if (S <= 0 || H <= 0 || W <= 0 || out_h <= 0 || out_w <= 0 || (channels != 1 && channels != 3)) return 0;
+    return resize_workspace_bytes(S, H, W, channels, out_h, out_w);
+}
+
+int cmda_resize_bilinear_u8(const uint8_t* d_src, int channels, int S, int H, int W, int out_h, int out_w, uint8_t* d_dst,
+                            void* d_workspace, size_t workspace_bytes, void* stream) {
+    if (S < 0 || H <= 0 || W <= 0 || out_h <= 0 || out_w <= 0 || (channels != 1 && channels != 3)) return CMDA_ERR_BAD_ARG;
+    if (S == 0) return CMDA_OK;
+    if (!d_src || !d_dst || !d_workspace) return CMDA_ERR_BAD_ARG;
+    if (reinterpret_cast<uintptr_t>(d_workspace) & 255) return CMDA_ERR_WORKSPACE;
+    return launch_resize_bilinear(d_src, channels, S, H, W, out_h, out_w, d_dst, d_workspace, workspace_bytes,
+                                  static_cast<cudaStream_t>(stream));
+}
+
+int cmda_u8_crop_to_centered_f32(const uint8_t* d_src, int S, int H, int W, const cmda_vg_augment* h_aug, int crop_w, int crop_h,
+                                 int repeat, float* d_out, void* stream) {
+    if (S < 0 || H <= 0 || W <= 0 || crop_w <= 0 || crop_h <= 0 || repeat <= 0) return CMDA_ERR_BAD_ARG;
+    if (S == 0) return CMDA_OK;
+    if (!d_src || !h_aug || !d_out) return CMDA_ERR_BAD_ARG;
+    int cx[kMaxWindows], cy[kMaxWindows], fl[kMaxWindows];
+    for (int s0 = 0; s0 < S; s0 += kMaxWindows) {
+        const int sn = (S - s0) < kMaxWindows ? (S - s0) : kMaxWindows;
+        for (int k = 0; k < sn; ++k) {
+            const cmda_vg_augment& a = h_aug[s0 + k];
+            if (a.crop_x < 0 || a.crop_y < 0 || a.crop_x + crop_w > W || a.crop_y + crop_h > H) return CMDA_ERR_BAD_ARG;
+            cx[k] = a.crop_x; cy[k] = a.crop_y; fl[k] = a.flip;
+        }
+        const int rc = launch_u8_crop_center(d_src + static_cast<size_t>(s0) * H * W, sn, H, W, cx, cy, fl, crop_w, crop_h, repeat,
+                                             d_out + static_cast<size_t>(s0) * repeat * crop_w * crop_h,
+                                             static_cast<cudaStream_t>(stream));
+        if (rc != CMDA_OK) return rc;
+    }
+    return CMDA_OK;
 }
 
 int cmda_rgb_to_gray_u8(const uint8_t* d_rgb, int64_t n_pixels, uint8_t* d_gray, void* stream) {

@@ -149,6 +149,60 @@ def mixed_image_isr(mixed_img, means, stds, shift_direction='rightdown', shift_p
     return isr.expand(-1, 3, -1, -1).contiguous()
 
 
+def pil_resize_bilinear(images, size, *, out_device=None) -> torch.Tensor:
+    """``PIL.Image.resize(size, Image.BILINEAR)`` of uint8 ``[S, H, W]`` ('L') or ``[S, H, W, 3]`` ('RGB') images,
+    bit for bit, on the device (reference cityscapes_ic.py:152-153, 175-176).  ``size`` is ``(width, height)`` as in
+    PIL.  Returns uint8 ``[S, h, w(, 3)]``."""
+    home = _home(images)
+    dev = _cuda_device(home if home.type == "cuda" else None)
+    src = _to_u8_cuda(images, dev)
+    channels = 3 if (src.ndim == 4 and src.shape[-1] == 3) else 1
+    assert src.ndim == 3 + (channels == 3)
+    S, H, W = int(src.shape[0]), int(src.shape[1]), int(src.shape[2])
+    ow, oh = int(size[0]), int(size[1])
+    out = torch.empty((S, oh, ow, 3) if channels == 3 else (S, oh, ow), dtype=torch.uint8, device=dev)
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        ws = _lib.workspace(dev, L.cmda_resize_bilinear_workspace_bytes(S, H, W, channels, oh, ow))
+        _lib.check(L.cmda_resize_bilinear_u8(_lib.ptr(src), channels, S, H, W, oh, ow, _lib.ptr(out), _lib.ptr(ws), ws.numel(),
+                                             _lib.stream_ptr(dev)), "cmda_resize_bilinear_u8")
+    return out.to(out_device if out_device is not None else home)
+
+
+def u8_crop_to_centered(gray, crop_xy, crop_size, flips=None, repeat=3, *, out_device=None) -> torch.Tensor:
+    """``crop -> HorizontalFlip -> float32 -> (v / 255.0 - 0.5) / 0.5 -> repeat(repeat, 1, 1)`` of uint8 gray images
+    ``[S, H, W]`` (reference cityscapes_ic.py:177-183, 207-209).  ``crop_size`` is ``(w, h)``; returns float32
+    ``[S, repeat, h, w]``."""
+    home = _home(gray)
+    dev = _cuda_device(home if home.type == "cuda" else None)
+    src = _to_u8_cuda(gray, dev)
+    assert src.ndim == 3
+    S, H, W = (int(v) for v in src.shape)
+    cw, ch = int(crop_size[0]), int(crop_size[1])
+    aug = np.zeros((S, 3), dtype=np.int32)
+    xy = np.asarray(crop_xy, dtype=np.int64).reshape(-1, 2)
+    aug[:, 0:2] = xy if xy.shape[0] == S else np.broadcast_to(xy, (S, 2))
+    if flips is not None:
+        aug[:, 2] = np.asarray(flips, dtype=np.int32).reshape(-1)
+    if S and (aug[:, 0].min() < 0 or aug[:, 1].min() < 0 or (aug[:, 0] + cw).max() > W or (aug[:, 1] + ch).max() > H):
+        raise IndexError("crop outside the image")
+    out = torch.empty((S, int(repeat), ch, cw), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().cmda_u8_crop_to_centered_f32(_lib.ptr(src), S, H, W, _lib.host_ptr(aug), cw, ch, int(repeat),
+                                                           _lib.ptr(out), _lib.stream_ptr(dev)), "cmda_u8_crop_to_centered_f32")
+    return out.to(out_device if out_device is not None else home)
+
+
+def source_img_time_res(now, front, resize_size=(1024, 512), crop_xy=(0, 0), crop_size=(512, 512), flips=None, repeat=3):
+    """The Cityscapes source branch's ``img_time_res`` straight from a frame pair, on the device: the offline
+    ``get_image_change`` PNG (create_cityscapes_image_change.py:16-35) -> ``resize(BILINEAR)`` -> crop -> flip ->
+    ``(x / 255 - 0.5) / 0.5`` -> ``repeat(3, 1, 1)`` (cityscapes_ic.py:175-183, 207-209).  ``now`` / ``front``:
+    uint8 gray ``[S, H, W]``."""
+    u8 = image_change_batch(now, front, want_f32=False, want_u8=True, out_device=_cuda_device(None))
+    small = pil_resize_bilinear(u8, resize_size)
+    return u8_crop_to_centered(small, crop_xy, crop_size, flips, repeat)
+
+
 def get_ic(image_front, image_now, val_range, threshold, clip_range, *, out_device=None):
     """Drop-in for ``get_ic`` (reference utils.py:87-105) on two uint8 gray images ->
     ``[1, H, W]`` float32.  Same arithmetic as K4 with the val_range table."""

@@ -239,6 +239,21 @@ int cmda_isr_shift_u8(const uint8_t* d_img, int channels, int S, int H, int W, i
 int cmda_denorm_rgb_to_gray_u8(const float* d_img, int S, int H, int W, const float* h_mean, const float* h_std,
                                uint8_t* d_gray, uint8_t* d_rgb, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Cityscapes source branch of the loader on the device.
+ * cmda_resize_bilinear_u8 replaces PIL's Image.resize(size, Image.BILINEAR) on 8-bit 'L' (channels = 1) or
+ * 'RGB' (channels = 3, interleaved) images, bit for bit
+ * (/root/reference/mmseg/datasets/cityscapes_ic.py:152-153, 175-176: raw_image / image-change PNG -> 1024 x 512).
+ *  d_src [S, H, W, channels] uint8 -> d_dst [S, out_h, out_w, channels] uint8.
+ * cmda_u8_crop_to_centered_f32 replaces cityscapes_ic.py:177-183, 207-209 on a gray image:
+ *   crop(box=(x, y, x + crop_w, y + crop_h)) -> HorizontalFlip -> float32 -> (v / 255.0 - 0.5) / 0.5 -> repeat(3, 1, 1)
+ *  d_src [S, H, W] uint8, h_aug [S] crop origin + flip, d_out [S, repeat, crop_h, crop_w] float32. */
+size_t cmda_resize_bilinear_workspace_bytes(int S, int H, int W, int channels, int out_h, int out_w);
+int cmda_resize_bilinear_u8(const uint8_t* d_src, int channels, int S, int H, int W, int out_h, int out_w, uint8_t* d_dst,
+                            void* d_workspace, size_t workspace_bytes, void* stream);
+int cmda_u8_crop_to_centered_f32(const uint8_t* d_src, int S, int H, int W, const cmda_vg_augment* h_aug, int crop_w,
+                                 int crop_h, int repeat, float* d_out, void* stream);
+
 /* PIL 'L' conversion alone (parity of the integer stage). d_rgb [n,3] -> d_gray [n]. */
 int cmda_rgb_to_gray_u8(const uint8_t* d_rgb, int64_t n_pixels, uint8_t* d_gray, void* stream);
 

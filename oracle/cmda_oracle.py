@@ -317,6 +317,71 @@ def mixed_image_to_gray(img, means, stds, return_rgb=False):
     return (gray, rgb) if return_rgb else gray
 
 
+def _pil_bilinear_coeffs(in_size: int, out_size: int):
+    """Pillow ``precompute_coeffs`` + ``normalize_coeffs_8bpc`` (src/libImaging/Resample.c, Pillow 7+; the
+    library is absent from /root/reference, its algorithm is restated here and pinned against the installed
+    Pillow by tests/test_oracle_golden.py): bounds ``(xmin, count)`` and 22-bit fixed-point taps per output index."""
+    scale = in_size / out_size
+    filterscale = max(scale, 1.0)
+    support = 1.0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    bounds = np.zeros((out_size, 2), np.int64)
+    kk = np.zeros((out_size, ksize), np.int64)
+    ss = 1.0 / filterscale
+    for xx in range(out_size):
+        center = 0.0 + (xx + 0.5) * scale
+        xmin = max(int(center - support + 0.5), 0)
+        xmax = min(int(center + support + 0.5), in_size) - xmin
+        w = [max(1.0 - abs((x + xmin - center + 0.5) * ss), 0.0) for x in range(xmax)]
+        ww = 0.0
+        for v in w:
+            ww += v
+        for x in range(xmax):
+            v = w[x] / ww if ww != 0.0 else w[x]
+            kk[xx, x] = int(-0.5 + v * (1 << 22)) if v < 0 else int(0.5 + v * (1 << 22))
+        bounds[xx] = (xmin, xmax)
+    return bounds, kk
+
+
+def pil_resize_bilinear(img: np.ndarray, size) -> np.ndarray:
+    """``Image.resize(size, Image.BILINEAR)`` of a uint8 ``[H, W]`` or ``[H, W, 3]`` image (cityscapes_ic.py:153, 176):
+    horizontal pass, then vertical pass on the 8-bit intermediate, int32 accumulation from 2^21, clip to 0..255."""
+    img = np.asarray(img, dtype=np.uint8)
+    ow, oh = int(size[0]), int(size[1])
+    a = img.astype(np.int64)
+    if ow != a.shape[1]:
+        b, kk = _pil_bilinear_coeffs(a.shape[1], ow)
+        out = np.empty((a.shape[0], ow) + a.shape[2:], np.int64)
+        for xx in range(ow):
+            acc = np.full((a.shape[0],) + a.shape[2:], 1 << 21, np.int64)
+            for x in range(int(b[xx, 1])):
+                acc += a[:, b[xx, 0] + x] * kk[xx, x]
+            out[:, xx] = np.clip(acc >> 22, 0, 255)
+        a = out
+    if oh != a.shape[0]:
+        b, kk = _pil_bilinear_coeffs(a.shape[0], oh)
+        out = np.empty((oh,) + a.shape[1:], np.int64)
+        for yy in range(oh):
+            acc = np.full(a.shape[1:], 1 << 21, np.int64)
+            for y in range(int(b[yy, 1])):
+                acc += a[b[yy, 0] + y] * kk[yy, y]
+            out[yy] = np.clip(acc >> 22, 0, 255)
+        a = out
+    return a.astype(np.uint8)
+
+
+def u8_crop_to_centered(gray, crop_xy, crop_size, flip_flag=False, repeat=3):
+    """cityscapes_ic.py:177-183, 207-209: crop -> HorizontalFlip -> float32 -> ``(x / 255.0 - 0.5) / 0.5`` ->
+    ``repeat(3, 1, 1)`` with the reference's torch float32 arithmetic."""
+    import torch
+    x, y = crop_xy
+    g = np.asarray(gray, dtype=np.uint8)[y: y + crop_size[1], x: x + crop_size[0]]
+    if flip_flag:
+        g = g[:, ::-1]
+    t = (torch.from_numpy(np.ascontiguousarray(g, dtype=np.float32))[None] / 255.0 - 0.5) / 0.5
+    return t.repeat(repeat, 1, 1).numpy()
+
+
 def log_lut_val_range(val_range) -> np.ndarray:
     """The 256 possible values of ``np.log(img/255*(v1-v0)+v0)`` (utils.py:88-91):
     float32 numpy arithmetic with weak Python scalars, evaluated by numpy itself."""

@@ -567,6 +567,40 @@ def test_mixed_image_isr_on_device(cm):
                 assert np.array_equal(bits(got[s, c]), bits(ref[0]))
 
 
+@pytest.mark.parametrize("shape,out_wh", [((2, 1024, 2048), (1024, 512)), ((2, 256, 512, 3), (256, 128)), ((1, 67, 131), (200, 90)),
+                                          ((3, 45, 60, 3), (31, 77)), ((1, 64, 96), (96, 32))])
+def test_pil_resize_bilinear_bit_exact(cm, shape, out_wh):
+    """f-4: Image.resize(BILINEAR) on the device against Pillow itself, bit for bit ('L' and 'RGB', the Cityscapes
+    2048x1024 -> 1024x512, up-scaling, odd sizes, an unchanged axis)."""
+    from PIL import Image
+    rng = np.random.default_rng(13)
+    img = rng.integers(0, 256, size=shape, dtype=np.uint8)
+    got = cm.pil_resize_bilinear(torch.from_numpy(img).cuda(), out_wh).cpu().numpy()
+    mode = "RGB" if len(shape) == 4 else "L"
+    for s in range(shape[0]):
+        ref = np.asarray(Image.fromarray(img[s], mode=mode).resize(out_wh, resample=Image.BILINEAR))
+        assert np.array_equal(got[s], ref)
+
+
+def test_source_img_time_res_on_device(cm):
+    """f-4: frame pair -> get_image_change PNG payload -> resize(BILINEAR) -> crop -> flip -> (x/255-0.5)/0.5 -> x3
+    (create_cityscapes_image_change.py:16-35 + cityscapes_ic.py:175-183, 207-209), bit-exact against the chain of the
+    reference's own calls (oracle get_image_change, Pillow resize, torch arithmetic)."""
+    from PIL import Image
+    from cmda_b200 import synth
+    pairs = [synth.make_frame_pair(256, 512, seed=synth.seed_for(3, 40 + s)) for s in range(2)]
+    now = np.stack([a for a, _ in pairs]); front = np.stack([b for _, b in pairs])
+    xy, flips = [(17, 5), (100, 60)], [1, 0]
+    got = cm.source_img_time_res(torch.from_numpy(now).cuda(), torch.from_numpy(front).cuda(), resize_size=(256, 128),
+                                 crop_xy=xy, crop_size=(128, 64), flips=flips)
+    assert got.shape == (2, 3, 64, 128) and got.is_cuda
+    for s in range(2):
+        png = O.get_image_change(now[s], front[s])
+        small = np.asarray(Image.fromarray(png, mode="L").resize((256, 128), resample=Image.BILINEAR))
+        ref = O.u8_crop_to_centered(small, xy[s], (128, 64), bool(flips[s]), 3)
+        assert np.array_equal(bits(got[s]), bits(ref))
+
+
 # ------------------------------------------------------------------ a1: slicer
 def test_images_to_events_index_golden(cm):
     c = INDEX["index_table"]

@@ -139,3 +139,16 @@ def test_mixed_image_to_gray_matches_torch_and_pil():
     gray, rgb = O.mixed_image_to_gray(img[0].numpy(), means.numpy().ravel(), stds.numpy().ravel(), return_rgb=True)
     assert np.array_equal(rgb, np.asarray(pil))
     assert np.array_equal(gray, np.asarray(pil.convert('L')))             # utils.py:126
+
+
+@pytest.mark.parametrize("mode,in_hw,out_wh", [("L", (64, 96), (48, 32)), ("RGB", (50, 70), (35, 25)), ("L", (40, 60), (90, 55)),
+                                               ("RGB", (33, 47), (47, 33)), ("L", (128, 256), (128, 64)), ("L", (31, 64), (64, 17))])
+def test_pil_resize_bilinear_matches_pillow(mode, in_hw, out_wh):
+    """f-4: the restated Resample.c algorithm against the installed Pillow, bit for bit (down-, up- and mixed scaling,
+    2:1 like 2048x1024 -> 1024x512, odd sizes, one axis unchanged)."""
+    from PIL import Image
+    rng = np.random.default_rng(7)
+    shape = in_hw + ((3,) if mode == "RGB" else ())
+    img = rng.integers(0, 256, size=shape, dtype=np.uint8)
+    ref = np.asarray(Image.fromarray(img, mode=mode).resize(out_wh, resample=Image.BILINEAR))
+    assert np.array_equal(O.pil_resize_bilinear(img, out_wh), ref)
