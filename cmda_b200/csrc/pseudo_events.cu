@@ -225,22 +225,34 @@ isr_apply_kernel(const uint8_t* __restrict__ gray, int H, int W, int shift, Term
 // touch.  The shifted copy of utils.py:129-132 never reads outside the image: border pixels stay unshifted,
 // which is a per-byte select here.  Same arithmetic as the generic kernels above; rows are the work items of
 // persistent CTAs so that the bank-replicated log table is filled once per CTA.
-__device__ __forceinline__ unsigned load_cols_u32(const uint8_t* __restrict__ row, int W, int start) {
-    // byte j of the result = row[start + j] for every start + j inside [0, W); bytes outside the row are
-    // undefined (the caller's border select discards them)
-    if (start < 0) {
-        if (start <= -4) return 0u;
-        return __ldg(reinterpret_cast<const unsigned*>(row)) << (8 * -start);
+// Column-shift geometry of one thread (4 consecutive pixels starting at column c of every row it visits):
+// which two aligned words hold the shifted columns, by how many bits to funnel them, and which of the four
+// bytes are shifted at all (border pixels stay unshifted, utils.py:129-130).  Row invariant: computed once.
+struct ColShift {
+    int off0, off1;        // byte offsets inside a row of the two aligned words (clamped into the row)
+    unsigned funnel;       // bit count of the funnel shift
+    unsigned mask;         // 0xff per byte that takes the shifted value
+};
+__device__ __forceinline__ ColShift col_shift_of(int c, int W, int delta /* +s: left (c + s), -s: right (c - s) */) {
+    ColShift g;
+    const int start = c + delta;
+    g.mask = 0u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int cj = c + j;
+        const bool shifted = delta > 0 ? (cj < W - delta) : (cj >= -delta);
+        if (shifted) g.mask |= 255u << (8 * j);
     }
-    if (start > W - 4) {
-        if (start >= W) return 0u;
-        return __ldg(reinterpret_cast<const unsigned*>(row + W - 4)) >> (8 * (start - (W - 4)));
-    }
-    const int a = start & ~3, off = start - a;
-    const unsigned w0 = __ldg(reinterpret_cast<const unsigned*>(row + a));
-    if (off == 0) return w0;
-    const unsigned w1 = __ldg(reinterpret_cast<const unsigned*>(row + a + 4));     // a <= W - 8 here
-    return __funnelshift_r(w0, w1, off * 8);
+    // byte j of funnel(w0, w1) must be row[start + j] for every shifted byte; unshifted bytes are masked away,
+    // so the offsets only need to be valid addresses
+    int a = start & ~3;                       // floor to a multiple of 4 (also for negative start)
+    g.funnel = static_cast<unsigned>(start - a) * 8u;
+    g.off0 = min(max(a, 0), W - 4);
+    g.off1 = min(max(a + 4, 0), W - 4);
+    // a shifted byte always comes from a column inside [0, W): when a < 0 (or a + 4 > W - 4) the clamped word is
+    // only read for bytes that are masked away, except when the clamp moved a word that still matters; that
+    // happens only for the word that starts inside the row, which the clamp leaves where it is
+    return g;
 }
 
 template <int NT, bool APPLY>
@@ -253,18 +265,22 @@ isr_vec_kernel(const uint8_t* __restrict__ gray, int S, int H, int W, int shift,
     const int words = W >> 2;
     const int cw = blockIdx.x * 256 + threadIdx.x;
     const int c = cw * 4;
+    const bool live = cw < words;
     const float inv = NT == 4 ? 0.25f : 0.5f;   // x / 4 and x / 2 are exact scalings
     const long long n_rows = static_cast<long long>(S) * H;
     // consecutive rows per CTA: an image's rows stay together (one min/max flush per image)
     const long long per_cta = (n_rows + gridDim.y - 1) / gridDim.y;
     const long long row_begin = per_cta * blockIdx.y, row_end = min(row_begin + per_cta, n_rows);
+    if (row_begin >= row_end) return;
+    ColShift left{}, right{};
+    if (live) { left = col_shift_of(c, W, shift); right = col_shift_of(c, W, -shift); }
+    int img = static_cast<int>(row_begin / H), r = static_cast<int>(row_begin - static_cast<long long>(img) * H);
     int cur_img = -1;
     TermRange rng[NT];
     MinMaxAcc acc[NT];
 #pragma unroll
     for (int k = 0; k < NT; ++k) acc[k].init();
     for (long long row = row_begin; row < row_end; ++row) {
-        const int img = static_cast<int>(row / H), r = static_cast<int>(row - static_cast<long long>(img) * H);
         if (img != cur_img) {
             if (!APPLY && cur_img >= 0) {
                 flush_minmax<NT>(acc, ws + static_cast<size_t>(cur_img) * 16);
@@ -277,45 +293,43 @@ isr_vec_kernel(const uint8_t* __restrict__ gray, int S, int H, int W, int shift,
             }
             cur_img = img;
         }
-        if (cw >= words) continue;
-        const uint8_t* g = gray + static_cast<size_t>(img) * H * W;
-        const uint8_t* grow = g + static_cast<size_t>(r) * W;
-        const unsigned base_w = __ldg(reinterpret_cast<const unsigned*>(grow + c));
-        float base[4], res[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        if (live) {
+            const uint8_t* g = gray + static_cast<size_t>(img) * H * W;
+            const uint8_t* grow = g + static_cast<size_t>(r) * W;
+            const unsigned base_w = __ldg(reinterpret_cast<const unsigned*>(grow + c));
+            float base[4], res[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) base[j] = CMDA_LUT((base_w >> (8 * j)) & 255u);
+            for (int j = 0; j < 4; ++j) base[j] = CMDA_LUT((base_w >> (8 * j)) & 255u);
 #pragma unroll
-        for (int k = 0; k < NT; ++k) {
-            const int dir = terms.dir[k];
-            unsigned shw;
-            if (dir >= 2) {                          // row shift: one aligned word holds the four shifted pixels
-                int rr = r;
-                if (dir == 2) { if (r < H - shift) rr = r + shift; }      // up:   utils.py:131
-                else { if (r >= shift) rr = r - shift; }                  // down: utils.py:132
-                shw = __ldg(reinterpret_cast<const unsigned*>(g + static_cast<size_t>(rr) * W + c));
-            } else {
-                const int delta = dir == 0 ? shift : -shift;              // left: c + s (utils.py:129); right: c - s (utils.py:130)
-                shw = load_cols_u32(grow, W, c + delta);
+            for (int k = 0; k < NT; ++k) {
+                const int dir = terms.dir[k];
+                unsigned shw;
+                if (dir >= 2) {                          // row shift: one aligned word holds the four shifted pixels
+                    int rr = r;
+                    if (dir == 2) { if (r < H - shift) rr = r + shift; }      // up:   utils.py:131
+                    else { if (r >= shift) rr = r - shift; }                  // down: utils.py:132
+                    shw = __ldg(reinterpret_cast<const unsigned*>(g + static_cast<size_t>(rr) * W + c));
+                } else {
+                    const ColShift& cs = dir == 0 ? left : right;             // left: utils.py:129, right: utils.py:130
+                    const unsigned w0 = __ldg(reinterpret_cast<const unsigned*>(grow + cs.off0));
+                    const unsigned w1 = __ldg(reinterpret_cast<const unsigned*>(grow + cs.off1));
+                    shw = (__funnelshift_r(w0, w1, cs.funnel) & cs.mask) | (base_w & ~cs.mask);   // border: unshifted
+                }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int cj = c + j;
-                    const bool shifted = dir == 0 ? (cj < W - shift) : (cj >= shift);
-                    if (!shifted) shw = (shw & ~(255u << (8 * j))) | (base_w & (255u << (8 * j)));   // border: unshifted
+                    const float d = __fsub_rn(CMDA_LUT((shw >> (8 * j)) & 255u), base[j]);   // utils.py:92
+                    if (APPLY) {
+                        const float tv = __fmul_rn(normalize_term(d, thr, clip, rng[k]), inv);
+                        res[j] = (k == 0) ? tv : __fadd_rn(res[j], tv);                       // utils.py:137 / 151, left to right
+                    } else {
+                        acc[k].add(d);
+                    }
                 }
             }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float d = __fsub_rn(CMDA_LUT((shw >> (8 * j)) & 255u), base[j]);   // utils.py:92
-                if (APPLY) {
-                    const float tv = __fmul_rn(normalize_term(d, thr, clip, rng[k]), inv);
-                    res[j] = (k == 0) ? tv : __fadd_rn(res[j], tv);                       // utils.py:137 / 151, left to right
-                } else {
-                    acc[k].add(d);
-                }
-            }
+            if (APPLY) stg_stream_f4(out + static_cast<size_t>(img) * H * W + static_cast<size_t>(r) * W + c,
+                                     make_float4(res[0], res[1], res[2], res[3]));
         }
-        if (APPLY) stg_stream_f4(out + static_cast<size_t>(img) * H * W + static_cast<size_t>(r) * W + c,
-                                 make_float4(res[0], res[1], res[2], res[3]));
+        if (++r == H) { r = 0; ++img; }
     }
     if (!APPLY && cur_img >= 0) flush_minmax<NT>(acc, ws + static_cast<size_t>(cur_img) * 16);
 }
