@@ -414,7 +414,7 @@ def run_gpu(args, rank, local_rank, world):
     del store_p
 
     # ---- end to end through the host-buffer front door ----------------------------------------
-    pipe = HostEventsPipeline(t, x, y, p, rmap, args.bins, H, W, device=dev, windows_per_group=4, mode=args.mode,
+    pipe = HostEventsPipeline(t, x, y, p, rmap, args.bins, H, W, device=dev, windows_per_group=1, mode=args.mode,
                               max_window_events=args.events)
     host_out = torch.empty((WINDOWS_PER_GPU, args.bins, H, W), dtype=torch.float32).pin_memory()
     for _ in range(max(1, min(args.warmup, 2))):
