@@ -378,19 +378,28 @@ struct GatherStats {
 // no intermediate plane buffer exists, and the only global traffic besides R is the stencil row and the
 // output.  Tiles whose box does not fit (degenerate maps) or whose rows are incomplete gather straight from
 // R, one pixel at a time.
-constexpr int kOutW = 64, kOutH = 8, kOutThreads = kOutW * kOutH;
-constexpr int kStageBytes = 64 * 1024;       // shared memory for the staged planes of one tile
+#ifndef CMDA_OUT_ROWS_PER_THREAD
+#define CMDA_OUT_ROWS_PER_THREAD 1
+#endif
+#ifndef CMDA_STAGE_KB
+#define CMDA_STAGE_KB 64
+#endif
+constexpr int kOutW = 64, kOutRowsPerThread = CMDA_OUT_ROWS_PER_THREAD, kOutH = 8 * kOutRowsPerThread, kOutThreads = kOutW * 8;
+constexpr int kStageBytes = CMDA_STAGE_KB * 1024;       // shared memory for the staged planes of one tile
 
 __global__ void __launch_bounds__(kOutThreads)
 out_tile_box_kernel(MapSlots ms, int H, int W, size_t ncells_padded) {
     const int slot = blockIdx.y;
     const unsigned npx = static_cast<unsigned>(H) * static_cast<unsigned>(W);
     const int tiles_x = (W + kOutW - 1) / kOutW;
-    const int X = (blockIdx.x % tiles_x) * kOutW + (threadIdx.x % kOutW), Y = (blockIdx.x / tiles_x) * kOutH + (threadIdx.x / kOutW);
+    const int X = (blockIdx.x % tiles_x) * kOutW + (threadIdx.x % kOutW);
     const Stencil sc = stencil_at(plan_of(ms, slot), ncells_padded, npx);
     int4* boxes = reinterpret_cast<int4*>(plan_of(ms, slot) + index_bytes_of(ncells_padded, npx) + stencil_bytes(npx));
     int x0 = INT32_MAX, y0 = INT32_MAX, x1 = -1, y1 = -1, bad = 0;
-    if (X < W && Y < H) {
+    for (int rpt = 0; rpt < kOutRowsPerThread; ++rpt) {
+        const int Y = (blockIdx.x / tiles_x) * kOutH + rpt * 8 + (threadIdx.x / kOutW);
+        if (X >= W || Y >= H) continue;
+        {
         const unsigned px = static_cast<unsigned>(Y) * W + X;
         const unsigned n = sc.n[px];
         if (n == kEllOverflow) bad = 1;
@@ -400,6 +409,7 @@ out_tile_box_kernel(MapSlots ms, int H, int W, size_t ncells_padded) {
                 const int pxx = static_cast<int>(P & 0xffffu), pyy = static_cast<int>(P >> 16);
                 x0 = min(x0, pxx); x1 = max(x1, pxx); y0 = min(y0, pyy); y1 = max(y1, pyy);
             }
+        }
     }
     __shared__ int s_r[5][kOutThreads / 32];
     x0 = __reduce_min_sync(0xffffffffu, x0); y0 = __reduce_min_sync(0xffffffffu, y0);
@@ -459,9 +469,7 @@ rectify_gather_kernel(const void* __restrict__ R, WindowTable tab, MapSlots ms, 
     const unsigned npx = static_cast<unsigned>(H) * static_cast<unsigned>(W);
     const bool identity = maps == nullptr;
     const int tiles_x = (W + kOutW - 1) / kOutW;
-    const int X = (blockIdx.x % tiles_x) * kOutW + (threadIdx.x % kOutW), Y = (blockIdx.x / tiles_x) * kOutH + (threadIdx.x / kOutW);
-    const bool inside = X < W && Y < H;
-    const unsigned px = static_cast<unsigned>(Y) * W + X;
+    const int X = (blockIdx.x % tiles_x) * kOutW + (threadIdx.x % kOutW);
     float* out = raw + static_cast<size_t>(s) * B * npx;
 
     int4 box;
@@ -486,7 +494,10 @@ rectify_gather_kernel(const void* __restrict__ R, WindowTable tab, MapSlots ms, 
     __syncthreads();
 
     GatherStats st{0.0, 0.0, 0, INFINITY, -INFINITY};
-    if (inside) {
+    for (int rpt = 0; rpt < kOutRowsPerThread; ++rpt) {
+        const int Y = (blockIdx.x / tiles_x) * kOutH + rpt * 8 + (threadIdx.x / kOutW);
+        if (X >= W || Y >= H) continue;
+        const unsigned px = static_cast<unsigned>(Y) * W + X;
         double acc[BA];
 #pragma unroll
         for (int b = 0; b < BA; ++b) acc[b] = 0.0;
