@@ -49,7 +49,10 @@ def _to_u8_cuda(img, dev) -> torch.Tensor:
     if isinstance(img, torch.Tensor):
         assert img.dtype == torch.uint8, "uint8 image expected"
         return img.to(dev, non_blocking=True).contiguous()
-    return torch.from_numpy(np.ascontiguousarray(img, dtype=np.uint8)).to(dev, non_blocking=True)
+    a = np.ascontiguousarray(img, dtype=np.uint8)
+    if not a.flags.writeable:          # e.g. np.asarray(PIL image): torch wants a writable buffer to wrap
+        a = a.copy()
+    return torch.from_numpy(a).to(dev, non_blocking=True)
 
 
 def _home(img) -> torch.device:

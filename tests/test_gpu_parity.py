@@ -454,6 +454,43 @@ def test_events_vg_full_size_properties(cm, bins):
     assert np.all(o[raw.cpu().numpy() == 0] == 0)
 
 
+def test_abi_error_codes_on_device(cm):
+    """The C ABI never throws: bad workspaces, unknown modes and unsupported shapes come back as CMDA_ERR_* codes,
+    and AUTO falls back to GLOBAL where FACTORED does not apply (B > 24)."""
+    from cmda_b200 import _lib, synth
+    L = cm.lib()
+    H, W, n = 48, 64, 2000
+    t, x, y, p = synth.make_events(n, H, W, seed=3)
+    store = cm.EventStore(t, x, y, p, synth.make_rectify_map(H, W, seed=1), height=H, width=W, device="cuda:0", plan=False)
+    starts, ends, clip = np.array([0], np.int64), np.array([n], np.int64), np.array([1.0], np.float32)
+    out = torch.empty((1, 5, H, W), dtype=torch.float32, device="cuda")
+    need = L.cmda_events_vg_workspace_bytes(n, 1, H, W, 5, _lib.VOXEL_AUTO)
+    ws = torch.empty(need + 512, dtype=torch.uint8, device="cuda")
+
+    def call(ws_ptr, ws_bytes, mode, bins=5, o=out):
+        return L.cmda_events_vg_batch(_lib.ptr(store.t), _lib.ptr(store.x), _lib.ptr(store.y), _lib.ptr(store.p),
+                                      _lib.host_ptr(starts), _lib.host_ptr(ends), 1, _lib.ptr(store.rectify_map), None, H, W, bins,
+                                      _lib.host_ptr(clip), 1.0, 1, 1, _lib.ptr(o), None, None, ws_ptr, ws_bytes, mode,
+                                      torch.cuda.current_stream().cuda_stream)
+
+    assert call(ws.data_ptr(), need, _lib.VOXEL_AUTO) == 0
+    assert call(ws.data_ptr(), need - 1, _lib.VOXEL_AUTO) == -3            # CMDA_ERR_WORKSPACE: too small
+    assert call(ws.data_ptr() + 8, need, _lib.VOXEL_AUTO) == -3            # ... misaligned
+    assert call(ws.data_ptr(), need, 17) == -1                             # CMDA_ERR_BAD_ARG: unknown mode
+    assert call(None, need, _lib.VOXEL_AUTO) == -1
+    big = torch.empty((1, 30, H, W), dtype=torch.float32, device="cuda")
+    need30 = L.cmda_events_vg_workspace_bytes(n, 1, H, W, 30, _lib.VOXEL_FACTORED)
+    ws30 = torch.empty(max(need30, L.cmda_events_vg_workspace_bytes(n, 1, H, W, 30, _lib.VOXEL_AUTO)) + 256, dtype=torch.uint8,
+                       device="cuda")
+    assert call(ws30.data_ptr(), ws30.numel(), _lib.VOXEL_FACTORED, bins=30, o=big) == -4   # CMDA_ERR_UNSUPPORTED
+    assert L.cmda_events_vg_resolved_mode(n, 1, H, W, 30, _lib.VOXEL_AUTO) == _lib.VOXEL_GLOBAL
+    assert call(ws30.data_ptr(), ws30.numel(), _lib.VOXEL_AUTO, bins=30, o=big) == 0
+    torch.cuda.synchronize()
+    ref = O.get_events_vg(t, x, y, p, store.rectify_map[0].cpu().numpy(), W, H, 30, n - 1, 0, clip_range=1.0)
+    np.testing.assert_allclose(big[0].cpu().numpy(), ref, rtol=0, atol=1e-5)
+    assert L.cmda_strerror(-4) == b"unsupported shape" and L.cmda_last_cuda_error() == 0
+
+
 def test_events_vg_bad_windows(cm):
     from cmda_b200 import synth
     t, x, y, p = synth.make_events(1000, 48, 64, seed=1)
