@@ -454,6 +454,55 @@ def test_events_vg_full_size_properties(cm, bins):
     assert np.all(o[raw.cpu().numpy() == 0] == 0)
 
 
+@pytest.mark.parametrize("seed", list(range(32)))
+def test_events_vg_randomised_differential(cm, seed):
+    """Seeded differential test of every voxel mode against the oracle on small adversarial inputs: odd grid sizes,
+    1..9 bins, duplicate timestamps, maps with NaN / +-inf / huge / negative / exactly-integer / exactly-on-the-border
+    entries, several windows and maps per call."""
+    rng = np.random.default_rng(1000 + seed)
+    if seed < 24:
+        H, W, n = int(rng.integers(3, 70)), int(rng.integers(4, 90)), int(rng.integers(2, 600))
+    else:           # several gather / partition tiles in each direction
+        H, W, n = int(rng.integers(100, 300)), int(rng.integers(100, 400)), int(rng.integers(5000, 40000))
+    B = int(rng.integers(1, 10))
+    t = np.sort(rng.integers(0, max(2, n // 3), size=n)).astype(np.uint32) + np.uint32(rng.integers(0, 1 << 20))
+    x = rng.integers(0, W, size=n).astype(np.uint16)
+    y = rng.integers(0, H, size=n).astype(np.uint16)
+    p = rng.integers(0, 2, size=n).astype(np.uint8)
+    maps = []
+    for k in range(2):
+        ys, xs = np.meshgrid(np.arange(H, dtype=np.float64), np.arange(W, dtype=np.float64), indexing="ij")
+        a, b = rng.uniform(0.6, 1.5), rng.uniform(-0.2, 0.2)
+        mx = a * xs + b * ys + rng.uniform(-3, 3) + rng.normal(0, 0.3, size=xs.shape)
+        my = rng.uniform(0.6, 1.5) * ys - b * xs + rng.uniform(-3, 3) + rng.normal(0, 0.3, size=xs.shape)
+        m = np.stack([mx, my], axis=-1).astype(np.float32)
+        special = np.array([np.nan, np.inf, -np.inf, 1e10, -1e10, -0.5, -1.0, -1.5, 0.0, 1.0, W - 1.0, float(W), W - 0.25, H - 1.0,
+                            float(H), 2.5, -0.0], dtype=np.float32)
+        idx = rng.integers(0, H * W, size=max(4, H * W // 6))
+        m.reshape(-1, 2)[idx, rng.integers(0, 2, size=idx.size)] = rng.choice(special, size=idx.size)
+        if k == 1:   # a fold: many raw pixels land in the same cell (overfull cells, rows with > 8 sources)
+            m[: H // 2, :, 0] = np.float32(W / 2 + 0.3) + rng.normal(0, 0.2, size=(H // 2, W)).astype(np.float32)
+        maps.append(m)
+    maps = np.stack(maps)
+    store = cm.EventStore(t, x, y, p, maps, height=H, width=W, device="cuda:0", plan=bool(seed % 2))
+    starts = [0, int(n // 3), int(n // 2)]
+    fins = [n - 1, int(2 * n // 3), int(n // 2)]            # the last one is a single-event window
+    mids = [0, 1, int(seed % 2)]
+    ref = {}
+    for s in range(3):
+        sl = slice(starts[s], fins[s] + 1)
+        tf, xf, yf, pf = O.rectify_events(t[sl], x[sl], y[sl], p[sl], maps[mids[s]])
+        ref[s] = O.events_to_voxel_grid(tf, xf, yf, pf, W, H, B, return_aux=True)
+    for mode in ("global", "tiled", "factored", "exact"):
+        raw, counts = cm.events_vg_batch(store, starts, fins, B, map_ids=mids, mode=mode, normalize=False, return_bin_counts=True)
+        for s in range(3):
+            g, aux = ref[s]
+            assert_raw_close(raw[s], g, aux["abs_weight_sum"], aux["n_contrib"])
+            assert np.array_equal(counts[s].cpu().numpy(), aux["bin_counts"]), mode
+            if mode == "exact":
+                assert np.array_equal(bits(raw[s]), bits(g))
+
+
 def test_abi_error_codes_on_device(cm):
     """The C ABI never throws: bad workspaces, unknown modes and unsupported shapes come back as CMDA_ERR_* codes,
     and AUTO falls back to GLOBAL where FACTORED does not apply (B > 24)."""
