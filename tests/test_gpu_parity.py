@@ -628,6 +628,47 @@ def test_pseudo_events_large_vs_c_oracle(cm, h, w):
         assert np.array_equal(bits(got[:, 0]), bits(ref)), direction
 
 
+@pytest.mark.parametrize("seed", list(range(40)))
+def test_pseudo_events_randomised_differential(cm, seed):
+    """Seeded differential test of both pseudo-event generators against the numpy oracle, bit for bit: tiny and odd
+    image sizes (every vector tail), every direction, shifts up to size-1, constant / two-level / saturated images
+    (empty positive or negative side, d == 0 everywhere), thresholds that swallow everything."""
+    rng = np.random.default_rng(7000 + seed)
+    H, W = int(rng.integers(2, 80)), int(rng.integers(2, 150))
+    kind = seed % 5
+    if kind == 0:
+        img = rng.integers(0, 256, size=(H, W), dtype=np.uint8)
+    elif kind == 1:
+        img = np.full((H, W), int(rng.integers(0, 256)), dtype=np.uint8)
+    elif kind == 2:
+        img = (rng.integers(0, 2, size=(H, W)) * 255).astype(np.uint8)
+    elif kind == 3:
+        img = np.clip(np.add.outer(np.arange(H) * 3, np.arange(W) * 2) + rng.integers(-2, 3, size=(H, W)), 0, 255).astype(np.uint8)
+    else:
+        img = rng.integers(100, 104, size=(H, W), dtype=np.uint8)       # differences mostly inside the dead zone
+    other = np.clip(img.astype(np.int32) + rng.integers(-40, 41, size=(H, W)) * (rng.random((H, W)) < 0.3), 0, 255).astype(np.uint8)
+    if kind == 1:
+        other = img.copy()
+    val_range = [(1, 100), (0.01, 1.01), (0.5, 7.25), (1e-3, 255.0)][seed % 4]
+    thr = float(rng.choice([0.0, 0.005, 0.04, 0.3, 2.0]))
+    clip = float(rng.choice([0.05, 0.1, 0.2, 0.8]))
+    shift = int(rng.integers(1, min(H, W)))
+    for direction in ("rightdown", "rightup", "leftdown", "leftup", "all"):
+        got = cm.get_image_change_from_pil(torch.from_numpy(img).cuda(), W, H, shift_pixel=shift, val_range=val_range,
+                                           _threshold=thr, _clip_range=clip, shift_direction=direction)
+        ref = O.get_image_change_from_pil(img, W, H, shift_pixel=shift, val_range=val_range, _threshold=thr,
+                                          _clip_range=clip, shift_direction=direction)
+        assert got.shape == ref.shape and np.array_equal(bits(got), bits(ref)), (direction, H, W, shift)
+    got = cm.get_ic(torch.from_numpy(other).cuda(), torch.from_numpy(img).cuda(), val_range=val_range, threshold=thr,
+                    clip_range=clip)
+    assert np.array_equal(bits(got), bits(O.get_ic(other, img, val_range, thr, clip)))
+    la, th2, cr2 = float(rng.choice([1.0, 50.0, 0.5])), float(rng.choice([0.0, 0.1, 0.5])), float(rng.choice([0.3, 0.8]))
+    f32, u8 = cm.image_change_batch(torch.from_numpy(img[None]).cuda(), torch.from_numpy(other[None]).cuda(), log_add=la,
+                                    threshold=th2, clip_range=cr2, want_f32=True, want_u8=True)
+    assert np.array_equal(bits(f32[0]), bits(O.get_image_change(img, other, la, th2, cr2, return_float=True)))
+    assert np.array_equal(u8[0].cpu().numpy(), O.get_image_change(img, other, la, th2, cr2))
+
+
 def test_mixed_image_isr_on_device(cm):
     """a9 (dacs.py:729-744): normalised float image on the GPU -> ISR on the GPU, bit-exact against the
     reference's sequence (denorm, clamp, uint8, PIL 'L', get_image_change_from_pil, repeat 3)."""
