@@ -126,7 +126,27 @@ def host_ptr(a: np.ndarray | None):
 
 
 def stream_ptr(device) -> int:
-    return torch.cuda.current_stream(device).cuda_stream
+    """cudaStream_t of torch's current stream on ``device`` (the raw-handle query: this sits on every call's path)."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    return torch._C._cuda_getCurrentRawStream(idx)
+
+
+class on_device:
+    """``torch.cuda.device(dev)`` that costs nothing when ``dev`` is already the current device."""
+    __slots__ = ("_ctx",)
+
+    def __init__(self, device):
+        idx = device.index
+        self._ctx = None if idx is None or idx == torch.cuda.current_device() else torch.cuda.device(idx)
+
+    def __enter__(self):
+        if self._ctx is not None:
+            self._ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self._ctx is not None:
+            self._ctx.__exit__(*exc)
+        return False
 
 
 _workspaces: dict = {}

@@ -461,12 +461,12 @@ int cmda_isr_shift_u8(const uint8_t* d_img, int channels, int S, int H, int W, i
     return launch_isr(gray, S, H, W, shift_pixel, direction, h_lut, thr, clip, d_out, slots, st);
 }
 
-int cmda_denorm_rgb_to_gray_u8(const float* d_img, int S, int H, int W, const float* h_mean, const float* h_std,
+int cmda_denorm_rgb_to_gray_u8(const float* d_img, int S, int H, int W, const float* mean, const float* stdv,
                                uint8_t* d_gray, uint8_t* d_rgb, void* stream) {
     if (S < 0 || H <= 0 || W <= 0) return CMDA_ERR_BAD_ARG;
     if (S == 0) return CMDA_OK;
-    if (!d_img || !h_mean || !h_std || !d_gray) return CMDA_ERR_BAD_ARG;
-    return launch_denorm_to_gray(d_img, S, H, W, h_mean, h_std, d_gray, d_rgb, static_cast<cudaStream_t>(stream));
+    if (!d_img || !mean || !stdv || !d_gray) return CMDA_ERR_BAD_ARG;
+    return launch_denorm_to_gray(d_img, S, H, W, mean, stdv, d_gray, d_rgb, static_cast<cudaStream_t>(stream));
 }
 
 size_t cmda_resize_bilinear_workspace_bytes(int S, int H, int W, int channels, int out_h, int out_w) {

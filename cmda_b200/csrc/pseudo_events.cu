@@ -462,9 +462,13 @@ struct Denorm3 {
     float mean[3], std[3];
 };
 __global__ void __launch_bounds__(256)
-denorm_to_gray_kernel(const float* __restrict__ img, long long npx, Denorm3 q, uint8_t* __restrict__ gray,
-                      uint8_t* __restrict__ rgb) {
+denorm_to_gray_kernel(const float* __restrict__ img, long long npx, Denorm3 q, const float* __restrict__ d_mean,
+                      const float* __restrict__ d_std, uint8_t* __restrict__ gray, uint8_t* __restrict__ rgb) {
     const int s = blockIdx.y;
+    if (d_mean != nullptr) {          // constants that live in device memory (the reference's CUDA tensors)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { q.mean[c] = __ldg(d_mean + c); q.std[c] = __ldg(d_std + c); }
+    }
     const float* base = img + static_cast<size_t>(s) * 3 * npx;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < npx;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -484,10 +488,21 @@ denorm_to_gray_kernel(const float* __restrict__ img, long long npx, Denorm3 q, u
     }
 }
 
-int launch_denorm_to_gray(const float* img, int S, int H, int W, const float* h_mean, const float* h_std, uint8_t* gray,
+static bool is_device_pointer(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+int launch_denorm_to_gray(const float* img, int S, int H, int W, const float* mean, const float* stdv, uint8_t* gray,
                           uint8_t* rgb, cudaStream_t st) {
-    Denorm3 q;
-    for (int c = 0; c < 3; ++c) { q.mean[c] = h_mean[c]; q.std[c] = h_std[c]; }
+    Denorm3 q = {};
+    const bool dev_m = is_device_pointer(mean), dev_s = is_device_pointer(stdv);
+    if (dev_m != dev_s) return CMDA_ERR_BAD_ARG;
+    const float* d_mean = dev_m ? mean : nullptr;
+    const float* d_std = dev_m ? stdv : nullptr;
+    if (!dev_m)
+        for (int c = 0; c < 3; ++c) { q.mean[c] = mean[c]; q.std[c] = stdv[c]; }
     const long long npx = static_cast<long long>(H) * W;
     long long gx = (npx + 255) / 256;
     const long long cap = (148LL * 8 + S - 1) / S;
@@ -496,7 +511,7 @@ int launch_denorm_to_gray(const float* img, int S, int H, int W, const float* h_
     for (int s0 = 0; s0 < S; s0 += 32768) {
         const int sn = (S - s0) < 32768 ? (S - s0) : 32768;
         denorm_to_gray_kernel<<<dim3(static_cast<unsigned>(gx), sn), 256, 0, st>>>(
-            img + static_cast<size_t>(s0) * 3 * npx, npx, q, gray + static_cast<size_t>(s0) * npx,
+            img + static_cast<size_t>(s0) * 3 * npx, npx, q, d_mean, d_std, gray + static_cast<size_t>(s0) * npx,
             rgb ? rgb + static_cast<size_t>(s0) * npx * 3 : nullptr);
         CMDA_LAUNCH_CHECK();
     }

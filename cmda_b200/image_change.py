@@ -66,7 +66,7 @@ def rgb_to_gray(rgb, *, out_device=None) -> torch.Tensor:
     src = _to_u8_cuda(rgb, dev)
     assert src.shape[-1] == 3
     out = torch.empty(src.shape[:-1], dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         _lib.check(_lib.lib().cmda_rgb_to_gray_u8(_lib.ptr(src), out.numel(), _lib.ptr(out), _lib.stream_ptr(dev)),
                    "cmda_rgb_to_gray_u8")
     return out.to(out_device if out_device is not None else home)
@@ -92,7 +92,7 @@ def isr_batch(images, shift_pixel, val_range, _threshold, _clip_range, shift_dir
     if out is None:
         out = torch.empty((S, 1, H, W), dtype=torch.float32, device=dev)
     assert out.is_cuda and out.is_contiguous() and out.numel() == S * H * W
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         ws = _lib.workspace(dev, L.cmda_image_workspace_bytes(S, H, W, channels))
         _lib.check(L.cmda_isr_shift_u8(_lib.ptr(src), channels, S, H, W, int(shift_pixel),
                                        _lib.DIRECTIONS[shift_direction], _lib.host_ptr(lut), float(thr), float(clip),
@@ -120,6 +120,20 @@ def get_image_change_from_pil(pil_image, width, height, data_type=None, shift_pi
     return isr_batch(img, shift_pixel, val_range, _threshold, _clip_range, shift_direction, out_device=out_device)[0]
 
 
+def _three_floats(v, dev):
+    """The 3 channel constants of ``denorm`` as ``(keep_alive, pointer)``.  The reference keeps ``means`` / ``stds``
+    as ``[B, 3, 1, 1]`` CUDA tensors (dacs_transforms.py:38-49) and uses row 0 for every sample
+    (``.numpy()[0]`` of the broadcast, dacs.py:730-731): a float32 CUDA tensor is handed to the kernel as it is
+    (no read-back, which would synchronise the device once per train step); anything else goes through the host."""
+    if isinstance(v, torch.Tensor) and v.is_cuda and v.device == dev:
+        t = v.detach().reshape(-1)[:3].to(torch.float32).contiguous()       # views only for the reference's tensors
+        assert t.numel() == 3
+        return t, t.data_ptr()
+    a = np.ascontiguousarray(torch.as_tensor(v).detach().float().cpu().reshape(-1)[:3].numpy(), dtype=np.float32)
+    assert a.size == 3
+    return a, _lib.host_ptr(a)
+
+
 def denorm_to_gray(img, means, stds, *, return_rgb=False):
     """``clamp(denorm(img, means, stds), 0, 1) * 255 -> uint8 -> PIL 'L'`` on the device
     (reference dacs.py:730-733 with dacs_transforms.py:52-53).  ``img`` is a CUDA float32
@@ -129,14 +143,15 @@ def denorm_to_gray(img, means, stds, *, return_rgb=False):
     assert img.ndim == 4 and img.shape[1] == 3 and img.dtype == torch.float32
     img = img.contiguous()
     dev = img.device
-    m = np.ascontiguousarray(torch.as_tensor(means).detach().float().cpu().reshape(-1).numpy(), dtype=np.float32)
-    sd = np.ascontiguousarray(torch.as_tensor(stds).detach().float().cpu().reshape(-1).numpy(), dtype=np.float32)
-    assert m.size == 3 and sd.size == 3
+    (m_keep, m_ptr), (sd_keep, sd_ptr) = _three_floats(means, dev), _three_floats(stds, dev)
+    if isinstance(m_keep, torch.Tensor) != isinstance(sd_keep, torch.Tensor):     # both on the same side
+        m_keep, m_ptr = _three_floats(torch.as_tensor(means).cpu(), dev)
+        sd_keep, sd_ptr = _three_floats(torch.as_tensor(stds).cpu(), dev)
     S, _, H, W = (int(v) for v in img.shape)
     gray = torch.empty((S, H, W), dtype=torch.uint8, device=dev)
     rgb = torch.empty((S, H, W, 3), dtype=torch.uint8, device=dev) if return_rgb else None
-    with torch.cuda.device(dev):
-        _lib.check(_lib.lib().cmda_denorm_rgb_to_gray_u8(_lib.ptr(img), S, H, W, _lib.host_ptr(m), _lib.host_ptr(sd),
+    with _lib.on_device(dev):
+        _lib.check(_lib.lib().cmda_denorm_rgb_to_gray_u8(_lib.ptr(img), S, H, W, m_ptr, sd_ptr,
                                                          _lib.ptr(gray), _lib.ptr(rgb), _lib.stream_ptr(dev)),
                    "cmda_denorm_rgb_to_gray_u8")
     return (gray, rgb) if return_rgb else gray
@@ -165,7 +180,7 @@ def pil_resize_bilinear(images, size, *, out_device=None) -> torch.Tensor:
     ow, oh = int(size[0]), int(size[1])
     out = torch.empty((S, oh, ow, 3) if channels == 3 else (S, oh, ow), dtype=torch.uint8, device=dev)
     L = _lib.lib()
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         ws = _lib.workspace(dev, L.cmda_resize_bilinear_workspace_bytes(S, H, W, channels, oh, ow))
         _lib.check(L.cmda_resize_bilinear_u8(_lib.ptr(src), channels, S, H, W, oh, ow, _lib.ptr(out), _lib.ptr(ws), ws.numel(),
                                              _lib.stream_ptr(dev)), "cmda_resize_bilinear_u8")
@@ -190,7 +205,7 @@ def u8_crop_to_centered(gray, crop_xy, crop_size, flips=None, repeat=3, *, out_d
     if S and (aug[:, 0].min() < 0 or aug[:, 1].min() < 0 or (aug[:, 0] + cw).max() > W or (aug[:, 1] + ch).max() > H):
         raise IndexError("crop outside the image")
     out = torch.empty((S, int(repeat), ch, cw), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         _lib.check(_lib.lib().cmda_u8_crop_to_centered_f32(_lib.ptr(src), S, H, W, _lib.host_ptr(aug), cw, ch, int(repeat),
                                                            _lib.ptr(out), _lib.stream_ptr(dev)), "cmda_u8_crop_to_centered_f32")
     return out.to(out_device if out_device is not None else home)
@@ -224,7 +239,7 @@ def _pair(now, front, lut, thr, clip, dev, want_f32, want_u8):
     L = _lib.lib()
     out_f = torch.empty((S, H, W), dtype=torch.float32, device=dev) if want_f32 else None
     out_u = torch.empty((S, H, W), dtype=torch.uint8, device=dev) if want_u8 else None
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         ws = _lib.workspace(dev, L.cmda_image_workspace_bytes(S, H, W, 1))
         _lib.check(L.cmda_logdiff_pair_u8(_lib.ptr(now), _lib.ptr(front), S, H, W, _lib.host_ptr(lut), float(thr),
                                           float(clip), _lib.ptr(out_f), _lib.ptr(out_u), _lib.ptr(ws), ws.numel(),

@@ -29,7 +29,7 @@ def searchsorted_right(t, queries, *, device=None) -> torch.Tensor:
     t_d = _dev_tensor(t, np.uint32, dev)
     q_d = _dev_tensor(queries, np.int64, dev)
     out = torch.empty(q_d.shape, dtype=torch.int64, device=dev)
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         _lib.check(_lib.lib().cmda_searchsorted_right_u32(_lib.ptr(t_d), t_d.numel(), _lib.ptr(q_d), q_d.numel(),
                                                           _lib.ptr(out), _lib.stream_ptr(dev)),
                    "cmda_searchsorted_right_u32")
@@ -47,7 +47,7 @@ def images_to_events_index(t, t_offset, ms_to_idx, images_timestamps, *, device=
     n_ts = int(ts_d.numel())
     index = torch.empty((n_ts,), dtype=torch.int64, device=dev)
     status = torch.empty((n_ts,), dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         _lib.check(_lib.lib().cmda_images_to_events_index(_lib.ptr(t_d), t_d.numel(), _lib.ptr(ms_d), ms_d.numel(),
                                                           int(t_offset), _lib.ptr(ts_d), n_ts, _lib.ptr(index),
                                                           _lib.ptr(status), _lib.stream_ptr(dev)),

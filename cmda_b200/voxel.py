@@ -65,7 +65,7 @@ def events_to_voxel_grid(time, x, y, pol, width, height, num_bins, normalize_fla
     L = _lib.lib()
     grid = torch.empty((num_bins, height, width), dtype=torch.float32, device=dev)
     counts = torch.empty((num_bins,), dtype=torch.int64, device=dev) if return_bin_counts else None
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         nbytes = L.cmda_events_vg_workspace_bytes(n, 1, height, width, num_bins, mode_id)
         ws = _lib.workspace(dev, nbytes)
         _lib.check(L.cmda_voxel_grid_f32(_lib.ptr(t_), _lib.ptr(x_), _lib.ptr(y_), _lib.ptr(p_), n, width, height,
@@ -94,7 +94,7 @@ def events_norm(events, clip_range=1.0, final_range=1.0, enforce_no_events_zero=
     g = _as_tensor(events, torch.float32, dev).clone()
     L = _lib.lib()
     clip = np.array([clip_range], dtype=np.float32)
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         ws = _lib.workspace(dev, L.cmda_events_norm_workspace_bytes(1))
         _lib.check(L.cmda_events_norm_batch(_lib.ptr(g), 1, g.numel(), _lib.host_ptr(clip), float(final_range),
                                             int(bool(enforce_no_events_zero)), _lib.ptr(ws), ws.numel(),
@@ -180,7 +180,7 @@ def events_vg_batch(store: EventStore, starts, finishes, num_bins, clip_ranges=N
     raw = torch.empty_like(out) if (return_raw and normalize) else None
     counts = torch.empty((S, B), dtype=torch.int64, device=dev) if return_bin_counts else None
     total = int(np.clip(ends - starts, 0, None).sum())
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         ws = _lib.workspace(dev, L.cmda_events_vg_workspace_bytes(total, S, H, W, B, mode_id))
         _lib.check(L.cmda_events_vg_batch_planned(
             _lib.ptr(store.t), _lib.ptr(store.x), _lib.ptr(store.y), _lib.ptr(store.p), _lib.host_ptr(starts),
@@ -233,7 +233,7 @@ def events_vg_augmented_batch(store: EventStore, starts, finishes, num_bins, cli
         out = torch.empty((S, int(repeat) * Bo, oh, ow), dtype=torch.float32, device=dev)
     assert out.is_cuda and out.is_contiguous() and out.shape == (S, int(repeat) * Bo, oh, ow)
     total = int(np.clip(ends - starts, 0, None).sum())
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         ws = _lib.workspace(dev, L.cmda_events_vg_augmented_workspace_bytes(total, S, H, W, B, mode_id))
         _lib.check(L.cmda_events_vg_augmented_batch(
             _lib.ptr(store.t), _lib.ptr(store.x), _lib.ptr(store.y), _lib.ptr(store.p), _lib.host_ptr(starts),
@@ -254,7 +254,7 @@ def remap_events(store: EventStore, start: int, finish: int, num_bins: int, map_
     xr, yr, tn = f(torch.float32), f(torch.float32), f(torch.float32)
     x0, y0, t0 = f(torch.int32), f(torch.int32), f(torch.int32)
     rmap = None if store.rectify_map is None else store.rectify_map[map_id]
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         _lib.check(L.cmda_remap_events(_lib.ptr(store.t), _lib.ptr(store.x), _lib.ptr(store.y), _lib.ptr(store.p),
                                        start, finish + 1, _lib.ptr(rmap), store.height, store.width, num_bins,
                                        _lib.ptr(xr), _lib.ptr(yr), _lib.ptr(tn), _lib.ptr(x0), _lib.ptr(y0),

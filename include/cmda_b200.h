@@ -233,10 +233,12 @@ int cmda_isr_shift_u8(const uint8_t* d_img, int channels, int S, int H, int W, i
  *   clamp(denorm(img, mean, std), 0, 1) * 255 -> np.uint8 -> Image.fromarray -> convert('L')
  * (denorm = img.mul(std).add(mean) / 255.0, mmseg/models/utils/dacs_transforms.py:52-53).
  *  d_img   [S, 3, H, W] float32, the normalised image batch as the model sees it
- *  h_mean, h_std  3 floats each (img_norm_cfg mean / std)
+ *  mean, stdv   3 floats each (img_norm_cfg mean / std), in HOST or DEVICE memory (both in the same kind;
+ *               told apart with cudaPointerGetAttributes).  The reference keeps them in CUDA tensors
+ *               (dacs_transforms.py:38-49): passing those pointers avoids a synchronising read-back.
  *  d_gray  [S, H, W] uint8 'L' plane: feed it to cmda_isr_shift_u8(channels = 1)
  *  d_rgb   optional [S, H, W, 3] uint8, the bytes PIL would have been handed (may be NULL) */
-int cmda_denorm_rgb_to_gray_u8(const float* d_img, int S, int H, int W, const float* h_mean, const float* h_std,
+int cmda_denorm_rgb_to_gray_u8(const float* d_img, int S, int H, int W, const float* mean, const float* stdv,
                                uint8_t* d_gray, uint8_t* d_rgb, void* stream);
 
 /* ------------------------------------------------------------------------------------

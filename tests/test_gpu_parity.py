@@ -684,6 +684,11 @@ def test_mixed_image_isr_on_device(cm):
     for s in range(S):
         g_ref, rgb_ref = O.mixed_image_to_gray(img[s], means, stds, return_rgb=True)
         assert np.array_equal(gray[s].cpu().numpy(), g_ref) and np.array_equal(rgb[s].cpu().numpy(), rgb_ref)
+    # constants from the host, and the reference's [B, 3, 1, 1] device tensors (row 0 rules, dacs.py:730-731): same bytes
+    assert torch.equal(cm.denorm_to_gray(d_img, means, stds), gray)
+    m2 = torch.cat([m, m * 0 + 7.0]); sd2 = torch.cat([sd, sd * 0 + 3.0])
+    assert torch.equal(cm.denorm_to_gray(d_img, m2, sd2), gray)
+    assert torch.equal(cm.denorm_to_gray(d_img, m.double(), np.asarray(stds)), gray)
     for direction in ("leftdown", "rightup"):
         got = cm.mixed_image_isr(d_img, m, sd, shift_direction=direction, **parms)
         assert got.is_cuda and got.shape == (S, 3, H, W)
