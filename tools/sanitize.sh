@@ -4,7 +4,7 @@
 # uninitialised global memory, e.g. a workspace region a kernel assumed zeroed).  Run on a B200:
 #   bash tools/sanitize.sh > gpurun_out/sanitizer.txt 2>&1
 SEL='golden or randomised or modes_identical or abi_error or fused_augment or resize or mixed_image or from_timestamps'
-for tool in memcheck racecheck initcheck; do
+for tool in ${TOOLS:-memcheck racecheck}; do      # TOOLS=initcheck is very slow here (>15 min): pick a small -k selection
   echo "=== compute-sanitizer --tool $tool"
   timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 --print-limit 20 \
       python -m pytest tests -m gpu -x -q -p no:cacheprovider -k "$SEL" 2>&1 | grep -v "^=========$" | tail -40
