@@ -344,6 +344,8 @@ def run_gpu(args, rank, local_rank, world):
 
     L = cmda_b200.lib()     # raises if the CUDA extension is missing
     torch.cuda.set_device(local_rank)
+    from cmda_b200.sharding import bind_to_gpu_numa
+    affinity = bind_to_gpu_numa(local_rank)      # before any pinned host buffer is allocated
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -489,7 +491,8 @@ def run_gpu(args, rank, local_rank, world):
             "metric": "voxelized_events_per_s", "value": value, "unit": "Mevents/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(args, world), resolved_mode=_lib.VOXEL_MODE_NAMES[resolved]),
+            "config": dict(workload_config(args, world), resolved_mode=_lib.VOXEL_MODE_NAMES[resolved],
+                           rank0_cpu_affinity=affinity),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mevents/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "steps": e2e_steps, "matches_device_path": same},

@@ -6,7 +6,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["shard_round_robin", "shard_lpt", "gather_objects"]
+__all__ = ["shard_round_robin", "shard_lpt", "gather_objects", "bind_to_gpu_numa"]
 
 
 def shard_round_robin(n_units: int, world_size: int, rank: int) -> list:
@@ -41,3 +41,36 @@ def gather_objects(obj, group=None) -> list:
     out = [None] * dist.get_world_size(group)
     dist.all_gather_object(out, obj, group=group)
     return out
+
+
+def bind_to_gpu_numa(device_index: int) -> dict:
+    """Restrict this process (one per GPU) to the CPUs NVML reports as local to its GPU, so that the pinned host
+    buffers it allocates afterwards land on that GPU's NUMA node (Linux places pages on the node of the allocating
+    thread) and the H2D / D2H DMA of the host-buffer path does not cross the inter-socket link.  Never widens the
+    set the process was given and never leaves it empty; returns what it did (``{"bound": bool, ...}``)."""
+    import os
+    info = {"bound": False}
+    if os.environ.get("CMDA_NO_NUMA_BIND"):
+        return dict(info, skipped="CMDA_NO_NUMA_BIND")
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        try:
+            pr = torch.cuda.get_device_properties(device_index)
+            bus_id = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus_id.encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        local = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        target = local & allowed
+        info.update(gpu_local_cpus=len(local), allowed_cpus=len(allowed), target_cpus=len(target))
+        if target and target != allowed:
+            os.sched_setaffinity(0, target)
+            info["bound"] = True
+    except Exception as e:            # no NVML, no permission, not Linux: leave the process where it is
+        info["error"] = f"{type(e).__name__}: {e}"[:120]
+    return info
