@@ -333,6 +333,70 @@ def train_step_input_leg(dev, steps=20, warmup=3):
     return res
 
 
+# ------------------------------------------------------------------------------------ variants of the headline
+def variants_leg(store, starts, fins, rmap, args, dev, steps=10, warmup=3):
+    """SURVEY.md 8(d)'s other device-resident cases, reported beside the headline (same kernels, same timing
+    rules: CUDA events, 3 warm-ups, inputs larger than L2 except C1): the shipped events_bins = 1; the 5-map variant
+    of C2 (5 night sequences, window s -> map s mod 5, plans rebuilt inside every step); the skewed variant (10 % of
+    the events on 1 % of the pixels: contention stress for the per-event atomics); C4's 20 M-event windows; C1's
+    single 1 M-event window (latency).  The skewed and C4 inputs are generated on the device with torch's
+    generator (they feed no parity test)."""
+    import torch
+    import cmda_b200
+    from cmda_b200 import synth
+
+    def timed(st, s0, f0, bins, **kw):
+        s0, f0 = np.asarray(s0, dtype=np.int64), np.asarray(f0, dtype=np.int64)
+        out = torch.empty((len(s0), bins, H, W), dtype=torch.float32, device=dev)
+        for _ in range(warmup):
+            cmda_b200.events_vg_batch(st, s0, f0, bins, mode=args.mode, out=out, **kw)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(steps):
+            cmda_b200.events_vg_batch(st, s0, f0, bins, mode=args.mode, out=out, **kw)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / steps
+        n = int((f0 - s0 + 1).sum())
+        return {"Mevents_per_s": n / (ms * 1e-3) / 1e6, "ms_per_step": ms, "windows": int(len(s0)), "events_per_step": n,
+                "bins": bins}
+
+    res = {}
+    S = len(starts)
+    if args.bins != 1:
+        res["C2_bins_1"] = timed(store, starts, fins, 1)
+    maps = np.stack([rmap] + [synth.make_rectify_map(H, W, seed=synth.seed_for(2, 900 + k)) for k in range(4)])
+    store5 = cmda_b200.EventStore(store.t, store.x, store.y, store.p, maps, height=H, width=W, device=dev, plan=False)
+    res["C2_five_maps"] = timed(store5, starts, fins, args.bins, map_ids=[s % 5 for s in range(S)])
+    store5 = cmda_b200.EventStore(store.t, store.x, store.y, store.p, maps, height=H, width=W, device=dev)
+    res["C2_five_maps_prebuilt_plans"] = timed(store5, starts, fins, args.bins, map_ids=[s % 5 for s in range(S)])
+    del store5
+    g = torch.Generator(device=dev).manual_seed(20251)
+    n = len(store)
+    hot = torch.randperm(H * W, generator=g, device=dev)[: H * W // 100]
+    pick = hot[torch.randint(hot.numel(), (n,), generator=g, device=dev)]
+    move = torch.rand((n,), generator=g, device=dev) < 0.1
+    xs = torch.where(move, pick % W, store.x.view(torch.int16).to(torch.int64)).to(torch.int16).view(torch.uint16)
+    ys = torch.where(move, pick // W, store.y.view(torch.int16).to(torch.int64)).to(torch.int16).view(torch.uint16)
+    del pick, move
+    skew = cmda_b200.EventStore(store.t, xs, ys, store.p, rmap, height=H, width=W, device=dev, plan=False)
+    res["C2_skewed_10pct_on_1pct"] = timed(skew, starts, fins, args.bins)
+    del skew, xs, ys
+    n4, s4 = 20_000_000, 4
+    t4 = torch.cat([torch.sort(torch.randint(0, 50_000, (n4,), generator=g, device=dev, dtype=torch.int32))[0] + 10_000_000
+                    for _ in range(s4)]).view(torch.uint32)
+    x4 = torch.randint(0, W, (s4 * n4,), generator=g, device=dev, dtype=torch.int16).view(torch.uint16)
+    y4 = torch.randint(0, H, (s4 * n4,), generator=g, device=dev, dtype=torch.int16).view(torch.uint16)
+    p4 = torch.randint(0, 2, (s4 * n4,), generator=g, device=dev, dtype=torch.uint8)
+    c4 = cmda_b200.EventStore(t4, x4, y4, p4, rmap, height=H, width=W, device=dev, plan=False)
+    res["C4_20M_event_windows"] = timed(c4, [k * n4 for k in range(s4)], [(k + 1) * n4 - 1 for k in range(s4)], args.bins)
+    del c4, t4, x4, y4, p4
+    n1 = min(1_000_000, int(fins[0] - starts[0] + 1))
+    res["C1_single_1M_window"] = timed(store, [int(starts[0])], [int(starts[0]) + n1 - 1], args.bins)
+    return res
+
+
 # ------------------------------------------------------------------------------------ GPU leg
 def run_gpu(args, rank, local_rank, world):
     import torch
@@ -483,10 +547,13 @@ def run_gpu(args, rank, local_rank, world):
             cpu = {"value": rate, "unit": "Mevents/s", "cores": min(cores, nw), "kind": "port",
                    "sample": f"{nw} of the step's {WINDOWS_PER_GPU} windows x {args.events} events, one window "
                              f"per thread, {dt:.1f} s"}
-        pseudo = c5 = None
+        pseudo = c5 = variants = None
         if world == 1 and not args.no_pseudo:
             pseudo = pseudo_events_leg(dev, peak)
             c5 = train_step_input_leg(dev)
+        if world == 1 and not args.no_variants:
+            del pipe, host_out
+            variants = variants_leg(store, starts, fins, rmap, args, dev)
         line = {
             "metric": "voxelized_events_per_s", "value": value, "unit": "Mevents/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -501,6 +568,7 @@ def run_gpu(args, rank, local_rank, world):
                                         "ms_per_step": planned_ms,
                                         "note": "cmda_rectify_plan_build once per sequence instead of inside every step"},
             "roofline": roofline, "cpu_baseline": cpu, "pseudo_events": pseudo, "train_step_input_path": c5,
+            "variants": variants,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -518,6 +586,7 @@ def main():
     ap.add_argument("--mode", default="auto", choices=["auto", "global", "tiled", "factored"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pseudo", action="store_true", help="skip the pseudo-event (config C3) leg")
+    ap.add_argument("--no-variants", action="store_true", help="skip the other device-resident cases of SURVEY.md 8(d)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cmda_b200" else args.warmup
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)

@@ -577,7 +577,7 @@ regroup_partials_kernel(const PartialStats* __restrict__ block_partials, int nbl
 }
 
 // ---- workspace + launch sequence ---------------------------------------------------------------
-constexpr int kMaxDistinctMaps = 4;    // inverse indices held at once; api.cu cuts window groups accordingly
+constexpr int kMaxDistinctMaps = 8;    // plans held at once when the call builds its own (DSEC has 5 night sequences); api.cu cuts window groups accordingly
 
 static size_t ncells_padded_of(int H, int W) {
     return align_up(static_cast<size_t>(H + 1) * (W + 1) + 2, 64);
