@@ -183,12 +183,12 @@ sensor_accumulate_kernel(const uint32_t* __restrict__ t, const uint16_t* __restr
 }
 
 // One R cell chain -> planes: plane_b = C_b - F_b + F_(b-1), the temporal corners 1 - f and f of
-// dsec.py:49-52, as a float64 holding the exact 2^-30 fixed-point integer; for B == 1 the plane is the
-// signed event count.  f(b, value) is called for b = 0 .. B-1 in order.
+// dsec.py:49-52, as a float64 holding the exact 2^-24 fixed-point integer (kFracBits); for B == 1 the plane
+// is the signed event count.  f(b, value) is called for b = 0 .. B-1 in order.
 template <typename F>
 __device__ __forceinline__ void planes_of_pixel(const void* __restrict__ R, unsigned s, unsigned P, unsigned npx, int B, F&& f) {
     if (B == 1) {
-        f(0, static_cast<double>(__ldg(reinterpret_cast<const int*>(R) + static_cast<size_t>(s) * npx + P)) * 1073741824.0);
+        f(0, static_cast<double>(__ldg(reinterpret_cast<const int*>(R) + static_cast<size_t>(s) * npx + P)) * 16777216.0);
         return;
     }
     const long long* r = reinterpret_cast<const long long*>(R) + static_cast<size_t>(s) * B * npx + P;
@@ -200,7 +200,7 @@ __device__ __forceinline__ void planes_of_pixel(const void* __restrict__ R, unsi
         const long long c = (cell - fr) >> kCountShift;
         const long long pl = c * (1LL << kFracBits) - fr + f_prev; // 2^-24 fixed point, |pl| < 2^44
         f_prev = fr;
-        f(b, static_cast<double>(pl * 64));                        // 2^-30 fixed point, exact
+        f(b, static_cast<double>(pl));                             // exact: |pl| < 2^53
     }
 }
 
@@ -366,7 +366,7 @@ stencil_build_kernel(const float2* __restrict__ maps, MapSlots ms, int H, int W,
 // ---- stage B ----------------------------------------------------------------------------------
 struct GatherStats {
     double sum, sumsq;
-    long long nnz;
+    int nnz;
     float mn, mx;
 };
 
@@ -379,12 +379,19 @@ struct GatherStats {
 // output.  Tiles whose box does not fit (degenerate maps) or whose rows are incomplete gather straight from
 // R, one pixel at a time.
 #ifndef CMDA_OUT_ROWS_PER_THREAD
-#define CMDA_OUT_ROWS_PER_THREAD 1
+#define CMDA_OUT_ROWS_PER_THREAD 2
 #endif
 #ifndef CMDA_STAGE_KB
-#define CMDA_STAGE_KB 64
+#define CMDA_STAGE_KB 48
 #endif
-constexpr int kOutW = 64, kOutRowsPerThread = CMDA_OUT_ROWS_PER_THREAD, kOutH = 8 * kOutRowsPerThread, kOutThreads = kOutW * 8;
+#ifndef CMDA_OUT_TY
+#define CMDA_OUT_TY 4
+#endif
+#ifndef CMDA_OUT_W
+#define CMDA_OUT_W 64
+#endif
+constexpr int kOutW = CMDA_OUT_W, kOutTY = CMDA_OUT_TY, kOutRowsPerThread = CMDA_OUT_ROWS_PER_THREAD,
+              kOutH = kOutTY * kOutRowsPerThread, kOutThreads = kOutW * kOutTY;
 constexpr int kStageBytes = CMDA_STAGE_KB * 1024;       // shared memory for the staged planes of one tile
 
 __global__ void __launch_bounds__(kOutThreads)
@@ -397,7 +404,7 @@ out_tile_box_kernel(MapSlots ms, int H, int W, size_t ncells_padded) {
     int4* boxes = reinterpret_cast<int4*>(plan_of(ms, slot) + index_bytes_of(ncells_padded, npx) + stencil_bytes(npx));
     int x0 = INT32_MAX, y0 = INT32_MAX, x1 = -1, y1 = -1, bad = 0;
     for (int rpt = 0; rpt < kOutRowsPerThread; ++rpt) {
-        const int Y = (blockIdx.x / tiles_x) * kOutH + rpt * 8 + (threadIdx.x / kOutW);
+        const int Y = (blockIdx.x / tiles_x) * kOutH + rpt * kOutTY + (threadIdx.x / kOutW);
         if (X >= W || Y >= H) continue;
         {
         const unsigned px = static_cast<unsigned>(Y) * W + X;
@@ -447,12 +454,12 @@ __device__ __noinline__ GatherRow<BT> gather_pixel_from_cells(const void* __rest
         planes_of_pixel(R, s, P, npx, B, [&](int b, double pl) {
 #pragma unroll
             for (int bb = 0; bb < BT; ++bb)
-                if (bb == b) iacc[bb] += __double2ll_rn(static_cast<double>(w) * pl);
+                if (bb == b) iacc[bb] += __double2ll_rn(static_cast<double>(w) * (pl * 64.0));   // 2^-30 quanta
         });
     });
     GatherRow<BT> r;
 #pragma unroll
-    for (int b = 0; b < BT; ++b) r.v[b] = static_cast<double>(iacc[b]);
+    for (int b = 0; b < BT; ++b) r.v[b] = static_cast<double>(iacc[b]) * 0.015625;       // back to 2^-24 units (exact)
     return r;
 }
 
@@ -483,19 +490,23 @@ rectify_gather_kernel(const void* __restrict__ R, WindowTable tab, MapSlots ms, 
     }
     const bool staged = box.z > 0 && static_cast<size_t>(box.z) * box.w * B * sizeof(double) <= kStageBytes;
     if (staged) {
-        // warps over the rows of the box, lanes over its columns (coalesced row segments of R)
-        for (unsigned ly = threadIdx.x >> 5; ly < static_cast<unsigned>(box.w); ly += kOutThreads / 32)
-            for (unsigned lx = threadIdx.x & 31; lx < static_cast<unsigned>(box.z); lx += 32) {
-                const unsigned P = (box.y + ly) * W + box.x + lx;
-                double* dst = s_planes + static_cast<size_t>(ly * box.z + lx) * B;
-                planes_of_pixel(R, s, P, npx, B, [&](int b, double pl) { dst[b] = pl; });
-            }
+        // the cells of the box in row-major order over the threads: consecutive lanes read consecutive cells of a
+        // row of R (coalesced row segments) and no lane idles on a short row.  cell / box.z by multiplication:
+        // exact while cells * box.z < 2^32 (cells <= kStageBytes / 8).
+        const unsigned cells = static_cast<unsigned>(box.z) * static_cast<unsigned>(box.w);
+        const unsigned inv_w = 0xffffffffu / static_cast<unsigned>(box.z) + 1u;
+        for (unsigned c = threadIdx.x; c < cells; c += kOutThreads) {
+            const unsigned ly = box.z == 1 ? c : __umulhi(c, inv_w), lx = c - ly * static_cast<unsigned>(box.z);
+            const unsigned P = (box.y + ly) * W + box.x + lx;
+            double* dst = s_planes + static_cast<size_t>(c) * B;
+            planes_of_pixel(R, s, P, npx, B, [&](int b, double pl) { dst[b] = pl; });
+        }
     }
     __syncthreads();
 
     GatherStats st{0.0, 0.0, 0, INFINITY, -INFINITY};
     for (int rpt = 0; rpt < kOutRowsPerThread; ++rpt) {
-        const int Y = (blockIdx.x / tiles_x) * kOutH + rpt * 8 + (threadIdx.x / kOutW);
+        const int Y = (blockIdx.x / tiles_x) * kOutH + rpt * kOutTY + (threadIdx.x / kOutW);
         if (X >= W || Y >= H) continue;
         const unsigned px = static_cast<unsigned>(Y) * W + X;
         double acc[BA];
@@ -525,7 +536,7 @@ rectify_gather_kernel(const void* __restrict__ R, WindowTable tab, MapSlots ms, 
 #pragma unroll
         for (int b = 0; b < BA; ++b) {
             if (b < B) {
-                const float v = __double2float_rn(acc[b] * 9.31322574615478515625e-10);   // * 2^-30 (exact), one rounding
+                const float v = __double2float_rn(acc[b] * 5.9604644775390625e-08);       // * 2^-24 (exact), one rounding
                 out[static_cast<unsigned>(b) * npx + px] = v;
                 if (v != 0.0f) {                                   // dsec.py:88
                     st.nnz += 1;
@@ -539,11 +550,11 @@ rectify_gather_kernel(const void* __restrict__ R, WindowTable tab, MapSlots ms, 
     }
     // fixed-order block reduction -> one partial per (window, block)
     __shared__ double s_sum[kOutThreads / 32], s_sq[kOutThreads / 32];
-    __shared__ long long s_n[kOutThreads / 32];
+    __shared__ int s_n[kOutThreads / 32];
     __shared__ float s_mn[kOutThreads / 32], s_mx[kOutThreads / 32];
     st.sum = warp_sum(st.sum);
     st.sumsq = warp_sum(st.sumsq);
-    st.nnz = warp_sum(st.nnz);
+    st.nnz = __reduce_add_sync(0xffffffffu, st.nnz);
     st.mn = warp_min(st.mn);
     st.mx = warp_max(st.mx);
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
