@@ -276,27 +276,28 @@ rectify_index_sort_kernel(MapSlots ms, int H, int W, size_t ncells_padded) {
 // ---- gather stencil of one map ---------------------------------------------------------------------
 // The rectification splat is a sparse linear map from sensor space to the rectified grid (about four
 // non-zeros per output pixel) that depends on the map only, not on the window or the bin.  It is
-// materialised once per call per distinct map in ELL form (kEll entries per output pixel, SoA so that a
-// warp's loads coalesce): raw pixel index + float32 weight fl(tent(X, x) * tent(Y, y)) (dsec.py:51-52
-// with value = 1).  Rows with more than kEll entries (degenerate maps) are flagged and gathered from
+// materialised once per call per distinct map (or once per sequence by the caller) in ELL form: kEll 8-byte
+// entries per output pixel, entry-major so that a warp's loads coalesce, each the source pixel + the float32
+// weight fl(tent(X, x) * tent(Y, y)) (dsec.py:51-52 with value = 1).  Rows with more than kEll entries (degenerate maps) are flagged and gathered from
 // the cell lists directly.
 constexpr int kEll = 8;
 constexpr unsigned kEllOverflow = 0xffu;
 
 struct Stencil {
-    unsigned* P;          // [kEll][npx]
-    float* w;             // [kEll][npx]
-    unsigned char* n;     // [npx]   entries of the row, or kEllOverflow
+    uint2* e;             // [kEll][npx]  .x = source pixel, .y = float32 weight bits
+    unsigned char* n;     // [npx]        entries of the row, or kEllOverflow
 };
+// .x is written by stencil_build_kernel as (row << 16 | column) of the raw pixel and rewritten by
+// out_tile_box_kernel as the pixel's cell index inside the box of the output tile that owns the row
+// ((row - box.y) * box.w + column - box.x): the gather kernel multiplies it by B and reads shared memory.
 __device__ __host__ __forceinline__ size_t stencil_bytes(size_t npx) {
-    return (npx * kEll * (sizeof(unsigned) + sizeof(float)) + npx + 255) / 256 * 256;
+    return (npx * kEll * sizeof(uint2) + npx + 255) / 256 * 256;
 }
 __device__ __forceinline__ Stencil stencil_at(char* plan, size_t ncells_padded, size_t npx) {
     char* b = plan + index_bytes_of(ncells_padded, npx);
     Stencil st;
-    st.P = reinterpret_cast<unsigned*>(b);
-    st.w = reinterpret_cast<float*>(b + npx * kEll * sizeof(unsigned));
-    st.n = reinterpret_cast<unsigned char*>(b + npx * kEll * (sizeof(unsigned) + sizeof(float)));
+    st.e = reinterpret_cast<uint2*>(b);
+    st.n = reinterpret_cast<unsigned char*>(b + npx * kEll * sizeof(uint2));
     return st;
 }
 
@@ -353,10 +354,8 @@ stencil_build_kernel(const float2* __restrict__ maps, MapSlots ms, int H, int W,
     unsigned n = 0;
     const bool overfull = for_each_source(ix, map, X, Y, W, false, [&](unsigned P, float w) {
         if (w == 0.0f) return;
-        if (n < kEll) {   // the source pixel as (row << 16 | column): the gather needs no division
-            sc.P[n * npx + px] = ((P / static_cast<unsigned>(W)) << 16) | (P % static_cast<unsigned>(W));
-            sc.w[n * npx + px] = w;
-        }
+        if (n < kEll)     // the source pixel as (row << 16 | column) for out_tile_box_kernel
+            sc.e[n * npx + px] = make_uint2(((P / static_cast<unsigned>(W)) << 16) | (P % static_cast<unsigned>(W)), __float_as_uint(w));
         ++n;
     });
     // a row is usable when it is complete and its order reproducible (sorted slots only)
@@ -412,13 +411,14 @@ out_tile_box_kernel(MapSlots ms, int H, int W, size_t ncells_padded) {
         if (n == kEllOverflow) bad = 1;
         else
             for (unsigned k = 0; k < n; ++k) {
-                const unsigned P = sc.P[k * npx + px];
+                const unsigned P = sc.e[k * npx + px].x;
                 const int pxx = static_cast<int>(P & 0xffffu), pyy = static_cast<int>(P >> 16);
                 x0 = min(x0, pxx); x1 = max(x1, pxx); y0 = min(y0, pyy); y1 = max(y1, pyy);
             }
         }
     }
     __shared__ int s_r[5][kOutThreads / 32];
+    __shared__ int4 s_box;
     x0 = __reduce_min_sync(0xffffffffu, x0); y0 = __reduce_min_sync(0xffffffffu, y0);
     x1 = __reduce_max_sync(0xffffffffu, x1); y1 = __reduce_max_sync(0xffffffffu, y1);
     bad = __reduce_max_sync(0xffffffffu, bad);
@@ -434,6 +434,22 @@ out_tile_box_kernel(MapSlots ms, int H, int W, size_t ncells_padded) {
         if (bad) box = make_int4(0, 0, -1, -1);                    // incomplete rows: per-pixel path
         else if (x1 >= x0) box = make_int4(x0, y0, x1 - x0 + 1, y1 - y0 + 1);
         boxes[blockIdx.x] = box;
+        s_box = box;
+    }
+    __syncthreads();
+    // the rows of a stageable tile now address the cells of its box
+    const int4 box = s_box;
+    if (box.z <= 0) return;
+    for (int rpt = 0; rpt < kOutRowsPerThread; ++rpt) {
+        const int Y = (blockIdx.x / tiles_x) * kOutH + rpt * kOutTY + (threadIdx.x / kOutW);
+        if (X >= W || Y >= H) continue;
+        const unsigned px = static_cast<unsigned>(Y) * W + X;
+        const unsigned n = sc.n[px];
+        for (unsigned k = 0; k < n; ++k) {
+            const unsigned P = sc.e[k * npx + px].x;
+            sc.e[k * npx + px].x = ((P >> 16) - static_cast<unsigned>(box.y)) * static_cast<unsigned>(box.z) +
+                                   ((P & 0xffffu) - static_cast<unsigned>(box.x));
+        }
     }
 }
 
@@ -513,19 +529,22 @@ rectify_gather_kernel(const void* __restrict__ R, WindowTable tab, MapSlots ms, 
 #pragma unroll
         for (int b = 0; b < BA; ++b) acc[b] = 0.0;
         if (staged) {
-            auto accumulate = [&](unsigned yx, float w) {     // yx = row << 16 | column of the source pixel
+            auto accumulate = [&](unsigned cell, float w) {   // cell = index of the source pixel inside the box
                 const double md = static_cast<double>(w);
-                const double* src = s_planes + (((yx >> 16) - box.y) * box.z + ((yx & 0xffffu) - box.x)) * B;
+                const double* src = s_planes + cell * B;
 #pragma unroll
                 for (int b = 0; b < BA; ++b)
                     if (b < B) acc[b] = fma(md, src[b], acc[b]);       // the row's fixed order: reproducible
             };
             if (identity) {
-                accumulate((static_cast<unsigned>(Y) << 16) | static_cast<unsigned>(X), 1.0f);
+                accumulate(static_cast<unsigned>(Y - box.y) * box.z + static_cast<unsigned>(X - box.x), 1.0f);
             } else {
                 const Stencil sc = stencil_at(plan_of(ms, ms.slot[s]), ncells_padded, npx);
                 const unsigned n = sc.n[px];
-                for (unsigned k = 0; k < n; ++k) accumulate(__ldg(sc.P + k * npx + px), __ldg(sc.w + k * npx + px));
+                for (unsigned k = 0; k < n; ++k) {
+                    const uint2 e = __ldg(sc.e + k * npx + px);
+                    accumulate(e.x, __uint_as_float(e.y));
+                }
             }
         } else if (box.z != 0) {     // box.z == 0: no source pixel reaches this tile, the sums stay 0
             const GatherRow<BA> row = gather_pixel_from_cells<BA>(R, s, npx, maps + static_cast<size_t>(tab.w[s].map_id) * npx,
