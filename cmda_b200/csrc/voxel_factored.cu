@@ -480,11 +480,13 @@ __device__ __noinline__ GatherRow<BT> gather_pixel_from_cells(const void* __rest
 }
 
 // BT: compile-time number of bins (0: run-time B <= 24).
+// Shared memory of one CTA: the planes of the largest box worth staging.  B = 1 planes are 8 bytes per cell, so a
+// quarter of the budget holds a box four times the tile: more CTAs per SM (5 at 48 registers).
+constexpr int kStageBytesB1 = kStageBytes / 4;
 template <int BT>
-__global__ void __launch_bounds__(kOutThreads)
-rectify_gather_kernel(const void* __restrict__ R, WindowTable tab, MapSlots ms, const float2* __restrict__ maps,
-                      size_t ncells_padded, int H, int W, int Brt, float* __restrict__ raw,
-                      PartialStats* __restrict__ block_partials) {
+__device__ __forceinline__ void rectify_gather_body(const void* __restrict__ R, const WindowTable& tab, const MapSlots& ms,
+                                                    const float2* __restrict__ maps, size_t ncells_padded, int H, int W, int Brt,
+                                                    float* __restrict__ raw, PartialStats* __restrict__ block_partials) {
     extern __shared__ double s_planes[];                     // [box pixels][B]
     constexpr int BA = BT ? BT : 24;
     const int B = BT ? BT : Brt;
@@ -504,7 +506,7 @@ rectify_gather_kernel(const void* __restrict__ R, WindowTable tab, MapSlots ms, 
         box = __ldg(reinterpret_cast<const int4*>(plan_of(ms, ms.slot[s]) + index_bytes_of(ncells_padded, npx) + stencil_bytes(npx)) +
                     blockIdx.x);
     }
-    const bool staged = box.z > 0 && static_cast<size_t>(box.z) * box.w * B * sizeof(double) <= kStageBytes;
+    const bool staged = box.z > 0 && static_cast<size_t>(box.z) * box.w * B * sizeof(double) <= (BT == 1 ? kStageBytesB1 : kStageBytes);
     if (staged) {
         // the cells of the box in row-major order over the threads: consecutive lanes read consecutive cells of a
         // row of R (coalesced row segments) and no lane idles on a short row.  cell / box.z by multiplication:
@@ -588,6 +590,21 @@ rectify_gather_kernel(const void* __restrict__ R, WindowTable tab, MapSlots ms, 
         }
         block_partials[static_cast<size_t>(s) * gridDim.x + blockIdx.x] = o;
     }
+}
+template <int BT>
+__global__ void __launch_bounds__(kOutThreads)
+rectify_gather_kernel(const void* __restrict__ R, const __grid_constant__ WindowTable tab, const __grid_constant__ MapSlots ms,
+                      const float2* __restrict__ maps, size_t ncells_padded, int H, int W, int Brt, float* __restrict__ raw,
+                      PartialStats* __restrict__ block_partials) {
+    rectify_gather_body<BT>(R, tab, ms, maps, ncells_padded, H, W, Brt, raw, block_partials);
+}
+// B = 1 (the shipped events_bins): 48 registers -> 5 CTAs per SM
+template <>
+__global__ void __launch_bounds__(kOutThreads, 5)
+rectify_gather_kernel<1>(const void* __restrict__ R, const __grid_constant__ WindowTable tab, const __grid_constant__ MapSlots ms,
+                         const float2* __restrict__ maps, size_t ncells_padded, int H, int W, int Brt, float* __restrict__ raw,
+                         PartialStats* __restrict__ block_partials) {
+    rectify_gather_body<1>(R, tab, ms, maps, ncells_padded, H, W, Brt, raw, block_partials);
 }
 
 // [S][nblk] block partials -> the [S][kStatBlocks] partials the normaliser consumes; slot j is the
@@ -728,8 +745,9 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
         dim3 grid(nblk, S);
 #define CMDA_GATHER(BT)                                                                                                  \
     do {                                                                                                                 \
-        CMDA_CUDA_TRY(cudaFuncSetAttribute(rectify_gather_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageBytes)); \
-        rectify_gather_kernel<BT><<<grid, kOutThreads, kStageBytes, st>>>(R, tab, ms, maps2, nc, H, W, B, raw, block_partials);  \
+        constexpr int stage = BT == 1 ? kStageBytesB1 : kStageBytes;                                                     \
+        CMDA_CUDA_TRY(cudaFuncSetAttribute(rectify_gather_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, stage));     \
+        rectify_gather_kernel<BT><<<grid, kOutThreads, stage, st>>>(R, tab, ms, maps2, nc, H, W, B, raw, block_partials);        \
     } while (0)
         switch (B) {
             case 1: CMDA_GATHER(1); break;
