@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import random
 
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -65,6 +66,25 @@ class DSECEvents:
         obj.images_to_events_index = images_to_events_index(obj.store.t, t_offset, ms_to_idx, images_timestamps,
                                                             device=obj.store.device)
         return obj
+
+    @classmethod
+    def from_cache(cls, path, images_to_events_index=None, device=None, **kwargs):
+        """Build the object from a decoded-sequence cache directory (``cmda_b200.store_io``: events.h5 decoded once,
+        instead of being re-opened and blosc-decoded per sample as in dsec.py:287, 342-345).  The arrays are streamed
+        from the memory-mapped files to the device; the per-image event index comes from the cached image
+        timestamps (K1 on the device) unless ``images_to_events_index`` is given."""
+        from . import store_io
+        from .voxel import _cuda_device
+        seq = store_io.load_sequence(path)
+        dev = _cuda_device(device)
+        t, x, y, p = (store_io.upload(seq[k], dev) for k in ("t", "x", "y", "p"))
+        rmap = store_io.upload(seq["rectify_map"], dev)
+        if images_to_events_index is not None:
+            return cls(t, x, y, p, rmap, images_to_events_index, device=dev, **kwargs)
+        if "images_timestamps" not in seq:
+            raise ValueError(f"{path}: no image timestamps in the cache and no images_to_events_index given")
+        return cls.from_timestamps(t, x, y, p, rmap, np.asarray(seq["ms_to_idx"]), seq["t_offset"],
+                                   np.asarray(seq["images_timestamps"]), device=dev, **kwargs)
 
     # ---- dsec.py:341-366 -------------------------------------------------------------
     def _clip_for(self, finish, start):

@@ -19,7 +19,10 @@ __all__ = ["searchsorted_right", "images_to_events_index", "write_index_txt", "w
 def _dev_tensor(a, np_dtype, dev):
     if isinstance(a, torch.Tensor):
         return a.to(dev, non_blocking=True).contiguous()
-    return torch.from_numpy(np.ascontiguousarray(a, dtype=np_dtype)).to(dev, non_blocking=True)
+    a = np.ascontiguousarray(a, dtype=np_dtype)
+    if not a.flags.writeable:          # e.g. a memory-mapped cache file: torch wants a writable buffer to wrap
+        a = a.copy()
+    return torch.from_numpy(a).to(dev, non_blocking=True)
 
 
 def searchsorted_right(t, queries, *, device=None) -> torch.Tensor:

@@ -764,6 +764,38 @@ def test_dsec_events_from_timestamps(cm):
     np.testing.assert_allclose(item[0].cpu().numpy(), ref[0, :440], rtol=0, atol=1e-5)
 
 
+def test_dsec_events_from_cache(cm, tmp_path):
+    """f-3: a sequence written once in the decoded cache format and streamed back from the memory-mapped files gives
+    the same object (index table, windows, grids bit for bit) as the arrays it was written from; the chunked
+    pinned upload is exact for sizes around its chunk boundaries."""
+    from cmda_b200 import store_io, synth
+    c = INDEX["index_table"]
+    n = c["t"].shape[0]
+    rng = np.random.default_rng(4)
+    x = rng.integers(0, 640, n).astype(np.uint16)
+    y = rng.integers(0, 480, n).astype(np.uint16)
+    p = rng.integers(0, 2, n).astype(np.uint8)
+    rmap = synth.make_rectify_map(480, 640, seed=2)
+    d = store_io.save_sequence(str(tmp_path / "seq"), c["t"], x, y, p, c["ms_to_idx"], int(c["t_offset"]), rmap, c["timestamps"])
+    kw = dict(events_bins=5, outputs={'events_vg', 'label'}, device="cuda:0")
+    a = cm.DSECEvents.from_cache(d, **kw)
+    b = cm.DSECEvents.from_timestamps(c["t"], x, y, p, rmap, c["ms_to_idx"], int(c["t_offset"]), c["timestamps"], **kw)
+    assert a.images_to_events_index == b.images_to_events_index == [int(v) for v in c["result"]]
+    assert torch.equal(a.store.t.view(torch.int32), b.store.t.view(torch.int32)) and torch.equal(a.store.rectify_map, b.store.rectify_map)
+    valid = [i for i in range(1, len(a.images_to_events_index))
+             if a.images_to_events_index[i - 1] >= 0 and a.images_to_events_index[i] > a.images_to_events_index[i - 1]]
+    for i in valid[:: max(1, len(valid) // 3)]:
+        assert torch.equal(a.events_vg_for_image(i), b.events_vg_for_image(i))
+    # explicit index table instead of cached timestamps
+    a2 = cm.DSECEvents.from_cache(d, images_to_events_index=c["result"], **kw)
+    assert a2.images_to_events_index == a.images_to_events_index
+    for nbytes, chunk in ((0, 64), (1, 64), (64, 64), (65, 64), (1000, 64), (4096, 1 << 20)):
+        h = rng.integers(0, 256, nbytes).astype(np.uint8)
+        assert np.array_equal(store_io.upload(h, torch.device("cuda:0"), chunk_bytes=chunk).cpu().numpy(), h)
+    h32 = rng.integers(0, 1 << 32, 777, dtype=np.uint64).astype(np.uint32)
+    assert np.array_equal(store_io.upload(h32, torch.device("cuda:0"), chunk_bytes=100).view(torch.int32).cpu().numpy(), h32.view(np.int32))
+
+
 def test_images_to_events_index_range_error(cm):
     c = INDEX["index_table"]
     bad = c["ms_to_idx"].copy()
