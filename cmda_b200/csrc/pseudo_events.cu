@@ -124,12 +124,34 @@ __device__ __forceinline__ TermRange decode_range(const unsigned* __restrict__ s
 // constant above (same operations, same bits).
 __device__ __forceinline__ float normalize_term(float d, float thr, float clip, const TermRange& r) {
     if (fabsf(d) <= thr) d = 0.0f;
-    if (d < 0.0f) {
-        const float neg = fminf(fmaxf(d, -clip), 0.0f);
-        return __fadd_rn(r.p_of_zero, normalize_neg(neg, r));
+    const bool neg = d < 0.0f;
+    float part;
+    if (clip >= 0.0f) {
+        // clamp(d, 0, clip) for d >= 0 and clamp(d, -clip, 0) for d < 0 are both clamp(d, -clip, clip)
+        part = fminf(fmaxf(d, -clip), clip);
+    } else {        // a negative clip range (min > max in the reference's clamps): spelled out
+        part = neg ? fminf(fmaxf(d, -clip), 0.0f) : fminf(fmaxf(d, 0.0f), clip);
     }
-    const float pos = fminf(fmaxf(d, 0.0f), clip);
-    return __fadd_rn(normalize_pos(pos, r), r.n_of_zero);
+    // the side's own min / denominator; the other side contributes its per-image constant
+    float v = div_by_reused(__fsub_rn(part, neg ? r.nmin : r.pmin), neg ? r.nden : r.pden, neg ? r.rnden : r.rpden);
+    if (neg) v = __fadd_rn(v, -1.0f);                                  // * (0 - (-1)) + (-1)
+    return __fadd_rn(v, neg ? r.p_of_zero : r.n_of_zero);               // events + neg (commutative)
+}
+
+// Compile-time view of terms_of(): number of terms of a direction code and the shift of term k.
+__host__ __device__ constexpr int term_count(int direction) { return direction == CMDA_DIR_ALL ? 4 : 2; }
+__host__ __device__ constexpr int term_dir(int direction, int k) {
+    if (direction == CMDA_DIR_ALL) return k == 0 ? 2 : (k == 1 ? 0 : (k == 2 ? 3 : 1));
+    if (k == 0) return (direction == CMDA_DIR_LEFTDOWN || direction == CMDA_DIR_LEFTUP) ? 0 : 1;
+    return (direction == CMDA_DIR_RIGHTUP || direction == CMDA_DIR_LEFTUP) ? 2 : 3;
+}
+
+// Table value of byte J of a packed word: the byte scaled to its 128-byte row of the bank-replicated table and the
+// lane's bank offset merged in by one logic op (shift, and-or, load).
+template <int J>
+__device__ __forceinline__ float lut_of_byte(const float* s_lut, unsigned w, unsigned lane_bytes) {
+    const unsigned row = J == 0 ? (w << 7) : (w >> (8 * J - 7));
+    return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(s_lut) + ((row & 0x7f80u) | lane_bytes));
 }
 
 template <int NT>
@@ -255,32 +277,36 @@ __device__ __forceinline__ ColShift col_shift_of(int c, int W, int delta /* +s: 
     return g;
 }
 
-template <int NT, bool APPLY>
+template <int DIRECTION, bool APPLY>
 __global__ void __launch_bounds__(256)
-isr_vec_kernel(const uint8_t* __restrict__ gray, int S, int H, int W, int shift, TermList terms, LogLut lut_in, float thr,
-               float clip, unsigned* __restrict__ ws, float* __restrict__ out) {
+isr_vec_kernel(const uint8_t* __restrict__ gray, int S, int H, int W, int shift, LogLut lut_in, float thr, float clip,
+               unsigned* __restrict__ ws, float* __restrict__ out) {
+    constexpr int NT = term_count(DIRECTION);
     __shared__ float s_lut[kLutWords];
     load_banked_lut(s_lut, lut_in);
     __syncthreads();
     const int words = W >> 2;
     const int cw = blockIdx.x * 256 + threadIdx.x;
     const int c = cw * 4;
-    const bool live = cw < words;
     const float inv = NT == 4 ? 0.25f : 0.5f;   // x / 4 and x / 2 are exact scalings
     const long long n_rows = static_cast<long long>(S) * H;
     // consecutive rows per CTA: an image's rows stay together (one min/max flush per image)
     const long long per_cta = (n_rows + gridDim.y - 1) / gridDim.y;
     const long long row_begin = per_cta * blockIdx.y, row_end = min(row_begin + per_cta, n_rows);
-    if (row_begin >= row_end) return;
-    ColShift left{}, right{};
-    if (live) { left = col_shift_of(c, W, shift); right = col_shift_of(c, W, -shift); }
+    if (row_begin >= row_end || cw >= words) return;
+    const unsigned lane_bytes = (threadIdx.x & 31u) * 4u;
+    const ColShift left = col_shift_of(c, W, shift), right = col_shift_of(c, W, -shift);
     int img = static_cast<int>(row_begin / H), r = static_cast<int>(row_begin - static_cast<long long>(img) * H);
     int cur_img = -1;
+    // the images are contiguous: row `row` of the batch starts at word row * words
+    const unsigned* row_w = reinterpret_cast<const unsigned*>(gray) + row_begin * words;
+    float4* out4 = APPLY ? reinterpret_cast<float4*>(out) + row_begin * words + cw : nullptr;
+    const long long shift_words = static_cast<long long>(shift) * words;
     TermRange rng[NT];
     MinMaxAcc acc[NT];
 #pragma unroll
     for (int k = 0; k < NT; ++k) acc[k].init();
-    for (long long row = row_begin; row < row_end; ++row) {
+    for (long long row = row_begin; row < row_end; ++row, row_w += words, out4 += APPLY ? words : 0) {
         if (img != cur_img) {
             if (!APPLY && cur_img >= 0) {
                 flush_minmax<NT>(acc, ws + static_cast<size_t>(cur_img) * 16);
@@ -293,42 +319,38 @@ isr_vec_kernel(const uint8_t* __restrict__ gray, int S, int H, int W, int shift,
             }
             cur_img = img;
         }
-        if (live) {
-            const uint8_t* g = gray + static_cast<size_t>(img) * H * W;
-            const uint8_t* grow = g + static_cast<size_t>(r) * W;
-            const unsigned base_w = __ldg(reinterpret_cast<const unsigned*>(grow + c));
-            float base[4], res[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        const unsigned base_w = __ldg(row_w + cw);
+        const float base[4] = {lut_of_byte<0>(s_lut, base_w, lane_bytes), lut_of_byte<1>(s_lut, base_w, lane_bytes),
+                               lut_of_byte<2>(s_lut, base_w, lane_bytes), lut_of_byte<3>(s_lut, base_w, lane_bytes)};
+        float res[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) base[j] = CMDA_LUT((base_w >> (8 * j)) & 255u);
+        for (int k = 0; k < NT; ++k) {
+            const int dir = term_dir(DIRECTION, k);       // a constant once the loop is unrolled
+            unsigned shw;
+            if (dir == 2) {                              // up: rows r < H - s take row r + s (utils.py:131)
+                shw = __ldg(row_w + cw + (r < H - shift ? shift_words : 0));
+            } else if (dir == 3) {                       // down: rows r >= s take row r - s (utils.py:132)
+                shw = __ldg(row_w + cw - (r >= shift ? shift_words : 0));
+            } else {                                     // left (utils.py:129) / right (utils.py:130)
+                const ColShift& cs = dir == 0 ? left : right;
+                const unsigned w0 = __ldg(row_w + (cs.off0 >> 2));
+                const unsigned w1 = __ldg(row_w + (cs.off1 >> 2));
+                shw = (__funnelshift_r(w0, w1, cs.funnel) & cs.mask) | (base_w & ~cs.mask);   // border: unshifted
+            }
+            const float sh[4] = {lut_of_byte<0>(s_lut, shw, lane_bytes), lut_of_byte<1>(s_lut, shw, lane_bytes),
+                                 lut_of_byte<2>(s_lut, shw, lane_bytes), lut_of_byte<3>(s_lut, shw, lane_bytes)};
 #pragma unroll
-            for (int k = 0; k < NT; ++k) {
-                const int dir = terms.dir[k];
-                unsigned shw;
-                if (dir >= 2) {                          // row shift: one aligned word holds the four shifted pixels
-                    int rr = r;
-                    if (dir == 2) { if (r < H - shift) rr = r + shift; }      // up:   utils.py:131
-                    else { if (r >= shift) rr = r - shift; }                  // down: utils.py:132
-                    shw = __ldg(reinterpret_cast<const unsigned*>(g + static_cast<size_t>(rr) * W + c));
+            for (int j = 0; j < 4; ++j) {
+                const float d = __fsub_rn(sh[j], base[j]);                                    // utils.py:92
+                if (APPLY) {
+                    const float tv = __fmul_rn(normalize_term(d, thr, clip, rng[k]), inv);
+                    res[j] = (k == 0) ? tv : __fadd_rn(res[j], tv);                           // utils.py:137 / 151, left to right
                 } else {
-                    const ColShift& cs = dir == 0 ? left : right;             // left: utils.py:129, right: utils.py:130
-                    const unsigned w0 = __ldg(reinterpret_cast<const unsigned*>(grow + cs.off0));
-                    const unsigned w1 = __ldg(reinterpret_cast<const unsigned*>(grow + cs.off1));
-                    shw = (__funnelshift_r(w0, w1, cs.funnel) & cs.mask) | (base_w & ~cs.mask);   // border: unshifted
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float d = __fsub_rn(CMDA_LUT((shw >> (8 * j)) & 255u), base[j]);   // utils.py:92
-                    if (APPLY) {
-                        const float tv = __fmul_rn(normalize_term(d, thr, clip, rng[k]), inv);
-                        res[j] = (k == 0) ? tv : __fadd_rn(res[j], tv);                       // utils.py:137 / 151, left to right
-                    } else {
-                        acc[k].add(d);
-                    }
+                    acc[k].add(d);
                 }
             }
-            if (APPLY) stg_stream_f4(out + static_cast<size_t>(img) * H * W + static_cast<size_t>(r) * W + c,
-                                     make_float4(res[0], res[1], res[2], res[3]));
         }
+        if (APPLY) stg_stream_f4(reinterpret_cast<float*>(out4), make_float4(res[0], res[1], res[2], res[3]));
         if (++r == H) { r = 0; ++img; }
     }
     if (!APPLY && cur_img >= 0) flush_minmax<NT>(acc, ws + static_cast<size_t>(cur_img) * 16);
@@ -346,6 +368,7 @@ pair_minmax_kernel(const uint8_t* __restrict__ now, const uint8_t* __restrict__ 
     const uint8_t* b = front + static_cast<size_t>(img) * npx;
     MinMaxAcc acc[1];
     acc[0].init();
+    const unsigned lane_bytes = (threadIdx.x & 31u) * 4u;
     if (vec) {
         const long long n16 = npx / 16;
         for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n16;
@@ -354,11 +377,12 @@ pair_minmax_kernel(const uint8_t* __restrict__ now, const uint8_t* __restrict__ 
             const uint4 vb = __ldg(reinterpret_cast<const uint4*>(b) + i);
             const unsigned wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    acc[0].add(__fsub_rn(CMDA_LUT((wa[q] >> (8 * j)) & 255u), CMDA_LUT((wb[q] >> (8 * j)) & 255u)));  // :21
-                }
+            for (int q = 0; q < 4; ++q) {                                                        // :21
+                acc[0].add(__fsub_rn(lut_of_byte<0>(s_lut, wa[q], lane_bytes), lut_of_byte<0>(s_lut, wb[q], lane_bytes)));
+                acc[0].add(__fsub_rn(lut_of_byte<1>(s_lut, wa[q], lane_bytes), lut_of_byte<1>(s_lut, wb[q], lane_bytes)));
+                acc[0].add(__fsub_rn(lut_of_byte<2>(s_lut, wa[q], lane_bytes), lut_of_byte<2>(s_lut, wb[q], lane_bytes)));
+                acc[0].add(__fsub_rn(lut_of_byte<3>(s_lut, wa[q], lane_bytes), lut_of_byte<3>(s_lut, wb[q], lane_bytes)));
+            }
         }
     } else {
         for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < npx;
@@ -387,6 +411,7 @@ pair_apply_kernel(const uint8_t* __restrict__ now, const uint8_t* __restrict__ f
     const uint8_t* a = now + static_cast<size_t>(img) * npx;
     const uint8_t* b = front + static_cast<size_t>(img) * npx;
     const TermRange rng = decode_range(ws + static_cast<size_t>(img) * 16, thr, clip);
+    const unsigned lane_bytes = (threadIdx.x & 31u) * 4u;
     float* of = out_f32 ? out_f32 + static_cast<size_t>(img) * npx : nullptr;
     uint8_t* ou = out_u8 ? out_u8 + static_cast<size_t>(img) * npx : nullptr;
     if (VEC) {
@@ -399,12 +424,14 @@ pair_apply_kernel(const uint8_t* __restrict__ now, const uint8_t* __restrict__ f
             unsigned packed[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
+                const float d[4] = {
+                    __fsub_rn(lut_of_byte<0>(s_lut, wa[q], lane_bytes), lut_of_byte<0>(s_lut, wb[q], lane_bytes)),
+                    __fsub_rn(lut_of_byte<1>(s_lut, wa[q], lane_bytes), lut_of_byte<1>(s_lut, wb[q], lane_bytes)),
+                    __fsub_rn(lut_of_byte<2>(s_lut, wa[q], lane_bytes), lut_of_byte<2>(s_lut, wb[q], lane_bytes)),
+                    __fsub_rn(lut_of_byte<3>(s_lut, wa[q], lane_bytes), lut_of_byte<3>(s_lut, wb[q], lane_bytes))};
                 float r[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float d = __fsub_rn(CMDA_LUT((wa[q] >> (8 * j)) & 255u), CMDA_LUT((wb[q] >> (8 * j)) & 255u));
-                    r[j] = normalize_term(d, thr, clip, rng);
-                }
+                for (int j = 0; j < 4; ++j) r[j] = normalize_term(d[j], thr, clip, rng);
                 if (of) stg_stream_f4(of + i * 16 + q * 4, make_float4(r[0], r[1], r[2], r[3]));
                 packed[q] = quantise_u8(r[0]) | (quantise_u8(r[1]) << 8) | (quantise_u8(r[2]) << 16) |
                             (quantise_u8(r[3]) << 24);
@@ -549,13 +576,20 @@ int launch_isr(const uint8_t* gray, int S, int H, int W, int shift, int directio
         long long gy = (148LL * 6 + gx - 1) / gx;          // 6 CTAs of 33 KB shared memory per SM
         if (gy > n_rows) gy = n_rows;
         dim3 grid(gx, static_cast<unsigned>(gy));
-        if (terms.n == 4) {
-            isr_vec_kernel<4, false><<<grid, 256, 0, s>>>(gray, S, H, W, shift, terms, lut, thr, clip, ws, out);
-            isr_vec_kernel<4, true><<<grid, 256, 0, s>>>(gray, S, H, W, shift, terms, lut, thr, clip, ws, out);
-        } else {
-            isr_vec_kernel<2, false><<<grid, 256, 0, s>>>(gray, S, H, W, shift, terms, lut, thr, clip, ws, out);
-            isr_vec_kernel<2, true><<<grid, 256, 0, s>>>(gray, S, H, W, shift, terms, lut, thr, clip, ws, out);
+#define CMDA_ISR_VEC(D)                                                                                          \
+    case D:                                                                                                      \
+        isr_vec_kernel<D, false><<<grid, 256, 0, s>>>(gray, S, H, W, shift, lut, thr, clip, ws, out);             \
+        isr_vec_kernel<D, true><<<grid, 256, 0, s>>>(gray, S, H, W, shift, lut, thr, clip, ws, out);              \
+        break
+        switch (direction) {
+            CMDA_ISR_VEC(CMDA_DIR_RIGHTDOWN);
+            CMDA_ISR_VEC(CMDA_DIR_RIGHTUP);
+            CMDA_ISR_VEC(CMDA_DIR_LEFTDOWN);
+            CMDA_ISR_VEC(CMDA_DIR_LEFTUP);
+            CMDA_ISR_VEC(CMDA_DIR_ALL);
+            default: return CMDA_ERR_BAD_ARG;
         }
+#undef CMDA_ISR_VEC
         CMDA_LAUNCH_CHECK();
         return CMDA_OK;
     }

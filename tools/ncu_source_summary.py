@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Summarise `ncu --page source --csv` of one kernel: executed warp instructions by opcode and the
-hottest SASS lines by stall samples.  usage: ncu_source_summary.py <rep> <kernel-regex> [top]"""
+hottest SASS lines by stall samples.  usage: ncu_source_summary.py <rep> <kernel-regex> [top] [which]
+(`which`: index of the captured launch among those the regex matches, default 0)"""
 import csv
 import subprocess
 import sys
@@ -11,8 +12,9 @@ top = int(sys.argv[3]) if len(sys.argv) > 3 else 25
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", f"regex:{pat}"],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
-# several kernels may follow each other: take the first block
-hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
+# several kernels may follow each other: take the block asked for
+which = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+hdr_i = [i for i, r in enumerate(rows) if r and r[0] == "Address"][which]
 hdr = rows[hdr_i]
 body = []
 for r in rows[hdr_i + 1:]:
