@@ -166,7 +166,9 @@ __device__ __forceinline__ float norm_one(float e, const NormParams& q, bool enf
         // only the part on z's side of zero differs from voxel to voxel; the other one is the
         // per-grid constant computed in make_norm_params (same operations, same bits)
         const bool neg = z < 0.0f;
-        const float part = neg ? neg_part(z, q.clip) : pos_part(z, q.clip);
+        // clamp(z, 0, clip) for z >= 0 and clamp(z, -clip, 0) for z < 0 are both clamp(z, -clip, clip) when clip >= 0
+        const float part = q.clip >= 0.0f ? fminf(fmaxf(z, -q.clip), q.clip)
+                                          : (neg ? neg_part(z, q.clip) : pos_part(z, q.clip));
         float v = div_by_reused(__fsub_rn(part, neg ? q.nmin : q.pmin), neg ? q.nden : q.pden, neg ? q.rnden : q.rpden);
         v = __fadd_rn(__fmul_rn(v, q.final_range), neg ? -q.final_range : 0.0f);         // * (r - 0) + 0 | * (0 - (-r)) + (-r)
         return neg ? __fadd_rn(q.p_of_zero, v) : __fadd_rn(v, q.n_of_zero);
@@ -189,9 +191,20 @@ norm_apply_kernel(const float* raw, float* out, long long V,   // raw may alias 
     const float* r = raw + static_cast<size_t>(s) * V;
     float* o = out + static_cast<size_t>(s) * V;
     if (VEC) {
+        // four independent 16-byte loads in flight per thread before the first is consumed
         const long long n4 = V / 4;
-        for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
-             i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+        long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+        for (; i + 3 * stride < n4; i += 4 * stride) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = reinterpret_cast<const float4*>(r)[i + u * stride];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                stg_stream_f4(o + (i + u * stride) * 4, make_float4(norm_one(v[u].x, q, enforce), norm_one(v[u].y, q, enforce),
+                                                                    norm_one(v[u].z, q, enforce), norm_one(v[u].w, q, enforce)));
+        }
+        for (; i < n4; i += stride) {
             const float4 v = reinterpret_cast<const float4*>(r)[i];
             stg_stream_f4(o + i * 4, make_float4(norm_one(v.x, q, enforce), norm_one(v.y, q, enforce),
                                                  norm_one(v.z, q, enforce), norm_one(v.w, q, enforce)));
