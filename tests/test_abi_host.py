@@ -124,3 +124,37 @@ def test_index_txt_format(tmp_path):
     write_index_txt([-1, 5, 77], str(p))
     assert p.read_text() == "-1\n5\n77\n"
     assert [int(v) for v in np.loadtxt(str(p), dtype=str, encoding="utf-8")] == [-1, 5, 77]
+
+
+def test_bind_to_gpu_numa_is_harmless_without_nvml():
+    """No GPU / NVML here: the affinity helper reports what it did and leaves the process where it was."""
+    import os
+    from cmda_b200.sharding import bind_to_gpu_numa
+    before = os.sched_getaffinity(0)
+    info = bind_to_gpu_numa(0)
+    assert info["bound"] is False and os.sched_getaffinity(0) == before
+    os.environ["CMDA_NO_NUMA_BIND"] = "1"
+    try:
+        assert bind_to_gpu_numa(0) == {"bound": False, "skipped": "CMDA_NO_NUMA_BIND"}
+    finally:
+        del os.environ["CMDA_NO_NUMA_BIND"]
+
+
+def test_reference_arm_line_has_the_contract_keys():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm) on a tiny sample: one JSON line with
+    the contract's keys, the same metric / unit / config as the GPU arm, zero copy bytes."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--events", "20000"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-400:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["metric"] == "voxelized_events_per_s" and line["unit"] == "Mevents/s"
+    assert line["value"] > 0 and line["e2e"] == {"value": line["value"], "unit": "Mevents/s", "h2d_bytes_per_step": 0,
+                                                 "d2h_bytes_per_step": 0}
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and "workload" in line["config"]
