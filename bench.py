@@ -407,9 +407,31 @@ def variants_leg(store, starts, fins, rmap, args, dev, steps=10, warmup=3):
 
 
 # ------------------------------------------------------------------------------------ GPU leg
+class _StdoutGuard:
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL writes its version banner to fd 1 when
+    NCCL_DEBUG is set): everything written to stdout while the guard is active goes to stderr; `emit` writes the
+    line to the real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self._real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self._real, (text + "\n").encode())
+
+    def close(self):
+        sys.stdout.flush()
+        os.dup2(self._real, 1)
+        os.close(self._real)
+
+
 def run_gpu(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
+
+    guard = _StdoutGuard()
 
     import cmda_b200
     from cmda_b200 import _lib
@@ -579,9 +601,10 @@ def run_gpu(args, rank, local_rank, world):
             "roofline": roofline, "cpu_baseline": cpu, "pseudo_events": pseudo, "train_step_input_path": c5,
             "variants": variants,
         }
-        print(json.dumps(line), flush=True)
+        guard.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    guard.close()
 
 
 def main():
