@@ -28,7 +28,8 @@ class DSECEvents:
     def __init__(self, t, x, y, p, rectify_map, images_to_events_index, events_num=-1, events_bins=5,
                  events_clip_range=None, crop_size=(400, 400), after_crop_resize_size=(512, 512),
                  image_change_range=1, outputs={'events_vg', 'image'}, output_num=1, events_bins_5_avg_1=False,
-                 enforce_3_channels=True, device=None, mode="auto", fused_augment=True):
+                 enforce_3_channels=True, device=None, mode="auto", fused_augment=True, isr_parms='',
+                 shift_type='rightdown', isr_type='real_time'):
         self.events_num = events_num
         self.events_bins = events_bins
         self.events_bins_5_avg_1 = events_bins_5_avg_1
@@ -48,6 +49,14 @@ class DSECEvents:
         self.events_width = 640                                # dsec.py:161
         self.rectify_events = True                             # dsec.py:167
         self.enforce_3_channels = enforce_3_channels
+        self.isr_type = isr_type
+        assert self.isr_type in {'raw', 'denoised', 'real_time'}           # dsec.py:175
+        self.image_change_parms = {'val_range': (1, 10 ** 2), '_threshold': 0.04, '_clip_range': 0.2, 'shift_pixel': 3}
+        if isr_parms != '':                                                # dsec.py:178-181
+            assert isinstance(isr_parms, dict)
+            self.image_change_parms = isr_parms
+        self.shift_type = shift_type
+        assert self.shift_type in {'all', 'random', 'rightdown'}           # dsec.py:183
         self.images_to_events_index = [int(v) for v in images_to_events_index]
         self.mode = mode
         self.fused_augment = fused_augment     # crop / flip / resize / repeat inside the normaliser kernel (one launch less,
@@ -97,6 +106,39 @@ class DSECEvents:
         clip = self._clip_for(events_finish_index, events_start_index)
         return events_vg_batch(self.store, [events_start_index], [events_finish_index], self.events_bins, [clip],
                                mode=self.mode)[0]
+
+    # ---- dsec.py:228-262 -------------------------------------------------------------
+    def warp_img_self_res(self, warp_image, crop_xy=None, flip_flag=False):
+        """The ``'warp_img_self_res'`` entry of ``__getitem__`` for ``isr_type='real_time'`` (dsec.py:252-262): the
+        warp image (uint8 RGB ``[H, W, 3]``; array, tensor or PIL) is cropped at ``crop_xy``, flipped and resized with
+        PIL's BILINEAR in train mode (dsec.py:229-233), then ``get_image_change_from_pil`` with the shift direction of
+        ``shift_type`` (``'random'``: ``direct[x % 2][y % 2]``, dsec.py:253-255) and ``repeat(3, 1, 1)``.  Everything
+        after the upload runs on the device; returns a CUDA float32 ``[3 or 1, h, w]`` tensor.  The ``'raw'`` /
+        ``'denoised'`` types read precomputed PNGs (file I/O) and stay with the caller."""
+        from .image_change import _to_u8_cuda, get_image_change_from_pil, pil_resize_bilinear
+        if self.isr_type != 'real_time':
+            raise NotImplementedError("isr_type 'raw' / 'denoised' read precomputed images (dsec.py:237-250)")
+        if hasattr(warp_image, "convert"):
+            warp_image = np.asarray(warp_image.convert('RGB'))
+        img = _to_u8_cuda(warp_image, self.store.device)
+        assert img.ndim == 3 and img.shape[2] == 3
+        x, y = crop_xy if crop_xy is not None else (None, None)
+        if 'label' not in self.outputs:                                    # train-time augmentation, dsec.py:229-233
+            assert crop_xy is not None
+            img = img[y: y + self.crop_size[1], x: x + self.crop_size[0]]
+            if flip_flag:
+                img = img.flip(1)
+            img = pil_resize_bilinear(img.contiguous()[None], self.after_crop_resize_size)[0]
+        if self.shift_type == 'random':                                    # dsec.py:253-255
+            direct = [['leftdown', 'leftup'], ['rightdown', 'rightup']]
+            this_shift_direction = direct[x % 2][y % 2]
+        else:
+            this_shift_direction = self.shift_type
+        res = get_image_change_from_pil(img, width=int(img.shape[1]), height=int(img.shape[0]),
+                                        shift_direction=this_shift_direction, **self.image_change_parms)
+        if self.enforce_3_channels and res.shape[0] == 1:                  # dsec.py:259-260
+            res = res.repeat(3, 1, 1)
+        return res
 
     # ---- dsec.py:286-320 -------------------------------------------------------------
     def events_vg_for_image(self, now_image_index, crop_xy=None, flip_flag=False):

@@ -764,6 +764,39 @@ def test_dsec_events_from_timestamps(cm):
     np.testing.assert_allclose(item[0].cpu().numpy(), ref[0, :440], rtol=0, atol=1e-5)
 
 
+@pytest.mark.parametrize("shift_type,crop_xy,flip", [("random", (37, 61), True), ("random", (140, 20), False), ("rightdown", (3, 4), False),
+                                                      ("all", (0, 0), True)])
+def test_dsec_warp_img_self_res(cm, shift_type, crop_xy, flip):
+    """The real-time ISR entry of DSECDataset.__getitem__ (dsec.py:228-262) on the device against PIL (crop,
+    FLIP_LEFT_RIGHT, resize BILINEAR) + the oracle's get_image_change_from_pil: bit-exact, train and test mode."""
+    from PIL import Image
+    from cmda_b200 import synth
+    rng = np.random.default_rng(11)
+    t, x, y, p = synth.make_events(1000, 480, 640, seed=1)
+    rmap = synth.make_rectify_map(480, 640, seed=2)
+    ys, xs = np.mgrid[0:480, 0:640]
+    rgb = np.stack([(xs * 0.3 + ys * 0.2) % 256, (xs * 0.1 + 40 * np.sin(ys / 17.0) + 128) % 256, (ys * 0.5) % 256], axis=-1)
+    rgb = np.clip(rgb + rng.normal(0, 6, size=rgb.shape), 0, 255).astype(np.uint8)
+    parms = {'val_range': (0.01, 1.01), '_threshold': 0.005, '_clip_range': 0.1, 'shift_pixel': 1}    # shipped cs2dsec isr_parms
+    ds = cm.DSECEvents(t, x, y, p, rmap, [0, 999], events_bins=1, isr_parms=parms, shift_type=shift_type, device="cuda:0")
+    got = ds.warp_img_self_res(rgb, crop_xy=crop_xy, flip_flag=flip)
+    pil = Image.fromarray(rgb, mode="RGB").crop(box=(crop_xy[0], crop_xy[1], crop_xy[0] + 400, crop_xy[1] + 400))
+    if flip:
+        pil = pil.transpose(Image.FLIP_LEFT_RIGHT)
+    pil = pil.resize(size=(512, 512), resample=Image.BILINEAR)
+    direction = [['leftdown', 'leftup'], ['rightdown', 'rightup']][crop_xy[0] % 2][crop_xy[1] % 2] if shift_type == "random" else shift_type
+    ref = O.get_image_change_from_pil(pil, 512, 512, shift_direction=direction, **parms)
+    assert got.is_cuda and got.shape == (3, 512, 512)
+    for c in range(3):
+        assert np.array_equal(bits(got[c]), bits(ref[0]))
+    # test mode: the full image, no augmentation, default parameters (dsec.py:177)
+    dt = cm.DSECEvents(t, x, y, p, rmap, [0, 999], events_bins=1, outputs={'events_vg', 'label'}, device="cuda:0")
+    got = dt.warp_img_self_res(Image.fromarray(rgb, mode="RGB"))
+    ref = O.get_image_change_from_pil(rgb, 640, 480, shift_pixel=3, val_range=(1, 100), _threshold=0.04, _clip_range=0.2,
+                                      shift_direction='rightdown')
+    assert got.shape == (3, 480, 640) and np.array_equal(bits(got[1]), bits(ref[0]))
+
+
 def test_dsec_events_from_cache(cm, tmp_path):
     """f-3: a sequence written once in the decoded cache format and streamed back from the memory-mapped files gives
     the same object (index table, windows, grids bit for bit) as the arrays it was written from; the chunked
