@@ -82,8 +82,9 @@ class HostEventsPipeline:
                                                   _lib.VOXEL_MODES[self.mode])
         self._ws = torch.empty((nbytes,), dtype=torch.uint8, device=self.device)
 
-    def __call__(self, starts, finishes, clip_ranges=None, out=None):
+    def __call__(self, starts, finishes, clip_ranges=None, out=None, map_ids=None):
         """Inclusive windows ``[start, finish]`` -> pinned host tensor ``[S, B, H, W]``.
+        ``map_ids[s]`` selects the rectify map of window ``s`` when several were given.
         Returns after the last device->host copy has completed."""
         L = _lib.lib()
         starts = np.ascontiguousarray(starts, dtype=np.int64)
@@ -91,6 +92,9 @@ class HostEventsPipeline:
         S = int(starts.shape[0])
         if S and (starts.min() < 0 or ends.max() > self.n_total):
             raise IndexError("event window outside the store")
+        mids = None if map_ids is None else np.ascontiguousarray(map_ids, dtype=np.int32)
+        if mids is not None and S and (self.rmap is None or mids.min() < 0 or mids.max() >= self.rmap.shape[0]):
+            raise IndexError("map id outside the rectify maps of the pipeline")
         if out is None:
             out = torch.empty((S, self.B, self.H, self.W), dtype=torch.float32).pin_memory()
         assert out.is_pinned() and out.shape == (S, self.B, self.H, self.W)
@@ -123,12 +127,13 @@ class HostEventsPipeline:
                                  dtype=np.float32)
                 hs = np.array(d_starts, dtype=np.int64)
                 he = np.array(d_ends, dtype=np.int64)
+                hm = None if mids is None else np.ascontiguousarray(mids[g[0]:g[0] + len(g)])
                 self.compute.wait_event(slot["ready"])
                 with torch.cuda.stream(self.compute):
                     ev = slot["ev"]
                     _lib.check(L.cmda_events_vg_batch_planned(
                         _lib.ptr(ev[0]), _lib.ptr(ev[1]), _lib.ptr(ev[2]), _lib.ptr(ev[3]), _lib.host_ptr(hs),
-                        _lib.host_ptr(he), len(g), _lib.ptr(self.rmap), None, self.H, self.W, self.B,
+                        _lib.host_ptr(he), len(g), _lib.ptr(self.rmap), _lib.host_ptr(hm), self.H, self.W, self.B,
                         _lib.host_ptr(clips), 1.0, 1, 1, _lib.ptr(slot["out"]), None, None, _lib.ptr(self._ws),
                         self._ws.numel(), mode_id, _lib.ptr(self.plans), self.compute.cuda_stream),
                         "cmda_events_vg_batch_planned")

@@ -503,6 +503,34 @@ def test_events_vg_randomised_differential(cm, seed):
                 assert np.array_equal(bits(raw[s]), bits(g))
 
 
+@pytest.mark.parametrize("group,bins", [(1, 5), (3, 1), (4, 5)])
+def test_host_events_pipeline_matches_device_path(cm, group, bins):
+    """The host-buffer front door (pinned SoA in, pinned grids out, three streams, double-buffered slots) gives the
+    device-resident path's bits: ragged windows, an empty one, unaligned starts, two maps, more groups than slots."""
+    from cmda_b200 import synth
+    from cmda_b200.pipeline import HostEventsPipeline
+    H, W = 480, 640
+    n = 120_000
+    t, x, y, p = synth.make_events(n, H, W, seed=77)
+    maps = np.stack([synth.make_rectify_map(H, W, seed=5), synth.make_rectify_map(H, W, seed=6)])
+    starts = np.array([0, 10_001, 30_000, 30_007, 55_555, 90_000, 90_001, 119_000, 64, 1])
+    fins = np.array([9_999, 29_998, 30_006, 55_000, 89_999, 89_999, 118_999, 119_999, 127, 119_998])   # one empty window
+    mids = [0, 1, 1, 0, 1, 0, 0, 1, 1, 0]
+    store = cm.EventStore(t, x, y, p, maps, height=H, width=W, device="cuda:0")
+    ref = cm.events_vg_batch(store, starts, fins, bins, map_ids=mids)
+    pipe = HostEventsPipeline(t, x, y, p, maps, bins, H, W, device="cuda:0", windows_per_group=group)
+    got = pipe(starts, fins, map_ids=mids)
+    assert got.is_pinned() and got.shape == ref.shape
+    assert torch.equal(got, ref.cpu())
+    again = pipe(starts[::-1].copy(), fins[::-1].copy(), map_ids=mids[::-1])      # reuse of slots and workspace
+    assert torch.equal(again, ref.cpu().flip(0))
+    assert pipe.bytes_per_call(starts, fins) == (9 * int(np.clip(fins + 1 - starts, 0, None).sum()), 4 * 10 * bins * H * W)
+    with pytest.raises(IndexError):
+        pipe([0], [n])
+    with pytest.raises(IndexError):
+        pipe([0], [10], map_ids=[2])
+
+
 def test_abi_error_codes_on_device(cm):
     """The C ABI never throws: bad workspaces, unknown modes and unsupported shapes come back as CMDA_ERR_* codes,
     and AUTO falls back to GLOBAL where FACTORED does not apply (B > 24)."""
