@@ -531,6 +531,50 @@ def test_host_events_pipeline_matches_device_path(cm, group, bins):
         pipe([0], [10], map_ids=[2])
 
 
+@pytest.mark.parametrize("mode", ["global", "tiled", "factored"])
+def test_events_vg_many_windows_and_maps(cm, mode):
+    """More windows than one launch group holds (64) and more distinct maps than one FACTORED group builds plans for
+    (8): the group loop's offsets into the outputs, the per-bin counts, the statistics partials and the per-group plan
+    slots, with and without prebuilt plans, against the oracle window by window."""
+    from cmda_b200 import synth
+    H, W, B, S, n_maps = 40, 56, 3, 150, 11
+    rng = np.random.default_rng(99)
+    n = 30_000
+    t, x, y, p = synth.make_events(n, H, W, seed=31)
+    maps = np.stack([synth.make_rectify_map(H, W, seed=200 + k) for k in range(n_maps)])
+    starts = np.sort(rng.integers(0, n - 400, size=S))
+    fins = starts + rng.integers(0, 400, size=S)
+    fins[7] = starts[7] - 1                                  # an empty window in the first group
+    fins[100] = starts[100]                                  # a single-event window in the second
+    mids = rng.integers(0, n_maps, size=S)
+    mids[:12] = np.arange(12) % n_maps                       # > 8 distinct maps inside the first windows
+    refs = []
+    for s in range(S):
+        sl = slice(int(starts[s]), int(fins[s]) + 1)
+        if fins[s] < starts[s]:
+            refs.append((np.zeros((B, H, W), np.float32), dict(abs_weight_sum=np.zeros((B, H, W)), n_contrib=np.zeros((B, H, W)),
+                                                               bin_counts=np.zeros(B, np.int64))))
+            continue
+        tf, xf, yf, pf = O.rectify_events(t[sl], x[sl], y[sl], p[sl], maps[mids[s]])
+        refs.append(O.events_to_voxel_grid(tf, xf, yf, pf, W, H, B, return_aux=True))
+    outs = []
+    for plan in (False, True):
+        store = cm.EventStore(t, x, y, p, maps, height=H, width=W, device="cuda:0", plan=plan)
+        raw, counts = cm.events_vg_batch(store, starts, fins, B, map_ids=mids, mode=mode, normalize=False, return_bin_counts=True)
+        norm = cm.events_vg_batch(store, starts, fins, B, map_ids=mids, mode=mode)
+        for s in range(S):
+            g, aux = refs[s]
+            assert_raw_close(raw[s], g, aux["abs_weight_sum"], aux["n_contrib"])
+            assert np.array_equal(counts[s].cpu().numpy(), aux["bin_counts"]), (mode, s)
+        for s in (0, 7, 63, 64, 100, 128, 149):
+            if fins[s] > starts[s]:
+                clip = O.default_clip_range(int(fins[s]), int(starts[s]))
+                ref_n = O.events_norm(refs[s][0].copy(), clip, 1.0, True)
+                check_normalised(norm[s], raw[s], ref_n, refs[s][0], clip)
+        outs.append((raw, norm))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])      # per-call plans == prebuilt plans
+
+
 def test_abi_error_codes_on_device(cm):
     """The C ABI never throws: bad workspaces, unknown modes and unsupported shapes come back as CMDA_ERR_* codes,
     and AUTO falls back to GLOBAL where FACTORED does not apply (B > 24)."""
