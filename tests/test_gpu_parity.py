@@ -531,6 +531,32 @@ def test_host_events_pipeline_matches_device_path(cm, group, bins):
         pipe([0], [10], map_ids=[2])
 
 
+def test_events_vg_fused_augment_many_windows(cm):
+    """The augmented entry point past one launch group (70 windows, per-window crop origins / flips / maps): the
+    per-group augmentation table and raw-grid offsets, against the unfused path + the oracle's post-voxel stage."""
+    from cmda_b200 import synth
+    H, W, B, S = 40, 56, 2, 70
+    rng = np.random.default_rng(123)
+    n = 20_000
+    t, x, y, p = synth.make_events(n, H, W, seed=41)
+    maps = np.stack([synth.make_rectify_map(H, W, seed=300 + k) for k in range(3)])
+    store = cm.EventStore(t, x, y, p, maps, height=H, width=W, device="cuda:0")
+    starts = np.sort(rng.integers(0, n - 500, size=S))
+    fins = starts + rng.integers(50, 500, size=S)
+    mids = rng.integers(0, 3, size=S)
+    crop_size, out_size = (24, 20), (32, 28)                    # (w, h)
+    xy = [(int(rng.integers(0, W - 24 + 1)), int(rng.integers(0, H - 20 + 1))) for _ in range(S)]
+    flips = [int(v) for v in rng.integers(0, 2, size=S)]
+    got = cm.events_vg_augmented_batch(store, starts, fins, B, crop_xy=xy, crop_size=crop_size, out_size=out_size, flips=flips,
+                                       repeat=3, map_ids=mids)
+    grid = cm.events_vg_batch(store, starts, fins, B, map_ids=mids)
+    assert got.shape == (S, 3 * B, 28, 32)
+    for s in range(S):
+        exp = O.events_vg_post(grid[s].cpu().numpy(), crop_xy=xy[s], crop_size=crop_size, out_size=out_size,
+                               flip_flag=bool(flips[s]), avg_bins=False, enforce_3_channels=True, test_mode=False)
+        np.testing.assert_allclose(got[s].cpu().numpy(), exp, rtol=0, atol=1e-5, err_msg=f"window {s}")
+
+
 @pytest.mark.parametrize("mode", ["global", "tiled", "factored"])
 def test_events_vg_many_windows_and_maps(cm, mode):
     """More windows than one launch group holds (64) and more distinct maps than one FACTORED group builds plans for
