@@ -277,6 +277,38 @@ __device__ __forceinline__ ColShift col_shift_of(int c, int W, int delta /* +s: 
     return g;
 }
 
+// The packed words one thread needs for its four pixels of one row: its own word and, per term, the word `shift`
+// rows above / below or the two aligned words that hold the columns `shift` to the left / right.  Loaded one row
+// ahead of their use so that the L2 latency of row r + 1 hides behind the arithmetic of row r.
+template <int DIRECTION>
+struct IsrRowWords {
+    unsigned base;
+    unsigned a[term_count(DIRECTION)], b[term_count(DIRECTION)];     // b only for the column-shift terms
+};
+template <int DIRECTION>
+__device__ __forceinline__ IsrRowWords<DIRECTION> isr_load_row(const unsigned* __restrict__ row_w, int cw, int r, int H, int shift,
+                                                               long long shift_words, const ColShift& left,
+                                                               const ColShift& right) {
+    IsrRowWords<DIRECTION> w;
+    w.base = __ldg(row_w + cw);
+#pragma unroll
+    for (int k = 0; k < term_count(DIRECTION); ++k) {
+        const int dir = term_dir(DIRECTION, k);
+        if (dir == 2) {                              // up: rows r < H - s take row r + s (utils.py:131)
+            w.a[k] = __ldg(row_w + cw + (r < H - shift ? shift_words : 0));
+            w.b[k] = 0u;
+        } else if (dir == 3) {                       // down: rows r >= s take row r - s (utils.py:132)
+            w.a[k] = __ldg(row_w + cw - (r >= shift ? shift_words : 0));
+            w.b[k] = 0u;
+        } else {                                     // left (utils.py:129) / right (utils.py:130)
+            const ColShift& cs = dir == 0 ? left : right;
+            w.a[k] = __ldg(row_w + (cs.off0 >> 2));
+            w.b[k] = __ldg(row_w + (cs.off1 >> 2));
+        }
+    }
+    return w;
+}
+
 template <int DIRECTION, bool APPLY>
 __global__ void __launch_bounds__(256)
 isr_vec_kernel(const uint8_t* __restrict__ gray, int S, int H, int W, int shift, LogLut lut_in, float thr, float clip,
@@ -306,7 +338,11 @@ isr_vec_kernel(const uint8_t* __restrict__ gray, int S, int H, int W, int shift,
     MinMaxAcc acc[NT];
 #pragma unroll
     for (int k = 0; k < NT; ++k) acc[k].init();
+    IsrRowWords<DIRECTION> cur = isr_load_row<DIRECTION>(row_w, cw, r, H, shift, shift_words, left, right);
     for (long long row = row_begin; row < row_end; ++row, row_w += words, out4 += APPLY ? words : 0) {
+        const int r_next = r + 1 == H ? 0 : r + 1;
+        IsrRowWords<DIRECTION> nxt = cur;
+        if (row + 1 < row_end) nxt = isr_load_row<DIRECTION>(row_w + words, cw, r_next, H, shift, shift_words, left, right);
         if (img != cur_img) {
             if (!APPLY && cur_img >= 0) {
                 flush_minmax<NT>(acc, ws + static_cast<size_t>(cur_img) * 16);
@@ -319,23 +355,17 @@ isr_vec_kernel(const uint8_t* __restrict__ gray, int S, int H, int W, int shift,
             }
             cur_img = img;
         }
-        const unsigned base_w = __ldg(row_w + cw);
+        const unsigned base_w = cur.base;
         const float base[4] = {lut_of_byte<0>(s_lut, base_w, lane_bytes), lut_of_byte<1>(s_lut, base_w, lane_bytes),
                                lut_of_byte<2>(s_lut, base_w, lane_bytes), lut_of_byte<3>(s_lut, base_w, lane_bytes)};
         float res[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
         for (int k = 0; k < NT; ++k) {
             const int dir = term_dir(DIRECTION, k);       // a constant once the loop is unrolled
-            unsigned shw;
-            if (dir == 2) {                              // up: rows r < H - s take row r + s (utils.py:131)
-                shw = __ldg(row_w + cw + (r < H - shift ? shift_words : 0));
-            } else if (dir == 3) {                       // down: rows r >= s take row r - s (utils.py:132)
-                shw = __ldg(row_w + cw - (r >= shift ? shift_words : 0));
-            } else {                                     // left (utils.py:129) / right (utils.py:130)
+            unsigned shw = cur.a[k];
+            if (dir < 2) {                                // column shift: funnel the two words, border bytes stay unshifted
                 const ColShift& cs = dir == 0 ? left : right;
-                const unsigned w0 = __ldg(row_w + (cs.off0 >> 2));
-                const unsigned w1 = __ldg(row_w + (cs.off1 >> 2));
-                shw = (__funnelshift_r(w0, w1, cs.funnel) & cs.mask) | (base_w & ~cs.mask);   // border: unshifted
+                shw = (__funnelshift_r(cur.a[k], cur.b[k], cs.funnel) & cs.mask) | (base_w & ~cs.mask);
             }
             const float sh[4] = {lut_of_byte<0>(s_lut, shw, lane_bytes), lut_of_byte<1>(s_lut, shw, lane_bytes),
                                  lut_of_byte<2>(s_lut, shw, lane_bytes), lut_of_byte<3>(s_lut, shw, lane_bytes)};
@@ -351,7 +381,9 @@ isr_vec_kernel(const uint8_t* __restrict__ gray, int S, int H, int W, int shift,
             }
         }
         if (APPLY) stg_stream_f4(reinterpret_cast<float*>(out4), make_float4(res[0], res[1], res[2], res[3]));
-        if (++r == H) { r = 0; ++img; }
+        cur = nxt;
+        r = r_next;
+        if (r == 0) ++img;
     }
     if (!APPLY && cur_img >= 0) flush_minmax<NT>(acc, ws + static_cast<size_t>(cur_img) * 16);
 }
