@@ -354,16 +354,17 @@ def variants_leg(store, starts, fins, rmap, args, dev, steps=10, warmup=3):
     import cmda_b200
     from cmda_b200 import synth
 
-    def timed(st, s0, f0, bins, **kw):
+    def timed(st, s0, f0, bins, mode=None, **kw):
+        mode = mode or args.mode
         s0, f0 = np.asarray(s0, dtype=np.int64), np.asarray(f0, dtype=np.int64)
         out = torch.empty((len(s0), bins, H, W), dtype=torch.float32, device=dev)
         for _ in range(warmup):
-            cmda_b200.events_vg_batch(st, s0, f0, bins, mode=args.mode, out=out, **kw)
+            cmda_b200.events_vg_batch(st, s0, f0, bins, mode=mode, out=out, **kw)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(dev)
         e0.record()
         for _ in range(steps):
-            cmda_b200.events_vg_batch(st, s0, f0, bins, mode=args.mode, out=out, **kw)
+            cmda_b200.events_vg_batch(st, s0, f0, bins, mode=mode, out=out, **kw)
         e1.record()
         torch.cuda.synchronize(dev)
         ms = e0.elapsed_time(e1) / steps
@@ -375,6 +376,11 @@ def variants_leg(store, starts, fins, rmap, args, dev, steps=10, warmup=3):
     S = len(starts)
     if args.bins != 1:
         res["C2_bins_1"] = timed(store, starts, fins, 1)
+    if args.mode in ("auto", "factored"):
+        # the opt-in BANDED stage A (band partition + shared-memory accumulation instead of one L2 atomic per event;
+        # bit-identical output): the same step, for the record
+        res["C2_banded_stage_A"] = timed(store, starts, fins, args.bins, mode="banded")
+        res["C2_bins_1_banded_stage_A"] = timed(store, starts, fins, 1, mode="banded")
     maps = np.stack([rmap] + [synth.make_rectify_map(H, W, seed=synth.seed_for(2, 900 + k)) for k in range(4)])
     store5 = cmda_b200.EventStore(store.t, store.x, store.y, store.p, maps, height=H, width=W, device=dev, plan=False)
     res["C2_five_maps"] = timed(store5, starts, fins, args.bins, map_ids=[s % 5 for s in range(S)])
@@ -550,6 +556,11 @@ def run_gpu(args, rank, local_rank, world):
             names = ["memset(sensor grid)", "rectify_index_{build,sort}+stencil_build+out_tile_box kernels",
                      "sensor_accumulate_kernel", "rectify_gather+regroup_partials kernels", "norm_apply_kernel"]
             launches_per_step = 8   # kernels only (memsets not counted)
+        elif resolved == _lib.VOXEL_BANDED:
+            names = ["memset(none: every sensor-grid cell is stored)", "rectify_index_{build,sort}+stencil_build+out_tile_box kernels",
+                     "band_partition_kernel", "band_accumulate_kernel", "rectify_gather+regroup_partials kernels",
+                     "norm_apply_kernel"]
+            launches_per_step = 9
         else:
             names = ["memset(int64 grid)", "tile_bbox+tile_count+tile_scan kernels", "tile_partition_kernel",
                      "tile_accumulate_kernel", "convert_stats_kernel", "norm_apply_kernel"]
@@ -615,7 +626,7 @@ def main():
     ap.add_argument("--impl", default="cmda_b200", choices=["cmda_b200", "reference"])
     ap.add_argument("--bins", type=int, default=5)
     ap.add_argument("--events", type=int, default=EVENTS_PER_WINDOW)
-    ap.add_argument("--mode", default="auto", choices=["auto", "global", "tiled", "factored"])
+    ap.add_argument("--mode", default="auto", choices=["auto", "global", "tiled", "factored", "banded"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pseudo", action="store_true", help="skip the pseudo-event (config C3) leg")
     ap.add_argument("--no-variants", action="store_true", help="skip the other device-resident cases of SURVEY.md 8(d)")

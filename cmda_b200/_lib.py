@@ -14,13 +14,14 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcmda_b200.so")
+# CMDA_B200_LIB points at another build of the same ABI (kernel-shape sweeps: tools/build_variant.sh)
+LIB_PATH = os.environ.get("CMDA_B200_LIB") or os.path.join(_HERE, "libcmda_b200.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 OK = 0
-VOXEL_GLOBAL, VOXEL_TILED, VOXEL_AUTO, VOXEL_EXACT, VOXEL_FACTORED = 0, 1, 2, 3, 4
+VOXEL_GLOBAL, VOXEL_TILED, VOXEL_AUTO, VOXEL_EXACT, VOXEL_FACTORED, VOXEL_BANDED = 0, 1, 2, 3, 4, 5
 VOXEL_MODES = {"global": VOXEL_GLOBAL, "tiled": VOXEL_TILED, "auto": VOXEL_AUTO, "exact": VOXEL_EXACT,
-               "factored": VOXEL_FACTORED}
+               "factored": VOXEL_FACTORED, "banded": VOXEL_BANDED}
 VOXEL_MODE_NAMES = {v: k for k, v in VOXEL_MODES.items()}
 DIRECTIONS = {"rightdown": 0, "rightup": 1, "leftdown": 2, "leftup": 3, "all": 4}
 

@@ -37,7 +37,9 @@ int factored_max_maps(void);
 size_t factored_plan_bytes(int H, int W);
 int launch_plan_build(const float*, int, int, int, void*, cudaStream_t);
 int launch_factored(const uint32_t*, const uint16_t*, const uint16_t*, const uint8_t*, const WindowTable&, int, long long,
-                    const float*, int, int, int, void*, int64_t*, float*, PartialStats*, void*, size_t, const void*, cudaStream_t);
+                    const float*, int, int, int, void*, int64_t*, float*, PartialStats*, void*, size_t, const void*, int, cudaStream_t);
+int banded_supported(int H, int W, int B);
+size_t banded_scratch_bytes(long long total_events, int group, int H, int W, int B);
 int exact_supported(int H, int W, int B);
 size_t exact_workspace_bytes(long long max_window_events);
 int launch_exact_raw(const uint32_t*, const uint16_t*, const uint16_t*, const uint8_t*, const WindowTable&, int, const float*, int,
@@ -124,7 +126,7 @@ int cmda_images_to_events_index(const uint32_t* d_t, int64_t n, const int64_t* d
 
 int cmda_events_vg_resolved_mode(int64_t total_events, int S, int H, int W, int B, int mode) {
     if (S <= 0 || H <= 0 || W <= 0 || B <= 0 || total_events < 0) return CMDA_ERR_BAD_ARG;
-    if (mode < CMDA_VOXEL_GLOBAL || mode > CMDA_VOXEL_FACTORED) return CMDA_ERR_BAD_ARG;
+    if (mode < CMDA_VOXEL_GLOBAL || mode > CMDA_VOXEL_BANDED) return CMDA_ERR_BAD_ARG;
     return resolve_mode(mode, total_events, S, H, W, B);
 }
 
@@ -135,6 +137,8 @@ size_t cmda_events_vg_workspace_bytes(int64_t total_events, int S, int H, int W,
     if (mode == CMDA_VOXEL_TILED && tiled_supported(H, W, B)) need += tiled_workspace_bytes(total_events, S, H, W, B);
     if ((mode == CMDA_VOXEL_FACTORED || mode == CMDA_VOXEL_AUTO) && factored_supported(H, W, B))
         need += factored_scratch_bytes(group, H, W, B);
+    if (mode == CMDA_VOXEL_BANDED && banded_supported(H, W, B))
+        need += factored_scratch_bytes(group, H, W, B) + 256 + banded_scratch_bytes(total_events, group, H, W, B);
     if (mode == CMDA_VOXEL_EXACT) need += exact_workspace_bytes(total_events);    // total_events bounds the largest window
     return need + 256;
 }
@@ -157,7 +161,7 @@ int events_vg_impl(const uint32_t* d_t, const uint16_t* d_x, const uint16_t* d_y
     if (S == 0) return CMDA_OK;
     if (!d_t || !d_x || !d_y || !d_p || !h_win_start || !h_win_end || !d_out || !d_workspace) return CMDA_ERR_BAD_ARG;
     if (normalize && !h_clip) return CMDA_ERR_BAD_ARG;
-    if (mode < CMDA_VOXEL_GLOBAL || mode > CMDA_VOXEL_FACTORED) return CMDA_ERR_BAD_ARG;
+    if (mode < CMDA_VOXEL_GLOBAL || mode > CMDA_VOXEL_BANDED) return CMDA_ERR_BAD_ARG;
     if (reinterpret_cast<uintptr_t>(d_workspace) & 255) return CMDA_ERR_WORKSPACE;
     long long total = 0;
     for (int s = 0; s < S; ++s) {
@@ -185,6 +189,8 @@ int events_vg_impl(const uint32_t* d_t, const uint16_t* d_x, const uint16_t* d_y
     if (use_mode == CMDA_VOXEL_TILED && !tiled_supported(H, W, B)) return CMDA_ERR_UNSUPPORTED;
     if (use_mode == CMDA_VOXEL_FACTORED && !factored_supported(H, W, B)) return CMDA_ERR_UNSUPPORTED;
     if (use_mode == CMDA_VOXEL_EXACT && !exact_supported(H, W, B)) return CMDA_ERR_UNSUPPORTED;
+    if (use_mode == CMDA_VOXEL_BANDED && !banded_supported(H, W, B)) return CMDA_ERR_UNSUPPORTED;
+    const bool factored_like = use_mode == CMDA_VOXEL_FACTORED || use_mode == CMDA_VOXEL_BANDED;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long V = static_cast<long long>(B) * H * W;
 
@@ -198,7 +204,7 @@ int events_vg_impl(const uint32_t* d_t, const uint16_t* d_x, const uint16_t* d_y
         // a launch group: at most kMaxWindows windows and, for FACTORED, at most factored_max_maps()
         // distinct rectify maps (one inverse index each)
         sn = (S - s0) < kMaxWindows ? (S - s0) : kMaxWindows;
-        if (use_mode == CMDA_VOXEL_FACTORED && h_map_id && d_rectify_map && !d_plans) {
+        if (factored_like && h_map_id && d_rectify_map && !d_plans) {
             int ids[kMaxWindows], n_ids = 0, k = 0;
             for (; k < sn; ++k) {
                 const int id = h_map_id[s0 + k];
@@ -246,10 +252,11 @@ int events_vg_impl(const uint32_t* d_t, const uint16_t* d_x, const uint16_t* d_y
         int rc;
         phase_mark(st);
         long long* acc = reinterpret_cast<long long*>(scratch);
-        if (use_mode == CMDA_VOXEL_FACTORED) {
+        if (factored_like) {
             const size_t ab = acc_bytes(sn, H, W, B);
             rc = launch_factored(d_t, d_x, d_y, d_p, tab, sn, max_events, d_rectify_map, H, W, B, acc, bins_g, raw_g,
-                                 part_g, scratch + ab, scratch_bytes - ab, d_plans, st);   // marks: memset | plans | accumulate
+                                 part_g, scratch + ab, scratch_bytes - ab, d_plans, use_mode == CMDA_VOXEL_BANDED,
+                                 st);   // marks: memset | plans | accumulate
             if (rc != CMDA_OK) return rc;
             phase_mark(st);
             if (normalize) {
@@ -359,12 +366,12 @@ int cmda_voxel_grid_f32(const float* d_time, const float* d_x, const float* d_y,
                         int mode, void* stream) {
     if (n < 0 || H <= 0 || W <= 0 || B <= 0 || !d_grid || !d_workspace) return CMDA_ERR_BAD_ARG;
     if (n > 0 && (!d_time || !d_x || !d_y || !d_pol)) return CMDA_ERR_BAD_ARG;
-    if (mode < CMDA_VOXEL_GLOBAL || mode > CMDA_VOXEL_FACTORED) return CMDA_ERR_BAD_ARG;
+    if (mode < CMDA_VOXEL_GLOBAL || mode > CMDA_VOXEL_BANDED) return CMDA_ERR_BAD_ARG;
     if (reinterpret_cast<uintptr_t>(d_workspace) & 255) return CMDA_ERR_WORKSPACE;
     if (workspace_bytes < cmda_events_vg_workspace_bytes(n, 1, H, W, B, mode)) return CMDA_ERR_WORKSPACE;
     // float32 events are already rectified: there is no map gather to tile, so this entry point
     // runs the GLOBAL scatter (AUTO resolves to it); TILED / EXACT are refused explicitly
-    if (mode == CMDA_VOXEL_TILED || mode == CMDA_VOXEL_FACTORED) return CMDA_ERR_UNSUPPORTED;
+    if (mode == CMDA_VOXEL_TILED || mode == CMDA_VOXEL_FACTORED || mode == CMDA_VOXEL_BANDED) return CMDA_ERR_UNSUPPORTED;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long V = static_cast<long long>(B) * H * W;
     char* ws = static_cast<char*>(d_workspace);

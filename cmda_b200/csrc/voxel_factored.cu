@@ -182,6 +182,344 @@ sensor_accumulate_kernel(const uint32_t* __restrict__ t, const uint16_t* __restr
     }
 }
 
+// ---- stage A, BANDED variant ---------------------------------------------------------------------
+// Same R as sensor_accumulate_kernel, bit for bit, without one L2 atomic per event (the L2 RED rate,
+// about 190 G/s, is what bounds that kernel).  Two passes:
+//   band_partition_kernel   a CTA takes one chunk of kBandChunk consecutive events of a window, computes what
+//       stage A needs of each (temporal bin t0, fraction f as 2^-24 fixed point, sign, raw pixel) and sorts the
+//       chunk in shared memory by bucket = (t0, band), a band being kBandRows full sensor rows.  The sorted
+//       chunk goes back to the chunk's own slice of the record buffer with straight coalesced stores (5 bytes
+//       per event: u32 = f << 8 | cell low byte, u8 = cell high bits | sign << 7; B == 1: one u16), next to the
+//       chunk's bucket offsets.  No global cursor, no count pass, record order reproducible.
+//   band_accumulate_kernel  one CTA per (window, t0, band): its R cells (one band of one plane) live in shared
+//       memory as two 32-bit words; warps walk the runs of their bucket through the chunks of the window and
+//       add every record with native shared-memory integer atomics (the carry out of the low word follows from
+//       the value the atomic returns), then the band is STORED to R, coalesced -- every R cell is written by
+//       exactly one CTA, so R needs no zero fill either.
+// The sums are the same exact integers as the RED path: R, and everything after it, is bit-identical.
+// Precondition: polarity in {0, 1} (the DSEC alphabet); the record keeps one sign bit.
+#ifndef CMDA_BAND_ROWS
+#define CMDA_BAND_ROWS 20
+#endif
+#ifndef CMDA_BAND_ACC_THREADS
+#define CMDA_BAND_ACC_THREADS 512
+#endif
+#ifndef CMDA_BAND_XSUB
+#define CMDA_BAND_XSUB 1          // measured: sub-buckets make both passes slower (profiles/r01_banded_sweep.txt)
+#endif
+#ifndef CMDA_BAND_INTERLEAVE
+#define CMDA_BAND_INTERLEAVE 1    // low / high word of a cell in adjacent shared-memory banks
+#endif
+#ifndef CMDA_BAND_RCP
+#define CMDA_BAND_RCP 1
+#endif
+#ifndef CMDA_BAND_UNROLL
+#define CMDA_BAND_UNROLL 8        // B > 1: record loads in flight per lane (4: 0.225 ms, 8: 0.218, 16: 0.213 on C2)
+#endif
+#ifndef CMDA_BAND_UNROLL_B1
+#define CMDA_BAND_UNROLL_B1 4     // B == 1 (4: 0.098 ms, 8: 0.110 on C2)
+#endif
+constexpr int kBandPartThreads = 512;
+constexpr int kBandPartGroups = 2;                                              // 8 events per group
+constexpr int kBandChunk = kBandPartThreads * kBandPartGroups * 8;              // events per partition CTA
+constexpr int kBandAccThreads = CMDA_BAND_ACC_THREADS;
+constexpr int kBandMaxBuckets = 2047;     // (temporal bin, band) buckets of one chunk (2047: an all-ones slot word means "dropped")
+constexpr int kBandMaxFine = 2047;        // ... times the sub-buckets the partition pass ranks in (11 bits of the slot word)
+constexpr int kBandMaxCells64 = 24576;     // B > 1: two 32-bit words per cell in shared memory (192 KB)
+constexpr int kBandMaxCells32 = 32768;     // B == 1: 15-bit cell index in the record
+
+struct BandGeom {
+    int rows;             // sensor rows per band
+    int nbands;
+    int nbuckets;         // nbands * (B > 1 ? B : 1)
+    unsigned inv_rows;    // floor(2^32 / rows) + 1: y / rows = umulhi(y, inv_rows) for y < 2^16 (rows > 1)
+    int xsub_log2;        // the partition pass ranks inside 2^xsub_log2 sub-buckets (low bits of x) per bucket: the
+                          // sub-buckets of a bucket are adjacent in the sorted chunk, so the runs stay whole, and a
+                          // warp's 32 rank atomics spread over that many more shared-memory words
+};
+struct BandTable {
+    long long rec_base[kMaxWindows];   // first record slot of the window's chunks
+    int chunk_base[kMaxWindows];       // first row of the window in the chunk offset table
+    int nchunks[kMaxWindows];
+};
+
+static bool pick_band_geom(int H, int W, int B, BandGeom& g) {
+    if (H < 1 || W < 1 || H > 65535 || W > 65535 || B < 1 || B > 24) return false;
+    const int max_cells = B > 1 ? kBandMaxCells64 : kBandMaxCells32;
+    int rows = max_cells / W;
+    if (rows < 1) return false;
+    if (rows > CMDA_BAND_ROWS) rows = CMDA_BAND_ROWS;
+    if (rows > H) rows = H;
+    g.rows = rows;
+    g.nbands = (H + rows - 1) / rows;
+    g.nbuckets = g.nbands * (B > 1 ? B : 1);
+    g.inv_rows = rows > 1 ? 0xffffffffu / static_cast<unsigned>(rows) + 1u : 0u;
+    g.xsub_log2 = 0;
+    while ((2 << g.xsub_log2) <= CMDA_BAND_XSUB && (g.nbuckets << (g.xsub_log2 + 1)) <= kBandMaxFine) ++g.xsub_log2;
+    return g.nbuckets <= kBandMaxBuckets;
+}
+
+template <bool HAS_T, bool VEC>
+__global__ void __launch_bounds__(kBandPartThreads, 2)
+band_partition_kernel(const uint32_t* __restrict__ t, const uint16_t* __restrict__ x, const uint16_t* __restrict__ y,
+                      const uint8_t* __restrict__ p, const __grid_constant__ WindowTable tab,
+                      const __grid_constant__ BandTable bt, BandGeom g, int H, int W, int B, unsigned* __restrict__ table,
+                      unsigned* __restrict__ rec32, unsigned char* __restrict__ rec8, unsigned short* __restrict__ rec16,
+                      unsigned long long* __restrict__ bin_counts) {
+    extern __shared__ __align__(16) unsigned char s_band_raw[];
+    const int NBC = g.nbuckets;                                                 // buckets the table knows
+    const int NB = g.nbuckets << g.xsub_log2;                                   // buckets ranked in here
+    const unsigned xsub_mask = (1u << g.xsub_log2) - 1u;
+    unsigned* s_hist = reinterpret_cast<unsigned*>(s_band_raw);                 // [NB]      bucket counts
+    unsigned* s_loff = s_hist + NB;                                             // [NB + 1]  exclusive offsets
+    unsigned* s_stage32 = s_loff + ((NB + 1 + 3) & ~3);                         // [kBandChunk] (B > 1)
+    unsigned char* s_stage8 = reinterpret_cast<unsigned char*>(s_stage32 + kBandChunk);     // [kBandChunk] (B > 1)
+    unsigned short* s_stage16 = reinterpret_cast<unsigned short*>(s_stage32);   // [kBandChunk] (B == 1)
+    __shared__ unsigned s_warp[kBandPartThreads / 32];
+    __shared__ unsigned s_bins[32];
+
+    const int s = blockIdx.y, c = blockIdx.x;
+    if (c >= bt.nchunks[s]) return;
+    const WindowDesc wd = tab.w[s];                                             // end > start: the window has chunks
+    const long long g0 = wd.start >> 3, g1 = (wd.end + 7) >> 3;                 // groups of 8 events
+    const long long first = g0 + static_cast<long long>(c) * (kBandPartThreads * kBandPartGroups);
+
+    // every load of the chunk is issued before anything waits on one
+    SensEv8 ev[kBandPartGroups];
+#pragma unroll
+    for (int j = 0; j < kBandPartGroups; ++j) {
+        const long long grp = first + static_cast<long long>(j) * kBandPartThreads + threadIdx.x;
+        if (grp < g1) {
+            ev[j] = sens_load8<HAS_T, VEC>(t, x, y, p, grp << 3, wd.start, wd.end);
+        } else {
+            ev[j].x = make_uint4(~0u, ~0u, ~0u, ~0u);                           // 0xffff is outside any sensor: dropped
+            ev[j].y = ev[j].x; ev[j].t0 = make_uint4(0, 0, 0, 0); ev[j].t1 = ev[j].t0; ev[j].p = make_uint2(0u, 0u);
+        }
+    }
+    const RawWindowTime rw = raw_window_time(t, wd.start, wd.end, B);
+    // den is 1 or NaN (single-timestamp window: every corner is masked, SURVEY.md Q3 -> no records at all)
+    const bool dead = !(rw.den == 1.0f);
+    const float r_dT = __frcp_rn(rw.fdT);                                       // dead windows never use it
+    for (int k = threadIdx.x; k < NB; k += kBandPartThreads) s_hist[k] = 0u;
+    if (threadIdx.x < 32) s_bins[threadIdx.x] = 0u;
+    __syncthreads();
+
+    const bool count_bins = bin_counts != nullptr;
+    unsigned slot[kBandPartGroups][8];      // bucket << 21 | rank inside the chunk's bucket << 8 | (B > 1) cell high bits
+                                            // | neg << 7   (0xffffffff: dropped)
+    unsigned rec[kBandPartGroups][8];       // B > 1: f << 8 | cell low byte;  B == 1: cell | neg << 15
+    unsigned local_bins = 0;
+#pragma unroll
+    for (int j = 0; j < kBandPartGroups; ++j) {
+        const unsigned xs[4] = {ev[j].x.x, ev[j].x.y, ev[j].x.z, ev[j].x.w}, ys[4] = {ev[j].y.x, ev[j].y.y, ev[j].y.z, ev[j].y.w};
+        const unsigned ts[8] = {ev[j].t0.x, ev[j].t0.y, ev[j].t0.z, ev[j].t0.w, ev[j].t1.x, ev[j].t1.y, ev[j].t1.z, ev[j].t1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            slot[j][e] = 0xffffffffu;
+            rec[j][e] = 0u;
+            const unsigned ex = (e & 1) ? (xs[e >> 1] >> 16) : (xs[e >> 1] & 0xffffu);
+            const unsigned ey = (e & 1) ? (ys[e >> 1] >> 16) : (ys[e >> 1] & 0xffffu);
+            if (dead || ex >= static_cast<unsigned>(W) || ey >= static_cast<unsigned>(H)) continue;
+            const unsigned pol = ((e < 4 ? ev[j].p.x : ev[j].p.y) >> (8 * (e & 3))) & 0xffu;
+            const unsigned neg = pol == 0u ? 1u : 0u;                           // value = 2 * pol - 1 (dsec.py:45), pol in {0, 1}
+            const unsigned band = g.rows > 1 ? __umulhi(ey, g.inv_rows) : ey;
+            const unsigned cell = (ey - band * static_cast<unsigned>(g.rows)) * static_cast<unsigned>(W) + ex;
+            unsigned bucket = band, rec_hi = 0u;
+            if constexpr (HAS_T) {
+                // dt / dT correctly rounded (dsec.py:348): the division, or its reciprocal + FMA-correction form
+                // (common.cuh div_by_reused: 0 <= dt <= 2^32, dT >= 1, quotients are 0 or >= 2^-32: all normal)
+                const float fdt = __uint2float_rn(ts[e] - rw.t_first);
+                const float t01 = CMDA_BAND_RCP ? div_by_reused(fdt, rw.fdT, r_dT) : __fdiv_rn(fdt, rw.fdT);
+                const float tn = __fmul_rn(rw.cm1, t01);
+                // dsec.py:43; tn is finite and >= 0 here (dT > 0), so the saturating conversion agrees with
+                // trunc_like_x86 on everything the range test keeps
+                const int tb = __float2int_rz(tn);
+                if (static_cast<unsigned>(tb) >= static_cast<unsigned>(B)) continue;    // both temporal corners masked
+                const float f = __fsub_rn(tn, __int2float_rn(tb));              // exact (Sterbenz)
+                const unsigned fq = static_cast<unsigned>(__float2int_rn(__fmul_rn(f, 16777216.0f)));   // < 2^24
+                rec[j][e] = (fq << 8) | (cell & 0xffu);
+                rec_hi = (cell >> 8) | (neg << 7);
+                bucket += static_cast<unsigned>(tb) * static_cast<unsigned>(g.nbands);
+                if (count_bins) atomicAdd(&s_bins[tb], 1u);
+            } else {
+                rec[j][e] = cell | (neg << 15);
+                ++local_bins;
+            }
+            if (CMDA_BAND_XSUB > 1) bucket = (bucket << g.xsub_log2) | (ex & xsub_mask);
+            slot[j][e] = (bucket << 21) | (atomicAdd(&s_hist[bucket], 1u) << 8) | rec_hi;
+        }
+    }
+    if (!HAS_T && count_bins) {
+        local_bins = __reduce_add_sync(0xffffffffu, local_bins);
+        if ((threadIdx.x & 31) == 0 && local_bins) atomicAdd(&s_bins[0], local_bins);
+    }
+    __syncthreads();
+    // exclusive scan of the bucket histogram (each thread owns a contiguous run of buckets)
+    const int per = (NB + kBandPartThreads - 1) / kBandPartThreads;
+    unsigned mine = 0;
+    for (int j = 0; j < per; ++j) {
+        const int k = threadIdx.x * per + j;
+        if (k < NB) mine += s_hist[k];
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned a = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += a;
+    }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        const unsigned a = (lane < kBandPartThreads / 32) ? s_warp[lane] : 0u;
+        unsigned ia = a;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned u = __shfl_up_sync(0xffffffffu, ia, o);
+            if (lane >= o) ia += u;
+        }
+        if (lane < kBandPartThreads / 32) s_warp[lane] = ia - a;
+    }
+    __syncthreads();
+    unsigned run = s_warp[wid] + inc - mine;
+    unsigned* row = table + static_cast<size_t>(bt.chunk_base[s] + c) * (NBC + 1);
+    for (int j = 0; j < per; ++j) {
+        const int k = threadIdx.x * per + j;
+        if (k < NB) {
+            s_loff[k] = run;
+            if ((static_cast<unsigned>(k) & xsub_mask) == 0u) row[k >> g.xsub_log2] = run;
+            run += s_hist[k];
+            if (k == NB - 1) { s_loff[NB] = run; row[NBC] = run; }
+        }
+    }
+    __syncthreads();
+    // stage the records sorted by bucket
+#pragma unroll
+    for (int j = 0; j < kBandPartGroups; ++j) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const unsigned sl = slot[j][e];
+            if (sl == 0xffffffffu) continue;
+            const unsigned pos = s_loff[sl >> 21] + ((sl >> 8) & 0x1fffu);
+            if constexpr (HAS_T) {
+                s_stage32[pos] = rec[j][e];
+                s_stage8[pos] = static_cast<unsigned char>(sl & 0xffu);
+            } else {
+                s_stage16[pos] = static_cast<unsigned short>(rec[j][e]);
+            }
+        }
+    }
+    __syncthreads();
+    // copy out: the chunk's slice of the record buffer receives the sorted chunk front to back
+    const unsigned total = s_loff[NB];
+    const size_t base = static_cast<size_t>(bt.rec_base[s]) + static_cast<size_t>(c) * kBandChunk;
+    if constexpr (HAS_T) {
+        for (unsigned i = threadIdx.x; i < total; i += kBandPartThreads) rec32[base + i] = s_stage32[i];
+        // base is a multiple of 4: four high bytes per store
+        const unsigned* s8w = reinterpret_cast<const unsigned*>(s_stage8);
+        unsigned* d8w = reinterpret_cast<unsigned*>(rec8 + base);
+        for (unsigned i = threadIdx.x; i < (total + 3) / 4; i += kBandPartThreads) d8w[i] = s8w[i];
+    } else {
+        const unsigned* s16w = reinterpret_cast<const unsigned*>(s_stage16);
+        unsigned* d16w = reinterpret_cast<unsigned*>(rec16 + base);
+        for (unsigned i = threadIdx.x; i < (total + 1) / 2; i += kBandPartThreads) d16w[i] = s16w[i];
+    }
+    if (count_bins && threadIdx.x < B && threadIdx.x < 32) {
+        const unsigned cnt = s_bins[threadIdx.x];
+        if (cnt) atomicAdd(bin_counts + static_cast<size_t>(s) * B + threadIdx.x, static_cast<unsigned long long>(cnt));
+    }
+}
+
+template <bool HAS_T>
+__global__ void __launch_bounds__(kBandAccThreads)
+band_accumulate_kernel(const unsigned* __restrict__ table, const unsigned* __restrict__ rec32,
+                       const unsigned char* __restrict__ rec8, const unsigned short* __restrict__ rec16,
+                       const __grid_constant__ BandTable bt, BandGeom g, int H, int W, int B, void* __restrict__ R) {
+    constexpr int kBandUnroll = HAS_T ? CMDA_BAND_UNROLL : CMDA_BAND_UNROLL_B1;
+    extern __shared__ __align__(16) unsigned s_band_acc[];      // B > 1: (lo, hi) per cell;  B == 1: count[cells]
+    const unsigned cells = static_cast<unsigned>(g.rows) * static_cast<unsigned>(W);
+    // cell c: low word at s_lo[c * kStride], high word at s_hi[c * kStride]
+    constexpr unsigned kStride = (HAS_T && CMDA_BAND_INTERLEAVE) ? 2u : 1u;
+    unsigned* s_lo = s_band_acc;
+    int* s_hi = reinterpret_cast<int*>(s_band_acc + (CMDA_BAND_INTERLEAVE ? 1u : cells));
+    // item = (window, temporal bin, band), band fastest: neighbouring CTAs read the same chunks
+    const int Bk = HAS_T ? B : 1;
+    int item = blockIdx.x;
+    const int band = item % g.nbands;
+    item /= g.nbands;
+    const int k = item % Bk, s = item / Bk;
+    const unsigned band_rows = static_cast<unsigned>(min(g.rows, H - band * g.rows));
+    const unsigned band_cells = band_rows * static_cast<unsigned>(W);
+    for (unsigned i = threadIdx.x; i < (HAS_T ? 2u * cells : cells); i += kBandAccThreads) s_band_acc[i] = 0u;
+    __syncthreads();
+
+    const int nchunks = bt.nchunks[s];
+    const unsigned bucket = static_cast<unsigned>(k) * static_cast<unsigned>(g.nbands) + static_cast<unsigned>(band);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    constexpr int nwarps = kBandAccThreads / 32;
+    const size_t row_words = static_cast<size_t>(g.nbuckets) + 1;
+    const unsigned* tbl = table + static_cast<size_t>(bt.chunk_base[s]) * row_words + bucket;
+    const size_t base_s = static_cast<size_t>(bt.rec_base[s]);
+    for (int c0 = 0; c0 < nchunks; c0 += 32 * nwarps) {
+        // chunk c belongs to warp c % nwarps: a temporal bin's chunks (contiguous for time-sorted events) spread
+        // over all warps; lane l holds the run bounds of the warp's l-th chunk of this round
+        const int c = c0 + lane * nwarps + wid;
+        unsigned a = 0u, b = 0u;
+        if (c < nchunks) {
+            a = __ldg(tbl + static_cast<size_t>(c) * row_words);
+            b = __ldg(tbl + static_cast<size_t>(c) * row_words + 1);
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, b > a);
+        while (todo) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            const unsigned ra = __shfl_sync(0xffffffffu, a, j), rb = __shfl_sync(0xffffffffu, b, j);
+            const size_t base = base_s + static_cast<size_t>(c0 + j * nwarps + wid) * kBandChunk;
+            for (unsigned i0 = ra; i0 < rb; i0 += 32u * kBandUnroll) {
+                unsigned r32[kBandUnroll], r8[kBandUnroll];
+#pragma unroll
+                for (int u = 0; u < kBandUnroll; ++u) {         // the loads of these records are in flight together
+                    const unsigned i = i0 + 32u * u + lane;
+                    r32[u] = 0u; r8[u] = 0u;
+                    if (i < rb) {
+                        if constexpr (HAS_T) { r32[u] = __ldg(rec32 + base + i); r8[u] = __ldg(rec8 + base + i); }
+                        else r32[u] = __ldg(rec16 + base + i);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kBandUnroll; ++u) {
+                    if (i0 + 32u * u + lane >= rb) continue;
+                    if constexpr (HAS_T) {
+                        const unsigned cell = (r32[u] & 0xffu) | ((r8[u] & 0x7fu) << 8);
+                        long long v = (1LL << kCountShift) + static_cast<long long>(r32[u] >> 8);
+                        if (r8[u] & 0x80u) v = -v;
+                        const unsigned lo = static_cast<unsigned>(static_cast<unsigned long long>(v));
+                        const int hi = static_cast<int>(v >> 32);
+                        const unsigned old = atomicAdd(s_lo + cell * kStride, lo);
+                        const unsigned nw = old + lo;
+                        atomicAdd(s_hi + cell * kStride, hi + static_cast<int>(nw < old));      // carry out of the low word
+                    } else {
+                        atomicAdd(reinterpret_cast<int*>(s_lo) + (r32[u] & 0x7fffu), (r32[u] & 0x8000u) ? -1 : 1);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // the band of this plane, stored once
+    const size_t plane = static_cast<size_t>(H) * W;
+    const size_t band_off = static_cast<size_t>(band) * g.rows * W;
+    if constexpr (HAS_T) {
+        long long* dst = reinterpret_cast<long long*>(R) + (static_cast<size_t>(s) * B + k) * plane + band_off;
+        for (unsigned i = threadIdx.x; i < band_cells; i += kBandAccThreads)
+            dst[i] = static_cast<long long>((static_cast<unsigned long long>(static_cast<unsigned>(s_hi[i * kStride])) << 32) |
+                                            s_lo[i * kStride]);
+    } else {
+        int* dst = reinterpret_cast<int*>(R) + static_cast<size_t>(s) * plane + band_off;
+        for (unsigned i = threadIdx.x; i < band_cells; i += kBandAccThreads) dst[i] = static_cast<int>(s_lo[i]);
+    }
+}
+
 // One R cell chain -> planes: plane_b = C_b - F_b + F_(b-1), the temporal corners 1 - f and f of
 // dsec.py:49-52, as a float64 holding the exact 2^-24 fixed-point integer (kFracBits); for B == 1 the plane
 // is the signed event count.  f(b, value) is called for b = 0 .. B-1 in order.
@@ -650,6 +988,47 @@ size_t factored_scratch_bytes(int group, int H, int W, int B) {
            align_up(sizeof(PartialStats) * static_cast<size_t>(group) * gather_blocks(H, W), 256);
 }
 
+// BANDED stage A: chunk offset table + record buffer, for windows of `total_events` events in all
+struct BandScratch {
+    unsigned* table;            // [chunks][nbuckets + 1]
+    unsigned* rec32;            // [chunks * kBandChunk]   (B > 1)
+    unsigned char* rec8;        // [chunks * kBandChunk]   (B > 1)
+    unsigned short* rec16;      // [chunks * kBandChunk]   (B == 1)
+    size_t total_bytes;
+};
+static long long band_chunks_of(long long start, long long end) {
+    if (end <= start) return 0;
+    const long long groups = ((end + 7) >> 3) - (start >> 3);
+    const long long per = static_cast<long long>(kBandPartThreads) * kBandPartGroups;
+    return (groups + per - 1) / per;
+}
+static BandScratch band_carve(char* base, long long chunks, const BandGeom& g, int B) {
+    BandScratch z{};
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += align_up(bytes, 256); return p; };
+    const size_t slots = static_cast<size_t>(chunks > 0 ? chunks : 1) * kBandChunk;
+    z.table = reinterpret_cast<unsigned*>(take(sizeof(unsigned) * static_cast<size_t>(chunks > 0 ? chunks : 1) * (g.nbuckets + 1)));
+    if (B > 1) {
+        z.rec32 = reinterpret_cast<unsigned*>(take(sizeof(unsigned) * slots));
+        z.rec8 = reinterpret_cast<unsigned char*>(take(slots));
+    } else {
+        z.rec16 = reinterpret_cast<unsigned short*>(take(sizeof(unsigned short) * slots));
+    }
+    z.total_bytes = off;
+    return z;
+}
+int banded_supported(int H, int W, int B) {
+    BandGeom g{};
+    return factored_supported(H, W, B) && pick_band_geom(H, W, B, g);
+}
+// upper bound for any launch group of at most `group` windows holding at most `total_events` events
+size_t banded_scratch_bytes(long long total_events, int group, int H, int W, int B) {
+    BandGeom g{};
+    if (!pick_band_geom(H, W, B, g)) return 0;
+    const long long chunks = total_events / kBandChunk + 2LL * group;
+    return band_carve(nullptr, chunks, g, B).total_bytes;
+}
+
 // Builds the plans of `n` slots (ms.map_of_slot / plan_of_slot / plan_base / plan_stride filled in).
 static int build_plans(const float2* maps2, const MapSlots& ms, int n, int H, int W, cudaStream_t st) {
     const size_t npx = static_cast<size_t>(H) * W;
@@ -684,8 +1063,11 @@ int launch_plan_build(const float* maps, int n_maps, int H, int W, void* plans, 
 
 int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, const uint8_t* p, const WindowTable& tab, int S,
                     long long max_events, const float* maps, int H, int W, int B, void* R, int64_t* bin_counts,
-                    float* raw, PartialStats* partials, void* scratch, size_t scratch_bytes, const void* plans, cudaStream_t st) {
+                    float* raw, PartialStats* partials, void* scratch, size_t scratch_bytes, const void* plans, int banded,
+                    cudaStream_t st) {
     if (!factored_supported(H, W, B)) return CMDA_ERR_UNSUPPORTED;
+    BandGeom bg{};
+    if (banded && !pick_band_geom(H, W, B, bg)) return CMDA_ERR_UNSUPPORTED;
     const size_t npx = static_cast<size_t>(H) * W;
     const size_t nc = ncells_padded_of(H, W);
     const int nblk = gather_blocks(H, W);
@@ -715,16 +1097,64 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
     PartialStats* block_partials = reinterpret_cast<PartialStats*>(static_cast<char*>(scratch) + own_bytes);
     const float2* maps2 = reinterpret_cast<const float2*>(maps);
 
-    // zero R (int64 cells for B > 1, int32 counts for B == 1)
+    // zero R (int64 cells for B > 1, int32 counts for B == 1); the BANDED stage A stores every cell instead
     const size_t r_bytes = (B == 1) ? sizeof(int) * S * npx : sizeof(long long) * S * B * npx;
-    CMDA_CUDA_TRY(cudaMemsetAsync(R, 0, r_bytes, st));
+    if (!banded) CMDA_CUDA_TRY(cudaMemsetAsync(R, 0, r_bytes, st));
     phase_mark(st);
     if (own_plans && n_slots) {
         const int rc = build_plans(maps2, ms, n_slots, H, W, st);
         if (rc != CMDA_OK) return rc;
     }
     phase_mark(st);
-    if (max_events > 0) {
+    if (banded) {
+        BandTable bt{};
+        long long chunks = 0, max_chunks = 0;
+        for (int s = 0; s < S; ++s) {
+            const long long n = band_chunks_of(tab.w[s].start, tab.w[s].end);
+            if (chunks + n > 0x7fffffffLL) return CMDA_ERR_UNSUPPORTED;
+            bt.rec_base[s] = chunks * kBandChunk;
+            bt.chunk_base[s] = static_cast<int>(chunks);
+            bt.nchunks[s] = static_cast<int>(n);
+            chunks += n;
+            if (n > max_chunks) max_chunks = n;
+        }
+        const size_t used = align_up(own_bytes + sizeof(PartialStats) * static_cast<size_t>(S) * nblk, 256);
+        const BandScratch z = band_carve(static_cast<char*>(scratch) + used, chunks, bg, B);
+        if (used + z.total_bytes > scratch_bytes) return CMDA_ERR_WORKSPACE;
+        const bool vec = ((reinterpret_cast<uintptr_t>(t) & 15) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && ((reinterpret_cast<uintptr_t>(p) & 7) == 0);
+        unsigned long long* ubins = reinterpret_cast<unsigned long long*>(bin_counts);
+        if (max_chunks > 0) {
+            const int fine = bg.nbuckets << bg.xsub_log2;
+            const size_t shm = sizeof(unsigned) * (fine + ((fine + 1 + 3) & ~3)) + (B > 1 ? 5u : 2u) * static_cast<size_t>(kBandChunk);
+            dim3 grid(static_cast<unsigned>(max_chunks), S);
+#define CMDA_BAND_PART(HAS_T, VEC)                                                                                             \
+    do {                                                                                                                       \
+        CMDA_CUDA_TRY(cudaFuncSetAttribute(band_partition_kernel<HAS_T, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                           static_cast<int>(shm)));                                                            \
+        band_partition_kernel<HAS_T, VEC><<<grid, kBandPartThreads, shm, st>>>(t, x, y, p, tab, bt, bg, H, W, B, z.table,     \
+                                                                               z.rec32, z.rec8, z.rec16, ubins);               \
+    } while (0)
+            if (B == 1) { if (vec) CMDA_BAND_PART(false, true); else CMDA_BAND_PART(false, false); }
+            else { if (vec) CMDA_BAND_PART(true, true); else CMDA_BAND_PART(true, false); }
+#undef CMDA_BAND_PART
+            CMDA_LAUNCH_CHECK();
+        }
+        phase_mark(st);
+        {
+            const size_t cells = static_cast<size_t>(bg.rows) * W;
+            const size_t shm = (B > 1 ? 2 : 1) * sizeof(unsigned) * cells;
+            const unsigned items = static_cast<unsigned>(S) * static_cast<unsigned>(bg.nbuckets);
+            if (B == 1) {
+                CMDA_CUDA_TRY(cudaFuncSetAttribute(band_accumulate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shm)));
+                band_accumulate_kernel<false><<<items, kBandAccThreads, shm, st>>>(z.table, z.rec32, z.rec8, z.rec16, bt, bg, H, W, B, R);
+            } else {
+                CMDA_CUDA_TRY(cudaFuncSetAttribute(band_accumulate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shm)));
+                band_accumulate_kernel<true><<<items, kBandAccThreads, shm, st>>>(z.table, z.rec32, z.rec8, z.rec16, bt, bg, H, W, B, R);
+            }
+            CMDA_LAUNCH_CHECK();
+        }
+    } else if (max_events > 0) {
         const bool vec = ((reinterpret_cast<uintptr_t>(t) & 15) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
                          ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && ((reinterpret_cast<uintptr_t>(p) & 7) == 0);
         const long long groups = (max_events + 7) / 8 + 1;

@@ -57,7 +57,9 @@ enum {
     CMDA_VOXEL_TILED = 1,    /* raw-tile multisplit + shared-memory fixed-point accumulation   */
     CMDA_VOXEL_AUTO = 2,     /* FACTORED where it applies (raw DSEC events), else GLOBAL       */
     CMDA_VOXEL_EXACT = 3,    /* stable sort by (voxel, corner pass) + ordered float32 accumulation */
-    CMDA_VOXEL_FACTORED = 4  /* sensor-space temporal accumulation + per-pixel rectify gather  */
+    CMDA_VOXEL_FACTORED = 4, /* sensor-space temporal accumulation + per-pixel rectify gather  */
+    CMDA_VOXEL_BANDED = 5    /* FACTORED with its per-event L2 atomics replaced by a band partition +
+                                shared-memory accumulation; bit-identical to FACTORED; polarity in {0, 1} */
 };
 
 /* Directions of the shift-pair generator (reference mmseg/datasets/utils.py:128-151). */

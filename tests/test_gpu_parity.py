@@ -353,6 +353,49 @@ def test_events_vg_modes_agree(cm):
             assert np.all(fa[s].cpu().numpy()[n_contrib == 0] == 0.0)
 
 
+@pytest.mark.parametrize("shape", [(480, 640), (37, 53), (40, 1500), (301, 7)])
+def test_events_vg_banded_identical_to_factored(cm, shape):
+    """BANDED replaces FACTORED's per-event L2 atomics by a band partition + shared-memory accumulation of the
+    SAME integers: raw grids, normalised grids and per-bin counts are bit-identical to FACTORED on ragged
+    batches (several maps, unaligned starts, an empty window, a one-event window, a single-timestamp window,
+    chunks that straddle temporal bins, out-of-sensor coordinates, unsorted timestamps)."""
+    from cmda_b200 import synth
+    H, W = shape
+    n = 300_000 if H * W > 100_000 else 60_000
+    t, x, y, p = synth.make_events(n, H, W, seed=synth.seed_for(1, 91), skew=0.15)
+    t[-3000:] = t[-3000]                                   # a run of identical timestamps at the end
+    x[1000:1010] = W + 5                                   # outside the sensor: dropped (numpy would raise)
+    y[2000:2005] = H
+    t[5000:5200] = t[5000:5200][::-1].copy()               # a locally unsorted stretch
+    rmaps = np.stack([synth.make_rectify_map(H, W, seed=5), synth.make_rectify_map(H, W, seed=6, k1=0.03)])
+    store = cm.EventStore(t, x, y, p, rmaps, height=H, width=W, device="cuda:0")
+    starts = [0, 1001, 7, 500, 777, n - 2500, 20_000]
+    fins = [n - 3500, n // 2, 20_000, 499, 777, n - 1, 20_000 + 8191 + 8192]     # full, half, small, empty, one event, one timestamp, two chunks
+    mids = [0, 1, 0, 1, 0, 1, 1]
+    for bins in (1, 2, 5):
+        fa, cf = cm.events_vg_batch(store, starts, fins, bins, map_ids=mids, mode="factored", normalize=False,
+                                    return_bin_counts=True)
+        ba, cb = cm.events_vg_batch(store, starts, fins, bins, map_ids=mids, mode="banded", normalize=False,
+                                    return_bin_counts=True)
+        assert np.array_equal(bits(fa), bits(ba)), f"B={bins}: BANDED raw grid differs from FACTORED"
+        assert torch.equal(cf, cb)
+        assert torch.count_nonzero(ba[3]) == 0 and torch.count_nonzero(ba[5]) == 0
+        fn = cm.events_vg_batch(store, starts, fins, bins, map_ids=mids, mode="factored")
+        bn = cm.events_vg_batch(store, starts, fins, bins, map_ids=mids, mode="banded")
+        assert np.array_equal(bits(fn), bits(bn)), f"B={bins}: BANDED normalised grid differs from FACTORED"
+    # no rectify map (identity); then a store whose arrays start off the 16-byte grid (scalar loads everywhere)
+    plain = cm.EventStore(t, x, y, p, None, height=H, width=W, device="cuda:0")
+    fa = cm.events_vg_batch(plain, starts[:3], fins[:3], 3, mode="factored", normalize=False)
+    ba = cm.events_vg_batch(plain, starts[:3], fins[:3], 3, mode="banded", normalize=False)
+    assert np.array_equal(bits(fa), bits(ba))
+    off = cm.EventStore(t, x, y, p, rmaps, height=H, width=W, device="cuda:0")
+    off.t, off.x, off.y, off.p = store.t[1:], store.x[1:], store.y[1:], store.p[1:]        # views: base + one element
+    assert off.x.data_ptr() % 16 != 0
+    fo = cm.events_vg_batch(off, [0, 3000], [40_000, 50_000], 5, map_ids=[0, 1], mode="factored", normalize=False)
+    bo = cm.events_vg_batch(off, [0, 3000], [40_000, 50_000], 5, map_ids=[0, 1], mode="banded", normalize=False)
+    assert np.array_equal(bits(fo), bits(bo))
+
+
 def test_events_vg_large_window_b1(cm):
     """B == 1 (the shipped events_bins) on a ragged batch with a > 2^20-event window, an unaligned start and a
     single-timestamp window: exact against the float64 sum of the reference's weights, bit-reproducible,
