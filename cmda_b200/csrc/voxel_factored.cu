@@ -520,6 +520,257 @@ band_accumulate_kernel(const unsigned* __restrict__ table, const unsigned* __res
     }
 }
 
+// ---- BANDED, second cut (CMDA_BAND_V2, off by default: written after the last GPU minute of round 1, so it has
+// never run; the ncu capture of the first cut -- profiles/r01_ncu_banded_b5_summary.txt -- is its brief) -----------
+// Same record format, same table, same R.  Partition: no per-event branches -- an event that is dropped (outside
+// the sensor, outside the temporal range, past the window, dead window) is ranked into one extra "trash" bucket
+// behind the real ones, so every lane runs the same straight-line code and the sorted chunk simply ends where the
+// trash begins; the per-bin event counts come from the bucket offsets instead of one more atomic per event.
+// Accumulate: per-run pointers with immediate offsets instead of 64-bit address arithmetic per record, 32-bit
+// arithmetic for the (low, high) addends, no divergence region per record (a lane without a record adds zero to
+// a cell of its own).
+#ifndef CMDA_BAND_V2
+#define CMDA_BAND_V2 0
+#endif
+#ifndef CMDA_BAND_V2_UNROLL
+#define CMDA_BAND_V2_UNROLL 4
+#endif
+static_assert(!CMDA_BAND_V2 || CMDA_BAND_XSUB == 1, "the second cut ranks in the table's own buckets");
+
+template <bool HAS_T, bool VEC>
+__global__ void __launch_bounds__(kBandPartThreads, 2)
+band_partition2_kernel(const uint32_t* __restrict__ t, const uint16_t* __restrict__ x, const uint16_t* __restrict__ y,
+                       const uint8_t* __restrict__ p, const __grid_constant__ WindowTable tab,
+                       const __grid_constant__ BandTable bt, BandGeom g, int H, int W, int B, unsigned* __restrict__ table,
+                       unsigned* __restrict__ rec32, unsigned char* __restrict__ rec8, unsigned short* __restrict__ rec16,
+                       unsigned long long* __restrict__ bin_counts) {
+    extern __shared__ __align__(16) unsigned char s_band_raw[];
+    const int NB = g.nbuckets;                                                  // real buckets; bucket NB is the trash
+    unsigned* s_hist = reinterpret_cast<unsigned*>(s_band_raw);                 // [NB + 1]
+    unsigned* s_loff = s_hist + NB + 1;                                         // [NB + 2]  exclusive offsets
+    unsigned* s_stage32 = s_loff + ((NB + 2 + 3) & ~3);                         // [kBandChunk] (B > 1)
+    unsigned char* s_stage8 = reinterpret_cast<unsigned char*>(s_stage32 + kBandChunk);     // [kBandChunk] (B > 1)
+    unsigned short* s_stage16 = reinterpret_cast<unsigned short*>(s_stage32);   // [kBandChunk] (B == 1)
+    __shared__ unsigned s_warp[kBandPartThreads / 32];
+
+    const int s = blockIdx.y, c = blockIdx.x;
+    if (c >= bt.nchunks[s]) return;
+    const WindowDesc wd = tab.w[s];
+    const long long g0 = wd.start >> 3, g1 = (wd.end + 7) >> 3;
+    const long long first = g0 + static_cast<long long>(c) * (kBandPartThreads * kBandPartGroups);
+    SensEv8 ev[kBandPartGroups];
+#pragma unroll
+    for (int j = 0; j < kBandPartGroups; ++j) {
+        const long long grp = first + static_cast<long long>(j) * kBandPartThreads + threadIdx.x;
+        if (grp < g1) {
+            ev[j] = sens_load8<HAS_T, VEC>(t, x, y, p, grp << 3, wd.start, wd.end);
+        } else {
+            ev[j].x = make_uint4(~0u, ~0u, ~0u, ~0u);                           // 0xffff is outside any sensor: trash
+            ev[j].y = ev[j].x; ev[j].t0 = make_uint4(0, 0, 0, 0); ev[j].t1 = ev[j].t0; ev[j].p = make_uint2(0u, 0u);
+        }
+    }
+    const RawWindowTime rw = raw_window_time(t, wd.start, wd.end, B);
+    const bool alive = rw.den == 1.0f;                                          // NaN: single-timestamp window
+    const float r_dT = __frcp_rn(rw.fdT);
+    for (int k = threadIdx.x; k <= NB; k += kBandPartThreads) s_hist[k] = 0u;
+    __syncthreads();
+
+    unsigned slot[kBandPartGroups][8];      // bucket << 21 | rank << 8 | (B > 1) cell high bits | neg << 7
+    unsigned rec[kBandPartGroups][8];       // B > 1: f << 8 | cell low byte;  B == 1: cell | neg << 15
+#pragma unroll
+    for (int j = 0; j < kBandPartGroups; ++j) {
+        const unsigned xs[4] = {ev[j].x.x, ev[j].x.y, ev[j].x.z, ev[j].x.w}, ys[4] = {ev[j].y.x, ev[j].y.y, ev[j].y.z, ev[j].y.w};
+        const unsigned ts[8] = {ev[j].t0.x, ev[j].t0.y, ev[j].t0.z, ev[j].t0.w, ev[j].t1.x, ev[j].t1.y, ev[j].t1.z, ev[j].t1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const unsigned ex = (e & 1) ? (xs[e >> 1] >> 16) : (xs[e >> 1] & 0xffffu);
+            const unsigned ey = (e & 1) ? (ys[e >> 1] >> 16) : (ys[e >> 1] & 0xffffu);
+            bool valid = alive && ex < static_cast<unsigned>(W) && ey < static_cast<unsigned>(H);
+            const unsigned pol = ((e < 4 ? ev[j].p.x : ev[j].p.y) >> (8 * (e & 3))) & 0xffu;
+            const unsigned neg = pol == 0u ? 1u : 0u;                           // value = 2 * pol - 1 (dsec.py:45), pol in {0, 1}
+            const unsigned band = g.rows > 1 ? __umulhi(ey, g.inv_rows) : ey;
+            const unsigned cell = (ey - band * static_cast<unsigned>(g.rows)) * static_cast<unsigned>(W) + ex;    // junk unless valid
+            unsigned bucket = band, rec_hi = 0u;
+            if constexpr (HAS_T) {
+                const float fdt = __uint2float_rn(ts[e] - rw.t_first);
+                const float tn = __fmul_rn(rw.cm1, div_by_reused(fdt, rw.fdT, r_dT));      // dsec.py:347-348, 38-39
+                const int tb = __float2int_rz(tn);                                          // dsec.py:43 (tn finite, >= 0 when alive)
+                valid = valid && static_cast<unsigned>(tb) < static_cast<unsigned>(B);
+                const float f = __fsub_rn(tn, __int2float_rn(tb));                          // exact (Sterbenz) when valid
+                const unsigned fq = static_cast<unsigned>(__float2int_rn(__fmul_rn(f, 16777216.0f)));
+                rec[j][e] = (fq << 8) | (cell & 0xffu);
+                rec_hi = ((cell >> 8) & 0x7fu) | (neg << 7);
+                bucket += static_cast<unsigned>(tb) * static_cast<unsigned>(g.nbands);
+            } else {
+                rec[j][e] = (cell & 0x7fffu) | (neg << 15);
+            }
+            bucket = valid ? bucket : static_cast<unsigned>(NB);
+            slot[j][e] = (bucket << 21) | (atomicAdd(&s_hist[bucket], 1u) << 8) | rec_hi;
+        }
+    }
+    __syncthreads();
+    // exclusive scan of the NB + 1 bucket counts (each thread owns a contiguous run of buckets; with the usual
+    // hundred-odd buckets only the first warps own any, the others go straight to the barriers)
+    const int per = (NB + 1 + kBandPartThreads - 1) / kBandPartThreads;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const bool owner_warp = wid * 32 * per <= NB;
+    unsigned mine = 0, inc = 0;
+    if (owner_warp) {
+        for (int j = 0; j < per; ++j) {
+            const int k = threadIdx.x * per + j;
+            if (k <= NB) mine += s_hist[k];
+        }
+        inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned a = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += a;
+        }
+    }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        const unsigned a = (lane < kBandPartThreads / 32) ? s_warp[lane] : 0u;
+        unsigned ia = a;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned u = __shfl_up_sync(0xffffffffu, ia, o);
+            if (lane >= o) ia += u;
+        }
+        if (lane < kBandPartThreads / 32) s_warp[lane] = ia - a;
+    }
+    __syncthreads();
+    if (owner_warp) {
+        unsigned run = s_warp[wid] + inc - mine;
+        unsigned* row = table + static_cast<size_t>(bt.chunk_base[s] + c) * (NB + 1);
+        for (int j = 0; j < per; ++j) {
+            const int k = threadIdx.x * per + j;
+            if (k <= NB) {
+                s_loff[k] = run;
+                row[k] = run;           // row[NB]: where the trash begins = the number of records
+                run += s_hist[k];
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kBandPartGroups; ++j) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const unsigned sl = slot[j][e];
+            const unsigned pos = s_loff[sl >> 21] + ((sl >> 8) & 0x1fffu);      // < kBandChunk: the trash is staged too
+            if constexpr (HAS_T) {
+                s_stage32[pos] = rec[j][e];
+                s_stage8[pos] = static_cast<unsigned char>(sl & 0xffu);
+            } else {
+                s_stage16[pos] = static_cast<unsigned short>(rec[j][e]);
+            }
+        }
+    }
+    __syncthreads();
+    const unsigned total = s_loff[NB];
+    const size_t base = static_cast<size_t>(bt.rec_base[s]) + static_cast<size_t>(c) * kBandChunk;
+    if constexpr (HAS_T) {
+        unsigned* d32 = rec32 + base;
+        for (unsigned i = threadIdx.x; i < total; i += kBandPartThreads) d32[i] = s_stage32[i];
+        const unsigned* s8w = reinterpret_cast<const unsigned*>(s_stage8);
+        unsigned* d8w = reinterpret_cast<unsigned*>(rec8 + base);
+        for (unsigned i = threadIdx.x; i < (total + 3) / 4; i += kBandPartThreads) d8w[i] = s8w[i];
+    } else {
+        const unsigned* s16w = reinterpret_cast<const unsigned*>(s_stage16);
+        unsigned* d16w = reinterpret_cast<unsigned*>(rec16 + base);
+        for (unsigned i = threadIdx.x; i < (total + 1) / 2; i += kBandPartThreads) d16w[i] = s16w[i];
+    }
+    // events per temporal bin: the buckets of bin b are [b * nbands, (b + 1) * nbands)
+    if (bin_counts != nullptr && threadIdx.x < (HAS_T ? B : 1)) {
+        const unsigned cnt = s_loff[(threadIdx.x + 1) * g.nbands] - s_loff[threadIdx.x * g.nbands];
+        if (cnt) atomicAdd(bin_counts + static_cast<size_t>(s) * B + threadIdx.x, static_cast<unsigned long long>(cnt));
+    }
+}
+
+template <bool HAS_T>
+__global__ void __launch_bounds__(kBandAccThreads)
+band_accumulate2_kernel(const unsigned* __restrict__ table, const unsigned* __restrict__ rec32,
+                        const unsigned char* __restrict__ rec8, const unsigned short* __restrict__ rec16,
+                        const __grid_constant__ BandTable bt, BandGeom g, int H, int W, int B, void* __restrict__ R) {
+    constexpr int U = CMDA_BAND_V2_UNROLL;
+    extern __shared__ __align__(16) unsigned s_band_acc[];      // B > 1: (lo, hi) per cell;  B == 1: count[cells]
+    const unsigned cells = static_cast<unsigned>(g.rows) * static_cast<unsigned>(W);
+    const int Bk = HAS_T ? B : 1;
+    int item = blockIdx.x;
+    const int band = item % g.nbands;
+    item /= g.nbands;
+    const int k = item % Bk, s = item / Bk;
+    const unsigned band_cells = static_cast<unsigned>(min(g.rows, H - band * g.rows)) * static_cast<unsigned>(W);
+    for (unsigned i = threadIdx.x; i < (HAS_T ? 2u * cells : cells); i += kBandAccThreads) s_band_acc[i] = 0u;
+    __syncthreads();
+
+    const int nchunks = bt.nchunks[s];
+    const unsigned bucket = static_cast<unsigned>(k) * static_cast<unsigned>(g.nbands) + static_cast<unsigned>(band);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    constexpr int nwarps = kBandAccThreads / 32;
+    const size_t row_words = static_cast<size_t>(g.nbuckets) + 1;
+    const unsigned* tbl = table + static_cast<size_t>(bt.chunk_base[s]) * row_words + bucket;
+    const size_t base_s = static_cast<size_t>(bt.rec_base[s]);
+    for (int c0 = 0; c0 < nchunks; c0 += 32 * nwarps) {
+        const int c = c0 + lane * nwarps + wid;
+        unsigned a = 0u, b = 0u;
+        if (c < nchunks) {
+            a = __ldg(tbl + static_cast<size_t>(c) * row_words);
+            b = __ldg(tbl + static_cast<size_t>(c) * row_words + 1);
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, b > a);
+        while (todo) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            const unsigned ra = __shfl_sync(0xffffffffu, a, j), len = __shfl_sync(0xffffffffu, b, j) - ra;
+            const size_t off = base_s + static_cast<size_t>(c0 + j * nwarps + wid) * kBandChunk + ra + lane;
+            const unsigned* p32 = rec32 + off;
+            const unsigned char* p8 = rec8 + off;
+            const unsigned short* p16 = rec16 + off;
+            for (unsigned k0 = lane; k0 < len + lane; k0 += 32u * U, p32 += 32 * U, p8 += 32 * U, p16 += 32 * U) {
+                unsigned r32[U], r8[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {                   // loads first: U records in flight per lane
+                    const bool v = k0 + 32u * u < len;
+                    r32[u] = 0u; r8[u] = 0u;
+                    if constexpr (HAS_T) { if (v) { r32[u] = __ldg(p32 + 32 * u); r8[u] = __ldg(p8 + 32 * u); } }
+                    else { if (v) r32[u] = __ldg(p16 + 32 * u); }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const bool v = k0 + 32u * u < len;
+                    if constexpr (HAS_T) {
+                        // sign * (2^44 + f) as the (high, low) words of the int64 addend; a lane without a record adds
+                        // zero to a cell of its own (cells 0..31: distinct banks), which keeps the code straight
+                        const unsigned fq = r32[u] >> 8;
+                        const bool neg = (r8[u] & 0x80u) != 0u;
+                        const unsigned cell = v ? ((r32[u] & 0xffu) | ((r8[u] & 0x7fu) << 8)) : static_cast<unsigned>(lane);
+                        const unsigned lo = v ? (neg ? 0u - fq : fq) : 0u;
+                        const int hi = v ? (neg ? -4096 - static_cast<int>(fq != 0u) : 4096) : 0;
+                        const unsigned old = atomicAdd(s_band_acc + 2u * cell, lo);
+                        atomicAdd(reinterpret_cast<int*>(s_band_acc) + 2u * cell + 1u, hi + static_cast<int>(old + lo < old));
+                    } else {
+                        const unsigned cell = v ? (r32[u] & 0x7fffu) : static_cast<unsigned>(lane);
+                        atomicAdd(reinterpret_cast<int*>(s_band_acc) + cell, v ? ((r32[u] & 0x8000u) ? -1 : 1) : 0);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const size_t plane = static_cast<size_t>(H) * W;
+    const size_t band_off = static_cast<size_t>(band) * g.rows * W;
+    if constexpr (HAS_T) {
+        long long* dst = reinterpret_cast<long long*>(R) + (static_cast<size_t>(s) * B + k) * plane + band_off;
+        const long long* src = reinterpret_cast<const long long*>(s_band_acc);     // (lo, hi) adjacent: the int64 itself
+        for (unsigned i = threadIdx.x; i < band_cells; i += kBandAccThreads) dst[i] = src[i];
+    } else {
+        int* dst = reinterpret_cast<int*>(R) + static_cast<size_t>(s) * plane + band_off;
+        for (unsigned i = threadIdx.x; i < band_cells; i += kBandAccThreads) dst[i] = static_cast<int>(s_band_acc[i]);
+    }
+}
+
 // One R cell chain -> planes: plane_b = C_b - F_b + F_(b-1), the temporal corners 1 - f and f of
 // dsec.py:49-52, as a float64 holding the exact 2^-24 fixed-point integer (kFracBits); for B == 1 the plane
 // is the signed event count.  f(b, value) is called for b = 0 .. B-1 in order.
@@ -1125,19 +1376,25 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
                          ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && ((reinterpret_cast<uintptr_t>(p) & 7) == 0);
         unsigned long long* ubins = reinterpret_cast<unsigned long long*>(bin_counts);
         if (max_chunks > 0) {
-            const int fine = bg.nbuckets << bg.xsub_log2;
+            const int fine = CMDA_BAND_V2 ? bg.nbuckets + 1 : (bg.nbuckets << bg.xsub_log2);
             const size_t shm = sizeof(unsigned) * (fine + ((fine + 1 + 3) & ~3)) + (B > 1 ? 5u : 2u) * static_cast<size_t>(kBandChunk);
             dim3 grid(static_cast<unsigned>(max_chunks), S);
+#if CMDA_BAND_V2
+#define CMDA_BAND_PART_KERNEL band_partition2_kernel
+#else
+#define CMDA_BAND_PART_KERNEL band_partition_kernel
+#endif
 #define CMDA_BAND_PART(HAS_T, VEC)                                                                                             \
     do {                                                                                                                       \
-        CMDA_CUDA_TRY(cudaFuncSetAttribute(band_partition_kernel<HAS_T, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+        CMDA_CUDA_TRY(cudaFuncSetAttribute(CMDA_BAND_PART_KERNEL<HAS_T, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                            static_cast<int>(shm)));                                                            \
-        band_partition_kernel<HAS_T, VEC><<<grid, kBandPartThreads, shm, st>>>(t, x, y, p, tab, bt, bg, H, W, B, z.table,     \
+        CMDA_BAND_PART_KERNEL<HAS_T, VEC><<<grid, kBandPartThreads, shm, st>>>(t, x, y, p, tab, bt, bg, H, W, B, z.table,     \
                                                                                z.rec32, z.rec8, z.rec16, ubins);               \
     } while (0)
             if (B == 1) { if (vec) CMDA_BAND_PART(false, true); else CMDA_BAND_PART(false, false); }
             else { if (vec) CMDA_BAND_PART(true, true); else CMDA_BAND_PART(true, false); }
 #undef CMDA_BAND_PART
+#undef CMDA_BAND_PART_KERNEL
             CMDA_LAUNCH_CHECK();
         }
         phase_mark(st);
@@ -1145,13 +1402,19 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
             const size_t cells = static_cast<size_t>(bg.rows) * W;
             const size_t shm = (B > 1 ? 2 : 1) * sizeof(unsigned) * cells;
             const unsigned items = static_cast<unsigned>(S) * static_cast<unsigned>(bg.nbuckets);
+#if CMDA_BAND_V2
+#define CMDA_BAND_ACC_KERNEL band_accumulate2_kernel
+#else
+#define CMDA_BAND_ACC_KERNEL band_accumulate_kernel
+#endif
             if (B == 1) {
-                CMDA_CUDA_TRY(cudaFuncSetAttribute(band_accumulate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shm)));
-                band_accumulate_kernel<false><<<items, kBandAccThreads, shm, st>>>(z.table, z.rec32, z.rec8, z.rec16, bt, bg, H, W, B, R);
+                CMDA_CUDA_TRY(cudaFuncSetAttribute(CMDA_BAND_ACC_KERNEL<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shm)));
+                CMDA_BAND_ACC_KERNEL<false><<<items, kBandAccThreads, shm, st>>>(z.table, z.rec32, z.rec8, z.rec16, bt, bg, H, W, B, R);
             } else {
-                CMDA_CUDA_TRY(cudaFuncSetAttribute(band_accumulate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shm)));
-                band_accumulate_kernel<true><<<items, kBandAccThreads, shm, st>>>(z.table, z.rec32, z.rec8, z.rec16, bt, bg, H, W, B, R);
+                CMDA_CUDA_TRY(cudaFuncSetAttribute(CMDA_BAND_ACC_KERNEL<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shm)));
+                CMDA_BAND_ACC_KERNEL<true><<<items, kBandAccThreads, shm, st>>>(z.table, z.rec32, z.rec8, z.rec16, bt, bg, H, W, B, R);
             }
+#undef CMDA_BAND_ACC_KERNEL
             CMDA_LAUNCH_CHECK();
         }
     } else if (max_events > 0) {
