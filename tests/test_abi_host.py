@@ -53,6 +53,33 @@ def test_argument_validation_without_device(L):
     assert L.cmda_events_norm_batch(None, 1, 0, None, 1.0, 1, None, 0, None) == -1
 
 
+def test_voxel_modes_and_banded_workspace(L):
+    """Mode ids mirror the header; AUTO resolves to FACTORED for DSEC-shaped grids; the opt-in BANDED mode needs
+    FACTORED's workspace plus its record buffer (5 bytes per event for B > 1, 2 for B == 1, chunk-granular) and
+    refuses grids whose rows do not fit a band (host code only: nothing here touches CUDA)."""
+    from cmda_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "cmda_b200.h")).read()
+    for name, mode_id in _lib.VOXEL_MODES.items():
+        assert re.search(rf"CMDA_VOXEL_{name.upper()}\s*=\s*{mode_id}\b", hdr), name
+    n, S, H, W = 5_000_000, 16, 480, 640
+    assert L.cmda_events_vg_resolved_mode(n * S, S, H, W, 5, _lib.VOXEL_AUTO) == _lib.VOXEL_FACTORED
+    assert L.cmda_events_vg_resolved_mode(n * S, S, H, W, 5, _lib.VOXEL_BANDED) == _lib.VOXEL_BANDED
+    assert L.cmda_events_vg_resolved_mode(n * S, S, H, W, 5, _lib.VOXEL_BANDED + 1) == -1
+    chunk = 8192
+    for bins, rec_bytes in ((5, 5), (1, 2)):
+        fact = L.cmda_events_vg_workspace_bytes(n * S, S, H, W, bins, _lib.VOXEL_FACTORED)
+        band = L.cmda_events_vg_workspace_bytes(n * S, S, H, W, bins, _lib.VOXEL_BANDED)
+        extra = band - fact
+        chunks = n * S // chunk + 2 * S
+        assert extra >= rec_bytes * n * S                                   # every event has a record slot
+        assert extra <= rec_bytes * chunks * chunk + 4 * chunks * (24 * bins + 1) + 4096     # ... and little else
+        # more events -> more workspace, never less
+        assert L.cmda_events_vg_workspace_bytes(2 * n * S, S, H, W, bins, _lib.VOXEL_BANDED) > band
+    # a grid wider than one band can hold (B > 1: 24 576 cells): BANDED adds nothing, FACTORED's size remains
+    wide = L.cmda_events_vg_workspace_bytes(1000, 1, 4, 30_000, 5, _lib.VOXEL_BANDED)
+    assert wide == L.cmda_events_vg_workspace_bytes(1000, 1, 4, 30_000, 5, _lib.VOXEL_GLOBAL)
+
+
 def test_product_has_no_oracle_import():
     """The product package must never route through oracle/ (or any CPU fallback)."""
     pkg = os.path.join(ROOT, "cmda_b200")
