@@ -1,0 +1,281 @@
+// TEST INFRASTRUCTURE ONLY -- a CPU stand-in for the handful of CUDA constructs the cmda_b200 kernels use, so that the
+// kernel SOURCE (a transformed copy made by tests/emu/build_emu.py) can be executed on the host for small inputs where
+// no GPU exists: every CUDA thread of a block is a ucontext fiber on ONE host thread, __syncthreads and the warp
+// collectives are rendezvous points, atomics are plain read-modify-writes (nothing runs concurrently).  It checks
+// kernel LOGIC (indexing, barriers, packing, carry arithmetic); it is not a product path, not an oracle and says
+// nothing about performance.  Never linked into libcmda_b200.so.
+#pragma once
+#include <ucontext.h>
+
+#include <climits>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <type_traits>
+#include <vector>
+
+#define __CUDACC__ 1
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __noinline__
+#define __launch_bounds__(...)
+#define __grid_constant__
+#define __align__(n) alignas(n)
+#define __shared__ static
+
+struct uint2 { unsigned x, y; };
+struct uint3 { unsigned x, y, z; };
+struct uint4 { unsigned x, y, z, w; };
+struct int4 { int x, y, z, w; };
+struct float2 { float x, y; };
+struct float4 { float x, y, z, w; };
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
+};
+inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
+inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
+inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
+inline float2 make_float2(float x, float y) { return float2{x, y}; }
+inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+
+typedef void* cudaStream_t;
+typedef void* cudaEvent_t;
+enum cudaError_t { cudaSuccess = 0 };
+inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaPeekAtLastError() { return cudaSuccess; }
+
+namespace emu {
+struct Fiber {
+    ucontext_t ctx;
+    uint3 tid;
+    bool done;
+    std::vector<char> stack;
+};
+struct WarpBox {
+    unsigned long long vals[32], snap[32];
+    int count;
+    unsigned gen;
+};
+struct State {
+    std::vector<Fiber> fibers;
+    std::vector<WarpBox> warps;
+    ucontext_t sched;
+    Fiber* cur = nullptr;
+    int nthreads = 0, bar_count = 0;
+    unsigned bar_gen = 0;
+    unsigned long progress = 0;
+    std::function<void()> body;
+};
+inline State& st() { static State s; return s; }
+inline void yield() { State& s = st(); swapcontext(&s.cur->ctx, &s.sched); }
+inline void trampoline() {
+    State& s = st();
+    s.body();
+    s.cur->done = true;
+    swapcontext(&s.cur->ctx, &s.sched);
+}
+inline int linear_tid() { return static_cast<int>(st().cur - st().fibers.data()); }
+
+// one block: every thread is a fiber, resumed round-robin until all have returned
+inline void run_block(dim3 block) {
+    State& s = st();
+    const int n = static_cast<int>(block.x * block.y * block.z);
+    s.nthreads = n;
+    s.bar_count = 0;
+    if (static_cast<int>(s.fibers.size()) < n) s.fibers.resize(n);
+    s.warps.assign((n + 31) / 32, WarpBox{});
+    for (int i = 0; i < n; ++i) {
+        Fiber& f = s.fibers[i];
+        if (f.stack.empty()) f.stack.resize(256 * 1024);
+        f.done = false;
+        f.tid = uint3{static_cast<unsigned>(i) % block.x, (static_cast<unsigned>(i) / block.x) % block.y,
+                      static_cast<unsigned>(i) / (block.x * block.y)};
+        getcontext(&f.ctx);
+        f.ctx.uc_stack.ss_sp = f.stack.data();
+        f.ctx.uc_stack.ss_size = f.stack.size();
+        f.ctx.uc_link = nullptr;
+        makecontext(&f.ctx, trampoline, 0);
+    }
+    for (;;) {
+        int alive = 0;
+        const unsigned long before = s.progress;
+        for (int i = 0; i < n; ++i) {
+            Fiber& f = s.fibers[i];
+            if (f.done) continue;
+            ++alive;
+            s.cur = &f;
+            swapcontext(&s.sched, &f.ctx);
+            if (f.done) ++s.progress;
+        }
+        if (!alive) break;
+        if (s.progress == before) {
+            std::fprintf(stderr, "cuda_emu: deadlock (a barrier or warp collective some threads never reach)\n");
+            std::abort();
+        }
+    }
+    s.cur = nullptr;
+}
+}  // namespace emu
+
+inline uint3 emu_block_idx{0, 0, 0};
+inline dim3 emu_block_dim, emu_grid_dim;
+#define threadIdx (emu::st().cur->tid)
+#define blockIdx emu_block_idx
+#define blockDim emu_block_dim
+#define gridDim emu_grid_dim
+
+// grid launch: blocks one after the other (x fastest)
+template <typename F>
+inline void emu_launch(dim3 grid, dim3 block, F&& body) {
+    emu::st().body = body;
+    emu_block_dim = block;
+    emu_grid_dim = grid;
+    for (unsigned z = 0; z < grid.z; ++z)
+        for (unsigned y = 0; y < grid.y; ++y)
+            for (unsigned x = 0; x < grid.x; ++x) {
+                emu_block_idx = uint3{x, y, z};
+                emu::run_block(block);
+            }
+}
+
+inline void __syncthreads() {
+    emu::State& s = emu::st();
+    const unsigned gen = s.bar_gen;
+    if (++s.bar_count == s.nthreads) {
+        s.bar_count = 0;
+        ++s.bar_gen;
+        ++s.progress;
+    } else {
+        while (s.bar_gen == gen) emu::yield();
+    }
+}
+
+// warp rendezvous: every lane deposits a value and sees all 32 (full masks only, as everywhere in these kernels)
+inline const unsigned long long* emu_warp_gather(unsigned mask, unsigned long long v) {
+    if (mask != 0xffffffffu) { std::fprintf(stderr, "cuda_emu: partial warp mask\n"); std::abort(); }
+    emu::State& s = emu::st();
+    const int t = emu::linear_tid();
+    emu::WarpBox& w = s.warps[t >> 5];
+    w.vals[t & 31] = v;
+    const unsigned gen = w.gen;
+    const int lanes = (s.nthreads - (t & ~31)) < 32 ? (s.nthreads - (t & ~31)) : 32;
+    if (++w.count == lanes) {
+        std::memcpy(w.snap, w.vals, sizeof(w.snap));
+        w.count = 0;
+        ++w.gen;
+        ++s.progress;
+    } else {
+        while (w.gen == gen) emu::yield();
+    }
+    return w.snap;
+}
+template <typename T>
+inline unsigned long long emu_bits(T v) {
+    static_assert(sizeof(T) <= 8, "");
+    unsigned long long b = 0;
+    std::memcpy(&b, &v, sizeof(T));
+    return b;
+}
+template <typename T>
+inline T emu_unbits(unsigned long long b) {
+    T v;
+    std::memcpy(&v, &b, sizeof(T));
+    return v;
+}
+inline int emu_lane() { return emu::linear_tid() & 31; }
+template <typename T>
+inline T __shfl_sync(unsigned m, T v, int src) { return emu_unbits<T>(emu_warp_gather(m, emu_bits(v))[src & 31]); }
+template <typename T>
+inline T __shfl_up_sync(unsigned m, T v, unsigned d) {
+    const unsigned long long* s = emu_warp_gather(m, emu_bits(v));
+    const int l = emu_lane();
+    return l >= static_cast<int>(d) ? emu_unbits<T>(s[l - d]) : v;
+}
+template <typename T>
+inline T __shfl_xor_sync(unsigned m, T v, int x) { return emu_unbits<T>(emu_warp_gather(m, emu_bits(v))[(emu_lane() ^ x) & 31]); }
+inline unsigned __ballot_sync(unsigned m, int pred) {
+    const unsigned long long* s = emu_warp_gather(m, pred ? 1ull : 0ull);
+    unsigned r = 0;
+    for (int i = 0; i < 32; ++i) r |= (s[i] ? 1u : 0u) << i;
+    return r;
+}
+template <typename T>
+inline T emu_reduce(unsigned m, T v, int op) {
+    const unsigned long long* s = emu_warp_gather(m, emu_bits(v));
+    T r = emu_unbits<T>(s[0]);
+    for (int i = 1; i < 32; ++i) {
+        const T x = emu_unbits<T>(s[i]);
+        r = op == 0 ? static_cast<T>(r + x) : op == 1 ? (x < r ? x : r) : (x > r ? x : r);
+    }
+    return r;
+}
+inline unsigned __reduce_add_sync(unsigned m, unsigned v) { return emu_reduce(m, v, 0); }
+inline int __reduce_add_sync(unsigned m, int v) { return emu_reduce(m, v, 0); }
+inline unsigned __reduce_min_sync(unsigned m, unsigned v) { return emu_reduce(m, v, 1); }
+inline int __reduce_min_sync(unsigned m, int v) { return emu_reduce(m, v, 1); }
+inline unsigned __reduce_max_sync(unsigned m, unsigned v) { return emu_reduce(m, v, 2); }
+inline int __reduce_max_sync(unsigned m, int v) { return emu_reduce(m, v, 2); }
+
+// atomics: nothing runs concurrently
+inline unsigned atomicAdd(unsigned* p, unsigned v) { const unsigned o = *p; *p = o + v; return o; }
+inline int atomicAdd(int* p, int v) { const int o = *p; *p = static_cast<int>(static_cast<unsigned>(o) + static_cast<unsigned>(v)); return o; }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }
+
+template <typename T>
+inline T __ldg(const T* p) { return *p; }
+inline unsigned __umulhi(unsigned a, unsigned b) { return static_cast<unsigned>((static_cast<unsigned long long>(a) * b) >> 32); }
+inline int __ffs(unsigned v) { return __builtin_ffs(static_cast<int>(v)); }
+inline float __fmul_rn(float a, float b) { return a * b; }
+inline float __fsub_rn(float a, float b) { return a - b; }
+inline float __fadd_rn(float a, float b) { return a + b; }
+inline float __fdiv_rn(float a, float b) { return a / b; }
+inline float __frcp_rn(float a) { return 1.0f / a; }
+inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
+inline float __uint2float_rn(unsigned v) { return static_cast<float>(v); }
+inline float __int2float_rn(int v) { return static_cast<float>(v); }
+inline int __float2int_rz(float v) {            // cvt.rzi.s32.f32: NaN -> 0, saturating
+    if (v != v) return 0;
+    if (v >= 2147483648.0f) return INT_MAX;
+    if (v <= -2147483648.0f) return INT_MIN;
+    return static_cast<int>(v);
+}
+inline int __float2int_rn(float v) {            // cvt.rni.s32.f32
+    if (v != v) return 0;
+    const float r = std::nearbyintf(v);
+    if (r >= 2147483648.0f) return INT_MAX;
+    if (r <= -2147483648.0f) return INT_MIN;
+    return static_cast<int>(r);
+}
+inline long long __float2ll_rn(float v) {
+    if (v != v) return 0;
+    const float r = std::nearbyintf(v);
+    if (r >= 9223372036854775808.0f) return LLONG_MAX;
+    if (r <= -9223372036854775808.0f) return LLONG_MIN;
+    return static_cast<long long>(r);
+}
+inline long long __double2ll_rn(double v) {
+    if (v != v) return 0;
+    const double r = std::nearbyint(v);
+    if (r >= 9223372036854775808.0) return LLONG_MAX;
+    if (r <= -9223372036854775808.0) return LLONG_MIN;
+    return static_cast<long long>(r);
+}
+inline float __double2float_rn(double v) { return static_cast<float>(v); }
+inline unsigned __float_as_uint(float v) { return emu_unbits<unsigned>(emu_bits(v)); }
+inline float __uint_as_float(unsigned v) { return emu_unbits<float>(v); }
+template <typename A, typename B>
+inline typename std::common_type<A, B>::type min(A a, B b) {
+    typedef typename std::common_type<A, B>::type T;
+    return static_cast<T>(a) < static_cast<T>(b) ? static_cast<T>(a) : static_cast<T>(b);
+}
+template <typename A, typename B>
+inline typename std::common_type<A, B>::type max(A a, B b) {
+    typedef typename std::common_type<A, B>::type T;
+    return static_cast<T>(a) > static_cast<T>(b) ? static_cast<T>(a) : static_cast<T>(b);
+}
