@@ -688,6 +688,40 @@ band_partition2_kernel(const uint32_t* __restrict__ t, const uint16_t* __restric
     }
 }
 
+// One round of the accumulate loop: U records per lane (record lane + 32 * u of the run's next 32 * U), all loads
+// first.  FULL: every lane has all its records.  Otherwise `rem` records are left: a lane without one adds zero to a
+// cell of its own (cells 0..31: distinct banks), which keeps the code straight.
+template <bool HAS_T, int U, bool FULL>
+__device__ __forceinline__ void band_add_round(const unsigned* __restrict__ p32, const unsigned char* __restrict__ p8,
+                                               const unsigned short* __restrict__ p16, unsigned rem, int lane,
+                                               unsigned* __restrict__ s_acc) {
+    unsigned r32[U], r8[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const bool v = FULL || static_cast<unsigned>(lane) + 32u * u < rem;
+        r32[u] = 0u; r8[u] = 0u;
+        if constexpr (HAS_T) { if (v) { r32[u] = __ldg(p32 + 32 * u); r8[u] = __ldg(p8 + 32 * u); } }
+        else { if (v) r32[u] = __ldg(p16 + 32 * u); }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const bool v = FULL || static_cast<unsigned>(lane) + 32u * u < rem;
+        if constexpr (HAS_T) {
+            // sign * (2^44 + f) as the (high, low) words of the int64 addend
+            const unsigned fq = r32[u] >> 8;
+            const bool neg = (r8[u] & 0x80u) != 0u;
+            const unsigned cell = v ? ((r32[u] & 0xffu) | ((r8[u] & 0x7fu) << 8)) : static_cast<unsigned>(lane);
+            const unsigned lo = v ? (neg ? 0u - fq : fq) : 0u;
+            const int hi = v ? (neg ? -4096 - static_cast<int>(fq != 0u) : 4096) : 0;
+            const unsigned old = atomicAdd(s_acc + 2u * cell, lo);
+            atomicAdd(reinterpret_cast<int*>(s_acc) + 2u * cell + 1u, hi + static_cast<int>(old + lo < old));
+        } else {
+            const unsigned cell = v ? (r32[u] & 0x7fffu) : static_cast<unsigned>(lane);
+            atomicAdd(reinterpret_cast<int*>(s_acc) + cell, v ? ((r32[u] & 0x8000u) ? -1 : 1) : 0);
+        }
+    }
+}
+
 template <bool HAS_T>
 __global__ void __launch_bounds__(kBandAccThreads)
 band_accumulate2_kernel(const unsigned* __restrict__ table, const unsigned* __restrict__ rec32,
@@ -728,34 +762,11 @@ band_accumulate2_kernel(const unsigned* __restrict__ table, const unsigned* __re
             const unsigned* p32 = rec32 + off;
             const unsigned char* p8 = rec8 + off;
             const unsigned short* p16 = rec16 + off;
-            for (unsigned k0 = lane; k0 < len + lane; k0 += 32u * U, p32 += 32 * U, p8 += 32 * U, p16 += 32 * U) {
-                unsigned r32[U], r8[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {                   // loads first: U records in flight per lane
-                    const bool v = k0 + 32u * u < len;
-                    r32[u] = 0u; r8[u] = 0u;
-                    if constexpr (HAS_T) { if (v) { r32[u] = __ldg(p32 + 32 * u); r8[u] = __ldg(p8 + 32 * u); } }
-                    else { if (v) r32[u] = __ldg(p16 + 32 * u); }
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const bool v = k0 + 32u * u < len;
-                    if constexpr (HAS_T) {
-                        // sign * (2^44 + f) as the (high, low) words of the int64 addend; a lane without a record adds
-                        // zero to a cell of its own (cells 0..31: distinct banks), which keeps the code straight
-                        const unsigned fq = r32[u] >> 8;
-                        const bool neg = (r8[u] & 0x80u) != 0u;
-                        const unsigned cell = v ? ((r32[u] & 0xffu) | ((r8[u] & 0x7fu) << 8)) : static_cast<unsigned>(lane);
-                        const unsigned lo = v ? (neg ? 0u - fq : fq) : 0u;
-                        const int hi = v ? (neg ? -4096 - static_cast<int>(fq != 0u) : 4096) : 0;
-                        const unsigned old = atomicAdd(s_band_acc + 2u * cell, lo);
-                        atomicAdd(reinterpret_cast<int*>(s_band_acc) + 2u * cell + 1u, hi + static_cast<int>(old + lo < old));
-                    } else {
-                        const unsigned cell = v ? (r32[u] & 0x7fffu) : static_cast<unsigned>(lane);
-                        atomicAdd(reinterpret_cast<int*>(s_band_acc) + cell, v ? ((r32[u] & 0x8000u) ? -1 : 1) : 0);
-                    }
-                }
-            }
+            // whole rounds of 32 * U records run without a single predicate; the last, partial round selects
+            unsigned done = 0;
+            for (; done + 32u * U <= len; done += 32u * U, p32 += 32 * U, p8 += 32 * U, p16 += 32 * U)
+                band_add_round<HAS_T, U, true>(p32, p8, p16, 0u, lane, s_band_acc);
+            if (done < len) band_add_round<HAS_T, U, false>(p32, p8, p16, len - done, lane, s_band_acc);
         }
     }
     __syncthreads();
