@@ -577,6 +577,7 @@ band_partition2_kernel(const uint32_t* __restrict__ t, const uint16_t* __restric
 
     unsigned slot[kBandPartGroups][8];      // bucket << 21 | rank << 8 | (B > 1) cell high bits | neg << 7
     unsigned rec[kBandPartGroups][8];       // B > 1: f << 8 | cell low byte;  B == 1: cell | neg << 15
+    int odd = 0;                            // a polarity byte beyond {0, 1}: its record says +1, band_fixup_kernel adds the rest
 #pragma unroll
     for (int j = 0; j < kBandPartGroups; ++j) {
         const unsigned xs[4] = {ev[j].x.x, ev[j].x.y, ev[j].x.z, ev[j].x.w}, ys[4] = {ev[j].y.x, ev[j].y.y, ev[j].y.z, ev[j].y.w};
@@ -587,7 +588,7 @@ band_partition2_kernel(const uint32_t* __restrict__ t, const uint16_t* __restric
             const unsigned ey = (e & 1) ? (ys[e >> 1] >> 16) : (ys[e >> 1] & 0xffffu);
             bool valid = alive && ex < static_cast<unsigned>(W) && ey < static_cast<unsigned>(H);
             const unsigned pol = ((e < 4 ? ev[j].p.x : ev[j].p.y) >> (8 * (e & 3))) & 0xffu;
-            const unsigned neg = pol == 0u ? 1u : 0u;                           // value = 2 * pol - 1 (dsec.py:45), pol in {0, 1}
+            const unsigned neg = pol == 0u ? 1u : 0u;                           // value = 2 * pol - 1 (dsec.py:45): -1, +1, or more
             const unsigned band = g.rows > 1 ? __umulhi(ey, g.inv_rows) : ey;
             const unsigned cell = (ey - band * static_cast<unsigned>(g.rows)) * static_cast<unsigned>(W) + ex;    // junk unless valid
             unsigned bucket = band, rec_hi = 0u;
@@ -605,10 +606,11 @@ band_partition2_kernel(const uint32_t* __restrict__ t, const uint16_t* __restric
                 rec[j][e] = (cell & 0x7fffu) | (neg << 15);
             }
             bucket = valid ? bucket : static_cast<unsigned>(NB);
+            odd |= static_cast<int>(valid && pol > 1u);
             slot[j][e] = (bucket << 21) | (atomicAdd(&s_hist[bucket], 1u) << 8) | rec_hi;
         }
     }
-    __syncthreads();
+    const int any_odd = __syncthreads_or(odd);
     // exclusive scan of the NB + 1 bucket counts (each thread owns a contiguous run of buckets; with the usual
     // hundred-odd buckets only the first warps own any, the others go straight to the barriers)
     const int per = (NB + 1 + kBandPartThreads - 1) / kBandPartThreads;
@@ -642,7 +644,8 @@ band_partition2_kernel(const uint32_t* __restrict__ t, const uint16_t* __restric
     __syncthreads();
     if (owner_warp) {
         unsigned run = s_warp[wid] + inc - mine;
-        unsigned* row = table + static_cast<size_t>(bt.chunk_base[s] + c) * (NB + 1);
+        unsigned* row = table + static_cast<size_t>(bt.chunk_base[s] + c) * (NB + 2);
+        if (threadIdx.x == 0) row[NB + 1] = static_cast<unsigned>(any_odd);     // read by band_fixup_kernel
         for (int j = 0; j < per; ++j) {
             const int k = threadIdx.x * per + j;
             if (k <= NB) {
@@ -743,7 +746,7 @@ band_accumulate2_kernel(const unsigned* __restrict__ table, const unsigned* __re
     const unsigned bucket = static_cast<unsigned>(k) * static_cast<unsigned>(g.nbands) + static_cast<unsigned>(band);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     constexpr int nwarps = kBandAccThreads / 32;
-    const size_t row_words = static_cast<size_t>(g.nbuckets) + 1;
+    const size_t row_words = static_cast<size_t>(g.nbuckets) + 2;      // offsets, record count, odd-polarity flag
     const unsigned* tbl = table + static_cast<size_t>(bt.chunk_base[s]) * row_words + bucket;
     const size_t base_s = static_cast<size_t>(bt.rec_base[s]);
     for (int c0 = 0; c0 < nchunks; c0 += 32 * nwarps) {
@@ -779,6 +782,59 @@ band_accumulate2_kernel(const unsigned* __restrict__ table, const unsigned* __re
     } else {
         int* dst = reinterpret_cast<int*>(R) + static_cast<size_t>(s) * plane + band_off;
         for (unsigned i = threadIdx.x; i < band_cells; i += kBandAccThreads) dst[i] = static_cast<int>(s_band_acc[i]);
+    }
+}
+
+
+// Arbitrary polarity bytes (the reference computes value = 2 * p - 1 for whatever p holds, dsec.py:45, 349): a record
+// carries one sign bit, so an event with p > 1 went through the passes above as +1; here the remaining value - 1 is
+// added with the RED of sensor_accumulate_kernel, after band_accumulate2_kernel has stored R.  DSEC stores {0, 1}: every
+// chunk flag is clear and the 32-chunks-per-CTA grid below costs a few hundred flag reads.
+constexpr int kBandFixupChunks = 32;
+template <bool HAS_T, bool VEC>
+__global__ void __launch_bounds__(kBandPartThreads)
+band_fixup_kernel(const uint32_t* __restrict__ t, const uint16_t* __restrict__ x, const uint16_t* __restrict__ y,
+                  const uint8_t* __restrict__ p, const __grid_constant__ WindowTable tab, const __grid_constant__ BandTable bt,
+                  BandGeom g, int H, int W, int B, const unsigned* __restrict__ table, void* __restrict__ R) {
+    const int s = blockIdx.y;
+    const int nchunks = bt.nchunks[s];
+    const WindowDesc wd = tab.w[s];
+    const size_t plane = static_cast<size_t>(H) * W;
+    for (int c = blockIdx.x * kBandFixupChunks; c < min((blockIdx.x + 1) * kBandFixupChunks, nchunks); ++c) {
+        if (__ldg(table + static_cast<size_t>(bt.chunk_base[s] + c) * (g.nbuckets + 2) + g.nbuckets + 1) == 0u) continue;   // uniform
+        const long long g0 = wd.start >> 3, g1 = (wd.end + 7) >> 3;
+        const long long first = g0 + static_cast<long long>(c) * (kBandPartThreads * kBandPartGroups);
+        const RawWindowTime rw = raw_window_time(t, wd.start, wd.end, B);      // alive: a dead window raises no flag
+        const float r_dT = __frcp_rn(rw.fdT);
+        for (int j = 0; j < kBandPartGroups; ++j) {
+            const long long grp = first + static_cast<long long>(j) * kBandPartThreads + threadIdx.x;
+            if (grp >= g1) continue;
+            const SensEv8 ev = sens_load8<HAS_T, VEC>(t, x, y, p, grp << 3, wd.start, wd.end);
+            const unsigned xs[4] = {ev.x.x, ev.x.y, ev.x.z, ev.x.w}, ys[4] = {ev.y.x, ev.y.y, ev.y.z, ev.y.w};
+            const unsigned ts[8] = {ev.t0.x, ev.t0.y, ev.t0.z, ev.t0.w, ev.t1.x, ev.t1.y, ev.t1.z, ev.t1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const unsigned pol = ((e < 4 ? ev.p.x : ev.p.y) >> (8 * (e & 3))) & 0xffu;
+                if (pol <= 1u) continue;
+                const unsigned ex = (e & 1) ? (xs[e >> 1] >> 16) : (xs[e >> 1] & 0xffffu);
+                const unsigned ey = (e & 1) ? (ys[e >> 1] >> 16) : (ys[e >> 1] & 0xffffu);
+                if (ex >= static_cast<unsigned>(W) || ey >= static_cast<unsigned>(H)) continue;
+                const long long rest = 2LL * pol - 2;                           // value - 1
+                const size_t pix = static_cast<size_t>(ey) * W + ex;
+                if constexpr (HAS_T) {
+                    const float fdt = __uint2float_rn(ts[e] - rw.t_first);
+                    const float tn = __fmul_rn(rw.cm1, div_by_reused(fdt, rw.fdT, r_dT));
+                    const int tb = __float2int_rz(tn);
+                    if (static_cast<unsigned>(tb) >= static_cast<unsigned>(B)) continue;
+                    const float f = __fsub_rn(tn, __int2float_rn(tb));
+                    const long long fq = static_cast<long long>(__float2int_rn(__fmul_rn(f, 16777216.0f)));
+                    atomicAdd(reinterpret_cast<unsigned long long*>(R) + (static_cast<size_t>(s) * B + tb) * plane + pix,
+                              static_cast<unsigned long long>(rest * ((1LL << kCountShift) + fq)));
+                } else {
+                    atomicAdd(reinterpret_cast<int*>(R) + static_cast<size_t>(s) * plane + pix, static_cast<int>(rest));
+                }
+            }
+        }
     }
 }
 
@@ -1269,7 +1325,8 @@ static BandScratch band_carve(char* base, long long chunks, const BandGeom& g, i
     size_t off = 0;
     auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += align_up(bytes, 256); return p; };
     const size_t slots = static_cast<size_t>(chunks > 0 ? chunks : 1) * kBandChunk;
-    z.table = reinterpret_cast<unsigned*>(take(sizeof(unsigned) * static_cast<size_t>(chunks > 0 ? chunks : 1) * (g.nbuckets + 1)));
+    // a row per chunk: bucket offsets, record count and (second cut) the odd-polarity flag
+    z.table = reinterpret_cast<unsigned*>(take(sizeof(unsigned) * static_cast<size_t>(chunks > 0 ? chunks : 1) * (g.nbuckets + 2)));
     if (B > 1) {
         z.rec32 = reinterpret_cast<unsigned*>(take(sizeof(unsigned) * slots));
         z.rec8 = reinterpret_cast<unsigned char*>(take(slots));
@@ -1426,6 +1483,18 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
                 CMDA_BAND_ACC_KERNEL<true><<<items, kBandAccThreads, shm, st>>>(z.table, z.rec32, z.rec8, z.rec16, bt, bg, H, W, B, R);
             }
 #undef CMDA_BAND_ACC_KERNEL
+#if CMDA_BAND_V2
+            if (max_chunks > 0) {
+                dim3 fgrid(static_cast<unsigned>((max_chunks + kBandFixupChunks - 1) / kBandFixupChunks), S);
+                if (B == 1) {
+                    if (vec) band_fixup_kernel<false, true><<<fgrid, kBandPartThreads, 0, st>>>(t, x, y, p, tab, bt, bg, H, W, B, z.table, R);
+                    else band_fixup_kernel<false, false><<<fgrid, kBandPartThreads, 0, st>>>(t, x, y, p, tab, bt, bg, H, W, B, z.table, R);
+                } else {
+                    if (vec) band_fixup_kernel<true, true><<<fgrid, kBandPartThreads, 0, st>>>(t, x, y, p, tab, bt, bg, H, W, B, z.table, R);
+                    else band_fixup_kernel<true, false><<<fgrid, kBandPartThreads, 0, st>>>(t, x, y, p, tab, bt, bg, H, W, B, z.table, R);
+                }
+            }
+#endif
             CMDA_LAUNCH_CHECK();
         }
     } else if (max_events > 0) {

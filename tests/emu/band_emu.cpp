@@ -30,6 +30,9 @@ static void run_banded(const uint32_t* t, const uint16_t* x, const uint16_t* y, 
         if (CUT == 1) band_accumulate_kernel<HAS_T>(table, rec32, rec8, rec16, bt, g, H, W, B, R);
         else band_accumulate2_kernel<HAS_T>(table, rec32, rec8, rec16, bt, g, H, W, B, R);
     });
+    if (CUT == 2 && max_chunks > 0)
+        emu_launch(dim3(static_cast<unsigned>((max_chunks + kBandFixupChunks - 1) / kBandFixupChunks), S), dim3(kBandPartThreads),
+                   [&] { band_fixup_kernel<HAS_T, VEC>(t, x, y, p, tab, bt, g, H, W, B, table, R); });
 }
 
 template <bool HAS_T, bool VEC>
@@ -85,7 +88,7 @@ extern "C" int emu_stage_a(const uint32_t* t, const uint16_t* x, const uint16_t*
     }
     const size_t slots = static_cast<size_t>(chunks > 0 ? chunks : 1) * kBandChunk;
     // garbage-filled scratch: nothing may rely on zeroed workspace
-    std::vector<unsigned> table(static_cast<size_t>(chunks > 0 ? chunks : 1) * (g.nbuckets + 1), 0xdeadbeefu);
+    std::vector<unsigned> table(static_cast<size_t>(chunks > 0 ? chunks : 1) * (g.nbuckets + 2), 0xdeadbeefu);
     std::vector<unsigned> rec32(B > 1 ? slots : 4, 0xa5a5a5a5u);
     std::vector<unsigned char> rec8(B > 1 ? slots : 4, 0x5a);
     std::vector<unsigned short> rec16(B == 1 ? slots : 4, 0xa5a5);

@@ -156,6 +156,23 @@ inline void __syncthreads() {
     }
 }
 
+inline int __syncthreads_or(int pred) {
+    emu::State& s = emu::st();
+    static int acc = 0, result = 0;
+    acc |= pred != 0;
+    const unsigned gen = s.bar_gen;
+    if (++s.bar_count == s.nthreads) {
+        result = acc;
+        acc = 0;
+        s.bar_count = 0;
+        ++s.bar_gen;
+        ++s.progress;
+    } else {
+        while (s.bar_gen == gen) emu::yield();
+    }
+    return result;
+}
+
 // warp rendezvous: every lane deposits a value and sees all 32 (full masks only, as everywhere in these kernels)
 inline const unsigned long long* emu_warp_gather(unsigned mask, unsigned long long v) {
     if (mask != 0xffffffffu) { std::fprintf(stderr, "cuda_emu: partial warp mask\n"); std::abort(); }

@@ -72,7 +72,7 @@ def test_voxel_modes_and_banded_workspace(L):
         extra = band - fact
         chunks = n * S // chunk + 2 * S
         assert extra >= rec_bytes * n * S                                   # every event has a record slot
-        assert extra <= rec_bytes * chunks * chunk + 4 * chunks * (24 * bins + 1) + 4096     # ... and little else
+        assert extra <= rec_bytes * chunks * chunk + 4 * chunks * (24 * bins + 2) + 4096     # ... and little else
         # more events -> more workspace, never less
         assert L.cmda_events_vg_workspace_bytes(2 * n * S, S, H, W, bins, _lib.VOXEL_BANDED) > band
     # a grid wider than one band can hold (B > 1: 24 576 cells): BANDED adds nothing, FACTORED's size remains

@@ -57,7 +57,7 @@ def direct_R(t, x, y, p, start, end, H, W, B):
     ok = (xx < W) & (yy < H) & (tb >= 0) & (tb < B)
     f = (tn - tb.astype(np.float32)).astype(np.float32)
     fq = np.rint(f * np.float32(16777216.0)).astype(np.int64)
-    sign = np.where(pp != 0, 1, -1).astype(np.int64)
+    sign = 2 * pp.astype(np.int64) - 1                              # dsec.py:45 on whatever the polarity byte holds
     val = sign * ((1 << 44) + fq) if B > 1 else sign
     np.add.at(R, (tb[ok], yy[ok], xx[ok]), val[ok])
     cnt = np.bincount(tb[ok], minlength=B).astype(np.uint64)
@@ -96,6 +96,28 @@ def test_banded_kernels_match_red_kernel_and_definition(emu, H, W, bins):
         got, got_bins = stage_a(emu, t, x, y, p, starts, ends, H, W, bins, variant)
         assert np.array_equal(got, red), f"BANDED cut {variant}: R differs from the RED kernel's"
         assert np.array_equal(got_bins, red_bins), f"BANDED cut {variant}: per-bin counts differ"
+
+
+@pytest.mark.parametrize("bins", [1, 4])
+def test_second_cut_handles_any_polarity_byte(emu, bins):
+    """value = 2 * p - 1 for whatever p holds (dsec.py:45, 349): the RED kernel multiplies by it, the second BANDED cut
+    records +1 and adds the rest in band_fixup_kernel for the chunks whose flag is up (the first cut keeps the DSEC
+    alphabet {0, 1} as a precondition)."""
+    H, W, n = 37, 53, 25_000
+    t, x, y, p = make_events(n, H, W, seed=77)
+    rng = np.random.default_rng(3)
+    weird = rng.choice(n, size=400, replace=False)
+    p[weird] = rng.choice(np.array([2, 3, 7, 128, 255], dtype=np.uint8), size=400)
+    p[9000:17500] = rng.integers(0, 2, size=8500).astype(np.uint8)          # at least one whole chunk without any
+    x[weird[:5]] = W                                                    # an odd polarity outside the sensor: dropped
+    starts, ends = [0, 5, 12_345], [n, 8192 + 5, 12_346]
+    red, red_bins = stage_a(emu, t, x, y, p, starts, ends, H, W, bins, 0)
+    for s in range(len(starts)):
+        want, cnt = direct_R(t, x, y, p, starts[s], ends[s], H, W, bins)
+        assert np.array_equal(red[s].astype(np.int64).reshape(bins, H, W), want)
+        assert np.array_equal(red_bins[s], cnt)
+    got, got_bins = stage_a(emu, t, x, y, p, starts, ends, H, W, bins, 2)
+    assert np.array_equal(got, red) and np.array_equal(got_bins, red_bins)
 
 
 def test_banded_kernels_scalar_load_path(emu):
