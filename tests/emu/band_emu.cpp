@@ -3,6 +3,7 @@
 // that the variants can be compared bit for bit where no GPU exists.  The kernel code is the transformed copy of
 // cmda_b200/csrc/voxel_factored.cu (everything above its host launch section) made by build_emu.py; the launch
 // bookkeeping below restates launch_factored's.
+#define EMU_DEFINE_SWITCH 1
 #include "gen/voxel_factored_kernels.inc"
 
 namespace cmda {

@@ -51,6 +51,84 @@ def generate() -> None:
         f.write(vf)
 
 
+def _split_top(text: str):
+    """Split at top-level commas (brackets of any kind nest)."""
+    parts, depth, cur = [], 0, ""
+    for ch in text:
+        if ch in "([{<":
+            depth += 1
+        elif ch in ")]}>":
+            depth -= 1
+        if ch == "," and depth == 0:
+            parts.append(cur)
+            cur = ""
+        else:
+            cur += ch
+    parts.append(cur)
+    return parts
+
+
+def transform_launches(src: str) -> str:
+    """`kernel<T...><<<grid, block, shm, stream>>>(args);` -> `emu_launch(grid, block, [&] { kernel<T...>(args); });`"""
+    out, pos = "", 0
+    pat = re.compile(r"([A-Za-z_][A-Za-z0-9_]*(?:<[^<>;(){}]*>)?)<<<")
+    while True:
+        m = pat.search(src, pos)
+        if not m:
+            return out + src[pos:]
+        close = src.index(">>>", m.end())
+        cfg = _split_top(src[m.end():close])
+        assert len(cfg) in (2, 3, 4), cfg
+        # the argument list: from the '(' after >>> to its matching ')'
+        a0 = close + 3
+        assert src[a0] == "(", src[a0:a0 + 20]
+        depth, i = 0, a0
+        while True:
+            if src[i] == "(":
+                depth += 1
+            elif src[i] == ")":
+                depth -= 1
+                if depth == 0:
+                    break
+            i += 1
+        args = src[a0 + 1:i]
+        out += src[pos:m.start()] + f"emu_launch({cfg[0].strip()}, {cfg[1].strip()}, [&] {{ {m.group(1)}({args}); }})"
+        pos = i + 1
+
+
+def generate_full() -> None:
+    """Whole translation units (kernels AND their host launch code) for the emulated voxel path."""
+    generate()
+    gen = os.path.join(BUILD, "gen")
+    for name in ("voxel_factored.cu", "norm.cu"):
+        with open(os.path.join(CSRC, name)) as f:
+            src = f.read()
+        src = re.sub(r"extern __shared__( __align__\(\d+\))?", "extern", src)
+        src = transform_launches(src)
+        assert "<<<" not in src and "asm" not in src.replace("masm", "")
+        with open(os.path.join(gen, name.replace(".cu", ".cpp")), "w") as f:
+            f.write(src)
+
+
+def build_vg(v2: bool = False, force: bool = False) -> str:
+    """tests/emu/_build/libvg_emu[_v2].so: launch_factored + launch_norm_apply (the real host launch code and every
+    kernel under it) on the emulation, behind emu_events_vg (vg_emu.cpp)."""
+    lib = os.path.join(BUILD, "libvg_emu_v2.so" if v2 else "libvg_emu.so")
+    srcs = [os.path.join(CSRC, n) for n in ("common.cuh", "event_math.cuh", "voxel_factored.cu", "norm.cu")] + \
+           [os.path.join(HERE, "vg_emu.cpp"), os.path.join(HERE, "include", "cuda_runtime.h"), os.path.abspath(__file__)]
+    if not force and os.path.isfile(lib) and all(os.path.getmtime(lib) >= os.path.getmtime(s) for s in srcs):
+        return lib
+    generate_full()
+    gen = os.path.join(BUILD, "gen")
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-w",
+           "-I", os.path.join(HERE, "include"), "-I", gen] + (["-DCMDA_BAND_V2=1"] if v2 else []) + \
+          ["-o", lib, os.path.join(HERE, "vg_emu.cpp"), os.path.join(gen, "voxel_factored.cpp"), os.path.join(gen, "norm.cpp")]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("emulation build failed:\n" + res.stderr[-8000:])
+    return lib
+
+
 def build(force: bool = False) -> str:
     srcs = [os.path.join(CSRC, n) for n in ("common.cuh", "event_math.cuh", "voxel_factored.cu")] + \
            [os.path.join(HERE, "band_emu.cpp"), os.path.join(HERE, "include", "cuda_runtime.h"), os.path.abspath(__file__)]
@@ -67,3 +145,5 @@ def build(force: bool = False) -> str:
 
 if __name__ == "__main__":
     print(build(force=True))
+    print(build_vg(False, force=True))
+    print(build_vg(True, force=True))

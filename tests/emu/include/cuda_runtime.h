@@ -1,12 +1,10 @@
 // TEST INFRASTRUCTURE ONLY -- a CPU stand-in for the handful of CUDA constructs the cmda_b200 kernels use, so that the
 // kernel SOURCE (a transformed copy made by tests/emu/build_emu.py) can be executed on the host for small inputs where
-// no GPU exists: every CUDA thread of a block is a ucontext fiber on ONE host thread, __syncthreads and the warp
+// no GPU exists: every CUDA thread of a block is a fiber (own stack, hand-rolled switch) on ONE host thread, __syncthreads and the warp
 // collectives are rendezvous points, atomics are plain read-modify-writes (nothing runs concurrently).  It checks
 // kernel LOGIC (indexing, barriers, packing, carry arithmetic); it is not a product path, not an oracle and says
 // nothing about performance.  Never linked into libcmda_b200.so.
 #pragma once
-#include <ucontext.h>
-
 #include <climits>
 #include <cmath>
 #include <cstdint>
@@ -49,10 +47,28 @@ typedef void* cudaEvent_t;
 enum cudaError_t { cudaSuccess = 0 };
 inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaPeekAtLastError() { return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { std::memset(p, v, n); return cudaSuccess; }
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+template <typename F>
+inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+
+#if !defined(__x86_64__)
+#error "tests/emu switches fibers with a few lines of x86-64 assembly"
+#endif
+// emu_switch(&save_sp, new_sp): push the callee-saved registers, park this stack pointer, adopt the other one.
+// (ucontext's swapcontext costs a signal-mask system call per switch; a block of 512 threads switches a lot.)
+extern "C" void emu_switch(void** save_sp, void* new_sp);
+#ifdef EMU_DEFINE_SWITCH
+asm(".text\n.globl emu_switch\n.type emu_switch,@function\nemu_switch:\n"
+    "  pushq %rbp\n  pushq %rbx\n  pushq %r12\n  pushq %r13\n  pushq %r14\n  pushq %r15\n"
+    "  movq %rsp, (%rdi)\n  movq %rsi, %rsp\n"
+    "  popq %r15\n  popq %r14\n  popq %r13\n  popq %r12\n  popq %rbx\n  popq %rbp\n  ret\n"
+    ".size emu_switch,.-emu_switch\n");
+#endif
 
 namespace emu {
 struct Fiber {
-    ucontext_t ctx;
+    void* sp;
     uint3 tid;
     bool done;
     std::vector<char> stack;
@@ -65,7 +81,7 @@ struct WarpBox {
 struct State {
     std::vector<Fiber> fibers;
     std::vector<WarpBox> warps;
-    ucontext_t sched;
+    void* sched_sp = nullptr;
     Fiber* cur = nullptr;
     int nthreads = 0, bar_count = 0;
     unsigned bar_gen = 0;
@@ -73,12 +89,13 @@ struct State {
     std::function<void()> body;
 };
 inline State& st() { static State s; return s; }
-inline void yield() { State& s = st(); swapcontext(&s.cur->ctx, &s.sched); }
+inline void yield() { State& s = st(); emu_switch(&s.cur->sp, s.sched_sp); }
 inline void trampoline() {
     State& s = st();
     s.body();
     s.cur->done = true;
-    swapcontext(&s.cur->ctx, &s.sched);
+    emu_switch(&s.cur->sp, s.sched_sp);      // never resumed
+    std::abort();
 }
 inline int linear_tid() { return static_cast<int>(st().cur - st().fibers.data()); }
 
@@ -96,11 +113,12 @@ inline void run_block(dim3 block) {
         f.done = false;
         f.tid = uint3{static_cast<unsigned>(i) % block.x, (static_cast<unsigned>(i) / block.x) % block.y,
                       static_cast<unsigned>(i) / (block.x * block.y)};
-        getcontext(&f.ctx);
-        f.ctx.uc_stack.ss_sp = f.stack.data();
-        f.ctx.uc_stack.ss_size = f.stack.size();
-        f.ctx.uc_link = nullptr;
-        makecontext(&f.ctx, trampoline, 0);
+        // first switch "returns" into trampoline with the stack the ABI expects at a function entry (rsp = 16k + 8)
+        uintptr_t top = (reinterpret_cast<uintptr_t>(f.stack.data()) + f.stack.size()) & ~static_cast<uintptr_t>(15);
+        void** frame = reinterpret_cast<void**>(top) - 8;       // r15 r14 r13 r12 rbx rbp | return address | pad
+        for (int k = 0; k < 8; ++k) frame[k] = nullptr;
+        frame[6] = reinterpret_cast<void*>(&trampoline);
+        f.sp = frame;
     }
     for (;;) {
         int alive = 0;
@@ -110,7 +128,7 @@ inline void run_block(dim3 block) {
             if (f.done) continue;
             ++alive;
             s.cur = &f;
-            swapcontext(&s.sched, &f.ctx);
+            emu_switch(&s.sched_sp, f.sp);
             if (f.done) ++s.progress;
         }
         if (!alive) break;
@@ -284,8 +302,14 @@ inline long long __double2ll_rn(double v) {
     return static_cast<long long>(r);
 }
 inline float __double2float_rn(double v) { return static_cast<float>(v); }
+inline float __ll2float_rn(long long v) { return static_cast<float>(v); }
+inline float __fsqrt_rn(float v) { return std::sqrt(v); }
+inline float __int_as_float(int v) { return emu_unbits<float>(static_cast<unsigned>(v)); }
+inline int __float_as_int(float v) { return static_cast<int>(emu_unbits<unsigned>(emu_bits(v))); }
 inline unsigned __float_as_uint(float v) { return emu_unbits<unsigned>(emu_bits(v)); }
 inline float __uint_as_float(unsigned v) { return emu_unbits<float>(v); }
+using std::isnan;
+using std::isinf;
 template <typename A, typename B>
 inline typename std::common_type<A, B>::type min(A a, B b) {
     typedef typename std::common_type<A, B>::type T;

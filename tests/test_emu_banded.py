@@ -7,10 +7,13 @@ no code path with the product (which has no CPU fallback) and proves nothing abo
 (`-m gpu`) remain the gate for the CUDA build."""
 import ctypes
 import os
+import platform
 import sys
 
 import numpy as np
 import pytest
+
+pytestmark = pytest.mark.skipif(platform.machine() != "x86_64", reason="tests/emu switches fibers with x86-64 assembly")
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
 import build_emu  # noqa: E402
