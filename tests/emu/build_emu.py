@@ -129,6 +129,46 @@ def build_vg(v2: bool = False, force: bool = False) -> str:
     return lib
 
 
+FULL_UNITS = ("api.cu", "slicer.cu", "voxel_global.cu", "voxel_factored.cu", "norm.cu", "pseudo_events.cu", "resize.cu")
+
+
+def build_abi(v2: bool = False, force: bool = False) -> str:
+    """tests/emu/_build/libcmda_b200_emu[_v2].so: the C ABI of include/cmda_b200.h with every translation unit except
+    the TILED (inline-PTX shared atomics) and EXACT (cub sort) modes compiled against the emulation; those two modes
+    answer CMDA_ERR_UNSUPPORTED (abi_emu.cpp).  "Device" pointers are host pointers."""
+    lib = os.path.join(BUILD, "libcmda_b200_emu_v2.so" if v2 else "libcmda_b200_emu.so")
+    srcs = [os.path.join(CSRC, n) for n in ("common.cuh", "event_math.cuh") + FULL_UNITS] + \
+           [os.path.join(HERE, "abi_emu.cpp"), os.path.join(HERE, "include", "cuda_runtime.h"), os.path.abspath(__file__),
+            os.path.join(ROOT, "include", "cmda_b200.h")]
+    if not force and os.path.isfile(lib) and all(os.path.getmtime(lib) >= os.path.getmtime(s) for s in srcs):
+        return lib
+    generate()
+    gen = os.path.join(BUILD, "gen")
+    objs, procs = [], []
+    flags = ["-std=c++17", "-O1", "-g", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-w", "-I", os.path.join(HERE, "include"),
+             "-I", gen] + (["-DCMDA_BAND_V2=1"] if v2 else [])
+    for name in FULL_UNITS:
+        with open(os.path.join(CSRC, name)) as f:
+            src = f.read()
+        src = re.sub(r"extern __shared__( __align__\(\d+\))?", "extern", src)
+        src = transform_launches(src)
+        assert "<<<" not in src and "asm" not in src.replace("masm", ""), name
+        cpp = os.path.join(gen, name.replace(".cu", ".cpp"))
+        with open(cpp, "w") as f:
+            f.write(src)
+        obj = os.path.join(gen, name.replace(".cu", "_v2.o" if v2 else ".o"))
+        objs.append(obj)
+        procs.append((name, subprocess.Popen(["g++"] + flags + ["-c", "-o", obj, cpp], stderr=subprocess.PIPE, text=True)))
+    for name, pr in procs:
+        err = pr.communicate()[1]
+        if pr.returncode != 0:
+            raise RuntimeError(f"emulation build of {name} failed:\n" + err[-8000:])
+    res = subprocess.run(["g++"] + flags + ["-shared", "-o", lib, os.path.join(HERE, "abi_emu.cpp")] + objs, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("emulation link failed:\n" + res.stderr[-8000:])
+    return lib
+
+
 def build(force: bool = False) -> str:
     srcs = [os.path.join(CSRC, n) for n in ("common.cuh", "event_math.cuh", "voxel_factored.cu")] + \
            [os.path.join(HERE, "band_emu.cpp"), os.path.join(HERE, "include", "cuda_runtime.h"), os.path.abspath(__file__)]
@@ -147,3 +187,5 @@ if __name__ == "__main__":
     print(build(force=True))
     print(build_vg(False, force=True))
     print(build_vg(True, force=True))
+    print(build_abi(False, force=True))
+    print(build_abi(True, force=True))

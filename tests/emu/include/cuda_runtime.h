@@ -29,7 +29,10 @@
 struct uint2 { unsigned x, y; };
 struct uint3 { unsigned x, y, z; };
 struct uint4 { unsigned x, y, z, w; };
+struct int2 { int x, y; };
 struct int4 { int x, y, z, w; };
+struct uchar4 { unsigned char x, y, z, w; };
+struct ushort2 { unsigned short x, y; };
 struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };
 struct dim3 {
@@ -38,6 +41,7 @@ struct dim3 {
 };
 inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
 inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
+inline int2 make_int2(int x, int y) { return int2{x, y}; }
 inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
 inline float2 make_float2(float x, float y) { return float2{x, y}; }
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
@@ -48,6 +52,15 @@ enum cudaError_t { cudaSuccess = 0 };
 inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaPeekAtLastError() { return cudaSuccess; }
 inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { std::memset(p, v, n); return cudaSuccess; }
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { std::memmove(d, s, n); return cudaSuccess; }
+enum cudaMemoryType { cudaMemoryTypeUnregistered, cudaMemoryTypeHost, cudaMemoryTypeDevice, cudaMemoryTypeManaged };
+struct cudaPointerAttributes { cudaMemoryType type; };
+inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void*) { a->type = cudaMemoryTypeHost; return cudaSuccess; }
+inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = std::malloc(1); return cudaSuccess; }
+inline cudaError_t cudaEventDestroy(cudaEvent_t e) { std::free(e); return cudaSuccess; }
+inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.0f; return cudaSuccess; }
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 template <typename F>
 inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
@@ -75,7 +88,8 @@ struct Fiber {
 };
 struct WarpBox {
     unsigned long long vals[32], snap[32];
-    int count;
+    unsigned present, snap_present;     // lanes that deposited (threads that have exited take no part: CUDA's rule
+    int count, alive;                   // for *_sync is "all non-exited threads named in the mask")
     unsigned gen;
 };
 struct State {
@@ -83,30 +97,34 @@ struct State {
     std::vector<WarpBox> warps;
     void* sched_sp = nullptr;
     Fiber* cur = nullptr;
-    int nthreads = 0, bar_count = 0;
+    int nthreads = 0, alive = 0, bar_count = 0;
     unsigned bar_gen = 0;
     unsigned long progress = 0;
     std::function<void()> body;
 };
 inline State& st() { static State s; return s; }
+inline int linear_tid() { return static_cast<int>(st().cur - st().fibers.data()); }
 inline void yield() { State& s = st(); emu_switch(&s.cur->sp, s.sched_sp); }
 inline void trampoline() {
     State& s = st();
     s.body();
     s.cur->done = true;
+    --s.alive;
+    --s.warps[linear_tid() >> 5].alive;
     emu_switch(&s.cur->sp, s.sched_sp);      // never resumed
     std::abort();
 }
-inline int linear_tid() { return static_cast<int>(st().cur - st().fibers.data()); }
 
 // one block: every thread is a fiber, resumed round-robin until all have returned
 inline void run_block(dim3 block) {
     State& s = st();
     const int n = static_cast<int>(block.x * block.y * block.z);
     s.nthreads = n;
+    s.alive = n;
     s.bar_count = 0;
     if (static_cast<int>(s.fibers.size()) < n) s.fibers.resize(n);
     s.warps.assign((n + 31) / 32, WarpBox{});
+    for (int i = 0; i < n; ++i) ++s.warps[i >> 5].alive;
     for (int i = 0; i < n; ++i) {
         Fiber& f = s.fibers[i];
         if (f.stack.empty()) f.stack.resize(256 * 1024);
@@ -162,15 +180,21 @@ inline void emu_launch(dim3 grid, dim3 block, F&& body) {
             }
 }
 
+// barriers and warp collectives wait for the threads that have not exited (a waiter re-checks after every switch:
+// the thread it was waiting for may have returned instead of arriving)
 inline void __syncthreads() {
     emu::State& s = emu::st();
     const unsigned gen = s.bar_gen;
-    if (++s.bar_count == s.nthreads) {
-        s.bar_count = 0;
-        ++s.bar_gen;
-        ++s.progress;
-    } else {
-        while (s.bar_gen == gen) emu::yield();
+    ++s.bar_count;
+    for (;;) {
+        if (s.bar_gen != gen) return;
+        if (s.bar_count >= s.alive) {
+            s.bar_count = 0;
+            ++s.bar_gen;
+            ++s.progress;
+            return;
+        }
+        emu::yield();
     }
 }
 
@@ -179,36 +203,44 @@ inline int __syncthreads_or(int pred) {
     static int acc = 0, result = 0;
     acc |= pred != 0;
     const unsigned gen = s.bar_gen;
-    if (++s.bar_count == s.nthreads) {
-        result = acc;
-        acc = 0;
-        s.bar_count = 0;
-        ++s.bar_gen;
-        ++s.progress;
-    } else {
-        while (s.bar_gen == gen) emu::yield();
+    ++s.bar_count;
+    for (;;) {
+        if (s.bar_gen != gen) return result;
+        if (s.bar_count >= s.alive) {
+            result = acc;
+            acc = 0;
+            s.bar_count = 0;
+            ++s.bar_gen;
+            ++s.progress;
+            return result;
+        }
+        emu::yield();
     }
-    return result;
 }
 
 // warp rendezvous: every lane deposits a value and sees all 32 (full masks only, as everywhere in these kernels)
-inline const unsigned long long* emu_warp_gather(unsigned mask, unsigned long long v) {
+inline const emu::WarpBox& emu_warp_gather(unsigned mask, unsigned long long v) {
     if (mask != 0xffffffffu) { std::fprintf(stderr, "cuda_emu: partial warp mask\n"); std::abort(); }
     emu::State& s = emu::st();
     const int t = emu::linear_tid();
     emu::WarpBox& w = s.warps[t >> 5];
     w.vals[t & 31] = v;
+    w.present |= 1u << (t & 31);
     const unsigned gen = w.gen;
-    const int lanes = (s.nthreads - (t & ~31)) < 32 ? (s.nthreads - (t & ~31)) : 32;
-    if (++w.count == lanes) {
-        std::memcpy(w.snap, w.vals, sizeof(w.snap));
-        w.count = 0;
-        ++w.gen;
-        ++s.progress;
-    } else {
-        while (w.gen == gen) emu::yield();
+    ++w.count;
+    for (;;) {
+        if (w.gen != gen) return w;
+        if (w.count >= w.alive) {
+            std::memcpy(w.snap, w.vals, sizeof(w.snap));
+            w.snap_present = w.present;
+            w.present = 0;
+            w.count = 0;
+            ++w.gen;
+            ++s.progress;
+            return w;
+        }
+        emu::yield();
     }
-    return w.snap;
 }
 template <typename T>
 inline unsigned long long emu_bits(T v) {
@@ -225,28 +257,31 @@ inline T emu_unbits(unsigned long long b) {
 }
 inline int emu_lane() { return emu::linear_tid() & 31; }
 template <typename T>
-inline T __shfl_sync(unsigned m, T v, int src) { return emu_unbits<T>(emu_warp_gather(m, emu_bits(v))[src & 31]); }
+inline T __shfl_sync(unsigned m, T v, int src) { return emu_unbits<T>(emu_warp_gather(m, emu_bits(v)).snap[src & 31]); }
 template <typename T>
 inline T __shfl_up_sync(unsigned m, T v, unsigned d) {
-    const unsigned long long* s = emu_warp_gather(m, emu_bits(v));
+    const unsigned long long* s = emu_warp_gather(m, emu_bits(v)).snap;
     const int l = emu_lane();
     return l >= static_cast<int>(d) ? emu_unbits<T>(s[l - d]) : v;
 }
 template <typename T>
-inline T __shfl_xor_sync(unsigned m, T v, int x) { return emu_unbits<T>(emu_warp_gather(m, emu_bits(v))[(emu_lane() ^ x) & 31]); }
+inline T __shfl_xor_sync(unsigned m, T v, int x) { return emu_unbits<T>(emu_warp_gather(m, emu_bits(v)).snap[(emu_lane() ^ x) & 31]); }
 inline unsigned __ballot_sync(unsigned m, int pred) {
-    const unsigned long long* s = emu_warp_gather(m, pred ? 1ull : 0ull);
+    const emu::WarpBox& w = emu_warp_gather(m, pred ? 1ull : 0ull);
     unsigned r = 0;
-    for (int i = 0; i < 32; ++i) r |= (s[i] ? 1u : 0u) << i;
+    for (int i = 0; i < 32; ++i) r |= ((w.snap_present >> i & 1u) && w.snap[i] ? 1u : 0u) << i;
     return r;
 }
 template <typename T>
 inline T emu_reduce(unsigned m, T v, int op) {
-    const unsigned long long* s = emu_warp_gather(m, emu_bits(v));
-    T r = emu_unbits<T>(s[0]);
-    for (int i = 1; i < 32; ++i) {
-        const T x = emu_unbits<T>(s[i]);
-        r = op == 0 ? static_cast<T>(r + x) : op == 1 ? (x < r ? x : r) : (x > r ? x : r);
+    const emu::WarpBox& w = emu_warp_gather(m, emu_bits(v));
+    T r = v;                                   // this lane is present by construction
+    bool first = true;
+    for (int i = 0; i < 32; ++i) {
+        if (!(w.snap_present >> i & 1u)) continue;
+        const T x = emu_unbits<T>(w.snap[i]);
+        r = first ? x : op == 0 ? static_cast<T>(r + x) : op == 1 ? (x < r ? x : r) : (x > r ? x : r);
+        first = false;
     }
     return r;
 }
@@ -261,6 +296,13 @@ inline int __reduce_max_sync(unsigned m, int v) { return emu_reduce(m, v, 2); }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { const unsigned o = *p; *p = o + v; return o; }
 inline int atomicAdd(int* p, int v) { const int o = *p; *p = static_cast<int>(static_cast<unsigned>(o) + static_cast<unsigned>(v)); return o; }
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }
+inline unsigned atomicMax(unsigned* p, unsigned v) { const unsigned o = *p; if (v > o) *p = v; return o; }
+inline int atomicMax(int* p, int v) { const int o = *p; if (v > o) *p = v; return o; }
+inline unsigned atomicMin(unsigned* p, unsigned v) { const unsigned o = *p; if (v < o) *p = v; return o; }
+inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) {       // shf.r.wrap
+    const unsigned long long v = (static_cast<unsigned long long>(hi) << 32) | lo;
+    return static_cast<unsigned>(v >> (sh & 31u));
+}
 
 template <typename T>
 inline T __ldg(const T* p) { return *p; }

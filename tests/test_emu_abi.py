@@ -1,0 +1,228 @@
+"""The C ABI of include/cmda_b200.h on the CPU: every translation unit of libcmda_b200 except the TILED and EXACT voxel
+modes is compiled for the host against the fiber emulation of tests/emu/ ("device" pointers are numpy buffers) and
+run against the committed golden fixtures -- outputs of the reference's own functions -- and the oracle, with the GPU
+suite's rules: bit-exact integers, indices and pseudo-events; stated tolerances for float voxel sums.  Both builds of
+the BANDED stage A (first cut and -DCMDA_BAND_V2) are covered.  This checks the LOGIC of the kernel source and of the
+host code around it where no GPU exists; it is test infrastructure, shares no path with the product (which has no
+CPU fallback), and the `-m gpu` tests remain the gate for the CUDA build."""
+import ctypes
+import os
+import platform
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.skipif(platform.machine() != "x86_64", reason="tests/emu switches fibers with x86-64 assembly")
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+import build_emu  # noqa: E402
+import golden_io  # noqa: E402
+from oracle import cmda_oracle as O  # noqa: E402
+
+VOXEL = golden_io.load("voxel")
+NORM = golden_io.load("norm")
+VG = golden_io.load("events_vg")
+ISR = golden_io.load("isr")
+IC = golden_io.load("image_change")
+INDEX = golden_io.load("index")
+GLOBAL, AUTO, FACTORED, BANDED = 0, 2, 4, 5
+DIRECTIONS = {"rightdown": 0, "rightup": 1, "leftdown": 2, "leftup": 3, "all": 4}
+
+
+def _bind(path):
+    from cmda_b200 import _lib
+    lib = ctypes.CDLL(path)
+    for name, (restype, argtypes) in _lib.SIGNATURES.items():
+        fn = getattr(lib, name)          # the emulated build exports the whole ABI
+        fn.restype, fn.argtypes = restype, argtypes
+    return lib
+
+
+@pytest.fixture(scope="module")
+def libs():
+    return {"cut1": _bind(build_emu.build_abi(False)), "cut2": _bind(build_emu.build_abi(True))}
+
+
+def ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def workspace(nbytes):
+    raw = np.full(nbytes + 512, 0xA5, dtype=np.uint8)              # garbage: nothing may rely on a zeroed workspace
+    off = (-raw.ctypes.data) % 256
+    return raw[off:off + nbytes]
+
+
+def events_vg(L, c, mode, clip):
+    t, x, y, p = (np.ascontiguousarray(c[k]) for k in ("t", "x", "y", "p"))
+    W, H, B = int(c["width"]), int(c["height"]), int(c["bins"])
+    rmap = np.ascontiguousarray(c["rectify_map"], dtype=np.float32)
+    starts = np.array([int(c["start"])], dtype=np.int64)
+    ends = np.array([int(c["finish"]) + 1], dtype=np.int64)
+    clips = np.array([clip], dtype=np.float32)
+    out = np.full((1, B, H, W), np.nan, dtype=np.float32)
+    raw = np.full((1, B, H, W), np.nan, dtype=np.float32)
+    counts = np.full((1, B), -1, dtype=np.int64)
+    need = L.cmda_events_vg_workspace_bytes(int(ends[0] - starts[0]), 1, H, W, B, mode)
+    ws = workspace(need)
+    rc = L.cmda_events_vg_batch(ptr(t), ptr(x), ptr(y), ptr(p), ptr(starts), ptr(ends), 1, ptr(rmap), None, H, W, B, ptr(clips),
+                                1.0, 1, 1, ptr(out), ptr(raw), ptr(counts), ptr(ws), need, mode, None)
+    assert rc == 0, L.cmda_strerror(rc)
+    return out[0], raw[0], counts[0], rmap
+
+
+def test_emulated_build_exports_the_whole_abi(libs):
+    for L in libs.values():
+        assert L.cmda_version() == 100
+        assert L.cmda_events_vg_resolved_mode(1000, 1, 480, 640, 5, AUTO) == FACTORED
+
+
+@pytest.mark.parametrize("name", sorted(k for k in VG if VG[k]["rectify_map"].ndim == 3))
+@pytest.mark.parametrize("mode", [GLOBAL, FACTORED, BANDED])
+def test_events_vg_golden(libs, name, mode):
+    c = VG[name]
+    W, H, B = int(c["width"]), int(c["height"]), int(c["bins"])
+    start, finish = int(c["start"]), int(c["finish"])
+    clip = float(c["clip"][0]) if c["clip"].size else O.default_clip_range(finish, start)
+    sl = slice(start, finish + 1)
+    for key, L in libs.items():
+        if key == "cut2" and mode != BANDED:
+            continue                                                # the two builds differ in the BANDED kernels only
+        out, raw, counts, rmap = events_vg(L, c, mode, clip)
+        tf, xf, yf, pf = O.rectify_events(c["t"][sl], c["x"][sl], c["y"][sl], c["p"][sl], rmap)
+        ref_raw, aux = O.events_to_voxel_grid(tf, xf, yf, pf, W, H, B, return_aux=True)
+        tol = 1e-5 * np.maximum(np.abs(ref_raw), aux["abs_weight_sum"]) + aux["n_contrib"] * 2.0 ** -31
+        assert np.all(np.abs(raw.astype(np.float64) - ref_raw.astype(np.float64)) <= tol)
+        assert np.all(raw[aux["n_contrib"] == 0] == 0.0)
+        assert np.array_equal(counts, aux["bin_counts"])
+        # events_norm: within 1e-5 of the oracle on our raw grid; of the reference's output unless a voxel whose
+        # exact sum is zero kept a float32 residue in the reference (tests/test_gpu_parity.py::check_normalised)
+        np.testing.assert_allclose(out, O.events_norm(raw.copy(), clip, 1.0, True), rtol=0, atol=1e-5)
+        if not ((raw == 0) != (ref_raw == 0)).any():
+            np.testing.assert_allclose(out, c["result"], rtol=0, atol=1e-5)
+    # integer side outputs: bit-exact
+    L = libs["cut1"]
+    n = finish + 1 - start
+    xr, yr, tn = (np.empty(n, np.float32) for _ in range(3))
+    x0, y0, t0 = (np.empty(n, np.int32) for _ in range(3))
+    t, x, y, p = (np.ascontiguousarray(c[k]) for k in ("t", "x", "y", "p"))
+    assert L.cmda_remap_events(ptr(t), ptr(x), ptr(y), ptr(p), start, finish + 1, ptr(rmap), H, W, B, ptr(xr), ptr(yr), ptr(tn),
+                               ptr(x0), ptr(y0), ptr(t0), None) == 0
+    assert np.array_equal(bits(xr), bits(xf)) and np.array_equal(bits(yr), bits(yf))
+    assert np.array_equal(x0, np.trunc(xf).astype(np.int32)) and np.array_equal(y0, np.trunc(yf).astype(np.int32))
+
+
+@pytest.mark.parametrize("name", sorted(VOXEL))
+def test_voxel_grid_f32_golden(libs, name):
+    c, L = VOXEL[name], libs["cut1"]
+    W, H, B, n = int(c["width"]), int(c["height"]), int(c["bins"]), int(c["time"].shape[0])
+    tm, x, y, pol = (np.ascontiguousarray(c[k], dtype=np.float32) for k in ("time", "x", "y", "pol"))
+    grid = np.full((B, H, W), np.nan, dtype=np.float32)
+    need = L.cmda_events_vg_workspace_bytes(n, 1, H, W, B, GLOBAL)
+    ws = workspace(need)
+    assert L.cmda_voxel_grid_f32(ptr(tm), ptr(x), ptr(y), ptr(pol), n, W, H, B, ptr(grid), None, ptr(ws), need, GLOBAL, None) == 0
+    ref, aux = O.events_to_voxel_grid(tm, x, y, pol, W, H, B, return_aux=True)
+    assert np.array_equal(bits(ref), bits(c["grid"])), "the oracle reproduces the reference's grid bit for bit"
+    tol = 1e-5 * np.maximum(np.abs(ref), aux["abs_weight_sum"]) + aux["n_contrib"] * 2.0 ** -31
+    assert np.all(np.abs(grid.astype(np.float64) - ref.astype(np.float64)) <= tol)
+
+
+@pytest.mark.parametrize("name", sorted(k for k in NORM if k.startswith("norm_")))
+def test_events_norm_golden(libs, name):
+    c, L = NORM[name], libs["cut1"]
+    grid = np.ascontiguousarray(NORM["normgrid_" + str(c["grid"])]["events"], dtype=np.float32).copy()
+    clips = np.array([float(c["clip_range"])], dtype=np.float32)
+    need = L.cmda_events_norm_workspace_bytes(1)
+    ws = workspace(need)
+    assert L.cmda_events_norm_batch(ptr(grid), 1, grid.size, ptr(clips), float(c["final_range"]), int(c["enforce"]), ptr(ws), need,
+                                    None) == 0
+    np.testing.assert_allclose(grid, c["result"], rtol=0, atol=1e-5)
+
+
+def test_images_to_events_index_golden(libs):
+    c, L = INDEX["index_table"], libs["cut1"]
+    t = np.ascontiguousarray(c["t"], dtype=np.uint32)
+    ms = np.ascontiguousarray(c["ms_to_idx"], dtype=np.int64)
+    ts = np.ascontiguousarray(c["timestamps"], dtype=np.int64)
+    idx = np.full(ts.shape[0], -7, dtype=np.int64)
+    status = np.full(ts.shape[0], -7, dtype=np.int32)
+    assert L.cmda_images_to_events_index(ptr(t), t.shape[0], ptr(ms), ms.shape[0], int(c["t_offset"]), ptr(ts), ts.shape[0], ptr(idx),
+                                         ptr(status), None) == 0
+    assert np.array_equal(idx, np.asarray(c["result"], dtype=np.int64)) and not status.any()
+    q = np.array([0, int(t[0]), int(t[777]), int(t[-1]), 2 ** 33], dtype=np.int64)
+    got = np.empty(q.shape[0], dtype=np.int64)
+    assert L.cmda_searchsorted_right_u32(ptr(t), t.shape[0], ptr(q), q.shape[0], ptr(got), None) == 0
+    assert np.array_equal(got, np.searchsorted(t.astype(np.int64), q, side="right"))
+
+
+def _isr(L, img, channels, c):
+    from cmda_b200 import image_change as ic
+    vr = tuple(float(v) for v in c["val_range"])
+    lut = ic.log_lut_val_range(vr)
+    span = np.log(vr[1]) - np.log(vr[0])                               # utils.py:93-94 (float64), compared in float32
+    thr, clip = np.float32(span * float(c["threshold"])), np.float32(span * float(c["clip_range"]))
+    H, W = img.shape[0], img.shape[1]
+    out = np.full((1, H, W), np.nan, dtype=np.float32)
+    need = L.cmda_image_workspace_bytes(1, H, W, channels)
+    ws = workspace(need)
+    src = np.ascontiguousarray(img)
+    rc = L.cmda_isr_shift_u8(ptr(src), channels, 1, H, W, int(c["shift_pixel"]), DIRECTIONS[str(c["direction"])], ptr(lut), float(thr),
+                             float(clip), ptr(out), ptr(ws), need, None)
+    assert rc == 0
+    return out, lut
+
+
+@pytest.mark.parametrize("name", sorted(k for k in ISR if "lut" in ISR[k]))
+def test_isr_golden_bit_exact(libs, name):
+    c, L = ISR[name], libs["cut1"]
+    out, lut = _isr(L, ISR["isr_input"]["rgb"], 3, c)
+    assert np.array_equal(bits(lut), bits(c["lut"])), "host LUT == the reference's np.log values"
+    assert np.array_equal(bits(out), bits(c["result"]))
+    out, _ = _isr(L, ISR["isr_input"]["gray"], 1, c)
+    assert np.array_equal(bits(out), bits(c["result"]))
+
+
+def test_rgb_to_gray_bit_exact(libs):
+    L = libs["cut1"]
+    rgb = np.ascontiguousarray(ISR["isr_input"]["rgb"])
+    gray = np.zeros(rgb.shape[:2], dtype=np.uint8)
+    assert L.cmda_rgb_to_gray_u8(ptr(rgb), gray.size, ptr(gray), None) == 0
+    assert np.array_equal(gray, ISR["isr_input"]["gray"])
+
+
+@pytest.mark.parametrize("name", sorted(IC))
+def test_image_change_pair_golden(libs, name):
+    from cmda_b200 import image_change as ic
+    c, L = IC[name], libs["cut1"]
+    now, front = np.ascontiguousarray(c["now"]), np.ascontiguousarray(c["front"])
+    H, W = now.shape
+    lut = ic.log_lut_log_add(ic.log_add)
+    assert np.array_equal(bits(lut), bits(c["lut"]))
+    f32 = np.full((1, H, W), np.nan, dtype=np.float32)
+    u8 = np.zeros((1, H, W), dtype=np.uint8)
+    need = L.cmda_image_workspace_bytes(1, H, W, 1)
+    ws = workspace(need)
+    assert L.cmda_logdiff_pair_u8(ptr(now), ptr(front), 1, H, W, ptr(lut), float(np.float32(ic.threshold)),
+                                  float(np.float32(ic.clip_range)), ptr(f32), ptr(u8), ptr(ws), need, None) == 0
+    assert np.array_equal(u8[0], c["result"])
+    assert np.array_equal(bits(f32[0]), bits(O.get_image_change(now, front, return_float=True)))
+
+
+@pytest.mark.parametrize("shape,size,channels", [((67, 131), (50, 40), 1), ((64, 96), (48, 32), 3), ((33, 47), (47, 60), 1)])
+def test_resize_bilinear_matches_pillow(libs, shape, size, channels):
+    from PIL import Image
+    L = libs["cut1"]
+    rng = np.random.default_rng(shape[0])
+    img = rng.integers(0, 256, size=shape + ((3,) if channels == 3 else ()), dtype=np.uint8)
+    out_w, out_h = size
+    dst = np.zeros((out_h, out_w) + ((3,) if channels == 3 else ()), dtype=np.uint8)
+    need = L.cmda_resize_bilinear_workspace_bytes(1, shape[0], shape[1], channels, out_h, out_w)
+    ws = workspace(need)
+    assert L.cmda_resize_bilinear_u8(ptr(img), channels, 1, shape[0], shape[1], out_h, out_w, ptr(dst), ptr(ws), need, None) == 0
+    want = np.asarray(Image.fromarray(img, mode="RGB" if channels == 3 else "L").resize((out_w, out_h), Image.BILINEAR))
+    assert np.array_equal(dst, want)
