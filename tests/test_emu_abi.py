@@ -226,3 +226,98 @@ def test_resize_bilinear_matches_pillow(libs, shape, size, channels):
     assert L.cmda_resize_bilinear_u8(ptr(img), channels, 1, shape[0], shape[1], out_h, out_w, ptr(dst), ptr(ws), need, None) == 0
     want = np.asarray(Image.fromarray(img, mode="RGB" if channels == 3 else "L").resize((out_w, out_h), Image.BILINEAR))
     assert np.array_equal(dst, want)
+
+
+def _vg_batch(L, t, x, y, p, starts, fins, maps, mids, H, W, B, mode, aug=None, normalize=1):
+    """cmda_events_vg_batch (or, with aug = (xy, crop_size, out_size, flips, repeat), cmda_events_vg_augmented_batch)
+    with the reference's default clip; returns (out, bin_counts)."""
+    S = len(starts)
+    st = np.ascontiguousarray(starts, dtype=np.int64)
+    en = np.ascontiguousarray(fins, dtype=np.int64) + 1
+    clips = np.array([O.default_clip_range(int(f), int(s)) for s, f in zip(starts, fins)], dtype=np.float32)
+    ids = None if mids is None else np.ascontiguousarray(mids, dtype=np.int32)
+    m = np.ascontiguousarray(maps, dtype=np.float32)
+    total = int(np.clip(en - st, 0, None).sum())
+    counts = np.full((S, B), -1, dtype=np.int64)
+    if aug is None:
+        out = np.full((S, B, H, W), np.nan, dtype=np.float32)
+        need = L.cmda_events_vg_workspace_bytes(total, S, H, W, B, mode)
+        ws = workspace(need)
+        rc = L.cmda_events_vg_batch(ptr(t), ptr(x), ptr(y), ptr(p), ptr(st), ptr(en), S, ptr(m), ptr(ids), H, W, B, ptr(clips), 1.0, 1,
+                                    normalize, ptr(out), None, ptr(counts), ptr(ws), need, mode, None)
+    else:
+        xy, crop_size, out_size, flips, repeat = aug
+        table = np.array([[cx, cy, fl] for (cx, cy), fl in zip(xy, flips)], dtype=np.int32)
+        out = np.full((S, repeat * B, out_size[1], out_size[0]), np.nan, dtype=np.float32)
+        need = L.cmda_events_vg_augmented_workspace_bytes(total, S, H, W, B, mode)
+        ws = workspace(need)
+        rc = L.cmda_events_vg_augmented_batch(ptr(t), ptr(x), ptr(y), ptr(p), ptr(st), ptr(en), S, ptr(m), ptr(ids), H, W, B, ptr(clips),
+                                              1.0, 1, ptr(table), crop_size[0], crop_size[1], out_size[0], out_size[1], 0, repeat,
+                                              ptr(out), None, ptr(counts), ptr(ws), need, mode, None, None)
+    assert rc == 0, L.cmda_strerror(rc)
+    return out, counts
+
+
+def test_many_windows_and_maps_through_the_group_loop(libs):
+    """More windows than one launch group holds (64) and more distinct maps than one group builds plans for (8):
+    the offsets of api.cu's group loop, with the FACTORED stage A and both BANDED cuts, window by window against the
+    oracle."""
+    from cmda_b200 import synth
+    H, W, B, S, n_maps = 40, 56, 3, 150, 11
+    rng = np.random.default_rng(99)
+    n = 30_000
+    t, x, y, p = synth.make_events(n, H, W, seed=31)
+    maps = np.stack([synth.make_rectify_map(H, W, seed=200 + k) for k in range(n_maps)])
+    starts = np.sort(rng.integers(0, n - 400, size=S))
+    fins = starts + rng.integers(0, 400, size=S)
+    fins[7] = starts[7] - 1                                  # an empty window in the first group
+    fins[100] = starts[100]                                  # a single-event window in the second
+    mids = rng.integers(0, n_maps, size=S)
+    mids[:12] = np.arange(12) % n_maps                       # > 8 distinct maps inside the first windows
+    base, base_counts = _vg_batch(libs["cut1"], t, x, y, p, starts, fins, maps, mids, H, W, B, FACTORED)
+    raw, _ = _vg_batch(libs["cut1"], t, x, y, p, starts, fins, maps, mids, H, W, B, FACTORED, normalize=0)
+    for s in range(S):
+        if fins[s] < starts[s]:
+            assert not raw[s].any() and int(base_counts[s].sum()) == 0
+            continue
+        sl = slice(int(starts[s]), int(fins[s]) + 1)
+        tf, xf, yf, pf = O.rectify_events(t[sl], x[sl], y[sl], p[sl], maps[mids[s]])
+        g, aux = O.events_to_voxel_grid(tf, xf, yf, pf, W, H, B, return_aux=True)
+        tol = 1e-5 * np.maximum(np.abs(g), aux["abs_weight_sum"]) + aux["n_contrib"] * 2.0 ** -31
+        assert np.all(np.abs(raw[s].astype(np.float64) - g.astype(np.float64)) <= tol), f"window {s}"
+        assert np.array_equal(base_counts[s], aux["bin_counts"]), f"window {s}"
+        clip = O.default_clip_range(int(fins[s]), int(starts[s]))
+        np.testing.assert_allclose(base[s], O.events_norm(raw[s].copy(), clip, 1.0, True), rtol=0, atol=1e-5, err_msg=f"window {s}")
+    for key in ("cut1", "cut2"):
+        out, counts = _vg_batch(libs[key], t, x, y, p, starts, fins, maps, mids, H, W, B, BANDED)
+        assert np.array_equal(bits(out), bits(base)) and np.array_equal(counts, base_counts), key
+
+
+def test_fused_augmentation_many_windows(libs):
+    """dsec.py:304-319 fused into the normaliser (crop / flip / bilinear resize / repeat) past one launch group, on
+    top of the FACTORED and both BANDED stage A: against the unfused path + the oracle's post-voxel stage."""
+    from cmda_b200 import synth
+    H, W, B, S = 40, 56, 2, 70
+    rng = np.random.default_rng(123)
+    n = 20_000
+    t, x, y, p = synth.make_events(n, H, W, seed=41)
+    maps = np.stack([synth.make_rectify_map(H, W, seed=300 + k) for k in range(3)])
+    starts = np.sort(rng.integers(0, n - 500, size=S))
+    fins = starts + rng.integers(50, 500, size=S)
+    mids = rng.integers(0, 3, size=S)
+    crop_size, out_size = (24, 20), (32, 28)                    # (w, h)
+    xy = [(int(rng.integers(0, W - 24 + 1)), int(rng.integers(0, H - 20 + 1))) for _ in range(S)]
+    flips = [int(v) for v in rng.integers(0, 2, size=S)]
+    grid, _ = _vg_batch(libs["cut1"], t, x, y, p, starts, fins, maps, mids, H, W, B, FACTORED)
+    first = None
+    for key, mode in (("cut1", FACTORED), ("cut1", BANDED), ("cut2", BANDED)):
+        got, _ = _vg_batch(libs[key], t, x, y, p, starts, fins, maps, mids, H, W, B, mode, aug=(xy, crop_size, out_size, flips, 3))
+        assert got.shape == (S, 3 * B, 28, 32)
+        if first is None:
+            first = got
+            for s in range(S):
+                exp = O.events_vg_post(grid[s], crop_xy=xy[s], crop_size=crop_size, out_size=out_size, flip_flag=bool(flips[s]),
+                                       avg_bins=False, enforce_3_channels=True, test_mode=False)
+                np.testing.assert_allclose(got[s], exp, rtol=0, atol=1e-5, err_msg=f"window {s}")
+        else:
+            assert np.array_equal(bits(got), bits(first)), (key, mode)
