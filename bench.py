@@ -412,6 +412,25 @@ def variants_leg(store, starts, fins, rmap, args, dev, steps=10, warmup=3):
     return res
 
 
+# ------------------------------------------------------------------------------------ experimental: BANDED2
+def banded2_leg(args):
+    """The second cut of the BANDED stage A (mode "banded2") on the C2 step, in a process of its own
+    (tools/banded2_check.py): its logic was verified on the CPU emulation (tests/test_emu_*.py) but it had not run on
+    hardware when round 1 ended.  Checked against FACTORED (bit-identical or not) and timed next to FACTORED and the
+    first cut; whatever happens there, this process, its CUDA context and the bench line are untouched."""
+    import subprocess
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "banded2_check.py"), "--events", str(args.events), "--bins", str(args.bins)]
+    if args.bins != 1:
+        cmd.append("1")
+    try:
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+        if res.returncode != 0:
+            return {"error": f"exit {res.returncode}: {res.stderr.strip()[-300:]}"}
+        return json.loads(res.stdout.strip().splitlines()[-1])
+    except Exception as e:      # noqa: BLE001 -- an experimental leg must not cost the bench line
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+
 # ------------------------------------------------------------------------------------ GPU leg
 class _StdoutGuard:
     """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL writes its version banner to fd 1 when
@@ -556,9 +575,9 @@ def run_gpu(args, rank, local_rank, world):
             names = ["memset(sensor grid)", "rectify_index_{build,sort}+stencil_build+out_tile_box kernels",
                      "sensor_accumulate_kernel", "rectify_gather+regroup_partials kernels", "norm_apply_kernel"]
             launches_per_step = 8   # kernels only (memsets not counted)
-        elif resolved == _lib.VOXEL_BANDED:
+        elif resolved in (_lib.VOXEL_BANDED, _lib.VOXEL_BANDED2):
             names = ["memset(none: every sensor-grid cell is stored)", "rectify_index_{build,sort}+stencil_build+out_tile_box kernels",
-                     "band_partition_kernel", "band_accumulate_kernel", "rectify_gather+regroup_partials kernels",
+                     "band_partition_kernel", "band_accumulate(+fixup) kernel", "rectify_gather+regroup_partials kernels",
                      "norm_apply_kernel"]
             launches_per_step = 9
         else:
@@ -596,6 +615,9 @@ def run_gpu(args, rank, local_rank, world):
         if world == 1 and not args.no_variants:
             del pipe, host_out
             variants = variants_leg(store, starts, fins, rmap, args, dev)
+        experimental = None
+        if world == 1 and not args.no_variants and args.mode in ("auto", "factored"):
+            experimental = {"banded2_stage_A": banded2_leg(args)}      # a process of its own (see there)
         line = {
             "metric": "voxelized_events_per_s", "value": value, "unit": "Mevents/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -610,7 +632,7 @@ def run_gpu(args, rank, local_rank, world):
                                         "ms_per_step": planned_ms,
                                         "note": "cmda_rectify_plan_build once per sequence instead of inside every step"},
             "roofline": roofline, "cpu_baseline": cpu, "pseudo_events": pseudo, "train_step_input_path": c5,
-            "variants": variants,
+            "variants": variants, "experimental": experimental,
         }
         guard.emit(json.dumps(line))
     if world > 1:
@@ -626,7 +648,7 @@ def main():
     ap.add_argument("--impl", default="cmda_b200", choices=["cmda_b200", "reference"])
     ap.add_argument("--bins", type=int, default=5)
     ap.add_argument("--events", type=int, default=EVENTS_PER_WINDOW)
-    ap.add_argument("--mode", default="auto", choices=["auto", "global", "tiled", "factored", "banded"])
+    ap.add_argument("--mode", default="auto", choices=["auto", "global", "tiled", "factored", "banded", "banded2"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pseudo", action="store_true", help="skip the pseudo-event (config C3) leg")
     ap.add_argument("--no-variants", action="store_true", help="skip the other device-resident cases of SURVEY.md 8(d)")

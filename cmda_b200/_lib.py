@@ -19,9 +19,9 @@ LIB_PATH = os.environ.get("CMDA_B200_LIB") or os.path.join(_HERE, "libcmda_b200.
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 OK = 0
-VOXEL_GLOBAL, VOXEL_TILED, VOXEL_AUTO, VOXEL_EXACT, VOXEL_FACTORED, VOXEL_BANDED = 0, 1, 2, 3, 4, 5
+VOXEL_GLOBAL, VOXEL_TILED, VOXEL_AUTO, VOXEL_EXACT, VOXEL_FACTORED, VOXEL_BANDED, VOXEL_BANDED2 = 0, 1, 2, 3, 4, 5, 6
 VOXEL_MODES = {"global": VOXEL_GLOBAL, "tiled": VOXEL_TILED, "auto": VOXEL_AUTO, "exact": VOXEL_EXACT,
-               "factored": VOXEL_FACTORED, "banded": VOXEL_BANDED}
+               "factored": VOXEL_FACTORED, "banded": VOXEL_BANDED, "banded2": VOXEL_BANDED2}
 VOXEL_MODE_NAMES = {v: k for k, v in VOXEL_MODES.items()}
 DIRECTIONS = {"rightdown": 0, "rightup": 1, "leftdown": 2, "leftup": 3, "all": 4}
 

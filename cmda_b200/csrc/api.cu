@@ -126,7 +126,7 @@ int cmda_images_to_events_index(const uint32_t* d_t, int64_t n, const int64_t* d
 
 int cmda_events_vg_resolved_mode(int64_t total_events, int S, int H, int W, int B, int mode) {
     if (S <= 0 || H <= 0 || W <= 0 || B <= 0 || total_events < 0) return CMDA_ERR_BAD_ARG;
-    if (mode < CMDA_VOXEL_GLOBAL || mode > CMDA_VOXEL_BANDED) return CMDA_ERR_BAD_ARG;
+    if (mode < CMDA_VOXEL_GLOBAL || mode > CMDA_VOXEL_BANDED2) return CMDA_ERR_BAD_ARG;
     return resolve_mode(mode, total_events, S, H, W, B);
 }
 
@@ -137,7 +137,7 @@ size_t cmda_events_vg_workspace_bytes(int64_t total_events, int S, int H, int W,
     if (mode == CMDA_VOXEL_TILED && tiled_supported(H, W, B)) need += tiled_workspace_bytes(total_events, S, H, W, B);
     if ((mode == CMDA_VOXEL_FACTORED || mode == CMDA_VOXEL_AUTO) && factored_supported(H, W, B))
         need += factored_scratch_bytes(group, H, W, B);
-    if (mode == CMDA_VOXEL_BANDED && banded_supported(H, W, B))
+    if ((mode == CMDA_VOXEL_BANDED || mode == CMDA_VOXEL_BANDED2) && banded_supported(H, W, B))
         need += factored_scratch_bytes(group, H, W, B) + 256 + banded_scratch_bytes(total_events, group, H, W, B);
     if (mode == CMDA_VOXEL_EXACT) need += exact_workspace_bytes(total_events);    // total_events bounds the largest window
     return need + 256;
@@ -161,7 +161,7 @@ int events_vg_impl(const uint32_t* d_t, const uint16_t* d_x, const uint16_t* d_y
     if (S == 0) return CMDA_OK;
     if (!d_t || !d_x || !d_y || !d_p || !h_win_start || !h_win_end || !d_out || !d_workspace) return CMDA_ERR_BAD_ARG;
     if (normalize && !h_clip) return CMDA_ERR_BAD_ARG;
-    if (mode < CMDA_VOXEL_GLOBAL || mode > CMDA_VOXEL_BANDED) return CMDA_ERR_BAD_ARG;
+    if (mode < CMDA_VOXEL_GLOBAL || mode > CMDA_VOXEL_BANDED2) return CMDA_ERR_BAD_ARG;
     if (reinterpret_cast<uintptr_t>(d_workspace) & 255) return CMDA_ERR_WORKSPACE;
     long long total = 0;
     for (int s = 0; s < S; ++s) {
@@ -189,8 +189,9 @@ int events_vg_impl(const uint32_t* d_t, const uint16_t* d_x, const uint16_t* d_y
     if (use_mode == CMDA_VOXEL_TILED && !tiled_supported(H, W, B)) return CMDA_ERR_UNSUPPORTED;
     if (use_mode == CMDA_VOXEL_FACTORED && !factored_supported(H, W, B)) return CMDA_ERR_UNSUPPORTED;
     if (use_mode == CMDA_VOXEL_EXACT && !exact_supported(H, W, B)) return CMDA_ERR_UNSUPPORTED;
-    if (use_mode == CMDA_VOXEL_BANDED && !banded_supported(H, W, B)) return CMDA_ERR_UNSUPPORTED;
-    const bool factored_like = use_mode == CMDA_VOXEL_FACTORED || use_mode == CMDA_VOXEL_BANDED;
+    const int banded = use_mode == CMDA_VOXEL_BANDED ? 1 : use_mode == CMDA_VOXEL_BANDED2 ? 2 : 0;     // which cut of the BANDED stage A
+    if (banded && !banded_supported(H, W, B)) return CMDA_ERR_UNSUPPORTED;
+    const bool factored_like = use_mode == CMDA_VOXEL_FACTORED || banded;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long V = static_cast<long long>(B) * H * W;
 
@@ -255,8 +256,7 @@ int events_vg_impl(const uint32_t* d_t, const uint16_t* d_x, const uint16_t* d_y
         if (factored_like) {
             const size_t ab = acc_bytes(sn, H, W, B);
             rc = launch_factored(d_t, d_x, d_y, d_p, tab, sn, max_events, d_rectify_map, H, W, B, acc, bins_g, raw_g,
-                                 part_g, scratch + ab, scratch_bytes - ab, d_plans, use_mode == CMDA_VOXEL_BANDED,
-                                 st);   // marks: memset | plans | accumulate
+                                 part_g, scratch + ab, scratch_bytes - ab, d_plans, banded, st);   // marks: memset | plans | accumulate
             if (rc != CMDA_OK) return rc;
             phase_mark(st);
             if (normalize) {
@@ -366,12 +366,12 @@ int cmda_voxel_grid_f32(const float* d_time, const float* d_x, const float* d_y,
                         int mode, void* stream) {
     if (n < 0 || H <= 0 || W <= 0 || B <= 0 || !d_grid || !d_workspace) return CMDA_ERR_BAD_ARG;
     if (n > 0 && (!d_time || !d_x || !d_y || !d_pol)) return CMDA_ERR_BAD_ARG;
-    if (mode < CMDA_VOXEL_GLOBAL || mode > CMDA_VOXEL_BANDED) return CMDA_ERR_BAD_ARG;
+    if (mode < CMDA_VOXEL_GLOBAL || mode > CMDA_VOXEL_BANDED2) return CMDA_ERR_BAD_ARG;
     if (reinterpret_cast<uintptr_t>(d_workspace) & 255) return CMDA_ERR_WORKSPACE;
     if (workspace_bytes < cmda_events_vg_workspace_bytes(n, 1, H, W, B, mode)) return CMDA_ERR_WORKSPACE;
     // float32 events are already rectified: there is no map gather to tile, so this entry point
     // runs the GLOBAL scatter (AUTO resolves to it); TILED / EXACT are refused explicitly
-    if (mode == CMDA_VOXEL_TILED || mode == CMDA_VOXEL_FACTORED || mode == CMDA_VOXEL_BANDED) return CMDA_ERR_UNSUPPORTED;
+    if (mode == CMDA_VOXEL_TILED || mode >= CMDA_VOXEL_FACTORED) return CMDA_ERR_UNSUPPORTED;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long V = static_cast<long long>(B) * H * W;
     char* ws = static_cast<char*>(d_workspace);

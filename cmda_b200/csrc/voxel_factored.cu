@@ -520,8 +520,9 @@ band_accumulate_kernel(const unsigned* __restrict__ table, const unsigned* __res
     }
 }
 
-// ---- BANDED, second cut (CMDA_BAND_V2, off by default: written after the last GPU minute of round 1, so it has
-// never run; the ncu capture of the first cut -- profiles/r01_ncu_banded_b5_summary.txt -- is its brief) -----------
+// ---- BANDED, second cut (mode CMDA_VOXEL_BANDED2: written after the last GPU minute of round 1 from the ncu capture
+// of the first cut -- profiles/r01_ncu_banded_b5_summary.txt; its logic is verified on the CPU emulation of tests/emu,
+// its first run on hardware is pending, which is why it is a mode of its own next to the measured first cut) --------
 // Same record format, same table, same R.  Partition: no per-event branches -- an event that is dropped (outside
 // the sensor, outside the temporal range, past the window, dead window) is ranked into one extra "trash" bucket
 // behind the real ones, so every lane runs the same straight-line code and the sorted chunk simply ends where the
@@ -529,13 +530,10 @@ band_accumulate_kernel(const unsigned* __restrict__ table, const unsigned* __res
 // Accumulate: per-run pointers with immediate offsets instead of 64-bit address arithmetic per record, 32-bit
 // arithmetic for the (low, high) addends, no divergence region per record (a lane without a record adds zero to
 // a cell of its own).
-#ifndef CMDA_BAND_V2
-#define CMDA_BAND_V2 0
-#endif
 #ifndef CMDA_BAND_V2_UNROLL
 #define CMDA_BAND_V2_UNROLL 4
 #endif
-static_assert(!CMDA_BAND_V2 || CMDA_BAND_XSUB == 1, "the second cut ranks in the table's own buckets");
+static_assert(CMDA_BAND_XSUB == 1, "the second cut ranks in the table's own buckets");
 
 template <bool HAS_T, bool VEC>
 __global__ void __launch_bounds__(kBandPartThreads, 2)
@@ -1444,25 +1442,25 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
                          ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && ((reinterpret_cast<uintptr_t>(p) & 7) == 0);
         unsigned long long* ubins = reinterpret_cast<unsigned long long*>(bin_counts);
         if (max_chunks > 0) {
-            const int fine = CMDA_BAND_V2 ? bg.nbuckets + 1 : (bg.nbuckets << bg.xsub_log2);
+            const int fine = banded == 2 ? bg.nbuckets + 1 : (bg.nbuckets << bg.xsub_log2);
             const size_t shm = sizeof(unsigned) * (fine + ((fine + 1 + 3) & ~3)) + (B > 1 ? 5u : 2u) * static_cast<size_t>(kBandChunk);
             dim3 grid(static_cast<unsigned>(max_chunks), S);
-#if CMDA_BAND_V2
-#define CMDA_BAND_PART_KERNEL band_partition2_kernel
-#else
-#define CMDA_BAND_PART_KERNEL band_partition_kernel
-#endif
-#define CMDA_BAND_PART(HAS_T, VEC)                                                                                             \
+#define CMDA_BAND_PART(KERNEL, HAS_T, VEC)                                                                                     \
     do {                                                                                                                       \
-        CMDA_CUDA_TRY(cudaFuncSetAttribute(CMDA_BAND_PART_KERNEL<HAS_T, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+        CMDA_CUDA_TRY(cudaFuncSetAttribute(KERNEL<HAS_T, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,                    \
                                            static_cast<int>(shm)));                                                            \
-        CMDA_BAND_PART_KERNEL<HAS_T, VEC><<<grid, kBandPartThreads, shm, st>>>(t, x, y, p, tab, bt, bg, H, W, B, z.table,     \
-                                                                               z.rec32, z.rec8, z.rec16, ubins);               \
+        KERNEL<HAS_T, VEC><<<grid, kBandPartThreads, shm, st>>>(t, x, y, p, tab, bt, bg, H, W, B, z.table, z.rec32, z.rec8,    \
+                                                                z.rec16, ubins);                                               \
     } while (0)
-            if (B == 1) { if (vec) CMDA_BAND_PART(false, true); else CMDA_BAND_PART(false, false); }
-            else { if (vec) CMDA_BAND_PART(true, true); else CMDA_BAND_PART(true, false); }
+#define CMDA_BAND_PART_ANY(KERNEL)                                                                                             \
+    do {                                                                                                                       \
+        if (B == 1) { if (vec) CMDA_BAND_PART(KERNEL, false, true); else CMDA_BAND_PART(KERNEL, false, false); }               \
+        else { if (vec) CMDA_BAND_PART(KERNEL, true, true); else CMDA_BAND_PART(KERNEL, true, false); }                        \
+    } while (0)
+            if (banded == 2) CMDA_BAND_PART_ANY(band_partition2_kernel);
+            else CMDA_BAND_PART_ANY(band_partition_kernel);
+#undef CMDA_BAND_PART_ANY
 #undef CMDA_BAND_PART
-#undef CMDA_BAND_PART_KERNEL
             CMDA_LAUNCH_CHECK();
         }
         phase_mark(st);
@@ -1470,21 +1468,20 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
             const size_t cells = static_cast<size_t>(bg.rows) * W;
             const size_t shm = (B > 1 ? 2 : 1) * sizeof(unsigned) * cells;
             const unsigned items = static_cast<unsigned>(S) * static_cast<unsigned>(bg.nbuckets);
-#if CMDA_BAND_V2
-#define CMDA_BAND_ACC_KERNEL band_accumulate2_kernel
-#else
-#define CMDA_BAND_ACC_KERNEL band_accumulate_kernel
-#endif
-            if (B == 1) {
-                CMDA_CUDA_TRY(cudaFuncSetAttribute(CMDA_BAND_ACC_KERNEL<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shm)));
-                CMDA_BAND_ACC_KERNEL<false><<<items, kBandAccThreads, shm, st>>>(z.table, z.rec32, z.rec8, z.rec16, bt, bg, H, W, B, R);
-            } else {
-                CMDA_CUDA_TRY(cudaFuncSetAttribute(CMDA_BAND_ACC_KERNEL<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shm)));
-                CMDA_BAND_ACC_KERNEL<true><<<items, kBandAccThreads, shm, st>>>(z.table, z.rec32, z.rec8, z.rec16, bt, bg, H, W, B, R);
-            }
-#undef CMDA_BAND_ACC_KERNEL
-#if CMDA_BAND_V2
-            if (max_chunks > 0) {
+#define CMDA_BAND_ACC(KERNEL)                                                                                                 \
+    do {                                                                                                                       \
+        if (B == 1) {                                                                                                          \
+            CMDA_CUDA_TRY(cudaFuncSetAttribute(KERNEL<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shm))); \
+            KERNEL<false><<<items, kBandAccThreads, shm, st>>>(z.table, z.rec32, z.rec8, z.rec16, bt, bg, H, W, B, R);         \
+        } else {                                                                                                               \
+            CMDA_CUDA_TRY(cudaFuncSetAttribute(KERNEL<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shm))); \
+            KERNEL<true><<<items, kBandAccThreads, shm, st>>>(z.table, z.rec32, z.rec8, z.rec16, bt, bg, H, W, B, R);          \
+        }                                                                                                                      \
+    } while (0)
+            if (banded == 2) CMDA_BAND_ACC(band_accumulate2_kernel);
+            else CMDA_BAND_ACC(band_accumulate_kernel);
+#undef CMDA_BAND_ACC
+            if (banded == 2 && max_chunks > 0) {
                 dim3 fgrid(static_cast<unsigned>((max_chunks + kBandFixupChunks - 1) / kBandFixupChunks), S);
                 if (B == 1) {
                     if (vec) band_fixup_kernel<false, true><<<fgrid, kBandPartThreads, 0, st>>>(t, x, y, p, tab, bt, bg, H, W, B, z.table, R);
@@ -1494,7 +1491,6 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
                     else band_fixup_kernel<true, false><<<fgrid, kBandPartThreads, 0, st>>>(t, x, y, p, tab, bt, bg, H, W, B, z.table, R);
                 }
             }
-#endif
             CMDA_LAUNCH_CHECK();
         }
     } else if (max_events > 0) {

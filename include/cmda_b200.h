@@ -58,8 +58,10 @@ enum {
     CMDA_VOXEL_AUTO = 2,     /* FACTORED where it applies (raw DSEC events), else GLOBAL       */
     CMDA_VOXEL_EXACT = 3,    /* stable sort by (voxel, corner pass) + ordered float32 accumulation */
     CMDA_VOXEL_FACTORED = 4, /* sensor-space temporal accumulation + per-pixel rectify gather  */
-    CMDA_VOXEL_BANDED = 5    /* FACTORED with its per-event L2 atomics replaced by a band partition +
+    CMDA_VOXEL_BANDED = 5,   /* FACTORED with its per-event L2 atomics replaced by a band partition +
                                 shared-memory accumulation; bit-identical to FACTORED; polarity in {0, 1} */
+    CMDA_VOXEL_BANDED2 = 6   /* second cut of BANDED: fewer instructions per event, any polarity byte; same
+                                output; verified on the CPU emulation of tests/emu, first hardware run pending */
 };
 
 /* Directions of the shift-pair generator (reference mmseg/datasets/utils.py:128-151). */

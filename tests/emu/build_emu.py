@@ -110,10 +110,10 @@ def generate_full() -> None:
             f.write(src)
 
 
-def build_vg(v2: bool = False, force: bool = False) -> str:
-    """tests/emu/_build/libvg_emu[_v2].so: launch_factored + launch_norm_apply (the real host launch code and every
+def build_vg(force: bool = False) -> str:
+    """tests/emu/_build/libvg_emu.so: launch_factored + launch_norm_apply (the real host launch code and every
     kernel under it) on the emulation, behind emu_events_vg (vg_emu.cpp)."""
-    lib = os.path.join(BUILD, "libvg_emu_v2.so" if v2 else "libvg_emu.so")
+    lib = os.path.join(BUILD, "libvg_emu.so")
     srcs = [os.path.join(CSRC, n) for n in ("common.cuh", "event_math.cuh", "voxel_factored.cu", "norm.cu")] + \
            [os.path.join(HERE, "vg_emu.cpp"), os.path.join(HERE, "include", "cuda_runtime.h"), os.path.abspath(__file__)]
     if not force and os.path.isfile(lib) and all(os.path.getmtime(lib) >= os.path.getmtime(s) for s in srcs):
@@ -121,7 +121,7 @@ def build_vg(v2: bool = False, force: bool = False) -> str:
     generate_full()
     gen = os.path.join(BUILD, "gen")
     cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-w",
-           "-I", os.path.join(HERE, "include"), "-I", gen] + (["-DCMDA_BAND_V2=1"] if v2 else []) + \
+           "-I", os.path.join(HERE, "include"), "-I", gen] + \
           ["-o", lib, os.path.join(HERE, "vg_emu.cpp"), os.path.join(gen, "voxel_factored.cpp"), os.path.join(gen, "norm.cpp")]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
@@ -132,11 +132,11 @@ def build_vg(v2: bool = False, force: bool = False) -> str:
 FULL_UNITS = ("api.cu", "slicer.cu", "voxel_global.cu", "voxel_factored.cu", "norm.cu", "pseudo_events.cu", "resize.cu")
 
 
-def build_abi(v2: bool = False, force: bool = False) -> str:
-    """tests/emu/_build/libcmda_b200_emu[_v2].so: the C ABI of include/cmda_b200.h with every translation unit except
+def build_abi(force: bool = False) -> str:
+    """tests/emu/_build/libcmda_b200_emu.so: the C ABI of include/cmda_b200.h with every translation unit except
     the TILED (inline-PTX shared atomics) and EXACT (cub sort) modes compiled against the emulation; those two modes
     answer CMDA_ERR_UNSUPPORTED (abi_emu.cpp).  "Device" pointers are host pointers."""
-    lib = os.path.join(BUILD, "libcmda_b200_emu_v2.so" if v2 else "libcmda_b200_emu.so")
+    lib = os.path.join(BUILD, "libcmda_b200_emu.so")
     srcs = [os.path.join(CSRC, n) for n in ("common.cuh", "event_math.cuh") + FULL_UNITS] + \
            [os.path.join(HERE, "abi_emu.cpp"), os.path.join(HERE, "include", "cuda_runtime.h"), os.path.abspath(__file__),
             os.path.join(ROOT, "include", "cmda_b200.h")]
@@ -146,7 +146,7 @@ def build_abi(v2: bool = False, force: bool = False) -> str:
     gen = os.path.join(BUILD, "gen")
     objs, procs = [], []
     flags = ["-std=c++17", "-O1", "-g", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-w", "-I", os.path.join(HERE, "include"),
-             "-I", gen] + (["-DCMDA_BAND_V2=1"] if v2 else [])
+             "-I", gen]
     for name in FULL_UNITS:
         with open(os.path.join(CSRC, name)) as f:
             src = f.read()
@@ -156,7 +156,7 @@ def build_abi(v2: bool = False, force: bool = False) -> str:
         cpp = os.path.join(gen, name.replace(".cu", ".cpp"))
         with open(cpp, "w") as f:
             f.write(src)
-        obj = os.path.join(gen, name.replace(".cu", "_v2.o" if v2 else ".o"))
+        obj = os.path.join(gen, name.replace(".cu", ".o"))
         objs.append(obj)
         procs.append((name, subprocess.Popen(["g++"] + flags + ["-c", "-o", obj, cpp], stderr=subprocess.PIPE, text=True)))
     for name, pr in procs:
@@ -185,7 +185,5 @@ def build(force: bool = False) -> str:
 
 if __name__ == "__main__":
     print(build(force=True))
-    print(build_vg(False, force=True))
-    print(build_vg(True, force=True))
-    print(build_abi(False, force=True))
-    print(build_abi(True, force=True))
+    print(build_vg(force=True))
+    print(build_abi(force=True))

@@ -25,7 +25,7 @@ int launch_norm_apply(const float*, float*, int, long long, const PartialStats*,
 using namespace cmda;
 
 // out / raw: [S][B][H][W] float32 (raw may be NULL); bins: [S][B] (may be NULL); maps: [n_maps][H][W][2] or NULL;
-// map_ids: [S] or NULL.  banded: 0 = FACTORED (L2 RED stage A), 1 = BANDED (whichever cut the library was built with).
+// map_ids: [S] or NULL.  banded: 0 = FACTORED (L2 RED stage A), 1 = BANDED, 2 = its second cut.
 extern "C" int emu_events_vg(const uint32_t* t, const uint16_t* x, const uint16_t* y, const uint8_t* p, const int64_t* starts,
                              const int64_t* ends, int S, const float* maps, const int32_t* map_ids, int H, int W, int B,
                              const float* clips, int banded, int normalize, float* out, float* raw, int64_t* bins) {

@@ -64,11 +64,13 @@ def test_voxel_modes_and_banded_workspace(L):
     n, S, H, W = 5_000_000, 16, 480, 640
     assert L.cmda_events_vg_resolved_mode(n * S, S, H, W, 5, _lib.VOXEL_AUTO) == _lib.VOXEL_FACTORED
     assert L.cmda_events_vg_resolved_mode(n * S, S, H, W, 5, _lib.VOXEL_BANDED) == _lib.VOXEL_BANDED
-    assert L.cmda_events_vg_resolved_mode(n * S, S, H, W, 5, _lib.VOXEL_BANDED + 1) == -1
+    assert L.cmda_events_vg_resolved_mode(n * S, S, H, W, 5, _lib.VOXEL_BANDED2) == _lib.VOXEL_BANDED2
+    assert L.cmda_events_vg_resolved_mode(n * S, S, H, W, 5, _lib.VOXEL_BANDED2 + 1) == -1
     chunk = 8192
     for bins, rec_bytes in ((5, 5), (1, 2)):
         fact = L.cmda_events_vg_workspace_bytes(n * S, S, H, W, bins, _lib.VOXEL_FACTORED)
         band = L.cmda_events_vg_workspace_bytes(n * S, S, H, W, bins, _lib.VOXEL_BANDED)
+        assert L.cmda_events_vg_workspace_bytes(n * S, S, H, W, bins, _lib.VOXEL_BANDED2) == band      # the two cuts share it
         extra = band - fact
         chunks = n * S // chunk + 2 * S
         assert extra >= rec_bytes * n * S                                   # every event has a record slot

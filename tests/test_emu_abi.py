@@ -1,8 +1,8 @@
 """The C ABI of include/cmda_b200.h on the CPU: every translation unit of libcmda_b200 except the TILED and EXACT voxel
 modes is compiled for the host against the fiber emulation of tests/emu/ ("device" pointers are numpy buffers) and
 run against the committed golden fixtures -- outputs of the reference's own functions -- and the oracle, with the GPU
-suite's rules: bit-exact integers, indices and pseudo-events; stated tolerances for float voxel sums.  Both builds of
-the BANDED stage A (first cut and -DCMDA_BAND_V2) are covered.  This checks the LOGIC of the kernel source and of the
+suite's rules: bit-exact integers, indices and pseudo-events; stated tolerances for float voxel sums.  Both cuts of
+the BANDED stage A (modes BANDED and BANDED2) are covered.  This checks the LOGIC of the kernel source and of the
 host code around it where no GPU exists; it is test infrastructure, shares no path with the product (which has no
 CPU fallback), and the `-m gpu` tests remain the gate for the CUDA build."""
 import ctypes
@@ -26,7 +26,7 @@ VG = golden_io.load("events_vg")
 ISR = golden_io.load("isr")
 IC = golden_io.load("image_change")
 INDEX = golden_io.load("index")
-GLOBAL, AUTO, FACTORED, BANDED = 0, 2, 4, 5
+GLOBAL, AUTO, FACTORED, BANDED, BANDED2 = 0, 2, 4, 5, 6
 DIRECTIONS = {"rightdown": 0, "rightup": 1, "leftdown": 2, "leftup": 3, "all": 4}
 
 
@@ -40,8 +40,8 @@ def _bind(path):
 
 
 @pytest.fixture(scope="module")
-def libs():
-    return {"cut1": _bind(build_emu.build_abi(False)), "cut2": _bind(build_emu.build_abi(True))}
+def L():
+    return _bind(build_emu.build_abi())
 
 
 def ptr(a):
@@ -76,23 +76,20 @@ def events_vg(L, c, mode, clip):
     return out[0], raw[0], counts[0], rmap
 
 
-def test_emulated_build_exports_the_whole_abi(libs):
-    for L in libs.values():
-        assert L.cmda_version() == 100
-        assert L.cmda_events_vg_resolved_mode(1000, 1, 480, 640, 5, AUTO) == FACTORED
+def test_emulated_build_exports_the_whole_abi(L):
+    assert L.cmda_version() == 100
+    assert L.cmda_events_vg_resolved_mode(1000, 1, 480, 640, 5, AUTO) == FACTORED
 
 
 @pytest.mark.parametrize("name", sorted(k for k in VG if VG[k]["rectify_map"].ndim == 3))
-@pytest.mark.parametrize("mode", [GLOBAL, FACTORED, BANDED])
-def test_events_vg_golden(libs, name, mode):
+@pytest.mark.parametrize("mode", [GLOBAL, FACTORED, BANDED, BANDED2])
+def test_events_vg_golden(L, name, mode):
     c = VG[name]
     W, H, B = int(c["width"]), int(c["height"]), int(c["bins"])
     start, finish = int(c["start"]), int(c["finish"])
     clip = float(c["clip"][0]) if c["clip"].size else O.default_clip_range(finish, start)
     sl = slice(start, finish + 1)
-    for key, L in libs.items():
-        if key == "cut2" and mode != BANDED:
-            continue                                                # the two builds differ in the BANDED kernels only
+    if True:
         out, raw, counts, rmap = events_vg(L, c, mode, clip)
         tf, xf, yf, pf = O.rectify_events(c["t"][sl], c["x"][sl], c["y"][sl], c["p"][sl], rmap)
         ref_raw, aux = O.events_to_voxel_grid(tf, xf, yf, pf, W, H, B, return_aux=True)
@@ -106,7 +103,6 @@ def test_events_vg_golden(libs, name, mode):
         if not ((raw == 0) != (ref_raw == 0)).any():
             np.testing.assert_allclose(out, c["result"], rtol=0, atol=1e-5)
     # integer side outputs: bit-exact
-    L = libs["cut1"]
     n = finish + 1 - start
     xr, yr, tn = (np.empty(n, np.float32) for _ in range(3))
     x0, y0, t0 = (np.empty(n, np.int32) for _ in range(3))
@@ -118,8 +114,8 @@ def test_events_vg_golden(libs, name, mode):
 
 
 @pytest.mark.parametrize("name", sorted(VOXEL))
-def test_voxel_grid_f32_golden(libs, name):
-    c, L = VOXEL[name], libs["cut1"]
+def test_voxel_grid_f32_golden(L, name):
+    c = VOXEL[name]
     W, H, B, n = int(c["width"]), int(c["height"]), int(c["bins"]), int(c["time"].shape[0])
     tm, x, y, pol = (np.ascontiguousarray(c[k], dtype=np.float32) for k in ("time", "x", "y", "pol"))
     grid = np.full((B, H, W), np.nan, dtype=np.float32)
@@ -133,8 +129,8 @@ def test_voxel_grid_f32_golden(libs, name):
 
 
 @pytest.mark.parametrize("name", sorted(k for k in NORM if k.startswith("norm_")))
-def test_events_norm_golden(libs, name):
-    c, L = NORM[name], libs["cut1"]
+def test_events_norm_golden(L, name):
+    c = NORM[name]
     grid = np.ascontiguousarray(NORM["normgrid_" + str(c["grid"])]["events"], dtype=np.float32).copy()
     clips = np.array([float(c["clip_range"])], dtype=np.float32)
     need = L.cmda_events_norm_workspace_bytes(1)
@@ -144,8 +140,8 @@ def test_events_norm_golden(libs, name):
     np.testing.assert_allclose(grid, c["result"], rtol=0, atol=1e-5)
 
 
-def test_images_to_events_index_golden(libs):
-    c, L = INDEX["index_table"], libs["cut1"]
+def test_images_to_events_index_golden(L):
+    c = INDEX["index_table"]
     t = np.ascontiguousarray(c["t"], dtype=np.uint32)
     ms = np.ascontiguousarray(c["ms_to_idx"], dtype=np.int64)
     ts = np.ascontiguousarray(c["timestamps"], dtype=np.int64)
@@ -178,8 +174,8 @@ def _isr(L, img, channels, c):
 
 
 @pytest.mark.parametrize("name", sorted(k for k in ISR if "lut" in ISR[k]))
-def test_isr_golden_bit_exact(libs, name):
-    c, L = ISR[name], libs["cut1"]
+def test_isr_golden_bit_exact(L, name):
+    c = ISR[name]
     out, lut = _isr(L, ISR["isr_input"]["rgb"], 3, c)
     assert np.array_equal(bits(lut), bits(c["lut"])), "host LUT == the reference's np.log values"
     assert np.array_equal(bits(out), bits(c["result"]))
@@ -187,8 +183,7 @@ def test_isr_golden_bit_exact(libs, name):
     assert np.array_equal(bits(out), bits(c["result"]))
 
 
-def test_rgb_to_gray_bit_exact(libs):
-    L = libs["cut1"]
+def test_rgb_to_gray_bit_exact(L):
     rgb = np.ascontiguousarray(ISR["isr_input"]["rgb"])
     gray = np.zeros(rgb.shape[:2], dtype=np.uint8)
     assert L.cmda_rgb_to_gray_u8(ptr(rgb), gray.size, ptr(gray), None) == 0
@@ -196,9 +191,9 @@ def test_rgb_to_gray_bit_exact(libs):
 
 
 @pytest.mark.parametrize("name", sorted(IC))
-def test_image_change_pair_golden(libs, name):
+def test_image_change_pair_golden(L, name):
     from cmda_b200 import image_change as ic
-    c, L = IC[name], libs["cut1"]
+    c = IC[name]
     now, front = np.ascontiguousarray(c["now"]), np.ascontiguousarray(c["front"])
     H, W = now.shape
     lut = ic.log_lut_log_add(ic.log_add)
@@ -214,9 +209,8 @@ def test_image_change_pair_golden(libs, name):
 
 
 @pytest.mark.parametrize("shape,size,channels", [((67, 131), (50, 40), 1), ((64, 96), (48, 32), 3), ((33, 47), (47, 60), 1)])
-def test_resize_bilinear_matches_pillow(libs, shape, size, channels):
+def test_resize_bilinear_matches_pillow(L, shape, size, channels):
     from PIL import Image
-    L = libs["cut1"]
     rng = np.random.default_rng(shape[0])
     img = rng.integers(0, 256, size=shape + ((3,) if channels == 3 else ()), dtype=np.uint8)
     out_w, out_h = size
@@ -258,7 +252,7 @@ def _vg_batch(L, t, x, y, p, starts, fins, maps, mids, H, W, B, mode, aug=None, 
     return out, counts
 
 
-def test_many_windows_and_maps_through_the_group_loop(libs):
+def test_many_windows_and_maps_through_the_group_loop(L):
     """More windows than one launch group holds (64) and more distinct maps than one group builds plans for (8):
     the offsets of api.cu's group loop, with the FACTORED stage A and both BANDED cuts, window by window against the
     oracle."""
@@ -274,8 +268,8 @@ def test_many_windows_and_maps_through_the_group_loop(libs):
     fins[100] = starts[100]                                  # a single-event window in the second
     mids = rng.integers(0, n_maps, size=S)
     mids[:12] = np.arange(12) % n_maps                       # > 8 distinct maps inside the first windows
-    base, base_counts = _vg_batch(libs["cut1"], t, x, y, p, starts, fins, maps, mids, H, W, B, FACTORED)
-    raw, _ = _vg_batch(libs["cut1"], t, x, y, p, starts, fins, maps, mids, H, W, B, FACTORED, normalize=0)
+    base, base_counts = _vg_batch(L, t, x, y, p, starts, fins, maps, mids, H, W, B, FACTORED)
+    raw, _ = _vg_batch(L, t, x, y, p, starts, fins, maps, mids, H, W, B, FACTORED, normalize=0)
     for s in range(S):
         if fins[s] < starts[s]:
             assert not raw[s].any() and int(base_counts[s].sum()) == 0
@@ -288,12 +282,12 @@ def test_many_windows_and_maps_through_the_group_loop(libs):
         assert np.array_equal(base_counts[s], aux["bin_counts"]), f"window {s}"
         clip = O.default_clip_range(int(fins[s]), int(starts[s]))
         np.testing.assert_allclose(base[s], O.events_norm(raw[s].copy(), clip, 1.0, True), rtol=0, atol=1e-5, err_msg=f"window {s}")
-    for key in ("cut1", "cut2"):
-        out, counts = _vg_batch(libs[key], t, x, y, p, starts, fins, maps, mids, H, W, B, BANDED)
-        assert np.array_equal(bits(out), bits(base)) and np.array_equal(counts, base_counts), key
+    for mode in (BANDED, BANDED2):
+        out, counts = _vg_batch(L, t, x, y, p, starts, fins, maps, mids, H, W, B, mode)
+        assert np.array_equal(bits(out), bits(base)) and np.array_equal(counts, base_counts), mode
 
 
-def test_fused_augmentation_many_windows(libs):
+def test_fused_augmentation_many_windows(L):
     """dsec.py:304-319 fused into the normaliser (crop / flip / bilinear resize / repeat) past one launch group, on
     top of the FACTORED and both BANDED stage A: against the unfused path + the oracle's post-voxel stage."""
     from cmda_b200 import synth
@@ -308,10 +302,10 @@ def test_fused_augmentation_many_windows(libs):
     crop_size, out_size = (24, 20), (32, 28)                    # (w, h)
     xy = [(int(rng.integers(0, W - 24 + 1)), int(rng.integers(0, H - 20 + 1))) for _ in range(S)]
     flips = [int(v) for v in rng.integers(0, 2, size=S)]
-    grid, _ = _vg_batch(libs["cut1"], t, x, y, p, starts, fins, maps, mids, H, W, B, FACTORED)
+    grid, _ = _vg_batch(L, t, x, y, p, starts, fins, maps, mids, H, W, B, FACTORED)
     first = None
-    for key, mode in (("cut1", FACTORED), ("cut1", BANDED), ("cut2", BANDED)):
-        got, _ = _vg_batch(libs[key], t, x, y, p, starts, fins, maps, mids, H, W, B, mode, aug=(xy, crop_size, out_size, flips, 3))
+    for mode in (FACTORED, BANDED, BANDED2):
+        got, _ = _vg_batch(L, t, x, y, p, starts, fins, maps, mids, H, W, B, mode, aug=(xy, crop_size, out_size, flips, 3))
         assert got.shape == (S, 3 * B, 28, 32)
         if first is None:
             first = got
@@ -320,4 +314,4 @@ def test_fused_augmentation_many_windows(libs):
                                        avg_bins=False, enforce_3_channels=True, test_mode=False)
                 np.testing.assert_allclose(got[s], exp, rtol=0, atol=1e-5, err_msg=f"window {s}")
         else:
-            assert np.array_equal(bits(got), bits(first)), (key, mode)
+            assert np.array_equal(bits(got), bits(first)), mode

@@ -28,8 +28,8 @@ def _load(path):
 
 
 @pytest.fixture(scope="module")
-def libs():
-    return _load(build_emu.build_vg(False)), _load(build_emu.build_vg(True))
+def lib():
+    return _load(build_emu.build_vg())
 
 
 def events_vg(lib, t, x, y, p, starts, fins, maps, mids, H, W, B, banded, normalize=True):
@@ -66,15 +66,14 @@ def check_normalised(out, raw, t, x, y, p, start, fin, rmap, W, H, bins):
 
 
 @pytest.mark.parametrize("bins", [1, 5])
-def test_emulated_voxel_path_against_the_oracle(libs, bins):
+def test_emulated_voxel_path_against_the_oracle(lib, bins):
     from cmda_b200 import synth
-    lib1, lib2 = libs
     H, W, n = 480, 640, 150_000
     t, x, y, p = synth.make_events(n, H, W, seed=synth.seed_for(3, bins), skew=0.2)
     t[-2000:] = t[-2000]
     maps = np.stack([synth.make_rectify_map(H, W, seed=5), synth.make_rectify_map(H, W, seed=6, k1=0.03)])
     starts, fins, mids = [0, 1001, 600, n - 1500, 40_000], [n - 2500, 70_000, 599, n - 1, 40_000], [0, 1, 0, 1, 1]
-    out, raw, counts = events_vg(lib1, t, x, y, p, starts, fins, maps, mids, H, W, bins, banded=False)
+    out, raw, counts = events_vg(lib, t, x, y, p, starts, fins, maps, mids, H, W, bins, banded=0)
     for s in range(len(starts)):
         if fins[s] < starts[s]:                                        # empty window: zero raw grid, events_norm of zeros
             assert not raw[s].any()
@@ -93,25 +92,24 @@ def test_emulated_voxel_path_against_the_oracle(libs, bins):
     for s in live:                                                      # one map per oracle call
         check_normalised(out[s], raw[s], t, x, y, p, starts[s], fins[s], maps[mids[s]], W, H, bins)
     # the BANDED stage A, first and second cut: the same R, hence the same bits all the way down
-    for lib in (lib1, lib2):
-        o2, r2, c2 = events_vg(lib, t, x, y, p, starts, fins, maps, mids, H, W, bins, banded=True)
+    for cut in (1, 2):
+        o2, r2, c2 = events_vg(lib, t, x, y, p, starts, fins, maps, mids, H, W, bins, banded=cut)
         assert np.array_equal(r2.view(np.uint32), raw.view(np.uint32))
         assert np.array_equal(o2.view(np.uint32), out.view(np.uint32))
         assert np.array_equal(c2, counts)
 
 
-def test_emulated_voxel_path_small_grids_and_no_map(libs):
+def test_emulated_voxel_path_small_grids_and_no_map(lib):
     from cmda_b200 import synth
-    lib1, lib2 = libs
     for (H, W), bins in (((37, 53), 3), ((24, 700), 2)):
         n = 20_000
         t, x, y, p = synth.make_events(n, H, W, seed=synth.seed_for(4, H))
         rmap = synth.make_rectify_map(H, W, seed=9)
         starts, fins = [0, 33], [n - 1, 9000]
         for maps in (rmap[None], None):
-            out, raw, counts = events_vg(lib1, t, x, y, p, starts, fins, maps, None, H, W, bins, banded=False)
+            out, raw, counts = events_vg(lib, t, x, y, p, starts, fins, maps, None, H, W, bins, banded=0)
             for s in range(2):
                 check_normalised(out[s], raw[s], t, x, y, p, starts[s], fins[s], None if maps is None else rmap, W, H, bins)
-            for lib in (lib1, lib2):
-                o2, r2, c2 = events_vg(lib, t, x, y, p, starts, fins, maps, None, H, W, bins, banded=True)
+            for cut in (1, 2):
+                o2, r2, c2 = events_vg(lib, t, x, y, p, starts, fins, maps, None, H, W, bins, banded=cut)
                 assert np.array_equal(o2.view(np.uint32), out.view(np.uint32)) and np.array_equal(c2, counts)
