@@ -1,5 +1,5 @@
 """Kernel-logic checks without a GPU: the stage-A kernels of cmda_b200/csrc/voxel_factored.cu -- the L2-RED kernel,
-the BANDED pair and its second cut (-DCMDA_BAND_V2) -- are compiled for the host against a fiber-based stand-in for
+the BANDED pair and its second cut (mode BANDED2) -- are compiled for the host against a fiber-based stand-in for
 CUDA (tests/emu/) and run on small windows.  All three must produce the same sensor-space grid R and the same
 per-bin event counts, bit for bit, and R must equal a direct numpy restatement of its definition
 (R[t0][y][x] += sign * (2^44 + round(f * 2^24)), voxel_factored.cu header).  This is test infrastructure: it shares

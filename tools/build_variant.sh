@@ -1,7 +1,7 @@
 #!/bin/bash
 # Builds cmda_b200/variants/lib_<name>.so: the library with voxel_factored.cu compiled under extra -D flags
 # (kernel-shape sweeps without touching the shipped build).  Use: CMDA_B200_LIB=cmda_b200/variants/lib_<name>.so python bench.py ...
-#   tools/build_variant.sh rows40 "-DCMDA_BAND_ROWS=40"
+#   tools/build_variant.sh rows40 "-DCMDA_BAND_ROWS=40"      (CMDA_BAND_V2_UNROLL, CMDA_BAND_UNROLL, ... : voxel_factored.cu)
 set -e
 cd "$(dirname "$0")/../cmda_b200/csrc"
 name=$1; shift
