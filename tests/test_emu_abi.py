@@ -315,3 +315,82 @@ def test_fused_augmentation_many_windows(L):
                 np.testing.assert_allclose(got[s], exp, rtol=0, atol=1e-5, err_msg=f"window {s}")
         else:
             assert np.array_equal(bits(got), bits(first)), mode
+
+
+def test_denorm_to_gray_and_crop_to_centered(L):
+    """f-2 / f-4 hand-offs: normalised float image -> uint8 RGB -> PIL 'L' (dacs.py:730-733), and crop -> flip ->
+    (x / 255 - 0.5) / 0.5 -> repeat (cityscapes_ic.py:177-183, 207-209): bit-exact against the oracle."""
+    rng = np.random.default_rng(21)
+    means, stds = np.array([123.675, 116.28, 103.53], np.float32), np.array([58.395, 57.12, 57.375], np.float32)
+    S, H, W = 2, 48, 64
+    img = rng.normal(0.0, 1.4, size=(S, 3, H, W)).astype(np.float32)
+    gray = np.zeros((S, H, W), dtype=np.uint8)
+    rgb = np.zeros((S, H, W, 3), dtype=np.uint8)
+    assert L.cmda_denorm_rgb_to_gray_u8(ptr(img), S, H, W, ptr(means), ptr(stds), ptr(gray), ptr(rgb), None) == 0
+    for s in range(S):
+        g_ref, rgb_ref = O.mixed_image_to_gray(img[s], means, stds, return_rgb=True)
+        assert np.array_equal(gray[s], g_ref) and np.array_equal(rgb[s], rgb_ref)
+    table = np.array([[5, 3, 0], [17, 9, 1]], dtype=np.int32)              # crop_x, crop_y, flip
+    cw, ch, rep = 40, 32, 3
+    out = np.full((S, rep, ch, cw), np.nan, dtype=np.float32)
+    assert L.cmda_u8_crop_to_centered_f32(ptr(gray), S, H, W, ptr(table), cw, ch, rep, ptr(out), None) == 0
+    for s in range(S):
+        want = O.u8_crop_to_centered(gray[s], (int(table[s, 0]), int(table[s, 1])), (cw, ch), flip_flag=bool(table[s, 2]), repeat=rep)
+        assert np.array_equal(bits(out[s]), bits(want))
+
+
+@pytest.mark.parametrize("avg,test_mode", [(True, False), (False, True)])
+def test_fused_augmentation_options(L, avg, test_mode):
+    """The other options of dsec.py:304-319 in the fused normaliser: mean over the bins (events_bins_5_avg_1) and the
+    test-mode crop [:, :440, :] without resize, against the oracle's post-voxel stage applied to the unfused grid."""
+    from cmda_b200 import synth
+    H, W, B, n = 480, 640, 5, 60_000
+    t, x, y, p = synth.make_events(n, H, W, seed=synth.seed_for(5, 5))
+    rmap = synth.make_rectify_map(H, W, seed=12)[None]
+    starts, fins = [0, 5000], [n - 1, 40_000]
+    crop_size, out_size = ((W, 440), (W, 440)) if test_mode else ((400, 400), (512, 512))
+    xy = [(0, 0), (0, 0)] if test_mode else [(37, 61), (240, 80)]
+    flips = [0, 0] if test_mode else [1, 0]
+    grid, _ = _vg_batch(L, t, x, y, p, starts, fins, rmap, None, H, W, B, FACTORED)
+    S = 2
+    st = np.ascontiguousarray(starts, dtype=np.int64)
+    en = np.ascontiguousarray(fins, dtype=np.int64) + 1
+    clips = np.array([O.default_clip_range(int(f), int(s)) for s, f in zip(starts, fins)], dtype=np.float32)
+    table = np.array([[cx, cy, fl] for (cx, cy), fl in zip(xy, flips)], dtype=np.int32)
+    Bo = 1 if avg else B
+    for mode in (FACTORED, BANDED2):
+        out = np.full((S, 3 * Bo, out_size[1], out_size[0]), np.nan, dtype=np.float32)
+        need = L.cmda_events_vg_augmented_workspace_bytes(int((en - st).sum()), S, H, W, B, mode)
+        ws = workspace(need)
+        rc = L.cmda_events_vg_augmented_batch(ptr(t), ptr(x), ptr(y), ptr(p), ptr(st), ptr(en), S, ptr(rmap), None, H, W, B, ptr(clips),
+                                              1.0, 1, ptr(table), crop_size[0], crop_size[1], out_size[0], out_size[1], int(avg), 3,
+                                              ptr(out), None, None, ptr(ws), need, mode, None, None)
+        assert rc == 0, L.cmda_strerror(rc)
+        for s in range(S):
+            exp = O.events_vg_post(grid[s], crop_xy=xy[s], crop_size=crop_size, out_size=out_size, flip_flag=bool(flips[s]),
+                                   avg_bins=avg, enforce_3_channels=True, test_mode=test_mode)
+            np.testing.assert_allclose(out[s], exp, rtol=0, atol=1e-5)
+
+
+def test_prebuilt_plans_equal_per_call_plans(L):
+    """cmda_rectify_plan_build once per sequence == the plans built inside every call: same bits."""
+    from cmda_b200 import synth
+    H, W, B, n = 120, 160, 3, 30_000
+    t, x, y, p = synth.make_events(n, H, W, seed=8)
+    maps = np.stack([synth.make_rectify_map(H, W, seed=40 + k) for k in range(3)]).astype(np.float32)
+    starts, fins, mids = [0, 100, 7000], [n - 1, 9000, 20_000], np.array([2, 0, 1], dtype=np.int32)
+    base, counts = _vg_batch(L, t, x, y, p, starts, fins, maps, mids, H, W, B, FACTORED)
+    nb = L.cmda_rectify_plan_bytes(H, W)
+    plans = workspace(3 * nb)
+    assert L.cmda_rectify_plan_build(ptr(maps), 3, H, W, ptr(plans), None) == 0
+    st = np.ascontiguousarray(starts, dtype=np.int64)
+    en = np.ascontiguousarray(fins, dtype=np.int64) + 1
+    clips = np.array([O.default_clip_range(int(f), int(s)) for s, f in zip(starts, fins)], dtype=np.float32)
+    for mode in (FACTORED, BANDED, BANDED2):
+        out = np.full((3, B, H, W), np.nan, dtype=np.float32)
+        need = L.cmda_events_vg_workspace_bytes(int((en - st).sum()), 3, H, W, B, mode)
+        ws = workspace(need)
+        rc = L.cmda_events_vg_batch_planned(ptr(t), ptr(x), ptr(y), ptr(p), ptr(st), ptr(en), 3, ptr(maps), ptr(mids), H, W, B,
+                                            ptr(clips), 1.0, 1, 1, ptr(out), None, None, ptr(ws), need, mode, ptr(plans), None)
+        assert rc == 0, L.cmda_strerror(rc)
+        assert np.array_equal(bits(out), bits(base)), mode
