@@ -15,5 +15,5 @@ mkdir -p gpurun_out
 import json,sys;d=json.load(sys.stdin);print('$m B=$b', round(d['ms_per_step'],3), [round(v,3) for v in d['roofline']['phase_ms'].values()], d['e2e']['matches_device_path'])"
     done
   done
-  echo "== split_probe"; timeout 90 python tools/split_probe.py --bins 5 2>&1 | tail -8
+  echo "== split_probe"; timeout 90 python tools/split_probe.py --bins 5 2>&1 | tail -8; timeout 90 python tools/split_probe.py --bins 5 --second banded2 --splits 4,6,8,10 2>&1 | tail -5
 } | tee gpurun_out/round2_first_call.txt

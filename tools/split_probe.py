@@ -20,6 +20,7 @@ ap.add_argument("--events", type=int, default=bench.EVENTS_PER_WINDOW)
 ap.add_argument("--windows", type=int, default=bench.WINDOWS_PER_GPU)
 ap.add_argument("--steps", type=int, default=20)
 ap.add_argument("--splits", default="0,4,6,8,10,12,16", help="windows given to FACTORED, comma separated")
+ap.add_argument("--second", default="banded", choices=["banded", "banded2"], help="mode of the second stream")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 t, x, y, p, rmap, starts, fins = bench.make_workload(a.windows, a.events, seed_base=0)
@@ -34,7 +35,7 @@ fork, join = torch.cuda.Event(), [torch.cuda.Event(), torch.cuda.Event()]
 def step(k):
     main = torch.cuda.current_stream(dev)
     fork.record(main)
-    parts = ((side[0], "factored", slice(0, k)), (side[1], "banded", slice(k, S)))
+    parts = ((side[0], "factored", slice(0, k)), (side[1], a.second, slice(k, S)))
     for i, (st, mode, sl) in enumerate(parts):
         if sl.stop - sl.start <= 0:
             continue
@@ -58,5 +59,5 @@ for k in [int(v) for v in a.splits.split(",")]:
         step(k)
     e1.record()
     torch.cuda.synchronize(dev)
-    print(f"B={a.bins} factored windows {k:2d} | banded windows {S - k:2d}: {e0.elapsed_time(e1) / a.steps:.3f} ms per step, "
+    print(f"B={a.bins} factored windows {k:2d} | {a.second} windows {S - k:2d}: {e0.elapsed_time(e1) / a.steps:.3f} ms per step, "
           f"bit-identical to FACTORED alone: {same}", flush=True)
