@@ -219,8 +219,17 @@ sensor_accumulate_kernel(const uint32_t* __restrict__ t, const uint16_t* __restr
 #ifndef CMDA_BAND_UNROLL_B1
 #define CMDA_BAND_UNROLL_B1 4     // B == 1 (4: 0.098 ms, 8: 0.110 on C2)
 #endif
-constexpr int kBandPartThreads = 512;
-constexpr int kBandPartGroups = 2;                                              // 8 events per group
+#ifndef CMDA_BAND_PART_THREADS
+#define CMDA_BAND_PART_THREADS 512
+#endif
+#ifndef CMDA_BAND_PART_GROUPS
+#define CMDA_BAND_PART_GROUPS 2
+#endif
+constexpr int kBandPartThreads = CMDA_BAND_PART_THREADS;                        // 512 x 2 or 1024 x 1: the chunk stays 8 192 events
+constexpr int kBandPartGroups = CMDA_BAND_PART_GROUPS;                          // 8 events per group
+constexpr int kBandPartMinBlocks = 2048 / kBandPartThreads > 2 ? 2 : 2048 / kBandPartThreads;
+static_assert(kBandPartThreads % 32 == 0 && kBandPartThreads <= 1024 && kBandPartThreads * kBandPartGroups * 8 <= 8192,
+              "the rank of a record inside its chunk takes 13 bits of the slot word");
 constexpr int kBandChunk = kBandPartThreads * kBandPartGroups * 8;              // events per partition CTA
 constexpr int kBandAccThreads = CMDA_BAND_ACC_THREADS;
 constexpr int kBandMaxBuckets = 2047;     // (temporal bin, band) buckets of one chunk (2047: an all-ones slot word means "dropped")
@@ -260,7 +269,7 @@ static bool pick_band_geom(int H, int W, int B, BandGeom& g) {
 }
 
 template <bool HAS_T, bool VEC>
-__global__ void __launch_bounds__(kBandPartThreads, 2)
+__global__ void __launch_bounds__(kBandPartThreads, kBandPartMinBlocks)
 band_partition_kernel(const uint32_t* __restrict__ t, const uint16_t* __restrict__ x, const uint16_t* __restrict__ y,
                       const uint8_t* __restrict__ p, const __grid_constant__ WindowTable tab,
                       const __grid_constant__ BandTable bt, BandGeom g, int H, int W, int B, unsigned* __restrict__ table,
@@ -534,9 +543,22 @@ band_accumulate_kernel(const unsigned* __restrict__ table, const unsigned* __res
 #define CMDA_BAND_V2_UNROLL 4
 #endif
 static_assert(CMDA_BAND_XSUB == 1, "the second cut ranks in the table's own buckets");
+// CTA shape of the second cut's partition pass: 1 024 threads x one group of 8 events compile to 32 registers (two CTAs =
+// 64 warps per SM, no spills) where 512 x 2 needs 64 registers and spills 30 of them; same 8 192-event chunk
+#ifndef CMDA_BAND2_PART_THREADS
+#define CMDA_BAND2_PART_THREADS 1024
+#endif
+#ifndef CMDA_BAND2_PART_GROUPS
+#define CMDA_BAND2_PART_GROUPS 1
+#endif
+constexpr int kBand2PartThreads = CMDA_BAND2_PART_THREADS;
+constexpr int kBand2PartGroups = CMDA_BAND2_PART_GROUPS;
+constexpr int kBand2PartMinBlocks = 2048 / kBand2PartThreads > 2 ? 2 : 2048 / kBand2PartThreads;
+static_assert(kBand2PartThreads % 32 == 0 && kBand2PartThreads <= 1024 && kBand2PartThreads * kBand2PartGroups * 8 == kBandChunk,
+              "both cuts share the chunk size (record buffer layout, chunk table)");
 
 template <bool HAS_T, bool VEC>
-__global__ void __launch_bounds__(kBandPartThreads, 2)
+__global__ void __launch_bounds__(kBand2PartThreads, kBand2PartMinBlocks)
 band_partition2_kernel(const uint32_t* __restrict__ t, const uint16_t* __restrict__ x, const uint16_t* __restrict__ y,
                        const uint8_t* __restrict__ p, const __grid_constant__ WindowTable tab,
                        const __grid_constant__ BandTable bt, BandGeom g, int H, int W, int B, unsigned* __restrict__ table,
@@ -549,17 +571,17 @@ band_partition2_kernel(const uint32_t* __restrict__ t, const uint16_t* __restric
     unsigned* s_stage32 = s_loff + ((NB + 2 + 3) & ~3);                         // [kBandChunk] (B > 1)
     unsigned char* s_stage8 = reinterpret_cast<unsigned char*>(s_stage32 + kBandChunk);     // [kBandChunk] (B > 1)
     unsigned short* s_stage16 = reinterpret_cast<unsigned short*>(s_stage32);   // [kBandChunk] (B == 1)
-    __shared__ unsigned s_warp[kBandPartThreads / 32];
+    __shared__ unsigned s_warp[kBand2PartThreads / 32];
 
     const int s = blockIdx.y, c = blockIdx.x;
     if (c >= bt.nchunks[s]) return;
     const WindowDesc wd = tab.w[s];
     const long long g0 = wd.start >> 3, g1 = (wd.end + 7) >> 3;
-    const long long first = g0 + static_cast<long long>(c) * (kBandPartThreads * kBandPartGroups);
-    SensEv8 ev[kBandPartGroups];
+    const long long first = g0 + static_cast<long long>(c) * (kBand2PartThreads * kBand2PartGroups);
+    SensEv8 ev[kBand2PartGroups];
 #pragma unroll
-    for (int j = 0; j < kBandPartGroups; ++j) {
-        const long long grp = first + static_cast<long long>(j) * kBandPartThreads + threadIdx.x;
+    for (int j = 0; j < kBand2PartGroups; ++j) {
+        const long long grp = first + static_cast<long long>(j) * kBand2PartThreads + threadIdx.x;
         if (grp < g1) {
             ev[j] = sens_load8<HAS_T, VEC>(t, x, y, p, grp << 3, wd.start, wd.end);
         } else {
@@ -570,14 +592,14 @@ band_partition2_kernel(const uint32_t* __restrict__ t, const uint16_t* __restric
     const RawWindowTime rw = raw_window_time(t, wd.start, wd.end, B);
     const bool alive = rw.den == 1.0f;                                          // NaN: single-timestamp window
     const float r_dT = __frcp_rn(rw.fdT);
-    for (int k = threadIdx.x; k <= NB; k += kBandPartThreads) s_hist[k] = 0u;
+    for (int k = threadIdx.x; k <= NB; k += kBand2PartThreads) s_hist[k] = 0u;
     __syncthreads();
 
-    unsigned slot[kBandPartGroups][8];      // bucket << 21 | rank << 8 | (B > 1) cell high bits | neg << 7
-    unsigned rec[kBandPartGroups][8];       // B > 1: f << 8 | cell low byte;  B == 1: cell | neg << 15
+    unsigned slot[kBand2PartGroups][8];      // bucket << 21 | rank << 8 | (B > 1) cell high bits | neg << 7
+    unsigned rec[kBand2PartGroups][8];       // B > 1: f << 8 | cell low byte;  B == 1: cell | neg << 15
     int odd = 0;                            // a polarity byte beyond {0, 1}: its record says +1, band_fixup_kernel adds the rest
 #pragma unroll
-    for (int j = 0; j < kBandPartGroups; ++j) {
+    for (int j = 0; j < kBand2PartGroups; ++j) {
         const unsigned xs[4] = {ev[j].x.x, ev[j].x.y, ev[j].x.z, ev[j].x.w}, ys[4] = {ev[j].y.x, ev[j].y.y, ev[j].y.z, ev[j].y.w};
         const unsigned ts[8] = {ev[j].t0.x, ev[j].t0.y, ev[j].t0.z, ev[j].t0.w, ev[j].t1.x, ev[j].t1.y, ev[j].t1.z, ev[j].t1.w};
 #pragma unroll
@@ -611,7 +633,7 @@ band_partition2_kernel(const uint32_t* __restrict__ t, const uint16_t* __restric
     const int any_odd = __syncthreads_or(odd);
     // exclusive scan of the NB + 1 bucket counts (each thread owns a contiguous run of buckets; with the usual
     // hundred-odd buckets only the first warps own any, the others go straight to the barriers)
-    const int per = (NB + 1 + kBandPartThreads - 1) / kBandPartThreads;
+    const int per = (NB + 1 + kBand2PartThreads - 1) / kBand2PartThreads;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const bool owner_warp = wid * 32 * per <= NB;
     unsigned mine = 0, inc = 0;
@@ -630,14 +652,14 @@ band_partition2_kernel(const uint32_t* __restrict__ t, const uint16_t* __restric
     if (lane == 31) s_warp[wid] = inc;
     __syncthreads();
     if (wid == 0) {
-        const unsigned a = (lane < kBandPartThreads / 32) ? s_warp[lane] : 0u;
+        const unsigned a = (lane < kBand2PartThreads / 32) ? s_warp[lane] : 0u;
         unsigned ia = a;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const unsigned u = __shfl_up_sync(0xffffffffu, ia, o);
             if (lane >= o) ia += u;
         }
-        if (lane < kBandPartThreads / 32) s_warp[lane] = ia - a;
+        if (lane < kBand2PartThreads / 32) s_warp[lane] = ia - a;
     }
     __syncthreads();
     if (owner_warp) {
@@ -655,7 +677,7 @@ band_partition2_kernel(const uint32_t* __restrict__ t, const uint16_t* __restric
     }
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < kBandPartGroups; ++j) {
+    for (int j = 0; j < kBand2PartGroups; ++j) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const unsigned sl = slot[j][e];
@@ -673,14 +695,14 @@ band_partition2_kernel(const uint32_t* __restrict__ t, const uint16_t* __restric
     const size_t base = static_cast<size_t>(bt.rec_base[s]) + static_cast<size_t>(c) * kBandChunk;
     if constexpr (HAS_T) {
         unsigned* d32 = rec32 + base;
-        for (unsigned i = threadIdx.x; i < total; i += kBandPartThreads) d32[i] = s_stage32[i];
+        for (unsigned i = threadIdx.x; i < total; i += kBand2PartThreads) d32[i] = s_stage32[i];
         const unsigned* s8w = reinterpret_cast<const unsigned*>(s_stage8);
         unsigned* d8w = reinterpret_cast<unsigned*>(rec8 + base);
-        for (unsigned i = threadIdx.x; i < (total + 3) / 4; i += kBandPartThreads) d8w[i] = s8w[i];
+        for (unsigned i = threadIdx.x; i < (total + 3) / 4; i += kBand2PartThreads) d8w[i] = s8w[i];
     } else {
         const unsigned* s16w = reinterpret_cast<const unsigned*>(s_stage16);
         unsigned* d16w = reinterpret_cast<unsigned*>(rec16 + base);
-        for (unsigned i = threadIdx.x; i < (total + 1) / 2; i += kBandPartThreads) d16w[i] = s16w[i];
+        for (unsigned i = threadIdx.x; i < (total + 1) / 2; i += kBand2PartThreads) d16w[i] = s16w[i];
     }
     // events per temporal bin: the buckets of bin b are [b * nbands, (b + 1) * nbands)
     if (bin_counts != nullptr && threadIdx.x < (HAS_T ? B : 1)) {
@@ -1445,20 +1467,20 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
             const int fine = banded == 2 ? bg.nbuckets + 1 : (bg.nbuckets << bg.xsub_log2);
             const size_t shm = sizeof(unsigned) * (fine + ((fine + 1 + 3) & ~3)) + (B > 1 ? 5u : 2u) * static_cast<size_t>(kBandChunk);
             dim3 grid(static_cast<unsigned>(max_chunks), S);
-#define CMDA_BAND_PART(KERNEL, HAS_T, VEC)                                                                                     \
+#define CMDA_BAND_PART(KERNEL, THREADS, HAS_T, VEC)                                                                            \
     do {                                                                                                                       \
         CMDA_CUDA_TRY(cudaFuncSetAttribute(KERNEL<HAS_T, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,                    \
                                            static_cast<int>(shm)));                                                            \
-        KERNEL<HAS_T, VEC><<<grid, kBandPartThreads, shm, st>>>(t, x, y, p, tab, bt, bg, H, W, B, z.table, z.rec32, z.rec8,    \
-                                                                z.rec16, ubins);                                               \
+        KERNEL<HAS_T, VEC><<<grid, THREADS, shm, st>>>(t, x, y, p, tab, bt, bg, H, W, B, z.table, z.rec32, z.rec8, z.rec16,    \
+                                                       ubins);                                                                 \
     } while (0)
-#define CMDA_BAND_PART_ANY(KERNEL)                                                                                             \
+#define CMDA_BAND_PART_ANY(KERNEL, THREADS)                                                                                    \
     do {                                                                                                                       \
-        if (B == 1) { if (vec) CMDA_BAND_PART(KERNEL, false, true); else CMDA_BAND_PART(KERNEL, false, false); }               \
-        else { if (vec) CMDA_BAND_PART(KERNEL, true, true); else CMDA_BAND_PART(KERNEL, true, false); }                        \
+        if (B == 1) { if (vec) CMDA_BAND_PART(KERNEL, THREADS, false, true); else CMDA_BAND_PART(KERNEL, THREADS, false, false); } \
+        else { if (vec) CMDA_BAND_PART(KERNEL, THREADS, true, true); else CMDA_BAND_PART(KERNEL, THREADS, true, false); }      \
     } while (0)
-            if (banded == 2) CMDA_BAND_PART_ANY(band_partition2_kernel);
-            else CMDA_BAND_PART_ANY(band_partition_kernel);
+            if (banded == 2) CMDA_BAND_PART_ANY(band_partition2_kernel, kBand2PartThreads);
+            else CMDA_BAND_PART_ANY(band_partition_kernel, kBandPartThreads);
 #undef CMDA_BAND_PART_ANY
 #undef CMDA_BAND_PART
             CMDA_LAUNCH_CHECK();

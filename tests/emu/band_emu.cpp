@@ -23,7 +23,7 @@ static void run_banded(const uint32_t* t, const uint16_t* x, const uint16_t* y, 
                        unsigned* table, unsigned* rec32, unsigned char* rec8, unsigned short* rec16, void* R,
                        unsigned long long* bins) {
     if (max_chunks > 0)
-        emu_launch(dim3(static_cast<unsigned>(max_chunks), S), dim3(kBandPartThreads), [&] {
+        emu_launch(dim3(static_cast<unsigned>(max_chunks), S), dim3(CUT == 1 ? kBandPartThreads : kBand2PartThreads), [&] {
             if (CUT == 1) band_partition_kernel<HAS_T, VEC>(t, x, y, p, tab, bt, g, H, W, B, table, rec32, rec8, rec16, bins);
             else band_partition2_kernel<HAS_T, VEC>(t, x, y, p, tab, bt, g, H, W, B, table, rec32, rec8, rec16, bins);
         });
