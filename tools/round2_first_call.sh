@@ -5,6 +5,10 @@
 #   2. phase times (partition | accumulate) of BANDED and BANDED2                     (bench.py --mode ...)
 #   3. the windows of a step split across two streams, FACTORED | BANDED              (tools/split_probe.py)
 # Outputs in gpurun_out/round2_first_call.txt.   Use: gpurun --timeout 300 -- tools/round2_first_call.sh
+# Optional, BEFORE the call (here, on the CPU; the .so files travel): kernel-shape variants that the sweep at the end picks up
+#   tools/build_variant.sh b2p512  "-DCMDA_BAND2_PART_THREADS=512 -DCMDA_BAND2_PART_GROUPS=2"   # BANDED2 partition at 64 registers
+#   tools/build_variant.sh acc1024 "-DCMDA_BAND_ACC_THREADS=1024"                               # 64 resident warps in the accumulate pass
+#   tools/build_variant.sh u8      "-DCMDA_BAND_V2_UNROLL=8"                                    # 256-record rounds
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 {
@@ -16,4 +20,5 @@ import json,sys;d=json.load(sys.stdin);print('$m B=$b', round(d['ms_per_step'],3
     done
   done
   echo "== split_probe"; timeout 90 python tools/split_probe.py --bins 5 2>&1 | tail -8; timeout 90 python tools/split_probe.py --bins 5 --second banded2 --splits 4,6,8,10 2>&1 | tail -5
+  if ls cmda_b200/variants/lib_*.so > /dev/null 2>&1; then echo "== variants (banded2)"; MODE=banded2 VBINS="5 1" tools/banded_sweep.sh 2>&1 | grep lib_; fi
 } | tee gpurun_out/round2_first_call.txt
