@@ -91,6 +91,8 @@ def test_product_has_no_oracle_import():
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "cmda_oracle" not in text, f
+                # ... nor through the CPU emulation of tests/emu (a kernel-logic checker, test infrastructure only)
+                assert "emu_launch" not in text and "libcmda_b200_emu" not in text and "build_emu" not in text, f
 
 
 def test_missing_library_fails_loudly(monkeypatch):
