@@ -1267,8 +1267,15 @@ __device__ __forceinline__ void rectify_gather_body(const void* __restrict__ R, 
         block_partials[static_cast<size_t>(s) * gridDim.x + blockIdx.x] = o;
     }
 }
+// B > 1: 80 registers -> 3 CTAs per SM.  -DCMDA_GATHER_MINBLOCKS=4 asks ptxas for 64 (a sweep parameter for
+// tools/build_variant.sh; naming even "1" changes ptxas' budget -- 106 registers -- so the default names nothing)
+#ifdef CMDA_GATHER_MINBLOCKS
+#define CMDA_GATHER_BOUNDS __launch_bounds__(kOutThreads, CMDA_GATHER_MINBLOCKS)
+#else
+#define CMDA_GATHER_BOUNDS __launch_bounds__(kOutThreads)
+#endif
 template <int BT>
-__global__ void __launch_bounds__(kOutThreads)
+__global__ void CMDA_GATHER_BOUNDS
 rectify_gather_kernel(const void* __restrict__ R, const __grid_constant__ WindowTable tab, const __grid_constant__ MapSlots ms,
                       const float2* __restrict__ maps, size_t ncells_padded, int H, int W, int Brt, float* __restrict__ raw,
                       PartialStats* __restrict__ block_partials) {
