@@ -394,3 +394,37 @@ def test_prebuilt_plans_equal_per_call_plans(L):
                                             ptr(clips), 1.0, 1, 1, ptr(out), None, None, ptr(ws), need, mode, ptr(plans), None)
         assert rc == 0, L.cmda_strerror(rc)
         assert np.array_equal(bits(out), bits(base)), mode
+
+
+def test_randomised_geometry_all_stage_a_forms_agree(L):
+    """Seeded random grids (odd sizes, 1-9 bins, widths that leave one row per band), ragged windows with duplicate
+    timestamps, out-of-sensor events and polarity bytes beyond {0, 1} (BANDED2 only: BANDED keeps the DSEC alphabet):
+    FACTORED, BANDED and BANDED2 produce the same raw grids and per-bin counts, bit for bit."""
+    from cmda_b200 import synth
+    rng = np.random.default_rng(20260117)
+    for it in range(10):
+        H = int(rng.integers(3, 70))
+        W = int(rng.choice([int(rng.integers(3, 90)), int(rng.integers(1200, 1700)), 24_000]))
+        if W > 2000:
+            H = int(rng.integers(1, 4))
+        B = int(rng.integers(1, 10))
+        n = int(rng.integers(200, 12_000))
+        t, x, y, p = synth.make_events(n, H, W, seed=int(rng.integers(1 << 30)))
+        t = np.sort((t - t.min()) // int(rng.choice([1, 7, 400]))).astype(np.uint32) + 5        # duplicate timestamps
+        x[rng.random(n) < 0.01] = W + int(rng.integers(0, 3))
+        y[rng.random(n) < 0.01] = H
+        rmap = synth.make_rectify_map(H, W, seed=it)[None]
+        S = int(rng.integers(1, 6))
+        starts = np.sort(rng.integers(0, n, size=S))
+        fins = np.minimum(starts + rng.integers(-1, n, size=S), n - 1)
+        for odd in (False, True):
+            if odd:
+                p = p.copy()
+                p[rng.random(n) < 0.02] = int(rng.integers(2, 256))
+            base, counts = _vg_batch(L, t, x, y, p, starts, fins, rmap, None, H, W, B, FACTORED, normalize=0)
+            for mode in ((BANDED2,) if odd else (BANDED, BANDED2)):
+                got, c2 = _vg_batch(L, t, x, y, p, starts, fins, rmap, None, H, W, B, mode, normalize=0)
+                assert np.array_equal(bits(got), bits(base)) and np.array_equal(c2, counts), (it, H, W, B, mode, odd)
+            for s in range(S):
+                if fins[s] < starts[s]:
+                    assert not base[s].any() and int(counts[s].sum()) == 0
