@@ -134,3 +134,16 @@ def test_banded_kernels_scalar_load_path(emu):
     for variant in (1, 2):
         got, got_bins = stage_a(emu, t, x, y, p, starts, ends, H, W, bins, variant)
         assert np.array_equal(got, red) and np.array_equal(got_bins, red_bins)
+
+
+@pytest.mark.parametrize("bins", [1, 3])
+def test_window_longer_than_one_round_of_run_bounds(emu, bins):
+    """A 4.4 M-event window is 538 chunks: the accumulate pass loads the run bounds of 512 chunks per round (32 lanes x
+    16 warps), so its outer loop takes a second turn."""
+    H, W, n = 24, 40, 4_400_000
+    t, x, y, p = make_events(n, H, W, seed=13, span=2_000_000)
+    starts, ends = [3], [n - 2]
+    red, red_bins = stage_a(emu, t, x, y, p, starts, ends, H, W, bins, 0)
+    for variant in (1, 2):
+        got, got_bins = stage_a(emu, t, x, y, p, starts, ends, H, W, bins, variant)
+        assert np.array_equal(got, red) and np.array_equal(got_bins, red_bins), variant
