@@ -428,3 +428,41 @@ def test_randomised_geometry_all_stage_a_forms_agree(L):
             for s in range(S):
                 if fins[s] < starts[s]:
                     assert not base[s].any() and int(counts[s].sum()) == 0
+
+
+@pytest.mark.parametrize("shape", [(67, 131), (40, 56), (9, 5), (33, 260)])
+def test_pseudo_events_odd_sizes_every_direction(L, shape):
+    """Sizes that leave the 4-pixel vector paths, tiny images, shifts up to the image size, constant and two-level
+    images: both generators bit-exact against the oracle, every direction, batches of several images."""
+    from cmda_b200 import image_change as ic
+    H, W = shape
+    rng = np.random.default_rng(H * 1000 + W)
+    imgs = np.stack([rng.integers(0, 256, size=(H, W), dtype=np.uint8),
+                     np.full((H, W), int(rng.integers(0, 256)), dtype=np.uint8),
+                     (rng.integers(0, 2, size=(H, W)) * 255).astype(np.uint8)])
+    S = imgs.shape[0]
+    for vr, thr_f, clip_f, shift in (((1, 100), 0.04, 0.2, 3), ((0.01, 1.01), 0.005, 0.1, 1), ((1e-5, 255 + 1e-5), 0.0, 0.04, min(H, W))):
+        lut = ic.log_lut_val_range(tuple(float(v) for v in vr))
+        span = np.log(vr[1]) - np.log(vr[0])
+        thr, clip = np.float32(span * thr_f), np.float32(span * clip_f)
+        for name, code in DIRECTIONS.items():
+            out = np.full((S, 1, H, W), np.nan, dtype=np.float32)
+            need = L.cmda_image_workspace_bytes(S, H, W, 1)
+            ws = workspace(need)
+            assert L.cmda_isr_shift_u8(ptr(imgs), 1, S, H, W, shift, code, ptr(lut), float(thr), float(clip), ptr(out), ptr(ws), need,
+                                       None) == 0
+            for s in range(S):
+                want = O.get_image_change_from_pil(imgs[s], W, H, shift_pixel=shift, val_range=vr, _threshold=thr_f,
+                                                   _clip_range=clip_f, shift_direction=name)
+                assert np.array_equal(bits(out[s]), bits(want)), (vr, name, s)
+    front = np.roll(imgs, 1, axis=2)
+    lut = ic.log_lut_log_add(ic.log_add)
+    f32 = np.full((S, H, W), np.nan, dtype=np.float32)
+    u8 = np.zeros((S, H, W), dtype=np.uint8)
+    need = L.cmda_image_workspace_bytes(S, H, W, 1)
+    ws = workspace(need)
+    assert L.cmda_logdiff_pair_u8(ptr(imgs), ptr(front), S, H, W, ptr(lut), float(np.float32(ic.threshold)),
+                                  float(np.float32(ic.clip_range)), ptr(f32), ptr(u8), ptr(ws), need, None) == 0
+    for s in range(S):
+        assert np.array_equal(u8[s], O.get_image_change(imgs[s], front[s]))
+        assert np.array_equal(bits(f32[s]), bits(O.get_image_change(imgs[s], front[s], return_float=True)))
