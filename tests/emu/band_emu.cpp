@@ -103,3 +103,5 @@ extern "C" int emu_stage_a(const uint32_t* t, const uint16_t* x, const uint16_t*
 #undef RUN
     return 0;
 }
+
+char* emu_shared_window = nullptr;      // no kernel of this library uses shared-window addresses

@@ -129,13 +129,29 @@ def build_vg(force: bool = False) -> str:
     return lib
 
 
-FULL_UNITS = ("api.cu", "slicer.cu", "voxel_global.cu", "voxel_factored.cu", "norm.cu", "pseudo_events.cu", "resize.cu")
+def _transform_tiled(src: str) -> str:
+    """voxel_tiled.cu: `atom.shared.add.u32` / predicated `red.shared.add.s32` on 32-bit shared-window addresses ->
+    the same read-modify-writes through emu_shared_window (abi_emu.cpp points it at the kernel's shared array)."""
+    a0 = 'if constexpr (XOFF == 0) asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(q) : "memory");'
+    a1 = 'else asm volatile("atom.shared.add.u32 %0, [%1+4], %2;" : "=r"(old) : "r"(addr), "r"(q) : "memory");'
+    assert a0 in src and a1 in src
+    src = src.replace(a0, "old = atomicAdd(reinterpret_cast<unsigned*>(emu_shared_window + addr + XOFF), static_cast<unsigned>(q));")
+    src = src.replace(a1, "")
+    r0 = src.index("    if constexpr (XOFF == 0)\n        asm volatile(\"{ .reg .pred p;")
+    r1 = src.index("\n}", r0)
+    src = src[:r0] + "    if (d != 0) atomicAdd(reinterpret_cast<int*>(emu_shared_window + haddr + XOFF), d);" + src[r1:]
+    return src
+
+
+FULL_UNITS = ("api.cu", "slicer.cu", "voxel_global.cu", "voxel_tiled.cu", "voxel_factored.cu", "voxel_exact.cu", "norm.cu",
+              "pseudo_events.cu", "resize.cu")
 
 
 def build_abi(force: bool = False) -> str:
-    """tests/emu/_build/libcmda_b200_emu.so: the C ABI of include/cmda_b200.h with every translation unit except
-    the TILED (inline-PTX shared atomics) and EXACT (cub sort) modes compiled against the emulation; those two modes
-    answer CMDA_ERR_UNSUPPORTED (abi_emu.cpp).  "Device" pointers are host pointers."""
+    """tests/emu/_build/libcmda_b200_emu.so: the C ABI of include/cmda_b200.h with every translation unit compiled
+    against the emulation.  Two more mechanical edits make that possible: TILED's two inline-PTX shared-memory atomics
+    become the C++ they abbreviate (shared-window addresses are offsets into the kernel's shared array), and EXACT's
+    cub::DeviceRadixSort::SortPairs resolves to a stable host sort (include/cub/).  "Device" pointers are host pointers."""
     lib = os.path.join(BUILD, "libcmda_b200_emu.so")
     srcs = [os.path.join(CSRC, n) for n in ("common.cuh", "event_math.cuh") + FULL_UNITS] + \
            [os.path.join(HERE, "abi_emu.cpp"), os.path.join(HERE, "include", "cuda_runtime.h"), os.path.abspath(__file__),
@@ -152,6 +168,8 @@ def build_abi(force: bool = False) -> str:
             src = f.read()
         src = re.sub(r"extern __shared__( __align__\(\d+\))?", "extern", src)
         src = transform_launches(src)
+        if name == "voxel_tiled.cu":
+            src = _transform_tiled(src)
         assert "<<<" not in src and "asm" not in src.replace("masm", ""), name
         cpp = os.path.join(gen, name.replace(".cu", ".cpp"))
         with open(cpp, "w") as f:

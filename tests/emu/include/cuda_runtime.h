@@ -306,6 +306,10 @@ inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) {       /
 
 template <typename T>
 inline T __ldg(const T* p) { return *p; }
+// shared-window addresses (cvta.to.shared) are byte offsets from emu_shared_window, which the harness points at the
+// dynamic shared array of the kernels that use them
+extern char* emu_shared_window;
+inline size_t __cvta_generic_to_shared(const void* p) { return static_cast<size_t>(static_cast<const char*>(p) - emu_shared_window); }
 inline unsigned __umulhi(unsigned a, unsigned b) { return static_cast<unsigned>((static_cast<unsigned long long>(a) * b) >> 32); }
 inline int __ffs(unsigned v) { return __builtin_ffs(static_cast<int>(v)); }
 inline float __fmul_rn(float a, float b) { return a * b; }

@@ -59,3 +59,5 @@ extern "C" int emu_events_vg(const uint32_t* t, const uint16_t* x, const uint16_
     std::free(ws);
     return rc;
 }
+
+char* emu_shared_window = nullptr;      // no kernel of this library uses shared-window addresses

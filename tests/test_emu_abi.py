@@ -1,5 +1,4 @@
-"""The C ABI of include/cmda_b200.h on the CPU: every translation unit of libcmda_b200 except the TILED and EXACT voxel
-modes is compiled for the host against the fiber emulation of tests/emu/ ("device" pointers are numpy buffers) and
+"""The C ABI of include/cmda_b200.h on the CPU: every translation unit of libcmda_b200 is compiled for the host against the fiber emulation of tests/emu/ ("device" pointers are numpy buffers) and
 run against the committed golden fixtures -- outputs of the reference's own functions -- and the oracle, with the GPU
 suite's rules: bit-exact integers, indices and pseudo-events; stated tolerances for float voxel sums.  Both cuts of
 the BANDED stage A (modes BANDED and BANDED2) are covered.  This checks the LOGIC of the kernel source and of the
@@ -466,3 +465,40 @@ def test_pseudo_events_odd_sizes_every_direction(L, shape):
     for s in range(S):
         assert np.array_equal(u8[s], O.get_image_change(imgs[s], front[s]))
         assert np.array_equal(bits(f32[s]), bits(O.get_image_change(imgs[s], front[s], return_float=True)))
+
+
+TILED, EXACT = 1, 3
+
+
+@pytest.mark.parametrize("name", sorted(k for k in VG if VG[k]["rectify_map"].ndim == 3))
+def test_events_vg_golden_tiled_and_exact(L, name):
+    """TILED sums the same quantised weights as GLOBAL: the same bits.  EXACT performs the reference's own float32
+    additions in the reference's own order: its raw grid is BIT-IDENTICAL to the oracle's (which reproduces the
+    reference's grid bit for bit, test_voxel_grid_f32_golden) and its normalised grid is within 1e-5 of the fixture."""
+    c = VG[name]
+    W, H, B = int(c["width"]), int(c["height"]), int(c["bins"])
+    start, finish = int(c["start"]), int(c["finish"])
+    clip = float(c["clip"][0]) if c["clip"].size else O.default_clip_range(finish, start)
+    sl = slice(start, finish + 1)
+    g_out, g_raw, g_counts, rmap = events_vg(L, c, GLOBAL, clip)
+    t_out, t_raw, t_counts, _ = events_vg(L, c, TILED, clip)
+    assert np.array_equal(bits(t_raw), bits(g_raw)) and np.array_equal(bits(t_out), bits(g_out)) and np.array_equal(t_counts, g_counts)
+    e_out, e_raw, e_counts, _ = events_vg(L, c, EXACT, clip)
+    tf, xf, yf, pf = O.rectify_events(c["t"][sl], c["x"][sl], c["y"][sl], c["p"][sl], rmap)
+    ref_raw, aux = O.events_to_voxel_grid(tf, xf, yf, pf, W, H, B, return_aux=True)
+    assert np.array_equal(bits(e_raw), bits(ref_raw)), "EXACT must reproduce the reference's raw grid bit for bit"
+    assert np.array_equal(e_counts, aux["bin_counts"])
+    np.testing.assert_allclose(e_out, c["result"], rtol=0, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", sorted(VOXEL))
+def test_voxel_grid_f32_golden_exact_mode(L, name):
+    """events_to_voxel_grid through the EXACT mode against the fixture the reference itself produced: the same bits."""
+    c = VOXEL[name]
+    W, H, B, n = int(c["width"]), int(c["height"]), int(c["bins"]), int(c["time"].shape[0])
+    tm, x, y, pol = (np.ascontiguousarray(c[k], dtype=np.float32) for k in ("time", "x", "y", "pol"))
+    grid = np.full((B, H, W), np.nan, dtype=np.float32)
+    need = L.cmda_events_vg_workspace_bytes(n, 1, H, W, B, EXACT)
+    ws = workspace(need)
+    assert L.cmda_voxel_grid_f32(ptr(tm), ptr(x), ptr(y), ptr(pol), n, W, H, B, ptr(grid), None, ptr(ws), need, EXACT, None) == 0
+    assert np.array_equal(bits(grid), bits(c["grid"]))
