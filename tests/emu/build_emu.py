@@ -5,6 +5,7 @@ edits: `extern __shared__` -> `extern` (the harness defines the arrays), the thr
 common.cuh -> plain loads / stores, and the header include path."""
 import os
 import re
+import shlex
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -13,6 +14,7 @@ CSRC = os.path.join(ROOT, "cmda_b200", "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(BUILD, "libband_emu.so")
 CUT = "// ---- workspace + launch sequence"
+EXTRA = shlex.split(os.environ.get("EMU_EXTRA_FLAGS", ""))      # e.g. -fsanitize=address (tools/emu_asan.sh)
 
 
 def _transform_common(src: str) -> str:
@@ -120,8 +122,8 @@ def build_vg(force: bool = False) -> str:
         return lib
     generate_full()
     gen = os.path.join(BUILD, "gen")
-    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-w",
-           "-I", os.path.join(HERE, "include"), "-I", gen] + \
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-w"] + EXTRA + \
+          ["-I", os.path.join(HERE, "include"), "-I", gen] + \
           ["-o", lib, os.path.join(HERE, "vg_emu.cpp"), os.path.join(gen, "voxel_factored.cpp"), os.path.join(gen, "norm.cpp")]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
@@ -161,8 +163,8 @@ def build_abi(force: bool = False) -> str:
     generate()
     gen = os.path.join(BUILD, "gen")
     objs, procs = [], []
-    flags = ["-std=c++17", "-O1", "-g", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-w", "-I", os.path.join(HERE, "include"),
-             "-I", gen]
+    flags = ["-std=c++17", "-O1", "-g", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-w"] + EXTRA + \
+            ["-I", os.path.join(HERE, "include"), "-I", gen]
     for name in FULL_UNITS:
         with open(os.path.join(CSRC, name)) as f:
             src = f.read()
@@ -193,8 +195,8 @@ def build(force: bool = False) -> str:
     if not force and os.path.isfile(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(s) for s in srcs):
         return LIB
     generate()
-    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-w",
-           "-I", os.path.join(HERE, "include"), "-I", BUILD, "-o", LIB, os.path.join(HERE, "band_emu.cpp")]
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-w"] + EXTRA + \
+          ["-I", os.path.join(HERE, "include"), "-I", BUILD, "-o", LIB, os.path.join(HERE, "band_emu.cpp")]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("emulation build failed:\n" + res.stderr[-6000:])
