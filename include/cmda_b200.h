@@ -251,6 +251,7 @@ int cmda_denorm_rgb_to_gray_u8(const float* d_img, int S, int H, int W, const fl
  * 'RGB' (channels = 3, interleaved) images, bit for bit
  * (/root/reference/mmseg/datasets/cityscapes_ic.py:152-153, 175-176: raw_image / image-change PNG -> 1024 x 512).
  *  d_src [S, H, W, channels] uint8 -> d_dst [S, out_h, out_w, channels] uint8.
+ *  Down-scaling by more than 31x along an axis (more than 64 filter taps) returns CMDA_ERR_UNSUPPORTED.
  * cmda_u8_crop_to_centered_f32 replaces cityscapes_ic.py:177-183, 207-209 on a gray image:
  *   crop(box=(x, y, x + crop_w, y + crop_h)) -> HorizontalFlip -> float32 -> (v / 255.0 - 0.5) / 0.5 -> repeat(3, 1, 1)
  *  d_src [S, H, W] uint8, h_aug [S] crop origin + flip, d_out [S, repeat, crop_h, crop_w] float32. */
