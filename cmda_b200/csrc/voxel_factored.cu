@@ -782,13 +782,15 @@ band_accumulate2_kernel(const unsigned* __restrict__ table, const unsigned* __re
             todo &= todo - 1u;
             const unsigned ra = __shfl_sync(0xffffffffu, a, j), len = __shfl_sync(0xffffffffu, b, j) - ra;
             const size_t off = base_s + static_cast<size_t>(c0 + j * nwarps + wid) * kBandChunk + ra + lane;
-            const unsigned* p32 = rec32 + off;
-            const unsigned char* p8 = rec8 + off;
-            const unsigned short* p16 = rec16 + off;
+            const unsigned* p32 = HAS_T ? rec32 + off : nullptr;               // the format that is not in use has no buffer
+            const unsigned char* p8 = HAS_T ? rec8 + off : nullptr;
+            const unsigned short* p16 = HAS_T ? nullptr : rec16 + off;
             // whole rounds of 32 * U records run without a single predicate; the last, partial round selects
             unsigned done = 0;
-            for (; done + 32u * U <= len; done += 32u * U, p32 += 32 * U, p8 += 32 * U, p16 += 32 * U)
+            for (; done + 32u * U <= len; done += 32u * U) {
                 band_add_round<HAS_T, U, true>(p32, p8, p16, 0u, lane, s_band_acc);
+                if constexpr (HAS_T) { p32 += 32 * U; p8 += 32 * U; } else { p16 += 32 * U; }
+            }
             if (done < len) band_add_round<HAS_T, U, false>(p32, p8, p16, len - done, lane, s_band_acc);
         }
     }
