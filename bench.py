@@ -188,57 +188,91 @@ def ncu_traffic(kernel_key):
 
 
 # ------------------------------------------------------------------------------------ CPU legs
-def cpu_oracle_pass(t, x, y, p, rmap, starts, fins, bins, n_windows, threads):
-    """One pass of the oracle port over `n_windows` windows with `threads` OpenMP threads -> (events, seconds)."""
+def host_cores():
+    """Host threads this process may use.  torchrun exports OMP_NUM_THREADS=1 to its ranks; the CPU legs size
+    their own pools and ignore it."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_port_rate(args, n_windows=WINDOWS_PER_GPU, min_seconds=3.0):
+    """Mevents/s of the oracle PORT (oracle/cmda_oracle.c: the reference's arithmetic in the reference's order, one
+    window per OpenMP thread) on the step's windows: one untimed pass, then whole passes until `min_seconds` of
+    wall time have been measured.  Secondary figure next to the reference's own Python."""
     from oracle import c_oracle
     c_oracle.build()
-    s, f = starts[:n_windows], fins[:n_windows]
-    t0 = time.perf_counter()
-    c_oracle.get_events_vg_batch(t, x, y, p, s, f, rmap, W, H, bins, nthreads=threads)
-    return float((f - s + 1).sum()), time.perf_counter() - t0
+    cores = host_cores()
+    t, x, y, p, rmap, starts, fins = make_workload(n_windows, args.events, seed_base=0)
+
+    def one_pass():
+        t0 = time.perf_counter()
+        c_oracle.get_events_vg_batch(t, x, y, p, starts, fins, rmap, W, H, args.bins, nthreads=cores)
+        return time.perf_counter() - t0
+
+    one_pass()
+    reps, dt = 0, 0.0
+    while reps < 2 or (dt < min_seconds and reps < 12):
+        dt += one_pass()
+        reps += 1
+    ev = float((fins - starts + 1).sum()) * reps
+    return {"value": ev / dt / 1e6, "unit": "Mevents/s", "cores": min(cores, n_windows), "kind": "port",
+            "sample": f"{reps} passes over {n_windows} windows x {args.events} events, one window per OpenMP thread, {dt:.1f} s wall"}
 
 
-def cpu_oracle_rate(t, x, y, p, rmap, starts, fins, bins, n_windows, threads):
-    """Mevents/s of the oracle port: one untimed pass, then passes until a few seconds of wall time have been
-    measured (a single pass is too short to be stable)."""
-    cpu_oracle_pass(t, x, y, p, rmap, starts, fins, bins, n_windows, threads)
-    reps, dt, ev = 0, 0.0, 0.0
-    while reps < 3 or (dt < 3.0 and reps < 12):
-        e, d = cpu_oracle_pass(t, x, y, p, rmap, starts, fins, bins, n_windows, threads)
-        ev += e; dt += d; reps += 1
-    return ev / dt / 1e6, dt, reps
+def reference_event_specs(args, n_windows=WINDOWS_PER_GPU):
+    from cmda_b200 import synth
+    return [dict(kind="events_vg", n=args.events, H=H, W=W, bins=args.bins, seed=synth.seed_for(2, w),
+                 map_seed=synth.seed_for(2, 999), t_base=10_000_000 + w * WINDOW_US, window_us=WINDOW_US)
+            for w in range(n_windows)]
+
+
+def reference_rate(specs, units_per_step, steps, warmup, unit="Mevents/s", what="windows"):
+    """The reference's OWN Python (oracle/_ref, staged by build()) on the host cores: one spawned worker process per
+    core (at most one per work item), like the DataLoader workers the reference runs this path in
+    (builder.py:151-163); a step = every item once.  Returns (cpu_baseline dict, per-step seconds)."""
+    from oracle import ref_runner
+    cores = host_cores()
+    with ref_runner.WorkerPool(specs, cores=cores) as pool:
+        for _ in range(warmup):
+            pool.step()
+        times = [pool.step() for _ in range(steps)]
+        nw = pool.n_workers
+    value = units_per_step * len(times) / sum(times) / 1e6
+    return ({"value": value, "unit": unit, "cores": cores, "kind": "reference",
+             "sample": f"{len(times)} steps x {len(specs)} {what}, the reference's own functions (oracle/_ref) in {nw} worker "
+                       f"processes x {max(1, cores // nw)} torch threads, {sum(times):.1f} s wall"}, times)
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU implementation of the path.  The reference is
-    pure Python (no sources to compile into oracle/_ref) and /root/reference does not travel to
-    the GPU box, so this arm times the oracle port: the C restatement that performs the
-    reference's arithmetic in the reference's order, one window per host thread."""
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores -- the
+    unmodified Python of oracle/_ref (dsec.py:341-366 get_events_vg: slice, t-normalise, rectify_map gather,
+    events_to_voxel_grid, events_norm) when it is staged, else the C port of oracle/ (kind says which).  Same
+    config / metric / unit as the CUDA arm; rank 0 alone runs, the other ranks exit."""
     if rank != 0:
         return
-    from oracle import c_oracle
-    c_oracle.build()
-    cores = max(1, min(os.cpu_count() or 1, c_oracle.max_threads()))
-    n_windows = max(1, min(WINDOWS_PER_GPU, cores))
-    n_events = args.events                 # bounded sample: one window per host thread, at most 16
-    t, x, y, p, rmap, starts, fins = make_workload(n_windows, n_events, seed_base=0)
-    for _ in range(min(args.warmup, 1)):
-        cpu_oracle_pass(t, x, y, p, rmap, starts, fins, args.bins, n_windows, cores)
-    times = []
-    for _ in range(args.steps):
-        times.append(cpu_oracle_pass(t, x, y, p, rmap, starts, fins, args.bins, n_windows, cores)[1])
-    total = float((fins - starts + 1).sum()) * args.steps
-    value = total / sum(times) / 1e6
-    sample = f"{n_windows} windows x {n_events} events per step ({args.steps} steps), one window per thread"
+    from oracle import ref_runner
+    events_per_step = WINDOWS_PER_GPU * args.events
+    extra = {}
+    if ref_runner.available():
+        cpu, times = reference_rate(reference_event_specs(args), events_per_step, args.steps, min(args.warmup, 1))
+        ms = 1e3 * sum(times) / len(times)
+        extra["cpu_port"] = cpu_port_rate(args, min_seconds=2.0)
+    else:
+        cpu = cpu_port_rate(args, min_seconds=max(3.0, 0.5 * args.steps))
+        ms = 1e3 * events_per_step / (cpu["value"] * 1e6)
+    value = cpu["value"]
     line = {
         "impl": "reference", "metric": "voxelized_events_per_s", "value": value, "unit": "Mevents/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * sum(times) / args.steps, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, world),
-        "cpu_baseline": {"value": value, "unit": "Mevents/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": cpu,
         "e2e": {"value": value, "unit": "Mevents/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    line.update(extra)
     print(json.dumps(line), flush=True)
 
 
@@ -597,17 +631,16 @@ def run_gpu(args, rank, local_rank, world):
                         "phase_ms": phases,
                         "whole_step": {"achieved": alg / (ms_per_step * 1e-3) / 1e9,
                                        "frac": alg / (ms_per_step * 1e-3) / 1e9 / peak}}
-        # CPU baseline on a bounded sample of the same workload (rank 0, N=1 only)
-        cpu = None
+        # CPU baseline on a bounded sample of the same workload (rank 0, N=1 only): the reference's own Python
+        # (oracle/_ref) in worker processes, same protocol as `--impl reference`; the C port as a second figure
+        cpu = cpu_port = None
         if world == 1 and not args.no_cpu_baseline:
-            from oracle import c_oracle
-            c_oracle.build()
-            cores = max(1, min(os.cpu_count() or 1, c_oracle.max_threads()))
-            nw = max(1, min(WINDOWS_PER_GPU, cores))
-            rate, dt, reps = cpu_oracle_rate(t, x, y, p, rmap, starts, fins, args.bins, nw, cores)
-            cpu = {"value": rate, "unit": "Mevents/s", "cores": min(cores, nw), "kind": "port",
-                   "sample": f"{reps} passes over {nw} of the step's {WINDOWS_PER_GPU} windows x {args.events} events, one "
-                             f"window per thread, {dt:.1f} s wall"}
+            from oracle import ref_runner
+            cpu_port = cpu_port_rate(args)
+            if ref_runner.available():
+                cpu, _ = reference_rate(reference_event_specs(args), events_per_step, steps=2, warmup=1)
+            else:
+                cpu = cpu_port
         pseudo = c5 = variants = None
         if world == 1 and not args.no_pseudo:
             pseudo = pseudo_events_leg(dev, peak)
@@ -622,8 +655,8 @@ def run_gpu(args, rank, local_rank, world):
             "metric": "voxelized_events_per_s", "value": value, "unit": "Mevents/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(args, world), resolved_mode=_lib.VOXEL_MODE_NAMES[resolved],
-                           rank0_cpu_affinity=affinity),
+            "config": workload_config(args, world),
+            "resolved_mode": _lib.VOXEL_MODE_NAMES[resolved], "rank0_cpu_affinity": affinity,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mevents/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "steps": e2e_steps, "matches_device_path": same},
@@ -631,7 +664,7 @@ def run_gpu(args, rank, local_rank, world):
             "with_prebuilt_map_plans": {"value": world * events_per_step / (planned_ms * 1e-3) / 1e6, "unit": "Mevents/s",
                                         "ms_per_step": planned_ms,
                                         "note": "cmda_rectify_plan_build once per sequence instead of inside every step"},
-            "roofline": roofline, "cpu_baseline": cpu, "pseudo_events": pseudo, "train_step_input_path": c5,
+            "roofline": roofline, "cpu_baseline": cpu, "cpu_port": cpu_port, "pseudo_events": pseudo, "train_step_input_path": c5,
             "variants": variants, "experimental": experimental,
         }
         guard.emit(json.dumps(line))

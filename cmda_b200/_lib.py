@@ -6,6 +6,7 @@ the boundary is a plain address.
 """
 from __future__ import annotations
 
+import collections
 import ctypes
 import os
 import subprocess
@@ -150,18 +151,28 @@ class on_device:
         return False
 
 
-_workspaces: dict = {}
+_WORKSPACE_SLOTS = 8          # scratch buffers kept per process (least recently used beyond that are dropped)
+_workspaces: "collections.OrderedDict" = collections.OrderedDict()
 
 
 def workspace(device: torch.device, nbytes: int) -> torch.Tensor:
-    """A grow-only scratch buffer per (device, stream); the library itself never allocates."""
+    """A scratch buffer per (device, stream); the library itself never allocates.  A buffer is allocated while its
+    stream is torch's current stream, so the caching allocator orders its reuse after the work queued on that
+    stream: dropping a buffer (the cache keeps the `_WORKSPACE_SLOTS` most recently used ones, so short-lived
+    streams do not pin memory for ever) is safe without a synchronisation."""
     key = (device.index if device.index is not None else torch.cuda.current_device(), stream_ptr(device))
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
+        buf = None
+        _workspaces.pop(key, None)           # release the smaller buffer before the larger one is allocated
         buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
         _workspaces[key] = buf
+    _workspaces.move_to_end(key)
+    while len(_workspaces) > _WORKSPACE_SLOTS:
+        _workspaces.popitem(last=False)
     return buf
 
 
 def release_workspaces() -> None:
+    """Drop every cached scratch buffer (pipelines call this on teardown)."""
     _workspaces.clear()

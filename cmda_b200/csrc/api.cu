@@ -54,10 +54,17 @@ static size_t acc_bytes(int S, int H, int W, int B) {
     return align_up(sizeof(long long) * static_cast<size_t>(S) * B * H * W, 256);
 }
 
+// AUTO: FACTORED wherever the sensor-space formulation applies.  Its stage A is the L2 RED kernel, except for
+// B == 1 (the shipped events_bins) on large batches, where the BANDED cut (band partition + shared-memory counting,
+// bit-identical R) is faster: measured on C2 0.39 vs 0.50 ms per 80 M events (profiles/r02_*); below the threshold
+// the banded passes' fixed cost per (window, band) item loses to the 2-6 us the RED kernel needs.
+constexpr long long kAutoBandedMinEvents = 8LL << 20;
 static int resolve_mode(int mode, long long total_events, int S, int H, int W, int B) {
-    (void)total_events; (void)S;
-    if (mode == CMDA_VOXEL_AUTO) return factored_supported(H, W, B) ? CMDA_VOXEL_FACTORED : CMDA_VOXEL_GLOBAL;
-    return mode;
+    (void)S;
+    if (mode != CMDA_VOXEL_AUTO) return mode;
+    if (!factored_supported(H, W, B)) return CMDA_VOXEL_GLOBAL;
+    if (B == 1 && total_events >= kAutoBandedMinEvents && banded_supported(H, W, B)) return CMDA_VOXEL_BANDED;
+    return CMDA_VOXEL_FACTORED;
 }
 
 }  // namespace cmda
@@ -135,10 +142,13 @@ size_t cmda_events_vg_workspace_bytes(int64_t total_events, int S, int H, int W,
     const int group = S < kMaxWindows ? S : kMaxWindows;
     size_t need = stats_bytes(S) + acc_bytes(group, H, W, B);       // both paths sum into the int64 grid
     if (mode == CMDA_VOXEL_TILED && tiled_supported(H, W, B)) need += tiled_workspace_bytes(total_events, S, H, W, B);
-    if ((mode == CMDA_VOXEL_FACTORED || mode == CMDA_VOXEL_AUTO) && factored_supported(H, W, B))
+    // AUTO may resolve to FACTORED or (B == 1) BANDED depending on the batch: sized for either, so that a workspace
+    // sized for a larger batch always serves a smaller one
+    const bool banded = (mode == CMDA_VOXEL_BANDED || mode == CMDA_VOXEL_BANDED2 || (mode == CMDA_VOXEL_AUTO && B == 1)) &&
+                        banded_supported(H, W, B);
+    if ((mode == CMDA_VOXEL_FACTORED || mode == CMDA_VOXEL_AUTO || banded) && factored_supported(H, W, B))
         need += factored_scratch_bytes(group, H, W, B);
-    if ((mode == CMDA_VOXEL_BANDED || mode == CMDA_VOXEL_BANDED2) && banded_supported(H, W, B))
-        need += factored_scratch_bytes(group, H, W, B) + 256 + banded_scratch_bytes(total_events, group, H, W, B);
+    if (banded) need += 256 + banded_scratch_bytes(total_events, group, H, W, B);
     if (mode == CMDA_VOXEL_EXACT) need += exact_workspace_bytes(total_events);    // total_events bounds the largest window
     return need + 256;
 }

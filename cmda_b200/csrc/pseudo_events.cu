@@ -515,8 +515,11 @@ __global__ void rgb_to_gray_kernel(const uint8_t* __restrict__ rgb, long long n,
 // ------------------------------------------------------------------ a9: normalised float image -> 'L' bytes
 // dacs.py:730-733: clamp(denorm(img, mean, std), 0, 1) * 255 -> np.uint8 (truncation) -> PIL 'L'.  denorm is
 // img.mul(std).add(mean) / 255.0 (mmseg/models/utils/dacs_transforms.py:52-53); every step one float32
-// rounding, as torch evaluates it.  d_img is [S, 3, H, W]; the gray plane (and optionally the HWC bytes PIL
+// rounding, as torch evaluates it ON CUDA TENSORS (dacs.py:729): a tensor divided by a Python scalar is computed
+// as a * fl(1 / 255) there (ATen's div kernel, CPU-scalar fast path), not as a true division.  d_img is [S, 3, H, W]; the gray plane (and optionally the HWC bytes PIL
 // would have been handed) come out without the image ever leaving the device.
+// fl(1 / 255) in float32, as torch computes the reciprocal of the scalar divisor
+__device__ constexpr float kInv255 = 1.0f / 255.0f;
 struct Denorm3 {
     float mean[3], std[3];
 };
@@ -534,7 +537,7 @@ denorm_to_gray_kernel(const float* __restrict__ img, long long npx, Denorm3 q, c
         unsigned c8[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            float v = __fdiv_rn(__fadd_rn(__fmul_rn(__ldg(base + c * npx + i), q.std[c]), q.mean[c]), 255.0f);   // denorm
+            float v = __fmul_rn(__fadd_rn(__fmul_rn(__ldg(base + c * npx + i), q.std[c]), q.mean[c]), kInv255);   // denorm
             v = fminf(fmaxf(v, 0.0f), 1.0f);                                                                    // torch.clamp(0, 1)
             c8[c] = static_cast<unsigned>(__float2int_rz(__fmul_rn(v, 255.0f))) & 255u;                           // * 255 -> np.uint8
         }

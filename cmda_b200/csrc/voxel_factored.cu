@@ -30,12 +30,43 @@
 // Each contribution therefore differs by at most 2^-24 relative -- far inside the 1e-5 bar --
 // and for B == 1 (wt = 1) the result is the exact sum of the reference's float32 weights.
 //
-// Capacity of one R cell: |C| < 2^19 and |F| < 2^19 events of net polarity per (pixel, temporal
-// interval, window); a DVS pixel cannot fire that often inside one interval (refractory
-// period), see DESIGN.md.
+// Capacity of one R cell: |C| < 2^19 and |F| < 2^19 in units of |value| = |2 * pol - 1| per (pixel, temporal
+// interval, window); B == 1: a signed 32-bit count.  A DVS pixel cannot fire that often inside one interval
+// (refractory period), but the API accepts any stream, so the capacity is GUARDED, not assumed: stage A keeps a
+// conservative per-window sketch (sum of |value| per hashed pixel class, an upper bound of what any single cell
+// received) or, in the BANDED cuts, the record count of each (window, bin, band) bucket; a window whose bound
+// reaches the capacity -- or that holds something a cut cannot represent (polarity bytes beyond {0, 1} in a
+// one-sign-bit record) -- is FLAGGED, and flagged windows are recomputed by the fallback kernels below with the
+// GLOBAL formulation (reference weights per corner, 2^-30 quanta, 64-bit integer sums: capacity 2^33 per voxel),
+// which stage B then converts instead of gathering.  No host round trip: the fallback kernels are always
+// launched and exit at once for unflagged windows.
 #include "event_math.cuh"
 
 namespace cmda {
+
+// ---- capacity guard ------------------------------------------------------------------------------
+constexpr int kSketch = 256;                                   // hashed pixel classes per window
+constexpr unsigned long long kCellLimit64 = 1ull << 19;        // |C| and |F| / 2^24 of an int64 R cell
+constexpr unsigned long long kCellLimit32 = 1ull << 31;        // B == 1: int32 count
+struct Guard {
+    unsigned long long* sketch;    // [S][kSketch]  sum of |value| per pixel class (RED path)
+    unsigned* flags;               // [S]           non-zero: recompute the window with the fallback
+    unsigned long long limit;
+};
+__host__ __device__ inline size_t guard_bytes_of(int S) {
+    return (static_cast<size_t>(S) * (kSketch * sizeof(unsigned long long) + sizeof(unsigned)) + 255) / 256 * 256;
+}
+__device__ __forceinline__ unsigned sketch_class(unsigned pix) { return (pix * 2654435761u) >> 24; }
+// Block-uniform: does window s need the fallback?  Every thread of the block must call it.  Evaluated by
+// fallback_zero_kernel (the first kernel after stage A), which also folds the sketch verdict into flags[s]; the
+// kernels after it read the flag alone.
+__device__ __forceinline__ bool window_flagged(const Guard& g, int s) {
+    int hit = 0;
+    if (threadIdx.x == 0) hit = g.flags[s] != 0u;
+    for (int k = threadIdx.x; k < kSketch; k += blockDim.x) hit |= g.sketch[static_cast<size_t>(s) * kSketch + k] >= g.limit;
+    return __syncthreads_or(hit) != 0;
+}
+__device__ __forceinline__ bool window_flag_resolved(const Guard& g, int s) { return __ldg(g.flags + s) != 0u; }
 
 #ifndef CMDA_SENS_THREADS
 #define CMDA_SENS_THREADS 256
@@ -111,8 +142,9 @@ template <bool HAS_T, bool VEC>
 __global__ void __launch_bounds__(kSensThreads, CMDA_SENS_MINBLOCKS)
 sensor_accumulate_kernel(const uint32_t* __restrict__ t, const uint16_t* __restrict__ x, const uint16_t* __restrict__ y,
                          const uint8_t* __restrict__ p, WindowTable tab, int H, int W, int B, void* __restrict__ R,
-                         unsigned long long* __restrict__ bin_counts) {
+                         unsigned long long* __restrict__ bin_counts, unsigned long long* __restrict__ sketch) {
     __shared__ unsigned s_bins[32];
+    __shared__ unsigned s_sketch[kSketch];
     const int s = blockIdx.y;
     const WindowDesc wd = tab.w[s];
     const long long g0 = wd.start >> 3, g1 = (wd.end + 7) >> 3;          // groups of 8 events
@@ -123,10 +155,9 @@ sensor_accumulate_kernel(const uint32_t* __restrict__ t, const uint16_t* __restr
     // (single-timestamp window: every t_norm is NaN, every corner is masked)
     if (!(rw.den == 1.0f)) return;
     const bool count_bins = bin_counts != nullptr;
-    if (count_bins) {
-        if (threadIdx.x < 32) s_bins[threadIdx.x] = 0u;
-        __syncthreads();
-    }
+    if (threadIdx.x < 32) s_bins[threadIdx.x] = 0u;
+    for (int k = threadIdx.x; k < kSketch; k += kSensThreads) s_sketch[k] = 0u;
+    __syncthreads();
     const size_t plane = static_cast<size_t>(H) * W;
     unsigned long long* R64 = reinterpret_cast<unsigned long long*>(R) + static_cast<size_t>(s) * B * plane;
     int* R32 = reinterpret_cast<int*>(R) + static_cast<size_t>(s) * plane;
@@ -151,6 +182,8 @@ sensor_accumulate_kernel(const uint32_t* __restrict__ t, const uint16_t* __restr
             const int pol = static_cast<int>(((e < 4 ? cur.p.x : cur.p.y) >> (8 * (e & 3))) & 0xffu);
             const int value = 2 * pol - 1;                                     // dsec.py:45 on the uint8 polarity
             const unsigned pix = ey * static_cast<unsigned>(W) + ex;
+            // capacity guard: what this pixel's class has received (an upper bound for each of its cells)
+            atomicAdd(&s_sketch[sketch_class(pix)], static_cast<unsigned>(pol ? value : 1));
             if constexpr (HAS_T) {
                 const float tn = __fmul_rn(rw.cm1, __fdiv_rn(__uint2float_rn(ts[e] - rw.t_first), rw.fdT));
                 const int tb = trunc_like_x86(tn);                             // dsec.py:43
@@ -169,16 +202,18 @@ sensor_accumulate_kernel(const uint32_t* __restrict__ t, const uint16_t* __restr
         if (CMDA_SENS_PREFETCH) cur = nxt;
         else if (j + 1 < kSensGroupsPerThread && grp < g1) cur = sens_load8<HAS_T, VEC>(t, x, y, p, grp << 3, wd.start, wd.end);
     }
-    if (count_bins) {
-        if (!HAS_T) {
-            local_bins = __reduce_add_sync(0xffffffffu, local_bins);
-            if ((threadIdx.x & 31) == 0 && local_bins) atomicAdd(&s_bins[0], local_bins);
-        }
-        __syncthreads();
-        if (threadIdx.x < B && threadIdx.x < 32) {
-            const unsigned c = s_bins[threadIdx.x];
-            if (c) atomicAdd(bin_counts + static_cast<size_t>(s) * B + threadIdx.x, static_cast<unsigned long long>(c));
-        }
+    if (count_bins && !HAS_T) {
+        local_bins = __reduce_add_sync(0xffffffffu, local_bins);
+        if ((threadIdx.x & 31) == 0 && local_bins) atomicAdd(&s_bins[0], local_bins);
+    }
+    __syncthreads();
+    if (count_bins && threadIdx.x < B && threadIdx.x < 32) {
+        const unsigned c = s_bins[threadIdx.x];
+        if (c) atomicAdd(bin_counts + static_cast<size_t>(s) * B + threadIdx.x, static_cast<unsigned long long>(c));
+    }
+    for (int k = threadIdx.x; k < kSketch; k += kSensThreads) {
+        const unsigned c = s_sketch[k];
+        if (c) atomicAdd(sketch + static_cast<size_t>(s) * kSketch + k, static_cast<unsigned long long>(c));
     }
 }
 
@@ -274,7 +309,7 @@ band_partition_kernel(const uint32_t* __restrict__ t, const uint16_t* __restrict
                       const uint8_t* __restrict__ p, const __grid_constant__ WindowTable tab,
                       const __grid_constant__ BandTable bt, BandGeom g, int H, int W, int B, unsigned* __restrict__ table,
                       unsigned* __restrict__ rec32, unsigned char* __restrict__ rec8, unsigned short* __restrict__ rec16,
-                      unsigned long long* __restrict__ bin_counts) {
+                      unsigned long long* __restrict__ bin_counts, unsigned* __restrict__ flags) {
     extern __shared__ __align__(16) unsigned char s_band_raw[];
     const int NBC = g.nbuckets;                                                 // buckets the table knows
     const int NB = g.nbuckets << g.xsub_log2;                                   // buckets ranked in here
@@ -318,6 +353,12 @@ band_partition_kernel(const uint32_t* __restrict__ t, const uint16_t* __restrict
                                             // | neg << 7   (0xffffffff: dropped)
     unsigned rec[kBandPartGroups][8];       // B > 1: f << 8 | cell low byte;  B == 1: cell | neg << 15
     unsigned local_bins = 0;
+    // a record keeps one sign bit: a window that holds a polarity byte beyond {0, 1} (value = 2 * pol - 1 is then
+    // neither -1 nor +1, dsec.py:45) is flagged and recomputed by the fallback (capacity guard above)
+    unsigned odd = 0u;
+#pragma unroll
+    for (int j = 0; j < kBandPartGroups; ++j) odd |= (ev[j].p.x | ev[j].p.y) & 0xfefefefeu;
+    if (odd != 0u && !dead) flags[s] = 1u;
 #pragma unroll
     for (int j = 0; j < kBandPartGroups; ++j) {
         const unsigned xs[4] = {ev[j].x.x, ev[j].x.y, ev[j].x.z, ev[j].x.w}, ys[4] = {ev[j].y.x, ev[j].y.y, ev[j].y.z, ev[j].y.w};
@@ -443,7 +484,8 @@ template <bool HAS_T>
 __global__ void __launch_bounds__(kBandAccThreads)
 band_accumulate_kernel(const unsigned* __restrict__ table, const unsigned* __restrict__ rec32,
                        const unsigned char* __restrict__ rec8, const unsigned short* __restrict__ rec16,
-                       const __grid_constant__ BandTable bt, BandGeom g, int H, int W, int B, void* __restrict__ R) {
+                       const __grid_constant__ BandTable bt, BandGeom g, int H, int W, int B, void* __restrict__ R,
+                       unsigned* __restrict__ flags) {
     constexpr int kBandUnroll = HAS_T ? CMDA_BAND_UNROLL : CMDA_BAND_UNROLL_B1;
     extern __shared__ __align__(16) unsigned s_band_acc[];      // B > 1: (lo, hi) per cell;  B == 1: count[cells]
     const unsigned cells = static_cast<unsigned>(g.rows) * static_cast<unsigned>(W);
@@ -469,6 +511,7 @@ band_accumulate_kernel(const unsigned* __restrict__ table, const unsigned* __res
     const size_t row_words = static_cast<size_t>(g.nbuckets) + 1;
     const unsigned* tbl = table + static_cast<size_t>(bt.chunk_base[s]) * row_words + bucket;
     const size_t base_s = static_cast<size_t>(bt.rec_base[s]);
+    unsigned long long my_records = 0;      // capacity guard: records of this bucket seen by this lane's chunks
     for (int c0 = 0; c0 < nchunks; c0 += 32 * nwarps) {
         // chunk c belongs to warp c % nwarps: a temporal bin's chunks (contiguous for time-sorted events) spread
         // over all warps; lane l holds the run bounds of the warp's l-th chunk of this round
@@ -478,6 +521,7 @@ band_accumulate_kernel(const unsigned* __restrict__ table, const unsigned* __res
             a = __ldg(tbl + static_cast<size_t>(c) * row_words);
             b = __ldg(tbl + static_cast<size_t>(c) * row_words + 1);
         }
+        if (b > a) my_records += b - a;
         unsigned todo = __ballot_sync(0xffffffffu, b > a);
         while (todo) {
             const int j = __ffs(todo) - 1;
@@ -514,7 +558,15 @@ band_accumulate_kernel(const unsigned* __restrict__ table, const unsigned* __res
             }
         }
     }
-    __syncthreads();
+    // a bucket with fewer records than a cell can hold cannot have overflowed one (records are +-1 events)
+    if (__syncthreads_or(my_records >= (HAS_T ? kCellLimit64 : kCellLimit32) / kBandAccThreads) != 0) {
+        __shared__ unsigned long long s_total;
+        if (threadIdx.x == 0) s_total = 0ull;
+        __syncthreads();
+        if (my_records) atomicAdd(&s_total, my_records);
+        __syncthreads();
+        if (threadIdx.x == 0 && s_total >= (HAS_T ? kCellLimit64 : kCellLimit32)) flags[s] = 1u;
+    }
     // the band of this plane, stored once
     const size_t plane = static_cast<size_t>(H) * W;
     const size_t band_off = static_cast<size_t>(band) * g.rows * W;
@@ -563,7 +615,7 @@ band_partition2_kernel(const uint32_t* __restrict__ t, const uint16_t* __restric
                        const uint8_t* __restrict__ p, const __grid_constant__ WindowTable tab,
                        const __grid_constant__ BandTable bt, BandGeom g, int H, int W, int B, unsigned* __restrict__ table,
                        unsigned* __restrict__ rec32, unsigned char* __restrict__ rec8, unsigned short* __restrict__ rec16,
-                       unsigned long long* __restrict__ bin_counts) {
+                       unsigned long long* __restrict__ bin_counts, unsigned* __restrict__ /*flags: second cut flags in the accumulate pass*/) {
     extern __shared__ __align__(16) unsigned char s_band_raw[];
     const int NB = g.nbuckets;                                                  // real buckets; bucket NB is the trash
     unsigned* s_hist = reinterpret_cast<unsigned*>(s_band_raw);                 // [NB + 1]
@@ -749,7 +801,8 @@ template <bool HAS_T>
 __global__ void __launch_bounds__(kBandAccThreads)
 band_accumulate2_kernel(const unsigned* __restrict__ table, const unsigned* __restrict__ rec32,
                         const unsigned char* __restrict__ rec8, const unsigned short* __restrict__ rec16,
-                        const __grid_constant__ BandTable bt, BandGeom g, int H, int W, int B, void* __restrict__ R) {
+                        const __grid_constant__ BandTable bt, BandGeom g, int H, int W, int B, void* __restrict__ R,
+                        unsigned* __restrict__ flags) {
     constexpr int U = CMDA_BAND_V2_UNROLL;
     extern __shared__ __align__(16) unsigned s_band_acc[];      // B > 1: (lo, hi) per cell;  B == 1: count[cells]
     const unsigned cells = static_cast<unsigned>(g.rows) * static_cast<unsigned>(W);
@@ -769,6 +822,7 @@ band_accumulate2_kernel(const unsigned* __restrict__ table, const unsigned* __re
     const size_t row_words = static_cast<size_t>(g.nbuckets) + 2;      // offsets, record count, odd-polarity flag
     const unsigned* tbl = table + static_cast<size_t>(bt.chunk_base[s]) * row_words + bucket;
     const size_t base_s = static_cast<size_t>(bt.rec_base[s]);
+    unsigned long long my_records = 0;      // capacity guard, as in the first cut
     for (int c0 = 0; c0 < nchunks; c0 += 32 * nwarps) {
         const int c = c0 + lane * nwarps + wid;
         unsigned a = 0u, b = 0u;
@@ -776,6 +830,7 @@ band_accumulate2_kernel(const unsigned* __restrict__ table, const unsigned* __re
             a = __ldg(tbl + static_cast<size_t>(c) * row_words);
             b = __ldg(tbl + static_cast<size_t>(c) * row_words + 1);
         }
+        if (b > a) my_records += b - a;
         unsigned todo = __ballot_sync(0xffffffffu, b > a);
         while (todo) {
             const int j = __ffs(todo) - 1;
@@ -794,7 +849,14 @@ band_accumulate2_kernel(const unsigned* __restrict__ table, const unsigned* __re
             if (done < len) band_add_round<HAS_T, U, false>(p32, p8, p16, len - done, lane, s_band_acc);
         }
     }
-    __syncthreads();
+    if (__syncthreads_or(my_records >= (HAS_T ? kCellLimit64 : kCellLimit32) / kBandAccThreads) != 0) {
+        __shared__ unsigned long long s_total;
+        if (threadIdx.x == 0) s_total = 0ull;
+        __syncthreads();
+        if (my_records) atomicAdd(&s_total, my_records);
+        __syncthreads();
+        if (threadIdx.x == 0 && s_total >= (HAS_T ? kCellLimit64 : kCellLimit32)) flags[s] = 1u;
+    }
     const size_t plane = static_cast<size_t>(H) * W;
     const size_t band_off = static_cast<size_t>(band) * g.rows * W;
     if constexpr (HAS_T) {
@@ -857,6 +919,51 @@ band_fixup_kernel(const uint32_t* __restrict__ t, const uint16_t* __restrict__ x
                 }
             }
         }
+    }
+}
+
+// ---- capacity guard: fallback for flagged windows -----------------------------------------------------
+// The GLOBAL formulation (voxel_global.cu) restricted to the flagged windows of the group: per event the map
+// gather, the reference's float32 corner weights (dsec.py:47-52, bit-identical products) quantised to 2^-30, one
+// 64-bit integer RED per corner into FB[window] = [B][H][W] (the window's own R planes for B > 1, a region of its
+// own for B == 1) -- associative sums, bit-reproducible, capacity 2^33 per voxel.  Always launched; a block of an
+// unflagged window reads the window's 2 KB sketch and exits.
+constexpr int kFallbackThreads = 256;
+__global__ void __launch_bounds__(kFallbackThreads)
+fallback_zero_kernel(Guard guard, long long* __restrict__ FB, size_t V) {
+    const int s = blockIdx.y;
+    const bool flagged = window_flagged(guard, s);
+    if (!flagged) return;
+    if (threadIdx.x == 0) guard.flags[s] = 1u;              // the sketch verdict, for the kernels that follow
+    long long* g = FB + static_cast<size_t>(s) * V;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * kFallbackThreads + threadIdx.x; i < V;
+         i += static_cast<size_t>(gridDim.x) * kFallbackThreads)
+        g[i] = 0;
+}
+__global__ void __launch_bounds__(kFallbackThreads)
+fallback_scatter_kernel(const uint32_t* __restrict__ t, const uint16_t* __restrict__ x, const uint16_t* __restrict__ y,
+                        const uint8_t* __restrict__ p, const __grid_constant__ WindowTable tab, const float2* __restrict__ maps,
+                        int H, int W, int B, Guard guard, long long* __restrict__ FB) {
+    const int s = blockIdx.y;
+    const WindowDesc wd = tab.w[s];
+    const long long n = wd.end - wd.start;
+    if (n <= 0) return;
+    if (!window_flag_resolved(guard, s)) return;
+    const size_t V = static_cast<size_t>(B) * H * W;
+    unsigned long long* g = reinterpret_cast<unsigned long long*>(FB) + static_cast<size_t>(s) * V;
+    const float2* map = maps ? maps + static_cast<size_t>(wd.map_id) * H * W : nullptr;
+    const RawWindowTime rw = raw_window_time(t, wd.start, wd.end, B);
+    for (long long i = static_cast<long long>(blockIdx.x) * kFallbackThreads + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * kFallbackThreads) {
+        const long long gi = wd.start + i;
+        bool ok = true;
+        const Event e = make_raw_event(__ldg(t + gi), __ldg(x + gi), __ldg(y + gi), __ldg(p + gi), map, H, W, rw, ok);
+        const Origin o = origin_of(e, H, W, B);
+        if (!ok || !o.any) continue;
+        for_each_corner(e, o, H, W, B, [&](int xl, int yl, int tl, float w) {
+            const long long q = quantise(w);
+            if (q != 0) atomicAdd(g + (static_cast<size_t>(tl) * H + yl) * W + xl, static_cast<unsigned long long>(q));
+        });
     }
 }
 
@@ -1164,7 +1271,8 @@ constexpr int kStageBytesB1 = kStageBytes / 4;
 template <int BT>
 __device__ __forceinline__ void rectify_gather_body(const void* __restrict__ R, const WindowTable& tab, const MapSlots& ms,
                                                     const float2* __restrict__ maps, size_t ncells_padded, int H, int W, int Brt,
-                                                    float* __restrict__ raw, PartialStats* __restrict__ block_partials) {
+                                                    float* __restrict__ raw, PartialStats* __restrict__ block_partials,
+                                                    const Guard& guard, const long long* __restrict__ FB) {
     extern __shared__ double s_planes[];                     // [box pixels][B]
     constexpr int BA = BT ? BT : 24;
     const int B = BT ? BT : Brt;
@@ -1174,6 +1282,9 @@ __device__ __forceinline__ void rectify_gather_body(const void* __restrict__ R, 
     const int tiles_x = (W + kOutW - 1) / kOutW;
     const int X = (blockIdx.x % tiles_x) * kOutW + (threadIdx.x % kOutW);
     float* out = raw + static_cast<size_t>(s) * B * npx;
+    // capacity guard: a flagged window was recomputed by the fallback kernels into FB (2^-30 fixed point, output space)
+    const bool flagged = window_flag_resolved(guard, static_cast<int>(s));
+    const long long* fb = FB + static_cast<size_t>(s) * B * npx;
 
     int4 box;
     if (identity) {
@@ -1184,7 +1295,8 @@ __device__ __forceinline__ void rectify_gather_body(const void* __restrict__ R, 
         box = __ldg(reinterpret_cast<const int4*>(plan_of(ms, ms.slot[s]) + index_bytes_of(ncells_padded, npx) + stencil_bytes(npx)) +
                     blockIdx.x);
     }
-    const bool staged = box.z > 0 && static_cast<size_t>(box.z) * box.w * B * sizeof(double) <= (BT == 1 ? kStageBytesB1 : kStageBytes);
+    const bool staged = !flagged && box.z > 0 &&
+                        static_cast<size_t>(box.z) * box.w * B * sizeof(double) <= (BT == 1 ? kStageBytesB1 : kStageBytes);
     if (staged) {
         // the cells of the box in row-major order over the threads: consecutive lanes read consecutive cells of a
         // row of R (coalesced row segments) and no lane idles on a short row.  cell / box.z by multiplication:
@@ -1208,7 +1320,9 @@ __device__ __forceinline__ void rectify_gather_body(const void* __restrict__ R, 
         double acc[BA];
 #pragma unroll
         for (int b = 0; b < BA; ++b) acc[b] = 0.0;
-        if (staged) {
+        if (flagged) {
+            // handled below: the value is the converted fixed-point sum
+        } else if (staged) {
             auto accumulate = [&](unsigned cell, float w) {   // cell = index of the source pixel inside the box
                 const double md = static_cast<double>(w);
                 const double* src = s_planes + cell * B;
@@ -1235,7 +1349,9 @@ __device__ __forceinline__ void rectify_gather_body(const void* __restrict__ R, 
 #pragma unroll
         for (int b = 0; b < BA; ++b) {
             if (b < B) {
-                const float v = __double2float_rn(acc[b] * 5.9604644775390625e-08);       // * 2^-24 (exact), one rounding
+                // * 2^-24 (exact), one rounding; flagged: correctly rounded float32 of the exact 2^-30 integer sum
+                const float v = flagged ? __fmul_rn(__ll2float_rn(__ldg(fb + static_cast<size_t>(b) * npx + px)), kFixInv)
+                                        : __double2float_rn(acc[b] * 5.9604644775390625e-08);
                 out[static_cast<unsigned>(b) * npx + px] = v;
                 if (v != 0.0f) {                                   // dsec.py:88
                     st.nnz += 1;
@@ -1280,16 +1396,18 @@ template <int BT>
 __global__ void CMDA_GATHER_BOUNDS
 rectify_gather_kernel(const void* __restrict__ R, const __grid_constant__ WindowTable tab, const __grid_constant__ MapSlots ms,
                       const float2* __restrict__ maps, size_t ncells_padded, int H, int W, int Brt, float* __restrict__ raw,
-                      PartialStats* __restrict__ block_partials) {
-    rectify_gather_body<BT>(R, tab, ms, maps, ncells_padded, H, W, Brt, raw, block_partials);
+                      PartialStats* __restrict__ block_partials, const __grid_constant__ Guard guard,
+                      const long long* __restrict__ FB) {
+    rectify_gather_body<BT>(R, tab, ms, maps, ncells_padded, H, W, Brt, raw, block_partials, guard, FB);
 }
 // B = 1 (the shipped events_bins): 48 registers -> 5 CTAs per SM
 template <>
 __global__ void __launch_bounds__(kOutThreads, 5)
 rectify_gather_kernel<1>(const void* __restrict__ R, const __grid_constant__ WindowTable tab, const __grid_constant__ MapSlots ms,
                          const float2* __restrict__ maps, size_t ncells_padded, int H, int W, int Brt, float* __restrict__ raw,
-                         PartialStats* __restrict__ block_partials) {
-    rectify_gather_body<1>(R, tab, ms, maps, ncells_padded, H, W, Brt, raw, block_partials);
+                         PartialStats* __restrict__ block_partials, const __grid_constant__ Guard guard,
+                         const long long* __restrict__ FB) {
+    rectify_gather_body<1>(R, tab, ms, maps, ncells_padded, H, W, Brt, raw, block_partials, guard, FB);
 }
 
 // [S][nblk] block partials -> the [S][kStatBlocks] partials the normaliser consumes; slot j is the
@@ -1328,10 +1446,13 @@ int factored_max_maps(void) { return kMaxDistinctMaps; }
 size_t factored_plan_bytes(int H, int W) { return factored_supported(H, W, 1) ? plan_bytes_of(H, W) : 0; }
 
 // plans of the distinct maps of one window group (when the caller brings none) + the per-block statistics partials
+// capacity guard (sketch + flags) and, for B == 1, the fallback's int64 grid (B > 1: a flagged window's own R planes)
+static size_t guard_region_bytes(int group, int H, int W, int B) {
+    return guard_bytes_of(group) + (B == 1 ? align_up(sizeof(long long) * static_cast<size_t>(group) * H * W, 256) : 0);
+}
 size_t factored_scratch_bytes(int group, int H, int W, int B) {
-    (void)B;
     const int maps = group < kMaxDistinctMaps ? group : kMaxDistinctMaps;
-    return static_cast<size_t>(maps) * plan_bytes_of(H, W) +
+    return guard_region_bytes(group, H, W, B) + static_cast<size_t>(maps) * plan_bytes_of(H, W) +
            align_up(sizeof(PartialStats) * static_cast<size_t>(group) * gather_blocks(H, W), 256);
 }
 
@@ -1438,6 +1559,17 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
             ms.slot[s] = found;
         }
     }
+    // scratch: [guard: sketch + flags][B == 1: fallback grid][own plans][block partials][BANDED tables + records]
+    Guard guard{};
+    guard.sketch = reinterpret_cast<unsigned long long*>(scratch);
+    guard.flags = reinterpret_cast<unsigned*>(guard.sketch + static_cast<size_t>(S) * kSketch);
+    guard.limit = B == 1 ? kCellLimit32 : kCellLimit64;
+    const size_t guard_bytes = guard_bytes_of(S);
+    const size_t guard_region = guard_region_bytes(S, H, W, B);
+    if (guard_region > scratch_bytes) return CMDA_ERR_WORKSPACE;
+    long long* FB = B == 1 ? reinterpret_cast<long long*>(static_cast<char*>(scratch) + guard_bytes) : static_cast<long long*>(R);
+    scratch = static_cast<char*>(scratch) + guard_region;
+    scratch_bytes -= guard_region;
     ms.plan_stride = plan_bytes_of(H, W);
     ms.plan_base = own_plans ? static_cast<char*>(scratch) : const_cast<char*>(static_cast<const char*>(plans));
     const size_t own_bytes = own_plans ? static_cast<size_t>(n_slots) * ms.plan_stride : 0;
@@ -1445,9 +1577,15 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
     PartialStats* block_partials = reinterpret_cast<PartialStats*>(static_cast<char*>(scratch) + own_bytes);
     const float2* maps2 = reinterpret_cast<const float2*>(maps);
 
-    // zero R (int64 cells for B > 1, int32 counts for B == 1); the BANDED stage A stores every cell instead
+    // zero R (int64 cells for B > 1, int32 counts for B == 1; the BANDED stage A stores every cell instead) and the
+    // guard; one memset when the two are adjacent (B > 1: the guard follows R's last plane)
     const size_t r_bytes = (B == 1) ? sizeof(int) * S * npx : sizeof(long long) * S * B * npx;
-    if (!banded) CMDA_CUDA_TRY(cudaMemsetAsync(R, 0, r_bytes, st));
+    if (!banded && static_cast<char*>(R) + r_bytes == reinterpret_cast<char*>(guard.sketch)) {
+        CMDA_CUDA_TRY(cudaMemsetAsync(R, 0, r_bytes + guard_bytes, st));
+    } else {
+        if (!banded) CMDA_CUDA_TRY(cudaMemsetAsync(R, 0, r_bytes, st));
+        CMDA_CUDA_TRY(cudaMemsetAsync(guard.sketch, 0, guard_bytes, st));
+    }
     phase_mark(st);
     if (own_plans && n_slots) {
         const int rc = build_plans(maps2, ms, n_slots, H, W, st);
@@ -1481,7 +1619,7 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
         CMDA_CUDA_TRY(cudaFuncSetAttribute(KERNEL<HAS_T, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,                    \
                                            static_cast<int>(shm)));                                                            \
         KERNEL<HAS_T, VEC><<<grid, THREADS, shm, st>>>(t, x, y, p, tab, bt, bg, H, W, B, z.table, z.rec32, z.rec8, z.rec16,    \
-                                                       ubins);                                                                 \
+                                                       ubins, guard.flags);                                                    \
     } while (0)
 #define CMDA_BAND_PART_ANY(KERNEL, THREADS)                                                                                    \
     do {                                                                                                                       \
@@ -1503,10 +1641,10 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
     do {                                                                                                                       \
         if (B == 1) {                                                                                                          \
             CMDA_CUDA_TRY(cudaFuncSetAttribute(KERNEL<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shm))); \
-            KERNEL<false><<<items, kBandAccThreads, shm, st>>>(z.table, z.rec32, z.rec8, z.rec16, bt, bg, H, W, B, R);         \
+            KERNEL<false><<<items, kBandAccThreads, shm, st>>>(z.table, z.rec32, z.rec8, z.rec16, bt, bg, H, W, B, R, guard.flags); \
         } else {                                                                                                               \
             CMDA_CUDA_TRY(cudaFuncSetAttribute(KERNEL<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shm))); \
-            KERNEL<true><<<items, kBandAccThreads, shm, st>>>(z.table, z.rec32, z.rec8, z.rec16, bt, bg, H, W, B, R);          \
+            KERNEL<true><<<items, kBandAccThreads, shm, st>>>(z.table, z.rec32, z.rec8, z.rec16, bt, bg, H, W, B, R, guard.flags); \
         }                                                                                                                      \
     } while (0)
             if (banded == 2) CMDA_BAND_ACC(band_accumulate2_kernel);
@@ -1532,12 +1670,20 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
         dim3 grid(static_cast<unsigned>((groups + per - 1) / per), S);
         unsigned long long* ubins = reinterpret_cast<unsigned long long*>(bin_counts);
         if (B == 1) {
-            if (vec) sensor_accumulate_kernel<false, true><<<grid, kSensThreads, 0, st>>>(t, x, y, p, tab, H, W, B, R, ubins);
-            else sensor_accumulate_kernel<false, false><<<grid, kSensThreads, 0, st>>>(t, x, y, p, tab, H, W, B, R, ubins);
+            if (vec) sensor_accumulate_kernel<false, true><<<grid, kSensThreads, 0, st>>>(t, x, y, p, tab, H, W, B, R, ubins, guard.sketch);
+            else sensor_accumulate_kernel<false, false><<<grid, kSensThreads, 0, st>>>(t, x, y, p, tab, H, W, B, R, ubins, guard.sketch);
         } else {
-            if (vec) sensor_accumulate_kernel<true, true><<<grid, kSensThreads, 0, st>>>(t, x, y, p, tab, H, W, B, R, ubins);
-            else sensor_accumulate_kernel<true, false><<<grid, kSensThreads, 0, st>>>(t, x, y, p, tab, H, W, B, R, ubins);
+            if (vec) sensor_accumulate_kernel<true, true><<<grid, kSensThreads, 0, st>>>(t, x, y, p, tab, H, W, B, R, ubins, guard.sketch);
+            else sensor_accumulate_kernel<true, false><<<grid, kSensThreads, 0, st>>>(t, x, y, p, tab, H, W, B, R, ubins, guard.sketch);
         }
+        CMDA_LAUNCH_CHECK();
+    }
+    // capacity guard: recompute the flagged windows (none on DSEC data: both kernels exit at once)
+    if (max_events > 0) {
+        fallback_zero_kernel<<<dim3(16, S), kFallbackThreads, 0, st>>>(guard, FB, static_cast<size_t>(B) * npx);
+        long long gx = (max_events + kFallbackThreads * 8 - 1) / (kFallbackThreads * 8);
+        if (gx > 64) gx = 64;
+        fallback_scatter_kernel<<<dim3(static_cast<unsigned>(gx), S), kFallbackThreads, 0, st>>>(t, x, y, p, tab, maps2, H, W, B, guard, FB);
         CMDA_LAUNCH_CHECK();
     }
     phase_mark(st);
@@ -1547,7 +1693,7 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
     do {                                                                                                                 \
         constexpr int stage = BT == 1 ? kStageBytesB1 : kStageBytes;                                                     \
         CMDA_CUDA_TRY(cudaFuncSetAttribute(rectify_gather_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, stage));     \
-        rectify_gather_kernel<BT><<<grid, kOutThreads, stage, st>>>(R, tab, ms, maps2, nc, H, W, B, raw, block_partials);        \
+        rectify_gather_kernel<BT><<<grid, kOutThreads, stage, st>>>(R, tab, ms, maps2, nc, H, W, B, raw, block_partials, guard, FB); \
     } while (0)
         switch (B) {
             case 1: CMDA_GATHER(1); break;

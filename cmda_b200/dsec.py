@@ -102,7 +102,10 @@ class DSECEvents:
         return (finish - start) / 500000 * 1.5                 # dsec.py:362
 
     def get_events_vg(self, events_finish_index, events_start_index):
-        """``[events_bins, 480, 640]`` float32 in [-1, 1] on the GPU."""
+        """``[events_bins, 480, 640]`` float32 in [-1, 1] on the GPU.  An empty slice raises ``IndexError`` as the
+        reference's ``events_t[0]`` does (dsec.py:347); the batched entry point documents its own convention."""
+        if events_start_index > events_finish_index:
+            raise IndexError("index 0 is out of bounds for axis 0 with size 0")
         clip = self._clip_for(events_finish_index, events_start_index)
         return events_vg_batch(self.store, [events_start_index], [events_finish_index], self.events_bins, [clip],
                                mode=self.mode)[0]
@@ -145,7 +148,14 @@ class DSECEvents:
         """The ``'events_vg'`` entry of ``__getitem__`` for image ``now_image_index``.
         ``crop_xy``/``flip_flag`` are the augmentation draws of dsec.py:206-210 (made by the
         caller so that image, ISR and events share them).  Returns ``None`` where the
-        reference does (start > finish, dsec.py:301-302)."""
+        reference does (start > finish, dsec.py:301-302).
+
+        ``output_num > 1``: the reference's own post-voxel statements only work for one window -- on the 4-D
+        ``[output_num, bins, H, W]`` tensor ``events_vg[:, y:y+ch, x:x+cw]`` (dsec.py:310) slices the BINS and ROW
+        axes and ``F.interpolate(events_vg[None], size=(h, w))`` (dsec.py:314) raises for a 5-D input, and test mode's
+        ``[:, :440, :]`` (dsec.py:317) cuts the bins axis.  This method INTENTIONALLY differs there: crop / flip /
+        resize / ``[:440]`` always act on the last two (spatial) axes of every window, the repeat on the channel
+        axis; for ``output_num == 1`` (the only value the reference's configs use) it is the reference's result."""
         bounds = []
         for i in range(self.output_num):                       # dsec.py:295-302
             b = window_bounds(self.images_to_events_index, now_image_index, self.image_change_range,

@@ -111,7 +111,15 @@ class EventStore:
         self.device = _cuda_device(device)
         def put(a, np_dtype, torch_dtype):
             if isinstance(a, torch.Tensor):
-                assert a.dtype == torch_dtype or a.element_size() == np.dtype(np_dtype).itemsize, "DSEC dtype expected"
+                if a.dtype != torch_dtype:
+                    # a same-size signed view (torch has few unsigned ops) is accepted when no value is negative:
+                    # its bits are then the unsigned value; anything else would be silently reinterpreted
+                    signed = {torch.uint32: torch.int32, torch.uint16: torch.int16}.get(torch_dtype)
+                    if a.dtype != signed:
+                        raise TypeError(f"DSEC dtype {torch_dtype} expected, got {a.dtype}")
+                    if a.numel() and int(a.min()) < 0:
+                        raise ValueError(f"negative values in a {a.dtype} array passed for {torch_dtype}")
+                    a = a.view(torch_dtype)
                 return a.to(self.device, non_blocking=True).contiguous()
             return torch.from_numpy(np.ascontiguousarray(a, dtype=np_dtype)).to(self.device, non_blocking=True)
 
@@ -148,6 +156,31 @@ class EventStore:
         return int(self.t.shape[0])
 
 
+def _check_windows(store, starts, finishes, clip_ranges, map_ids):
+    """Validation shared by the batched entry points: inclusive windows inside the store, per-window clip ranges
+    (``None`` -> the reference's default, dsec.py:362), map ids inside the store's rectify maps (and its plans).
+    The C ABI cannot know how many maps / plans the device arrays hold, so the range check lives here."""
+    starts = np.ascontiguousarray(starts, dtype=np.int64)
+    ends = np.ascontiguousarray(finishes, dtype=np.int64) + 1
+    S = int(starts.shape[0])
+    if ends.shape != starts.shape or starts.ndim != 1:
+        raise ValueError("starts / finishes must be 1-D and of equal length")
+    if S and (starts.min() < 0 or ends.max() > len(store)):
+        raise IndexError("event window outside the store")
+    clips = np.empty(S, dtype=np.float32)
+    for s in range(S):
+        c = None if clip_ranges is None else clip_ranges[s]
+        clips[s] = default_clip_range(int(ends[s]) - 1, int(starts[s])) if c is None else c
+    mids = None if map_ids is None else np.ascontiguousarray(map_ids, dtype=np.int32)
+    if mids is not None:
+        if mids.shape != (S,):
+            raise ValueError("map_ids must hold one id per window")
+        n_maps = 0 if store.rectify_map is None else int(store.rectify_map.shape[0])
+        if S and store.rectify_map is not None and (mids.min() < 0 or mids.max() >= n_maps):
+            raise IndexError("map_id outside the store's rectify maps")
+    return starts, ends, S, clips, mids
+
+
 def events_vg_batch(store: EventStore, starts, finishes, num_bins, clip_ranges=None, *, map_ids=None,
                     normalize=True, final_range=1.0, enforce_no_events_zero=True, mode="auto", out=None,
                     return_raw=False, return_bin_counts=False):
@@ -156,22 +189,16 @@ def events_vg_batch(store: EventStore, starts, finishes, num_bins, clip_ranges=N
 
     ``clip_ranges[s] is None`` (or ``clip_ranges is None``) selects the reference's default
     ``(finish - start) / 500000 * 1.5`` (dsec.py:362).
+
+    An EMPTY window (``finish < start``) is legal in a batch: its raw grid is all zero and ``events_norm`` of an
+    all-zero grid follows (with ``enforce_no_events_zero`` every voxel is the normalised value of 0).  The
+    reference never gets there: ``__getitem__`` returns ``None`` for ``start > finish`` (dsec.py:301-302, mirrored by
+    ``DSECEvents.events_vg_for_image``) and ``get_events_vg`` itself would raise on ``events_t[0]`` (mirrored by
+    ``DSECEvents.get_events_vg``).
     """
     L = _lib.lib()
     dev = store.device
-    starts = np.ascontiguousarray(starts, dtype=np.int64)
-    ends = np.ascontiguousarray(finishes, dtype=np.int64) + 1
-    S = int(starts.shape[0])
-    n_total = len(store)
-    if S and (starts.min() < 0 or ends.max() > n_total):
-        raise IndexError("event window outside the store")
-    clips = np.empty(S, dtype=np.float32)
-    for s in range(S):
-        c = None if clip_ranges is None else clip_ranges[s]
-        clips[s] = default_clip_range(int(ends[s]) - 1, int(starts[s])) if c is None else c
-    mids = None if map_ids is None else np.ascontiguousarray(map_ids, dtype=np.int32)
-    if mids is not None and store.rectify_map is not None and S and mids.max() >= store.rectify_map.shape[0]:
-        raise IndexError("map_id outside the store's rectify maps")
+    starts, ends, S, clips, mids = _check_windows(store, starts, finishes, clip_ranges, map_ids)
     H, W, B = store.height, store.width, int(num_bins)
     mode_id = _lib.VOXEL_MODES[mode]
     if out is None:
@@ -207,16 +234,7 @@ def events_vg_augmented_batch(store: EventStore, starts, finishes, num_bins, cli
     ``crop_size = out_size = (W, 440)``.  Returns ``[S, repeat * Bo, out_h, out_w]`` float32 on the device."""
     L = _lib.lib()
     dev = store.device
-    starts = np.ascontiguousarray(starts, dtype=np.int64)
-    ends = np.ascontiguousarray(finishes, dtype=np.int64) + 1
-    S = int(starts.shape[0])
-    if S and (starts.min() < 0 or ends.max() > len(store)):
-        raise IndexError("event window outside the store")
-    clips = np.empty(S, dtype=np.float32)
-    for s in range(S):
-        c = None if clip_ranges is None else clip_ranges[s]
-        clips[s] = default_clip_range(int(ends[s]) - 1, int(starts[s])) if c is None else c
-    mids = None if map_ids is None else np.ascontiguousarray(map_ids, dtype=np.int32)
+    starts, ends, S, clips, mids = _check_windows(store, starts, finishes, clip_ranges, map_ids)
     H, W, B = store.height, store.width, int(num_bins)
     cw, ch = (int(v) for v in crop_size)
     ow, oh = (int(v) for v in out_size)

@@ -86,6 +86,28 @@ def get_events_vg_batch(t, x, y, p, starts, finishes, rectify_map, width, height
     return (out, raw) if return_raw else out
 
 
+def voxel_aux_batch(t, x, y, p, starts, finishes, rectify_map, width, height, bins, nthreads=0):
+    """Per voxel the sum of |w| (float64) and the number of contributions of each window: the tolerance inputs
+    of the raw-grid comparisons (tests/test_gpu_parity.py), at sizes where numpy takes minutes."""
+    t = np.ascontiguousarray(t, dtype=np.uint32)
+    x = np.ascontiguousarray(x, dtype=np.uint16)
+    y = np.ascontiguousarray(y, dtype=np.uint16)
+    p = np.ascontiguousarray(p, dtype=np.uint8)
+    starts = np.ascontiguousarray(starts, dtype=np.int64)
+    finishes = np.ascontiguousarray(finishes, dtype=np.int64)
+    S = starts.shape[0]
+    rmap = np.ascontiguousarray(rectify_map, dtype=np.float32) if rectify_map is not None else None
+    abs_w = np.empty((S, bins, height, width), np.float64)
+    n_contrib = np.empty((S, bins, height, width), np.int32)
+    i64p = ctypes.POINTER(ctypes.c_int64)
+    lib().oracle_voxel_aux_batch(
+        _p(t, ctypes.POINTER(ctypes.c_uint32)), _p(x, ctypes.POINTER(ctypes.c_uint16)),
+        _p(y, ctypes.POINTER(ctypes.c_uint16)), _p(p, _u8p), _p(starts, i64p), _p(finishes, i64p), S,
+        _p(rmap, _f32p), width, height, bins, _p(abs_w, ctypes.POINTER(ctypes.c_double)),
+        _p(n_contrib, ctypes.POINTER(ctypes.c_int32)), int(nthreads))
+    return abs_w, n_contrib
+
+
 _DIR_MODE = {"rightdown": 0, "rightup": 1, "leftdown": 2, "leftup": 3, "all": 4}
 
 

@@ -161,6 +161,54 @@ int oracle_get_events_vg_batch(const uint32_t* t, const uint16_t* x, const uint1
     return err;
 }
 
+/* Tolerance inputs of the parity tests for the same windows: per voxel the sum of |w| over its contributions
+ * (float64) and their number -- the weights are the float32 products of dsec.py:51-52, the corners those of
+ * dsec.py:47-50.  Test infrastructure for the full-size comparisons (numpy takes minutes at 80 M events). */
+int oracle_voxel_aux_batch(const uint32_t* t, const uint16_t* x, const uint16_t* y, const uint8_t* p,
+                           const int64_t* start, const int64_t* finish, int S, const float* rectify_map,
+                           int W, int H, int B, double* abs_w, int32_t* n_contrib, int nthreads) {
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int s = 0; s < S; ++s) {
+        const int64_t n = finish[s] - start[s] + 1;
+        const size_t gsz = (size_t)B * H * W;
+        double* aw = abs_w + (size_t)s * gsz;
+        int32_t* nc = n_contrib + (size_t)s * gsz;
+        memset(aw, 0, gsz * sizeof(double));
+        memset(nc, 0, gsz * sizeof(int32_t));
+        if (n <= 0) continue;
+        const int64_t o = start[s];
+        const uint32_t t_first = t[o];
+        const float t_last = (float)(uint32_t)(t[o + n - 1] - t_first);
+        const float t01_first = 0.0f / t_last;
+        const float den = t_last / t_last - t01_first;
+        const float cm1 = (float)(B - 1);
+        for (int64_t i = 0; i < n; ++i) {
+            const float t01 = (float)(uint32_t)(t[o + i] - t_first) / t_last;
+            const float tn = (cm1 * (t01 - t01_first)) / den;
+            float xf, yf;
+            if (rectify_map) {
+                const float* m = rectify_map + ((size_t)y[o + i] * W + x[o + i]) * 2;
+                xf = m[0]; yf = m[1];
+            } else { xf = (float)x[o + i]; yf = (float)y[o + i]; }
+            const float value = 2.0f * (float)p[o + i] - 1.0f;
+            for (int pass = 0; pass < 8; ++pass) {
+                const int64_t xl = trunc_i(xf) + ((pass >> 2) & 1), yl = trunc_i(yf) + ((pass >> 1) & 1), tl = trunc_i(tn) + (pass & 1);
+                if (!(xl < W && xl >= 0 && yl < H && yl >= 0 && tl >= 0 && tl < B)) continue;
+                float w = value * (1.0f - fabsf((float)xl - xf));
+                w = w * (1.0f - fabsf((float)yl - yf));
+                w = w * (1.0f - fabsf((float)tl - tn));
+                const int64_t idx = (int64_t)H * W * tl + (int64_t)W * yl + xl;
+                aw[idx] += fabs((double)w);
+                nc[idx] += 1;
+            }
+        }
+    }
+    return 0;
+}
+
 /* utils.py:95-104 == create_cityscapes_image_change.py:22-31 on d[n] (in place). */
 static void dead_zone_split_norm(float* d, int64_t n, float thr, float clip, float* scratch) {
     for (int64_t i = 0; i < n; ++i) {

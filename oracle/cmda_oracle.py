@@ -301,16 +301,23 @@ def pil_gray_L(rgb: np.ndarray) -> np.ndarray:
     return ((19595 * r + 38470 * g + 7471 * b + 32768) >> 16).astype(np.uint8)
 
 
-def mixed_image_to_gray(img, means, stds, return_rgb=False):
+def mixed_image_to_gray(img, means, stds, return_rgb=False, cuda_division=True):
     """dacs.py:730-733 on one normalised float32 image ``[3, H, W]``:
     ``clamp(denorm(img, means, stds), 0, 1) * 255`` -> HWC -> ``np.uint8`` (truncation) ->
     ``Image.fromarray`` -> ``convert('L')`` (the first statement of get_image_change_from_pil,
     utils.py:126).  ``denorm`` is ``img.mul(std).add(mean) / 255.0``
-    (mmseg/models/utils/dacs_transforms.py:52-53); float32, one rounding per operation."""
+    (mmseg/models/utils/dacs_transforms.py:52-53); float32, one rounding per operation.
+
+    The reference evaluates denorm on CUDA tensors (dacs.py:729), where torch divides a tensor by a Python scalar
+    as ``a * fl(1 / 255)`` (ATen div kernel, CPU-scalar fast path, torch 1.7 through 2.x), not as a true division;
+    the two differ by one ulp on some inputs, which the truncation to uint8 turns into a gray level.
+    ``cuda_division=True`` (default) restates the arithmetic the reference actually runs; ``False`` is torch's
+    CPU arithmetic (a true division), used to pin this function against torch + PIL where there is no GPU."""
     img = np.asarray(img, dtype=F32)
     m = np.asarray(means, dtype=F32).reshape(3, 1, 1)
     sd = np.asarray(stds, dtype=F32).reshape(3, 1, 1)
-    v = ((img * sd).astype(F32) + m).astype(F32) / F32(255.0)
+    v = ((img * sd).astype(F32) + m).astype(F32)
+    v = (v * (F32(1.0) / F32(255.0))).astype(F32) if cuda_division else v / F32(255.0)
     v = np.clip(v.astype(F32), F32(0.0), F32(1.0)) * F32(255.0)
     rgb = np.uint8(np.transpose(v.astype(F32), (1, 2, 0)))
     gray = pil_gray_L(rgb)

@@ -188,4 +188,20 @@ def test_reference_arm_line_has_the_contract_keys():
     assert line["impl"] == "reference" and line["metric"] == "voxelized_events_per_s" and line["unit"] == "Mevents/s"
     assert line["value"] > 0 and line["e2e"] == {"value": line["value"], "unit": "Mevents/s", "h2d_bytes_per_step": 0,
                                                  "d2h_bytes_per_step": 0}
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and "workload" in line["config"]
+    # the reference's own Python when oracle/_ref is staged (build() does that where /root/reference exists), else the C port
+    from oracle import ref_runner
+    assert line["cpu_baseline"]["kind"] == ("reference" if ref_runner.available() else "port")
+    assert line["cpu_baseline"]["cores"] >= 1 and "workload" in line["config"]
+    # torchrun exports OMP_NUM_THREADS=1 to its ranks: the arm must not shrink its sample or its thread count with it
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", LOCAL_RANK="0", WORLD_SIZE="2")
+    out2 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                           "--warmup", "0", "--events", "20000"], capture_output=True, text=True, timeout=300, cwd=root, env=env)
+    assert out2.returncode == 0, out2.stderr[-400:]
+    line2 = json.loads(out2.stdout.strip().splitlines()[-1])
+    assert line2["cpu_baseline"]["cores"] == line["cpu_baseline"]["cores"] and "16 windows" in line2["cpu_baseline"]["sample"]
+    assert {k: v for k, v in line2["config"].items() if k != "parallelism"} == \
+           {k: v for k, v in line["config"].items() if k != "parallelism"}
+    env["RANK"] = "1"
+    out3 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                           "--warmup", "0", "--events", "20000"], capture_output=True, text=True, timeout=300, cwd=root, env=env)
+    assert out3.returncode == 0 and out3.stdout.strip() == ""          # the other ranks exit without work

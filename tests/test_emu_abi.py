@@ -502,3 +502,36 @@ def test_voxel_grid_f32_golden_exact_mode(L, name):
     ws = workspace(need)
     assert L.cmda_voxel_grid_f32(ptr(tm), ptr(x), ptr(y), ptr(pol), n, W, H, B, ptr(grid), None, ptr(ws), need, EXACT, None) == 0
     assert np.array_equal(bits(grid), bits(c["grid"]))
+
+
+def test_capacity_guard_routes_overflowing_windows_to_the_fallback(L):
+    """An R cell holds |C| < 2^19 in units of |2 * pol - 1|.  A hot pixel with polarity byte 255 (value 509) reaches
+    that with ~1 100 events per temporal interval: without the guard the sensor-space sums wrap and the grid is wrong.
+    The sketch of the RED path / the flags of the BANDED cut must route such a window to the fallback (the GLOBAL
+    formulation) and leave its neighbours on the fast path: every window within the raw-grid bound of the oracle."""
+    from cmda_b200 import synth
+    H, W, B = 24, 40, 3
+    rng = np.random.default_rng(5)
+    n_hot, n_bg = 2600, 3000
+    t, x, y, p = synth.make_events(n_hot + n_bg, H, W, seed=77)
+    # window 0: a single hot pixel, every polarity byte 255 (1 300 events per interval x 509 > 2^19: a real overflow);
+    # window 1: ordinary DSEC events
+    x[:n_hot], y[:n_hot], p[:n_hot] = 7, 5, 255
+    t[:n_hot] = np.sort(t[:n_hot])
+    t[n_hot:] = np.sort(t[n_hot:])
+    rmap = synth.make_rectify_map(H, W, seed=3)[None]
+    starts, fins = np.array([0, n_hot]), np.array([n_hot - 1, n_hot + n_bg - 1])
+    for mode in (FACTORED, BANDED, AUTO):
+        raw, counts = _vg_batch(L, t, x, y, p, starts, fins, rmap, None, H, W, B, mode, normalize=0)
+        for s in range(2):
+            sl = slice(int(starts[s]), int(fins[s]) + 1)
+            tf, xf, yf, pf = O.rectify_events(t[sl], x[sl], y[sl], p[sl], rmap[0])
+            g, aux = O.events_to_voxel_grid(tf, xf, yf, pf, W, H, B, return_aux=True)
+            tol = 1e-5 * np.maximum(np.abs(g), aux["abs_weight_sum"]) + aux["n_contrib"] * 2.0 ** -31
+            assert np.all(np.abs(raw[s].astype(np.float64) - g.astype(np.float64)) <= tol), (mode, s)
+            assert np.array_equal(counts[s], aux["bin_counts"]), (mode, s)
+    # B == 1 through BANDED: the record keeps one sign bit, so the polarity byte alone flags the window
+    raw1, _ = _vg_batch(L, t, x, y, p, starts, fins, rmap, None, H, W, 1, BANDED, normalize=0)
+    base1, _ = _vg_batch(L, t, x, y, p, starts, fins, rmap, None, H, W, 1, FACTORED, normalize=0)
+    np.testing.assert_allclose(raw1[0], base1[0], rtol=1e-6, atol=1e-3)
+    assert np.array_equal(bits(raw1[1]), bits(base1[1]))

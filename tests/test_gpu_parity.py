@@ -396,9 +396,6 @@ def test_events_vg_banded_identical_to_factored(cm, shape):
     assert np.array_equal(bits(fo), bits(bo))
 
 
-@pytest.mark.xfail(strict=False, reason="BANDED2 (second cut of the BANDED stage A) was written after the last GPU minute of "
-                   "round 1: its logic is verified on the CPU emulation (tests/test_emu_*.py), its first run on hardware "
-                   "is this test")
 def test_events_vg_banded2_identical_to_factored():
     """The second cut must reproduce FACTORED bit for bit like the first, and additionally for polarity bytes beyond
     {0, 1} (value = 2 * p - 1 for whatever p holds, dsec.py:45).  Runs in a process of its own
@@ -515,6 +512,121 @@ def test_events_vg_full_size_properties(cm, bins):
     o = out.cpu().numpy()
     assert np.isfinite(o).all() and o.min() >= -1.0 and o.max() <= 1.0
     assert np.all(o[raw.cpu().numpy() == 0] == 0)
+
+
+# ------------------------------------------------------------------ BASELINE sizes, voxel by voxel against the oracle
+def _expected_bin_counts(t, start, fin, bins):
+    sl = slice(int(start), int(fin) + 1)
+    tn = O.t_norm_of(((t[sl] - t[sl][0]).astype(np.float32) / np.float32(t[sl][-1] - t[sl][0])).astype(np.float32), bins)
+    return np.bincount(np.trunc(tn).astype(np.int64), minlength=bins)
+
+
+def _compare_windows_with_oracle(cm, store, t, x, y, p, rmap, starts, fins, bins, modes, H=480, W=640):
+    """Every window of the batch, every voxel: raw grid inside the stated bound of the reference's float32 grid
+    (C oracle = dsec.py:26-58 in the reference's order), normalised grid <= 1e-5, per-bin counts exact."""
+    ref, ref_raw = C.get_events_vg_batch(t, x, y, p, starts, fins, rmap, W, H, bins, return_raw=True)
+    abs_w, n_contrib = C.voxel_aux_batch(t, x, y, p, starts, fins, rmap, W, H, bins)
+    want_counts = np.stack([_expected_bin_counts(t, a, b, bins) for a, b in zip(starts, fins)])
+    first = None
+    for mode in modes:
+        out, raw, counts = cm.events_vg_batch(store, starts, fins, bins, mode=mode, return_raw=True, return_bin_counts=True)
+        assert np.array_equal(counts.cpu().numpy(), want_counts), mode
+        for s in range(len(starts)):
+            assert_raw_close(raw[s], ref_raw[s], abs_w[s], n_contrib[s])
+            check_normalised(out[s], raw[s], ref[s], ref_raw[s], O.default_clip_range(int(fins[s]), int(starts[s])))
+        if mode in ("auto", "factored", "banded", "banded2"):     # one sensor-space sum, whatever the stage A: same bits
+            if first is None:
+                first = raw.clone()
+            else:
+                assert np.array_equal(bits(raw), bits(first)), mode
+        del out, raw, counts
+
+
+@pytest.mark.parametrize("bins", [5, 1])
+def test_c1_window_every_mode_vs_oracle(cm, bins):
+    """BASELINE C1: one 640 x 480 window of 1 M events, every voxel mode, voxel by voxel against the oracle."""
+    from cmda_b200 import synth
+    H, W, n = 480, 640, 1_000_000
+    t, x, y, p = synth.make_events(n, H, W, seed=synth.seed_for(1, 0))
+    rmap = synth.make_rectify_map(H, W, seed=synth.seed_for(1, 999))
+    store = cm.EventStore(t, x, y, p, rmap, height=H, width=W, device="cuda:0")
+    _compare_windows_with_oracle(cm, store, t, x, y, p, rmap, np.array([0]), np.array([n - 1]), bins,
+                                 ["auto", "factored", "banded", "banded2", "global", "tiled"])
+    # EXACT: the reference's own float32 grid, bit for bit
+    raw = cm.events_vg_batch(store, [0], [n - 1], bins, mode="exact", normalize=False)
+    _, ref_raw = C.get_events_vg_batch(t, x, y, p, [0], [n - 1], rmap, W, H, bins, return_raw=True)
+    assert np.array_equal(bits(raw), bits(ref_raw))
+
+
+@pytest.mark.parametrize("bins", [5, 1])
+def test_c2_full_step_vs_oracle(cm, bins):
+    """BASELINE C2, the bench's own step: 16 windows x 5 M events, every voxel of every window against the oracle
+    for the shipped default (auto) and both BANDED cuts."""
+    import bench
+    S, n = 16, 5_000_000
+    t, x, y, p, rmap, starts, fins = bench.make_workload(S, n, seed_base=0)
+    store = cm.EventStore(t, x, y, p, rmap, height=bench.H, width=bench.W, device="cuda:0")
+    _compare_windows_with_oracle(cm, store, t, x, y, p, rmap, starts, fins, bins, ["auto", "factored", "banded", "banded2"])
+
+
+def test_c2_window_exact_mode_bit_identical_at_5m(cm):
+    """EXACT mode on one 5 M-event window (B = 5): the raw grid is the reference's float32 grid bit for bit."""
+    import bench
+    n = 5_000_000
+    t, x, y, p, rmap, starts, fins = bench.make_workload(1, n, seed_base=3)
+    store = cm.EventStore(t, x, y, p, rmap, height=bench.H, width=bench.W, device="cuda:0", plan=False)
+    raw = cm.events_vg_batch(store, starts, fins, 5, mode="exact", normalize=False)
+    _, ref_raw = C.get_events_vg_batch(t, x, y, p, starts, fins, rmap, bench.W, bench.H, 5, return_raw=True)
+    assert np.array_equal(bits(raw), bits(ref_raw))
+
+
+def test_c4_window_vs_oracle(cm):
+    """BASELINE C4: a dense 20 M-event window (B = 5), voxel by voxel against the oracle."""
+    from cmda_b200 import synth
+    H, W, n = 480, 640, 20_000_000
+    t, x, y, p = synth.make_events(n, H, W, seed=synth.seed_for(4, 0))
+    rmap = synth.make_rectify_map(H, W, seed=synth.seed_for(4, 999))
+    store = cm.EventStore(t, x, y, p, rmap, height=H, width=W, device="cuda:0")
+    _compare_windows_with_oracle(cm, store, t, x, y, p, rmap, np.array([0]), np.array([n - 1]), 5, ["auto", "banded", "banded2"])
+
+
+@pytest.mark.parametrize("bins", [5, 1])
+def test_hot_pixel_window_is_guarded(cm, bins):
+    """Capacity guard: an R cell of the sensor-space sums holds |C| < 2^19 events per (pixel, temporal interval).  A
+    stuck pixel firing 3 M same-polarity events in one window (750 k per interval at B = 5) overflows it; the sketch
+    of the RED path and the record counts of the BANDED cuts must send that window -- and only that window -- to the
+    fallback, and the result must match the oracle like any other window.  Window 1 is ordinary and stays bit-identical
+    to a run without the hot window."""
+    from cmda_b200 import synth
+    H, W, n_hot, n_bg = 480, 640, 3_000_000, 400_000
+    t1, x1, y1, p1 = synth.make_events(n_hot, H, W, seed=synth.seed_for(1, 70))
+    x1[:], y1[:], p1[:] = 123, 45, 1
+    t2, x2, y2, p2 = synth.make_events(n_bg, H, W, seed=synth.seed_for(1, 71), t_base=10_050_000)
+    t, x, y, p = np.concatenate([t1, t2]), np.concatenate([x1, x2]), np.concatenate([y1, y2]), np.concatenate([p1, p2])
+    rmap = synth.make_rectify_map(H, W, seed=8)
+    store = cm.EventStore(t, x, y, p, rmap, height=H, width=W, device="cuda:0")
+    starts, fins = np.array([0, n_hot]), np.array([n_hot - 1, n_hot + n_bg - 1])
+    ref, ref_raw = C.get_events_vg_batch(t, x, y, p, starts, fins, rmap, W, H, bins, return_raw=True)
+    abs_w, n_contrib = C.voxel_aux_batch(t, x, y, p, starts, fins, rmap, W, H, bins)
+    alone = cm.events_vg_batch(store, starts[1:], fins[1:], bins, mode="factored", normalize=False)
+    for mode in ("auto", "factored", "banded", "banded2", "global"):
+        out, raw = cm.events_vg_batch(store, starts, fins, bins, mode=mode, return_raw=True)
+        for s in range(2):
+            assert_raw_close(raw[s], ref_raw[s], abs_w[s], n_contrib[s])
+            np.testing.assert_allclose(out[s].cpu().numpy(), O.events_norm(raw[s].cpu().numpy(), O.default_clip_range(int(fins[s]), int(starts[s])), 1.0, True),
+                                       rtol=0, atol=1e-5)
+        if mode != "global":
+            assert np.array_equal(bits(raw[1]), bits(alone[0])), mode
+
+
+def test_auto_mode_resolution(cm):
+    """AUTO: FACTORED (RED stage A) in general; the BANDED cut for B = 1 on large batches, where it is faster."""
+    from cmda_b200 import _lib
+    L = cm.lib()
+    H, W = 480, 640
+    assert L.cmda_events_vg_resolved_mode(80_000_000, 16, H, W, 5, _lib.VOXEL_AUTO) == _lib.VOXEL_FACTORED
+    assert L.cmda_events_vg_resolved_mode(80_000_000, 16, H, W, 1, _lib.VOXEL_AUTO) == _lib.VOXEL_BANDED
+    assert L.cmda_events_vg_resolved_mode(660_000, 2, H, W, 1, _lib.VOXEL_AUTO) == _lib.VOXEL_FACTORED
 
 
 @pytest.mark.parametrize("seed", list(range(32)))
@@ -858,6 +970,30 @@ def test_mixed_image_isr_on_device(cm):
                                               **parms)
             for c in range(3):
                 assert np.array_equal(bits(got[s, c]), bits(ref[0]))
+
+
+def test_denorm_to_gray_matches_torch_on_cuda(cm):
+    """a9 pinned to what the reference RUNS: dacs.py:730-733 and dacs_transforms.py:52-53 executed by torch on CUDA
+    tensors (where `/ 255.0` is a multiplication by fl(1/255), not a division), then np.uint8 + PIL on the host.
+    Un-jittered pixels sit exactly on gray levels, where the two arithmetics disagree: include them."""
+    from PIL import Image
+    rng = np.random.default_rng(29)
+    means = torch.tensor([123.675, 116.28, 103.53]).view(1, 3, 1, 1).cuda()
+    stds = torch.tensor([58.395, 57.12, 57.375]).view(1, 3, 1, 1).cuda()
+    S, H, W = 2, 64, 96
+    levels = torch.from_numpy(rng.integers(0, 256, size=(S, 3, H, W)).astype(np.float32)).cuda()
+    on_levels = (levels - means) / stds                                   # the loader's normalisation of 8-bit pixels
+    noisy = torch.from_numpy(rng.normal(0.0, 1.4, size=(S, 3, H, W)).astype(np.float32)).cuda()
+    for img in (on_levels, noisy):
+        mixed = torch.clamp(img.mul(stds).add(means) / 255.0, 0, 1) * 255                   # dacs.py:730, on the device
+        gray, rgb = cm.denorm_to_gray(img, means, stds, return_rgb=True)
+        for s in range(S):
+            hwc = np.uint8(np.transpose(mixed[s].cpu().numpy(), (1, 2, 0)))                  # dacs.py:731-733
+            pil = Image.fromarray(hwc)
+            assert np.array_equal(rgb[s].cpu().numpy(), hwc)
+            assert np.array_equal(gray[s].cpu().numpy(), np.asarray(pil.convert('L')))       # utils.py:126
+            g_ref = O.mixed_image_to_gray(img[s].cpu().numpy(), means.cpu().numpy().ravel(), stds.cpu().numpy().ravel())
+            assert np.array_equal(g_ref, np.asarray(pil.convert('L')))                       # the oracle restates the same
 
 
 @pytest.mark.parametrize("shape,out_wh", [((2, 1024, 2048), (1024, 512)), ((2, 256, 512, 3), (256, 128)), ((1, 67, 131), (200, 90)),

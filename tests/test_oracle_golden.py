@@ -136,7 +136,8 @@ def test_mixed_image_to_gray_matches_torch_and_pil():
     mixed = torch.clamp(img.mul(stds).add(means) / 255.0, 0, 1) * 255     # dacs.py:730 + dacs_transforms.py:52-53
     mixed = np.transpose(mixed.cpu().numpy()[0], (1, 2, 0))               # dacs.py:731
     pil = Image.fromarray(np.uint8(mixed))                                # dacs.py:733
-    gray, rgb = O.mixed_image_to_gray(img[0].numpy(), means.numpy().ravel(), stds.numpy().ravel(), return_rgb=True)
+    gray, rgb = O.mixed_image_to_gray(img[0].numpy(), means.numpy().ravel(), stds.numpy().ravel(), return_rgb=True,
+                                      cuda_division=False)   # torch on the CPU divides; on CUDA it multiplies by fl(1/255)
     assert np.array_equal(rgb, np.asarray(pil))
     assert np.array_equal(gray, np.asarray(pil.convert('L')))             # utils.py:126
 
