@@ -56,6 +56,9 @@ SIGNATURES = {
     "cmda_rectify_plan_build": (_int, [_vp, _int, _int, _int, _vp, _vp]),
     "cmda_events_vg_batch_planned": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _vp, _vp, _int, _int, _int, _vp, _f32, _int,
                                             _int, _vp, _vp, _vp, _vp, _sz, _int, _vp, _vp]),
+    "cmda_pack_events_p4": (_int, [_vp, _vp, _vp, _vp, _i64, ctypes.c_uint32, _i64, _vp, _vp, _vp, _vp]),
+    "cmda_events_vg_batch_p4": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _int, _vp, _vp, _int, _int, _int, _vp, _f32, _int,
+                                       _int, _vp, _vp, _vp, _vp, _sz, _int, _vp, _vp]),
     "cmda_voxel_grid_f32": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _int, _int, _vp, _vp, _vp, _sz, _int, _vp]),
     "cmda_events_norm_workspace_bytes": (_sz, [_int]),
     "cmda_events_norm_batch": (_int, [_vp, _int, _i64, _vp, _f32, _int, _vp, _sz, _vp]),

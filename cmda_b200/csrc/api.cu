@@ -1,6 +1,8 @@
 // extern "C" entry points of libcmda_b200.so (see include/cmda_b200.h): argument
 // validation, workspace carving, launch sequencing.  No allocation, no global state, no
 // synchronisation, no CPU fallback.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace cmda {
@@ -36,8 +38,11 @@ size_t factored_scratch_bytes(int group, int H, int W, int B);
 int factored_max_maps(void);
 size_t factored_plan_bytes(int H, int W);
 int launch_plan_build(const float*, int, int, int, void*, cudaStream_t);
-int launch_factored(const uint32_t*, const uint16_t*, const uint16_t*, const uint8_t*, const WindowTable&, int, long long,
-                    const float*, int, int, int, void*, int64_t*, float*, PartialStats*, void*, size_t, const void*, int, cudaStream_t);
+int launch_factored(const uint32_t*, const uint16_t*, const uint16_t*, const uint8_t*, const PackedSrc*, const WindowTable&, int,
+                    long long, const float*, int, int, int, void*, int64_t*, float*, PartialStats*, void*, size_t, const void*, int,
+                    cudaStream_t);
+int launch_pack_p4(const uint32_t*, const uint16_t*, const uint16_t*, const uint8_t*, int64_t, uint32_t, int64_t, uint32_t*, int64_t*,
+                   int32_t*, cudaStream_t);
 int banded_supported(int H, int W, int B);
 size_t banded_scratch_bytes(long long total_events, int group, int H, int W, int B);
 int exact_supported(int H, int W, int B);
@@ -160,16 +165,25 @@ struct AugmentArgs {      // post-voxel augmentation fused into the normaliser (
     const cmda_vg_augment* h_aug;
     int crop_w, crop_h, out_w, out_h, avg_bins, repeat;
 };
+struct PackedArgs {       // the packed (P4) source of cmda_events_vg_batch_p4, or none
+    PackedSrc src;
+    const int64_t* h_ms_to_idx;     // host copy of the table: the window-level bucket search happens here
+    const int64_t* h_win_src;       // [S] store index of each window's first event, or NULL (= h_win_start)
+};
 
 int events_vg_impl(const uint32_t* d_t, const uint16_t* d_x, const uint16_t* d_y, const uint8_t* d_p,
                    const int64_t* h_win_start, const int64_t* h_win_end, int S, const float* d_rectify_map,
                    const int32_t* h_map_id, int H, int W, int B, const float* h_clip, float final_range,
                    int enforce_no_events_zero, int normalize, float* d_out, float* d_raw_out, int64_t* d_bin_counts,
                    void* d_workspace, size_t workspace_bytes, int mode, void* stream, const AugmentArgs* aug,
-                   const void* d_plans) {
+                   const void* d_plans, const PackedArgs* packed = nullptr) {
     if (S < 0 || H <= 0 || W <= 0 || B <= 0) return CMDA_ERR_BAD_ARG;
     if (S == 0) return CMDA_OK;
-    if (!d_t || !d_x || !d_y || !d_p || !h_win_start || !h_win_end || !d_out || !d_workspace) return CMDA_ERR_BAD_ARG;
+    if (!packed && (!d_t || !d_x || !d_y || !d_p)) return CMDA_ERR_BAD_ARG;
+    if (packed && (!packed->src.rec || !packed->src.ms_to_idx || !packed->h_ms_to_idx || packed->src.n_ms < 1 ||
+                   packed->src.n_ms > 0x7ffffff0LL || packed->h_ms_to_idx[0] != 0))
+        return CMDA_ERR_BAD_ARG;
+    if (!h_win_start || !h_win_end || !d_out || !d_workspace) return CMDA_ERR_BAD_ARG;
     if (normalize && !h_clip) return CMDA_ERR_BAD_ARG;
     if (mode < CMDA_VOXEL_GLOBAL || mode > CMDA_VOXEL_BANDED2) return CMDA_ERR_BAD_ARG;
     if (reinterpret_cast<uintptr_t>(d_workspace) & 255) return CMDA_ERR_WORKSPACE;
@@ -196,6 +210,8 @@ int events_vg_impl(const uint32_t* d_t, const uint16_t* d_x, const uint16_t* d_y
     }
     if (workspace_bytes < base_need) return CMDA_ERR_WORKSPACE;
     const int use_mode = resolve_mode(mode, total, S, H, W, B);
+    // the packed source feeds the sensor-space formulation only (FACTORED's RED kernel and the first BANDED cut)
+    if (packed && use_mode != CMDA_VOXEL_FACTORED && use_mode != CMDA_VOXEL_BANDED) return CMDA_ERR_UNSUPPORTED;
     if (use_mode == CMDA_VOXEL_TILED && !tiled_supported(H, W, B)) return CMDA_ERR_UNSUPPORTED;
     if (use_mode == CMDA_VOXEL_FACTORED && !factored_supported(H, W, B)) return CMDA_ERR_UNSUPPORTED;
     if (use_mode == CMDA_VOXEL_EXACT && !exact_supported(H, W, B)) return CMDA_ERR_UNSUPPORTED;
@@ -238,6 +254,16 @@ int events_vg_impl(const uint32_t* d_t, const uint16_t* d_x, const uint16_t* d_y
             tab.w[k].clip = h_clip ? h_clip[s] : 1.0f;
             const long long n = tab.w[k].end - tab.w[k].start;
             if (n > max_events) max_events = n;
+            if (packed && n > 0) {
+                // millisecond buckets of the window's first and last event: largest k with ms_to_idx[k] <= index
+                const long long src = packed->h_win_src ? packed->h_win_src[s] : tab.w[k].start;
+                const int64_t* tb = packed->h_ms_to_idx;
+                const long long n_ms = packed->src.n_ms;
+                if (src < 0 || src + n > tb[n_ms]) return CMDA_ERR_BAD_ARG;
+                tab.w[k].src_shift = src - tab.w[k].start;
+                tab.w[k].ms_lo = static_cast<int>(std::upper_bound(tb, tb + n_ms, static_cast<int64_t>(src)) - tb - 1);
+                tab.w[k].ms_hi = static_cast<int>(std::upper_bound(tb, tb + n_ms, static_cast<int64_t>(src + n - 1)) - tb - 1);
+            }
         }
         float* out_g = d_out + static_cast<size_t>(s0) * V;
         float* raw_g = (normalize && d_raw_out) ? d_raw_out + static_cast<size_t>(s0) * V : out_g;
@@ -265,7 +291,7 @@ int events_vg_impl(const uint32_t* d_t, const uint16_t* d_x, const uint16_t* d_y
         long long* acc = reinterpret_cast<long long*>(scratch);
         if (factored_like) {
             const size_t ab = acc_bytes(sn, H, W, B);
-            rc = launch_factored(d_t, d_x, d_y, d_p, tab, sn, max_events, d_rectify_map, H, W, B, acc, bins_g, raw_g,
+            rc = launch_factored(d_t, d_x, d_y, d_p, packed ? &packed->src : nullptr, tab, sn, max_events, d_rectify_map, H, W, B, acc, bins_g, raw_g,
                                  part_g, scratch + ab, scratch_bytes - ab, d_plans, banded, st);   // marks: memset | plans | accumulate
             if (rc != CMDA_OK) return rc;
             phase_mark(st);
@@ -338,6 +364,27 @@ int cmda_events_vg_batch_planned(const uint32_t* d_t, const uint16_t* d_x, const
     return events_vg_impl(d_t, d_x, d_y, d_p, h_win_start, h_win_end, S, d_rectify_map, h_map_id, H, W, B, h_clip, final_range,
                           enforce_no_events_zero, normalize, d_out, d_raw_out, d_bin_counts, d_workspace, workspace_bytes, mode,
                           stream, nullptr, d_plans);
+}
+
+int cmda_events_vg_batch_p4(const uint32_t* d_rec, const int64_t* d_ms_to_idx, const int64_t* h_ms_to_idx, int64_t n_ms,
+                            const int64_t* h_win_start, const int64_t* h_win_end, const int64_t* h_win_src, int S,
+                            const float* d_rectify_map, const int32_t* h_map_id, int H, int W, int B, const float* h_clip,
+                            float final_range, int enforce_no_events_zero, int normalize, float* d_out, float* d_raw_out,
+                            int64_t* d_bin_counts, void* d_workspace, size_t workspace_bytes, int mode, const void* d_plans,
+                            void* stream) {
+    if (W > 2048 || H > 1024) return CMDA_ERR_UNSUPPORTED;      // 11-bit x, 10-bit y
+    const PackedArgs pa{PackedSrc{d_rec, reinterpret_cast<const long long*>(d_ms_to_idx), n_ms}, h_ms_to_idx, h_win_src};
+    return events_vg_impl(nullptr, nullptr, nullptr, nullptr, h_win_start, h_win_end, S, d_rectify_map, h_map_id, H, W, B, h_clip,
+                          final_range, enforce_no_events_zero, normalize, d_out, d_raw_out, d_bin_counts, d_workspace,
+                          workspace_bytes, mode, stream, nullptr, d_plans, &pa);
+}
+
+int cmda_pack_events_p4(const uint32_t* d_t, const uint16_t* d_x, const uint16_t* d_y, const uint8_t* d_p, int64_t n,
+                        uint32_t t_base_us, int64_t n_ms, uint32_t* d_rec, int64_t* d_ms_to_idx, int32_t* d_status,
+                        void* stream) {
+    if (n < 0 || n_ms < 1) return CMDA_ERR_BAD_ARG;
+    if (!d_ms_to_idx || !d_status || (n > 0 && (!d_t || !d_x || !d_y || !d_p || !d_rec))) return CMDA_ERR_BAD_ARG;
+    return launch_pack_p4(d_t, d_x, d_y, d_p, n, t_base_us, n_ms, d_rec, d_ms_to_idx, d_status, static_cast<cudaStream_t>(stream));
 }
 
 size_t cmda_rectify_plan_bytes(int H, int W) {

@@ -65,6 +65,61 @@ __device__ __forceinline__ Event make_raw_event(uint32_t t, unsigned x, unsigned
     return e;
 }
 
+// ---- packed (P4) event source -----------------------------------------------------------------------
+// One 32-bit record per event: x | y << 11 | p << 21 | sub << 22 with sub = t_us - t_base - 1000 * ms, ms the
+// millisecond bucket of the event, which is not stored: it follows from the event's INDEX through the store's
+// ms_to_idx table (DSEC's own events.h5 carries that table; create_dsec_dataset_txt.py:16-35 uses it the same
+// way).  A CTA works on a run of consecutive events, so it looks its first event's bucket up once and keeps the
+// next bucket boundaries in shared memory; a thread then finds the bucket of an event by comparing its index
+// with at most a few boundaries (one, for any stream denser than a few events per millisecond).
+constexpr int kMsBounds = 32;
+struct MsWindow {
+    long long bound[kMsBounds];   // global index of the first event of bucket ms0 + 1 + j (LLONG_MAX past the table)
+    int ms0;                      // bucket of the run's first event
+};
+constexpr unsigned kP4XMask = 0x7ffu, kP4YMask = 0x3ffu;
+constexpr int kP4YShift = 11, kP4PShift = 21, kP4SubShift = 22;
+
+// largest k in [lo, hi] with ms_to_idx[k] <= idx (lo qualifies by construction)
+__device__ __forceinline__ int ms_search(const long long* __restrict__ ms_to_idx, int lo, int hi, long long idx) {
+    while (lo < hi) {
+        const int mid = lo + (hi - lo + 1) / 2;
+        if (__ldg(ms_to_idx + mid) <= idx) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+// Block-wide: every thread calls it; `first` is the global index of the run's first event (clamped into the window).
+__device__ __forceinline__ void ms_window_init(MsWindow& mw, const PackedSrc& pk, const WindowDesc& wd, long long first) {
+    if (threadIdx.x == 0) mw.ms0 = ms_search(pk.ms_to_idx, wd.ms_lo, wd.ms_hi, first);
+    __syncthreads();
+    for (int j = threadIdx.x; j < kMsBounds; j += blockDim.x) {
+        const long long k = static_cast<long long>(mw.ms0) + 1 + j;
+        mw.bound[j] = k <= pk.n_ms ? __ldg(pk.ms_to_idx + k) : 0x7fffffffffffffffLL;
+    }
+    __syncthreads();
+}
+// bucket of global event index idx >= the run's first event; k is the thread's cursor into mw.bound (monotone)
+__device__ __forceinline__ int ms_advance(const MsWindow& mw, const PackedSrc& pk, const WindowDesc& wd, long long idx, int& k) {
+    while (k < kMsBounds && mw.bound[k] <= idx) ++k;
+    if (k < kMsBounds) return mw.ms0 + k;
+    // a run that spans more than kMsBounds buckets (a stream of a few events per millisecond): search the table
+    return ms_search(pk.ms_to_idx, mw.ms0 + kMsBounds, wd.ms_hi, idx);
+}
+// window-relative microseconds of a record (t_base cancels in every difference the path takes)
+__device__ __forceinline__ uint32_t p4_time(uint32_t rec, int ms) {
+    return static_cast<uint32_t>(ms) * 1000u + (rec >> kP4SubShift);
+}
+__device__ __forceinline__ RawWindowTime raw_window_time_p4(const PackedSrc& pk, const WindowDesc& wd, int B) {
+    RawWindowTime w;
+    w.t_first = p4_time(__ldg(pk.rec + wd.start), wd.ms_lo);
+    w.fdT = __uint2float_rn(p4_time(__ldg(pk.rec + wd.end - 1), wd.ms_hi) - w.t_first);
+    w.t01_first = __fdiv_rn(0.0f, w.fdT);
+    const float t01_last = __fdiv_rn(w.fdT, w.fdT);
+    w.den = __fsub_rn(t01_last, w.t01_first);
+    w.cm1 = static_cast<float>(B - 1);
+    return w;
+}
+
 // Window constants of the float path (events_to_voxel_grid called directly).
 struct F32WindowTime {
     float t_first, den, cm1;

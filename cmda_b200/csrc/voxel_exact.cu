@@ -92,8 +92,9 @@ exact_reduce_kernel(const unsigned* __restrict__ keys, const float* __restrict__
 }
 
 static size_t exact_sort_temp_bound(long long items) {
-    // generous closed-form bound on cub's temporary storage (histograms + per-tile look-back state)
-    return align_up(static_cast<size_t>(64) << 20, 256) + align_up(static_cast<size_t>(items) * 2, 256);
+    // closed-form bound on cub's temporary storage: histograms + per-tile look-back state, and -- SortPairs leaves
+    // its inputs intact, so it ping-pongs through a key and a value array of its own -- 8 bytes per item
+    return align_up(static_cast<size_t>(64) << 20, 256) + align_up(static_cast<size_t>(items) * 8 + 4096, 256);
 }
 
 int exact_supported(int H, int W, int B) {

@@ -32,41 +32,34 @@
 //
 // Capacity of one R cell: |C| < 2^19 and |F| < 2^19 in units of |value| = |2 * pol - 1| per (pixel, temporal
 // interval, window); B == 1: a signed 32-bit count.  A DVS pixel cannot fire that often inside one interval
-// (refractory period), but the API accepts any stream, so the capacity is GUARDED, not assumed: stage A keeps a
-// conservative per-window sketch (sum of |value| per hashed pixel class, an upper bound of what any single cell
-// received) or, in the BANDED cuts, the record count of each (window, bin, band) bucket; a window whose bound
-// reaches the capacity -- or that holds something a cut cannot represent (polarity bytes beyond {0, 1} in a
-// one-sign-bit record) -- is FLAGGED, and flagged windows are recomputed by the fallback kernels below with the
-// GLOBAL formulation (reference weights per corner, 2^-30 quanta, 64-bit integer sums: capacity 2^33 per voxel),
-// which stage B then converts instead of gathering.  No host round trip: the fallback kernels are always
-// launched and exit at once for unflagged windows.
+// (refractory period), but the API accepts any stream, so the capacity is GUARDED, not assumed.  A window whose
+// total |value| mass stays below the capacity needs nothing (the host knows its event count).  For larger windows
+// the RED kernel keeps, per CTA, a shared-memory sketch -- the |value| mass of its 8 192 consecutive events per
+// hashed pixel class, an upper bound of what any single cell received from this CTA -- and flags the window when
+// a class exceeds capacity / (CTAs of the window): if no CTA does, no cell can have received the capacity in
+// total (pigeonhole), whatever the stream looks like.  The BANDED cuts bound a cell by the record count of its
+// (window, bin, band) bucket, and flag a window that holds a polarity byte their one-sign-bit record cannot
+// represent.  Flagged windows are recomputed by the fallback kernels below with the GLOBAL formulation (reference
+// weights per corner, 2^-30 quanta, 64-bit integer sums: capacity 2^33 per voxel), which stage B then converts
+// instead of gathering.  No host round trip: the fallback kernels are always launched and exit at once for
+// unflagged windows.  On uniform streams the sketch stays two orders of magnitude below its threshold up to
+// ~100 M events per window; beyond that, or on a stream that really concentrates on one pixel class, the only
+// cost of a false alarm is the slower fallback.
 #include "event_math.cuh"
 
 namespace cmda {
 
 // ---- capacity guard ------------------------------------------------------------------------------
-constexpr int kSketch = 256;                                   // hashed pixel classes per window
+constexpr int kSketch = 1024;                                  // hashed pixel classes per CTA
 constexpr unsigned long long kCellLimit64 = 1ull << 19;        // |C| and |F| / 2^24 of an int64 R cell
 constexpr unsigned long long kCellLimit32 = 1ull << 31;        // B == 1: int32 count
 struct Guard {
-    unsigned long long* sketch;    // [S][kSketch]  sum of |value| per pixel class (RED path)
-    unsigned* flags;               // [S]           non-zero: recompute the window with the fallback
+    unsigned* flags;               // [S]  non-zero: recompute the window with the fallback
     unsigned long long limit;
 };
-__host__ __device__ inline size_t guard_bytes_of(int S) {
-    return (static_cast<size_t>(S) * (kSketch * sizeof(unsigned long long) + sizeof(unsigned)) + 255) / 256 * 256;
-}
-__device__ __forceinline__ unsigned sketch_class(unsigned pix) { return (pix * 2654435761u) >> 24; }
-// Block-uniform: does window s need the fallback?  Every thread of the block must call it.  Evaluated by
-// fallback_zero_kernel (the first kernel after stage A), which also folds the sketch verdict into flags[s]; the
-// kernels after it read the flag alone.
-__device__ __forceinline__ bool window_flagged(const Guard& g, int s) {
-    int hit = 0;
-    if (threadIdx.x == 0) hit = g.flags[s] != 0u;
-    for (int k = threadIdx.x; k < kSketch; k += blockDim.x) hit |= g.sketch[static_cast<size_t>(s) * kSketch + k] >= g.limit;
-    return __syncthreads_or(hit) != 0;
-}
-__device__ __forceinline__ bool window_flag_resolved(const Guard& g, int s) { return __ldg(g.flags + s) != 0u; }
+__host__ __device__ inline size_t guard_bytes_of(int S) { return (static_cast<size_t>(S) * sizeof(unsigned) + 255) / 256 * 256; }
+__device__ __forceinline__ unsigned sketch_class(unsigned pix) { return (pix * 2654435761u) >> 22; }
+__device__ __forceinline__ bool window_flagged(const Guard& g, int s) { return __ldg(g.flags + s) != 0u; }
 
 #ifndef CMDA_SENS_THREADS
 #define CMDA_SENS_THREADS 256
@@ -138,26 +131,78 @@ __device__ __forceinline__ SensEv8 sens_load8(const uint32_t* __restrict__ t, co
     return r;
 }
 
+// The same 8 events from the packed (P4) source: two 128-bit loads, fields unpacked into the SoA layout above (so
+// that the kernels below have one body); the event's millisecond bucket comes from the CTA's MsWindow (the thread's
+// cursor k only moves forward: its groups are visited in ascending order).  lo / hi / i0 are DEVICE indices.
 template <bool HAS_T, bool VEC>
+__device__ __forceinline__ SensEv8 sens_load8_p4(const PackedSrc& pk, const MsWindow& mw, const WindowDesc& wd, long long i0,
+                                                 long long lo, long long hi, int& k) {
+    unsigned r[8];
+    bool in[8];
+    if (VEC && i0 >= lo && i0 + 8 <= hi) {
+        const uint4 a = ldg_stream_u4(pk.rec + i0), b = ldg_stream_u4(pk.rec + i0 + 4);
+        r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) in[e] = true;
+    } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            in[e] = (i0 + e >= lo) && (i0 + e < hi);
+            r[e] = in[e] ? __ldg(pk.rec + i0 + e) : 0u;
+        }
+    }
+    unsigned ax[8], ay[8], at[8];
+    unsigned long long ap = 0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        ax[e] = in[e] ? (r[e] & kP4XMask) : 0xffffu;                      // 0xffff is outside any sensor: dropped
+        ay[e] = (r[e] >> kP4YShift) & kP4YMask;
+        ap |= static_cast<unsigned long long>((r[e] >> kP4PShift) & 1u) << (8 * e);
+        at[e] = 0u;
+        if (HAS_T && in[e]) at[e] = p4_time(r[e], ms_advance(mw, pk, wd, i0 + e + wd.src_shift, k));
+    }
+    SensEv8 o;
+    o.x = make_uint4(ax[0] | (ax[1] << 16), ax[2] | (ax[3] << 16), ax[4] | (ax[5] << 16), ax[6] | (ax[7] << 16));
+    o.y = make_uint4(ay[0] | (ay[1] << 16), ay[2] | (ay[3] << 16), ay[4] | (ay[5] << 16), ay[6] | (ay[7] << 16));
+    o.t0 = make_uint4(at[0], at[1], at[2], at[3]);
+    o.t1 = make_uint4(at[4], at[5], at[6], at[7]);
+    o.p = make_uint2(static_cast<unsigned>(ap), static_cast<unsigned>(ap >> 32));
+    return o;
+}
+// one loader for both sources
+template <bool HAS_T, bool VEC, bool PK>
+__device__ __forceinline__ SensEv8 sens_load8_any(const uint32_t* __restrict__ t, const uint16_t* __restrict__ x,
+                                                  const uint16_t* __restrict__ y, const uint8_t* __restrict__ p,
+                                                  const PackedSrc& pk, const MsWindow& mw, const WindowDesc& wd, long long i0,
+                                                  int& k) {
+    if constexpr (PK) return sens_load8_p4<HAS_T, VEC>(pk, mw, wd, i0, wd.start, wd.end, k);
+    else return sens_load8<HAS_T, VEC>(t, x, y, p, i0, wd.start, wd.end);
+}
+
+template <bool HAS_T, bool VEC, bool SKETCH, bool PK>
 __global__ void __launch_bounds__(kSensThreads, CMDA_SENS_MINBLOCKS)
 sensor_accumulate_kernel(const uint32_t* __restrict__ t, const uint16_t* __restrict__ x, const uint16_t* __restrict__ y,
-                         const uint8_t* __restrict__ p, WindowTable tab, int H, int W, int B, void* __restrict__ R,
-                         unsigned long long* __restrict__ bin_counts, unsigned long long* __restrict__ sketch) {
+                         const uint8_t* __restrict__ p, const __grid_constant__ PackedSrc pk, const __grid_constant__ WindowTable tab,
+                         int H, int W, int B, void* __restrict__ R, unsigned long long* __restrict__ bin_counts, Guard guard) {
     __shared__ unsigned s_bins[32];
-    __shared__ unsigned s_sketch[kSketch];
+    __shared__ unsigned s_sketch[SKETCH ? kSketch : 1];
+    __shared__ MsWindow s_mw;
     const int s = blockIdx.y;
     const WindowDesc wd = tab.w[s];
     const long long g0 = wd.start >> 3, g1 = (wd.end + 7) >> 3;          // groups of 8 events
     const long long first = g0 + static_cast<long long>(blockIdx.x) * (kSensThreads * kSensGroupsPerThread);
     if (wd.end <= wd.start || first >= g1) return;
-    const RawWindowTime rw = raw_window_time(t, wd.start, wd.end, B);
+    const RawWindowTime rw = PK ? raw_window_time_p4(pk, wd, B) : raw_window_time(t, wd.start, wd.end, B);
     // den is 1 (then t01[0] = 0 and t_norm = (C-1) * (dt / dT): dsec.py:347-348, 38-39) or NaN
     // (single-timestamp window: every t_norm is NaN, every corner is masked)
     if (!(rw.den == 1.0f)) return;
+    if (PK && HAS_T) ms_window_init(s_mw, pk, wd, max(first << 3, wd.start) + wd.src_shift);
+    int ms_cursor = 0;
     const bool count_bins = bin_counts != nullptr;
     if (threadIdx.x < 32) s_bins[threadIdx.x] = 0u;
-    for (int k = threadIdx.x; k < kSketch; k += kSensThreads) s_sketch[k] = 0u;
-    __syncthreads();
+    if (SKETCH)
+        for (int k = threadIdx.x; k < kSketch; k += kSensThreads) s_sketch[k] = 0u;
+    if (SKETCH || count_bins) __syncthreads();
     const size_t plane = static_cast<size_t>(H) * W;
     unsigned long long* R64 = reinterpret_cast<unsigned long long*>(R) + static_cast<size_t>(s) * B * plane;
     int* R32 = reinterpret_cast<int*>(R) + static_cast<size_t>(s) * plane;
@@ -165,13 +210,14 @@ sensor_accumulate_kernel(const uint32_t* __restrict__ t, const uint16_t* __restr
 
     long long grp = first + threadIdx.x;
     SensEv8 cur{};
-    if (grp < g1) cur = sens_load8<HAS_T, VEC>(t, x, y, p, grp << 3, wd.start, wd.end);
+    if (grp < g1) cur = sens_load8_any<HAS_T, VEC, PK>(t, x, y, p, pk, s_mw, wd, grp << 3, ms_cursor);
 #pragma unroll 1
     for (int j = 0; j < kSensGroupsPerThread && grp < g1; ++j) {
         // the next group's loads are in flight while this group's atomics are issued
         const long long nxt_grp = grp + kSensThreads;
         SensEv8 nxt{};
-        if (CMDA_SENS_PREFETCH && j + 1 < kSensGroupsPerThread && nxt_grp < g1) nxt = sens_load8<HAS_T, VEC>(t, x, y, p, nxt_grp << 3, wd.start, wd.end);
+        if (CMDA_SENS_PREFETCH && j + 1 < kSensGroupsPerThread && nxt_grp < g1)
+            nxt = sens_load8_any<HAS_T, VEC, PK>(t, x, y, p, pk, s_mw, wd, nxt_grp << 3, ms_cursor);
         const unsigned xs[4] = {cur.x.x, cur.x.y, cur.x.z, cur.x.w}, ys[4] = {cur.y.x, cur.y.y, cur.y.z, cur.y.w};
         const unsigned ts[8] = {cur.t0.x, cur.t0.y, cur.t0.z, cur.t0.w, cur.t1.x, cur.t1.y, cur.t1.z, cur.t1.w};
 #pragma unroll
@@ -182,8 +228,8 @@ sensor_accumulate_kernel(const uint32_t* __restrict__ t, const uint16_t* __restr
             const int pol = static_cast<int>(((e < 4 ? cur.p.x : cur.p.y) >> (8 * (e & 3))) & 0xffu);
             const int value = 2 * pol - 1;                                     // dsec.py:45 on the uint8 polarity
             const unsigned pix = ey * static_cast<unsigned>(W) + ex;
-            // capacity guard: what this pixel's class has received (an upper bound for each of its cells)
-            atomicAdd(&s_sketch[sketch_class(pix)], static_cast<unsigned>(pol ? value : 1));
+            // capacity guard: what this pixel's class received from this CTA (an upper bound for each of its cells)
+            if (SKETCH) atomicAdd(&s_sketch[sketch_class(pix)], static_cast<unsigned>(pol ? value : 1));
             if constexpr (HAS_T) {
                 const float tn = __fmul_rn(rw.cm1, __fdiv_rn(__uint2float_rn(ts[e] - rw.t_first), rw.fdT));
                 const int tb = trunc_like_x86(tn);                             // dsec.py:43
@@ -200,20 +246,25 @@ sensor_accumulate_kernel(const uint32_t* __restrict__ t, const uint16_t* __restr
         }
         grp = nxt_grp;
         if (CMDA_SENS_PREFETCH) cur = nxt;
-        else if (j + 1 < kSensGroupsPerThread && grp < g1) cur = sens_load8<HAS_T, VEC>(t, x, y, p, grp << 3, wd.start, wd.end);
+        else if (j + 1 < kSensGroupsPerThread && grp < g1) cur = sens_load8_any<HAS_T, VEC, PK>(t, x, y, p, pk, s_mw, wd, grp << 3, ms_cursor);
     }
     if (count_bins && !HAS_T) {
         local_bins = __reduce_add_sync(0xffffffffu, local_bins);
         if ((threadIdx.x & 31) == 0 && local_bins) atomicAdd(&s_bins[0], local_bins);
     }
-    __syncthreads();
+    if (SKETCH || count_bins) __syncthreads();
     if (count_bins && threadIdx.x < B && threadIdx.x < 32) {
         const unsigned c = s_bins[threadIdx.x];
         if (c) atomicAdd(bin_counts + static_cast<size_t>(s) * B + threadIdx.x, static_cast<unsigned long long>(c));
     }
-    for (int k = threadIdx.x; k < kSketch; k += kSensThreads) {
-        const unsigned c = s_sketch[k];
-        if (c) atomicAdd(sketch + static_cast<size_t>(s) * kSketch + k, static_cast<unsigned long long>(c));
+    if (SKETCH) {
+        // pigeonhole: the window's CTAs together cannot give a cell the capacity if none gives a class this much
+        const unsigned long long ncta = static_cast<unsigned long long>((g1 - g0 + kSensThreads * kSensGroupsPerThread - 1) /
+                                                                        (kSensThreads * kSensGroupsPerThread));
+        const unsigned long long tau = guard.limit / ncta;
+        unsigned hit = 0u;
+        for (int k = threadIdx.x; k < kSketch; k += kSensThreads) hit |= s_sketch[k] >= tau;
+        if (hit) guard.flags[s] = 1u;
     }
 }
 
@@ -303,10 +354,10 @@ static bool pick_band_geom(int H, int W, int B, BandGeom& g) {
     return g.nbuckets <= kBandMaxBuckets;
 }
 
-template <bool HAS_T, bool VEC>
+template <bool HAS_T, bool VEC, bool PK>
 __global__ void __launch_bounds__(kBandPartThreads, kBandPartMinBlocks)
 band_partition_kernel(const uint32_t* __restrict__ t, const uint16_t* __restrict__ x, const uint16_t* __restrict__ y,
-                      const uint8_t* __restrict__ p, const __grid_constant__ WindowTable tab,
+                      const uint8_t* __restrict__ p, const __grid_constant__ PackedSrc pk, const __grid_constant__ WindowTable tab,
                       const __grid_constant__ BandTable bt, BandGeom g, int H, int W, int B, unsigned* __restrict__ table,
                       unsigned* __restrict__ rec32, unsigned char* __restrict__ rec8, unsigned short* __restrict__ rec16,
                       unsigned long long* __restrict__ bin_counts, unsigned* __restrict__ flags) {
@@ -328,19 +379,22 @@ band_partition_kernel(const uint32_t* __restrict__ t, const uint16_t* __restrict
     const long long g0 = wd.start >> 3, g1 = (wd.end + 7) >> 3;                 // groups of 8 events
     const long long first = g0 + static_cast<long long>(c) * (kBandPartThreads * kBandPartGroups);
 
+    __shared__ MsWindow s_mw;
+    if (PK && HAS_T) ms_window_init(s_mw, pk, wd, max(first << 3, wd.start) + wd.src_shift);
+    int ms_cursor = 0;
     // every load of the chunk is issued before anything waits on one
     SensEv8 ev[kBandPartGroups];
 #pragma unroll
     for (int j = 0; j < kBandPartGroups; ++j) {
         const long long grp = first + static_cast<long long>(j) * kBandPartThreads + threadIdx.x;
         if (grp < g1) {
-            ev[j] = sens_load8<HAS_T, VEC>(t, x, y, p, grp << 3, wd.start, wd.end);
+            ev[j] = sens_load8_any<HAS_T, VEC, PK>(t, x, y, p, pk, s_mw, wd, grp << 3, ms_cursor);
         } else {
             ev[j].x = make_uint4(~0u, ~0u, ~0u, ~0u);                           // 0xffff is outside any sensor: dropped
             ev[j].y = ev[j].x; ev[j].t0 = make_uint4(0, 0, 0, 0); ev[j].t1 = ev[j].t0; ev[j].p = make_uint2(0u, 0u);
         }
     }
-    const RawWindowTime rw = raw_window_time(t, wd.start, wd.end, B);
+    const RawWindowTime rw = PK ? raw_window_time_p4(pk, wd, B) : raw_window_time(t, wd.start, wd.end, B);
     // den is 1 or NaN (single-timestamp window: every corner is masked, SURVEY.md Q3 -> no records at all)
     const bool dead = !(rw.den == 1.0f);
     const float r_dT = __frcp_rn(rw.fdT);                                       // dead windows never use it
@@ -927,37 +981,43 @@ band_fixup_kernel(const uint32_t* __restrict__ t, const uint16_t* __restrict__ x
 // gather, the reference's float32 corner weights (dsec.py:47-52, bit-identical products) quantised to 2^-30, one
 // 64-bit integer RED per corner into FB[window] = [B][H][W] (the window's own R planes for B > 1, a region of its
 // own for B == 1) -- associative sums, bit-reproducible, capacity 2^33 per voxel.  Always launched; a block of an
-// unflagged window reads the window's 2 KB sketch and exits.
+// unflagged window reads one flag and exits.
 constexpr int kFallbackThreads = 256;
 __global__ void __launch_bounds__(kFallbackThreads)
 fallback_zero_kernel(Guard guard, long long* __restrict__ FB, size_t V) {
     const int s = blockIdx.y;
-    const bool flagged = window_flagged(guard, s);
-    if (!flagged) return;
-    if (threadIdx.x == 0) guard.flags[s] = 1u;              // the sketch verdict, for the kernels that follow
+    if (!window_flagged(guard, s)) return;
     long long* g = FB + static_cast<size_t>(s) * V;
     for (size_t i = static_cast<size_t>(blockIdx.x) * kFallbackThreads + threadIdx.x; i < V;
          i += static_cast<size_t>(gridDim.x) * kFallbackThreads)
         g[i] = 0;
 }
+template <bool PK>
 __global__ void __launch_bounds__(kFallbackThreads)
 fallback_scatter_kernel(const uint32_t* __restrict__ t, const uint16_t* __restrict__ x, const uint16_t* __restrict__ y,
-                        const uint8_t* __restrict__ p, const __grid_constant__ WindowTable tab, const float2* __restrict__ maps,
-                        int H, int W, int B, Guard guard, long long* __restrict__ FB) {
+                        const uint8_t* __restrict__ p, const __grid_constant__ PackedSrc pk, const __grid_constant__ WindowTable tab,
+                        const float2* __restrict__ maps, int H, int W, int B, Guard guard, long long* __restrict__ FB) {
     const int s = blockIdx.y;
     const WindowDesc wd = tab.w[s];
     const long long n = wd.end - wd.start;
     if (n <= 0) return;
-    if (!window_flag_resolved(guard, s)) return;
+    if (!window_flagged(guard, s)) return;
     const size_t V = static_cast<size_t>(B) * H * W;
     unsigned long long* g = reinterpret_cast<unsigned long long*>(FB) + static_cast<size_t>(s) * V;
     const float2* map = maps ? maps + static_cast<size_t>(wd.map_id) * H * W : nullptr;
-    const RawWindowTime rw = raw_window_time(t, wd.start, wd.end, B);
+    const RawWindowTime rw = PK ? raw_window_time_p4(pk, wd, B) : raw_window_time(t, wd.start, wd.end, B);
     for (long long i = static_cast<long long>(blockIdx.x) * kFallbackThreads + threadIdx.x; i < n;
          i += static_cast<long long>(gridDim.x) * kFallbackThreads) {
         const long long gi = wd.start + i;
         bool ok = true;
-        const Event e = make_raw_event(__ldg(t + gi), __ldg(x + gi), __ldg(y + gi), __ldg(p + gi), map, H, W, rw, ok);
+        Event e;
+        if constexpr (PK) {
+            const unsigned r = __ldg(pk.rec + gi);
+            const uint32_t te = p4_time(r, ms_search(pk.ms_to_idx, wd.ms_lo, wd.ms_hi, gi + wd.src_shift));
+            e = make_raw_event(te, r & kP4XMask, (r >> kP4YShift) & kP4YMask, (r >> kP4PShift) & 1u, map, H, W, rw, ok);
+        } else {
+            e = make_raw_event(__ldg(t + gi), __ldg(x + gi), __ldg(y + gi), __ldg(p + gi), map, H, W, rw, ok);
+        }
         const Origin o = origin_of(e, H, W, B);
         if (!ok || !o.any) continue;
         for_each_corner(e, o, H, W, B, [&](int xl, int yl, int tl, float w) {
@@ -1283,7 +1343,7 @@ __device__ __forceinline__ void rectify_gather_body(const void* __restrict__ R, 
     const int X = (blockIdx.x % tiles_x) * kOutW + (threadIdx.x % kOutW);
     float* out = raw + static_cast<size_t>(s) * B * npx;
     // capacity guard: a flagged window was recomputed by the fallback kernels into FB (2^-30 fixed point, output space)
-    const bool flagged = window_flag_resolved(guard, static_cast<int>(s));
+    const bool flagged = window_flagged(guard, static_cast<int>(s));
     const long long* fb = FB + static_cast<size_t>(s) * B * npx;
 
     int4 box;
@@ -1530,11 +1590,15 @@ int launch_plan_build(const float* maps, int n_maps, int H, int W, void* plans, 
     return CMDA_OK;
 }
 
-int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, const uint8_t* p, const WindowTable& tab, int S,
-                    long long max_events, const float* maps, int H, int W, int B, void* R, int64_t* bin_counts,
-                    float* raw, PartialStats* partials, void* scratch, size_t scratch_bytes, const void* plans, int banded,
-                    cudaStream_t st) {
+int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, const uint8_t* p, const PackedSrc* packed,
+                    const WindowTable& tab, int S, long long max_events, const float* maps, int H, int W, int B, void* R,
+                    int64_t* bin_counts, float* raw, PartialStats* partials, void* scratch, size_t scratch_bytes,
+                    const void* plans, int banded, cudaStream_t st) {
     if (!factored_supported(H, W, B)) return CMDA_ERR_UNSUPPORTED;
+    // the source: SoA arrays in DSEC dtypes, or the packed P4 stream (then t / x / y / p are NULL)
+    const bool PKS = packed != nullptr;
+    if (PKS && banded == 2) return CMDA_ERR_UNSUPPORTED;
+    const PackedSrc pk = PKS ? *packed : PackedSrc{nullptr, nullptr, 0};
     BandGeom bg{};
     if (banded && !pick_band_geom(H, W, B, bg)) return CMDA_ERR_UNSUPPORTED;
     const size_t npx = static_cast<size_t>(H) * W;
@@ -1559,10 +1623,9 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
             ms.slot[s] = found;
         }
     }
-    // scratch: [guard: sketch + flags][B == 1: fallback grid][own plans][block partials][BANDED tables + records]
+    // scratch: [guard flags][B == 1: fallback grid][own plans][block partials][BANDED tables + records]
     Guard guard{};
-    guard.sketch = reinterpret_cast<unsigned long long*>(scratch);
-    guard.flags = reinterpret_cast<unsigned*>(guard.sketch + static_cast<size_t>(S) * kSketch);
+    guard.flags = reinterpret_cast<unsigned*>(scratch);
     guard.limit = B == 1 ? kCellLimit32 : kCellLimit64;
     const size_t guard_bytes = guard_bytes_of(S);
     const size_t guard_region = guard_region_bytes(S, H, W, B);
@@ -1580,11 +1643,11 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
     // zero R (int64 cells for B > 1, int32 counts for B == 1; the BANDED stage A stores every cell instead) and the
     // guard; one memset when the two are adjacent (B > 1: the guard follows R's last plane)
     const size_t r_bytes = (B == 1) ? sizeof(int) * S * npx : sizeof(long long) * S * B * npx;
-    if (!banded && static_cast<char*>(R) + r_bytes == reinterpret_cast<char*>(guard.sketch)) {
+    if (!banded && static_cast<char*>(R) + r_bytes == reinterpret_cast<char*>(guard.flags)) {
         CMDA_CUDA_TRY(cudaMemsetAsync(R, 0, r_bytes + guard_bytes, st));
     } else {
         if (!banded) CMDA_CUDA_TRY(cudaMemsetAsync(R, 0, r_bytes, st));
-        CMDA_CUDA_TRY(cudaMemsetAsync(guard.sketch, 0, guard_bytes, st));
+        CMDA_CUDA_TRY(cudaMemsetAsync(guard.flags, 0, guard_bytes, st));
     }
     phase_mark(st);
     if (own_plans && n_slots) {
@@ -1607,29 +1670,39 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
         const size_t used = align_up(own_bytes + sizeof(PartialStats) * static_cast<size_t>(S) * nblk, 256);
         const BandScratch z = band_carve(static_cast<char*>(scratch) + used, chunks, bg, B);
         if (used + z.total_bytes > scratch_bytes) return CMDA_ERR_WORKSPACE;
-        const bool vec = ((reinterpret_cast<uintptr_t>(t) & 15) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
-                         ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && ((reinterpret_cast<uintptr_t>(p) & 7) == 0);
+        const bool vec = PKS ? (reinterpret_cast<uintptr_t>(pk.rec) & 15) == 0
+                             : ((reinterpret_cast<uintptr_t>(t) & 15) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
+                               ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && ((reinterpret_cast<uintptr_t>(p) & 7) == 0);
         unsigned long long* ubins = reinterpret_cast<unsigned long long*>(bin_counts);
         if (max_chunks > 0) {
             const int fine = banded == 2 ? bg.nbuckets + 1 : (bg.nbuckets << bg.xsub_log2);
             const size_t shm = sizeof(unsigned) * (fine + ((fine + 1 + 3) & ~3)) + (B > 1 ? 5u : 2u) * static_cast<size_t>(kBandChunk);
             dim3 grid(static_cast<unsigned>(max_chunks), S);
-#define CMDA_BAND_PART(KERNEL, THREADS, HAS_T, VEC)                                                                            \
+#define CMDA_BAND_PART1(HAS_T, VEC, PK)                                                                                        \
     do {                                                                                                                       \
-        CMDA_CUDA_TRY(cudaFuncSetAttribute(KERNEL<HAS_T, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,                    \
+        CMDA_CUDA_TRY(cudaFuncSetAttribute(band_partition_kernel<HAS_T, VEC, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                            static_cast<int>(shm)));                                                            \
-        KERNEL<HAS_T, VEC><<<grid, THREADS, shm, st>>>(t, x, y, p, tab, bt, bg, H, W, B, z.table, z.rec32, z.rec8, z.rec16,    \
-                                                       ubins, guard.flags);                                                    \
+        band_partition_kernel<HAS_T, VEC, PK><<<grid, kBandPartThreads, shm, st>>>(t, x, y, p, pk, tab, bt, bg, H, W, B, z.table, \
+                                                                                   z.rec32, z.rec8, z.rec16, ubins, guard.flags); \
     } while (0)
-#define CMDA_BAND_PART_ANY(KERNEL, THREADS)                                                                                    \
+#define CMDA_BAND_PART2(HAS_T, VEC)                                                                                            \
     do {                                                                                                                       \
-        if (B == 1) { if (vec) CMDA_BAND_PART(KERNEL, THREADS, false, true); else CMDA_BAND_PART(KERNEL, THREADS, false, false); } \
-        else { if (vec) CMDA_BAND_PART(KERNEL, THREADS, true, true); else CMDA_BAND_PART(KERNEL, THREADS, true, false); }      \
+        CMDA_CUDA_TRY(cudaFuncSetAttribute(band_partition2_kernel<HAS_T, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                           static_cast<int>(shm)));                                                            \
+        band_partition2_kernel<HAS_T, VEC><<<grid, kBand2PartThreads, shm, st>>>(t, x, y, p, tab, bt, bg, H, W, B, z.table,    \
+                                                                                 z.rec32, z.rec8, z.rec16, ubins, guard.flags); \
     } while (0)
-            if (banded == 2) CMDA_BAND_PART_ANY(band_partition2_kernel, kBand2PartThreads);
-            else CMDA_BAND_PART_ANY(band_partition_kernel, kBandPartThreads);
-#undef CMDA_BAND_PART_ANY
-#undef CMDA_BAND_PART
+#define CMDA_BAND_PART1_SRC(HAS_T, VEC) do { if (PKS) CMDA_BAND_PART1(HAS_T, VEC, true); else CMDA_BAND_PART1(HAS_T, VEC, false); } while (0)
+            if (banded == 2) {
+                if (B == 1) { if (vec) CMDA_BAND_PART2(false, true); else CMDA_BAND_PART2(false, false); }
+                else { if (vec) CMDA_BAND_PART2(true, true); else CMDA_BAND_PART2(true, false); }
+            } else {
+                if (B == 1) { if (vec) CMDA_BAND_PART1_SRC(false, true); else CMDA_BAND_PART1_SRC(false, false); }
+                else { if (vec) CMDA_BAND_PART1_SRC(true, true); else CMDA_BAND_PART1_SRC(true, false); }
+            }
+#undef CMDA_BAND_PART1_SRC
+#undef CMDA_BAND_PART2
+#undef CMDA_BAND_PART1
             CMDA_LAUNCH_CHECK();
         }
         phase_mark(st);
@@ -1663,19 +1736,26 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
             CMDA_LAUNCH_CHECK();
         }
     } else if (max_events > 0) {
-        const bool vec = ((reinterpret_cast<uintptr_t>(t) & 15) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
-                         ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && ((reinterpret_cast<uintptr_t>(p) & 7) == 0);
+        const bool vec = PKS ? (reinterpret_cast<uintptr_t>(pk.rec) & 15) == 0
+                             : ((reinterpret_cast<uintptr_t>(t) & 15) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
+                               ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && ((reinterpret_cast<uintptr_t>(p) & 7) == 0);
         const long long groups = (max_events + 7) / 8 + 1;
         const long long per = static_cast<long long>(kSensThreads) * kSensGroupsPerThread;
         dim3 grid(static_cast<unsigned>((groups + per - 1) / per), S);
         unsigned long long* ubins = reinterpret_cast<unsigned long long*>(bin_counts);
-        if (B == 1) {
-            if (vec) sensor_accumulate_kernel<false, true><<<grid, kSensThreads, 0, st>>>(t, x, y, p, tab, H, W, B, R, ubins, guard.sketch);
-            else sensor_accumulate_kernel<false, false><<<grid, kSensThreads, 0, st>>>(t, x, y, p, tab, H, W, B, R, ubins, guard.sketch);
-        } else {
-            if (vec) sensor_accumulate_kernel<true, true><<<grid, kSensThreads, 0, st>>>(t, x, y, p, tab, H, W, B, R, ubins, guard.sketch);
-            else sensor_accumulate_kernel<true, false><<<grid, kSensThreads, 0, st>>>(t, x, y, p, tab, H, W, B, R, ubins, guard.sketch);
-        }
+        // capacity guard: a window of fewer events than a cell holds cannot overflow one whatever its polarity bytes
+        // are worth (|value| <= 509); larger windows run the kernel with its per-CTA sketch
+        const bool sketch = static_cast<unsigned long long>(max_events) * 509ull >= guard.limit;
+#define CMDA_SENS(HAS_T, VEC, SK, PK) sensor_accumulate_kernel<HAS_T, VEC, SK, PK><<<grid, kSensThreads, 0, st>>>(t, x, y, p, pk, tab, H, W, B, R, ubins, guard)
+#define CMDA_SENS_SK(HAS_T, VEC)                                                                                                  \
+    do {                                                                                                                          \
+        if (PKS) { if (sketch) CMDA_SENS(HAS_T, VEC, true, true); else CMDA_SENS(HAS_T, VEC, false, true); }                      \
+        else { if (sketch) CMDA_SENS(HAS_T, VEC, true, false); else CMDA_SENS(HAS_T, VEC, false, false); }                        \
+    } while (0)
+        if (B == 1) { if (vec) CMDA_SENS_SK(false, true); else CMDA_SENS_SK(false, false); }
+        else { if (vec) CMDA_SENS_SK(true, true); else CMDA_SENS_SK(true, false); }
+#undef CMDA_SENS_SK
+#undef CMDA_SENS
         CMDA_LAUNCH_CHECK();
     }
     // capacity guard: recompute the flagged windows (none on DSEC data: both kernels exit at once)
@@ -1683,7 +1763,8 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
         fallback_zero_kernel<<<dim3(16, S), kFallbackThreads, 0, st>>>(guard, FB, static_cast<size_t>(B) * npx);
         long long gx = (max_events + kFallbackThreads * 8 - 1) / (kFallbackThreads * 8);
         if (gx > 64) gx = 64;
-        fallback_scatter_kernel<<<dim3(static_cast<unsigned>(gx), S), kFallbackThreads, 0, st>>>(t, x, y, p, tab, maps2, H, W, B, guard, FB);
+        if (PKS) fallback_scatter_kernel<true><<<dim3(static_cast<unsigned>(gx), S), kFallbackThreads, 0, st>>>(t, x, y, p, pk, tab, maps2, H, W, B, guard, FB);
+        else fallback_scatter_kernel<false><<<dim3(static_cast<unsigned>(gx), S), kFallbackThreads, 0, st>>>(t, x, y, p, pk, tab, maps2, H, W, B, guard, FB);
         CMDA_LAUNCH_CHECK();
     }
     phase_mark(st);

@@ -181,11 +181,12 @@ def _check_windows(store, starts, finishes, clip_ranges, map_ids):
     return starts, ends, S, clips, mids
 
 
-def events_vg_batch(store: EventStore, starts, finishes, num_bins, clip_ranges=None, *, map_ids=None,
+def events_vg_batch(store, starts, finishes, num_bins, clip_ranges=None, *, map_ids=None,
                     normalize=True, final_range=1.0, enforce_no_events_zero=True, mode="auto", out=None,
                     return_raw=False, return_bin_counts=False):
     """S windows ``[start, finish]`` (INCLUSIVE, as in dsec.py:342-345) of one store ->
-    ``[S, num_bins, H, W]`` float32 on the store's device: ``get_events_vg`` batched.
+    ``[S, num_bins, H, W]`` float32 on the store's device: ``get_events_vg`` batched.  ``store`` is an
+    ``EventStore`` (SoA arrays in DSEC dtypes) or a ``packed.PackedEventStore`` (4 bytes per event).
 
     ``clip_ranges[s] is None`` (or ``clip_ranges is None``) selects the reference's default
     ``(finish - start) / 500000 * 1.5`` (dsec.py:362).
@@ -209,12 +210,20 @@ def events_vg_batch(store: EventStore, starts, finishes, num_bins, clip_ranges=N
     total = int(np.clip(ends - starts, 0, None).sum())
     with _lib.on_device(dev):
         ws = _lib.workspace(dev, L.cmda_events_vg_workspace_bytes(total, S, H, W, B, mode_id))
-        _lib.check(L.cmda_events_vg_batch_planned(
-            _lib.ptr(store.t), _lib.ptr(store.x), _lib.ptr(store.y), _lib.ptr(store.p), _lib.host_ptr(starts),
-            _lib.host_ptr(ends), S, _lib.ptr(store.rectify_map), _lib.host_ptr(mids), H, W, B, _lib.host_ptr(clips),
-            float(final_range), int(bool(enforce_no_events_zero)), int(bool(normalize)), _lib.ptr(out), _lib.ptr(raw),
-            _lib.ptr(counts), _lib.ptr(ws), ws.numel(), mode_id, _lib.ptr(store.plans), _lib.stream_ptr(dev)),
-            "cmda_events_vg_batch_planned")
+        if hasattr(store, "rec"):        # packed.PackedEventStore: 4 bytes per event, same results bit for bit
+            _lib.check(L.cmda_events_vg_batch_p4(
+                _lib.ptr(store.rec), _lib.ptr(store.ms_to_idx), _lib.host_ptr(store.h_ms_to_idx), store.n_ms,
+                _lib.host_ptr(starts), _lib.host_ptr(ends), None, S, _lib.ptr(store.rectify_map), _lib.host_ptr(mids), H, W, B,
+                _lib.host_ptr(clips), float(final_range), int(bool(enforce_no_events_zero)), int(bool(normalize)), _lib.ptr(out),
+                _lib.ptr(raw), _lib.ptr(counts), _lib.ptr(ws), ws.numel(), mode_id, _lib.ptr(store.plans), _lib.stream_ptr(dev)),
+                "cmda_events_vg_batch_p4")
+        else:
+            _lib.check(L.cmda_events_vg_batch_planned(
+                _lib.ptr(store.t), _lib.ptr(store.x), _lib.ptr(store.y), _lib.ptr(store.p), _lib.host_ptr(starts),
+                _lib.host_ptr(ends), S, _lib.ptr(store.rectify_map), _lib.host_ptr(mids), H, W, B, _lib.host_ptr(clips),
+                float(final_range), int(bool(enforce_no_events_zero)), int(bool(normalize)), _lib.ptr(out), _lib.ptr(raw),
+                _lib.ptr(counts), _lib.ptr(ws), ws.numel(), mode_id, _lib.ptr(store.plans), _lib.stream_ptr(dev)),
+                "cmda_events_vg_batch_planned")
     res = [out]
     if return_raw:
         res.append(raw if normalize else out)

@@ -153,6 +153,38 @@ int cmda_events_vg_batch_planned(const uint32_t* d_t, const uint16_t* d_x, const
                                  size_t workspace_bytes, int mode, const void* d_plans, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * K2+K3 from the PACKED event stream ("P4"): 4 bytes per event instead of the 9 of the SoA arrays.
+ * Replaces: the same DSECDataset.get_events_vg (dsec.py:341-366); the packed stream stands in for the
+ * decoded events/{t,x,y,p} datasets of events.h5 (dsec.py:342-345) on the wire between host and device and
+ * in HBM -- the host->device copy of the events is what bounds the end-to-end rate of this path.
+ *
+ *   record  = x | y << 11 | p << 21 | sub << 22        (x < 2048, y < 1024, p in {0, 1}, sub < 1000)
+ *   t_us    = t_base + 1000 * ms + sub, ms = the event's millisecond bucket = the largest k with
+ *             ms_to_idx[k] <= event index  (ms_to_idx[k] = index of the first event with t_us - t_base >= 1000 k;
+ *             DSEC's events.h5 carries exactly this table: create_dsec_dataset_txt.py:16, 26-35)
+ *
+ * t_base never enters: the path only takes time differences inside a window.  Results are BIT-IDENTICAL to the SoA
+ * entry points on the stream the records were packed from (tests/test_gpu_parity.py).
+ *
+ *  cmda_pack_events_p4   packs a device-resident SoA stream (t ascending) and builds ms_to_idx [n_ms + 1]
+ *                        (entry n_ms = n); *d_status = number of events the format cannot hold (0 = lossless)
+ *  d_rec                 the packed records the windows index: the whole store, or a staging buffer holding only
+ *                        the windows' events (then h_win_src[s] = store index of window s's first event)
+ *  d_ms_to_idx / h_ms_to_idx   the table on the device and a host copy (the per-window bucket bracket is found on
+ *                        the host, the per-event bucket on the device); h_ms_to_idx[0] must be 0
+ *  mode                  AUTO, FACTORED or BANDED (the sensor-space formulation); others: CMDA_ERR_UNSUPPORTED
+ *  everything else as cmda_events_vg_batch_planned; the workspace size is the same function of (events, S, ...). */
+int cmda_pack_events_p4(const uint32_t* d_t, const uint16_t* d_x, const uint16_t* d_y, const uint8_t* d_p, int64_t n,
+                        uint32_t t_base_us, int64_t n_ms, uint32_t* d_rec, int64_t* d_ms_to_idx, int32_t* d_status,
+                        void* stream);
+int cmda_events_vg_batch_p4(const uint32_t* d_rec, const int64_t* d_ms_to_idx, const int64_t* h_ms_to_idx, int64_t n_ms,
+                            const int64_t* h_win_start, const int64_t* h_win_end, const int64_t* h_win_src, int S,
+                            const float* d_rectify_map, const int32_t* h_map_id, int H, int W, int B,
+                            const float* h_clip, float final_range, int enforce_no_events_zero, int normalize,
+                            float* d_out, float* d_raw_out, int64_t* d_bin_counts, void* d_workspace,
+                            size_t workspace_bytes, int mode, const void* d_plans, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * K2+K3 with the post-voxel augmentation of the dataset fused into the normaliser's apply phase
  * (SURVEY.md 8 f-1).
  * Replaces: DSECDataset.__getitem__, events branch after get_events_vg,

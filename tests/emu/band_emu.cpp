@@ -19,7 +19,6 @@ using namespace cmda;
 
 // capacity guard buffers of the stage-A kernels (sketch of the RED path, flags of the BANDED cuts): scratch here,
 // the guard itself is exercised through the C ABI (tests/test_emu_abi.py)
-static unsigned long long g_sketch[kMaxWindows * kSketch];
 static unsigned g_flags[kMaxWindows];
 
 template <bool HAS_T, bool VEC, int CUT>
@@ -29,7 +28,7 @@ static void run_banded(const uint32_t* t, const uint16_t* x, const uint16_t* y, 
                        unsigned long long* bins) {
     if (max_chunks > 0)
         emu_launch(dim3(static_cast<unsigned>(max_chunks), S), dim3(CUT == 1 ? kBandPartThreads : kBand2PartThreads), [&] {
-            if (CUT == 1) band_partition_kernel<HAS_T, VEC>(t, x, y, p, tab, bt, g, H, W, B, table, rec32, rec8, rec16, bins, g_flags);
+            if (CUT == 1) band_partition_kernel<HAS_T, VEC, false>(t, x, y, p, PackedSrc{nullptr, nullptr, 0}, tab, bt, g, H, W, B, table, rec32, rec8, rec16, bins, g_flags);
             else band_partition2_kernel<HAS_T, VEC>(t, x, y, p, tab, bt, g, H, W, B, table, rec32, rec8, rec16, bins, g_flags);
         });
     emu_launch(dim3(static_cast<unsigned>(S) * g.nbuckets), dim3(kBandAccThreads), [&] {
@@ -48,7 +47,7 @@ static void run_red(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
     const long long groups = (max_events + 7) / 8 + 1;
     const long long per = static_cast<long long>(kSensThreads) * kSensGroupsPerThread;
     emu_launch(dim3(static_cast<unsigned>((groups + per - 1) / per), S), dim3(kSensThreads),
-               [&] { sensor_accumulate_kernel<HAS_T, VEC>(t, x, y, p, tab, H, W, B, R, bins, g_sketch); });
+               [&] { sensor_accumulate_kernel<HAS_T, VEC, true, false>(t, x, y, p, PackedSrc{nullptr, nullptr, 0}, tab, H, W, B, R, bins, Guard{g_flags, B == 1 ? kCellLimit32 : kCellLimit64}); });
 }
 
 // variant 0: sensor_accumulate_kernel (R zeroed here, like the memset of launch_factored); 1: BANDED; 2: BANDED second cut.

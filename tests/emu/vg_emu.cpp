@@ -17,7 +17,7 @@ int factored_supported(int H, int W, int B);
 size_t factored_scratch_bytes(int group, int H, int W, int B);
 int banded_supported(int H, int W, int B);
 size_t banded_scratch_bytes(long long total_events, int group, int H, int W, int B);
-int launch_factored(const uint32_t*, const uint16_t*, const uint16_t*, const uint8_t*, const WindowTable&, int, long long,
+int launch_factored(const uint32_t*, const uint16_t*, const uint16_t*, const uint8_t*, const PackedSrc*, const WindowTable&, int, long long,
                     const float*, int, int, int, void*, int64_t*, float*, PartialStats*, void*, size_t, const void*, int, cudaStream_t);
 int launch_norm_apply(const float*, float*, int, long long, const PartialStats*, const WindowTable&, float, int, cudaStream_t);
 }  // namespace cmda
@@ -53,7 +53,7 @@ extern "C" int emu_events_vg(const uint32_t* t, const uint16_t* x, const uint16_
     PartialStats* partials = reinterpret_cast<PartialStats*>(ws);
     if (bins) std::memset(bins, 0, sizeof(int64_t) * S * B);
     float* raw_g = (normalize && raw) ? raw : out;
-    int rc = launch_factored(t, x, y, p, tab, S, max_events, maps, H, W, B, ws + stats, bins, raw_g, partials, ws + stats + ab,
+    int rc = launch_factored(t, x, y, p, nullptr, tab, S, max_events, maps, H, W, B, ws + stats, bins, raw_g, partials, ws + stats + ab,
                              scratch, nullptr, banded, nullptr);
     if (rc == CMDA_OK && normalize) rc = launch_norm_apply(raw_g, out, S, static_cast<long long>(V), partials, tab, 1.0f, 1, nullptr);
     std::free(ws);

@@ -535,3 +535,69 @@ def test_capacity_guard_routes_overflowing_windows_to_the_fallback(L):
     base1, _ = _vg_batch(L, t, x, y, p, starts, fins, rmap, None, H, W, 1, FACTORED, normalize=0)
     np.testing.assert_allclose(raw1[0], base1[0], rtol=1e-6, atol=1e-3)
     assert np.array_equal(bits(raw1[1]), bits(base1[1]))
+
+
+def _vg_batch_p4(L, rec, table, starts, fins, maps, mids, H, W, B, mode, src=None, normalize=1):
+    S = len(starts)
+    st = np.ascontiguousarray(starts, dtype=np.int64)
+    en = np.ascontiguousarray(fins, dtype=np.int64) + 1
+    base = st if src is None else np.ascontiguousarray(src, dtype=np.int64)
+    clips = np.array([O.default_clip_range(int(f), int(s)) for s, f in zip(starts, fins)], dtype=np.float32)
+    ids = None if mids is None else np.ascontiguousarray(mids, dtype=np.int32)
+    m = np.ascontiguousarray(maps, dtype=np.float32)
+    total = int(np.clip(en - st, 0, None).sum())
+    counts = np.full((S, B), -1, dtype=np.int64)
+    out = np.full((S, B, H, W), np.nan, dtype=np.float32)
+    need = L.cmda_events_vg_workspace_bytes(total, S, H, W, B, mode)
+    ws = workspace(need)
+    rc = L.cmda_events_vg_batch_p4(ptr(rec), ptr(table), ptr(table), len(table) - 1, ptr(st), ptr(en), None if src is None else ptr(base),
+                                   S, ptr(m), ptr(ids), H, W, B, ptr(clips), 1.0, 1, normalize, ptr(out), None, ptr(counts), ptr(ws),
+                                   need, mode, None, None)
+    assert rc == 0, L.cmda_strerror(rc)
+    return out, counts
+
+
+def test_packed_p4_source_is_bit_identical_to_soa(L):
+    """The packed event stream (4 bytes per event, millisecond bucket from ms_to_idx) through cmda_events_vg_batch_p4
+    against the SoA entry point on the stream it was packed from: raw grids, normalised grids and per-bin counts bit
+    for bit, for the RED kernel and the BANDED cut, B = 1 / 3 / 5; ragged windows (empty, one event, unaligned, one
+    timestamp), a sparse stream (a chunk spans far more than the 32 buckets a CTA keeps in shared memory) and a
+    staging buffer that holds only the windows' events (h_win_src).  The device packer against the numpy packer."""
+    from cmda_b200 import packed, synth
+    H, W = 33, 47
+    rng = np.random.default_rng(17)
+    for density, n in (("dense", 30_000), ("sparse", 3_000)):
+        t, x, y, p = synth.make_events(n, H, W, window_us=50_000 if density == "dense" else 40_000_000, seed=23)
+        rmap = synth.make_rectify_map(H, W, seed=9)[None]
+        rec, table, t_base = packed.pack_p4(t, x, y, p)
+        t2, x2, y2, p2 = packed.unpack_p4(rec, table, t_base)
+        assert np.array_equal(t, t2) and np.array_equal(x, x2) and np.array_equal(y, y2) and np.array_equal(p, p2)
+        # the device packer
+        drec = np.zeros(n, dtype=np.uint32)
+        dtab = np.zeros(len(table), dtype=np.int64)
+        status = np.full(1, 77, dtype=np.int32)
+        assert L.cmda_pack_events_p4(ptr(t), ptr(x), ptr(y), ptr(p), n, t_base, len(table) - 1, ptr(drec), ptr(dtab), ptr(status), None) == 0
+        assert status[0] == 0 and np.array_equal(drec, rec) and np.array_equal(dtab, table)
+        bad_p = p.copy(); bad_p[5] = 2
+        assert L.cmda_pack_events_p4(ptr(t), ptr(x), ptr(y), ptr(bad_p), n, t_base, len(table) - 1, ptr(drec), ptr(dtab), ptr(status), None) == 0
+        assert status[0] == 1
+        starts = np.array([0, 1001, 17, 5, n // 2, 123])
+        fins = np.array([n - 1, n - 7, 9000 if n > 9000 else n // 3, 4, n // 2, 2500])
+        dup = t.copy(); dup[starts[5]:fins[5] + 1] = dup[starts[5]]          # a single-timestamp window (Q3): all-zero grid
+        for tt in (t, dup):
+            rec_t, table_t, _ = packed.pack_p4(tt, x, y, p)
+            for B in (1, 3, 5):
+                for mode in (FACTORED, BANDED):
+                    base, counts = _vg_batch(L, tt, x, y, p, starts, fins, rmap, None, H, W, B, mode)
+                    got, c2 = _vg_batch_p4(L, rec_t, table_t, starts, fins, rmap, None, H, W, B, mode)
+                    assert np.array_equal(bits(got), bits(base)) and np.array_equal(c2, counts), (density, B, mode)
+        # a staging buffer holding two windows back to back, each at a 64-event boundary
+        B = 5
+        a0, a1, b0, b1 = 1001, 8000 if n > 9000 else 1500, 123, 2500
+        pos_b = (a1 - a0 + 1 + 63) // 64 * 64 + 64
+        stage = np.zeros(pos_b + (b1 - b0 + 1), dtype=np.uint32)
+        stage[:a1 - a0 + 1] = rec[a0:a1 + 1]
+        stage[pos_b:] = rec[b0:b1 + 1]
+        base, counts = _vg_batch(L, t, x, y, p, [a0, b0], [a1, b1], rmap, None, H, W, B, FACTORED)
+        got, c2 = _vg_batch_p4(L, stage, table, [0, pos_b], [a1 - a0, pos_b + b1 - b0], rmap, None, H, W, B, FACTORED, src=[a0, b0])
+        assert np.array_equal(bits(got), bits(base)) and np.array_equal(c2, counts), density
