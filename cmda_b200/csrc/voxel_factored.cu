@@ -635,344 +635,182 @@ band_accumulate_kernel(const unsigned* __restrict__ table, const unsigned* __res
     }
 }
 
-// ---- BANDED, second cut (mode CMDA_VOXEL_BANDED2: written after the last GPU minute of round 1 from the ncu capture
-// of the first cut -- profiles/r01_ncu_banded_b5_summary.txt; its logic is verified on the CPU emulation of tests/emu,
-// its first run on hardware is pending, which is why it is a mode of its own next to the measured first cut) --------
-// Same record format, same table, same R.  Partition: no per-event branches -- an event that is dropped (outside
-// the sensor, outside the temporal range, past the window, dead window) is ranked into one extra "trash" bucket
-// behind the real ones, so every lane runs the same straight-line code and the sorted chunk simply ends where the
-// trash begins; the per-bin event counts come from the bucket offsets instead of one more atomic per event.
-// Accumulate: per-run pointers with immediate offsets instead of 64-bit address arithmetic per record, 32-bit
-// arithmetic for the (low, high) addends, no divergence region per record (a lane without a record adds zero to
-// a cell of its own).
-#ifndef CMDA_BAND_V2_UNROLL
-#define CMDA_BAND_V2_UNROLL 4
-#endif
+// ---- BANDED, second cut of the partition pass (mode CMDA_VOXEL_BANDED2) -------------------------------------
+// Same records, same table, same accumulate pass, same R as the first cut: only the partition kernel differs.  The
+// first cut executes 93 instructions per event (profiles/r01_ncu_banded_b5_summary.txt: per-event branches, a division
+// subroutine, 64-bit addressing, one more atomic per event for the bin counts); this one is straight-line code:
+//   * dt / dT by the reused correctly rounded reciprocal (Markstein), then ONE conversion: T = rn(2^24 (C-1) dt/dT)
+//     = t0 * 2^24 + rn(f * 2^24) (scaling by a power of two commutes with the rounding of dsec.py:38-39's product,
+//     and adding the even integer t0 * 2^24 does not change a round-half-even), so t0 = T >> 24 and f = T & 0xffffff;
+//   * no branch per event: a dropped event (outside the sensor or the temporal range, past the window, dead window)
+//     is ranked into one extra "trash" bucket behind the real ones, so every lane runs the same code and the sorted
+//     chunk simply ends where the trash begins;
+//   * the record word is one byte permute (cell low byte | f << 8), the slot word two shift-adds;
+//   * per-bin event counts from the bucket offsets after the scan, not from an atomic per event;
+//   * 128-bit copy-out of the sorted chunk.
+// A record keeps one sign bit: a window with a polarity byte beyond {0, 1} is flagged for the fallback (capacity guard).
+constexpr int kPart3Threads = 512;
+constexpr int kPart3Groups = 2;                                               // x 8 events: the chunk stays 8 192 events
+static_assert(kPart3Threads * kPart3Groups * 8 == kBandChunk, "both cuts share the chunk size (record buffer layout, chunk table)");
 static_assert(CMDA_BAND_XSUB == 1, "the second cut ranks in the table's own buckets");
-// CTA shape of the second cut's partition pass: 1 024 threads x one group of 8 events compile to 32 registers (two CTAs =
-// 64 warps per SM, no spills) where 512 x 2 needs 64 registers and spills 30 of them; same 8 192-event chunk
-#ifndef CMDA_BAND2_PART_THREADS
-#define CMDA_BAND2_PART_THREADS 1024
-#endif
-#ifndef CMDA_BAND2_PART_GROUPS
-#define CMDA_BAND2_PART_GROUPS 1
-#endif
-constexpr int kBand2PartThreads = CMDA_BAND2_PART_THREADS;
-constexpr int kBand2PartGroups = CMDA_BAND2_PART_GROUPS;
-constexpr int kBand2PartMinBlocks = 2048 / kBand2PartThreads > 2 ? 2 : 2048 / kBand2PartThreads;
-static_assert(kBand2PartThreads % 32 == 0 && kBand2PartThreads <= 1024 && kBand2PartThreads * kBand2PartGroups * 8 == kBandChunk,
-              "both cuts share the chunk size (record buffer layout, chunk table)");
 
-template <bool HAS_T, bool VEC>
-__global__ void __launch_bounds__(kBand2PartThreads, kBand2PartMinBlocks)
-band_partition2_kernel(const uint32_t* __restrict__ t, const uint16_t* __restrict__ x, const uint16_t* __restrict__ y,
-                       const uint8_t* __restrict__ p, const __grid_constant__ WindowTable tab,
-                       const __grid_constant__ BandTable bt, BandGeom g, int H, int W, int B, unsigned* __restrict__ table,
-                       unsigned* __restrict__ rec32, unsigned char* __restrict__ rec8, unsigned short* __restrict__ rec16,
-                       unsigned long long* __restrict__ bin_counts, unsigned* __restrict__ /*flags: second cut flags in the accumulate pass*/) {
+template <bool HAS_T, bool VEC, bool PK>
+__global__ void __launch_bounds__(kPart3Threads, 2)
+band_partition3_kernel(const uint32_t* __restrict__ t, const uint16_t* __restrict__ x, const uint16_t* __restrict__ y,
+                       const uint8_t* __restrict__ p, const __grid_constant__ PackedSrc pk, const __grid_constant__ WindowTable tab,
+                       const __grid_constant__ BandTable bt, const __grid_constant__ BandGeom g, int H, int W, int B,
+                       unsigned* __restrict__ table, unsigned* __restrict__ rec32, unsigned char* __restrict__ rec8,
+                       unsigned short* __restrict__ rec16, unsigned long long* __restrict__ bin_counts,
+                       unsigned* __restrict__ flags) {
     extern __shared__ __align__(16) unsigned char s_band_raw[];
-    const int NB = g.nbuckets;                                                  // real buckets; bucket NB is the trash
-    unsigned* s_hist = reinterpret_cast<unsigned*>(s_band_raw);                 // [NB + 1]
-    unsigned* s_loff = s_hist + NB + 1;                                         // [NB + 2]  exclusive offsets
-    unsigned* s_stage32 = s_loff + ((NB + 2 + 3) & ~3);                         // [kBandChunk] (B > 1)
+    const int NB = g.nbuckets;
+    unsigned* s_hist = reinterpret_cast<unsigned*>(s_band_raw);                 // [NB + 1]  bucket counts; bucket NB is the trash
+    unsigned* s_off = s_hist + NB + 1;                                          // [NB + 2]  exclusive offsets
+    unsigned* s_stage32 = s_off + ((NB + 2 + 3) & ~3);                          // [kBandChunk] (B > 1)
     unsigned char* s_stage8 = reinterpret_cast<unsigned char*>(s_stage32 + kBandChunk);     // [kBandChunk] (B > 1)
     unsigned short* s_stage16 = reinterpret_cast<unsigned short*>(s_stage32);   // [kBandChunk] (B == 1)
-    __shared__ unsigned s_warp[kBand2PartThreads / 32];
+    __shared__ unsigned s_warp[kPart3Threads / 32];
+    __shared__ MsWindow s_mw;
 
     const int s = blockIdx.y, c = blockIdx.x;
     if (c >= bt.nchunks[s]) return;
-    const WindowDesc wd = tab.w[s];
-    const long long g0 = wd.start >> 3, g1 = (wd.end + 7) >> 3;
-    const long long first = g0 + static_cast<long long>(c) * (kBand2PartThreads * kBand2PartGroups);
-    SensEv8 ev[kBand2PartGroups];
+    const WindowDesc wd = tab.w[s];                                             // end > start: the window has chunks
+    const long long g0 = wd.start >> 3, g1 = (wd.end + 7) >> 3;                 // groups of 8 events
+    const long long first = g0 + static_cast<long long>(c) * (kPart3Threads * kPart3Groups);
+    if (PK && HAS_T) ms_window_init(s_mw, pk, wd, max(first << 3, wd.start) + wd.src_shift);
+    int ms_cursor = 0;
+    SensEv8 ev[kPart3Groups];
 #pragma unroll
-    for (int j = 0; j < kBand2PartGroups; ++j) {
-        const long long grp = first + static_cast<long long>(j) * kBand2PartThreads + threadIdx.x;
+    for (int j = 0; j < kPart3Groups; ++j) {
+        const long long grp = first + static_cast<long long>(j) * kPart3Threads + threadIdx.x;
         if (grp < g1) {
-            ev[j] = sens_load8<HAS_T, VEC>(t, x, y, p, grp << 3, wd.start, wd.end);
+            ev[j] = sens_load8_any<HAS_T, VEC, PK>(t, x, y, p, pk, s_mw, wd, grp << 3, ms_cursor);
         } else {
-            ev[j].x = make_uint4(~0u, ~0u, ~0u, ~0u);                           // 0xffff is outside any sensor: trash
+            ev[j].x = make_uint4(~0u, ~0u, ~0u, ~0u);                           // 0xffff is outside any sensor: dropped
             ev[j].y = ev[j].x; ev[j].t0 = make_uint4(0, 0, 0, 0); ev[j].t1 = ev[j].t0; ev[j].p = make_uint2(0u, 0u);
         }
     }
-    const RawWindowTime rw = raw_window_time(t, wd.start, wd.end, B);
-    const bool alive = rw.den == 1.0f;                                          // NaN: single-timestamp window
-    const float r_dT = __frcp_rn(rw.fdT);
-    for (int k = threadIdx.x; k <= NB; k += kBand2PartThreads) s_hist[k] = 0u;
+    const RawWindowTime rw = PK ? raw_window_time_p4(pk, wd, B) : raw_window_time(t, wd.start, wd.end, B);
+    // den is 1 or NaN (single-timestamp window: every corner is masked, SURVEY.md Q3 -> no records at all)
+    const bool alive = rw.den == 1.0f;
+    const float r_dT = __frcp_rn(rw.fdT);                                       // dead windows never use it
+    const float scale = __fmul_rn(rw.cm1, 16777216.0f);                         // (C - 1) * 2^24, exact
+    for (int k = threadIdx.x; k <= NB; k += kPart3Threads) s_hist[k] = 0u;
     __syncthreads();
 
-    unsigned slot[kBand2PartGroups][8];      // bucket << 21 | rank << 8 | (B > 1) cell high bits | neg << 7
-    unsigned rec[kBand2PartGroups][8];       // B > 1: f << 8 | cell low byte;  B == 1: cell | neg << 15
-    int odd = 0;                            // a polarity byte beyond {0, 1}: its record says +1, band_fixup_kernel adds the rest
+    const unsigned Wu = static_cast<unsigned>(W), Hu = alive ? static_cast<unsigned>(H) : 0u;   // dead: nothing is inside
+    const unsigned rows = static_cast<unsigned>(g.rows), nbands = static_cast<unsigned>(g.nbands), cpb = rows * Wu;
+    const bool one_row = g.rows == 1;
+    unsigned slot[kPart3Groups][8];         // bucket << 21 | (B > 1) (cell high bits | neg << 7) << 13 | rank
+    unsigned rec[kPart3Groups][8];          // B > 1: f << 8 | cell low byte;  B == 1: cell | neg << 15
+    unsigned odd = 0u;
 #pragma unroll
-    for (int j = 0; j < kBand2PartGroups; ++j) {
+    for (int j = 0; j < kPart3Groups; ++j) {
+        odd |= (ev[j].p.x | ev[j].p.y) & 0xfefefefeu;
         const unsigned xs[4] = {ev[j].x.x, ev[j].x.y, ev[j].x.z, ev[j].x.w}, ys[4] = {ev[j].y.x, ev[j].y.y, ev[j].y.z, ev[j].y.w};
         const unsigned ts[8] = {ev[j].t0.x, ev[j].t0.y, ev[j].t0.z, ev[j].t0.w, ev[j].t1.x, ev[j].t1.y, ev[j].t1.z, ev[j].t1.w};
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const unsigned ex = (e & 1) ? (xs[e >> 1] >> 16) : (xs[e >> 1] & 0xffffu);
             const unsigned ey = (e & 1) ? (ys[e >> 1] >> 16) : (ys[e >> 1] & 0xffffu);
-            bool valid = alive && ex < static_cast<unsigned>(W) && ey < static_cast<unsigned>(H);
-            const unsigned pol = ((e < 4 ? ev[j].p.x : ev[j].p.y) >> (8 * (e & 3))) & 0xffu;
-            const unsigned neg = pol == 0u ? 1u : 0u;                           // value = 2 * pol - 1 (dsec.py:45): -1, +1, or more
-            const unsigned band = g.rows > 1 ? __umulhi(ey, g.inv_rows) : ey;
-            const unsigned cell = (ey - band * static_cast<unsigned>(g.rows)) * static_cast<unsigned>(W) + ex;    // junk unless valid
-            unsigned bucket = band, rec_hi = 0u;
+            bool in = ex < Wu && ey < Hu;
+            const unsigned pol1 = ((e < 4 ? ev[j].p.x : ev[j].p.y) >> (8 * (e & 3))) & 1u;
+            const unsigned negbit = 128u - 128u * pol1;                         // value = 2 * pol - 1 (dsec.py:45): pol 0 -> -1
+            const unsigned band = one_row ? ey : __umulhi(ey, g.inv_rows);
+            const unsigned cell = ey * Wu + ex - band * cpb;                    // junk unless in
+            unsigned bucket = band, hi = 0u;
             if constexpr (HAS_T) {
                 const float fdt = __uint2float_rn(ts[e] - rw.t_first);
-                const float tn = __fmul_rn(rw.cm1, div_by_reused(fdt, rw.fdT, r_dT));      // dsec.py:347-348, 38-39
-                const int tb = __float2int_rz(tn);                                          // dsec.py:43 (tn finite, >= 0 when alive)
-                valid = valid && static_cast<unsigned>(tb) < static_cast<unsigned>(B);
-                const float f = __fsub_rn(tn, __int2float_rn(tb));                          // exact (Sterbenz) when valid
-                const unsigned fq = static_cast<unsigned>(__float2int_rn(__fmul_rn(f, 16777216.0f)));
-                rec[j][e] = (fq << 8) | (cell & 0xffu);
-                rec_hi = ((cell >> 8) & 0x7fu) | (neg << 7);
-                bucket += static_cast<unsigned>(tb) * static_cast<unsigned>(g.nbands);
+                const unsigned T = __float2uint_rn(__fmul_rn(scale, div_by_reused(fdt, rw.fdT, r_dT)));   // dsec.py:347-348, 38-39, 43
+                const unsigned tb = T >> kFracBits;
+                in = in && tb < static_cast<unsigned>(B);                       // both temporal corners masked otherwise
+                bucket = tb * nbands + band;
+                rec[j][e] = __byte_perm(cell, T, 0x6540);                       // cell low byte | (T & 0xffffff) << 8
+                hi = ((cell >> 8) & 0x7fu) | negbit;
             } else {
-                rec[j][e] = (cell & 0x7fffu) | (neg << 15);
+                rec[j][e] = (cell & 0x7fffu) | (negbit << 8);
             }
-            bucket = valid ? bucket : static_cast<unsigned>(NB);
-            odd |= static_cast<int>(valid && pol > 1u);
-            slot[j][e] = (bucket << 21) | (atomicAdd(&s_hist[bucket], 1u) << 8) | rec_hi;
+            bucket = in ? bucket : static_cast<unsigned>(NB);
+            slot[j][e] = (bucket << 21) + (hi << 13) + atomicAdd(&s_hist[bucket], 1u);
         }
     }
-    const int any_odd = __syncthreads_or(odd);
-    // exclusive scan of the NB + 1 bucket counts (each thread owns a contiguous run of buckets; with the usual
-    // hundred-odd buckets only the first warps own any, the others go straight to the barriers)
-    const int per = (NB + 1 + kBand2PartThreads - 1) / kBand2PartThreads;
+    const int any_odd = __syncthreads_or(static_cast<int>(odd != 0u));
+    if (any_odd && alive && threadIdx.x == 0) flags[s] = 1u;                     // one sign bit per record: see the capacity guard
+    // exclusive scan of the NB + 1 bucket counts (each thread owns a contiguous run of buckets)
+    const int per = (NB + 1 + kPart3Threads - 1) / kPart3Threads;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const bool owner_warp = wid * 32 * per <= NB;
-    unsigned mine = 0, inc = 0;
-    if (owner_warp) {
-        for (int j = 0; j < per; ++j) {
-            const int k = threadIdx.x * per + j;
-            if (k <= NB) mine += s_hist[k];
-        }
-        inc = mine;
+    unsigned mine = 0;
+    for (int q = 0; q < per; ++q) {
+        const int k = threadIdx.x * per + q;
+        if (k <= NB) mine += s_hist[k];
+    }
+    unsigned inc = mine;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned a = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += a;
-        }
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned a = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += a;
     }
     if (lane == 31) s_warp[wid] = inc;
     __syncthreads();
     if (wid == 0) {
-        const unsigned a = (lane < kBand2PartThreads / 32) ? s_warp[lane] : 0u;
+        const unsigned a = (lane < kPart3Threads / 32) ? s_warp[lane] : 0u;
         unsigned ia = a;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const unsigned u = __shfl_up_sync(0xffffffffu, ia, o);
             if (lane >= o) ia += u;
         }
-        if (lane < kBand2PartThreads / 32) s_warp[lane] = ia - a;
+        if (lane < kPart3Threads / 32) s_warp[lane] = ia - a;
     }
     __syncthreads();
-    if (owner_warp) {
+    {
         unsigned run = s_warp[wid] + inc - mine;
-        unsigned* row = table + static_cast<size_t>(bt.chunk_base[s] + c) * (NB + 2);
-        if (threadIdx.x == 0) row[NB + 1] = static_cast<unsigned>(any_odd);     // read by band_fixup_kernel
-        for (int j = 0; j < per; ++j) {
-            const int k = threadIdx.x * per + j;
+        unsigned* row = table + static_cast<size_t>(bt.chunk_base[s] + c) * (NB + 1);      // the first cut's table
+        for (int q = 0; q < per; ++q) {
+            const int k = threadIdx.x * per + q;
             if (k <= NB) {
-                s_loff[k] = run;
+                s_off[k] = run;
                 row[k] = run;           // row[NB]: where the trash begins = the number of records
                 run += s_hist[k];
             }
         }
     }
     __syncthreads();
+    // stage the records sorted by bucket
 #pragma unroll
-    for (int j = 0; j < kBand2PartGroups; ++j) {
+    for (int j = 0; j < kPart3Groups; ++j) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const unsigned sl = slot[j][e];
-            const unsigned pos = s_loff[sl >> 21] + ((sl >> 8) & 0x1fffu);      // < kBandChunk: the trash is staged too
+            const unsigned pos = s_off[sl >> 21] + (sl & 0x1fffu);              // < kBandChunk: the trash is staged too
             if constexpr (HAS_T) {
                 s_stage32[pos] = rec[j][e];
-                s_stage8[pos] = static_cast<unsigned char>(sl & 0xffu);
+                s_stage8[pos] = static_cast<unsigned char>(sl >> 13);
             } else {
                 s_stage16[pos] = static_cast<unsigned short>(rec[j][e]);
             }
         }
     }
     __syncthreads();
-    const unsigned total = s_loff[NB];
+    // copy out, 128 bits per lane: the chunk's slice of the record buffer starts on a multiple of kBandChunk records
+    const unsigned total = s_off[NB];
     const size_t base = static_cast<size_t>(bt.rec_base[s]) + static_cast<size_t>(c) * kBandChunk;
     if constexpr (HAS_T) {
-        unsigned* d32 = rec32 + base;
-        for (unsigned i = threadIdx.x; i < total; i += kBand2PartThreads) d32[i] = s_stage32[i];
-        const unsigned* s8w = reinterpret_cast<const unsigned*>(s_stage8);
-        unsigned* d8w = reinterpret_cast<unsigned*>(rec8 + base);
-        for (unsigned i = threadIdx.x; i < (total + 3) / 4; i += kBand2PartThreads) d8w[i] = s8w[i];
+        const uint4* s32 = reinterpret_cast<const uint4*>(s_stage32);
+        uint4* d32 = reinterpret_cast<uint4*>(rec32 + base);
+        for (unsigned i = threadIdx.x; i < (total + 3) / 4; i += kPart3Threads) d32[i] = s32[i];
+        const uint4* s8 = reinterpret_cast<const uint4*>(s_stage8);
+        uint4* d8 = reinterpret_cast<uint4*>(rec8 + base);
+        for (unsigned i = threadIdx.x; i < (total + 15) / 16; i += kPart3Threads) d8[i] = s8[i];
     } else {
-        const unsigned* s16w = reinterpret_cast<const unsigned*>(s_stage16);
-        unsigned* d16w = reinterpret_cast<unsigned*>(rec16 + base);
-        for (unsigned i = threadIdx.x; i < (total + 1) / 2; i += kBand2PartThreads) d16w[i] = s16w[i];
+        const uint4* s16 = reinterpret_cast<const uint4*>(s_stage16);
+        uint4* d16 = reinterpret_cast<uint4*>(rec16 + base);
+        for (unsigned i = threadIdx.x; i < (total + 7) / 8; i += kPart3Threads) d16[i] = s16[i];
     }
     // events per temporal bin: the buckets of bin b are [b * nbands, (b + 1) * nbands)
     if (bin_counts != nullptr && threadIdx.x < (HAS_T ? B : 1)) {
-        const unsigned cnt = s_loff[(threadIdx.x + 1) * g.nbands] - s_loff[threadIdx.x * g.nbands];
+        const unsigned cnt = s_off[(threadIdx.x + 1) * g.nbands] - s_off[threadIdx.x * g.nbands];
         if (cnt) atomicAdd(bin_counts + static_cast<size_t>(s) * B + threadIdx.x, static_cast<unsigned long long>(cnt));
-    }
-}
-
-// One round of the accumulate loop: U records per lane (record lane + 32 * u of the run's next 32 * U), all loads
-// first.  FULL: every lane has all its records.  Otherwise `rem` records are left: a lane without one adds zero to a
-// cell of its own (cells 0..31: distinct banks), which keeps the code straight.
-template <bool HAS_T, int U, bool FULL>
-__device__ __forceinline__ void band_add_round(const unsigned* __restrict__ p32, const unsigned char* __restrict__ p8,
-                                               const unsigned short* __restrict__ p16, unsigned rem, int lane,
-                                               unsigned* __restrict__ s_acc) {
-    unsigned r32[U], r8[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        const bool v = FULL || static_cast<unsigned>(lane) + 32u * u < rem;
-        r32[u] = 0u; r8[u] = 0u;
-        if constexpr (HAS_T) { if (v) { r32[u] = __ldg(p32 + 32 * u); r8[u] = __ldg(p8 + 32 * u); } }
-        else { if (v) r32[u] = __ldg(p16 + 32 * u); }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        const bool v = FULL || static_cast<unsigned>(lane) + 32u * u < rem;
-        if constexpr (HAS_T) {
-            // sign * (2^44 + f) as the (high, low) words of the int64 addend
-            const unsigned fq = r32[u] >> 8;
-            const bool neg = (r8[u] & 0x80u) != 0u;
-            const unsigned cell = v ? ((r32[u] & 0xffu) | ((r8[u] & 0x7fu) << 8)) : static_cast<unsigned>(lane);
-            const unsigned lo = v ? (neg ? 0u - fq : fq) : 0u;
-            const int hi = v ? (neg ? -4096 - static_cast<int>(fq != 0u) : 4096) : 0;
-            const unsigned old = atomicAdd(s_acc + 2u * cell, lo);
-            atomicAdd(reinterpret_cast<int*>(s_acc) + 2u * cell + 1u, hi + static_cast<int>(old + lo < old));
-        } else {
-            const unsigned cell = v ? (r32[u] & 0x7fffu) : static_cast<unsigned>(lane);
-            atomicAdd(reinterpret_cast<int*>(s_acc) + cell, v ? ((r32[u] & 0x8000u) ? -1 : 1) : 0);
-        }
-    }
-}
-
-template <bool HAS_T>
-__global__ void __launch_bounds__(kBandAccThreads)
-band_accumulate2_kernel(const unsigned* __restrict__ table, const unsigned* __restrict__ rec32,
-                        const unsigned char* __restrict__ rec8, const unsigned short* __restrict__ rec16,
-                        const __grid_constant__ BandTable bt, BandGeom g, int H, int W, int B, void* __restrict__ R,
-                        unsigned* __restrict__ flags) {
-    constexpr int U = CMDA_BAND_V2_UNROLL;
-    extern __shared__ __align__(16) unsigned s_band_acc[];      // B > 1: (lo, hi) per cell;  B == 1: count[cells]
-    const unsigned cells = static_cast<unsigned>(g.rows) * static_cast<unsigned>(W);
-    const int Bk = HAS_T ? B : 1;
-    int item = blockIdx.x;
-    const int band = item % g.nbands;
-    item /= g.nbands;
-    const int k = item % Bk, s = item / Bk;
-    const unsigned band_cells = static_cast<unsigned>(min(g.rows, H - band * g.rows)) * static_cast<unsigned>(W);
-    for (unsigned i = threadIdx.x; i < (HAS_T ? 2u * cells : cells); i += kBandAccThreads) s_band_acc[i] = 0u;
-    __syncthreads();
-
-    const int nchunks = bt.nchunks[s];
-    const unsigned bucket = static_cast<unsigned>(k) * static_cast<unsigned>(g.nbands) + static_cast<unsigned>(band);
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    constexpr int nwarps = kBandAccThreads / 32;
-    const size_t row_words = static_cast<size_t>(g.nbuckets) + 2;      // offsets, record count, odd-polarity flag
-    const unsigned* tbl = table + static_cast<size_t>(bt.chunk_base[s]) * row_words + bucket;
-    const size_t base_s = static_cast<size_t>(bt.rec_base[s]);
-    unsigned long long my_records = 0;      // capacity guard, as in the first cut
-    for (int c0 = 0; c0 < nchunks; c0 += 32 * nwarps) {
-        const int c = c0 + lane * nwarps + wid;
-        unsigned a = 0u, b = 0u;
-        if (c < nchunks) {
-            a = __ldg(tbl + static_cast<size_t>(c) * row_words);
-            b = __ldg(tbl + static_cast<size_t>(c) * row_words + 1);
-        }
-        if (b > a) my_records += b - a;
-        unsigned todo = __ballot_sync(0xffffffffu, b > a);
-        while (todo) {
-            const int j = __ffs(todo) - 1;
-            todo &= todo - 1u;
-            const unsigned ra = __shfl_sync(0xffffffffu, a, j), len = __shfl_sync(0xffffffffu, b, j) - ra;
-            const size_t off = base_s + static_cast<size_t>(c0 + j * nwarps + wid) * kBandChunk + ra + lane;
-            const unsigned* p32 = HAS_T ? rec32 + off : nullptr;               // the format that is not in use has no buffer
-            const unsigned char* p8 = HAS_T ? rec8 + off : nullptr;
-            const unsigned short* p16 = HAS_T ? nullptr : rec16 + off;
-            // whole rounds of 32 * U records run without a single predicate; the last, partial round selects
-            unsigned done = 0;
-            for (; done + 32u * U <= len; done += 32u * U) {
-                band_add_round<HAS_T, U, true>(p32, p8, p16, 0u, lane, s_band_acc);
-                if constexpr (HAS_T) { p32 += 32 * U; p8 += 32 * U; } else { p16 += 32 * U; }
-            }
-            if (done < len) band_add_round<HAS_T, U, false>(p32, p8, p16, len - done, lane, s_band_acc);
-        }
-    }
-    if (__syncthreads_or(my_records >= (HAS_T ? kCellLimit64 : kCellLimit32) / kBandAccThreads) != 0) {
-        __shared__ unsigned long long s_total;
-        if (threadIdx.x == 0) s_total = 0ull;
-        __syncthreads();
-        if (my_records) atomicAdd(&s_total, my_records);
-        __syncthreads();
-        if (threadIdx.x == 0 && s_total >= (HAS_T ? kCellLimit64 : kCellLimit32)) flags[s] = 1u;
-    }
-    const size_t plane = static_cast<size_t>(H) * W;
-    const size_t band_off = static_cast<size_t>(band) * g.rows * W;
-    if constexpr (HAS_T) {
-        long long* dst = reinterpret_cast<long long*>(R) + (static_cast<size_t>(s) * B + k) * plane + band_off;
-        const long long* src = reinterpret_cast<const long long*>(s_band_acc);     // (lo, hi) adjacent: the int64 itself
-        for (unsigned i = threadIdx.x; i < band_cells; i += kBandAccThreads) dst[i] = src[i];
-    } else {
-        int* dst = reinterpret_cast<int*>(R) + static_cast<size_t>(s) * plane + band_off;
-        for (unsigned i = threadIdx.x; i < band_cells; i += kBandAccThreads) dst[i] = static_cast<int>(s_band_acc[i]);
-    }
-}
-
-
-// Arbitrary polarity bytes (the reference computes value = 2 * p - 1 for whatever p holds, dsec.py:45, 349): a record
-// carries one sign bit, so an event with p > 1 went through the passes above as +1; here the remaining value - 1 is
-// added with the RED of sensor_accumulate_kernel, after band_accumulate2_kernel has stored R.  DSEC stores {0, 1}: every
-// chunk flag is clear and the 32-chunks-per-CTA grid below costs a few hundred flag reads.
-constexpr int kBandFixupChunks = 32;
-template <bool HAS_T, bool VEC>
-__global__ void __launch_bounds__(kBandPartThreads)
-band_fixup_kernel(const uint32_t* __restrict__ t, const uint16_t* __restrict__ x, const uint16_t* __restrict__ y,
-                  const uint8_t* __restrict__ p, const __grid_constant__ WindowTable tab, const __grid_constant__ BandTable bt,
-                  BandGeom g, int H, int W, int B, const unsigned* __restrict__ table, void* __restrict__ R) {
-    const int s = blockIdx.y;
-    const int nchunks = bt.nchunks[s];
-    const WindowDesc wd = tab.w[s];
-    const size_t plane = static_cast<size_t>(H) * W;
-    for (int c = blockIdx.x * kBandFixupChunks; c < min((blockIdx.x + 1) * kBandFixupChunks, nchunks); ++c) {
-        if (__ldg(table + static_cast<size_t>(bt.chunk_base[s] + c) * (g.nbuckets + 2) + g.nbuckets + 1) == 0u) continue;   // uniform
-        const long long g0 = wd.start >> 3, g1 = (wd.end + 7) >> 3;
-        const long long first = g0 + static_cast<long long>(c) * (kBandPartThreads * kBandPartGroups);
-        const RawWindowTime rw = raw_window_time(t, wd.start, wd.end, B);      // alive: a dead window raises no flag
-        const float r_dT = __frcp_rn(rw.fdT);
-        for (int j = 0; j < kBandPartGroups; ++j) {
-            const long long grp = first + static_cast<long long>(j) * kBandPartThreads + threadIdx.x;
-            if (grp >= g1) continue;
-            const SensEv8 ev = sens_load8<HAS_T, VEC>(t, x, y, p, grp << 3, wd.start, wd.end);
-            const unsigned xs[4] = {ev.x.x, ev.x.y, ev.x.z, ev.x.w}, ys[4] = {ev.y.x, ev.y.y, ev.y.z, ev.y.w};
-            const unsigned ts[8] = {ev.t0.x, ev.t0.y, ev.t0.z, ev.t0.w, ev.t1.x, ev.t1.y, ev.t1.z, ev.t1.w};
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const unsigned pol = ((e < 4 ? ev.p.x : ev.p.y) >> (8 * (e & 3))) & 0xffu;
-                if (pol <= 1u) continue;
-                const unsigned ex = (e & 1) ? (xs[e >> 1] >> 16) : (xs[e >> 1] & 0xffffu);
-                const unsigned ey = (e & 1) ? (ys[e >> 1] >> 16) : (ys[e >> 1] & 0xffffu);
-                if (ex >= static_cast<unsigned>(W) || ey >= static_cast<unsigned>(H)) continue;
-                const long long rest = 2LL * pol - 2;                           // value - 1
-                const size_t pix = static_cast<size_t>(ey) * W + ex;
-                if constexpr (HAS_T) {
-                    const float fdt = __uint2float_rn(ts[e] - rw.t_first);
-                    const float tn = __fmul_rn(rw.cm1, div_by_reused(fdt, rw.fdT, r_dT));
-                    const int tb = __float2int_rz(tn);
-                    if (static_cast<unsigned>(tb) >= static_cast<unsigned>(B)) continue;
-                    const float f = __fsub_rn(tn, __int2float_rn(tb));
-                    const long long fq = static_cast<long long>(__float2int_rn(__fmul_rn(f, 16777216.0f)));
-                    atomicAdd(reinterpret_cast<unsigned long long*>(R) + (static_cast<size_t>(s) * B + tb) * plane + pix,
-                              static_cast<unsigned long long>(rest * ((1LL << kCountShift) + fq)));
-                } else {
-                    atomicAdd(reinterpret_cast<int*>(R) + static_cast<size_t>(s) * plane + pix, static_cast<int>(rest));
-                }
-            }
-        }
     }
 }
 
@@ -1597,7 +1435,6 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
     if (!factored_supported(H, W, B)) return CMDA_ERR_UNSUPPORTED;
     // the source: SoA arrays in DSEC dtypes, or the packed P4 stream (then t / x / y / p are NULL)
     const bool PKS = packed != nullptr;
-    if (PKS && banded == 2) return CMDA_ERR_UNSUPPORTED;
     const PackedSrc pk = PKS ? *packed : PackedSrc{nullptr, nullptr, 0};
     BandGeom bg{};
     if (banded && !pick_band_geom(H, W, B, bg)) return CMDA_ERR_UNSUPPORTED;
@@ -1675,7 +1512,7 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
                                ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && ((reinterpret_cast<uintptr_t>(p) & 7) == 0);
         unsigned long long* ubins = reinterpret_cast<unsigned long long*>(bin_counts);
         if (max_chunks > 0) {
-            const int fine = banded == 2 ? bg.nbuckets + 1 : (bg.nbuckets << bg.xsub_log2);
+            const int fine = banded == 2 ? bg.nbuckets + 1 : (bg.nbuckets << bg.xsub_log2);     // second cut: + the trash bucket
             const size_t shm = sizeof(unsigned) * (fine + ((fine + 1 + 3) & ~3)) + (B > 1 ? 5u : 2u) * static_cast<size_t>(kBandChunk);
             dim3 grid(static_cast<unsigned>(max_chunks), S);
 #define CMDA_BAND_PART1(HAS_T, VEC, PK)                                                                                        \
@@ -1685,23 +1522,25 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
         band_partition_kernel<HAS_T, VEC, PK><<<grid, kBandPartThreads, shm, st>>>(t, x, y, p, pk, tab, bt, bg, H, W, B, z.table, \
                                                                                    z.rec32, z.rec8, z.rec16, ubins, guard.flags); \
     } while (0)
-#define CMDA_BAND_PART2(HAS_T, VEC)                                                                                            \
+#define CMDA_BAND_PART3(HAS_T, VEC, PK)                                                                                        \
     do {                                                                                                                       \
-        CMDA_CUDA_TRY(cudaFuncSetAttribute(band_partition2_kernel<HAS_T, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+        CMDA_CUDA_TRY(cudaFuncSetAttribute(band_partition3_kernel<HAS_T, VEC, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                            static_cast<int>(shm)));                                                            \
-        band_partition2_kernel<HAS_T, VEC><<<grid, kBand2PartThreads, shm, st>>>(t, x, y, p, tab, bt, bg, H, W, B, z.table,    \
+        band_partition3_kernel<HAS_T, VEC, PK><<<grid, kPart3Threads, shm, st>>>(t, x, y, p, pk, tab, bt, bg, H, W, B, z.table, \
                                                                                  z.rec32, z.rec8, z.rec16, ubins, guard.flags); \
     } while (0)
+#define CMDA_BAND_PART3_SRC(HAS_T, VEC) do { if (PKS) CMDA_BAND_PART3(HAS_T, VEC, true); else CMDA_BAND_PART3(HAS_T, VEC, false); } while (0)
 #define CMDA_BAND_PART1_SRC(HAS_T, VEC) do { if (PKS) CMDA_BAND_PART1(HAS_T, VEC, true); else CMDA_BAND_PART1(HAS_T, VEC, false); } while (0)
             if (banded == 2) {
-                if (B == 1) { if (vec) CMDA_BAND_PART2(false, true); else CMDA_BAND_PART2(false, false); }
-                else { if (vec) CMDA_BAND_PART2(true, true); else CMDA_BAND_PART2(true, false); }
+                if (B == 1) { if (vec) CMDA_BAND_PART3_SRC(false, true); else CMDA_BAND_PART3_SRC(false, false); }
+                else { if (vec) CMDA_BAND_PART3_SRC(true, true); else CMDA_BAND_PART3_SRC(true, false); }
             } else {
                 if (B == 1) { if (vec) CMDA_BAND_PART1_SRC(false, true); else CMDA_BAND_PART1_SRC(false, false); }
                 else { if (vec) CMDA_BAND_PART1_SRC(true, true); else CMDA_BAND_PART1_SRC(true, false); }
             }
 #undef CMDA_BAND_PART1_SRC
-#undef CMDA_BAND_PART2
+#undef CMDA_BAND_PART3_SRC
+#undef CMDA_BAND_PART3
 #undef CMDA_BAND_PART1
             CMDA_LAUNCH_CHECK();
         }
@@ -1720,19 +1559,8 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
             KERNEL<true><<<items, kBandAccThreads, shm, st>>>(z.table, z.rec32, z.rec8, z.rec16, bt, bg, H, W, B, R, guard.flags); \
         }                                                                                                                      \
     } while (0)
-            if (banded == 2) CMDA_BAND_ACC(band_accumulate2_kernel);
-            else CMDA_BAND_ACC(band_accumulate_kernel);
+            CMDA_BAND_ACC(band_accumulate_kernel);
 #undef CMDA_BAND_ACC
-            if (banded == 2 && max_chunks > 0) {
-                dim3 fgrid(static_cast<unsigned>((max_chunks + kBandFixupChunks - 1) / kBandFixupChunks), S);
-                if (B == 1) {
-                    if (vec) band_fixup_kernel<false, true><<<fgrid, kBandPartThreads, 0, st>>>(t, x, y, p, tab, bt, bg, H, W, B, z.table, R);
-                    else band_fixup_kernel<false, false><<<fgrid, kBandPartThreads, 0, st>>>(t, x, y, p, tab, bt, bg, H, W, B, z.table, R);
-                } else {
-                    if (vec) band_fixup_kernel<true, true><<<fgrid, kBandPartThreads, 0, st>>>(t, x, y, p, tab, bt, bg, H, W, B, z.table, R);
-                    else band_fixup_kernel<true, false><<<fgrid, kBandPartThreads, 0, st>>>(t, x, y, p, tab, bt, bg, H, W, B, z.table, R);
-                }
-            }
             CMDA_LAUNCH_CHECK();
         }
     } else if (max_events > 0) {

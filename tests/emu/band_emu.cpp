@@ -27,17 +27,13 @@ static void run_banded(const uint32_t* t, const uint16_t* x, const uint16_t* y, 
                        unsigned* table, unsigned* rec32, unsigned char* rec8, unsigned short* rec16, void* R,
                        unsigned long long* bins) {
     if (max_chunks > 0)
-        emu_launch(dim3(static_cast<unsigned>(max_chunks), S), dim3(CUT == 1 ? kBandPartThreads : kBand2PartThreads), [&] {
+        emu_launch(dim3(static_cast<unsigned>(max_chunks), S), dim3(CUT == 1 ? kBandPartThreads : kPart3Threads), [&] {
             if (CUT == 1) band_partition_kernel<HAS_T, VEC, false>(t, x, y, p, PackedSrc{nullptr, nullptr, 0}, tab, bt, g, H, W, B, table, rec32, rec8, rec16, bins, g_flags);
-            else band_partition2_kernel<HAS_T, VEC>(t, x, y, p, tab, bt, g, H, W, B, table, rec32, rec8, rec16, bins, g_flags);
+            else band_partition3_kernel<HAS_T, VEC, false>(t, x, y, p, PackedSrc{nullptr, nullptr, 0}, tab, bt, g, H, W, B, table, rec32, rec8, rec16, bins, g_flags);
         });
     emu_launch(dim3(static_cast<unsigned>(S) * g.nbuckets), dim3(kBandAccThreads), [&] {
-        if (CUT == 1) band_accumulate_kernel<HAS_T>(table, rec32, rec8, rec16, bt, g, H, W, B, R, g_flags);
-        else band_accumulate2_kernel<HAS_T>(table, rec32, rec8, rec16, bt, g, H, W, B, R, g_flags);
+        band_accumulate_kernel<HAS_T>(table, rec32, rec8, rec16, bt, g, H, W, B, R, g_flags);      // both cuts share the accumulate pass
     });
-    if (CUT == 2 && max_chunks > 0)
-        emu_launch(dim3(static_cast<unsigned>((max_chunks + kBandFixupChunks - 1) / kBandFixupChunks), S), dim3(kBandPartThreads),
-                   [&] { band_fixup_kernel<HAS_T, VEC>(t, x, y, p, tab, bt, g, H, W, B, table, R); });
 }
 
 template <bool HAS_T, bool VEC>

@@ -333,6 +333,19 @@ inline int __float2int_rn(float v) {            // cvt.rni.s32.f32
     if (r <= -2147483648.0f) return INT_MIN;
     return static_cast<int>(r);
 }
+inline unsigned __float2uint_rn(float v) {      // cvt.rni.u32.f32: NaN -> 0, saturating
+    if (v != v) return 0u;
+    const float r = std::nearbyintf(v);
+    if (r >= 4294967296.0f) return 0xffffffffu;
+    if (r <= 0.0f) return 0u;
+    return static_cast<unsigned>(r);
+}
+inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel) {      // prmt.b32 (default mode)
+    const unsigned long long pool = (static_cast<unsigned long long>(b) << 32) | a;
+    unsigned r = 0u;
+    for (int i = 0; i < 4; ++i) r |= static_cast<unsigned>((pool >> (8 * ((sel >> (4 * i)) & 7u))) & 0xffu) << (8 * i);
+    return r;
+}
 inline long long __float2ll_rn(float v) {
     if (v != v) return 0;
     const float r = std::nearbyintf(v);

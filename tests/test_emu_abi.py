@@ -397,8 +397,9 @@ def test_prebuilt_plans_equal_per_call_plans(L):
 
 def test_randomised_geometry_all_stage_a_forms_agree(L):
     """Seeded random grids (odd sizes, 1-9 bins, widths that leave one row per band), ragged windows with duplicate
-    timestamps, out-of-sensor events and polarity bytes beyond {0, 1} (BANDED2 only: BANDED keeps the DSEC alphabet):
-    FACTORED, BANDED and BANDED2 produce the same raw grids and per-bin counts, bit for bit."""
+    timestamps and out-of-sensor events: FACTORED, BANDED and BANDED2 produce the same raw grids and per-bin counts,
+    bit for bit.  With polarity bytes beyond {0, 1} the BANDED cuts flag the window (one sign bit per record) and the
+    fallback recomputes it with the reference's own weights: same counts, the GLOBAL mode's grid bit for bit."""
     from cmda_b200 import synth
     rng = np.random.default_rng(20260117)
     for it in range(10):
@@ -421,9 +422,21 @@ def test_randomised_geometry_all_stage_a_forms_agree(L):
                 p = p.copy()
                 p[rng.random(n) < 0.02] = int(rng.integers(2, 256))
             base, counts = _vg_batch(L, t, x, y, p, starts, fins, rmap, None, H, W, B, FACTORED, normalize=0)
-            for mode in ((BANDED2,) if odd else (BANDED, BANDED2)):
+            for mode in (BANDED, BANDED2):
                 got, c2 = _vg_batch(L, t, x, y, p, starts, fins, rmap, None, H, W, B, mode, normalize=0)
-                assert np.array_equal(bits(got), bits(base)) and np.array_equal(c2, counts), (it, H, W, B, mode, odd)
+                assert np.array_equal(c2, counts), (it, H, W, B, mode, odd)
+                if not odd:
+                    assert np.array_equal(bits(got), bits(base)), (it, H, W, B, mode)
+                    continue
+                # a window that holds such a byte (and is alive: two distinct timestamps) is recomputed with the GLOBAL
+                # formulation, bit for bit; the others keep the sensor-space sums
+                glob, _ = _vg_batch(L, t, x, y, p, starts, fins, rmap, None, H, W, B, GLOBAL, normalize=0)
+                for s in range(S):
+                    if fins[s] < starts[s]:
+                        continue
+                    sl = slice(int(starts[s]), int(fins[s]) + 1)
+                    flagged = bool((p[sl] > 1).any()) and t[sl][0] != t[sl][-1]
+                    assert np.array_equal(bits(got[s]), bits(glob[s] if flagged else base[s])), (it, H, W, B, mode, s, flagged)
             for s in range(S):
                 if fins[s] < starts[s]:
                     assert not base[s].any() and int(counts[s].sum()) == 0
@@ -521,7 +534,7 @@ def test_capacity_guard_routes_overflowing_windows_to_the_fallback(L):
     t[n_hot:] = np.sort(t[n_hot:])
     rmap = synth.make_rectify_map(H, W, seed=3)[None]
     starts, fins = np.array([0, n_hot]), np.array([n_hot - 1, n_hot + n_bg - 1])
-    for mode in (FACTORED, BANDED, AUTO):
+    for mode in (FACTORED, BANDED, BANDED2, AUTO):
         raw, counts = _vg_batch(L, t, x, y, p, starts, fins, rmap, None, H, W, B, mode, normalize=0)
         for s in range(2):
             sl = slice(int(starts[s]), int(fins[s]) + 1)

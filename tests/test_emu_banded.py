@@ -101,28 +101,6 @@ def test_banded_kernels_match_red_kernel_and_definition(emu, H, W, bins):
         assert np.array_equal(got_bins, red_bins), f"BANDED cut {variant}: per-bin counts differ"
 
 
-@pytest.mark.parametrize("bins", [1, 4])
-def test_second_cut_handles_any_polarity_byte(emu, bins):
-    """value = 2 * p - 1 for whatever p holds (dsec.py:45, 349): the RED kernel multiplies by it, the second BANDED cut
-    records +1 and adds the rest in band_fixup_kernel for the chunks whose flag is up (the first cut keeps the DSEC
-    alphabet {0, 1} as a precondition)."""
-    H, W, n = 37, 53, 25_000
-    t, x, y, p = make_events(n, H, W, seed=77)
-    rng = np.random.default_rng(3)
-    weird = rng.choice(n, size=400, replace=False)
-    p[weird] = rng.choice(np.array([2, 3, 7, 128, 255], dtype=np.uint8), size=400)
-    p[9000:17500] = rng.integers(0, 2, size=8500).astype(np.uint8)          # at least one whole chunk without any
-    x[weird[:5]] = W                                                    # an odd polarity outside the sensor: dropped
-    starts, ends = [0, 5, 12_345], [n, 8192 + 5, 12_346]
-    red, red_bins = stage_a(emu, t, x, y, p, starts, ends, H, W, bins, 0)
-    for s in range(len(starts)):
-        want, cnt = direct_R(t, x, y, p, starts[s], ends[s], H, W, bins)
-        assert np.array_equal(red[s].astype(np.int64).reshape(bins, H, W), want)
-        assert np.array_equal(red_bins[s], cnt)
-    got, got_bins = stage_a(emu, t, x, y, p, starts, ends, H, W, bins, 2)
-    assert np.array_equal(got, red) and np.array_equal(got_bins, red_bins)
-
-
 def test_banded_kernels_scalar_load_path(emu):
     """Arrays that start off the 16-byte grid take the scalar loads everywhere."""
     H, W, bins, n = 37, 53, 3, 20_000

@@ -397,9 +397,9 @@ def test_events_vg_banded_identical_to_factored(cm, shape):
 
 
 def test_events_vg_banded2_identical_to_factored():
-    """The second cut must reproduce FACTORED bit for bit like the first, and additionally for polarity bytes beyond
-    {0, 1} (value = 2 * p - 1 for whatever p holds, dsec.py:45).  Runs in a process of its own
-    (tools/banded2_check.py) so that a first hardware run cannot touch this process's CUDA context."""
+    """The second cut of the partition pass must reproduce FACTORED bit for bit like the first; windows with polarity
+    bytes beyond {0, 1} (value = 2 * p - 1 for whatever p holds, dsec.py:45) are flagged and recomputed by the fallback:
+    the same grid within 1e-5.  Through tools/banded2_check.py (which also times the three stage-A forms)."""
     import json
     import os
     import subprocess
@@ -410,7 +410,7 @@ def test_events_vg_banded2_identical_to_factored():
     assert res.returncode == 0, res.stderr[-2000:]
     out = json.loads(res.stdout.strip().splitlines()[-1])
     for key, r in out.items():
-        assert r["bit_identical_to_factored"] and r["bit_identical_with_polarity_bytes_beyond_0_1"], (key, r)
+        assert r["bit_identical_to_factored"] and r["within_1e-5_with_polarity_bytes_beyond_0_1"], (key, r)
 
 
 def test_events_vg_large_window_b1(cm):

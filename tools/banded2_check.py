@@ -37,7 +37,7 @@ for b in a.bins:
     same = bool(torch.equal(ref, got) and torch.equal(rc, gc))
     ref = cmda_b200.events_vg_batch(store_odd, starts[:k], fins[:k], b, mode="factored")
     got = cmda_b200.events_vg_batch(store_odd, starts[:k], fins[:k], b, mode="banded2")
-    same_odd = bool(torch.equal(ref, got))
+    same_odd = bool((ref - got).abs().max() <= 1e-5)      # a flagged window is recomputed by the fallback: same grid within the bar
     del ref, got
     out = torch.empty((a.windows, b, bench.H, bench.W), dtype=torch.float32, device=dev)
     ms = {}
@@ -53,7 +53,7 @@ for b in a.bins:
         torch.cuda.synchronize(dev)
         ms[mode] = e0.elapsed_time(e1) / a.steps
     n = int((np.asarray(fins) - np.asarray(starts) + 1).sum())
-    res[f"bins_{b}"] = {"bit_identical_to_factored": same, "bit_identical_with_polarity_bytes_beyond_0_1": same_odd,
+    res[f"bins_{b}"] = {"bit_identical_to_factored": same, "within_1e-5_with_polarity_bytes_beyond_0_1": same_odd,
                         "ms_per_step": ms, "Mevents_per_s_banded2": n / (ms["banded2"] * 1e-3) / 1e6,
                         "windows": a.windows, "events_per_window": a.events}
 print(json.dumps(res), flush=True)
