@@ -27,9 +27,11 @@ int launch_resize_bilinear(const uint8_t*, int, int, int, int, int, int, uint8_t
 int launch_u8_crop_center(const uint8_t*, int, int, int, const int*, const int*, const int*, int, int, int, float*, cudaStream_t);
 int launch_rgb_to_gray(const uint8_t*, int64_t, uint8_t*, cudaStream_t);
 int launch_denorm_to_gray(const float*, int, int, int, const float*, const float*, uint8_t*, uint8_t*, cudaStream_t);
-int launch_isr(const uint8_t*, int, int, int, int, int, const float*, float, float, float*, unsigned*, cudaStream_t);
-int launch_pair(const uint8_t*, const uint8_t*, int, int, int, const float*, float, float, float*, uint8_t*, unsigned*,
+int launch_isr(const uint8_t*, int, int, int, int, int, const float*, float, float, float*, unsigned*, size_t, cudaStream_t);
+int launch_pair(const uint8_t*, const uint8_t*, int, int, int, const float*, float, float, float*, uint8_t*, unsigned*, size_t,
                 cudaStream_t);
+size_t image_slot_bytes(int);
+size_t image_table_bytes(int, int, int);
 // TILED mode (voxel_tiled.cu)
 size_t tiled_workspace_bytes(int64_t total_events, int S, int H, int W, int B);
 int tiled_supported(int H, int W, int B);
@@ -484,7 +486,8 @@ int cmda_remap_events(const uint32_t* d_t, const uint16_t* d_x, const uint16_t* 
 
 size_t cmda_image_workspace_bytes(int S, int H, int W, int channels) {
     if (S <= 0 || H <= 0 || W <= 0) return 0;
-    size_t need = align_up(sizeof(unsigned) * 16 * static_cast<size_t>(S), 256);
+    // min / max slots | pair tables of the table-driven apply passes (large images) | gray plane of an RGB input
+    size_t need = image_slot_bytes(S) + align_up(image_table_bytes(S, H, W), 256);
     if (channels == 3) need += align_up(static_cast<size_t>(S) * H * W, 256);
     return need + 256;
 }
@@ -498,7 +501,8 @@ int cmda_logdiff_pair_u8(const uint8_t* d_now, const uint8_t* d_front, int S, in
     if ((reinterpret_cast<uintptr_t>(d_workspace) & 255) || workspace_bytes < cmda_image_workspace_bytes(S, H, W, 1))
         return CMDA_ERR_WORKSPACE;
     return launch_pair(d_now, d_front, S, H, W, h_lut, thr, clip, d_out_f32, d_out_u8,
-                       static_cast<unsigned*>(d_workspace), static_cast<cudaStream_t>(stream));
+                       static_cast<unsigned*>(d_workspace), image_slot_bytes(S) + image_table_bytes(S, H, W),
+                       static_cast<cudaStream_t>(stream));
 }
 
 int cmda_isr_shift_u8(const uint8_t* d_img, int channels, int S, int H, int W, int shift_pixel, int direction,
@@ -517,12 +521,13 @@ int cmda_isr_shift_u8(const uint8_t* d_img, int channels, int S, int H, int W, i
     unsigned* slots = static_cast<unsigned*>(d_workspace);
     const uint8_t* gray = d_img;
     if (channels == 3) {
-        uint8_t* g = reinterpret_cast<uint8_t*>(d_workspace) + align_up(sizeof(unsigned) * 16 * static_cast<size_t>(S), 256);
+        uint8_t* g = reinterpret_cast<uint8_t*>(d_workspace) + image_slot_bytes(S) + align_up(image_table_bytes(S, H, W), 256);
         int rc = launch_rgb_to_gray(d_img, static_cast<int64_t>(S) * H * W, g, st);
         if (rc != CMDA_OK) return rc;
         gray = g;
     }
-    return launch_isr(gray, S, H, W, shift_pixel, direction, h_lut, thr, clip, d_out, slots, st);
+    return launch_isr(gray, S, H, W, shift_pixel, direction, h_lut, thr, clip, d_out, slots,
+                      image_slot_bytes(S) + image_table_bytes(S, H, W), st);
 }
 
 int cmda_denorm_rgb_to_gray_u8(const float* d_img, int S, int H, int W, const float* mean, const float* stdv,

@@ -665,7 +665,7 @@ band_partition3_kernel(const uint32_t* __restrict__ t, const uint16_t* __restric
     extern __shared__ __align__(16) unsigned char s_band_raw[];
     const int NB = g.nbuckets;
     unsigned* s_hist = reinterpret_cast<unsigned*>(s_band_raw);                 // [NB + 1]  bucket counts; bucket NB is the trash
-    unsigned* s_off = s_hist + NB + 1;                                          // [NB + 2]  exclusive offsets
+    unsigned* s_off = s_hist + ((NB + 1 + 3) & ~3);                             // [NB + 2]  exclusive offsets (16-byte aligned: 128-bit copy-out)
     unsigned* s_stage32 = s_off + ((NB + 2 + 3) & ~3);                          // [kBandChunk] (B > 1)
     unsigned char* s_stage8 = reinterpret_cast<unsigned char*>(s_stage32 + kBandChunk);     // [kBandChunk] (B > 1)
     unsigned short* s_stage16 = reinterpret_cast<unsigned short*>(s_stage32);   // [kBandChunk] (B == 1)
@@ -1513,7 +1513,8 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
         unsigned long long* ubins = reinterpret_cast<unsigned long long*>(bin_counts);
         if (max_chunks > 0) {
             const int fine = banded == 2 ? bg.nbuckets + 1 : (bg.nbuckets << bg.xsub_log2);     // second cut: + the trash bucket
-            const size_t shm = sizeof(unsigned) * (fine + ((fine + 1 + 3) & ~3)) + (B > 1 ? 5u : 2u) * static_cast<size_t>(kBandChunk);
+            const size_t shm = sizeof(unsigned) * ((banded == 2 ? ((fine + 3) & ~3) : fine) + ((fine + 1 + 3) & ~3)) +
+                               (B > 1 ? 5u : 2u) * static_cast<size_t>(kBandChunk);
             dim3 grid(static_cast<unsigned>(max_chunks), S);
 #define CMDA_BAND_PART1(HAS_T, VEC, PK)                                                                                        \
     do {                                                                                                                       \

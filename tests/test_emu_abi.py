@@ -614,3 +614,63 @@ def test_packed_p4_source_is_bit_identical_to_soa(L):
         base, counts = _vg_batch(L, t, x, y, p, [a0, b0], [a1, b1], rmap, None, H, W, B, FACTORED)
         got, c2 = _vg_batch_p4(L, stage, table, [0, pos_b], [a1 - a0, pos_b + b1 - b0], rmap, None, H, W, B, FACTORED, src=[a0, b0])
         assert np.array_equal(bits(got), bits(base)) and np.array_equal(c2, counts), density
+
+
+def test_table_driven_frame_pair_path(L):
+    """Images of >= 2^17 pixels take the table-driven apply pass (one evaluation per (now, front) byte pair and image,
+    then a gather; shared-memory band + global table for the pairs outside it): bit-exact against the oracle for
+    the three output selections, two different images per batch (a persistent CTA crosses from one image's table to
+    the next), with pairs far outside the band."""
+    from cmda_b200 import image_change as ic
+    from cmda_b200 import synth
+    H, W, S = 256, 512, 2
+    rng = np.random.default_rng(41)
+    now = np.stack([synth.make_frame_pair(H, W, seed=s)[0] for s in range(S)])
+    front = np.stack([synth.make_frame_pair(H, W, seed=s)[1] for s in range(S)])
+    now[0, :3, :] = rng.integers(0, 256, size=(3, W))              # |now - front| beyond the shared-memory band
+    front[1, 7, :] = 255 - now[1, 7, :]
+    lut = ic.log_lut_log_add(ic.log_add)
+    need = L.cmda_image_workspace_bytes(S, H, W, 1)
+    assert need > S * 4 * 65536 * 4                                 # the tables are part of the workspace at this size
+    ref_u8 = np.stack([O.get_image_change(now[s], front[s]) for s in range(S)])
+    ref_f32 = np.stack([O.get_image_change(now[s], front[s], return_float=True) for s in range(S)])
+    for want_f32, want_u8 in ((True, True), (False, True), (True, False)):
+        f32 = np.full((S, H, W), np.nan, dtype=np.float32)
+        u8 = np.full((S, H, W), 7, dtype=np.uint8)
+        ws = workspace(need)
+        assert L.cmda_logdiff_pair_u8(ptr(now), ptr(front), S, H, W, ptr(lut), float(np.float32(ic.threshold)),
+                                      float(np.float32(ic.clip_range)), ptr(f32) if want_f32 else None,
+                                      ptr(u8) if want_u8 else None, ptr(ws), need, None) == 0
+        if want_u8:
+            assert np.array_equal(u8, ref_u8)
+        if want_f32:
+            assert np.array_equal(bits(f32), bits(ref_f32))
+
+
+def test_table_driven_shift_pair_path(L):
+    """Images of >= 2^17 pixels take the table-driven ISR passes (log-difference table for pass 1, one value table per
+    (image, term) for pass 2, shared-memory bands + global tables for the pairs outside them): bit-exact against the
+    oracle for every direction and three parameter sets, batches of different images (smooth, random -- mostly outside
+    the band -- and two-level), shifts 1, 3 and a large one, a width that leaves the last column CTA half empty."""
+    from cmda_b200 import image_change as ic
+    from cmda_b200 import synth
+    H, W = 128, 1028
+    rng = np.random.default_rng(43)
+    imgs = np.stack([synth.make_smooth_image(H, W, seed=3), rng.integers(0, 256, size=(H, W), dtype=np.uint8),
+                     (rng.integers(0, 2, size=(H, W)) * 255).astype(np.uint8)])
+    S = imgs.shape[0]
+    need = L.cmda_image_workspace_bytes(S, H, W, 1)
+    assert need > S * 4 * 65536 * 4
+    for vr, thr_f, clip_f, shift in (((0.01, 1.01), 0.005, 0.1, 1), ((1, 100), 0.04, 0.2, 3), ((1e-5, 255 + 1e-5), 0.0, 0.04, 77)):
+        lut = ic.log_lut_val_range(tuple(float(v) for v in vr))
+        span = np.log(vr[1]) - np.log(vr[0])
+        thr, clip = np.float32(span * thr_f), np.float32(span * clip_f)
+        for name, code in DIRECTIONS.items():
+            out = np.full((S, 1, H, W), np.nan, dtype=np.float32)
+            ws = workspace(need)
+            assert L.cmda_isr_shift_u8(ptr(imgs), 1, S, H, W, shift, code, ptr(lut), float(thr), float(clip), ptr(out), ptr(ws), need,
+                                       None) == 0
+            for s in range(S):
+                want = O.get_image_change_from_pil(imgs[s], W, H, shift_pixel=shift, val_range=vr, _threshold=thr_f,
+                                                   _clip_range=clip_f, shift_direction=name)
+                assert np.array_equal(bits(out[s]), bits(want)), (vr, name, s)
