@@ -212,8 +212,8 @@ int events_vg_impl(const uint32_t* d_t, const uint16_t* d_x, const uint16_t* d_y
     }
     if (workspace_bytes < base_need) return CMDA_ERR_WORKSPACE;
     const int use_mode = resolve_mode(mode, total, S, H, W, B);
-    // the packed source feeds the sensor-space formulation only (FACTORED's RED kernel and the first BANDED cut)
-    if (packed && use_mode != CMDA_VOXEL_FACTORED && use_mode != CMDA_VOXEL_BANDED) return CMDA_ERR_UNSUPPORTED;
+    // the packed source feeds the sensor-space formulation only (FACTORED's RED kernel and the BANDED cuts)
+    if (packed && use_mode != CMDA_VOXEL_FACTORED && use_mode != CMDA_VOXEL_BANDED && use_mode != CMDA_VOXEL_BANDED2) return CMDA_ERR_UNSUPPORTED;
     if (use_mode == CMDA_VOXEL_TILED && !tiled_supported(H, W, B)) return CMDA_ERR_UNSUPPORTED;
     if (use_mode == CMDA_VOXEL_FACTORED && !factored_supported(H, W, B)) return CMDA_ERR_UNSUPPORTED;
     if (use_mode == CMDA_VOXEL_EXACT && !exact_supported(H, W, B)) return CMDA_ERR_UNSUPPORTED;

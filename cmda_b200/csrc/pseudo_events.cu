@@ -481,76 +481,42 @@ pair_apply_kernel(const uint8_t* __restrict__ now, const uint8_t* __restrict__ f
     }
 }
 
-// ------------------------------------------------------------------ K4 frame pair, table-driven apply (large images)
+// ------------------------------------------------------------------ K4 frame pair, table-driven u8 apply (large images)
 // The output of a pixel is a function of its (now, front) byte pair and of the image's four extrema only, and the
 // arithmetic kernels above are bound by instruction issue, not by memory (34 instructions per pixel:
-// profiles/r02_ncu_pseudo_summary.txt).  For images large enough to pay for it the per-pixel arithmetic is done ONCE
-// per byte pair instead: pair_table_kernel evaluates normalize_term (the same device function, hence the same
-// bits) for all 65 536 pairs of an image into a table in the workspace, and the apply pass becomes a gather:
-//   u8 output  : the 64 KB table of quantised values sits in shared memory whole;
-//   f32 output : the band |now - front| < kPairBand of the 256 KB table sits in shared memory (odd row stride:
-//                the bank of an entry follows the front byte, which varies across a warp), the rare pair outside the
-//                band is read from the table in global memory.
-// Persistent CTAs (one per SM, or two for the u8 table) walk an even share of the batch's 16-pixel groups and
-// refill their table when they cross into the next image.
-constexpr int kPairBand = 64;
-constexpr int kPairRow = 2 * kPairBand + 1;
+// profiles/r02_ncu_pseudo_summary.txt).  For the uint8 output of get_image_change (what the reference writes to its
+// PNGs, create_cityscapes_image_change.py:32-34) and images large enough to pay for it, the per-pixel arithmetic is
+// done ONCE per byte pair instead: pair_table_kernel evaluates normalize_term + the quantisation (the same device
+// functions, hence the same bits) for all 65 536 pairs of an image into a 64 KB table in the workspace, and the
+// apply pass is a gather from a copy of that table in shared memory (persistent CTAs, two per SM, walk an even share
+// of the batch's 16-pixel groups and refill the table when they cross into the next image): 0.100 vs 0.129 ms on C3.
+// The same idea for the float32 outputs (frame pair and shift pair: banded float tables in shared memory, global
+// table for the pairs outside the band) was built and measured in round 2 and dropped: it halves the instructions
+// per pixel but moves the bound to the load / store unit (gathers with 2-3-way bank conflicts, l1tex 60-75 % busy) and
+// ends up slower than the arithmetic kernels (frame pair 0.19 vs 0.154 ms, shift pair 0.28 vs 0.237 ms;
+// profiles/r02_pseudo_tables.txt).
 constexpr int kTabThreads = 1024;
-constexpr long long kTableMinPixels = 1LL << 17;      // below this the arithmetic kernels are cheaper than the tables
+#ifndef CMDA_TABLE_MIN_PIXELS
+#define CMDA_TABLE_MIN_PIXELS (1LL << 17)
+#endif
+constexpr long long kTableMinPixels = CMDA_TABLE_MIN_PIXELS;      // below this the arithmetic kernels are cheaper than the table
 
+constexpr int kTabRowsPerCta = 8;
 __global__ void __launch_bounds__(256)
-pair_table_kernel(LogLut lut_in, float thr, float clip, const unsigned* __restrict__ ws, float* __restrict__ tab32,
-                  uint8_t* __restrict__ tab8) {
+pair_table_kernel(LogLut lut_in, float thr, float clip, const unsigned* __restrict__ ws, uint8_t* __restrict__ tab8) {
     __shared__ float s_l[256];
+    __shared__ TermRange s_rng;
     s_l[threadIdx.x] = lut_in.v[threadIdx.x];
+    const int img = blockIdx.y, b = threadIdx.x;
+    if (threadIdx.x == 0) s_rng = decode_range(ws + static_cast<size_t>(img) * 16, thr, clip);
     __syncthreads();
-    const int img = blockIdx.y, a = blockIdx.x, b = threadIdx.x;
-    const TermRange rng = decode_range(ws + static_cast<size_t>(img) * 16, thr, clip);
-    const float r = normalize_term(__fsub_rn(s_l[a], s_l[b]), thr, clip, rng);        // d = log(now) - log(front), :21
-    const size_t i = (static_cast<size_t>(img) << 16) + (a << 8) + b;
-    if (tab32) tab32[i] = r;
-    if (tab8) tab8[i] = static_cast<uint8_t>(quantise_u8(r));
-}
-
-template <bool WANT_F32, bool WANT_U8>
-__global__ void __launch_bounds__(kTabThreads, 1)
-pair_apply_table_kernel(const uint8_t* __restrict__ now, const uint8_t* __restrict__ front, long long npx, int S,
-                        const float* __restrict__ tab32, float* __restrict__ out_f32, uint8_t* __restrict__ out_u8) {
-    extern __shared__ __align__(16) float s_tab[];          // [256][kPairRow]: entry (a, b) at a * kPairRow + (a - b + kPairBand)
-    const long long gpi = npx / 16, total = gpi * S;
-    const long long g_begin = total * blockIdx.x / gridDim.x, g_end = total * (blockIdx.x + 1) / gridDim.x;
-    for (long long img = g_begin / gpi; img < S && img * gpi < g_end; ++img) {
-        const long long lo = max(g_begin, img * gpi) - img * gpi, hi = min(g_end, (img + 1) * gpi) - img * gpi;
-        const float* tab = tab32 + (static_cast<size_t>(img) << 16);
-        __syncthreads();                                    // the previous image's gathers are done
-        for (int i = threadIdx.x; i < 256 * kPairRow; i += kTabThreads) {
-            const int a = i / kPairRow, k = i - a * kPairRow, b = a + kPairBand - k;
-            s_tab[i] = (b >= 0 && b < 256) ? __ldg(tab + (a << 8) + b) : 0.0f;
-        }
-        __syncthreads();
-        const uint4* pa = reinterpret_cast<const uint4*>(now + static_cast<size_t>(img) * npx);
-        const uint4* pb = reinterpret_cast<const uint4*>(front + static_cast<size_t>(img) * npx);
-        float* of = WANT_F32 ? out_f32 + static_cast<size_t>(img) * npx : nullptr;
-        uint4* ou = WANT_U8 ? reinterpret_cast<uint4*>(out_u8 + static_cast<size_t>(img) * npx) : nullptr;
-        for (long long gi = lo + threadIdx.x; gi < hi; gi += kTabThreads) {
-            const uint4 va = __ldg(pa + gi), vb = __ldg(pb + gi);
-            const unsigned wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
-            unsigned packed[4];
+    const TermRange rng = s_rng;
+    const float lb = s_l[b];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float r[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const unsigned a = (wa[q] >> (8 * j)) & 255u, b = (wb[q] >> (8 * j)) & 255u;
-                    const unsigned k = a - b + kPairBand;
-                    r[j] = k < 2u * kPairBand + 1u ? s_tab[a * kPairRow + k] : __ldg(tab + (a << 8) + b);
-                }
-                if (WANT_F32) stg_stream_f4(of + gi * 16 + q * 4, make_float4(r[0], r[1], r[2], r[3]));
-                if (WANT_U8)
-                    packed[q] = quantise_u8(r[0]) | (quantise_u8(r[1]) << 8) | (quantise_u8(r[2]) << 16) | (quantise_u8(r[3]) << 24);
-            }
-            if (WANT_U8) ou[gi] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-        }
+    for (int q = 0; q < kTabRowsPerCta; ++q) {
+        const int a = blockIdx.x * kTabRowsPerCta + q;
+        const float r = normalize_term(__fsub_rn(s_l[a], lb), thr, clip, rng);            // d = log(now) - log(front), :21
+        tab8[(static_cast<size_t>(img) << 16) + (a << 8) + b] = static_cast<uint8_t>(quantise_u8(r));
     }
 }
 
@@ -586,100 +552,6 @@ pair_apply_table8_kernel(const uint8_t* __restrict__ now, const uint8_t* __restr
             ou[gi] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
         }
     }
-}
-
-// ------------------------------------------------------------------ K5 shift pair, table-driven passes (large images)
-// Same idea for the shift pair: a term's value at a pixel is a function of the (pixel, shifted pixel) byte pair and of
-// the term's extrema.  Pass 1 gathers the log difference d = L[shifted] - L[pixel] from ONE table shared by the whole
-// batch (it depends on the log table only) instead of two table look-ups and a subtraction per term; pass 2 gathers
-// the finished, already halved / quartered term values from one table per (image, term).  The band |shifted - pixel|
-// <= kIsrBand of each table sits in shared memory (neighbouring pixels are close in value), pairs outside it are read
-// from the table in global memory.  Geometry and border handling are isr_vec_kernel's: 4 pixels per thread and row
-// from 32-bit loads and funnel shifts; a CTA is 256 column words x 4 interleaved rows and stays inside one image.
-template <int NT> __host__ __device__ constexpr int isr_band() { return NT == 4 ? 16 : 32; }
-
-__global__ void __launch_bounds__(256)
-isr_dtable_kernel(LogLut lut_in, float* __restrict__ dtab) {
-    __shared__ float s_l[256];
-    s_l[threadIdx.x] = lut_in.v[threadIdx.x];
-    __syncthreads();
-    dtab[(blockIdx.x << 8) + threadIdx.x] = __fsub_rn(s_l[threadIdx.x], s_l[blockIdx.x]);     // [pixel << 8 | shifted], utils.py:92
-}
-
-template <int NT>
-__global__ void __launch_bounds__(256)
-isr_table_build_kernel(const float* __restrict__ dtab, float thr, float clip, const unsigned* __restrict__ ws,
-                       float* __restrict__ tabs) {
-    const int img = blockIdx.y, a = blockIdx.x, b = threadIdx.x;
-    const float d = __ldg(dtab + (a << 8) + b);
-    const float inv = NT == 4 ? 0.25f : 0.5f;   // x / 4 and x / 2 are exact scalings
-#pragma unroll
-    for (int k = 0; k < NT; ++k) {
-        const TermRange rng = decode_range(ws + static_cast<size_t>(img) * 16 + k * 4, thr, clip);
-        tabs[((static_cast<size_t>(img) * NT + k) << 16) + (a << 8) + b] = __fmul_rn(normalize_term(d, thr, clip, rng), inv);
-    }
-}
-
-template <int DIRECTION, bool APPLY>
-__global__ void __launch_bounds__(kTabThreads, APPLY ? 1 : 2)
-isr_table_vec_kernel(const uint8_t* __restrict__ gray, int H, int W, int shift, const float* __restrict__ tabs,
-                     unsigned* __restrict__ ws, float* __restrict__ out) {
-    constexpr int NT = term_count(DIRECTION);
-    constexpr int HB = isr_band<NT>(), ROW = 2 * HB + 1, NTAB = APPLY ? NT : 1;
-    extern __shared__ __align__(16) float s_tab[];          // [NTAB][256][ROW]: entry (a, b) at a * ROW + (b - a + HB)
-    const int img = blockIdx.z;
-    const float* tab = tabs + (APPLY ? (static_cast<size_t>(img) * NT << 16) : 0);
-    for (int i = threadIdx.x; i < NTAB * 256 * ROW; i += kTabThreads) {
-        const int k = i / (256 * ROW), r = i - k * 256 * ROW, a = r / ROW, b = a - HB + (r - a * ROW);
-        s_tab[i] = (b >= 0 && b < 256) ? __ldg(tab + (static_cast<size_t>(k) << 16) + (a << 8) + b) : 0.0f;
-    }
-    __syncthreads();
-    const int words = W >> 2;
-    const int tx = threadIdx.x & 255, ty = threadIdx.x >> 8;
-    const int cw = blockIdx.x * 256 + tx;
-    const int per = (H + gridDim.y - 1) / gridDim.y;
-    const int r_begin = per * blockIdx.y, r_end = min(r_begin + per, H);
-    MinMaxAcc acc[NT];
-#pragma unroll
-    for (int k = 0; k < NT; ++k) acc[k].init();
-    if (cw < words) {
-        const ColShift left = col_shift_of(cw * 4, W, shift), right = col_shift_of(cw * 4, W, -shift);
-        const unsigned* img_w = reinterpret_cast<const unsigned*>(gray) + static_cast<size_t>(img) * H * words;
-        float4* out4 = APPLY ? reinterpret_cast<float4*>(out) + static_cast<size_t>(img) * H * words + cw : nullptr;
-        const long long shift_words = static_cast<long long>(shift) * words;
-        int r = r_begin + ty;
-        IsrRowWords<DIRECTION> cur{};
-        if (r < r_end) cur = isr_load_row<DIRECTION>(img_w + static_cast<size_t>(r) * words, cw, r, H, shift, shift_words, left, right);
-        for (; r < r_end; r += 4) {
-            IsrRowWords<DIRECTION> nxt = cur;
-            if (r + 4 < r_end)
-                nxt = isr_load_row<DIRECTION>(img_w + static_cast<size_t>(r + 4) * words, cw, r + 4, H, shift, shift_words, left, right);
-            const unsigned base_w = cur.base;
-            float res[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll
-            for (int k = 0; k < NT; ++k) {
-                const int dir = term_dir(DIRECTION, k);       // a constant once the loop is unrolled
-                unsigned shw = cur.a[k];
-                if (dir < 2) {                                // column shift: funnel the two words, border bytes stay unshifted
-                    const ColShift& cs = dir == 0 ? left : right;
-                    shw = (__funnelshift_r(cur.a[k], cur.b[k], cs.funnel) & cs.mask) | (base_w & ~cs.mask);
-                }
-                const float* st = s_tab + (APPLY ? k * 256 * ROW : 0);
-                const float* gt = tab + (APPLY ? (static_cast<size_t>(k) << 16) : 0);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const unsigned a = (base_w >> (8 * j)) & 255u, b = (shw >> (8 * j)) & 255u;
-                    const unsigned kk = b - a + HB;
-                    const float v = kk < static_cast<unsigned>(ROW) ? st[a * ROW + kk] : __ldg(gt + (a << 8) + b);
-                    if (APPLY) res[j] = (k == 0) ? v : __fadd_rn(res[j], v);                  // utils.py:137 / 151, left to right
-                    else acc[k].add(v);
-                }
-            }
-            if (APPLY) stg_stream_f4(reinterpret_cast<float*>(out4 + static_cast<size_t>(r) * words), make_float4(res[0], res[1], res[2], res[3]));
-            cur = nxt;
-        }
-    }
-    if (!APPLY) flush_minmax<NT>(acc, ws + static_cast<size_t>(img) * 16);
 }
 
 // ------------------------------------------------------------------ PIL 'L'
@@ -802,51 +674,13 @@ size_t image_slot_bytes(int S);
 size_t image_table_bytes(int S, int H, int W);
 
 int launch_isr(const uint8_t* gray, int S, int H, int W, int shift, int direction, const float* h_lut, float thr,
-               float clip, float* out, unsigned* ws, size_t ws_bytes, cudaStream_t s) {
+               float clip, float* out, unsigned* ws, size_t /*ws_bytes*/, cudaStream_t s) {
     LogLut lut;
     for (int i = 0; i < 256; ++i) lut.v[i] = h_lut[i];
     const TermList terms = terms_of(direction);
     const long long npx = static_cast<long long>(H) * W;
     CMDA_CUDA_TRY(cudaMemsetAsync(ws, 0, sizeof(unsigned) * 16 * S, s));
     if ((W % 4) == 0 && W >= 8 && (reinterpret_cast<uintptr_t>(gray) & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
-        if (S <= 65535 && image_table_bytes(S, H, W) != 0 && ws_bytes >= image_slot_bytes(S) + image_table_bytes(S, H, W)) {
-            // table-driven passes: the log-difference table of the batch, then one value table per (image, term)
-            float* tabs = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + image_slot_bytes(S));
-            float* dtab = tabs + static_cast<size_t>(S) * 4 * 65536;
-            const int gx = (W / 4 + 255) / 256;
-            // rows of an image are split over gy CTAs: the split that leaves the smallest idle tail on 148 SMs
-            int gy = 1;
-            double best = -1.0;
-            for (int c = 1; c <= 64 && H / c >= 16; ++c) {
-                const long long ctas = static_cast<long long>(gx) * c * S;
-                const double eff = static_cast<double>(ctas) / (static_cast<double>((ctas + 147) / 148) * 148.0);
-                if (ctas >= 148 && eff > best + 1e-9) { best = eff; gy = c; }
-            }
-            if (best < 0.0) gy = H / 16 > 0 ? (H / 16 < 64 ? H / 16 : 64) : 1;
-            dim3 grid(gx, gy, S);
-            isr_dtable_kernel<<<256, 256, 0, s>>>(lut, dtab);
-#define CMDA_ISR_TAB(D)                                                                                                    \
-    case D: {                                                                                                              \
-        constexpr int NT = term_count(D), ROW = 2 * isr_band<NT>() + 1;                                                     \
-        const int shm1 = 256 * ROW * static_cast<int>(sizeof(float)), shm2 = NT * shm1;                                     \
-        CMDA_CUDA_TRY(cudaFuncSetAttribute(isr_table_vec_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, shm1)); \
-        CMDA_CUDA_TRY(cudaFuncSetAttribute(isr_table_vec_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, shm2));  \
-        isr_table_vec_kernel<D, false><<<grid, kTabThreads, shm1, s>>>(gray, H, W, shift, dtab, ws, out);                   \
-        isr_table_build_kernel<NT><<<dim3(256, S), 256, 0, s>>>(dtab, thr, clip, ws, tabs);                                 \
-        isr_table_vec_kernel<D, true><<<grid, kTabThreads, shm2, s>>>(gray, H, W, shift, tabs, ws, out);                    \
-    } break
-            switch (direction) {
-                CMDA_ISR_TAB(CMDA_DIR_RIGHTDOWN);
-                CMDA_ISR_TAB(CMDA_DIR_RIGHTUP);
-                CMDA_ISR_TAB(CMDA_DIR_LEFTDOWN);
-                CMDA_ISR_TAB(CMDA_DIR_LEFTUP);
-                CMDA_ISR_TAB(CMDA_DIR_ALL);
-                default: return CMDA_ERR_BAD_ARG;
-            }
-#undef CMDA_ISR_TAB
-            CMDA_LAUNCH_CHECK();
-            return CMDA_OK;
-        }
         // vector fast path
         const int gx = (W / 4 + 255) / 256;
         const long long n_rows = static_cast<long long>(S) * H;
@@ -900,13 +734,12 @@ int launch_isr(const uint8_t* gray, int S, int H, int W, int shift, int directio
     return CMDA_OK;
 }
 
-// Workspace of the image entry points: 16 words of min / max slots per image, then (large images only) the per-image
-// pair tables of the table-driven apply passes: up to four float32 tables (one per ISR term; the frame pair uses one
-// plus its 64 KB table of quantised values), and one table of log differences shared by the batch (ISR pass 1).
+// Workspace of the image entry points: 16 words of min / max slots per image, then (large images only) the 64 KB
+// table of quantised values per image of the frame pair's table-driven uint8 pass.
 size_t image_slot_bytes(int S) { return align_up(sizeof(unsigned) * 16 * static_cast<size_t>(S), 256); }
 size_t image_table_bytes(int S, int H, int W) {
     if (static_cast<long long>(H) * W < kTableMinPixels) return 0;
-    return static_cast<size_t>(S) * 4 * 65536 * sizeof(float) + 65536 * sizeof(float);
+    return static_cast<size_t>(S) * 65536;
 }
 
 int launch_pair(const uint8_t* now, const uint8_t* front, int S, int H, int W, const float* h_lut, float thr,
@@ -917,7 +750,7 @@ int launch_pair(const uint8_t* now, const uint8_t* front, int S, int H, int W, c
     CMDA_CUDA_TRY(cudaMemsetAsync(ws, 0, sizeof(unsigned) * 16 * S, s));
     const bool all_vec = (npx % 16 == 0) && ((reinterpret_cast<uintptr_t>(now) & 15) == 0) && ((reinterpret_cast<uintptr_t>(front) & 15) == 0) &&
                          (!out_f32 || (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0) && (!out_u8 || (reinterpret_cast<uintptr_t>(out_u8) & 15) == 0);
-    const bool tables = all_vec && S <= 32768 && image_table_bytes(S, H, W) != 0 &&
+    const bool tables = all_vec && out_f32 == nullptr && S <= 32768 && image_table_bytes(S, H, W) != 0 &&
                         ws_bytes >= image_slot_bytes(S) + image_table_bytes(S, H, W);
     for (int s0 = 0; s0 < S; s0 += 32768) {
         const int sn = (S - s0) < 32768 ? (S - s0) : 32768;
@@ -933,24 +766,11 @@ int launch_pair(const uint8_t* now, const uint8_t* front, int S, int H, int W, c
         unsigned* w = ws + static_cast<size_t>(s0) * 16;
         pair_minmax_kernel<<<grid, kImgThreads, 0, s>>>(now + off, front + off, npx, vec, lut, thr, clip, w);
         if (tables) {
-            // one evaluation per byte pair and image, then a gather per pixel
-            float* tab32 = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + image_slot_bytes(S));
-            uint8_t* tab8 = reinterpret_cast<uint8_t*>(tab32 + static_cast<size_t>(S) * 65536);
-            const bool only_u8 = out_f32 == nullptr;
-            pair_table_kernel<<<dim3(256, sn), 256, 0, s>>>(lut, thr, clip, w, only_u8 ? nullptr : tab32, only_u8 ? tab8 : nullptr);
-            if (only_u8) {
-                CMDA_CUDA_TRY(cudaFuncSetAttribute(pair_apply_table8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-                pair_apply_table8_kernel<<<148 * 2, kTabThreads, 65536, s>>>(now, front, npx, sn, tab8, out_u8);
-            } else {
-                const int shm = 256 * kPairRow * static_cast<int>(sizeof(float));
-                if (out_u8) {
-                    CMDA_CUDA_TRY(cudaFuncSetAttribute(pair_apply_table_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, shm));
-                    pair_apply_table_kernel<true, true><<<148, kTabThreads, shm, s>>>(now, front, npx, sn, tab32, out_f32, out_u8);
-                } else {
-                    CMDA_CUDA_TRY(cudaFuncSetAttribute(pair_apply_table_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, shm));
-                    pair_apply_table_kernel<true, false><<<148, kTabThreads, shm, s>>>(now, front, npx, sn, tab32, out_f32, out_u8);
-                }
-            }
+            // uint8 output only: one evaluation per byte pair and image, then a gather per pixel
+            uint8_t* tab8 = reinterpret_cast<uint8_t*>(ws) + image_slot_bytes(S);
+            pair_table_kernel<<<dim3(256 / kTabRowsPerCta, sn), 256, 0, s>>>(lut, thr, clip, w, tab8);
+            CMDA_CUDA_TRY(cudaFuncSetAttribute(pair_apply_table8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+            pair_apply_table8_kernel<<<148 * 2, kTabThreads, 65536, s>>>(now, front, npx, sn, tab8, out_u8);
         } else if (vec)
             pair_apply_kernel<true><<<grid, kImgThreads, 0, s>>>(now + off, front + off, npx, lut, thr, clip, w,
                                                                  out_f32 ? out_f32 + off : nullptr,

@@ -172,7 +172,7 @@ int cmda_events_vg_batch_planned(const uint32_t* d_t, const uint16_t* d_x, const
  *                        the windows' events (then h_win_src[s] = store index of window s's first event)
  *  d_ms_to_idx / h_ms_to_idx   the table on the device and a host copy (the per-window bucket bracket is found on
  *                        the host, the per-event bucket on the device); h_ms_to_idx[0] must be 0
- *  mode                  AUTO, FACTORED or BANDED (the sensor-space formulation); others: CMDA_ERR_UNSUPPORTED
+ *  mode                  AUTO, FACTORED, BANDED or BANDED2 (the sensor-space formulation); others: CMDA_ERR_UNSUPPORTED
  *  everything else as cmda_events_vg_batch_planned; the workspace size is the same function of (events, S, ...). */
 int cmda_pack_events_p4(const uint32_t* d_t, const uint16_t* d_x, const uint16_t* d_y, const uint8_t* d_p, int64_t n,
                         uint32_t t_base_us, int64_t n_ms, uint32_t* d_rec, int64_t* d_ms_to_idx, int32_t* d_status,

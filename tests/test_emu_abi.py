@@ -600,7 +600,7 @@ def test_packed_p4_source_is_bit_identical_to_soa(L):
         for tt in (t, dup):
             rec_t, table_t, _ = packed.pack_p4(tt, x, y, p)
             for B in (1, 3, 5):
-                for mode in (FACTORED, BANDED):
+                for mode in (FACTORED, BANDED, BANDED2):
                     base, counts = _vg_batch(L, tt, x, y, p, starts, fins, rmap, None, H, W, B, mode)
                     got, c2 = _vg_batch_p4(L, rec_t, table_t, starts, fins, rmap, None, H, W, B, mode)
                     assert np.array_equal(bits(got), bits(base)) and np.array_equal(c2, counts), (density, B, mode)
@@ -617,10 +617,10 @@ def test_packed_p4_source_is_bit_identical_to_soa(L):
 
 
 def test_table_driven_frame_pair_path(L):
-    """Images of >= 2^17 pixels take the table-driven apply pass (one evaluation per (now, front) byte pair and image,
-    then a gather; shared-memory band + global table for the pairs outside it): bit-exact against the oracle for
-    the three output selections, two different images per batch (a persistent CTA crosses from one image's table to
-    the next), with pairs far outside the band."""
+    """Images of >= 2^17 pixels take the table-driven uint8 apply pass when only the uint8 output is asked for (one
+    evaluation per (now, front) byte pair and image, then a gather from a 64 KB table in shared memory): bit-exact
+    against the oracle for the three output selections (the float32 ones use the arithmetic kernels), two different
+    images per batch (a persistent CTA crosses from one image's table to the next)."""
     from cmda_b200 import image_change as ic
     from cmda_b200 import synth
     H, W, S = 256, 512, 2
@@ -631,7 +631,7 @@ def test_table_driven_frame_pair_path(L):
     front[1, 7, :] = 255 - now[1, 7, :]
     lut = ic.log_lut_log_add(ic.log_add)
     need = L.cmda_image_workspace_bytes(S, H, W, 1)
-    assert need > S * 4 * 65536 * 4                                 # the tables are part of the workspace at this size
+    assert need >= S * 65536                                        # the tables are part of the workspace at this size
     ref_u8 = np.stack([O.get_image_change(now[s], front[s]) for s in range(S)])
     ref_f32 = np.stack([O.get_image_change(now[s], front[s], return_float=True) for s in range(S)])
     for want_f32, want_u8 in ((True, True), (False, True), (True, False)):
@@ -645,32 +645,3 @@ def test_table_driven_frame_pair_path(L):
             assert np.array_equal(u8, ref_u8)
         if want_f32:
             assert np.array_equal(bits(f32), bits(ref_f32))
-
-
-def test_table_driven_shift_pair_path(L):
-    """Images of >= 2^17 pixels take the table-driven ISR passes (log-difference table for pass 1, one value table per
-    (image, term) for pass 2, shared-memory bands + global tables for the pairs outside them): bit-exact against the
-    oracle for every direction and three parameter sets, batches of different images (smooth, random -- mostly outside
-    the band -- and two-level), shifts 1, 3 and a large one, a width that leaves the last column CTA half empty."""
-    from cmda_b200 import image_change as ic
-    from cmda_b200 import synth
-    H, W = 128, 1028
-    rng = np.random.default_rng(43)
-    imgs = np.stack([synth.make_smooth_image(H, W, seed=3), rng.integers(0, 256, size=(H, W), dtype=np.uint8),
-                     (rng.integers(0, 2, size=(H, W)) * 255).astype(np.uint8)])
-    S = imgs.shape[0]
-    need = L.cmda_image_workspace_bytes(S, H, W, 1)
-    assert need > S * 4 * 65536 * 4
-    for vr, thr_f, clip_f, shift in (((0.01, 1.01), 0.005, 0.1, 1), ((1, 100), 0.04, 0.2, 3), ((1e-5, 255 + 1e-5), 0.0, 0.04, 77)):
-        lut = ic.log_lut_val_range(tuple(float(v) for v in vr))
-        span = np.log(vr[1]) - np.log(vr[0])
-        thr, clip = np.float32(span * thr_f), np.float32(span * clip_f)
-        for name, code in DIRECTIONS.items():
-            out = np.full((S, 1, H, W), np.nan, dtype=np.float32)
-            ws = workspace(need)
-            assert L.cmda_isr_shift_u8(ptr(imgs), 1, S, H, W, shift, code, ptr(lut), float(thr), float(clip), ptr(out), ptr(ws), need,
-                                       None) == 0
-            for s in range(S):
-                want = O.get_image_change_from_pil(imgs[s], W, H, shift_pixel=shift, val_range=vr, _threshold=thr_f,
-                                                   _clip_range=clip_f, shift_direction=name)
-                assert np.array_equal(bits(out[s]), bits(want)), (vr, name, s)

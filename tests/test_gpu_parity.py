@@ -744,7 +744,7 @@ def test_packed_store_bit_identical_to_soa(cm, bins):
     starts = np.array([0, 3, 1_000_001, 777, n - 1, 5000, 0])
     fins = np.array([n - 1, 2_000_000, 2_400_000, 776, n - 1, 4_000, n - 1])
     assert int(np.clip(fins + 1 - starts, 0, None).sum()) > (8 << 20)
-    for mode in ("factored", "banded", "auto"):
+    for mode in ("factored", "banded", "banded2", "auto"):
         a, ra, ca = cm.events_vg_batch(store, starts, fins, bins, mode=mode, return_raw=True, return_bin_counts=True)
         b, rb, cb = cm.events_vg_batch(pstore, starts, fins, bins, mode=mode, return_raw=True, return_bin_counts=True)
         assert np.array_equal(bits(a), bits(b)) and np.array_equal(bits(ra), bits(rb)) and torch.equal(ca, cb), mode
