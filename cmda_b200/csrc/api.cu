@@ -62,15 +62,17 @@ static size_t acc_bytes(int S, int H, int W, int B) {
 }
 
 // AUTO: FACTORED wherever the sensor-space formulation applies.  Its stage A is the L2 RED kernel, except for
-// B == 1 (the shipped events_bins) on large batches, where the BANDED cut (band partition + shared-memory counting,
-// bit-identical R) is faster: measured on C2 0.39 vs 0.50 ms per 80 M events (profiles/r02_*); below the threshold
-// the banded passes' fixed cost per (window, band) item loses to the 2-6 us the RED kernel needs.
+// B == 1 (the shipped events_bins) on large batches, where the BANDED stage A with the second cut of the partition
+// pass (band partition + shared-memory counting, bit-identical R) is faster: measured on C2 0.443 vs 0.536 ms per
+// 80 M events (first cut 0.463; profiles/r02_banded_phases.txt); at B = 5 the three forms are within 5 % of each
+// other (0.77 / 0.80 / 0.81 ms) and the RED kernel stays.  Below the threshold the banded passes' fixed cost per
+// (window, band) item loses to the 2-6 us the RED kernel needs.
 constexpr long long kAutoBandedMinEvents = 8LL << 20;
 static int resolve_mode(int mode, long long total_events, int S, int H, int W, int B) {
     (void)S;
     if (mode != CMDA_VOXEL_AUTO) return mode;
     if (!factored_supported(H, W, B)) return CMDA_VOXEL_GLOBAL;
-    if (B == 1 && total_events >= kAutoBandedMinEvents && banded_supported(H, W, B)) return CMDA_VOXEL_BANDED;
+    if (B == 1 && total_events >= kAutoBandedMinEvents && banded_supported(H, W, B)) return CMDA_VOXEL_BANDED2;
     return CMDA_VOXEL_FACTORED;
 }
 

@@ -630,12 +630,13 @@ def test_hot_pixel_window_is_guarded(cm, bins):
 
 
 def test_auto_mode_resolution(cm):
-    """AUTO: FACTORED (RED stage A) in general; the BANDED cut for B = 1 on large batches, where it is faster."""
+    """AUTO: FACTORED (RED stage A) in general; the BANDED stage A (second cut of the partition pass) for B = 1 on large
+    batches, where it is faster."""
     from cmda_b200 import _lib
     L = cm.lib()
     H, W = 480, 640
     assert L.cmda_events_vg_resolved_mode(80_000_000, 16, H, W, 5, _lib.VOXEL_AUTO) == _lib.VOXEL_FACTORED
-    assert L.cmda_events_vg_resolved_mode(80_000_000, 16, H, W, 1, _lib.VOXEL_AUTO) == _lib.VOXEL_BANDED
+    assert L.cmda_events_vg_resolved_mode(80_000_000, 16, H, W, 1, _lib.VOXEL_AUTO) == _lib.VOXEL_BANDED2
     assert L.cmda_events_vg_resolved_mode(660_000, 2, H, W, 1, _lib.VOXEL_AUTO) == _lib.VOXEL_FACTORED
 
 
