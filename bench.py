@@ -245,6 +245,44 @@ def reference_rate(specs, units_per_step, steps, warmup, unit="Mevents/s", what=
                        f"processes x {max(1, cores // nw)} torch threads, {sum(times):.1f} s wall"}, times)
 
 
+ISR_SHIPPED = dict(shift_pixel=1, val_range=(0.01, 1.01), _threshold=0.005, _clip_range=0.1)      # configs/fusion/cs2dsec...:46-49
+C3_IMAGES, C3_H, C3_W = 32, 1024, 2048
+C5_SAMPLES, C5_EVENTS = 2, 330_000
+
+
+def reference_side_legs(args, steps=1, warmup=1):
+    """CPU baselines beside C2, C3 and C5 from ONE pool of worker processes running the reference's own functions
+    (oracle/_ref): get_events_vg on the step's 16 windows; get_image_change / get_image_change_from_pil on C3's 32
+    images of 2048x1024 (create_cityscapes_image_change.py:16-35, utils.py:108-152); per sample of C5 the event
+    window + the loader's crop / flip / resize / x3 (dsec.py:286-320) + the two 512x512 ISR calls of a train step
+    (dsec.py:258-261, dacs.py:741-744).  Returns a dict of cpu_baseline entries."""
+    from cmda_b200 import synth
+    from oracle import ref_runner
+    cores = host_cores()
+    specs = reference_event_specs(args)
+    specs += [dict(kind="pair", H=C3_H, W=C3_W, seed=synth.seed_for(3, k)) for k in range(C3_IMAGES)]
+    specs += [dict(kind="isr", H=C3_H, W=C3_W, seed=synth.seed_for(3, 100 + k), parms=dict(ISR_SHIPPED, shift_direction="rightdown"))
+              for k in range(C3_IMAGES)]
+    specs += [dict(kind="c5", n=C5_EVENTS, H=H, W=W, bins=1, seed=synth.seed_for(5, k), map_seed=synth.seed_for(5, 99),
+                   post=(37, 61, 400, 400, 512, 512), parms=ISR_SHIPPED) for k in range(C5_SAMPLES)]
+    out = {}
+    with ref_runner.WorkerPool(specs, cores=cores) as pool:
+        nw = pool.n_workers
+        for key, kind, units, unit, what in (
+                ("events", "events_vg", WINDOWS_PER_GPU * args.events / 1e6, "Mevents/s", f"{WINDOWS_PER_GPU} windows x {args.events} events"),
+                ("frame_pair", "pair", C3_IMAGES, "images/s", f"{C3_IMAGES} pairs of {C3_W}x{C3_H}"),
+                ("shift_pair_isr", "isr", C3_IMAGES, "images/s", f"{C3_IMAGES} images of {C3_W}x{C3_H}"),
+                ("train_step_input_path", "c5", C5_SAMPLES, "samples/s", f"{C5_SAMPLES} samples (330 k-event window + crop/flip/resize + 2 ISR of 512x512)")):
+            n_steps = (2 if key == "events" else 3) * steps
+            for _ in range(warmup):
+                pool.step(kind)
+            times = [pool.step(kind) for _ in range(n_steps)]
+            out[key] = {"value": units * len(times) / sum(times), "unit": unit, "cores": cores, "kind": "reference",
+                        "sample": f"{len(times)} steps x {what}, the reference's own functions (oracle/_ref) in {nw} worker "
+                                  f"processes x {max(1, cores // nw)} torch threads, {sum(times):.1f} s wall"}
+    return out
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path on the box's host cores -- the
     unmodified Python of oracle/_ref (dsec.py:341-366 get_events_vg: slice, t-normalise, rectify_map gather,
@@ -376,6 +414,95 @@ def train_step_input_leg(dev, steps=20, warmup=3):
     return res
 
 
+# ------------------------------------------------------------------------------------ C4: strong scaling by sample
+C4_WINDOWS, C4_EVENTS = 64, 20_000_000
+
+
+def c4_strong_scaling_leg(args, rank, world, dev, barrier, steps=3, warmup=1):
+    """BASELINE config C4 as stated: 64 dense night windows of 20 M events each, sharded BY SAMPLE over the ranks
+    (longest-processing-time greedy, cmda_b200.sharding.shard_lpt: what the reference's DistributedSampler does with
+    whole samples, builder.py:135-141), no collective on the data path.  STRONG scaling: the 64 windows are the job at
+    every N.  Window k is generated on the device from a seed of k alone, so every N voxelises the same 64 windows.
+    Returns this rank's (seconds per pass, windows, events); the caller takes the max over ranks."""
+    import torch
+    import cmda_b200
+    from cmda_b200 import sharding, synth
+    mine = sharding.shard_lpt([C4_EVENTS] * C4_WINDOWS, world, rank)
+    ts, xs, ys, ps = [], [], [], []
+    for k in mine:
+        g = torch.Generator(device=dev).manual_seed(40_000 + k)
+        ts.append((torch.sort(torch.randint(0, WINDOW_US, (C4_EVENTS,), generator=g, device=dev, dtype=torch.int32))[0]
+                   + (10_000_000 + k * WINDOW_US)).view(torch.uint32))
+        xs.append(torch.randint(0, W, (C4_EVENTS,), generator=g, device=dev, dtype=torch.int16).view(torch.uint16))
+        ys.append(torch.randint(0, H, (C4_EVENTS,), generator=g, device=dev, dtype=torch.int16).view(torch.uint16))
+        ps.append(torch.randint(0, 2, (C4_EVENTS,), generator=g, device=dev, dtype=torch.uint8))
+    rmap = synth.make_rectify_map(H, W, seed=synth.seed_for(4, 999))
+    store = cmda_b200.EventStore(torch.cat(ts), torch.cat(xs), torch.cat(ys), torch.cat(ps), rmap, height=H, width=W, device=dev)
+    del ts, xs, ys, ps
+    n = len(mine)
+    starts = np.arange(n, dtype=np.int64) * C4_EVENTS
+    fins = starts + C4_EVENTS - 1
+    group = 4                                   # windows per call: 80 M events, like the C2 step
+    out = torch.empty((group, args.bins, H, W), dtype=torch.float32, device=dev)
+
+    def one_pass():
+        for g0 in range(0, n, group):
+            g1 = min(g0 + group, n)
+            cmda_b200.events_vg_batch(store, starts[g0:g1], fins[g0:g1], args.bins, mode=args.mode, out=out[:g1 - g0])
+
+    for _ in range(warmup):
+        one_pass()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one_pass()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    del store, out
+    return ms, n
+
+
+def model_step_leg(dev, steps=3, warmup=2):
+    """The consumer of the path, for scale: one MiT-b5 encoder + MLP head (SegFormer-B5; the reference's
+    FusionEncoderDecoder runs two such backbones, encoder_decoder.py:626-1003) in PLAIN PyTorch -- transformers'
+    SegformerForSemanticSegmentation with random weights -- forward + backward, float32, batch 2 x 3 x 512 x 512
+    (samples_per_gpu = 2).  Not part of the path and not optimised here: printed next to C5 as SURVEY.md 8(d) asks."""
+    try:
+        import torch
+        from transformers import SegformerConfig, SegformerForSemanticSegmentation
+        cfg = SegformerConfig(num_channels=3, depths=[3, 6, 40, 3], hidden_sizes=[64, 128, 320, 512], num_attention_heads=[1, 2, 5, 8],
+                              sr_ratios=[8, 4, 2, 1], decoder_hidden_size=768, num_labels=19)
+        torch.manual_seed(0)
+        model = SegformerForSemanticSegmentation(cfg).to(dev).train()
+        x = torch.randn((2, 3, 512, 512), device=dev)
+        y = torch.randint(0, 19, (2, 512, 512), device=dev)
+
+        def step():
+            model.zero_grad(set_to_none=True)
+            out = model(pixel_values=x, labels=y)
+            out.loss.backward()
+
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / steps
+        n_params = sum(p.numel() for p in model.parameters())
+        del model, x, y
+        torch.cuda.empty_cache()
+        return {"ms_per_step": ms, "what": "plain PyTorch SegFormer-B5 (one MiT-b5 backbone + MLP head, random init), forward + backward, "
+                                           "float32, batch 2 x 3 x 512 x 512", "parameters": n_params}
+    except Exception as e:      # noqa: BLE001 -- an informational leg must not cost the bench line
+        return {"error": f"{type(e).__name__}: {e}"[:200]}
+
+
 # ------------------------------------------------------------------------------------ variants of the headline
 def variants_leg(store, starts, fins, rmap, args, dev, steps=10, warmup=3):
     """SURVEY.md 8(d)'s other device-resident cases, reported beside the headline (same kernels, same timing
@@ -414,7 +541,15 @@ def variants_leg(store, starts, fins, rmap, args, dev, steps=10, warmup=3):
         # the opt-in BANDED stage A (band partition + shared-memory accumulation instead of one L2 atomic per event;
         # bit-identical output): the same step, for the record
         res["C2_banded_stage_A"] = timed(store, starts, fins, args.bins, mode="banded")
+        res["C2_banded2_stage_A"] = timed(store, starts, fins, args.bins, mode="banded2")
+        res["C2_bins_1_red_stage_A"] = timed(store, starts, fins, 1, mode="factored")
         res["C2_bins_1_banded_stage_A"] = timed(store, starts, fins, 1, mode="banded")
+    # the same step from the device-resident PACKED store (4 bytes per event instead of 9; bit-identical output)
+    pstore = cmda_b200.PackedEventStore.from_event_store(store)
+    res["C2_packed_store"] = timed(pstore, starts, fins, args.bins)
+    if args.bins != 1:
+        res["C2_bins_1_packed_store"] = timed(pstore, starts, fins, 1)
+    del pstore
     maps = np.stack([rmap] + [synth.make_rectify_map(H, W, seed=synth.seed_for(2, 900 + k)) for k in range(4)])
     store5 = cmda_b200.EventStore(store.t, store.x, store.y, store.p, maps, height=H, width=W, device=dev, plan=False)
     res["C2_five_maps"] = timed(store5, starts, fins, args.bins, map_ids=[s % 5 for s in range(S)])
@@ -448,10 +583,9 @@ def variants_leg(store, starts, fins, rmap, args, dev, steps=10, warmup=3):
 
 # ------------------------------------------------------------------------------------ experimental: BANDED2
 def banded2_leg(args):
-    """The second cut of the BANDED stage A (mode "banded2") on the C2 step, in a process of its own
-    (tools/banded2_check.py): its logic was verified on the CPU emulation (tests/test_emu_*.py) but it had not run on
-    hardware when round 1 ended.  Checked against FACTORED (bit-identical or not) and timed next to FACTORED and the
-    first cut; whatever happens there, this process, its CUDA context and the bench line are untouched."""
+    """The three forms of stage A (RED kernel, BANDED, BANDED with the second cut of the partition pass) on the C2 step with
+    prebuilt map plans, in a process of its own (tools/banded2_check.py): bit-identity of the banded forms against
+    FACTORED and ms per step of each."""
     import subprocess
     cmd = [sys.executable, os.path.join(ROOT, "tools", "banded2_check.py"), "--events", str(args.events), "--bins", str(args.bins)]
     if args.bins != 1:
@@ -624,13 +758,21 @@ def run_gpu(args, rank, local_rank, world):
     del store_r, d_out2
     e2e_ms, h2d, d2h, same = e2e_legs["p4"]["ms"], e2e_legs["p4"]["h2d"], e2e_legs["p4"]["d2h"], e2e_legs["p4"]["same"]
 
+    # ---- C4: 64 x 20 M-event windows sharded by sample, strong scaling ---------------------------------
+    c4_ms, c4_n = (0.0, 0)
+    if not args.no_c4:
+        del store
+        torch.cuda.empty_cache()
+        c4_ms, c4_n = c4_strong_scaling_leg(args, rank, world, dev, barrier)
+        store = cmda_b200.EventStore(t, x, y, p, rmap, height=H, width=W, device=dev, plan=False)
+
     # ---- max over ranks ----------------------------------------------------------------------
-    times = torch.tensor([ms_total, e2e_ms, planned_ms, e2e_legs["soa"]["ms"], e2e_legs["resident"]["ms"]], dtype=torch.float64,
+    times = torch.tensor([ms_total, e2e_ms, planned_ms, e2e_legs["soa"]["ms"], e2e_legs["resident"]["ms"], c4_ms], dtype=torch.float64,
                          device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     ms_total, e2e_ms, planned_ms = float(times[0]), float(times[1]), float(times[2])
-    e2e_legs["soa"]["ms"], e2e_legs["resident"]["ms"] = float(times[3]), float(times[4])
+    e2e_legs["soa"]["ms"], e2e_legs["resident"]["ms"], c4_ms = float(times[3]), float(times[4]), float(times[5])
 
     if rank == 0:
         ms_per_step = ms_total / args.steps
@@ -670,24 +812,30 @@ def run_gpu(args, rank, local_rank, world):
                                        "frac": alg / (ms_per_step * 1e-3) / 1e9 / peak}}
         # CPU baseline on a bounded sample of the same workload (rank 0, N=1 only): the reference's own Python
         # (oracle/_ref) in worker processes, same protocol as `--impl reference`; the C port as a second figure
-        cpu = cpu_port = None
+        cpu = cpu_port = side = None
         if world == 1 and not args.no_cpu_baseline:
             from oracle import ref_runner
             cpu_port = cpu_port_rate(args)
             if ref_runner.available():
-                cpu, _ = reference_rate(reference_event_specs(args), events_per_step, steps=2, warmup=1)
+                side = reference_side_legs(args)
+                cpu = side.pop("events")
             else:
                 cpu = cpu_port
         pseudo = c5 = variants = None
         if world == 1 and not args.no_pseudo:
             pseudo = pseudo_events_leg(dev, peak)
             c5 = train_step_input_leg(dev)
+            c5["model_step"] = model_step_leg(dev)
+            if side:       # the reference's CPU path beside each GPU number (BASELINE.json: north_star)
+                for k in ("frame_pair", "shift_pair_isr"):
+                    pseudo["cpu_baseline_" + k] = side[k]
+                c5["cpu_baseline"] = side["train_step_input_path"]
         if world == 1 and not args.no_variants:
-            del pipe, host_out
+            del host_out
             variants = variants_leg(store, starts, fins, rmap, args, dev)
         experimental = None
         if world == 1 and not args.no_variants and args.mode in ("auto", "factored"):
-            experimental = {"banded2_stage_A": banded2_leg(args)}      # a process of its own (see there)
+            experimental = {"stage_A_forms": banded2_leg(args)}      # a process of its own (see there)
         line = {
             "metric": "voxelized_events_per_s", "value": value, "unit": "Mevents/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -708,6 +856,11 @@ def run_gpu(args, rank, local_rank, world):
             "with_prebuilt_map_plans": {"value": world * events_per_step / (planned_ms * 1e-3) / 1e6, "unit": "Mevents/s",
                                         "ms_per_step": planned_ms,
                                         "note": "cmda_rectify_plan_build once per sequence instead of inside every step"},
+            "c4_strong_scaling": None if args.no_c4 else {
+                "config": f"C4: {C4_WINDOWS} windows x {C4_EVENTS} events (B={args.bins}) sharded by sample (shard_lpt) over {world} GPU(s), "
+                          "device resident, no collective; the same 64 windows at every N",
+                "Mevents_per_s": C4_WINDOWS * C4_EVENTS / (c4_ms * 1e-3) / 1e6, "ms_per_pass": c4_ms, "n_gpus": world,
+                "windows_rank0": c4_n, "scaling": "strong"},
             "roofline": roofline, "cpu_baseline": cpu, "cpu_port": cpu_port, "pseudo_events": pseudo, "train_step_input_path": c5,
             "variants": variants, "experimental": experimental,
         }
@@ -727,6 +880,7 @@ def main():
     ap.add_argument("--events", type=int, default=EVENTS_PER_WINDOW)
     ap.add_argument("--mode", default="auto", choices=["auto", "global", "tiled", "factored", "banded", "banded2"])
     ap.add_argument("--e2e-group", type=int, default=2, help="windows per host->device copy group of the e2e pipeline")
+    ap.add_argument("--no-c4", action="store_true", help="skip the C4 strong-scaling leg (64 x 20 M-event windows)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pseudo", action="store_true", help="skip the pseudo-event (config C3) leg")
     ap.add_argument("--no-variants", action="store_true", help="skip the other device-resident cases of SURVEY.md 8(d)")

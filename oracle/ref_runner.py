@@ -113,6 +113,14 @@ def _make_item(spec):
     if kind in ("isr", "pair"):
         now, front = synth.make_frame_pair(spec["H"], spec["W"], seed=spec["seed"])
         return dict(kind=kind, now=np.ascontiguousarray(now), front=np.ascontiguousarray(front), parms=spec.get("parms", {}))
+    if kind == "c5":       # one sample of the train-step input path: a 50 ms window + the target ISR + the mixed-image ISR
+        H, W = spec["H"], spec["W"]
+        t, x, y, p = synth.make_events(spec["n"], H, W, seed=spec["seed"])
+        rmap = synth.make_rectify_map(H, W, seed=spec["map_seed"])
+        ev = dict(kind="events_vg", t=t, x=x, y=y, p=p, rmap=rmap, H=H, W=W, B=spec["bins"], n=spec["n"], post=spec["post"])
+        oh, ow = spec["post"][5], spec["post"][4]
+        imgs = [np.ascontiguousarray(synth.make_smooth_image(oh, ow, seed=spec["seed"] + k)) for k in (1, 2)]
+        return dict(kind="c5", ev=ev, imgs=imgs, parms=spec["parms"])
     raise KeyError(kind)
 
 
@@ -129,6 +137,11 @@ def _run_item(ref, it):
         return float(vg.sum())
     if it["kind"] == "isr":
         return float(ref.isr(it["now"], **it["parms"]).sum())
+    if it["kind"] == "c5":
+        acc = _run_item(ref, it["ev"])
+        for k, img in enumerate(it["imgs"]):
+            acc += float(ref.isr(img, shift_direction=("rightdown", "leftup")[k], **it["parms"]).repeat(3, 1, 1).sum())
+        return acc
     out = ref.image_change(it["now"], it["front"])
     return float(out.size[0])
 
@@ -143,10 +156,12 @@ def _worker(conn, specs, threads):
         msg = conn.recv()
         if msg == "stop":
             return
+        kind = msg[1] if isinstance(msg, tuple) else None          # ("go", kind): only the items of that kind
         t0 = time.perf_counter()
         acc = 0.0
         for it in items:
-            acc += _run_item(ref, it)
+            if kind is None or it["kind"] == kind:
+                acc += _run_item(ref, it)
         conn.send((time.perf_counter() - t0, acc))
 
 
@@ -180,11 +195,11 @@ class WorkerPool:
         for c in self.conns:
             assert c.recv() == "ready"
 
-    def step(self) -> float:
-        """Every worker runs its items once; wall seconds from "go" to the last answer."""
+    def step(self, kind=None) -> float:
+        """Every worker runs its items (of `kind`, if given) once; wall seconds from "go" to the last answer."""
         t0 = time.perf_counter()
         for c in self.conns:
-            c.send("go")
+            c.send(("go", kind))
         for c in self.conns:
             c.recv()
         return time.perf_counter() - t0
