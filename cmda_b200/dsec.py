@@ -21,7 +21,7 @@ import torch.nn.functional as F
 from .slicer import images_to_events_index, window_bounds
 from .voxel import EventStore, events_vg_augmented_batch, events_vg_batch
 
-__all__ = ["DSECEvents"]
+__all__ = ["DSECEvents", "DSECDataset"]
 
 
 class DSECEvents:
@@ -197,3 +197,89 @@ class DSECEvents:
             reps[-3] = 3
             events_vg = events_vg.repeat(*reps)
         return events_vg
+
+
+class DSECDataset:
+    """``DSECDataset.__getitem__`` (reference mmseg/datasets/dsec.py:124, 189-339) over the CUDA path: the dict a sample
+    is, with the reference's keys, shapes, dtypes and value ranges for the entries this path produces --
+    ``'events_vg'`` (dsec.py:286-320), ``'warp_img_self_res'`` (dsec.py:236-262, ``isr_type='real_time'``),
+    ``'warp_image'`` (dsec.py:222-234, the crop / flip / BILINEAR resize / ToTensor / Normalize chain), ``'path'`` and
+    ``'img_metas'`` (dsec.py:322-337, a plain dict: mmcv's DataContainer belongs to the caller).  The augmentation
+    draws (flip, crop origin) are made here in the reference's order (dsec.py:204-209: ``random.random()``, then two
+    ``random.randint``), so a seeded run picks the same crops.
+
+    Files stay with the caller (image / label decoding is out of scope): one
+    ``DSECEvents`` per sequence holds the events, ``samples`` lists ``(sequence_key, now_image_index)`` -- what a line
+    of ``night_dataset_warp.txt`` encodes (dsec.py:199-201, 211) -- and ``warp_image_loader(sequence_key, index)``
+    returns the warp image as a uint8 RGB ``[440..480, 640, 3]`` array (dsec.py:223-224) when an output needs it.
+    Entries that need files this class is not given (``'image'``, ``'label'``, ``'19classes'``) raise ``KeyError``.
+    Registers itself under mmseg's ``DATASETS`` registry as ``DSECDatasetB200`` where mmseg is importable.
+    Everything returned lives on the sequence's CUDA device: use it from the process that owns the GPU."""
+
+    CLASSES = ('road', 'sidewalk', 'building', 'wall', 'fence', 'pole', 'traffic light', 'traffic sign', 'vegetation',
+               'terrain', 'sky', 'person', 'rider', 'car', 'truck', 'bus', 'train', 'motorcycle', 'bicycle')
+    _HANDLED = {'events_vg', 'warp_image', 'warp_img_self_res', 'path', 'img_metas'}
+
+    def __init__(self, sequences, samples, outputs={'events_vg', 'warp_image', 'warp_img_self_res'}, warp_image_loader=None):
+        self.sequences = dict(sequences)
+        self.samples = [(k, int(i)) for k, i in samples]
+        self.outputs = set(outputs)
+        missing = self.outputs - self._HANDLED
+        if missing:
+            raise KeyError(f"outputs {sorted(missing)} read files this adapter is not given (image / label I/O is the caller's)")
+        self.warp_image_loader = warp_image_loader
+        if ({'warp_image', 'warp_img_self_res'} & self.outputs) and warp_image_loader is None:
+            raise ValueError("'warp_image' / 'warp_img_self_res' need a warp_image_loader")
+        self.mean_std = ([0.485, 0.456, 0.406], [0.229, 0.224, 0.225])              # dsec.py:162
+
+    def __len__(self):
+        return len(self.samples)
+
+    def __getitem__(self, idx):
+        from .image_change import _to_u8_cuda, pil_resize_bilinear
+        key, now_image_index = self.samples[idx]
+        ev = self.sequences[key]
+        train = 'label' not in ev.outputs
+        output = dict()
+        flip_flag, x, y = False, None, None
+        if train:                                                                    # dsec.py:204-209
+            flip_flag = True if random.random() < 0.5 else False
+            x = random.randint(0, 640 - ev.crop_size[0])
+            y = random.randint(0, 480 - ev.crop_size[1])
+        if 'path' in self.outputs:
+            output['path'] = f"{key}/{now_image_index:06d}.png"
+        warp = None
+        if {'warp_image', 'warp_img_self_res'} & self.outputs:
+            warp = _to_u8_cuda(np.asarray(self.warp_image_loader(key, now_image_index)), ev.store.device)
+        if 'warp_image' in self.outputs:                                             # dsec.py:222-234
+            img = warp
+            if train:
+                img = img[y: y + ev.crop_size[1], x: x + ev.crop_size[0]]
+                if flip_flag:
+                    img = img.flip(1)
+                img = pil_resize_bilinear(img.contiguous()[None], ev.after_crop_resize_size)[0]
+            chw = img.permute(2, 0, 1).to(torch.float32).div(255)                    # ToTensor
+            mean = torch.tensor(self.mean_std[0], device=chw.device).view(3, 1, 1)
+            std = torch.tensor(self.mean_std[1], device=chw.device).view(3, 1, 1)
+            chw = (chw - mean) / std                                                 # Normalize
+            output['warp_image'] = chw if train else chw[:, :440]
+        if 'warp_img_self_res' in self.outputs:                                      # dsec.py:236-262
+            output['warp_img_self_res'] = ev.warp_img_self_res(warp, crop_xy=(x, y) if train else None, flip_flag=flip_flag)
+        if 'events_vg' in self.outputs:                                              # dsec.py:286-320
+            events_vg = ev.events_vg_for_image(now_image_index, crop_xy=(x, y) if train else None, flip_flag=flip_flag)
+            if events_vg is None:
+                return None                                                          # dsec.py:301-302
+            output['events_vg'] = events_vg
+        if 'img_metas' in self.outputs:                                              # dsec.py:322-337
+            output['img_metas'] = {
+                'img_norm_cfg': {'mean': [123.675, 116.28, 103.53], 'std': [58.395, 57.12, 57.375], 'to_rgb': True},
+                'img_shape': (440, 640), 'pad_shape': (440, 640), 'ori_shape': (440, 640),
+                'ori_filename': f"{key}_{now_image_index:06d}.png", 'flip': False}
+        return output
+
+
+try:        # the reference's plugin mechanism (dsec.py:124): only where mmseg / mmcv exist
+    from mmseg.datasets.builder import DATASETS as _DATASETS
+    _DATASETS.register_module(name="DSECDatasetB200", module=DSECDataset)
+except Exception:       # noqa: BLE001 -- mmseg is not part of this image
+    pass

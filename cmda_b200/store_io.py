@@ -16,8 +16,11 @@ the hot path) and a ``meta.json``::
     <dir>/images_timestamps.npy  int64 [I] images/timestamps.txt        (optional)
     <dir>/meta.json        {"format": "cmda_b200.sequence", "version": 1, "n_events": N, "t_offset": ..., "height": H, "width": W}
 
-``convert_dsec_h5`` writes it from a DSEC sequence with h5py + hdf5plugin where those are installed (they are
-not in this image: the function is exercised here only up to the import, see tests/test_store_io.py);
+    <dir>/rec.npy, rec_ms_to_idx.npy, rec_meta.json   the packed P4 stream (optional; cmda_b200.packed: 4 B/event)
+
+``convert_dsec_h5`` writes it from a DSEC sequence's ``events.h5`` + ``rectify_map.h5``: through h5py + hdf5plugin
+where those are installed, else through ``cmda_b200.h5lite`` (neither package is in this image; the reader is
+exercised on HDF5 files written by ``tests/h5_writer.py``, blosc / deflate / shuffle chunks included);
 ``load_sequence`` / ``DSECEvents.from_cache`` read it back.
 """
 from __future__ import annotations
@@ -27,7 +30,7 @@ import os
 
 import numpy as np
 
-__all__ = ["save_sequence", "load_sequence", "convert_dsec_h5", "upload", "FORMAT", "VERSION"]
+__all__ = ["save_sequence", "load_sequence", "convert_dsec_h5", "write_packed", "load_packed", "upload", "FORMAT", "VERSION"]
 
 FORMAT = "cmda_b200.sequence"
 VERSION = 1
@@ -85,22 +88,93 @@ def load_sequence(path, mmap=True) -> dict:
     return seq
 
 
-def convert_dsec_h5(events_h5_path, rectify_map_h5_path, out_dir, images_timestamps_path=None) -> str:
-    """Decode one DSEC sequence (the files of dsec.py:287-291 and create_dsec_dataset_txt.py:14-18) into the cache
-    format, once.  Needs h5py and hdf5plugin (blosc filter), like the reference; raises ``ImportError`` naming
-    them when they are missing."""
+def _open_h5(path):
+    """h5py + hdf5plugin where they are installed (what the reference uses, dsec.py:3-4), else the reader of
+    ``cmda_b200.h5lite`` (the subset of HDF5 + the Blosc filter that DSEC's files use)."""
     try:
         import hdf5plugin  # noqa: F401  (registers the blosc filter, dsec.py:3)
         import h5py
-    except ImportError as e:
-        raise ImportError("convert_dsec_h5 needs h5py and hdf5plugin to decode events.h5 "
-                          "(reference mmseg/datasets/dsec.py:3-4); install them or decode elsewhere and call "
-                          "save_sequence") from e
-    with h5py.File(events_h5_path, "r") as ev, h5py.File(rectify_map_h5_path, "r") as rm:
-        ts = None if images_timestamps_path is None else np.loadtxt(images_timestamps_path, dtype="int64")
-        return save_sequence(out_dir, ev["events/t"][()], ev["events/x"][()], ev["events/y"][()], ev["events/p"][()],
-                             np.asarray(ev["ms_to_idx"], dtype="int64"), int(ev["t_offset"][()]),
-                             np.asarray(rm["rectify_map"]), ts)
+        return h5py.File(path, "r")
+    except ImportError:
+        from . import h5lite
+        return h5lite.File(path)
+
+
+def convert_dsec_h5(events_h5_path, rectify_map_h5_path, out_dir, images_timestamps_path=None, chunk_events=1 << 24,
+                    packed=False) -> str:
+    """Decode one DSEC sequence (the files of dsec.py:287-291 and create_dsec_dataset_txt.py:14-18) into the cache
+    format, once: ``events/{t,x,y,p}``, ``ms_to_idx`` and ``t_offset`` of events.h5, ``rectify_map`` of
+    rectify_map.h5, optionally images/timestamps.txt.  The event datasets are streamed ``chunk_events`` at a time
+    into memory-mapped ``.npy`` files (a sequence holds ~4 x 10^8 events).  ``packed=True`` also writes the P4
+    stream of ``cmda_b200.packed`` (``rec.npy``, 4 bytes per event; its bucket table is DSEC's own ``ms_to_idx``)."""
+    os.makedirs(out_dir, exist_ok=True)
+    ev, rm = _open_h5(events_h5_path), _open_h5(rectify_map_h5_path)
+    try:
+        n = int(ev["events/t"].shape[0])
+        maps = {name: np.lib.format.open_memmap(os.path.join(out_dir, name + ".npy"), mode="w+", dtype=_DTYPES[name], shape=(n,))
+                for name in ("t", "x", "y", "p")}
+        for a in range(0, n, int(chunk_events)):
+            b = min(a + int(chunk_events), n)
+            for name in ("t", "x", "y", "p"):
+                src = np.asarray(ev["events/" + name][a:b])
+                dst = src.astype(_DTYPES[name])
+                if not np.array_equal(src, dst.astype(src.dtype)):
+                    raise ValueError(f"events/{name}: values do not fit {np.dtype(_DTYPES[name]).name}")
+                maps[name][a:b] = dst
+        for m in maps.values():
+            m.flush()
+        ms_to_idx = np.asarray(ev["ms_to_idx"]).astype(np.int64)
+        t_offset = int(np.asarray(ev["t_offset"][()]).reshape(-1)[0])
+        rmap = np.ascontiguousarray(np.asarray(rm["rectify_map"]), dtype=np.float32)
+    finally:
+        for f in (ev, rm):
+            if hasattr(f, "close"):
+                f.close()
+    if rmap.ndim != 3 or rmap.shape[2] != 2:
+        raise ValueError("rectify_map is [H, W, 2] (dsec.py:351-353)")
+    np.save(os.path.join(out_dir, "ms_to_idx.npy"), ms_to_idx)
+    np.save(os.path.join(out_dir, "rectify_map.npy"), rmap)
+    ts = None if images_timestamps_path is None else np.loadtxt(images_timestamps_path, dtype="int64")
+    if ts is not None:
+        np.save(os.path.join(out_dir, "images_timestamps.npy"), np.atleast_1d(ts).astype(np.int64))
+    meta = {"format": FORMAT, "version": VERSION, "n_events": n, "t_offset": t_offset, "height": int(rmap.shape[0]),
+            "width": int(rmap.shape[1]), "has_images_timestamps": ts is not None, "has_packed": bool(packed)}
+    if packed:
+        write_packed(out_dir, maps["t"], maps["x"], maps["y"], maps["p"], chunk_events=chunk_events)
+    with open(os.path.join(out_dir, "meta.json"), "w") as f:
+        json.dump(meta, f, indent=1)
+    return out_dir
+
+
+def write_packed(path, t, x, y, p, chunk_events=1 << 24) -> None:
+    """Add the packed (P4) stream to a cache directory: ``rec.npy`` uint32 [N] and ``rec_ms_to_idx.npy`` int64 (the
+    bucket table of the records: first event of every millisecond since ``rec_t_base``, stored in ``rec_meta.json``).
+    DSEC's own ``ms_to_idx`` is that table for ``t_base = 0``; it is rebuilt from ``t`` here so that the cache does not
+    depend on the file's copy being consistent."""
+    from . import packed as _packed
+    n = int(t.shape[0])
+    t_base = int(t[0]) // 1000 * 1000 if n else 0
+    rec = np.lib.format.open_memmap(os.path.join(path, "rec.npy"), mode="w+", dtype=np.uint32, shape=(n,))
+    for a in range(0, n, int(chunk_events)):
+        b = min(a + int(chunk_events), n)
+        rec[a:b] = _packed.pack_p4(t[a:b], x[a:b], y[a:b], p[a:b], t_base=t_base, check=True)[0]
+        if a and int(t[a]) < int(t[a - 1]):
+            raise ValueError("P4 needs ascending timestamps")
+    rec.flush()
+    np.save(os.path.join(path, "rec_ms_to_idx.npy"), _packed.ms_table(t, t_base))
+    with open(os.path.join(path, "rec_meta.json"), "w") as f:
+        json.dump({"t_base": t_base, "n_events": n}, f)
+
+
+def load_packed(path, mmap=True):
+    """``(rec, ms_to_idx, t_base)`` of a cache directory written with ``packed=True`` / ``write_packed``."""
+    with open(os.path.join(path, "rec_meta.json")) as f:
+        meta = json.load(f)
+    rec = np.load(os.path.join(path, "rec.npy"), mmap_mode="r" if mmap else None)
+    table = np.load(os.path.join(path, "rec_ms_to_idx.npy"))
+    if rec.dtype != np.uint32 or rec.shape != (int(meta["n_events"]),) or table[-1] != rec.shape[0]:
+        raise ValueError(f"{path}: packed stream disagrees with rec_meta.json")
+    return rec, table, int(meta["t_base"])
 
 
 def upload(a, device, chunk_bytes=256 << 20):

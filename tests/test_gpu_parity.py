@@ -249,6 +249,66 @@ def test_events_vg_dsec_shim(cm):
     assert ds_bad.events_vg_for_image(1) is None
 
 
+def test_dsec_dataset_getitem_dict(cm):
+    """The `__getitem__`-shaped adapter (dsec.py:189-339): same keys, shapes, dtypes and -- replaying the reference's own
+    statements with PIL / torchvision-style ops / the oracle on the host, with the same random draws -- same values:
+    'warp_image' (crop / flip / PIL BILINEAR resize / ToTensor / Normalize), 'warp_img_self_res' (real-time ISR with
+    the 'random' shift direction of dsec.py:253-255, bit-exact), 'events_vg' (<= 2e-5 after the bilinear resize),
+    'img_metas'; train and test mode; None for start > finish."""
+    import random
+    import torch.nn.functional as F
+    from PIL import Image
+    from cmda_b200 import synth
+    H, W, n = 480, 640, 400_000
+    t, x, y, p = synth.make_events(n, H, W, seed=synth.seed_for(5, 7))
+    rmap = synth.make_rectify_map(H, W, seed=13)
+    index = [0, 100_000, 230_000, n - 1, 120_000]                      # image 4 -> start > finish for range 1
+    warp = {("seq", k): synth.make_rgb_image(H, W, seed=40 + k) for k in range(5)}
+    parms = dict(shift_pixel=1, val_range=(0.01, 1.01), _threshold=0.005, _clip_range=0.1)
+    for outputs, train in (({'events_vg', 'warp_image', 'warp_img_self_res'}, True), ({'events_vg', 'warp_image', 'label', 'img_metas'}, False)):
+        ev = cm.DSECEvents(t, x, y, p, rmap, index, events_bins=1, outputs=outputs, isr_parms=parms, shift_type='random', device="cuda:0")
+        ds = cm.DSECDataset({"seq": ev}, [("seq", 2), ("seq", 3), ("seq", 4)],
+                            outputs=outputs - {'label'}, warp_image_loader=lambda k, i: warp[(k, i)])
+        assert len(ds) == 3
+        random.seed(123)
+        item = ds[0]
+        random.seed(123)
+        flip_flag = x0 = y0 = None
+        if train:
+            flip_flag = random.random() < 0.5
+            x0, y0 = random.randint(0, 640 - 400), random.randint(0, 480 - 400)
+        pil = Image.fromarray(warp[("seq", 2)])
+        if train:                                                       # dsec.py:226-231
+            pil = pil.crop(box=(x0, y0, x0 + 400, y0 + 400))
+            if flip_flag:
+                pil = pil.transpose(Image.FLIP_LEFT_RIGHT)
+            pil = pil.resize(size=(512, 512), resample=Image.BILINEAR)
+        arr = torch.from_numpy(np.asarray(pil).copy()).permute(2, 0, 1).float().div(255)
+        ref_img = (arr - torch.tensor([0.485, 0.456, 0.406]).view(3, 1, 1)) / torch.tensor([0.229, 0.224, 0.225]).view(3, 1, 1)
+        ref_img = ref_img if train else ref_img[:, :440]
+        assert item['warp_image'].is_cuda and item['warp_image'].shape == ref_img.shape
+        np.testing.assert_allclose(item['warp_image'].cpu().numpy(), ref_img.numpy(), rtol=0, atol=1e-6)
+        ref_vg = torch.from_numpy(O.get_events_vg(t, x, y, p, rmap, W, H, 1, index[2], index[1]))
+        if train:
+            ref_vg = ref_vg[:, y0:y0 + 400, x0:x0 + 400]
+            ref_vg = ref_vg.flip(-1) if flip_flag else ref_vg
+            ref_vg = F.interpolate(ref_vg[None], size=(512, 512), mode='bilinear', align_corners=False)[0]
+            direct = [['leftdown', 'leftup'], ['rightdown', 'rightup']][x0 % 2][y0 % 2]            # dsec.py:253-255
+            ref_isr = O.get_image_change_from_pil(np.asarray(pil), 512, 512, shift_direction=direct, **parms)
+            assert item['warp_img_self_res'].shape == (3, 512, 512)
+            for c in range(3):
+                assert np.array_equal(bits(item['warp_img_self_res'][c]), bits(ref_isr[0]))
+        else:
+            ref_vg = ref_vg[:, :440, :]
+            assert item['img_metas']['ori_shape'] == (440, 640) and item['img_metas']['flip'] is False
+        ref_vg = ref_vg.repeat(3, 1, 1)
+        assert item['events_vg'].shape == ref_vg.shape and item['events_vg'].dtype == torch.float32
+        np.testing.assert_allclose(item['events_vg'].cpu().numpy(), ref_vg.numpy(), rtol=0, atol=2e-5)
+        assert ds[2] is None                                            # dsec.py:301-302
+    with pytest.raises(KeyError):
+        cm.DSECDataset({"seq": ev}, [("seq", 1)], outputs={'events_vg', 'image'})
+
+
 @pytest.mark.parametrize("bins,avg,flip,test_mode", [(5, False, True, False), (1, False, False, False), (5, True, True, False),
                                                      (5, False, False, True), (3, False, True, False)])
 def test_events_vg_fused_augment(cm, bins, avg, flip, test_mode):

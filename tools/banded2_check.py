@@ -35,9 +35,11 @@ for b in a.bins:
     ref, rc = cmda_b200.events_vg_batch(store, starts[:k], fins[:k], b, mode="factored", return_bin_counts=True)
     got, gc = cmda_b200.events_vg_batch(store, starts[:k], fins[:k], b, mode="banded2", return_bin_counts=True)
     same = bool(torch.equal(ref, got) and torch.equal(rc, gc))
-    ref = cmda_b200.events_vg_batch(store_odd, starts[:k], fins[:k], b, mode="factored")
-    got = cmda_b200.events_vg_batch(store_odd, starts[:k], fins[:k], b, mode="banded2")
-    same_odd = bool((ref - got).abs().max() <= 1e-5)      # a flagged window is recomputed by the fallback: same grid within the bar
+    # polarity bytes beyond {0, 1}: the banded forms flag the window and the fallback recomputes it with the reference's
+    # per-event float32 weights; raw grids agree within the raw-grid bar (1e-5 of the largest magnitudes at play)
+    ref = cmda_b200.events_vg_batch(store_odd, starts[:k], fins[:k], b, mode="factored", normalize=False)
+    got = cmda_b200.events_vg_batch(store_odd, starts[:k], fins[:k], b, mode="banded2", normalize=False)
+    same_odd = bool((ref - got).abs().max() <= 1e-5 * max(1.0, float(ref.abs().max())))
     del ref, got
     out = torch.empty((a.windows, b, bench.H, bench.W), dtype=torch.float32, device=dev)
     ms = {}
