@@ -319,6 +319,7 @@ def workload_config(args, world):
                         f"rectify_map remap + voxel grid (B={args.bins}) + events_norm",
             "windows_per_gpu": WINDOWS_PER_GPU, "events_per_window": args.events, "bins": args.bins,
             "height": H, "width": W, "voxel_mode": args.mode, "parallelism": f"shard-by-window x{world}",
+            "event_store": "GPU arm: packed P4 stream, 4 B/event (SoA DSEC arrays as a variant); CPU arm: the DSEC arrays",
             "l2": "inputs (720 MB/step) exceed L2 (126 MB); no flush needed"}
 
 
@@ -545,8 +546,9 @@ def variants_leg(store, starts, fins, rmap, args, dev, steps=10, warmup=3):
         res["C2_bins_1_red_stage_A"] = timed(store, starts, fins, 1, mode="factored")
         res["C2_bins_1_banded_stage_A"] = timed(store, starts, fins, 1, mode="banded")
     # the same step from the device-resident PACKED store (4 bytes per event instead of 9; bit-identical output)
-    pstore = cmda_b200.PackedEventStore.from_event_store(store)
-    res["C2_packed_store"] = timed(pstore, starts, fins, args.bins)
+    # the headline step from the SoA store (the four DSEC arrays, 9 bytes per event) and, at B = 1, from the packed one
+    res["C2_soa_store"] = timed(store, starts, fins, args.bins)
+    pstore = cmda_b200.PackedEventStore.from_event_store(store, plan=False)
     if args.bins != 1:
         res["C2_bins_1_packed_store"] = timed(pstore, starts, fins, 1)
     del pstore
@@ -644,9 +646,13 @@ def run_gpu(args, rank, local_rank, world):
         torch.cuda.synchronize(dev)
 
     t, x, y, p, rmap, starts, fins = make_workload(WINDOWS_PER_GPU, args.events, seed_base=rank * WINDOWS_PER_GPU)
-    # headline: the map-derived gather plans are rebuilt inside every step (plan=False), like the reference re-reads
-    # the map for every sample; the variant with plans prebuilt once per sequence is reported separately below
-    store = cmda_b200.EventStore(t, x, y, p, rmap, height=H, width=W, device=dev, plan=False)
+    # headline: the events are resident in the framework's own device format -- the packed P4 stream (cmda_b200.packed:
+    # 4 bytes per event instead of the 9 of the four DSEC arrays; the same stream the e2e leg ships over PCIe; outputs
+    # bit-identical to the SoA store's, which is timed as the variant C2_soa_store) -- and the map-derived gather plans
+    # are rebuilt inside every step (plan=False), like the reference re-reads the map for every sample; the variant
+    # with plans prebuilt once per sequence is reported separately below
+    soa_store = cmda_b200.EventStore(t, x, y, p, rmap, height=H, width=W, device=dev, plan=False)
+    store = cmda_b200.PackedEventStore.from_event_store(soa_store, plan=False)
     out = torch.empty((WINDOWS_PER_GPU, args.bins, H, W), dtype=torch.float32, device=dev)
     events_per_step = int((fins - starts + 1).sum())
 
@@ -690,7 +696,7 @@ def run_gpu(args, rank, local_rank, world):
             L.cmda_event_destroy(e)
 
     # ---- same step with the rectify-map plans prebuilt once (EventStore default) -----------------
-    store_p = cmda_b200.EventStore(store.t, store.x, store.y, store.p, store.rectify_map, height=H, width=W, device=dev)
+    store_p = cmda_b200.PackedEventStore(store.rec, store.h_ms_to_idx, store.rectify_map, height=H, width=W, device=dev, plan=True)
     for _ in range(3):
         cmda_b200.events_vg_batch(store_p, starts, fins, args.bins, mode=args.mode, out=out)
     barrier()
@@ -701,7 +707,6 @@ def run_gpu(args, rank, local_rank, world):
     p1.record()
     barrier()
     planned_ms = p0.elapsed_time(p1) / args.steps
-    del store_p
 
     # ---- end to end through the host-buffer front door ----------------------------------------
     # Three ways a caller can hold the events (the timed region of each includes every copy it needs, every step):
@@ -734,7 +739,7 @@ def run_gpu(args, rank, local_rank, world):
         e2e_legs[wire] = {"ms": ms, "h2d": h2d_w, "d2h": d2h_w, "same": bool(torch.equal(host_out, out.cpu()))}
         pipe.close()
         del pipe
-    store_r = cmda_b200.EventStore(store.t, store.x, store.y, store.p, store.rectify_map, height=H, width=W, device=dev)
+    store_r = store_p
     half = WINDOWS_PER_GPU // 2
     d_out2 = [torch.empty((half, args.bins, H, W), dtype=torch.float32, device=dev) for _ in range(2)]
     side = torch.cuda.Stream(dev)
@@ -755,16 +760,16 @@ def run_gpu(args, rank, local_rank, world):
     ms = time_calls(resident_step)
     e2e_legs["resident"] = {"ms": ms, "h2d": 0, "d2h": 4 * WINDOWS_PER_GPU * args.bins * H * W,
                             "same": bool(torch.equal(host_out, out.cpu()))}
-    del store_r, d_out2
+    del store_r, store_p, d_out2
     e2e_ms, h2d, d2h, same = e2e_legs["p4"]["ms"], e2e_legs["p4"]["h2d"], e2e_legs["p4"]["d2h"], e2e_legs["p4"]["same"]
 
     # ---- C4: 64 x 20 M-event windows sharded by sample, strong scaling ---------------------------------
     c4_ms, c4_n = (0.0, 0)
     if not args.no_c4:
-        del store
+        del store, soa_store
         torch.cuda.empty_cache()
         c4_ms, c4_n = c4_strong_scaling_leg(args, rank, world, dev, barrier)
-        store = cmda_b200.EventStore(t, x, y, p, rmap, height=H, width=W, device=dev, plan=False)
+        soa_store = cmda_b200.EventStore(t, x, y, p, rmap, height=H, width=W, device=dev, plan=False)
 
     # ---- max over ranks ----------------------------------------------------------------------
     times = torch.tensor([ms_total, e2e_ms, planned_ms, e2e_legs["soa"]["ms"], e2e_legs["resident"]["ms"], c4_ms], dtype=torch.float64,
@@ -832,7 +837,7 @@ def run_gpu(args, rank, local_rank, world):
                 c5["cpu_baseline"] = side["train_step_input_path"]
         if world == 1 and not args.no_variants:
             del host_out
-            variants = variants_leg(store, starts, fins, rmap, args, dev)
+            variants = variants_leg(soa_store, starts, fins, rmap, args, dev)
         experimental = None
         if world == 1 and not args.no_variants and args.mode in ("auto", "factored"):
             experimental = {"stage_A_forms": banded2_leg(args)}      # a process of its own (see there)

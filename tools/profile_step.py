@@ -17,10 +17,13 @@ ap.add_argument("--mode", default="tiled")
 ap.add_argument("--events", type=int, default=bench.EVENTS_PER_WINDOW)
 ap.add_argument("--windows", type=int, default=bench.WINDOWS_PER_GPU)
 ap.add_argument("--steps", type=int, default=2)
+ap.add_argument("--store", default="p4", choices=["p4", "soa"], help="device-resident event format (bench.py's headline uses p4)")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 t, x, y, p, rmap, starts, fins = bench.make_workload(a.windows, a.events, seed_base=0)
-store = cmda_b200.EventStore(t, x, y, p, rmap, height=bench.H, width=bench.W, device=dev)
+store = cmda_b200.EventStore(t, x, y, p, rmap, height=bench.H, width=bench.W, device=dev, plan=False)
+if a.store == "p4":
+    store = cmda_b200.PackedEventStore.from_event_store(store, plan=False)
 out = torch.empty((a.windows, a.bins, bench.H, bench.W), dtype=torch.float32, device=dev)
 for _ in range(a.steps):
     cmda_b200.events_vg_batch(store, starts, fins, a.bins, mode=a.mode, out=out)
