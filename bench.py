@@ -177,14 +177,19 @@ def measured_peaks():
 
 
 def ncu_traffic(kernel_key):
-    """dram__bytes_read+write per launch of the dominant kernel from the committed ncu capture."""
+    """dram__bytes_read + dram__bytes_write per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/ncu_traffic.json, written by tools/ncu_traffic_json.py from the capture of tools/r02_evidence.sh) and the
+    commit that capture was taken from: a capture of another build says nothing about this one, so the label travels
+    with the number.  Returns (bytes or None, label or None)."""
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.isfile(path):
         try:
-            return json.load(open(path)).get(kernel_key)
+            d = json.load(open(path))
+            key = kernel_key.split("+")[0].split(" ")[0]
+            return d.get(key, d.get(kernel_key)), {"git": d.get("_git"), "source": d.get("_source")}
         except Exception:
-            return None
-    return None
+            return None, None
+    return None, None
 
 
 # ------------------------------------------------------------------------------------ CPU legs
@@ -809,8 +814,9 @@ def run_gpu(args, rank, local_rank, world):
         roofline = None
         if dom:
             achieved = alg / (kernel_phases[dom] * 1e-3) / 1e9
+            traffic, traffic_label = ncu_traffic(dom)
             roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                        "frac": achieved / peak, "traffic": ncu_traffic(dom), "peak_source": peak_src,
+                        "frac": achieved / peak, "traffic": traffic, "traffic_capture": traffic_label, "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": alg, "kernel_ms": kernel_phases[dom],
                         "phase_ms": phases,
                         "whole_step": {"achieved": alg / (ms_per_step * 1e-3) / 1e9,

@@ -18,6 +18,7 @@ now = torch.from_numpy(np.stack([pairs[s % 4][0] for s in range(S)])).cuda()
 front = torch.from_numpy(np.stack([pairs[s % 4][1] for s in range(S)])).cuda()
 for _ in range(2):
     f32, u8 = cmda_b200.image_change_batch(now, front, want_f32=True, want_u8=True)
+    u8_only = cmda_b200.image_change_batch(now, front, want_f32=False, want_u8=True)      # the table-driven uint8 pass
     isr = cmda_b200.isr_batch(now, 1, (0.01, 1.01), 0.005, 0.1, "rightdown")
 torch.cuda.synchronize()
 print("ok", float(f32.abs().sum()), float(isr.abs().sum()))
