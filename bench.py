@@ -768,6 +768,20 @@ def run_gpu(args, rank, local_rank, world):
     del store_r, store_p, d_out2
     e2e_ms, h2d, d2h, same = e2e_legs["p4"]["ms"], e2e_legs["p4"]["h2d"], e2e_legs["p4"]["d2h"], e2e_legs["p4"]["same"]
 
+    # ---- the host link alone: every rank copies 256 MB pinned -> device at the same time (what bounds e2e at N > 1) ----
+    probe_src = torch.empty((256 << 20,), dtype=torch.uint8).pin_memory()
+    probe_dst = torch.empty((256 << 20,), dtype=torch.uint8, device=dev)
+    probe_dst.copy_(probe_src, non_blocking=True)
+    barrier()
+    q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    q0.record()
+    for _ in range(4):
+        probe_dst.copy_(probe_src, non_blocking=True)
+    q1.record()
+    barrier()
+    h2d_probe_gbps = 4 * (256 << 20) / (q0.elapsed_time(q1) * 1e-3) / 1e9
+    del probe_src, probe_dst
+
     # ---- C4: 64 x 20 M-event windows sharded by sample, strong scaling ---------------------------------
     c4_ms, c4_n = (0.0, 0)
     if not args.no_c4:
@@ -777,10 +791,11 @@ def run_gpu(args, rank, local_rank, world):
         soa_store = cmda_b200.EventStore(t, x, y, p, rmap, height=H, width=W, device=dev, plan=False)
 
     # ---- max over ranks ----------------------------------------------------------------------
-    times = torch.tensor([ms_total, e2e_ms, planned_ms, e2e_legs["soa"]["ms"], e2e_legs["resident"]["ms"], c4_ms], dtype=torch.float64,
-                         device=dev)
+    times = torch.tensor([ms_total, e2e_ms, planned_ms, e2e_legs["soa"]["ms"], e2e_legs["resident"]["ms"], c4_ms, -h2d_probe_gbps],
+                         dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    h2d_probe_gbps = -float(times[6])                 # the slowest rank's link
     ms_total, e2e_ms, planned_ms = float(times[0]), float(times[1]), float(times[2])
     e2e_legs["soa"]["ms"], e2e_legs["resident"]["ms"], c4_ms = float(times[3]), float(times[4]), float(times[5])
 
@@ -858,7 +873,11 @@ def run_gpu(args, rank, local_rank, world):
                     "ms_per_step": e2e_ms, "steps": e2e_steps, "matches_device_path": same,
                     "wire": "p4: packed event stream, 4 B/event from pinned host memory (cmda_b200.packed; packed once, outside "
                             "the timed region, like the reference's events.h5 decode); grids back to pinned host memory",
-                    "windows_per_group": args.e2e_group},
+                    "windows_per_group": args.e2e_group,
+                    "h2d_GBps_per_gpu": h2d / (e2e_ms * 1e-3) / 1e9,
+                    "host_link_probe": {"h2d_GBps_per_gpu_all_ranks_copying": h2d_probe_gbps,
+                                        "what": "256 MB pinned -> device copies issued by every rank at once, slowest rank: the "
+                                                "ceiling of any host-fed path at this N on this box"}},
             "e2e_other_wires": {
                 k: {"value": world * events_per_step / (v["ms"] * 1e-3) / 1e6, "unit": "Mevents/s", "ms_per_step": v["ms"],
                     "h2d_bytes_per_step": v["h2d"], "d2h_bytes_per_step": v["d2h"], "matches_device_path": v["same"]}
