@@ -768,19 +768,34 @@ def run_gpu(args, rank, local_rank, world):
     del store_r, store_p, d_out2
     e2e_ms, h2d, d2h, same = e2e_legs["p4"]["ms"], e2e_legs["p4"]["h2d"], e2e_legs["p4"]["d2h"], e2e_legs["p4"]["same"]
 
-    # ---- the host link alone: every rank copies 256 MB pinned -> device at the same time (what bounds e2e at N > 1) ----
-    probe_src = torch.empty((256 << 20,), dtype=torch.uint8).pin_memory()
-    probe_dst = torch.empty((256 << 20,), dtype=torch.uint8, device=dev)
-    probe_dst.copy_(probe_src, non_blocking=True)
-    barrier()
-    q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    q0.record()
-    for _ in range(4):
-        probe_dst.copy_(probe_src, non_blocking=True)
-    q1.record()
-    barrier()
-    h2d_probe_gbps = 4 * (256 << 20) / (q0.elapsed_time(q1) * 1e-3) / 1e9
-    del probe_src, probe_dst
+    # ---- the host link alone: every rank copies 256 MB pinned <-> device at the same time (what bounds e2e at N > 1) ----
+    probe_h = torch.empty((256 << 20,), dtype=torch.uint8).pin_memory()
+    probe_h2 = torch.empty((256 << 20,), dtype=torch.uint8).pin_memory()
+    probe_d = torch.empty((256 << 20,), dtype=torch.uint8, device=dev)
+    probe_d2 = torch.empty((256 << 20,), dtype=torch.uint8, device=dev)
+    s_up, s_down = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def link_probe(up, down):
+        """GB/s per direction with `up` (H2D) and / or `down` (D2H) copies in flight on every rank."""
+        def issue():
+            if up:
+                with torch.cuda.stream(s_up):
+                    probe_d.copy_(probe_h, non_blocking=True)
+            if down:
+                with torch.cuda.stream(s_down):
+                    probe_h2.copy_(probe_d2, non_blocking=True)
+        issue()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(4):
+            issue()
+        s_up.synchronize(); s_down.synchronize()
+        dt = time.perf_counter() - t0
+        barrier()
+        return 4 * (256 << 20) / dt / 1e9
+
+    link = torch.tensor([-link_probe(True, False), -link_probe(False, True), -link_probe(True, True)], dtype=torch.float64, device=dev)
+    del probe_h, probe_h2, probe_d, probe_d2
 
     # ---- C4: 64 x 20 M-event windows sharded by sample, strong scaling ---------------------------------
     c4_ms, c4_n = (0.0, 0)
@@ -791,11 +806,11 @@ def run_gpu(args, rank, local_rank, world):
         soa_store = cmda_b200.EventStore(t, x, y, p, rmap, height=H, width=W, device=dev, plan=False)
 
     # ---- max over ranks ----------------------------------------------------------------------
-    times = torch.tensor([ms_total, e2e_ms, planned_ms, e2e_legs["soa"]["ms"], e2e_legs["resident"]["ms"], c4_ms, -h2d_probe_gbps],
-                         dtype=torch.float64, device=dev)
+    times = torch.cat([torch.tensor([ms_total, e2e_ms, planned_ms, e2e_legs["soa"]["ms"], e2e_legs["resident"]["ms"], c4_ms],
+                                    dtype=torch.float64, device=dev), link])
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    h2d_probe_gbps = -float(times[6])                 # the slowest rank's link
+    link_gbps = [-float(v) for v in times[6:9]]       # the slowest rank's link: H2D alone, D2H alone, each direction with both busy
     ms_total, e2e_ms, planned_ms = float(times[0]), float(times[1]), float(times[2])
     e2e_legs["soa"]["ms"], e2e_legs["resident"]["ms"], c4_ms = float(times[3]), float(times[4]), float(times[5])
 
@@ -875,8 +890,10 @@ def run_gpu(args, rank, local_rank, world):
                             "the timed region, like the reference's events.h5 decode); grids back to pinned host memory",
                     "windows_per_group": args.e2e_group,
                     "h2d_GBps_per_gpu": h2d / (e2e_ms * 1e-3) / 1e9,
-                    "host_link_probe": {"h2d_GBps_per_gpu_all_ranks_copying": h2d_probe_gbps,
-                                        "what": "256 MB pinned -> device copies issued by every rank at once, slowest rank: the "
+                    "host_link_probe": {"h2d_GBps_per_gpu_all_ranks_copying": link_gbps[0],
+                                        "d2h_GBps_per_gpu_all_ranks_copying": link_gbps[1],
+                                        "each_direction_GBps_per_gpu_both_busy": link_gbps[2],
+                                        "what": "256 MB pinned <-> device copies issued by every rank at once, slowest rank: the "
                                                 "ceiling of any host-fed path at this N on this box"}},
             "e2e_other_wires": {
                 k: {"value": world * events_per_step / (v["ms"] * 1e-3) / 1e6, "unit": "Mevents/s", "ms_per_step": v["ms"],

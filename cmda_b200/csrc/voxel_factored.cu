@@ -679,15 +679,37 @@ band_partition3_kernel(const uint32_t* __restrict__ t, const uint16_t* __restric
     const long long first = g0 + static_cast<long long>(c) * (kPart3Threads * kPart3Groups);
     if (PK && HAS_T) ms_window_init(s_mw, pk, wd, max(first << 3, wd.start) + wd.src_shift);
     int ms_cursor = 0;
-    SensEv8 ev[kPart3Groups];
+    // SoA source: 8 events per group in the SoA register layout.  Packed source: the 8 records themselves (an event
+    // past the window is the all-ones word: its sub-millisecond field, 1023, is no legal value) and, for B > 1, their
+    // window-relative microseconds -- no detour through the SoA layout.
+    SensEv8 ev[PK ? 1 : kPart3Groups];
+    unsigned pr[PK ? kPart3Groups : 1][8], pt[(PK && HAS_T) ? kPart3Groups : 1][8];
 #pragma unroll
     for (int j = 0; j < kPart3Groups; ++j) {
         const long long grp = first + static_cast<long long>(j) * kPart3Threads + threadIdx.x;
-        if (grp < g1) {
-            ev[j] = sens_load8_any<HAS_T, VEC, PK>(t, x, y, p, pk, s_mw, wd, grp << 3, ms_cursor);
+        if constexpr (PK) {
+            const long long i0 = grp << 3;
+            if (VEC && grp < g1 && i0 >= wd.start && i0 + 8 <= wd.end) {
+                const uint4 a = ldg_stream_u4(pk.rec + i0), b = ldg_stream_u4(pk.rec + i0 + 4);
+                pr[j][0] = a.x; pr[j][1] = a.y; pr[j][2] = a.z; pr[j][3] = a.w;
+                pr[j][4] = b.x; pr[j][5] = b.y; pr[j][6] = b.z; pr[j][7] = b.w;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    pr[j][e] = (grp < g1 && i0 + e >= wd.start && i0 + e < wd.end) ? __ldg(pk.rec + i0 + e) : 0xffffffffu;
+            }
+            if constexpr (HAS_T) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    pt[j][e] = pr[j][e] < 0xffc00000u ? p4_time(pr[j][e], ms_advance(s_mw, pk, wd, i0 + e + wd.src_shift, ms_cursor)) : 0u;
+            }
         } else {
-            ev[j].x = make_uint4(~0u, ~0u, ~0u, ~0u);                           // 0xffff is outside any sensor: dropped
-            ev[j].y = ev[j].x; ev[j].t0 = make_uint4(0, 0, 0, 0); ev[j].t1 = ev[j].t0; ev[j].p = make_uint2(0u, 0u);
+            if (grp < g1) {
+                ev[j] = sens_load8<HAS_T, VEC>(t, x, y, p, grp << 3, wd.start, wd.end);
+            } else {
+                ev[j].x = make_uint4(~0u, ~0u, ~0u, ~0u);                       // 0xffff is outside any sensor: dropped
+                ev[j].y = ev[j].x; ev[j].t0 = make_uint4(0, 0, 0, 0); ev[j].t1 = ev[j].t0; ev[j].p = make_uint2(0u, 0u);
+            }
         }
     }
     const RawWindowTime rw = PK ? raw_window_time_p4(pk, wd, B) : raw_window_time(t, wd.start, wd.end, B);
@@ -706,21 +728,34 @@ band_partition3_kernel(const uint32_t* __restrict__ t, const uint16_t* __restric
     unsigned odd = 0u;
 #pragma unroll
     for (int j = 0; j < kPart3Groups; ++j) {
-        odd |= (ev[j].p.x | ev[j].p.y) & 0xfefefefeu;
-        const unsigned xs[4] = {ev[j].x.x, ev[j].x.y, ev[j].x.z, ev[j].x.w}, ys[4] = {ev[j].y.x, ev[j].y.y, ev[j].y.z, ev[j].y.w};
-        const unsigned ts[8] = {ev[j].t0.x, ev[j].t0.y, ev[j].t0.z, ev[j].t0.w, ev[j].t1.x, ev[j].t1.y, ev[j].t1.z, ev[j].t1.w};
+        const SensEv8& g8 = ev[PK ? 0 : j];
+        if constexpr (!PK) odd |= (g8.p.x | g8.p.y) & 0xfefefefeu;             // (a packed record holds one polarity bit)
+        const unsigned xs[4] = {g8.x.x, g8.x.y, g8.x.z, g8.x.w}, ys[4] = {g8.y.x, g8.y.y, g8.y.z, g8.y.w};
+        const unsigned ts[8] = {g8.t0.x, g8.t0.y, g8.t0.z, g8.t0.w, g8.t1.x, g8.t1.y, g8.t1.z, g8.t1.w};
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const unsigned ex = (e & 1) ? (xs[e >> 1] >> 16) : (xs[e >> 1] & 0xffffu);
-            const unsigned ey = (e & 1) ? (ys[e >> 1] >> 16) : (ys[e >> 1] & 0xffffu);
-            bool in = ex < Wu && ey < Hu;
-            const unsigned pol1 = ((e < 4 ? ev[j].p.x : ev[j].p.y) >> (8 * (e & 3))) & 1u;
+            unsigned ex, ey, pol1, te;
+            bool in;
+            if constexpr (PK) {
+                const unsigned rr = pr[j][e];
+                ex = rr & kP4XMask;
+                ey = (rr >> kP4YShift) & kP4YMask;
+                pol1 = (rr >> kP4PShift) & 1u;
+                te = HAS_T ? pt[HAS_T ? j : 0][e] : 0u;
+                in = ex < Wu && ey < Hu && rr < 0xffc00000u;
+            } else {
+                ex = (e & 1) ? (xs[e >> 1] >> 16) : (xs[e >> 1] & 0xffffu);
+                ey = (e & 1) ? (ys[e >> 1] >> 16) : (ys[e >> 1] & 0xffffu);
+                pol1 = ((e < 4 ? g8.p.x : g8.p.y) >> (8 * (e & 3))) & 1u;
+                te = ts[e];
+                in = ex < Wu && ey < Hu;
+            }
             const unsigned negbit = 128u - 128u * pol1;                         // value = 2 * pol - 1 (dsec.py:45): pol 0 -> -1
             const unsigned band = one_row ? ey : __umulhi(ey, g.inv_rows);
             const unsigned cell = ey * Wu + ex - band * cpb;                    // junk unless in
             unsigned bucket = band, hi = 0u;
             if constexpr (HAS_T) {
-                const float fdt = __uint2float_rn(ts[e] - rw.t_first);
+                const float fdt = __uint2float_rn(te - rw.t_first);
                 const unsigned T = __float2uint_rn(__fmul_rn(scale, div_by_reused(fdt, rw.fdT, r_dT)));   // dsec.py:347-348, 38-39, 43
                 const unsigned tb = T >> kFracBits;
                 in = in && tb < static_cast<unsigned>(B);                       // both temporal corners masked otherwise

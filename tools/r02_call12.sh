@@ -11,7 +11,7 @@ for n in 1 $N; do
 import json
 d = json.load(open('gpurun_out/r02_bench_scale_n$n.json'))
 print('N=$n value', round(d['value']), 'e2e', round(d['e2e']['value']), 'soa', round(d['e2e_other_wires']['soa']['value']), 'resident', round(d['e2e_other_wires']['resident']['value']),
-      'h2d/gpu', round(d['e2e']['h2d_GBps_per_gpu'], 1), 'probe', round(d['e2e']['host_link_probe']['h2d_GBps_per_gpu_all_ranks_copying'], 1), 'c4', round(d['c4_strong_scaling']['Mevents_per_s']))
+      'h2d/gpu', round(d['e2e']['h2d_GBps_per_gpu'], 1), 'probe', d["e2e"]["host_link_probe"], 'c4', round(d['c4_strong_scaling']['Mevents_per_s']))
 PY
   python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus $n --steps 2 --warmup 0 \
       > gpurun_out/r02_bench_scale_ref_n$n.json 2>/dev/null
