@@ -208,45 +208,82 @@ sensor_accumulate_kernel(const uint32_t* __restrict__ t, const uint16_t* __restr
     int* R32 = reinterpret_cast<int*>(R) + static_cast<size_t>(s) * plane;
     unsigned local_bins = 0;   // B == 1: every in-sensor event falls into bin 0
 
-    long long grp = first + threadIdx.x;
-    SensEv8 cur{};
-    if (grp < g1) cur = sens_load8_any<HAS_T, VEC, PK>(t, x, y, p, pk, s_mw, wd, grp << 3, ms_cursor);
-#pragma unroll 1
-    for (int j = 0; j < kSensGroupsPerThread && grp < g1; ++j) {
-        // the next group's loads are in flight while this group's atomics are issued
-        const long long nxt_grp = grp + kSensThreads;
-        SensEv8 nxt{};
-        if (CMDA_SENS_PREFETCH && j + 1 < kSensGroupsPerThread && nxt_grp < g1)
-            nxt = sens_load8_any<HAS_T, VEC, PK>(t, x, y, p, pk, s_mw, wd, nxt_grp << 3, ms_cursor);
-        const unsigned xs[4] = {cur.x.x, cur.x.y, cur.x.z, cur.x.w}, ys[4] = {cur.y.x, cur.y.y, cur.y.z, cur.y.w};
-        const unsigned ts[8] = {cur.t0.x, cur.t0.y, cur.t0.z, cur.t0.w, cur.t1.x, cur.t1.y, cur.t1.z, cur.t1.w};
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const unsigned ex = (e & 1) ? (xs[e >> 1] >> 16) : (xs[e >> 1] & 0xffffu);
-            const unsigned ey = (e & 1) ? (ys[e >> 1] >> 16) : (ys[e >> 1] & 0xffffu);
-            if (ex >= static_cast<unsigned>(W) || ey >= static_cast<unsigned>(H)) continue;
-            const int pol = static_cast<int>(((e < 4 ? cur.p.x : cur.p.y) >> (8 * (e & 3))) & 0xffu);
-            const int value = 2 * pol - 1;                                     // dsec.py:45 on the uint8 polarity
-            const unsigned pix = ey * static_cast<unsigned>(W) + ex;
-            // capacity guard: what this pixel's class received from this CTA (an upper bound for each of its cells)
-            if (SKETCH) atomicAdd(&s_sketch[sketch_class(pix)], static_cast<unsigned>(pol ? value : 1));
-            if constexpr (HAS_T) {
-                const float tn = __fmul_rn(rw.cm1, __fdiv_rn(__uint2float_rn(ts[e] - rw.t_first), rw.fdT));
-                const int tb = trunc_like_x86(tn);                             // dsec.py:43
-                if (tb < 0 || tb >= B) continue;                               // corner t0 masked; t0 + 1 cannot be in range either
-                const float f = __fsub_rn(tn, __int2float_rn(tb));             // exact (Sterbenz)
-                const long long fq = static_cast<long long>(__float2int_rn(__fmul_rn(f, 16777216.0f)));
-                const long long cell = static_cast<long long>(value) * ((1LL << kCountShift) + fq);
-                atomicAdd(R64 + static_cast<size_t>(tb) * plane + pix, static_cast<unsigned long long>(cell));
-                if (count_bins) atomicAdd(&s_bins[tb], 1u);
-            } else {
-                atomicAdd(R32 + pix, value);
-                ++local_bins;
-            }
+    // dt / dT by the reused correctly rounded reciprocal (common.cuh), then one conversion for (t0, f):
+    // T = rn(2^24 (C - 1) dt / dT) = t0 * 2^24 + rn(f * 2^24) -- see band_partition3_kernel
+    const float r_dT = __frcp_rn(rw.fdT);
+    const float scale = __fmul_rn(rw.cm1, 16777216.0f);
+    auto one_event = [&](unsigned ex, unsigned ey, int pol, unsigned te) {
+        if (ex >= static_cast<unsigned>(W) || ey >= static_cast<unsigned>(H)) return;
+        const int value = 2 * pol - 1;                                         // dsec.py:45 on the uint8 polarity
+        const unsigned pix = ey * static_cast<unsigned>(W) + ex;
+        // capacity guard: what this pixel's class received from this CTA (an upper bound for each of its cells)
+        if (SKETCH) atomicAdd(&s_sketch[sketch_class(pix)], static_cast<unsigned>(pol ? value : 1));
+        if constexpr (HAS_T) {
+            const float fdt = __uint2float_rn(te - rw.t_first);
+            const unsigned T = __float2uint_rn(__fmul_rn(scale, div_by_reused(fdt, rw.fdT, r_dT)));   // dsec.py:347-348, 38-39, 43
+            const unsigned tb = T >> kFracBits;
+            if (tb >= static_cast<unsigned>(B)) return;                        // corner t0 masked; t0 + 1 cannot be in range either
+            const long long cell = static_cast<long long>(value) * ((1LL << kCountShift) + static_cast<long long>(T & 0xffffffu));
+            atomicAdd(R64 + static_cast<size_t>(tb) * plane + pix, static_cast<unsigned long long>(cell));
+            if (count_bins) atomicAdd(&s_bins[tb], 1u);
+        } else {
+            atomicAdd(R32 + pix, value);
+            ++local_bins;
         }
-        grp = nxt_grp;
-        if (CMDA_SENS_PREFETCH) cur = nxt;
-        else if (j + 1 < kSensGroupsPerThread && grp < g1) cur = sens_load8_any<HAS_T, VEC, PK>(t, x, y, p, pk, s_mw, wd, grp << 3, ms_cursor);
+    };
+    long long grp = first + threadIdx.x;
+    if constexpr (PK) {
+        // packed source: the 8 records of a group, consumed as they are (an event past the window is the all-ones
+        // word: its sub-millisecond field, 1023, is no legal value); the next group's records are in flight meanwhile
+        auto load = [&](long long g, unsigned (&r)[8]) {
+            const long long i0 = g << 3;
+            if (VEC && i0 >= wd.start && i0 + 8 <= wd.end) {
+                const uint4 a = ldg_stream_u4(pk.rec + i0), b = ldg_stream_u4(pk.rec + i0 + 4);
+                r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) r[e] = (i0 + e >= wd.start && i0 + e < wd.end) ? __ldg(pk.rec + i0 + e) : 0xffffffffu;
+            }
+        };
+        unsigned cur[8] = {~0u, ~0u, ~0u, ~0u, ~0u, ~0u, ~0u, ~0u};
+        if (grp < g1) load(grp, cur);
+#pragma unroll 1
+        for (int j = 0; j < kSensGroupsPerThread && grp < g1; ++j) {
+            const long long nxt_grp = grp + kSensThreads;
+            unsigned nxt[8] = {~0u, ~0u, ~0u, ~0u, ~0u, ~0u, ~0u, ~0u};
+            if (j + 1 < kSensGroupsPerThread && nxt_grp < g1) load(nxt_grp, nxt);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const unsigned r = cur[e];
+                if (r >= 0xffc00000u) continue;
+                unsigned te = 0u;
+                if constexpr (HAS_T) te = p4_time(r, ms_advance(s_mw, pk, wd, (grp << 3) + e + wd.src_shift, ms_cursor));
+                one_event(r & kP4XMask, (r >> kP4YShift) & kP4YMask, static_cast<int>((r >> kP4PShift) & 1u), te);
+            }
+            grp = nxt_grp;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) cur[e] = nxt[e];
+        }
+    } else {
+        SensEv8 cur{};
+        if (grp < g1) cur = sens_load8<HAS_T, VEC>(t, x, y, p, grp << 3, wd.start, wd.end);
+#pragma unroll 1
+        for (int j = 0; j < kSensGroupsPerThread && grp < g1; ++j) {
+            // the next group's loads are in flight while this group's atomics are issued
+            const long long nxt_grp = grp + kSensThreads;
+            SensEv8 nxt{};
+            if (CMDA_SENS_PREFETCH && j + 1 < kSensGroupsPerThread && nxt_grp < g1)
+                nxt = sens_load8<HAS_T, VEC>(t, x, y, p, nxt_grp << 3, wd.start, wd.end);
+            const unsigned xs[4] = {cur.x.x, cur.x.y, cur.x.z, cur.x.w}, ys[4] = {cur.y.x, cur.y.y, cur.y.z, cur.y.w};
+            const unsigned ts[8] = {cur.t0.x, cur.t0.y, cur.t0.z, cur.t0.w, cur.t1.x, cur.t1.y, cur.t1.z, cur.t1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                one_event((e & 1) ? (xs[e >> 1] >> 16) : (xs[e >> 1] & 0xffffu), (e & 1) ? (ys[e >> 1] >> 16) : (ys[e >> 1] & 0xffffu),
+                          static_cast<int>(((e < 4 ? cur.p.x : cur.p.y) >> (8 * (e & 3))) & 0xffu), ts[e]);
+            grp = nxt_grp;
+            if (CMDA_SENS_PREFETCH) cur = nxt;
+            else if (j + 1 < kSensGroupsPerThread && grp < g1) cur = sens_load8<HAS_T, VEC>(t, x, y, p, grp << 3, wd.start, wd.end);
+        }
     }
     if (count_bins && !HAS_T) {
         local_bins = __reduce_add_sync(0xffffffffu, local_bins);
