@@ -959,6 +959,26 @@ __device__ __forceinline__ void planes_of_pixel(const void* __restrict__ R, unsi
     }
 }
 
+// The same chain from cells already in registers (the staging loop of the gather loads two chains before it
+// converts), written on the 32-bit halves of a cell: the low 44 bits are (sext12(hi) : lo), so the count is
+// (hi - sext12(hi)) >> 12 with no borrow from the low word, and the plane is one 32 x 32 + 64 multiply-add.
+template <int BT>
+__device__ __forceinline__ void planes_of_cells(const long long (&cell)[BT], double* __restrict__ dst) {
+    static_assert(kCountShift == 44 && kFracBits == 24, "the half-word arithmetic below is written for 44 + 24 bits");
+    long long f_prev = 0;
+#pragma unroll
+    for (int b = 0; b < BT; ++b) {
+        const int hi = static_cast<int>(cell[b] >> 32);
+        const int fr_hi = static_cast<int>(static_cast<unsigned>(hi) << 20) >> 20;
+        const int c = (hi - fr_hi) >> 12;
+        const long long fr = static_cast<long long>((static_cast<unsigned long long>(static_cast<unsigned>(fr_hi)) << 32) |
+                                                    static_cast<unsigned>(cell[b]));
+        const long long pl = static_cast<long long>(c) * (1 << kFracBits) + (f_prev - fr);
+        f_prev = fr;
+        dst[b] = static_cast<double>(pl);
+    }
+}
+
 // ---- inverse index of one rectify map ------------------------------------------------------------
 // cell (cx, cy) = (x0 + 1, y0 + 1) over a (W + 1) x (H + 1) grid: x0 = -1 keeps the pixels whose only
 // in-grid corner is x0 + 1 = 0 (int() truncates toward zero).  Every cell has
@@ -1036,6 +1056,9 @@ rectify_index_sort_kernel(MapSlots ms, int H, int W, size_t ncells_padded) {
 // weight fl(tent(X, x) * tent(Y, y)) (dsec.py:51-52 with value = 1).  Rows with more than kEll entries (degenerate maps) are flagged and gathered from
 // the cell lists directly.
 constexpr int kEll = 8;
+// Stencil weights are stored times 2^-24, the unit of the planes (kFracBits): a power of two, so the product sum is
+// the same number and the gather's epilogue has no multiply.  Tent products are >= 2^-48 when not zero: no underflow.
+constexpr float kPlaneUnit = 5.9604644775390625e-08f;
 constexpr unsigned kEllOverflow = 0xffu;
 
 struct Stencil {
@@ -1110,7 +1133,8 @@ stencil_build_kernel(const float2* __restrict__ maps, MapSlots ms, int H, int W,
     const bool overfull = for_each_source(ix, map, X, Y, W, false, [&](unsigned P, float w) {
         if (w == 0.0f) return;
         if (n < kEll)     // the source pixel as (row << 16 | column) for out_tile_box_kernel
-            sc.e[n * npx + px] = make_uint2(((P / static_cast<unsigned>(W)) << 16) | (P % static_cast<unsigned>(W)), __float_as_uint(w));
+            sc.e[n * npx + px] = make_uint2(((P / static_cast<unsigned>(W)) << 16) | (P % static_cast<unsigned>(W)),
+                                            __float_as_uint(__fmul_rn(w, kPlaneUnit)));
         ++n;
     });
     // a row is usable when it is complete and its order reproducible (sorted slots only)
@@ -1230,7 +1254,7 @@ __device__ __noinline__ GatherRow<BT> gather_pixel_from_cells(const void* __rest
     });
     GatherRow<BT> r;
 #pragma unroll
-    for (int b = 0; b < BT; ++b) r.v[b] = static_cast<double>(iacc[b]) * 0.015625;       // back to 2^-24 units (exact)
+    for (int b = 0; b < BT; ++b) r.v[b] = static_cast<double>(iacc[b]) * 9.313225746154785e-10;   // 2^-30: events (exact)
     return r;
 }
 
@@ -1273,16 +1297,45 @@ __device__ __forceinline__ void rectify_gather_body(const void* __restrict__ R, 
         // exact while cells * box.z < 2^32 (cells <= kStageBytes / 8).
         const unsigned cells = static_cast<unsigned>(box.z) * static_cast<unsigned>(box.w);
         const unsigned inv_w = 0xffffffffu / static_cast<unsigned>(box.z) + 1u;
-        for (unsigned c = threadIdx.x; c < cells; c += kOutThreads) {
+        auto pixel_of = [&](unsigned c) {
             const unsigned ly = box.z == 1 ? c : __umulhi(c, inv_w), lx = c - ly * static_cast<unsigned>(box.z);
-            const unsigned P = (box.y + ly) * W + box.x + lx;
-            double* dst = s_planes + static_cast<size_t>(c) * B;
-            planes_of_pixel(R, s, P, npx, B, [&](int b, double pl) { dst[b] = pl; });
+            return (box.y + ly) * W + box.x + lx;
+        };
+        if constexpr (BT > 1) {
+            // two cells per trip, their 2 * B loads issued before the first conversion: the loop is bound by the
+            // latency of R, and a box is only 4-5 trips of the CTA
+            const long long* r = reinterpret_cast<const long long*>(R) + static_cast<size_t>(s) * BT * npx;
+            for (unsigned c = threadIdx.x; c < cells; c += 2 * kOutThreads) {
+                const unsigned c2 = c + kOutThreads;
+                const bool two = c2 < cells;
+                const unsigned P = pixel_of(c), P2 = pixel_of(two ? c2 : c);
+                long long ca[BT], cb[BT];
+#pragma unroll
+                for (unsigned b = 0; b < BT; ++b) ca[b] = __ldg(r + (b * npx + P));      // 32-bit offsets: BT * npx < 2^32
+#pragma unroll
+                for (unsigned b = 0; b < BT; ++b) cb[b] = two ? __ldg(r + (b * npx + P2)) : 0;
+                planes_of_cells<BT>(ca, s_planes + static_cast<size_t>(c) * BT);
+                if (two) planes_of_cells<BT>(cb, s_planes + static_cast<size_t>(c2) * BT);
+            }
+        } else {
+            for (unsigned c = threadIdx.x; c < cells; c += kOutThreads) {
+                double* dst = s_planes + static_cast<size_t>(c) * B;
+                planes_of_pixel(R, s, pixel_of(c), npx, B, [&](int b, double pl) { dst[b] = pl; });
+            }
         }
+    }
+    // the stencil rows of this thread's output pixels: requested before the barrier, consumed after it
+    const Stencil sc = identity ? Stencil{nullptr, nullptr} : stencil_at(plan_of(ms, ms.slot[s]), ncells_padded, npx);
+    unsigned n_of[kOutRowsPerThread];
+#pragma unroll
+    for (int rpt = 0; rpt < kOutRowsPerThread; ++rpt) {
+        const int Y = (blockIdx.x / tiles_x) * kOutH + rpt * kOutTY + (threadIdx.x / kOutW);
+        n_of[rpt] = (staged && !identity && X < W && Y < H) ? sc.n[static_cast<unsigned>(Y) * W + X] : 0u;
     }
     __syncthreads();
 
     GatherStats st{0.0, 0.0, 0, INFINITY, -INFINITY};
+#pragma unroll
     for (int rpt = 0; rpt < kOutRowsPerThread; ++rpt) {
         const int Y = (blockIdx.x / tiles_x) * kOutH + rpt * kOutTY + (threadIdx.x / kOutW);
         if (X >= W || Y >= H) continue;
@@ -1301,14 +1354,17 @@ __device__ __forceinline__ void rectify_gather_body(const void* __restrict__ R, 
                     if (b < B) acc[b] = fma(md, src[b], acc[b]);       // the row's fixed order: reproducible
             };
             if (identity) {
-                accumulate(static_cast<unsigned>(Y - box.y) * box.z + static_cast<unsigned>(X - box.x), 1.0f);
+                accumulate(static_cast<unsigned>(Y - box.y) * box.z + static_cast<unsigned>(X - box.x), kPlaneUnit);
             } else {
-                const Stencil sc = stencil_at(plan_of(ms, ms.slot[s]), ncells_padded, npx);
-                const unsigned n = sc.n[px];
-                for (unsigned k = 0; k < n; ++k) {
-                    const uint2 e = __ldg(sc.e + k * npx + px);
-                    accumulate(e.x, __uint_as_float(e.y));
-                }
+                // every entry of the row requested at once (a serial walk pays the latency of L2 per entry), then
+                // consumed in the row's order
+                const unsigned n = n_of[rpt];
+                uint2 e[kEll];
+#pragma unroll
+                for (unsigned k = 0; k < kEll; ++k) e[k] = k < n ? __ldg(sc.e + k * npx + px) : make_uint2(0u, 0u);
+#pragma unroll
+                for (unsigned k = 0; k < kEll; ++k)
+                    if (k < n) accumulate(e[k].x, __uint_as_float(e[k].y));
             }
         } else if (box.z != 0) {     // box.z == 0: no source pixel reaches this tile, the sums stay 0
             const GatherRow<BA> row = gather_pixel_from_cells<BA>(R, s, npx, maps + static_cast<size_t>(tab.w[s].map_id) * npx,
@@ -1319,9 +1375,10 @@ __device__ __forceinline__ void rectify_gather_body(const void* __restrict__ R, 
 #pragma unroll
         for (int b = 0; b < BA; ++b) {
             if (b < B) {
-                // * 2^-24 (exact), one rounding; flagged: correctly rounded float32 of the exact 2^-30 integer sum
+                // one rounding (the 2^-24 of the planes rides on the weights); flagged: correctly rounded float32 of the
+                // exact 2^-30 integer sum
                 const float v = flagged ? __fmul_rn(__ll2float_rn(__ldg(fb + static_cast<size_t>(b) * npx + px)), kFixInv)
-                                        : __double2float_rn(acc[b] * 5.9604644775390625e-08);
+                                        : __double2float_rn(acc[b]);
                 out[static_cast<unsigned>(b) * npx + px] = v;
                 if (v != 0.0f) {                                   // dsec.py:88
                     st.nnz += 1;
@@ -1410,7 +1467,7 @@ static size_t plan_bytes_of(int H, int W) {
 }
 
 int factored_supported(int H, int W, int B) {
-    return B >= 1 && B <= 24 && H >= 1 && W >= 1 && H < 65536 && W < 65536 && static_cast<long long>(H + 1) * (W + 1) < (1LL << 30);
+    return B >= 1 && B <= 24 && H >= 1 && W >= 1 && H < 65536 && W < 65536 && static_cast<long long>(H + 1) * (W + 1) < (1LL << 29);   // 5 planes: 32-bit cell offsets
 }
 int factored_max_maps(void) { return kMaxDistinctMaps; }
 size_t factored_plan_bytes(int H, int W) { return factored_supported(H, W, 1) ? plan_bytes_of(H, W) : 0; }

@@ -363,6 +363,8 @@ inline long long __double2ll_rn(double v) {
 inline float __double2float_rn(double v) { return static_cast<float>(v); }
 inline float __ll2float_rn(long long v) { return static_cast<float>(v); }
 inline float __fsqrt_rn(float v) { return std::sqrt(v); }
+inline long long __double_as_longlong(double v) { return static_cast<long long>(emu_bits(v)); }
+inline void __syncwarp(unsigned = 0xffffffffu) {}      // fibers run one at a time between barriers: nothing to order
 inline float __int_as_float(int v) { return emu_unbits<float>(static_cast<unsigned>(v)); }
 inline int __float_as_int(float v) { return static_cast<int>(emu_unbits<unsigned>(emu_bits(v))); }
 inline unsigned __float_as_uint(float v) { return emu_unbits<unsigned>(emu_bits(v)); }

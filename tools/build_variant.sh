@@ -7,8 +7,9 @@ cd "$(dirname "$0")/../cmda_b200/csrc"
 name=$1; shift
 mkdir -p build/variants ../variants
 make -j8 > /dev/null
+unit=${UNIT:-voxel_factored}      # UNIT=pseudo_events tools/build_variant.sh ... rebuilds that translation unit instead
 nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -Xcompiler -fPIC -cudart static \
-     -Xptxas -v $@ -c -o build/variants/voxel_factored_$name.o voxel_factored.cu 2> build/variants/$name.ptxas.log
-objs=$(ls build/*.o | grep -v voxel_factored.o)
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -cudart static -Xcompiler -fPIC -o ../variants/lib_$name.so $objs build/variants/voxel_factored_$name.o
+     -Xptxas -v "$@" -c -o build/variants/${unit}_$name.o $unit.cu 2> build/variants/$name.ptxas.log
+objs=$(ls build/*.o | grep -v $unit.o)
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -cudart static -Xcompiler -fPIC -o ../variants/lib_$name.so $objs build/variants/${unit}_$name.o
 echo built ../variants/lib_$name.so
