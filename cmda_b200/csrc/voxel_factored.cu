@@ -1160,13 +1160,13 @@ struct GatherStats {
 #define CMDA_OUT_ROWS_PER_THREAD 2
 #endif
 #ifndef CMDA_STAGE_KB
-#define CMDA_STAGE_KB 48
+#define CMDA_STAGE_KB 36
 #endif
 #ifndef CMDA_OUT_TY
-#define CMDA_OUT_TY 4
+#define CMDA_OUT_TY 8
 #endif
 #ifndef CMDA_OUT_W
-#define CMDA_OUT_W 64
+#define CMDA_OUT_W 32
 #endif
 constexpr int kOutW = CMDA_OUT_W, kOutTY = CMDA_OUT_TY, kOutRowsPerThread = CMDA_OUT_ROWS_PER_THREAD,
               kOutH = kOutTY * kOutRowsPerThread, kOutThreads = kOutW * kOutTY;
@@ -1412,13 +1412,13 @@ __device__ __forceinline__ void rectify_gather_body(const void* __restrict__ R, 
         block_partials[static_cast<size_t>(s) * gridDim.x + blockIdx.x] = o;
     }
 }
-// B > 1: 80 registers -> 3 CTAs per SM.  -DCMDA_GATHER_MINBLOCKS=4 asks ptxas for 64 (a sweep parameter for
-// tools/build_variant.sh; naming even "1" changes ptxas' budget -- 106 registers -- so the default names nothing)
-#ifdef CMDA_GATHER_MINBLOCKS
-#define CMDA_GATHER_BOUNDS __launch_bounds__(kOutThreads, CMDA_GATHER_MINBLOCKS)
-#else
-#define CMDA_GATHER_BOUNDS __launch_bounds__(kOutThreads)
+// 2 <= B <= 5: 64 registers (a few spilled words) -> 4 CTAs per SM x 36 KB of staging; the kernel waits on L2 / DRAM
+// latency, and the fourth CTA buys more than the spills cost (profiles/r02_gather_sweep.txt: 0.167 -> 0.149 ms on
+// C2).  Run-time B (BT = 0, up to 24 accumulators): 128 registers.
+#ifndef CMDA_GATHER_MINBLOCKS
+#define CMDA_GATHER_MINBLOCKS 4
 #endif
+#define CMDA_GATHER_BOUNDS __launch_bounds__(kOutThreads, BT == 0 ? 2 : CMDA_GATHER_MINBLOCKS)
 template <int BT>
 __global__ void CMDA_GATHER_BOUNDS
 rectify_gather_kernel(const void* __restrict__ R, const __grid_constant__ WindowTable tab, const __grid_constant__ MapSlots ms,

@@ -1,8 +1,8 @@
 """TEST INFRASTRUCTURE ONLY.  Builds tests/emu/_build/libband_emu.so: the kernel part of
 cmda_b200/csrc/voxel_factored.cu (everything above its host launch section), compiled for the HOST against the
 fiber-based stand-in for CUDA in tests/emu/include/cuda_runtime.h.  The sources are copied with three mechanical
-edits: `extern __shared__` -> `extern` (the harness defines the arrays), the inline-PTX helpers of common.cuh (streaming loads / stores, TMA bulk
-copies and their mbarrier) -> plain loads / stores / memcpy + block barrier, and the header include path."""
+edits: `extern __shared__` -> `extern` (the harness defines the arrays), the three inline-PTX load / store helpers of
+common.cuh -> plain loads / stores, and the header include path."""
 import os
 import re
 import shlex
@@ -28,11 +28,6 @@ def _transform_common(src: str) -> str:
     swap("ldg_stream_u4", "return *static_cast<const uint4*>(p);")
     swap("ldg_stream_u2", "return *static_cast<const uint2*>(p);")
     swap("stg_stream_f4", "*reinterpret_cast<float4*>(p) = v;")
-    # TMA bulk copies + their mbarrier: the copy happens at issue, the wait is the block barrier (every thread waits)
-    swap("bulk_barrier_init", "(void)bar;")
-    swap("bulk_barrier_expect", "(void)bar; (void)bytes;")
-    swap("bulk_copy_to_shared", "(void)bar; std::memcpy(dst, src, bytes);")
-    swap("bulk_barrier_wait", "(void)bar; __syncthreads();")
     assert "asm" not in src, "an inline-PTX helper of common.cuh is not covered by the emulation build"
     return src
 
