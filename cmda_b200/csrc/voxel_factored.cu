@@ -1557,6 +1557,34 @@ int launch_plan_build(const float* maps, int n_maps, int H, int W, void* plans, 
     return CMDA_OK;
 }
 
+// The map plans feed the gather, not stage A: when they are built per call they go to a side stream and run under
+// the memset of R and the RED kernel (which leave the SMs' issue slots mostly idle).  One side stream and a
+// fork / join event pair per (host thread, device), made on first use; any failure to make them means the serial order.
+// Event record / wait only: legal inside a stream capture, where they become graph edges.
+struct SideStream {
+    cudaStream_t stream;
+    cudaEvent_t fork, join;
+};
+static SideStream* side_stream() {
+    constexpr int kMaxDevices = 64;
+    thread_local SideStream tl[kMaxDevices] = {};
+    thread_local bool failed = false;
+    int dev = -1;
+    if (failed || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+    SideStream& z = tl[dev];
+    if (z.stream == nullptr) {
+        if (cudaStreamCreateWithFlags(&z.stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&z.fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&z.join, cudaEventDisableTiming) != cudaSuccess) {
+            (void)cudaGetLastError();
+            z.stream = nullptr;
+            failed = true;
+            return nullptr;
+        }
+    }
+    return &z;
+}
+
 int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, const uint8_t* p, const PackedSrc* packed,
                     const WindowTable& tab, int S, long long max_events, const float* maps, int H, int W, int B, void* R,
                     int64_t* bin_counts, float* raw, PartialStats* partials, void* scratch, size_t scratch_bytes,
@@ -1606,6 +1634,19 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
     PartialStats* block_partials = reinterpret_cast<PartialStats*>(static_cast<char*>(scratch) + own_bytes);
     const float2* maps2 = reinterpret_cast<const float2*>(maps);
 
+    SideStream* side = (own_plans && n_slots) ? side_stream() : nullptr;
+    if (side != nullptr) {
+        if (cudaEventRecord(side->fork, st) != cudaSuccess || cudaStreamWaitEvent(side->stream, side->fork, 0) != cudaSuccess) {
+            (void)cudaGetLastError();
+            side = nullptr;
+        }
+    }
+    struct Rejoin {      // an error return must not leave the side stream writing the caller's workspace unordered
+        SideStream* side;
+        cudaStream_t st;
+        bool armed;
+        ~Rejoin() { if (armed) (void)cudaStreamWaitEvent(st, side->join, 0); }
+    } rejoin{side, st, false};
     // zero R (int64 cells for B > 1, int32 counts for B == 1; the BANDED stage A stores every cell instead) and the
     // guard; one memset when the two are adjacent (B > 1: the guard follows R's last plane)
     const size_t r_bytes = (B == 1) ? sizeof(int) * S * npx : sizeof(long long) * S * B * npx;
@@ -1615,10 +1656,18 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
         if (!banded) CMDA_CUDA_TRY(cudaMemsetAsync(R, 0, r_bytes, st));
         CMDA_CUDA_TRY(cudaMemsetAsync(guard.flags, 0, guard_bytes, st));
     }
+    // (the fork precedes the memset in stream order: the plans also run under it)
     phase_mark(st);
     if (own_plans && n_slots) {
-        const int rc = build_plans(maps2, ms, n_slots, H, W, st);
-        if (rc != CMDA_OK) return rc;
+        if (side != nullptr) {
+            const int rc = build_plans(maps2, ms, n_slots, H, W, side->stream);
+            CMDA_CUDA_TRY(cudaEventRecord(side->join, side->stream));
+            rejoin.armed = true;        // from here every way out of this function orders `st` after the side stream
+            if (rc != CMDA_OK) return rc;
+        } else {
+            const int rc = build_plans(maps2, ms, n_slots, H, W, st);
+            if (rc != CMDA_OK) return rc;
+        }
     }
     phase_mark(st);
     if (banded) {
@@ -1726,6 +1775,10 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
         CMDA_LAUNCH_CHECK();
     }
     phase_mark(st);
+    if (rejoin.armed) {
+        rejoin.armed = false;
+        CMDA_CUDA_TRY(cudaStreamWaitEvent(st, side->join, 0));
+    }
     {
         dim3 grid(nblk, S);
 #define CMDA_GATHER(BT)                                                                                                  \

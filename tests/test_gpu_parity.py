@@ -819,6 +819,38 @@ def test_packed_store_bit_identical_to_soa(cm, bins):
         cm.PackedEventStore.from_event_store(bad)
 
 
+@pytest.mark.parametrize("bins", [5, 1])
+def test_per_call_plans_on_side_stream_and_under_graph_capture(cm, bins):
+    """A store without prebuilt plans builds them per call on the library's side stream (forked from and rejoined to
+    the caller's stream): same bits as the prebuilt-plan path, on a non-default stream too, and the whole call can be
+    captured into a CUDA graph and replayed (event record / wait only: no synchronisation inside the call)."""
+    from cmda_b200 import synth
+    H, W, n = 480, 640, 600_000
+    t, x, y, p = synth.make_events(n, H, W, seed=synth.seed_for(5, 51))
+    rmap = synth.make_rectify_map(H, W, seed=13)
+    planned = cm.EventStore(t, x, y, p, rmap, height=H, width=W, device="cuda:0", plan=True)
+    plain = cm.EventStore(t, x, y, p, rmap, height=H, width=W, device="cuda:0", plan=False)
+    starts, fins = np.array([0, 100_000, 7]), np.array([n - 1, 400_000, 6])
+    ref = cm.events_vg_batch(planned, starts, fins, bins)
+    for _ in range(3):                                            # repeated: the side stream's events are reused
+        assert np.array_equal(bits(cm.events_vg_batch(plain, starts, fins, bins)), bits(ref))
+    side = torch.cuda.Stream()
+    out = torch.empty_like(ref)
+    with torch.cuda.stream(side):
+        cm.events_vg_batch(plain, starts, fins, bins, out=out)
+    side.synchronize()
+    assert np.array_equal(bits(out), bits(ref))
+    out.zero_()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        cm.events_vg_batch(plain, starts, fins, bins, out=out)
+    for _ in range(2):
+        out.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert np.array_equal(bits(out), bits(ref))
+
+
 def test_events_vg_fused_augment_many_windows(cm):
     """The augmented entry point past one launch group (70 windows, per-window crop origins / flips / maps): the
     per-group augmentation table and raw-grid offsets, against the unfused path + the oracle's post-voxel stage."""
