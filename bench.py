@@ -825,11 +825,11 @@ def run_gpu(args, rank, local_rank, world):
             names = ["memset(int64 grid)", "voxel_scatter_global_kernel", "convert_stats_kernel", "norm_apply_kernel"]
             launches_per_step = 3
         elif resolved == _lib.VOXEL_FACTORED:
-            names = ["memset(sensor grid)", "rectify_index_{build,sort}+stencil_build+out_tile_box kernels",
+            names = ["memset(sensor grid)", "launch of rectify_index_{build,sort}+stencil_build+out_tile_box kernels (side stream: they run under stage A)",
                      "sensor_accumulate_kernel", "rectify_gather+regroup_partials kernels", "norm_apply_kernel"]
             launches_per_step = 8   # kernels only (memsets not counted)
         elif resolved in (_lib.VOXEL_BANDED, _lib.VOXEL_BANDED2):
-            names = ["memset(none: every sensor-grid cell is stored)", "rectify_index_{build,sort}+stencil_build+out_tile_box kernels",
+            names = ["memset(none: every sensor-grid cell is stored)", "launch of rectify_index_{build,sort}+stencil_build+out_tile_box kernels (side stream: they run under stage A)",
                      "band_partition_kernel", "band_accumulate(+fixup) kernel", "rectify_gather+regroup_partials kernels",
                      "norm_apply_kernel"]
             launches_per_step = 9

@@ -1,44 +1,58 @@
 #!/usr/bin/env python
-"""Probe: how much of the SM-bound stage B hides under the L2-atomic-bound stage A when two halves of the C2
-batch run on two streams (separate workspaces).  Not a bench number; it sizes the auxiliary-stream design."""
-import os, sys
+"""Does splitting the C2 step's windows over k streams (k calls of 16 / k windows, each with its own workspace) let the
+gather / normaliser of one group run under the RED kernel of another?  Prints ms per step for k = 1, 2, 4 and for the
+same k calls issued on ONE stream (the control: what the split costs without overlap)."""
+import argparse
+import os
+import sys
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
 import torch
+
 import bench
 import cmda_b200
 
+ap = argparse.ArgumentParser()
+ap.add_argument("--bins", type=int, default=5)
+ap.add_argument("--steps", type=int, default=20)
+ap.add_argument("--store", default="p4")
+a = ap.parse_args()
 dev = torch.device("cuda:0")
-S, B = 16, int(sys.argv[1]) if len(sys.argv) > 1 else 5
-t, x, y, p, rmap, starts, fins = bench.make_workload(S, 5_000_000, seed_base=0)
-store = cmda_b200.EventStore(t, x, y, p, rmap, height=bench.H, width=bench.W, device=dev)
-out = torch.empty((S, B, bench.H, bench.W), dtype=torch.float32, device=dev)
+t, x, y, p, rmap, starts, fins = bench.make_workload(16, 5_000_000, seed_base=0)
+store = cmda_b200.EventStore(t, x, y, p, rmap, height=bench.H, width=bench.W, device=dev, plan=False)
+if a.store == "p4":
+    store = cmda_b200.PackedEventStore.from_event_store(store, plan=False)
+out = torch.empty((16, a.bins, bench.H, bench.W), dtype=torch.float32, device=dev)
+ref = cmda_b200.events_vg_batch(store, starts, fins, a.bins).clone()
+main = torch.cuda.current_stream()
 
-def timed(fn, steps=20):
-    for _ in range(3):
-        fn()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        fn()
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / steps
 
-def single():
-    cmda_b200.events_vg_batch(store, starts, fins, B, out=out)
+def step(k, streams):
+    g = 16 // k
+    ev = torch.cuda.Event()
+    ev.record(main)
+    for j in range(k):
+        st = streams[j % len(streams)]
+        st.wait_event(ev)
+        with torch.cuda.stream(st):
+            cmda_b200.events_vg_batch(store, starts[j * g:(j + 1) * g], fins[j * g:(j + 1) * g], a.bins, out=out[j * g:(j + 1) * g])
+    for st in streams:
+        done = torch.cuda.Event()
+        done.record(st)
+        main.wait_event(done)
 
-print("one call, one stream           : %.3f ms" % timed(single))
-for parts in (2, 4, 8):
-    for prio in (False, True):
-        streams = [torch.cuda.Stream(dev, priority=(-1 if (prio and k % 2 == 1) else 0)) for k in range(parts)]
-        n = S // parts
-        def multi():
-            cur = torch.cuda.current_stream(dev)
-            for k, st in enumerate(streams):
-                st.wait_stream(cur)
-                with torch.cuda.stream(st):
-                    cmda_b200.events_vg_batch(store, starts[k * n:(k + 1) * n], fins[k * n:(k + 1) * n], B, out=out[k * n:(k + 1) * n])
-            for st in streams:
-                cur.wait_stream(st)
-        print("%d calls on %d streams%s : %.3f ms" % (parts, parts, " (odd streams high priority)" if prio else "                            ", timed(multi)))
+
+for k in (1, 2, 4, 8):
+    for label, streams in (("streams", [torch.cuda.Stream() for _ in range(k)]), ("one stream", [torch.cuda.Stream()])):
+        for _ in range(3):
+            step(k, streams)
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref), (k, label)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(main)
+        for _ in range(a.steps):
+            step(k, streams)
+        e1.record(main)
+        torch.cuda.synchronize()
+        print(f"B={a.bins} {a.store} k={k} {label}: {e0.elapsed_time(e1) / a.steps:.3f} ms/step")
