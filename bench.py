@@ -715,7 +715,9 @@ def run_gpu(args, rank, local_rank, world):
 
     # ---- end to end through the host-buffer front door ----------------------------------------
     # Three ways a caller can hold the events (the timed region of each includes every copy it needs, every step):
-    #   p4        pinned host memory, packed stream (4 B/event; packed once when the pipeline / cache is built)  <- `e2e`
+    #   p3        pinned host memory, the 3-byte wire form of the packed stream (packed once when the pipeline / cache is
+    #             built; unpacked to P4 records on the device, inside the timed region)                          <- `e2e`
+    #   p4        pinned host memory, packed stream (4 B/event)
     #   soa       pinned host memory, the four DSEC arrays as the reference slices them (9 B/event)
     #   resident  events already on the device (DSECEvents.from_cache): only the grids travel, device -> host
     host_out = torch.empty((WINDOWS_PER_GPU, args.bins, H, W), dtype=torch.float32).pin_memory()
@@ -735,7 +737,7 @@ def run_gpu(args, rank, local_rank, world):
         return max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0)) / e2e_steps
 
     e2e_legs = {}
-    for wire in ("p4", "soa"):
+    for wire in ("p3", "p4", "soa"):
         pipe = HostEventsPipeline(t, x, y, p, rmap, args.bins, H, W, device=dev, windows_per_group=args.e2e_group, mode=args.mode,
                                   max_window_events=args.events, wire=wire)
         ms = time_calls(lambda: pipe(starts, fins, out=host_out))
@@ -766,7 +768,8 @@ def run_gpu(args, rank, local_rank, world):
     e2e_legs["resident"] = {"ms": ms, "h2d": 0, "d2h": 4 * WINDOWS_PER_GPU * args.bins * H * W,
                             "same": bool(torch.equal(host_out, out.cpu()))}
     del store_r, store_p, d_out2
-    e2e_ms, h2d, d2h, same = e2e_legs["p4"]["ms"], e2e_legs["p4"]["h2d"], e2e_legs["p4"]["d2h"], e2e_legs["p4"]["same"]
+    HEAD_WIRE = "p3"
+    e2e_ms, h2d, d2h, same = (e2e_legs[HEAD_WIRE][k] for k in ("ms", "h2d", "d2h", "same"))
 
     # ---- the host link alone: every rank copies 256 MB pinned <-> device at the same time (what bounds e2e at N > 1) ----
     probe_h = torch.empty((256 << 20,), dtype=torch.uint8).pin_memory()
@@ -807,12 +810,14 @@ def run_gpu(args, rank, local_rank, world):
 
     # ---- max over ranks ----------------------------------------------------------------------
     times = torch.cat([torch.tensor([ms_total, e2e_ms, planned_ms, e2e_legs["soa"]["ms"], e2e_legs["resident"]["ms"], c4_ms],
-                                    dtype=torch.float64, device=dev), link])
+                                    dtype=torch.float64, device=dev), link,
+                       torch.tensor([e2e_legs["p4"]["ms"]], dtype=torch.float64, device=dev)])
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     link_gbps = [-float(v) for v in times[6:9]]       # the slowest rank's link: H2D alone, D2H alone, each direction with both busy
     ms_total, e2e_ms, planned_ms = float(times[0]), float(times[1]), float(times[2])
     e2e_legs["soa"]["ms"], e2e_legs["resident"]["ms"], c4_ms = float(times[3]), float(times[4]), float(times[5])
+    e2e_legs["p4"]["ms"] = float(times[9])
 
     if rank == 0:
         ms_per_step = ms_total / args.steps
@@ -886,8 +891,9 @@ def run_gpu(args, rank, local_rank, world):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mevents/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "steps": e2e_steps, "matches_device_path": same,
-                    "wire": "p4: packed event stream, 4 B/event from pinned host memory (cmda_b200.packed; packed once, outside "
-                            "the timed region, like the reference's events.h5 decode); grids back to pinned host memory",
+                    "wire": "p3: the 3-byte wire form of the packed event stream from pinned host memory (cmda_b200.packed; packed "
+                            "once, outside the timed region, like the reference's events.h5 decode), unpacked to the 4-byte "
+                            "records on the device inside the timed region; grids back to pinned host memory",
                     "windows_per_group": args.e2e_group,
                     "h2d_GBps_per_gpu": h2d / (e2e_ms * 1e-3) / 1e9,
                     "host_link_probe": {"h2d_GBps_per_gpu_all_ranks_copying": link_gbps[0],
@@ -898,7 +904,7 @@ def run_gpu(args, rank, local_rank, world):
             "e2e_other_wires": {
                 k: {"value": world * events_per_step / (v["ms"] * 1e-3) / 1e6, "unit": "Mevents/s", "ms_per_step": v["ms"],
                     "h2d_bytes_per_step": v["h2d"], "d2h_bytes_per_step": v["d2h"], "matches_device_path": v["same"]}
-                for k, v in e2e_legs.items() if k != "p4"},
+                for k, v in e2e_legs.items() if k != HEAD_WIRE},
             "gpu_launches": launches_per_step * args.steps,
             "with_prebuilt_map_plans": {"value": world * events_per_step / (planned_ms * 1e-3) / 1e6, "unit": "Mevents/s",
                                         "ms_per_step": planned_ms,

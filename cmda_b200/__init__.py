@@ -11,7 +11,7 @@ from .image_change import (denorm_to_gray, get_ic, get_image_change, get_image_c
                            source_img_time_res, u8_crop_to_centered)
 from .slicer import images_to_events_index, searchsorted_right, window_bounds, write_index_txt  # noqa: F401
 from .dsec import DSECDataset, DSECEvents  # noqa: F401
-from .packed import PackedEventStore, pack_p4, unpack_p4  # noqa: F401
+from .packed import PackedEventStore, pack_p3, pack_p4, unpack_p3, unpack_p4  # noqa: F401
 from . import packed, sharding, store_io, synth  # noqa: F401
 
 __version__ = "0.1.0"

@@ -57,6 +57,7 @@ SIGNATURES = {
     "cmda_events_vg_batch_planned": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _vp, _vp, _int, _int, _int, _vp, _f32, _int,
                                             _int, _vp, _vp, _vp, _vp, _sz, _int, _vp, _vp]),
     "cmda_pack_events_p4": (_int, [_vp, _vp, _vp, _vp, _i64, ctypes.c_uint32, _i64, _vp, _vp, _vp, _vp]),
+    "cmda_unpack_p3_to_p4": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp]),
     "cmda_events_vg_batch_p4": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _int, _vp, _vp, _int, _int, _int, _vp, _f32, _int,
                                        _int, _vp, _vp, _vp, _vp, _sz, _int, _vp, _vp]),
     "cmda_voxel_grid_f32": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _int, _int, _vp, _vp, _vp, _sz, _int, _vp]),

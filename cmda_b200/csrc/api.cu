@@ -43,6 +43,7 @@ int launch_plan_build(const float*, int, int, int, void*, cudaStream_t);
 int launch_factored(const uint32_t*, const uint16_t*, const uint16_t*, const uint8_t*, const PackedSrc*, const WindowTable&, int,
                     long long, const float*, int, int, int, void*, int64_t*, float*, PartialStats*, void*, size_t, const void*, int,
                     cudaStream_t);
+int launch_unpack_p3(const uint8_t*, const int64_t*, int64_t, int64_t, int64_t, int64_t, uint32_t*, cudaStream_t);
 int launch_pack_p4(const uint32_t*, const uint16_t*, const uint16_t*, const uint8_t*, int64_t, uint32_t, int64_t, uint32_t*, int64_t*,
                    int32_t*, cudaStream_t);
 int banded_supported(int H, int W, int B);
@@ -389,6 +390,14 @@ int cmda_pack_events_p4(const uint32_t* d_t, const uint16_t* d_x, const uint16_t
     if (n < 0 || n_ms < 1) return CMDA_ERR_BAD_ARG;
     if (!d_ms_to_idx || !d_status || (n > 0 && (!d_t || !d_x || !d_y || !d_p || !d_rec))) return CMDA_ERR_BAD_ARG;
     return launch_pack_p4(d_t, d_x, d_y, d_p, n, t_base_us, n_ms, d_rec, d_ms_to_idx, d_status, static_cast<cudaStream_t>(stream));
+}
+
+int cmda_unpack_p3_to_p4(const uint8_t* d_rec3, const int64_t* d_sub_to_idx, int64_t sub_lo, int64_t sub_hi, int64_t first,
+                         int64_t last, uint32_t* d_rec4, void* stream) {
+    if (first < 0 || last < first || sub_lo < 0) return CMDA_ERR_BAD_ARG;
+    if (last == first) return CMDA_OK;
+    if (sub_hi < sub_lo || !d_rec3 || !d_sub_to_idx || !d_rec4) return CMDA_ERR_BAD_ARG;
+    return launch_unpack_p3(d_rec3, d_sub_to_idx, sub_lo, sub_hi, first, last, d_rec4, static_cast<cudaStream_t>(stream));
 }
 
 size_t cmda_rectify_plan_bytes(int H, int W) {

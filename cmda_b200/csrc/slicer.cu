@@ -134,4 +134,42 @@ int launch_pack_p4(const uint32_t* t, const uint16_t* x, const uint16_t* y, cons
     return CMDA_OK;
 }
 
+// ---- the 3-byte WIRE form of the packed stream ("P3") -> P4 records --------------------------------------
+// record = x | y << 10 | p << 19 | d << 20 (x < 1024, y < 512), d = (t_us - t_base) mod 16; the 16-microsecond bucket
+// j of an event follows from its index through sub_to_idx (sub_to_idx[j] = index of the first event with
+// t_us - t_base >= 16 j), exactly as the millisecond bucket of a P4 record follows from ms_to_idx.  One warp per
+// bucket: its events are contiguous, no search.  t_base is a multiple of 1000, so (16 j + d) mod 1000 is the P4
+// record's sub-millisecond field.
+__global__ void __launch_bounds__(256)
+p3_unpack_kernel(const uint8_t* __restrict__ rec3, const long long* __restrict__ sub_to_idx, long long j_lo, long long j_hi,
+                 long long first, long long last, uint32_t* __restrict__ rec4) {
+    const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    for (long long j = j_lo + ((static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5); j <= j_hi; j += warps) {
+        long long lo = __ldg(sub_to_idx + j), hi = __ldg(sub_to_idx + j + 1);
+        lo = lo > first ? lo : first;
+        hi = hi < last ? hi : last;
+        const uint32_t ms_off = static_cast<uint32_t>((static_cast<unsigned long long>(j) * 16ull) % 1000ull);
+        for (long long i = lo + lane; i < hi; i += 32) {
+            const uint8_t* r = rec3 + 3 * (i - first);
+            const uint32_t v = static_cast<uint32_t>(__ldg(r)) | (static_cast<uint32_t>(__ldg(r + 1)) << 8) |
+                               (static_cast<uint32_t>(__ldg(r + 2)) << 16);
+            uint32_t sub = ms_off + (v >> 20);                    // < 999 + 16
+            sub = sub >= 1000u ? sub - 1000u : sub;
+            rec4[i - first] = (v & 1023u) | (((v >> 10) & 511u) << 11) | (((v >> 19) & 1u) << 21) | (sub << 22);
+        }
+    }
+}
+
+int launch_unpack_p3(const uint8_t* rec3, const int64_t* sub_to_idx, int64_t j_lo, int64_t j_hi, int64_t first, int64_t last,
+                     uint32_t* rec4, cudaStream_t s) {
+    if (last <= first || j_hi < j_lo) return CMDA_OK;
+    long long blocks = (j_hi - j_lo + 1 + 7) / 8;                  // 8 warps per block, one bucket per warp and trip
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    p3_unpack_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(rec3, reinterpret_cast<const long long*>(sub_to_idx), j_lo, j_hi,
+                                                                   first, last, rec4);
+    CMDA_LAUNCH_CHECK();
+    return CMDA_OK;
+}
+
 }  // namespace cmda

@@ -17,9 +17,12 @@ import torch
 
 from . import _lib
 
-__all__ = ["pack_p4", "unpack_p4", "ms_table", "PackedEventStore"]
+__all__ = ["pack_p4", "unpack_p4", "ms_table", "pack_p3", "unpack_p3", "sub_table", "p3_to_p4", "PackedEventStore"]
 
 X_BITS, Y_BITS = 11, 10
+# the 3-byte WIRE form ("P3", include/cmda_b200.h): x | y << 10 | p << 19 | d << 20 with d = (t - t_base) mod 16; the
+# 16-microsecond bucket of an event follows from its index through sub_to_idx as the millisecond does through ms_to_idx
+P3_X_BITS, P3_Y_BITS, P3_SUB_US = 10, 9, 16
 
 
 def ms_table(t, t_base: int, n_ms: int | None = None) -> np.ndarray:
@@ -67,6 +70,70 @@ def unpack_p4(rec, ms_to_idx, t_base: int):
     return (t, (rec & np.uint32((1 << X_BITS) - 1)).astype(np.uint16),
             ((rec >> np.uint32(X_BITS)) & np.uint32((1 << Y_BITS) - 1)).astype(np.uint16),
             ((rec >> np.uint32(X_BITS + Y_BITS)) & np.uint32(1)).astype(np.uint8))
+
+
+def sub_table(t, t_base: int, n_sub: int | None = None) -> np.ndarray:
+    """``sub_to_idx[k]`` = index of the first event with ``t - t_base >= 16 k`` for k = 0 .. n_sub; the last entry is
+    the number of events."""
+    t = np.asarray(t)
+    rel_last = int(t[-1]) - int(t_base) if t.size else 0
+    if n_sub is None:
+        n_sub = rel_last // P3_SUB_US + 1
+    q = int(t_base) + P3_SUB_US * np.arange(n_sub, dtype=np.int64)
+    table = np.empty(n_sub + 1, dtype=np.int64)
+    table[:n_sub] = np.searchsorted(t.astype(np.int64, copy=False), q, side="left")
+    table[n_sub] = t.size
+    return table
+
+
+def pack_p3(t, x, y, p, t_base: int | None = None, check: bool = True):
+    """Host-side packer of the 3-byte wire form: ``(rec3 uint8 [3 n], sub_to_idx int64 [n_sub + 1], t_base)``; ``t_base``
+    as in :func:`pack_p4` (the two forms of one stream share it).  Raises ``ValueError`` when the stream does not fit
+    (x >= 1024, y >= 512, polarity beyond {0, 1}, descending timestamps)."""
+    t = np.ascontiguousarray(t, dtype=np.uint32)
+    x = np.ascontiguousarray(x, dtype=np.uint16)
+    y = np.ascontiguousarray(y, dtype=np.uint16)
+    p = np.ascontiguousarray(p, dtype=np.uint8)
+    if t_base is None:
+        t_base = int(t[0]) // 1000 * 1000 if t.size else 0
+    if t_base % 1000:
+        raise ValueError("t_base is a whole millisecond (the P4 records the wire form unpacks to count from it)")
+    if check:
+        if t.size and (int(t[0]) < t_base or np.any(t[1:] < t[:-1])):
+            raise ValueError("P3 needs ascending timestamps at or after t_base")
+        if x.size and (int(x.max()) >= 1 << P3_X_BITS or int(y.max()) >= 1 << P3_Y_BITS or int(p.max()) > 1):
+            raise ValueError("P3 holds x < 1024, y < 512 and polarity in {0, 1}")
+    d = (t - np.uint32(t_base)) % np.uint32(P3_SUB_US)
+    v = x.astype(np.uint32) | (y.astype(np.uint32) << np.uint32(P3_X_BITS)) | \
+        (p.astype(np.uint32) << np.uint32(P3_X_BITS + P3_Y_BITS)) | (d << np.uint32(P3_X_BITS + P3_Y_BITS + 1))
+    rec3 = np.ascontiguousarray(v.view(np.uint8).reshape(-1, 4)[:, :3]).reshape(-1)      # little endian: the low 3 bytes
+    return rec3, sub_table(t, t_base), int(t_base)
+
+
+def _p3_words(rec3) -> np.ndarray:
+    b = np.asarray(rec3, dtype=np.uint8).reshape(-1, 3).astype(np.uint32)
+    return b[:, 0] | (b[:, 1] << np.uint32(8)) | (b[:, 2] << np.uint32(16))
+
+
+def unpack_p3(rec3, sub_to_idx, t_base: int):
+    """Inverse of :func:`pack_p3` (numpy): ``(t uint32, x uint16, y uint16, p uint8)``."""
+    v = _p3_words(rec3)
+    sub_to_idx = np.asarray(sub_to_idx, dtype=np.int64)
+    j = np.searchsorted(sub_to_idx[:-1], np.arange(v.size, dtype=np.int64), side="right") - 1
+    t = (np.int64(t_base) + P3_SUB_US * j + (v >> np.uint32(P3_X_BITS + P3_Y_BITS + 1)).astype(np.int64)).astype(np.uint32)
+    return (t, (v & np.uint32((1 << P3_X_BITS) - 1)).astype(np.uint16),
+            ((v >> np.uint32(P3_X_BITS)) & np.uint32((1 << P3_Y_BITS) - 1)).astype(np.uint16),
+            ((v >> np.uint32(P3_X_BITS + P3_Y_BITS)) & np.uint32(1)).astype(np.uint8))
+
+
+def p3_to_p4(rec3, sub_to_idx) -> np.ndarray:
+    """The P4 records of a P3 stream (numpy restatement of ``cmda_unpack_p3_to_p4``)."""
+    v = _p3_words(rec3)
+    sub_to_idx = np.asarray(sub_to_idx, dtype=np.int64)
+    j = np.searchsorted(sub_to_idx[:-1], np.arange(v.size, dtype=np.int64), side="right") - 1
+    sub = ((P3_SUB_US * j + (v >> np.uint32(P3_X_BITS + P3_Y_BITS + 1)).astype(np.int64)) % 1000).astype(np.uint32)
+    return (v & np.uint32(1023)) | (((v >> np.uint32(10)) & np.uint32(511)) << np.uint32(X_BITS)) | \
+        (((v >> np.uint32(19)) & np.uint32(1)) << np.uint32(X_BITS + Y_BITS)) | (sub << np.uint32(X_BITS + Y_BITS + 1))
 
 
 class PackedEventStore:

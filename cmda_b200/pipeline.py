@@ -10,8 +10,10 @@ The host->device copy of the events is what bounds this path end to end (the ker
 of magnitude faster than PCIe delivers their input), so the wire format matters more than any
 kernel: ``wire="soa"`` ships the four DSEC arrays as they are (9 bytes per event), ``wire="p4"``
 ships the packed stream of ``cmda_b200.packed`` (4 bytes per event, packed ONCE when the pipeline --
-or the decoded-sequence cache of ``store_io`` -- is built; bit-identical results).  Windows of a
-group that touch or overlap in the store travel as one copy per array.
+or the decoded-sequence cache of ``store_io`` -- is built; bit-identical results), ``wire="p3"`` its 3-byte
+wire form (sensors up to 1024 x 512; unpacked to P4 records on the device by ``cmda_unpack_p3_to_p4``,
+0.1 ms per 80 M events, before the same kernels run).  Windows of a group that touch or overlap in the
+store travel as one copy per array.
 """
 from __future__ import annotations
 
@@ -33,7 +35,8 @@ class HostEventsPipeline:
     ``t, x, y, p`` are numpy arrays or CPU tensors in DSEC dtypes; they are wrapped (and
     pinned once, if they are not already) so that every later call is pure DMA.  With
     ``wire="p4"`` they are packed once here (or pass ``packed=(rec, ms_to_idx)`` from a cache) and
-    only the packed stream is kept.  The rectify map is uploaded once.
+    only the packed stream is kept; ``wire="p3"`` likewise (``packed=(rec3, sub_to_idx, ms_to_idx)``).  The
+    rectify map is uploaded once.
     """
 
     def __init__(self, t, x, y, p, rectify_map, num_bins, height=480, width=640, device=None,
@@ -42,9 +45,24 @@ class HostEventsPipeline:
         self.H, self.W, self.B = int(height), int(width), int(num_bins)
         self.mode = mode
         self.group = int(windows_per_group)
-        assert wire in ("soa", "p4")
+        assert wire in ("soa", "p4", "p3")
         self.wire = wire
-        if wire == "p4":
+        if wire == "p3":
+            if packed is None:
+                tt = self._np(t, np.uint32)
+                rec3, sub, t_base = _packed.pack_p3(tt, self._np(x, np.uint16), self._np(y, np.uint16), self._np(p, np.uint8))
+                table = _packed.ms_table(tt, t_base)
+            else:
+                rec3, sub, table = packed
+            if self.W > 1 << _packed.P3_X_BITS or self.H > 1 << _packed.P3_Y_BITS:
+                raise ValueError("the P3 wire holds x < 1024 and y < 512: use wire='p4'")
+            self.host = [self._pin(rec3, np.uint8)]
+            self.h_sub_to_idx = np.ascontiguousarray(sub, dtype=np.int64)
+            self.d_sub_to_idx = torch.from_numpy(self.h_sub_to_idx).to(self.device)
+            self.h_ms_to_idx = np.ascontiguousarray(table, dtype=np.int64)
+            self.d_ms_to_idx = torch.from_numpy(self.h_ms_to_idx).to(self.device)
+            self.bytes_per_event = 3
+        elif wire == "p4":
             if packed is None:
                 rec, table, _ = _packed.pack_p4(self._np(t, np.uint32), self._np(x, np.uint16), self._np(y, np.uint16),
                                                 self._np(p, np.uint8))
@@ -57,7 +75,7 @@ class HostEventsPipeline:
         else:
             self.host = [self._pin(a, dt) for a, dt in ((t, np.uint32), (x, np.uint16), (y, np.uint16), (p, np.uint8))]
             self.bytes_per_event = 9
-        self.n_total = int(self.host[0].shape[0])
+        self.n_total = int(self.host[0].shape[0]) // (3 if wire == "p3" else 1)
         self.rmap = None
         if rectify_map is not None:
             m = torch.as_tensor(np.ascontiguousarray(rectify_map, dtype=np.float32))
@@ -99,11 +117,12 @@ class HostEventsPipeline:
         if n_events <= self._cap and self._slots:
             return
         self._cap = int(n_events)
-        dts = [h.dtype for h in self.host]
+        dts = [torch.uint32] if self.wire == "p3" else [h.dtype for h in self.host]
         self._slots = []
         for _ in range(2):   # double buffering
             self._slots.append(dict(
                 ev=[torch.empty((self._cap,), dtype=dt, device=self.device) for dt in dts],
+                ev3=torch.empty((3 * self._cap if self.wire == "p3" else 0,), dtype=torch.uint8, device=self.device),
                 out=torch.empty((self.group, self.B, self.H, self.W), dtype=torch.float32, device=self.device),
                 ready=torch.cuda.Event(), done=torch.cuda.Event(), drained=torch.cuda.Event()))
         L = _lib.lib()
@@ -169,8 +188,11 @@ class HostEventsPipeline:
                 self.copy_in.wait_event(slot["done"])
                 with torch.cuda.stream(self.copy_in):
                     for a, b, pos in ranges:
-                        for dev_arr, host_arr in zip(slot["ev"], self.host):
-                            dev_arr[pos:pos + (b - a)].copy_(host_arr[a:b], non_blocking=True)
+                        if self.wire == "p3":
+                            slot["ev3"][3 * pos:3 * (pos + b - a)].copy_(self.host[0][3 * a:3 * b], non_blocking=True)
+                        else:
+                            for dev_arr, host_arr in zip(slot["ev"], self.host):
+                                dev_arr[pos:pos + (b - a)].copy_(host_arr[a:b], non_blocking=True)
                         h2d += (b - a) * self.bytes_per_event
                     slot["ready"].record(self.copy_in)
                 clips = np.array([default_clip_range(int(ends[s]) - 1, int(starts[s]))
@@ -182,7 +204,14 @@ class HostEventsPipeline:
                 self.compute.wait_event(slot["ready"])
                 with torch.cuda.stream(self.compute):
                     ev = slot["ev"]
-                    if self.wire == "p4":
+                    if self.wire == "p3":        # wire records -> P4 records, range by range, then the P4 path
+                        for a, b, pos in ranges:
+                            j_lo = int(np.searchsorted(self.h_sub_to_idx, a, side="right")) - 1
+                            j_hi = int(np.searchsorted(self.h_sub_to_idx, b - 1, side="right")) - 1
+                            _lib.check(L.cmda_unpack_p3_to_p4(_lib.ptr(slot["ev3"][3 * pos:]), _lib.ptr(self.d_sub_to_idx), j_lo, j_hi,
+                                                              a, b, _lib.ptr(ev[0][pos:]), self.compute.cuda_stream),
+                                       "cmda_unpack_p3_to_p4")
+                    if self.wire in ("p4", "p3"):
                         src = np.ascontiguousarray(starts[g[0]:g[0] + len(g)])
                         _lib.check(L.cmda_events_vg_batch_p4(
                             _lib.ptr(ev[0]), _lib.ptr(self.d_ms_to_idx), _lib.host_ptr(self.h_ms_to_idx), len(self.h_ms_to_idx) - 1,

@@ -185,6 +185,23 @@ int cmda_events_vg_batch_p4(const uint32_t* d_rec, const int64_t* d_ms_to_idx, c
                             size_t workspace_bytes, int mode, const void* d_plans, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * The 3-byte WIRE form of the packed stream ("P3") -> P4 records on the device.
+ * Replaces: nothing in the reference -- it is the host->device transport of the decoded events/{t,x,y,p} slices of
+ * DSECDataset.get_events_vg (dsec.py:342-345) at 3 bytes per event; what the path computes on is the P4 stream above.
+ *
+ *   record3 = x | y << 10 | p << 19 | d << 20   (24 bits, little endian; x < 1024, y < 512, p in {0, 1})
+ *   t_us    = t_base + 16 * j + d, j = the event's 16-microsecond bucket = the largest k with
+ *             sub_to_idx[k] <= event index (sub_to_idx[k] = index of the first event with t_us - t_base >= 16 k;
+ *             entry n_sub = n); t_base is the P4 stream's (a multiple of 1000 us)
+ *
+ *  d_rec3 / d_rec4   the record of store event `first` and where its P4 record goes: events [first, last) are
+ *                    unpacked (a staging buffer that holds one copied range, or the whole store with first = 0)
+ *  sub_lo, sub_hi    the buckets of event `first` and of event `last - 1` (found on the host's copy of the table)
+ * The P4 records written are bit-identical to cmda_pack_events_p4's for the same stream. */
+int cmda_unpack_p3_to_p4(const uint8_t* d_rec3, const int64_t* d_sub_to_idx, int64_t sub_lo, int64_t sub_hi, int64_t first,
+                         int64_t last, uint32_t* d_rec4, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * K2+K3 with the post-voxel augmentation of the dataset fused into the normaliser's apply phase
  * (SURVEY.md 8 f-1).
  * Replaces: DSECDataset.__getitem__, events branch after get_events_vg,

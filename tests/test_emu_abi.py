@@ -616,6 +616,34 @@ def test_packed_p4_source_is_bit_identical_to_soa(L):
         assert np.array_equal(bits(got), bits(base)) and np.array_equal(c2, counts), density
 
 
+def test_p3_wire_unpacks_to_the_p4_records(L):
+    """The 3-byte wire form: cmda_unpack_p3_to_p4 writes exactly the records cmda_pack_events_p4 / pack_p4 make of the
+    same stream -- the whole store, a range that starts and ends inside 16-microsecond buckets (staging-buffer use),
+    an empty range; a dense stream (many events per bucket) and a sparse one (most buckets empty)."""
+    from cmda_b200 import packed, synth
+    H, W = 400, 1000
+    for n, window_us in ((30_000, 2_000), (3_000, 40_000_000)):
+        t, x, y, p = synth.make_events(n, H, W, window_us=window_us, seed=29)
+        rec4, _, t_base = packed.pack_p4(t, x, y, p)
+        rec3, sub, t_base3 = packed.pack_p3(t, x, y, p)
+        assert t_base3 == t_base and rec3.shape == (3 * n,) and sub[0] == 0 and sub[-1] == n
+        assert all(np.array_equal(a, b) for a, b in zip(packed.unpack_p3(rec3, sub, t_base), (t, x, y, p)))
+        assert np.array_equal(packed.p3_to_p4(rec3, sub), rec4)
+        for first, last in ((0, n), (1234, 2777), (7, 8), (n - 1, n)):
+            j_lo = int(np.searchsorted(sub, first, side="right")) - 1
+            j_hi = int(np.searchsorted(sub, last - 1, side="right")) - 1
+            out = np.full(last - first + 2, 0xdeadbeef, dtype=np.uint32)          # one guard word on either side
+            stage = np.ascontiguousarray(rec3[3 * first:3 * last])
+            assert L.cmda_unpack_p3_to_p4(ptr(stage), ptr(sub), j_lo, j_hi, first, last, out[1:].ctypes.data, None) == 0
+            assert np.array_equal(out[1:-1], rec4[first:last]) and out[0] == 0xdeadbeef and out[-1] == 0xdeadbeef, (n, first, last)
+        assert L.cmda_unpack_p3_to_p4(ptr(rec3), ptr(sub), 0, 0, 5, 5, None, None) == 0          # empty range: nothing touched
+        assert L.cmda_unpack_p3_to_p4(ptr(rec3), ptr(sub), 0, 0, 5, 4, None, None) != 0
+    with pytest.raises(ValueError):
+        packed.pack_p3(t, np.where(np.arange(n) == 3, 1024, x).astype(np.uint16), y, p)
+    with pytest.raises(ValueError):
+        packed.pack_p3(t, x, y, p, t_base=int(t[0]) // 1000 * 1000 - 16)
+
+
 def test_table_driven_frame_pair_path(L):
     """Images of >= 2^17 pixels take the table-driven uint8 apply pass when only the uint8 output is asked for (one
     evaluation per (now, front) byte pair and image, then a gather from a 64 KB table in shared memory): bit-exact

@@ -755,7 +755,7 @@ def test_events_vg_randomised_differential(cm, seed):
 @pytest.mark.parametrize("group,bins", [(1, 5), (3, 1), (4, 5)])
 def test_host_events_pipeline_matches_device_path(cm, group, bins):
     """The host-buffer front door (pinned events in, pinned grids out, three streams, double-buffered slots) gives the
-    device-resident path's bits for both wire formats (SoA 9 B/event, packed P4 4 B/event): ragged windows, an empty
+    device-resident path's bits for the three wire formats (SoA 9 B/event, packed P4 4 B/event, P3 3 B/event): ragged windows, an empty
     one, unaligned starts, overlapping and touching windows (shared copies), two maps, more groups than slots."""
     from cmda_b200 import synth
     from cmda_b200.pipeline import HostEventsPipeline
@@ -775,7 +775,7 @@ def test_host_events_pipeline_matches_device_path(cm, group, bins):
             covered[starts[s]:max(fins[s] + 1, starts[s])] = True
         return int(covered.sum())
 
-    for wire, bpe in (("soa", 9), ("p4", 4)):
+    for wire, bpe in (("soa", 9), ("p4", 4), ("p3", 3)):
         pipe = HostEventsPipeline(t, x, y, p, maps, bins, H, W, device="cuda:0", windows_per_group=group, wire=wire)
         got = pipe(starts, fins, map_ids=mids)
         assert got.is_pinned() and got.shape == ref.shape
@@ -849,6 +849,35 @@ def test_per_call_plans_on_side_stream_and_under_graph_capture(cm, bins):
         graph.replay()
         torch.cuda.synchronize()
         assert np.array_equal(bits(out), bits(ref))
+
+
+def test_p3_wire_unpacks_to_p4_on_device(cm):
+    """cmda_unpack_p3_to_p4 (3-byte wire records + the 16-microsecond bucket table -> P4 records) against the host
+    packer and the device packer of the same stream: bit-identical for the whole store and for a range cut inside
+    buckets into a staging buffer; a store built from the unpacked records voxelises like the SoA store."""
+    from cmda_b200 import _lib, packed, synth
+    H, W, n = 480, 640, 3_000_000
+    t, x, y, p = synth.make_events(n, H, W, seed=synth.seed_for(1, 60))
+    rec4, table, t_base = packed.pack_p4(t, x, y, p)
+    rec3, sub, _ = packed.pack_p3(t, x, y, p)
+    L = cm.lib()
+    dev = torch.device("cuda:0")
+    d3, dsub = torch.from_numpy(rec3).to(dev), torch.from_numpy(sub).to(dev)
+    for first, last in ((0, n), (1_000_003, 2_345_678)):
+        j_lo = int(np.searchsorted(sub, first, side="right")) - 1
+        j_hi = int(np.searchsorted(sub, last - 1, side="right")) - 1
+        out = torch.full((last - first + 64,), 0x7fffffff, dtype=torch.int32, device=dev)
+        _lib.check(L.cmda_unpack_p3_to_p4(_lib.ptr(d3[3 * first:]), _lib.ptr(dsub), j_lo, j_hi, first, last, _lib.ptr(out),
+                                          _lib.stream_ptr(dev)), "cmda_unpack_p3_to_p4")
+        got = out.cpu().numpy().view(np.uint32)
+        assert np.array_equal(got[:last - first], rec4[first:last]) and np.all(got[last - first:] == 0x7fffffff)
+        if first == 0:
+            whole = out[:n].clone()
+    rmap = synth.make_rectify_map(H, W, seed=3)
+    soa = cm.EventStore(t, x, y, p, rmap, height=H, width=W, device=dev)
+    pst = cm.PackedEventStore(whole, table, rmap, height=H, width=W, device=dev)       # the records the device unpacked
+    starts, fins = np.array([0, 500_000]), np.array([n - 1, 2_500_000])
+    assert np.array_equal(bits(cm.events_vg_batch(pst, starts, fins, 5)), bits(cm.events_vg_batch(soa, starts, fins, 5)))
 
 
 def test_events_vg_fused_augment_many_windows(cm):
