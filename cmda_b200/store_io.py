@@ -17,6 +17,7 @@ the hot path) and a ``meta.json``::
     <dir>/meta.json        {"format": "cmda_b200.sequence", "version": 1, "n_events": N, "t_offset": ..., "height": H, "width": W}
 
     <dir>/rec.npy, rec_ms_to_idx.npy, rec_meta.json   the packed P4 stream (optional; cmda_b200.packed: 4 B/event)
+    <dir>/rec3.npy, rec3_sub_to_idx.npy               its 3-byte wire form (optional; what HostEventsPipeline(wire="p3") ships)
 
 ``convert_dsec_h5`` writes it from a DSEC sequence's ``events.h5`` + ``rectify_map.h5``: through h5py + hdf5plugin
 where those are installed, else through ``cmda_b200.h5lite`` (neither package is in this image; the reader is
@@ -30,7 +31,8 @@ import os
 
 import numpy as np
 
-__all__ = ["save_sequence", "load_sequence", "convert_dsec_h5", "write_packed", "load_packed", "upload", "FORMAT", "VERSION"]
+__all__ = ["save_sequence", "load_sequence", "convert_dsec_h5", "write_packed", "load_packed", "load_packed_wire", "upload", "FORMAT",
+           "VERSION"]
 
 FORMAT = "cmda_b200.sequence"
 VERSION = 1
@@ -106,7 +108,8 @@ def convert_dsec_h5(events_h5_path, rectify_map_h5_path, out_dir, images_timesta
     format, once: ``events/{t,x,y,p}``, ``ms_to_idx`` and ``t_offset`` of events.h5, ``rectify_map`` of
     rectify_map.h5, optionally images/timestamps.txt.  The event datasets are streamed ``chunk_events`` at a time
     into memory-mapped ``.npy`` files (a sequence holds ~4 x 10^8 events).  ``packed=True`` also writes the P4
-    stream of ``cmda_b200.packed`` (``rec.npy``, 4 bytes per event; its bucket table is DSEC's own ``ms_to_idx``)."""
+    stream of ``cmda_b200.packed`` (``rec.npy``, 4 bytes per event; its bucket table is DSEC's own ``ms_to_idx``),
+    ``packed="p3"`` additionally its 3-byte wire form (``rec3.npy`` + the 16-microsecond bucket table)."""
     os.makedirs(out_dir, exist_ok=True)
     ev, rm = _open_h5(events_h5_path), _open_h5(rectify_map_h5_path)
     try:
@@ -140,17 +143,18 @@ def convert_dsec_h5(events_h5_path, rectify_map_h5_path, out_dir, images_timesta
     meta = {"format": FORMAT, "version": VERSION, "n_events": n, "t_offset": t_offset, "height": int(rmap.shape[0]),
             "width": int(rmap.shape[1]), "has_images_timestamps": ts is not None, "has_packed": bool(packed)}
     if packed:
-        write_packed(out_dir, maps["t"], maps["x"], maps["y"], maps["p"], chunk_events=chunk_events)
+        write_packed(out_dir, maps["t"], maps["x"], maps["y"], maps["p"], chunk_events=chunk_events, wire3=packed == "p3")
     with open(os.path.join(out_dir, "meta.json"), "w") as f:
         json.dump(meta, f, indent=1)
     return out_dir
 
 
-def write_packed(path, t, x, y, p, chunk_events=1 << 24) -> None:
+def write_packed(path, t, x, y, p, chunk_events=1 << 24, wire3=False) -> None:
     """Add the packed (P4) stream to a cache directory: ``rec.npy`` uint32 [N] and ``rec_ms_to_idx.npy`` int64 (the
     bucket table of the records: first event of every millisecond since ``rec_t_base``, stored in ``rec_meta.json``).
     DSEC's own ``ms_to_idx`` is that table for ``t_base = 0``; it is rebuilt from ``t`` here so that the cache does not
-    depend on the file's copy being consistent."""
+    depend on the file's copy being consistent.  ``wire3``: also ``rec3.npy`` uint8 [3 N] and ``rec3_sub_to_idx.npy``, the
+    3-byte wire form of the same stream (same ``t_base``)."""
     from . import packed as _packed
     n = int(t.shape[0])
     t_base = int(t[0]) // 1000 * 1000 if n else 0
@@ -162,8 +166,15 @@ def write_packed(path, t, x, y, p, chunk_events=1 << 24) -> None:
             raise ValueError("P4 needs ascending timestamps")
     rec.flush()
     np.save(os.path.join(path, "rec_ms_to_idx.npy"), _packed.ms_table(t, t_base))
+    if wire3:
+        rec3 = np.lib.format.open_memmap(os.path.join(path, "rec3.npy"), mode="w+", dtype=np.uint8, shape=(3 * n,))
+        for a in range(0, n, int(chunk_events)):
+            b = min(a + int(chunk_events), n)
+            rec3[3 * a:3 * b] = _packed.pack_p3(t[a:b], x[a:b], y[a:b], p[a:b], t_base=t_base, check=True)[0]
+        rec3.flush()
+        np.save(os.path.join(path, "rec3_sub_to_idx.npy"), _packed.sub_table(t, t_base))
     with open(os.path.join(path, "rec_meta.json"), "w") as f:
-        json.dump({"t_base": t_base, "n_events": n}, f)
+        json.dump({"t_base": t_base, "n_events": n, "wire3": bool(wire3)}, f)
 
 
 def load_packed(path, mmap=True):
@@ -175,6 +186,21 @@ def load_packed(path, mmap=True):
     if rec.dtype != np.uint32 or rec.shape != (int(meta["n_events"]),) or table[-1] != rec.shape[0]:
         raise ValueError(f"{path}: packed stream disagrees with rec_meta.json")
     return rec, table, int(meta["t_base"])
+
+
+def load_packed_wire(path, mmap=True):
+    """``(rec3, sub_to_idx, ms_to_idx, t_base)`` of a cache directory written with ``packed="p3"``: the ``packed=`` argument
+    of ``HostEventsPipeline(wire="p3")`` is its first three items."""
+    with open(os.path.join(path, "rec_meta.json")) as f:
+        meta = json.load(f)
+    if not meta.get("wire3"):
+        raise ValueError(f"{path}: no 3-byte wire form in this cache (convert with packed='p3')")
+    rec3 = np.load(os.path.join(path, "rec3.npy"), mmap_mode="r" if mmap else None)
+    sub = np.load(os.path.join(path, "rec3_sub_to_idx.npy"))
+    table = np.load(os.path.join(path, "rec_ms_to_idx.npy"))
+    if rec3.dtype != np.uint8 or rec3.shape != (3 * int(meta["n_events"]),) or sub[-1] != meta["n_events"]:
+        raise ValueError(f"{path}: wire stream disagrees with rec_meta.json")
+    return rec3, sub, table, int(meta["t_base"])
 
 
 def upload(a, device, chunk_bytes=256 << 20):

@@ -87,7 +87,7 @@ def test_convert_dsec_h5_reads_the_reference_file_layout(tmp_path, cname):
     the datasets; the packed P4 stream of the cache unpacks to the same events."""
     from cmda_b200 import packed
     ev_path, rm_path, ts_path, (t, x, y, p, rmap, ms, off, stamps) = _write_dsec_like_files(tmp_path, cname)
-    d = store_io.convert_dsec_h5(ev_path, rm_path, str(tmp_path / "seq"), ts_path, chunk_events=10_007, packed=True)
+    d = store_io.convert_dsec_h5(ev_path, rm_path, str(tmp_path / "seq"), ts_path, chunk_events=10_007, packed="p3")
     seq = store_io.load_sequence(d)
     assert seq["t_offset"] == off and (seq["height"], seq["width"]) == rmap.shape[:2]
     for name, ref in (("t", t), ("x", x), ("y", y), ("p", p), ("ms_to_idx", ms), ("rectify_map", rmap), ("images_timestamps", stamps)):
@@ -97,6 +97,9 @@ def test_convert_dsec_h5_reads_the_reference_file_layout(tmp_path, cname):
     assert np.array_equal(t2, t) and np.array_equal(x2, x) and np.array_equal(y2, y) and np.array_equal(p2, p)
     k = min(len(table), len(ms)) - 1
     assert t_base == 0 and np.array_equal(table[:k], ms[:k])                # the records' bucket table is DSEC's own ms_to_idx
+    rec3, sub, table3, t_base3 = store_io.load_packed_wire(d)                # the 3-byte wire form of the same stream
+    assert t_base3 == t_base and np.array_equal(table3, table) and np.array_equal(packed.p3_to_p4(np.asarray(rec3), sub), np.asarray(rec))
+    assert all(np.array_equal(a, b) for a, b in zip(packed.unpack_p3(np.asarray(rec3), sub, t_base), (t, x, y, p)))
 
 
 def test_h5lite_slices_groups_and_layouts(tmp_path):
