@@ -832,12 +832,14 @@ def run_gpu(args, rank, local_rank, world):
         elif resolved == _lib.VOXEL_FACTORED:
             names = ["memset(sensor grid)", "launch of rectify_index_{build,sort}+stencil_build+out_tile_box kernels (side stream: they run under stage A)",
                      "sensor_accumulate_kernel", "rectify_gather+regroup_partials kernels", "norm_apply_kernel"]
-            launches_per_step = 8   # kernels only (memsets not counted)
+            # kernels only (memsets not counted): 4 plan kernels, sensor_accumulate, fallback_zero + fallback_scatter (the
+            # capacity guard: always launched), rectify_gather, regroup_partials, norm_apply
+            launches_per_step = 10
         elif resolved in (_lib.VOXEL_BANDED, _lib.VOXEL_BANDED2):
             names = ["memset(none: every sensor-grid cell is stored)", "launch of rectify_index_{build,sort}+stencil_build+out_tile_box kernels (side stream: they run under stage A)",
                      "band_partition_kernel", "band_accumulate(+fixup) kernel", "rectify_gather+regroup_partials kernels",
                      "norm_apply_kernel"]
-            launches_per_step = 9
+            launches_per_step = 11  # as above with band_partition + band_accumulate in place of sensor_accumulate
         else:
             names = ["memset(int64 grid)", "tile_bbox+tile_count+tile_scan kernels", "tile_partition_kernel",
                      "tile_accumulate_kernel", "convert_stats_kernel", "norm_apply_kernel"]
