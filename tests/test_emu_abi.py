@@ -644,6 +644,42 @@ def test_p3_wire_unpacks_to_the_p4_records(L):
         packed.pack_p3(t, x, y, p, t_base=int(t[0]) // 1000 * 1000 - 16)
 
 
+@pytest.mark.parametrize("seed", list(range(12)))
+def test_p3_wire_randomised(L, seed):
+    """Adversarial streams through the P3 packer and the unpack kernel: runs of equal timestamps, gaps of seconds (empty
+    buckets by the thousand), a first event well after t_base, timestamps up to the last 16 microseconds before 2^32,
+    1 - 3 events, coordinates at the format's limits."""
+    from cmda_b200 import packed
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.choice([1, 2, 3, 17, 500, 5000]))
+    kind = seed % 4
+    if kind == 0:
+        t = np.sort(rng.integers(0, 40, size=n)) + 123_456
+    elif kind == 1:
+        t = np.cumsum(rng.choice([0, 0, 1, 15, 16, 17, 999, 1000, 1001, 2_000_000], size=n)) + 5_000
+    elif kind == 2:
+        t = (1 << 32) - 1 - np.sort(rng.integers(0, 3_000_000, size=n))[::-1]
+    else:
+        t = np.sort(rng.integers(0, 50_000, size=n)) + 1_000_000 * int(rng.integers(0, 4000))
+    t = t.astype(np.uint32)
+    x = rng.choice([0, 1, 639, 1023], size=n).astype(np.uint16)
+    y = rng.choice([0, 479, 511], size=n).astype(np.uint16)
+    p = rng.integers(0, 2, size=n).astype(np.uint8)
+    t_base = None if seed % 3 else int(t[0]) // 1000 * 1000 - 1000 * int(rng.integers(0, 3)) if int(t[0]) >= 3000 else None
+    rec4, _, tb = packed.pack_p4(t, x, y, p, t_base=t_base)
+    rec3, sub, tb3 = packed.pack_p3(t, x, y, p, t_base=t_base)
+    assert tb3 == tb and all(np.array_equal(a, b) for a, b in zip(packed.unpack_p3(rec3, sub, tb), (t, x, y, p)))
+    assert np.array_equal(packed.p3_to_p4(rec3, sub), rec4)
+    first = int(rng.integers(0, n))
+    last = int(rng.integers(first + 1, n + 1))
+    for a, b in ((0, n), (first, last)):
+        j_lo = int(np.searchsorted(sub, a, side="right")) - 1
+        j_hi = int(np.searchsorted(sub, b - 1, side="right")) - 1
+        out = np.zeros(b - a, dtype=np.uint32)
+        assert L.cmda_unpack_p3_to_p4(ptr(np.ascontiguousarray(rec3[3 * a:3 * b])), ptr(sub), j_lo, j_hi, a, b, ptr(out), None) == 0
+        assert np.array_equal(out, rec4[a:b]), (seed, a, b)
+
+
 def test_table_driven_frame_pair_path(L):
     """Images of >= 2^17 pixels take the table-driven uint8 apply pass when only the uint8 output is asked for (one
     evaluation per (now, front) byte pair and image, then a gather from a 64 KB table in shared memory): bit-exact
