@@ -4,7 +4,8 @@ axes, 24 bins), windows of 1-9 events, few distinct / unsorted / far-apart times
 send every pixel to one cell, mostly outside the grid, NaN / inf / border entries or integer coordinates.  Checks:
 per-bin counts equal everywhere and to the oracle's; TILED == GLOBAL, BANDED == BANDED2 == FACTORED, EXACT == the oracle,
 bit for bit; GLOBAL and FACTORED inside the raw-grid bound.  usage: emu_fuzz.py [seed] [seconds]   (CPU only)
-Round 1: seeds 1 and 2, 1 560 cases, no failure."""
+Round 1: seeds 1 and 2, 1 560 cases, no failure.  Round 2 (final kernels: 32 x 16 gather tiles, even-aligned boxes,
+side-stream plans): seeds 11 and 12, 600 s each, 4 434 cases, no failure."""
 import sys, ctypes, numpy as np, time
 import os
 ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
