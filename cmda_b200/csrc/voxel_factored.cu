@@ -1445,10 +1445,18 @@ regroup_partials_kernel(const PartialStats* __restrict__ block_partials, int nbl
     const int q = (nblk + kStatBlocks - 1) / kStatBlocks;
     PartialStats o;
     o.sum = 0.0; o.sumsq = 0.0; o.nnz = 0; o.min_nz = INFINITY; o.max_nz = -INFINITY;
-    for (int k = j * q; k < min((j + 1) * q, nblk); ++k) {
-        const PartialStats p = block_partials[static_cast<size_t>(s) * nblk + k];
-        o.sum += p.sum; o.sumsq += p.sumsq; o.nnz += p.nnz;
-        o.min_nz = fminf(o.min_nz, p.min_nz); o.max_nz = fmaxf(o.max_nz, p.max_nz);
+    const int k_end = min((j + 1) * q, nblk);
+    for (int k0 = j * q; k0 < k_end; k0 += 8) {          // eight partials in flight, then summed in order
+        PartialStats p[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (k0 + u < k_end) p[u] = block_partials[static_cast<size_t>(s) * nblk + k0 + u];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (k0 + u < k_end) {
+                o.sum += p[u].sum; o.sumsq += p[u].sumsq; o.nnz += p[u].nnz;
+                o.min_nz = fminf(o.min_nz, p[u].min_nz); o.max_nz = fmaxf(o.max_nz, p[u].max_nz);
+            }
     }
     partials[static_cast<size_t>(s) * kStatBlocks + j] = o;
 }
@@ -1670,6 +1678,9 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
         }
     }
     phase_mark(st);
+    // capacity guard: a window of fewer events than a cell holds cannot overflow one whatever its polarity bytes are
+    // worth (|value| <= 509; a packed record holds one polarity bit: |value| = 1)
+    const bool guard_sketch = static_cast<unsigned long long>(max_events) * (PKS ? 1ull : 509ull) >= guard.limit;
     if (banded) {
         BandTable bt{};
         long long chunks = 0, max_chunks = 0;
@@ -1752,7 +1763,7 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
         unsigned long long* ubins = reinterpret_cast<unsigned long long*>(bin_counts);
         // capacity guard: a window of fewer events than a cell holds cannot overflow one whatever its polarity bytes
         // are worth (|value| <= 509); larger windows run the kernel with its per-CTA sketch
-        const bool sketch = static_cast<unsigned long long>(max_events) * 509ull >= guard.limit;
+        const bool sketch = guard_sketch;
 #define CMDA_SENS(HAS_T, VEC, SK, PK) sensor_accumulate_kernel<HAS_T, VEC, SK, PK><<<grid, kSensThreads, 0, st>>>(t, x, y, p, pk, tab, H, W, B, R, ubins, guard)
 #define CMDA_SENS_SK(HAS_T, VEC)                                                                                                  \
     do {                                                                                                                          \
@@ -1765,8 +1776,9 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
 #undef CMDA_SENS
         CMDA_LAUNCH_CHECK();
     }
-    // capacity guard: recompute the flagged windows (none on DSEC data: both kernels exit at once)
-    if (max_events > 0) {
+    // capacity guard: recompute the flagged windows (none on DSEC data: both kernels exit at once).  The RED kernel
+    // without its sketch -- windows too small to fill a cell -- sets no flag: nothing to launch.
+    if (max_events > 0 && (banded || guard_sketch)) {
         fallback_zero_kernel<<<dim3(16, S), kFallbackThreads, 0, st>>>(guard, FB, static_cast<size_t>(B) * npx);
         long long gx = (max_events + kFallbackThreads * 8 - 1) / (kFallbackThreads * 8);
         if (gx > 64) gx = 64;
