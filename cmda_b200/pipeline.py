@@ -12,7 +12,7 @@ kernel: ``wire="soa"`` ships the four DSEC arrays as they are (9 bytes per event
 ships the packed stream of ``cmda_b200.packed`` (4 bytes per event, packed ONCE when the pipeline --
 or the decoded-sequence cache of ``store_io`` -- is built; bit-identical results), ``wire="p3"`` its 3-byte
 wire form (sensors up to 1024 x 512; unpacked to P4 records on the device by ``cmda_unpack_p3_to_p4``,
-0.1 ms per 80 M events, before the same kernels run).  Windows of a group that touch or overlap in the
+0.17 ms per 80 M events, before the same kernels run).  Windows of a group that touch or overlap in the
 store travel as one copy per array.
 """
 from __future__ import annotations
