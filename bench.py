@@ -325,7 +325,9 @@ def workload_config(args, world):
             "windows_per_gpu": WINDOWS_PER_GPU, "events_per_window": args.events, "bins": args.bins,
             "height": H, "width": W, "voxel_mode": args.mode, "parallelism": f"shard-by-window x{world}",
             "event_store": "GPU arm: packed P4 stream, 4 B/event (SoA DSEC arrays as a variant); CPU arm: the DSEC arrays",
-            "l2": "inputs (720 MB/step) exceed L2 (126 MB); no flush needed"}
+            "l2": f"inputs ({4 * WINDOWS_PER_GPU * args.events / 1e6:.0f} MB of packed events per step; "
+                  f"{9 * WINDOWS_PER_GPU * args.events / 1e6:.0f} MB as SoA arrays) and the {8 * WINDOWS_PER_GPU * args.bins * H * W / 1e6:.0f} MB "
+                  "sensor-space grid the step fills and reads back exceed L2 (126 MB); no flush needed"}
 
 
 # ------------------------------------------------------------------------------------ pseudo-event leg
