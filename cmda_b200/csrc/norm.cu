@@ -183,6 +183,7 @@ __global__ void __launch_bounds__(kNormThreads, 4)
 norm_apply_kernel(const float* raw, float* out, long long V,   // raw may alias out (in-place call)
                   const PartialStats* __restrict__ partials, WindowTable tab, float final_range, int enforce) {
     __shared__ NormParams s_q;
+    dependency_wait();
     const int s = blockIdx.y;
     if (threadIdx.x == 0)
         s_q = make_norm_params(partials + static_cast<size_t>(s) * kStatBlocks, V, tab.w[s].clip, final_range);
@@ -319,8 +320,9 @@ int launch_norm_apply(const float* raw, float* out, int S, long long V, const Pa
     if (gx > cap) gx = cap;
     if (gx < 1) gx = 1;
     dim3 grid(static_cast<unsigned>(gx), S);
-    if (vec) norm_apply_kernel<true><<<grid, kNormThreads, 0, s>>>(raw, out, V, partials, tab, final_range, enforce);
-    else norm_apply_kernel<false><<<grid, kNormThreads, 0, s>>>(raw, out, V, partials, tab, final_range, enforce);
+    // programmatic dependent launch: the CTAs may queue up while the kernel before (statistics regroup / conversion) drains
+    if (vec) CMDA_CUDA_TRY(launch_dependent(norm_apply_kernel<true>, grid, dim3(kNormThreads), 0, s, raw, out, V, partials, tab, final_range, enforce));
+    else CMDA_CUDA_TRY(launch_dependent(norm_apply_kernel<false>, grid, dim3(kNormThreads), 0, s, raw, out, V, partials, tab, final_range, enforce));
     CMDA_LAUNCH_CHECK();
     return CMDA_OK;
 }

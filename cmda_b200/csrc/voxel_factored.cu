@@ -184,6 +184,7 @@ __global__ void __launch_bounds__(kSensThreads, CMDA_SENS_MINBLOCKS)
 sensor_accumulate_kernel(const uint32_t* __restrict__ t, const uint16_t* __restrict__ x, const uint16_t* __restrict__ y,
                          const uint8_t* __restrict__ p, const __grid_constant__ PackedSrc pk, const __grid_constant__ WindowTable tab,
                          int H, int W, int B, void* __restrict__ R, unsigned long long* __restrict__ bin_counts, Guard guard) {
+    dependency_release();                    // the guard's kernels may queue up behind this grid
     __shared__ unsigned s_bins[32];
     __shared__ unsigned s_sketch[SKETCH ? kSketch : 1];
     __shared__ MsWindow s_mw;
@@ -577,6 +578,7 @@ band_accumulate_kernel(const unsigned* __restrict__ table, const unsigned* __res
                        const unsigned char* __restrict__ rec8, const unsigned short* __restrict__ rec16,
                        const __grid_constant__ BandTable bt, BandGeom g, int H, int W, int B, void* __restrict__ R,
                        unsigned* __restrict__ flags) {
+    dependency_release();
     constexpr int kBandUnroll = HAS_T ? CMDA_BAND_UNROLL : CMDA_BAND_UNROLL_B1;
     extern __shared__ __align__(16) unsigned s_band_acc[];      // B > 1: (lo, hi) per cell;  B == 1: count[cells]
     const unsigned cells = static_cast<unsigned>(g.rows) * static_cast<unsigned>(W);
@@ -895,6 +897,8 @@ band_partition3_kernel(const uint32_t* __restrict__ t, const uint16_t* __restric
 constexpr int kFallbackThreads = 256;
 __global__ void __launch_bounds__(kFallbackThreads)
 fallback_zero_kernel(Guard guard, long long* __restrict__ FB, size_t V) {
+    dependency_wait();
+    dependency_release();
     const int s = blockIdx.y;
     if (!window_flagged(guard, s)) return;
     long long* g = FB + static_cast<size_t>(s) * V;
@@ -907,6 +911,8 @@ __global__ void __launch_bounds__(kFallbackThreads)
 fallback_scatter_kernel(const uint32_t* __restrict__ t, const uint16_t* __restrict__ x, const uint16_t* __restrict__ y,
                         const uint8_t* __restrict__ p, const __grid_constant__ PackedSrc pk, const __grid_constant__ WindowTable tab,
                         const float2* __restrict__ maps, int H, int W, int B, Guard guard, long long* __restrict__ FB) {
+    dependency_wait();
+    dependency_release();
     const int s = blockIdx.y;
     const WindowDesc wd = tab.w[s];
     const long long n = wd.end - wd.start;
@@ -1268,6 +1274,8 @@ __device__ __forceinline__ void rectify_gather_body(const void* __restrict__ R, 
                                                     float* __restrict__ raw, PartialStats* __restrict__ block_partials,
                                                     const Guard& guard, const long long* __restrict__ FB) {
     extern __shared__ double s_planes[];                     // [box pixels][B]
+    dependency_wait();
+    dependency_release();
     constexpr int BA = BT ? BT : 24;
     const int B = BT ? BT : Brt;
     const unsigned s = blockIdx.y;
@@ -1441,6 +1449,8 @@ rectify_gather_kernel<1>(const void* __restrict__ R, const __grid_constant__ Win
 // in-order sum of blocks [j*q, (j+1)*q): a fixed order, hence bit-reproducible.
 __global__ void __launch_bounds__(kStatBlocks)
 regroup_partials_kernel(const PartialStats* __restrict__ block_partials, int nblk, PartialStats* __restrict__ partials) {
+    dependency_wait();
+    dependency_release();
     const int s = blockIdx.x, j = threadIdx.x;
     const int q = (nblk + kStatBlocks - 1) / kStatBlocks;
     PartialStats o;
@@ -1779,11 +1789,11 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
     // capacity guard: recompute the flagged windows (none on DSEC data: both kernels exit at once).  The RED kernel
     // without its sketch -- windows too small to fill a cell -- sets no flag: nothing to launch.
     if (max_events > 0 && (banded || guard_sketch)) {
-        fallback_zero_kernel<<<dim3(16, S), kFallbackThreads, 0, st>>>(guard, FB, static_cast<size_t>(B) * npx);
+        CMDA_CUDA_TRY(launch_dependent(fallback_zero_kernel, dim3(16, S), dim3(kFallbackThreads), 0, st, guard, FB, static_cast<size_t>(B) * npx));
         long long gx = (max_events + kFallbackThreads * 8 - 1) / (kFallbackThreads * 8);
         if (gx > 64) gx = 64;
-        if (PKS) fallback_scatter_kernel<true><<<dim3(static_cast<unsigned>(gx), S), kFallbackThreads, 0, st>>>(t, x, y, p, pk, tab, maps2, H, W, B, guard, FB);
-        else fallback_scatter_kernel<false><<<dim3(static_cast<unsigned>(gx), S), kFallbackThreads, 0, st>>>(t, x, y, p, pk, tab, maps2, H, W, B, guard, FB);
+        if (PKS) CMDA_CUDA_TRY(launch_dependent(fallback_scatter_kernel<true>, dim3(static_cast<unsigned>(gx), S), dim3(kFallbackThreads), 0, st, t, x, y, p, pk, tab, maps2, H, W, B, guard, FB));
+        else CMDA_CUDA_TRY(launch_dependent(fallback_scatter_kernel<false>, dim3(static_cast<unsigned>(gx), S), dim3(kFallbackThreads), 0, st, t, x, y, p, pk, tab, maps2, H, W, B, guard, FB));
         CMDA_LAUNCH_CHECK();
     }
     phase_mark(st);
@@ -1797,7 +1807,7 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
     do {                                                                                                                 \
         constexpr int stage = BT == 1 ? kStageBytesB1 : kStageBytes;                                                     \
         CMDA_CUDA_TRY(cudaFuncSetAttribute(rectify_gather_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, stage));     \
-        rectify_gather_kernel<BT><<<grid, kOutThreads, stage, st>>>(R, tab, ms, maps2, nc, H, W, B, raw, block_partials, guard, FB); \
+        CMDA_CUDA_TRY(launch_dependent(rectify_gather_kernel<BT>, grid, dim3(kOutThreads), stage, st, R, tab, ms, maps2, nc, H, W, B, raw, block_partials, guard, FB)); \
     } while (0)
         switch (B) {
             case 1: CMDA_GATHER(1); break;
@@ -1808,7 +1818,7 @@ int launch_factored(const uint32_t* t, const uint16_t* x, const uint16_t* y, con
             default: CMDA_GATHER(0); break;
         }
 #undef CMDA_GATHER
-        regroup_partials_kernel<<<S, kStatBlocks, 0, st>>>(block_partials, nblk, partials);
+        CMDA_CUDA_TRY(launch_dependent(regroup_partials_kernel, dim3(S), dim3(kStatBlocks), 0, st, block_partials, nblk, partials));
         CMDA_LAUNCH_CHECK();
     }
     return CMDA_OK;

@@ -28,6 +28,8 @@ def _transform_common(src: str) -> str:
     swap("ldg_stream_u4", "return *static_cast<const uint4*>(p);")
     swap("ldg_stream_u2", "return *static_cast<const uint2*>(p);")
     swap("stg_stream_f4", "*reinterpret_cast<float4*>(p) = v;")
+    swap("dependency_wait", ";")            # programmatic dependent launch: the emulation runs kernels one after another
+    swap("dependency_release", ";")
     assert "asm" not in src, "an inline-PTX helper of common.cuh is not covered by the emulation build"
     return src
 
