@@ -30,6 +30,11 @@ def _transform_common(src: str) -> str:
     swap("stg_stream_f4", "*reinterpret_cast<float4*>(p) = v;")
     swap("dependency_wait", ";")            # programmatic dependent launch: the emulation runs kernels one after another
     swap("dependency_release", ";")
+    # ... and launch_dependent() is an ordinary launch of the stand-in
+    pat = re.compile(r"(inline cudaError_t launch_dependent\(.*?\) \{)\n.*?\n\}\n", re.S)
+    assert pat.search(src), "launch_dependent"
+    src = pat.sub(lambda m: m.group(1) + "\n    (void)shm; (void)st;\n    emu_launch(grid, block, [&] { kernel(static_cast<KArgs>(args)...); });"
+                  "\n    return cudaSuccess;\n}\n", src, count=1)
     assert "asm" not in src, "an inline-PTX helper of common.cuh is not covered by the emulation build"
     return src
 

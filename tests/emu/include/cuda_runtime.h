@@ -16,7 +16,6 @@
 #include <vector>
 
 #define __CUDACC__ 1
-#define CMDA_HOST_EMULATION 1
 #define __global__
 #define __device__
 #define __host__
