@@ -10,9 +10,13 @@
  *    (`stream` is a cudaStream_t passed as void*; NULL = legacy default stream);
  *  - pointers named `d_*` are DEVICE pointers, `h_*` are HOST pointers read during the
  *    call (small per-window tables, 256-entry LUTs); they may be freed on return;
- *  - the caller owns every buffer including the workspace; the library allocates
- *    nothing and keeps no global state; calls are asynchronous on `stream`, never
- *    synchronise, and are re-entrant with one workspace per concurrent stream;
+ *  - the caller owns every buffer including the workspace; the library allocates no
+ *    device memory and keeps no global state, except one internal side stream and two
+ *    events per (host thread, device), made on first use by the voxel entry points that
+ *    build map plans per call (those kernels run beside the event accumulation);
+ *    calls are asynchronous on `stream`, never synchronise -- event record / wait and
+ *    programmatic dependent launches only, so a call can be captured into a CUDA graph --
+ *    and are re-entrant with one workspace per concurrent stream;
  *  - every function returns CMDA_OK (0) or a negative CMDA_ERR_* code; nothing throws
  *    or exits.  There is no CPU fallback anywhere behind this ABI.
  */
