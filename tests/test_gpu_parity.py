@@ -880,6 +880,41 @@ def test_p3_wire_unpacks_to_p4_on_device(cm):
     assert np.array_equal(bits(cm.events_vg_batch(pst, starts, fins, 5)), bits(cm.events_vg_batch(soa, starts, fins, 5)))
 
 
+def test_concurrent_host_threads_and_streams(cm):
+    """Two host threads, each on a stream of its own (own workspace, own side stream for the per-call plans), issue
+    calls at the same time: every result has the bits of the single-threaded call."""
+    import threading
+    from cmda_b200 import synth
+    H, W, n = 480, 640, 400_000
+    t, x, y, p = synth.make_events(n, H, W, seed=synth.seed_for(7, 52))
+    rmap = synth.make_rectify_map(H, W, seed=14)
+    store = cm.EventStore(t, x, y, p, rmap, height=H, width=W, device="cuda:0", plan=False)
+    windows = [(np.array([0, 50_000]), np.array([n - 1, 250_000])), (np.array([10, 300_000, 5]), np.array([199_999, n - 1, 4]))]
+    refs = [[cm.events_vg_batch(store, s, f, b).clone() for b in (5, 1)] for s, f in windows]
+    torch.cuda.synchronize()
+    errors = []
+
+    def worker(k):
+        try:
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream):
+                for it in range(25):
+                    for bi, b in enumerate((5, 1)):
+                        out = cm.events_vg_batch(store, windows[k][0], windows[k][1], b)
+                        stream.synchronize()
+                        if not torch.equal(out, refs[k][bi]):
+                            errors.append((k, it, b))
+        except Exception as e:      # noqa: BLE001
+            errors.append((k, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(2)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors[:3]
+
+
 def test_events_vg_fused_augment_many_windows(cm):
     """The augmented entry point past one launch group (70 windows, per-window crop origins / flips / maps): the
     per-group augmentation table and raw-grid offsets, against the unfused path + the oracle's post-voxel stage."""
